@@ -1,0 +1,321 @@
+/* karpsolve.h -- C ABI of libkarpsolve.so: the B200 solver behind Karpenter's
+ * provisioning hot path.
+ *
+ * What this boundary replaces (all paths relative to the reference tree,
+ * kubernetes-sigs/karpenter @ 7e9d4269):
+ *
+ *   kp_solve        <-> (*Scheduler).Solve            pkg/controllers/provisioning/scheduling/scheduler.go:381-436
+ *                       incl. NewScheduler prefilter   scheduler.go:116-184 and NewTopology topology.go:68-103
+ *   kp_consolidate  <-> consolidation.computeConsolidation   pkg/controllers/disruption/consolidation.go:136-229
+ *                       over SimulateScheduling               pkg/controllers/disruption/helpers.go:51-142
+ *   kp_problem      <-> the arguments of NewScheduler (nodePools, stateNodes, instanceTypes, daemonSetPods) and
+ *                       Solve (pods), with cloudprovider.InstanceType / Offering (pkg/cloudprovider/types.go:122-138,
+ *                       372-379) flattened to interned integer tables. Strings never cross: the caller (the cgo shim,
+ *                       see INTEGRATION.md) interns label keys/values and keeps the tables.
+ *   kp_result       <-> scheduling.Results             scheduler.go:237-241 (NewNodeClaims / ExistingNodes / PodErrors)
+ *
+ * Conventions: plain pointers + counts, no ownership transfer of inputs (the library copies what it needs during the
+ * call and retains no caller pointer after return -- the cgo pointer rule).  Outputs are owned by the library until
+ * kp_result_free / kp_consol_result_free.  Every entry point returns a kp_status.  There is NO CPU fallback: if no CUDA
+ * device is usable the call fails with KP_ERR_CUDA.
+ */
+#ifndef KARPSOLVE_H
+#define KARPSOLVE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KP_ABI_VERSION 1
+
+typedef enum kp_status {
+  KP_OK = 0,
+  KP_DEADLINE = 1,         /* partial results valid; maps to context.DeadlineExceeded (scheduler.go:411-414) */
+  KP_ERR_INVALID = 2,      /* malformed problem */
+  KP_ERR_CUDA = 3,         /* device / driver failure; message via kp_last_error */
+  KP_ERR_CAPACITY = 4,     /* a compiled limit was exceeded (e.g. > KP_MAX_RESOURCES) */
+  KP_ERR_UNSUPPORTED = 5   /* feature of the reference not built yet (minValues, reserved offerings, preferences) */
+} kp_status;
+
+/* ---- requirement encoding --------------------------------------------------------------------------------------
+ * One entry == one scheduling.Requirement in its canonical form (pkg/scheduling/requirement.go:36-43):
+ * {Key, complement, values, gte, lte, MinValues}.  The operator -> canonical mapping of NewRequirementWithFlexibility
+ * (requirement.go:48-102: NotIn/Exists -> complement, Gt N -> gte N+1, Lt N -> lte N-1) is applied by the caller.
+ * A requirement set (scheduling.Requirements, requirements.go:36) is a CSR row of entries; entries that repeat a key
+ * are folded with Requirements.Add (requirements.go:133-140), i.e. intersected, in row order.
+ */
+#define KP_REQ_COMPLEMENT 0x01u
+#define KP_REQ_HAS_GTE 0x02u
+#define KP_REQ_HAS_LTE 0x04u
+#define KP_REQ_HAS_MINVALUES 0x08u
+
+#define KP_KEY_WELL_KNOWN 0x01u /* member of v1.WellKnownLabels (pkg/apis/v1/labels.go:69-78) => AllowUndefined */
+#define KP_KEY_HOSTNAME 0x02u   /* corev1.LabelHostname: one implicit domain per node / NodeClaim */
+
+#define KP_RES_CPU 0x01u
+#define KP_RES_MEMORY 0x02u
+#define KP_RES_HUGEPAGES 0x04u /* name has prefix "hugepages-": subtracted from allocatable memory (types.go:206-215) */
+#define KP_RES_NODES 0x08u     /* resources.Node, only meaningful in NodePool limits (scheduler.go:607) */
+
+#define KP_MAX_RESOURCES 8
+
+/* taint effects / toleration operators (k8s.io/api core/v1) */
+#define KP_EFFECT_NONE 0
+#define KP_EFFECT_NO_SCHEDULE 1
+#define KP_EFFECT_PREFER_NO_SCHEDULE 2
+#define KP_EFFECT_NO_EXECUTE 3
+#define KP_TOL_EQUAL 0
+#define KP_TOL_EXISTS 1
+#define KP_TOL_LT 2
+#define KP_TOL_GT 3
+
+/* topology constraint kinds (topologygroup.go:36-40) */
+#define KP_TOPO_SPREAD 0
+#define KP_TOPO_AFFINITY 1
+#define KP_TOPO_ANTI_AFFINITY 2
+
+/* label-selector operators (metav1.LabelSelectorOperator) */
+#define KP_SEL_IN 0
+#define KP_SEL_NOT_IN 1
+#define KP_SEL_EXISTS 2
+#define KP_SEL_DOES_NOT_EXIST 3
+
+#define KP_NODE_SCHEDULABLE 0x01u /* member of stateNodes handed to NewScheduler */
+#define KP_NODE_INITIALIZED 0x02u /* StateNode.Initialized() (scheduler.go:742-750, helpers.go:121-140) */
+#define KP_NODE_MANAGED 0x04u
+
+typedef struct kp_problem {
+  /* ---- node-label universe ---- */
+  int32_t n_keys;
+  const uint8_t* key_flags;     /* [n_keys] KP_KEY_* */
+  const int32_t* key_value_off; /* [n_keys+1] value ids are local to their key: 0 .. nvalues-1 */
+  const int64_t* value_int;     /* [n_values] strconv.Atoi(value) (requirement.go:326-342) */
+  const uint8_t* value_is_int;  /* [n_values] 0 if Atoi fails */
+
+  /* ---- requirement sets ---- */
+  int32_t n_reqsets;
+  const int32_t* reqset_off; /* [n_reqsets+1] -> entry range */
+  int32_t n_reqs;
+  const int32_t* req_key;        /* [n_reqs] */
+  const uint8_t* req_flags;      /* [n_reqs] KP_REQ_* */
+  const int64_t* req_gte;        /* [n_reqs] */
+  const int64_t* req_lte;        /* [n_reqs] */
+  const int32_t* req_min_values; /* [n_reqs] */
+  const int32_t* req_val_off;    /* [n_reqs+1] */
+  const int32_t* req_vals;       /* value ids (local to req_key) */
+
+  /* ---- resources (dense vectors of n_resources int64, caller-chosen exact integer unit per resource) ---- */
+  int32_t n_resources;
+  const uint8_t* res_flags; /* [n_resources] KP_RES_* */
+
+  /* ---- taints / tolerations: strings interned in one table, id 0 == "" ---- */
+  int32_t n_tt_strings;
+  const int64_t* tt_int; /* [n_tt_strings] numeric value for Gt/Lt tolerations */
+  const uint8_t* tt_is_int;
+  int32_t n_taints;
+  const int32_t* taint_key;
+  const int32_t* taint_value;
+  const uint8_t* taint_effect;
+  int32_t n_taintsets;
+  const int32_t* taintset_off; /* [n_taintsets+1] */
+  const int32_t* taintset_ids;
+  int32_t n_tolerations;
+  const int32_t* tol_key; /* 0 == empty key */
+  const uint8_t* tol_op;  /* KP_TOL_* */
+  const int32_t* tol_value;
+  const uint8_t* tol_effect; /* KP_EFFECT_NONE matches all effects */
+  int32_t n_tolsets;
+  const int32_t* tolset_off;
+  const int32_t* tolset_ids;
+
+  /* ---- instance types (cloudprovider.InstanceType, types.go:122-138) ---- */
+  int32_t n_its;
+  const int32_t* it_reqset;       /* [n_its] InstanceType.Requirements */
+  const int64_t* it_capacity;     /* [n_its * n_resources] */
+  const uint32_t* it_cap_present; /* [n_its] bit r set iff Capacity has resource r */
+  const int64_t* it_overhead;     /* [n_its * n_resources] Overhead.Total() (types.go:366-368) */
+  const int32_t* it_off_off;      /* [n_its+1] offerings CSR */
+  const int32_t* off_reqset;      /* [n_offerings] Offering.Requirements */
+  const double* off_price;        /* [n_offerings] */
+  const uint8_t* off_available;   /* [n_offerings] */
+
+  /* ---- NodeClaimTemplates, one per NodePool, already in OrderByWeight order (utils/nodepool/nodepool.go:161) ---- */
+  int32_t n_templates;
+  const int32_t* tmpl_reqset;         /* NodePool requirements + template labels + karpenter.sh/nodepool label */
+  const int32_t* tmpl_taintset;       /* Spec.Taints */
+  const int32_t* tmpl_it_off;         /* [n_templates+1] instanceTypes[np.Name] before the NewScheduler prefilter */
+  const int32_t* tmpl_its;            /* global instance type indices, provider order */
+  const int64_t* tmpl_daemon;         /* [n_templates * n_resources] daemonOverhead (scheduler.go:782-792) */
+  const int64_t* tmpl_limits;         /* [n_templates * n_resources] NodePool.Spec.Limits */
+  const uint32_t* tmpl_limit_present; /* [n_templates] bit r set iff a limit is defined for r */
+
+  /* ---- pod label sets / selectors / namespaces (for TopologyGroup.selects, topologygroup.go:431-433) ---- */
+  int32_t n_labelsets;
+  const int32_t* labelset_off; /* [n_labelsets+1] */
+  const int32_t* label_key;    /* pod-label string ids (own id space) */
+  const int32_t* label_val;
+  int32_t n_selectors;
+  const int32_t* selector_off; /* [n_selectors+1] -> expression range; matchLabels are In-expressions */
+  const int32_t* selx_key;
+  const uint8_t* selx_op; /* KP_SEL_* */
+  const int32_t* selx_val_off;
+  const int32_t* selx_vals;
+  int32_t n_nssets;
+  const int32_t* nsset_off;
+  const int32_t* nsset_ids;
+
+  /* ---- pod classes: pods that are identical for scheduling purposes share one row ---- */
+  int32_t n_classes;
+  const int64_t* class_requests;      /* [n_classes * n_resources] RequestsForPods incl. pods:1 (resources.go:30-39) */
+  const int32_t* class_reqset;        /* PodData.Requirements (scheduler.go:471-491) */
+  const int32_t* class_strict_reqset; /* PodData.StrictRequirements */
+  const int32_t* class_tolset;
+  const int32_t* class_namespace;
+  const int32_t* class_labelset;
+  const int32_t* class_filter_off; /* [n_classes+1] TopologyNodeFilter.Requirements alternatives (topologynodefilter.go:38-64) */
+  const int32_t* class_filter_reqsets;
+  const int32_t* class_tsc_off; /* [n_classes+1] topology constraints owned by the class */
+  const uint8_t* tsc_type;      /* KP_TOPO_* */
+  const int32_t* tsc_key;
+  const int32_t* tsc_selector; /* -1 == nil selector (selects nothing) */
+  const int32_t* tsc_nsset;
+  const int32_t* tsc_max_skew;
+  const int32_t* tsc_min_domains;    /* -1 == nil */
+  const uint8_t* tsc_taint_policy;   /* 1 == Honor */
+  const uint8_t* tsc_affinity_policy;/* 1 == Honor */
+
+  /* ---- pods to schedule ---- */
+  int64_t n_pods;
+  const int32_t* pod_class;
+  const int64_t* pod_creation; /* CreationTimestamp, seconds */
+  const uint64_t* pod_uid_hi;  /* UID as a 128-bit number, ordered like the canonical lower-case UUID string */
+  const uint64_t* pod_uid_lo;
+
+  /* ---- cluster nodes (state.StateNode) in sortExistingNodes order (scheduler.go:738-751) ---- */
+  int32_t n_nodes;
+  const uint8_t* node_flags;      /* KP_NODE_* */
+  const int32_t* node_reqset;     /* labels as In{value}; hostname excluded (see node_hostname) */
+  const int32_t* node_hostname;   /* value id in the hostname key */
+  const int32_t* node_taintset;   /* StateNode.Taints() */
+  const int64_t* node_available;  /* [n_nodes * n_resources] remainingResources (existingnode.go:40-66) */
+  const uint32_t* node_avail_present;
+  const int64_t* node_capacity;   /* [n_nodes * n_resources] for NodePool limits (scheduler.go:728-735) */
+  const int32_t* node_template;   /* NodePool index or -1 */
+  /* pods already bound to cluster nodes, counted by countDomains (topology.go:328-426) */
+  int64_t n_running;
+  const int32_t* run_class;
+  const int32_t* run_node;
+
+  /* ---- options (scheduler.go:87-114) ---- */
+  int32_t min_values_best_effort;
+  int32_t claim_order_mode; /* 0 = Go sort.Slice (pdqsort_func) tie order, 1 = stable */
+} kp_problem;
+
+/* pod_target encoding */
+#define KP_TARGET_UNSCHEDULED (-1)
+#define KP_TARGET_CLAIM(k) (-2 - (k))
+
+/* pod_error codes */
+#define KP_PODERR_NONE 0
+#define KP_PODERR_NO_TEMPLATES 1       /* scheduler.go:510-512 */
+#define KP_PODERR_INCOMPATIBLE 2       /* every template rejected the pod (multierr of scheduler.go:683) */
+
+#define KP_SLOT_PRESENT 0x10u /* or-ed with KP_REQ_* in claim_req_flags */
+
+typedef struct kp_result {
+  int64_t n_pods;
+  int32_t* pod_target;    /* [n_pods] >=0 node index | KP_TARGET_CLAIM(k) | KP_TARGET_UNSCHEDULED */
+  uint8_t* pod_error;     /* [n_pods] KP_PODERR_* */
+  int32_t n_claims;       /* NewNodeClaims, index k = creation order */
+  int32_t* claim_template;/* [n_claims] */
+  int32_t* claim_npods;
+  int32_t* claim_rank;    /* [n_claims] position of claim k in the returned NewNodeClaims slice (scheduler.go:504) */
+  int64_t* claim_requests;/* [n_claims * n_resources] Spec.Resources.Requests */
+  int32_t it_words;
+  uint64_t* claim_its;    /* [n_claims * it_words] InstanceTypeOptions as a bitmap over global instance type ids */
+  int32_t n_keys;
+  int32_t mask_words;     /* sum over keys of ceil(nvalues/64) */
+  uint8_t* claim_req_flags; /* [n_claims * n_keys] */
+  int64_t* claim_req_gte;   /* [n_claims * n_keys] */
+  int64_t* claim_req_lte;
+  uint64_t* claim_req_mask; /* [n_claims * mask_words] */
+  /* topology-domain counters after the solve (what a multi-GPU run all-reduces) */
+  int32_t n_groups;
+  int32_t n_domain_slots;
+  int32_t* group_domain_off; /* [n_groups+1] */
+  int32_t* domain_counts;    /* [n_domain_slots] non-hostname groups only */
+  /* evaluation counters: define the algorithmic bytes of SURVEY.md section 8(d) */
+  int64_t n_existing_evals, n_inflight_evals, n_template_evals, n_commits;
+  double solve_ms; /* device time of the solve kernels (CUDA events) */
+  void* _impl;
+} kp_result;
+
+/* ---- consolidation ---- */
+#define KP_DECISION_NOOP 0
+#define KP_DECISION_DELETE 1
+#define KP_DECISION_REPLACE 2
+
+typedef struct kp_consol_input {
+  /* cluster pods that would be evicted, grouped by the node they run on */
+  const int32_t* node_pod_off; /* [n_nodes+1] into kp_problem pod arrays (pods of node i are rows off[i]..off[i+1]) */
+  const int32_t* node_it;      /* [n_nodes] instance type of the node, -1 unknown (consolidation.go:323-326) */
+  const uint8_t* node_is_spot; /* [n_nodes] Candidate.capacityType == spot */
+  int32_t n_subsets;
+  const int32_t* subset_off;   /* [n_subsets+1] */
+  const int32_t* subset_nodes; /* node indices; each subset is one computeConsolidation(candidates...) call */
+  int32_t spot_to_spot_enabled; /* FeatureGates.SpotToSpotConsolidation (consolidation.go:239) */
+  int32_t capacity_type_key;    /* key id of karpenter.sh/capacity-type, -1 if not interned */
+  int32_t ct_reserved, ct_spot, ct_on_demand; /* value ids in that key, -1 if not interned (types.go:45-47) */
+} kp_consol_input;
+
+typedef struct kp_consol_result {
+  int32_t n_subsets;
+  uint8_t* decision;          /* [n_subsets] KP_DECISION_* */
+  int32_t it_words;
+  uint64_t* replacement_its;  /* [n_subsets * it_words] instance types left after the price filter */
+  int32_t* n_new_claims;      /* [n_subsets] */
+  int32_t* n_unscheduled;     /* [n_subsets] */
+  double solve_ms;
+  void* _impl;
+} kp_consol_result;
+
+typedef struct kp_handle kp_handle;
+
+int kp_version(void);
+/* device < 0: cudaGetDevice() current */
+int kp_create(int device, kp_handle** out);
+void kp_destroy(kp_handle* h);
+const char* kp_last_error(kp_handle* h);
+
+/* Solve: host pointers in, host result out (H2D / D2H inside). deadline_ms <= 0: none. */
+int kp_solve(kp_handle* h, const kp_problem* p, int64_t deadline_ms, kp_result* out);
+void kp_result_free(kp_result* r);
+
+/* Two-step variant used by bench.py to time the device-resident solve separately from the transfers:
+ * kp_upload copies + encodes the problem into HBM, kp_solve_resident runs only the kernels. */
+int kp_upload(kp_handle* h, const kp_problem* p);
+int kp_solve_resident(kp_handle* h, int64_t deadline_ms, kp_result* out);
+
+int kp_consolidate(kp_handle* h, const kp_problem* cluster, const kp_consol_input* in, int64_t deadline_ms,
+                   kp_consol_result* out);
+void kp_consol_result_free(kp_consol_result* r);
+
+/* Feasibility matrix only (kernel K1): bit (class, template, it) == instance type `it` survives
+ * filterInstanceTypesByRequirements (nodeclaim.go:412-480) for a fresh NodeClaim of `template` holding one pod of
+ * `class`, ignoring topology.  out: [n_classes * n_templates * it_words] */
+int kp_feasibility(kp_handle* h, const kp_problem* p, uint64_t* out_bits, int32_t* out_it_words);
+
+typedef struct kp_stats {
+  double upload_ms, prep_ms, solve_ms, download_ms;
+  int64_t bytes_h2d, bytes_d2h;
+  int64_t kernel_launches;
+} kp_stats;
+int kp_get_stats(kp_handle* h, kp_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KARPSOLVE_H */

@@ -1,0 +1,121 @@
+"""ctypes binding of libkarpsolve.so (the CUDA product path). There is no CPU fallback: if the library is missing
+or no CUDA device is usable every call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import _abi
+
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(CSRC, "libkarpsolve.so")
+_LIB = None
+
+STATUS = {0: "OK", 1: "DEADLINE", 2: "INVALID", 3: "CUDA", 4: "CAPACITY", 5: "UNSUPPORTED"}
+
+
+class SolverError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"karpsolve: {STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("building libkarpsolve.so failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
+    if verbose:
+        print(out.stdout[-2000:])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the product path has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.kp_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.kp_destroy.argtypes = [C.c_void_p]
+        L.kp_last_error.argtypes = [C.c_void_p]
+        L.kp_last_error.restype = C.c_char_p
+        L.kp_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.kp_upload.argtypes = [C.c_void_p, C.c_void_p]
+        L.kp_solve_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.kp_result_free.argtypes = [C.c_void_p]
+        L.kp_consolidate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.kp_consol_result_free.argtypes = [C.c_void_p]
+        L.kp_feasibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kp_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+EXPORTS = ["kp_version", "kp_create", "kp_destroy", "kp_last_error", "kp_solve", "kp_result_free", "kp_upload",
+           "kp_solve_resident", "kp_consolidate", "kp_consol_result_free", "kp_feasibility", "kp_get_stats"]
+
+
+class Handle:
+    """kp_handle: one CUDA stream + device arena. Single caller at a time (like one reference Scheduler)."""
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        rc = lib().kp_create(device, C.byref(self._h))
+        if rc != 0:
+            raise SolverError(rc, "kp_create failed (no usable CUDA device; there is no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().kp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SolverError(rc, lib().kp_last_error(self._h).decode())
+
+    def solve(self, problem: _abi.Problem, deadline_ms: int = 0) -> dict:
+        r = _abi.kp_result()
+        self._check(lib().kp_solve(self._h, problem.ref(), deadline_ms, C.byref(r)))
+        out = _abi.result_to_dict(r, problem.n_resources)
+        lib().kp_result_free(C.byref(r))
+        return out
+
+    def upload(self, problem: _abi.Problem):
+        self._n_resources = problem.n_resources
+        self._check(lib().kp_upload(self._h, problem.ref()))
+
+    def solve_resident(self, deadline_ms: int = 0) -> dict:
+        r = _abi.kp_result()
+        self._check(lib().kp_solve_resident(self._h, deadline_ms, C.byref(r)))
+        out = _abi.result_to_dict(r, self._n_resources)
+        lib().kp_result_free(C.byref(r))
+        return out
+
+    def consolidate(self, problem: _abi.Problem, consol: _abi.ConsolInput, deadline_ms: int = 0) -> dict:
+        r = _abi.kp_consol_result()
+        self._check(lib().kp_consolidate(self._h, problem.ref(), consol.ref(), deadline_ms, C.byref(r)))
+        out = _abi.consol_result_to_dict(r)
+        lib().kp_consol_result_free(C.byref(r))
+        return out
+
+    def feasibility(self, problem: _abi.Problem) -> np.ndarray:
+        itw = (problem.n_its + 63) // 64
+        out = np.zeros((problem.n_classes, problem.n_templates, itw), np.uint64)
+        w = C.c_int32()
+        self._check(lib().kp_feasibility(self._h, problem.ref(), out.ctypes.data, C.byref(w)))
+        return out
+
+    def stats(self) -> dict:
+        s = _abi.kp_stats()
+        lib().kp_get_stats(self._h, C.byref(s))
+        return {n: getattr(s, n) for n, _ in s._fields_}

@@ -1,0 +1,594 @@
+// kp_api.cu -- the C ABI of include/karpsolve.h: device memory, transfers, kernel launches, result assembly.
+#include <cuda_runtime.h>
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/gather.h>
+#include <thrust/sequence.h>
+#include <thrust/sort.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "kp_consolidate.cuh"
+#include "kp_prep.hpp"
+#include "kp_solve.cuh"
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                   \
+      return KP_ERR_CUDA;                                                                            \
+    }                                                                                                \
+  } while (0)
+
+struct Arena {  // every device allocation of one upload; freed together
+  std::vector<void*> ptrs;
+  size_t bytes = 0;
+  template <class T>
+  cudaError_t alloc(T** out, size_t n) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(p);
+    bytes += n * sizeof(T);
+    *out = (T*)p;
+    return cudaSuccess;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+    bytes = 0;
+  }
+};
+
+struct kp_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  Arena arena;
+  KpDev dev;
+  HostTables host;
+  bool resident = false;
+  // copies of problem scalars needed to assemble results
+  int64_t P = 0;
+  int n_keys = 0, n_resources = 0, n_its = 0, hostname_key = -1, n_nodes = 0;
+  std::vector<int> key_nvalues;
+  std::vector<int64_t> tmpl_remaining0;
+  // pod sort inputs (device)
+  int32_t* d_pod_class = nullptr;
+  int64_t* d_pod_creation = nullptr;
+  uint64_t *d_uid_hi = nullptr, *d_uid_lo = nullptr;
+  int64_t* d_class_rank = nullptr;
+  kp_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+template <class T>
+static cudaError_t up(kp_handle* h, const T** dst, const std::vector<T>& v) {
+  T* p;
+  cudaError_t e = h->arena.alloc(&p, v.size());
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) e = cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+  h->stats.bytes_h2d += v.size() * sizeof(T);
+  *dst = p;
+  return e;
+}
+template <class T>
+static cudaError_t up_mut(kp_handle* h, T** dst, const std::vector<T>& v) {
+  const T* p;
+  cudaError_t e = up(h, &p, v);
+  *dst = const_cast<T*>(p);
+  return e;
+}
+template <class T>
+static cudaError_t up_raw(kp_handle* h, T** dst, const T* src, size_t n) {
+  T* p;
+  cudaError_t e = h->arena.alloc(&p, n);
+  if (e != cudaSuccess) return e;
+  if (n) e = cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+  h->stats.bytes_h2d += n * sizeof(T);
+  *dst = p;
+  return e;
+}
+template <class T>
+static cudaError_t zeros(kp_handle* h, T** dst, size_t n) {
+  T* p;
+  cudaError_t e = h->arena.alloc(&p, n);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), h->stream);
+  *dst = p;
+  return e;
+}
+
+__global__ void k_sort_keys(const int32_t* pod_class, const int64_t* class_rank, const int32_t* perm, int64_t n,
+                            int64_t* out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = class_rank[pod_class[perm[i]]];
+}
+template <class T>
+__global__ void k_gather(const T* src, const int32_t* perm, int64_t n, T* out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[perm[i]];
+}
+__global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+extern "C" {
+
+int kp_version(void) { return KP_ABI_VERSION; }
+
+int kp_create(int device, kp_handle** out) {
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return KP_ERR_CUDA;  // no CPU fallback
+  kp_handle* h = new kp_handle();
+  if (device < 0) cudaGetDevice(&device);
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&h->stream) != cudaSuccess) {
+    delete h;
+    return KP_ERR_CUDA;
+  }
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  cudaDeviceSetLimit(cudaLimitStackSize, 16384);  // pdqsort emulation recurses (log n deep)
+  *out = h;
+  return KP_OK;
+}
+
+void kp_destroy(kp_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  h->arena.release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* kp_last_error(kp_handle* h) { return h ? h->err.c_str() : "no handle"; }
+
+int kp_get_stats(kp_handle* h, kp_stats* out) {
+  *out = h->stats;
+  return KP_OK;
+}
+
+static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
+  HostTables& t = h->host;
+  KpDev& d = h->dev;
+  memset(&d, 0, sizeof(d));
+  d.K = t.K;
+  d.R = t.R;
+  d.T = t.T;
+  d.ITW = t.ITW;
+  d.N = t.N;
+  d.X = t.X;
+  d.G = t.G;
+  d.GH = t.GH;
+  d.E = t.E;
+  d.D = t.D;
+  d.n_reqsets = t.n_reqsets;
+  d.n_taintsets = t.n_taintsets;
+  d.n_tolsets = t.n_tolsets;
+  d.has_bounds = t.has_bounds;
+  d.hostname_key = t.hostname_key;
+  d.nodes_res = t.nodes_res;
+  d.n_rv = t.n_rv;
+  d.stable_order = p->claim_order_mode == 1;
+  CK(up(h, &d.key_wellknown, t.key_wellknown));
+  CK(up(h, &d.key_univ, t.key_univ));
+  CK(up(h, &d.val_int, t.val_int));
+  CK(up(h, &d.val_isint, t.val_isint));
+  CK(up(h, &d.rs_flags, t.rs_flags));
+  CK(up(h, &d.rs_mask, t.rs_mask));
+  CK(up(h, &d.rs_gte, t.rs_gte));
+  CK(up(h, &d.rs_lte, t.rs_lte));
+  CK(up(h, &d.rs_keys, t.rs_keys));
+  CK(up(h, &d.tol_ok, t.tol_ok));
+  CK(up(h, &d.itv, t.itv));
+  CK(up(h, &d.it_nokey, t.it_nokey));
+  CK(up(h, &d.it_dne, t.it_dne));
+  CK(up(h, &d.it_nonempty, t.it_nonempty));
+  CK(up(h, &d.it_valid, t.it_valid));
+  CK(up(h, &d.ge_vals, t.ge_vals));
+  CK(up(h, &d.ge_n, t.ge_n));
+  CK(up(h, &d.ge_bits, t.ge_bits));
+  CK(up(h, &d.offset_rs, t.offset_rs));
+  CK(up(h, &d.offset_bits, t.offset_bits));
+  CK(up(h, &d.it_capacity, t.it_capacity));
+  CK(up(h, &d.tmpl_rs, t.tmpl_rs));
+  CK(up(h, &d.tmpl_taintset, t.tmpl_taintset));
+  CK(up(h, &d.tmpl_its_raw, t.tmpl_its_raw));
+  CK(zeros(h, &d.tmpl_its, t.tmpl_its_raw.size()));
+  CK(up(h, &d.tmpl_daemon, t.tmpl_daemon));
+  CK(up_mut(h, &d.tmpl_remaining, t.tmpl_remaining));
+  CK(up(h, &d.tmpl_limit_present, t.tmpl_limit_present));
+  CK(up(h, &d.cls_req, t.cls_req));
+  CK(up(h, &d.cls_rs, t.cls_rs));
+  CK(up(h, &d.cls_strict_rs, t.cls_strict_rs));
+  CK(up(h, &d.cls_tolset, t.cls_tolset));
+  CK(up(h, &d.cls_rv, t.cls_rv));
+  CK(up(h, &d.cls_match_off, t.cls_match_off));
+  CK(up(h, &d.cls_match, t.cls_match));
+  CK(up(h, &d.cls_rec_off, t.cls_rec_off));
+  CK(up(h, &d.cls_rec, t.cls_rec));
+  CK(up(h, &d.groups, t.groups));
+  CK(up(h, &d.filter_rs, t.filter_rs));
+  CK(up_mut(h, &d.dom_cnt, t.dom_cnt));
+  CK(up_mut(h, &d.dom_reg, t.dom_reg));
+  CK(up_mut(h, &d.dom_pop, t.dom_pop));
+  CK(up_mut(h, &d.g_ndomains, t.g_ndomains));
+  CK(up_mut(h, &d.g_nempty, t.g_nempty));
+  CK(up(h, &d.node_taintset, t.node_taintset));
+  CK(up(h, &d.node_flags, t.node_flags));
+  CK(up_mut(h, &d.node_rem, t.node_rem));
+  CK(up_mut(h, &d.node_rem_present, t.node_rem_present));
+  CK(up_mut(h, &d.node_sflags, t.node_sflags));
+  CK(up_mut(h, &d.node_smask, t.node_smask));
+  CK(up_mut(h, &d.node_sgte, t.node_sgte));
+  CK(up_mut(h, &d.node_slte, t.node_slte));
+  CK(zeros(h, &d.node_npods, (size_t)std::max(t.E, 1)));
+  // claims
+  d.Cmax = cmax_hint;
+  size_t C = (size_t)d.Cmax;
+  CK(zeros(h, &d.c_tmpl, C));
+  CK(zeros(h, &d.c_npods, C));
+  CK(zeros(h, &d.c_req, C * t.R));
+  CK(zeros(h, &d.c_sflags, C * t.K));
+  CK(zeros(h, &d.c_smask, C * t.K));
+  CK(zeros(h, &d.c_sgte, C * t.K));
+  CK(zeros(h, &d.c_slte, C * t.K));
+  CK(zeros(h, &d.c_its, C * t.ITW));
+  CK(zeros(h, &d.order, C));
+  CK(zeros(h, &d.cnt_at, C));
+  CK(zeros(h, &d.rdead, (size_t)t.n_rv * ((C + 31) / 32)));
+  d.H = t.E + d.Cmax;
+  CK(zeros(h, &d.host_cnt, (size_t)std::max(t.GH, 1) * d.H));
+  for (int g = 0; g < t.GH; g++)
+    if (t.E)
+      CK(cudaMemcpyAsync(d.host_cnt + (size_t)g * d.H, t.host_cnt_nodes.data() + (size_t)g * t.E,
+                         (size_t)t.E * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CK(zeros(h, &d.n_claims, 1));
+  CK(zeros(h, &d.counters, 8));
+  CK(zeros(h, &d.status, 1));
+  return KP_OK;
+}
+
+// stack of state the solve mutates, so kp_solve_resident can be re-run on the same upload
+static int reset_dynamic(kp_handle* h) {
+  HostTables& t = h->host;
+  KpDev& d = h->dev;
+  auto cp = [&](void* dst, const void* src, size_t n) {
+    return n ? cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
+  };
+  CK(cp(d.tmpl_remaining, t.tmpl_remaining.data(), t.tmpl_remaining.size() * 8));
+  CK(cp(d.dom_cnt, t.dom_cnt.data(), t.dom_cnt.size() * 4));
+  CK(cp(d.dom_reg, t.dom_reg.data(), t.dom_reg.size() * 8));
+  CK(cp(d.dom_pop, t.dom_pop.data(), t.dom_pop.size() * 8));
+  CK(cp(d.g_ndomains, t.g_ndomains.data(), t.g_ndomains.size() * 4));
+  CK(cp(d.g_nempty, t.g_nempty.data(), t.g_nempty.size() * 4));
+  CK(cp(d.node_rem, t.node_rem.data(), t.node_rem.size() * 8));
+  CK(cp(d.node_rem_present, t.node_rem_present.data(), t.node_rem_present.size() * 4));
+  CK(cp(d.node_sflags, t.node_sflags.data(), t.node_sflags.size()));
+  CK(cp(d.node_smask, t.node_smask.data(), t.node_smask.size() * 8));
+  CK(cp(d.node_sgte, t.node_sgte.data(), t.node_sgte.size() * 8));
+  CK(cp(d.node_slte, t.node_slte.data(), t.node_slte.size() * 8));
+  CK(cudaMemsetAsync(d.node_npods, 0, (size_t)std::max(t.E, 1) * 4, h->stream));
+  size_t C = (size_t)d.Cmax;
+  CK(cudaMemsetAsync(d.c_npods, 0, C * 4, h->stream));
+  CK(cudaMemsetAsync(d.rdead, 0, (size_t)t.n_rv * ((C + 31) / 32) * 4, h->stream));
+  CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)std::max(t.GH, 1) * d.H * 4, h->stream));
+  for (int g = 0; g < t.GH; g++)
+    if (t.E)
+      CK(cudaMemcpyAsync(d.host_cnt + (size_t)g * d.H, t.host_cnt_nodes.data() + (size_t)g * t.E,
+                         (size_t)t.E * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(d.n_claims, 0, 4, h->stream));
+  CK(cudaMemsetAsync(d.counters, 0, 64, h->stream));
+  CK(cudaMemsetAsync(d.status, 0, 4, h->stream));
+  CK(cudaMemsetAsync(d.last_len, 0, (size_t)std::max<int64_t>(h->P, 1) * 4, h->stream));
+  return KP_OK;
+}
+
+static int do_upload(kp_handle* h, const kp_problem* p, int cmax) {
+  cudaSetDevice(h->device);
+  h->arena.release();
+  h->resident = false;
+  h->stats = kp_stats{};
+  auto t0 = std::chrono::steady_clock::now();
+  h->host = HostTables();
+  std::vector<uint8_t> active(p->n_nodes, 0);
+  for (int i = 0; i < p->n_nodes; i++) active[i] = (p->node_flags[i] & KP_NODE_SCHEDULABLE) != 0;
+  std::vector<int32_t> pending(p->pod_class, p->pod_class + p->n_pods);
+  int rc = kp_prepare(p, active, {}, pending, h->host, h->err);
+  if (rc != KP_OK) return rc;
+  auto t1 = std::chrono::steady_clock::now();
+  h->stats.prep_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  h->P = p->n_pods;
+  h->n_keys = p->n_keys;
+  h->n_resources = p->n_resources;
+  h->n_its = p->n_its;
+  h->n_nodes = p->n_nodes;
+  h->hostname_key = h->host.hostname_key;
+  h->key_nvalues.resize(p->n_keys);
+  for (int k = 0; k < p->n_keys; k++) h->key_nvalues[k] = p->key_value_off[k + 1] - p->key_value_off[k];
+  if (p->n_pods >= (1ll << 31) - 2) return h->err = "more than 2^31 pods", KP_ERR_CAPACITY;
+  rc = upload_tables(h, p, cmax);
+  if (rc != KP_OK) return rc;
+  KpDev& d = h->dev;
+  d.P = p->n_pods;
+  size_t P = (size_t)p->n_pods;
+  CK(up_raw(h, &h->d_pod_class, p->pod_class, P));
+  d.pod_class = h->d_pod_class;
+  if (p->pod_creation) {
+    CK(up_raw(h, &h->d_pod_creation, p->pod_creation, P));
+  } else {
+    CK(zeros(h, &h->d_pod_creation, P));
+  }
+  CK(up_raw(h, &h->d_uid_hi, p->pod_uid_hi, P));
+  CK(up_raw(h, &h->d_uid_lo, p->pod_uid_lo, P));
+  // class rank for byCPUAndMemoryDescending (queue.go:72-108): cpu desc, then memory desc
+  std::vector<int64_t> rank(std::max(h->host.X, 1), 0);
+  {
+    std::vector<int> idx(h->host.X);
+    for (int i = 0; i < h->host.X; i++) idx[i] = i;
+    auto key = [&](int x) { return std::make_pair(-h->host.cls_sort_cpu[x], -h->host.cls_sort_mem[x]); };
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return key(a) < key(b); });
+    int64_t r = -1;
+    for (size_t i = 0; i < idx.size(); i++) {
+      if (i == 0 || key(idx[i]) != key(idx[i - 1])) r++;
+      rank[idx[i]] = r;
+    }
+  }
+  CK(up_raw(h, &h->d_class_rank, rank.data(), rank.size()));
+  CK(zeros(h, &d.queue, P + 1));
+  CK(zeros(h, &d.last_len, P));
+  CK(zeros(h, &d.pod_target, P));
+  CK(zeros(h, &d.pod_error, P));
+  CK(cudaStreamSynchronize(h->stream));
+  auto t2 = std::chrono::steady_clock::now();
+  h->stats.upload_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+  h->resident = true;
+  return KP_OK;
+}
+
+int kp_upload(kp_handle* h, const kp_problem* p) {
+  // claim capacity: every pod could need its own NodeClaim; start with a generous bound and grow on demand
+  int64_t guess = std::min<int64_t>(p->n_pods, std::max<int64_t>(4096, p->n_pods / 8));
+  return do_upload(h, p, (int)std::max<int64_t>(guess, 1));
+}
+
+static int run_solve(kp_handle* h) {
+  KpDev& d = h->dev;
+  cudaSetDevice(h->device);
+  int rc = reset_dynamic(h);
+  if (rc != KP_OK) return rc;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  int64_t P = h->P;
+  h->stats.kernel_launches = 0;
+  // NewScheduler prefilter of template instance types (scheduler.go:147)
+  if (d.N > 0) {
+    k_feasibility<<<(d.N * 32 + 255) / 256, 256, 0, h->stream>>>(d, nullptr, 1);
+    h->stats.kernel_launches++;
+  }
+  // NewQueue: sort pods cpu desc, mem desc, creation asc, uid asc (queue.go:37-43). LSD passes of a stable sort.
+  if (P > 0) {
+    auto pol = thrust::cuda::par.on(h->stream);
+    thrust::device_ptr<int32_t> perm(d.queue);
+    thrust::sequence(pol, perm, perm + P);
+    int64_t* keys;
+    CK(cudaMallocAsync(&keys, P * 8, h->stream));
+    thrust::device_ptr<int64_t> k64(keys);
+    thrust::device_ptr<uint64_t> ku64((uint64_t*)keys);
+    int nb = (int)((P + 255) / 256);
+    k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_lo, d.queue, P, (uint64_t*)keys);
+    thrust::stable_sort_by_key(pol, ku64, ku64 + P, perm);
+    k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_hi, d.queue, P, (uint64_t*)keys);
+    thrust::stable_sort_by_key(pol, ku64, ku64 + P, perm);
+    k_gather<<<nb, 256, 0, h->stream>>>(h->d_pod_creation, d.queue, P, keys);
+    thrust::stable_sort_by_key(pol, k64, k64 + P, perm);
+    k_sort_keys<<<nb, 256, 0, h->stream>>>(d.pod_class, h->d_class_rank, d.queue, P, keys);
+    thrust::stable_sort_by_key(pol, k64, k64 + P, perm);
+    CK(cudaFreeAsync(keys, h->stream));
+    k_fill_i32<<<nb, 256, 0, h->stream>>>(d.pod_target, P, KP_TARGET_UNSCHEDULED);
+    h->stats.kernel_launches += 5;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveShared));
+    attr_set = true;
+  }
+  k_solve<<<1, SOLVE_THREADS, sizeof(SolveShared), h->stream>>>(d);
+  h->stats.kernel_launches++;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.solve_ms = ms;
+  return KP_OK;
+}
+
+static int download(kp_handle* h, kp_result* out) {
+  KpDev& d = h->dev;
+  auto t0 = std::chrono::steady_clock::now();
+  memset(out, 0, sizeof(*out));
+  int32_t nclaims = 0;
+  int64_t counters[8];
+  CK(cudaMemcpy(&nclaims, d.n_claims, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counters, d.counters, 64, cudaMemcpyDeviceToHost));
+  int64_t P = h->P;
+  int K = h->n_keys, R = h->n_resources, ITW = (h->n_its + 63) / 64;
+  size_t C = (size_t)nclaims, c1 = C ? C : 1;
+  out->n_pods = P;
+  out->pod_target = (int32_t*)malloc(sizeof(int32_t) * (P ? P : 1));
+  out->pod_error = (uint8_t*)malloc(P ? P : 1);
+  CK(cudaMemcpy(out->pod_target, d.pod_target, P * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out->pod_error, d.pod_error, P, cudaMemcpyDeviceToHost));
+  out->n_claims = nclaims;
+  out->claim_template = (int32_t*)calloc(c1, 4);
+  out->claim_npods = (int32_t*)calloc(c1, 4);
+  out->claim_rank = (int32_t*)calloc(c1, 4);
+  out->claim_requests = (int64_t*)calloc(c1 * R, 8);
+  out->it_words = ITW;
+  out->claim_its = (uint64_t*)calloc(c1 * (ITW ? ITW : 1), 8);
+  CK(cudaMemcpy(out->claim_template, d.c_tmpl, C * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out->claim_npods, d.c_npods, C * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out->claim_requests, d.c_req, C * R * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out->claim_its, d.c_its, C * ITW * 8, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> order(c1);
+  CK(cudaMemcpy(order.data(), d.order, C * 4, cudaMemcpyDeviceToHost));
+  for (size_t pos = 0; pos < C; pos++) out->claim_rank[order[pos]] = (int32_t)pos;
+  // requirement slots -> the ABI's per-key layout (FinalizeScheduling drops the hostname requirement: it is never
+  // materialised as a slot here)
+  std::vector<uint8_t> sf(c1 * K);
+  std::vector<uint64_t> sm(c1 * K);
+  std::vector<int64_t> sg(c1 * K), sl(c1 * K);
+  CK(cudaMemcpy(sf.data(), d.c_sflags, C * K, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sm.data(), d.c_smask, C * K * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sg.data(), d.c_sgte, C * K * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sl.data(), d.c_slte, C * K * 8, cudaMemcpyDeviceToHost));
+  std::vector<int> woff(K + 1, 0);
+  for (int k = 0; k < K; k++) woff[k + 1] = woff[k] + (k == h->hostname_key ? 0 : (h->key_nvalues[k] + 63) / 64);
+  int MW = woff[K];
+  out->n_keys = K;
+  out->mask_words = MW;
+  out->claim_req_flags = (uint8_t*)calloc(c1 * (K ? K : 1), 1);
+  out->claim_req_gte = (int64_t*)calloc(c1 * (K ? K : 1), 8);
+  out->claim_req_lte = (int64_t*)calloc(c1 * (K ? K : 1), 8);
+  out->claim_req_mask = (uint64_t*)calloc(c1 * (MW ? MW : 1), 8);
+  for (size_t c = 0; c < C; c++)
+    for (int k = 0; k < K; k++) {
+      uint8_t f = sf[c * K + k];
+      if (!(f & SF_PRESENT) || k == h->hostname_key) continue;
+      uint8_t of = KP_SLOT_PRESENT | ((f & SF_COMPLEMENT) ? KP_REQ_COMPLEMENT : 0) |
+                   ((f & SF_HAS_GTE) ? KP_REQ_HAS_GTE : 0) | ((f & SF_HAS_LTE) ? KP_REQ_HAS_LTE : 0);
+      out->claim_req_flags[c * K + k] = of;
+      if (f & SF_HAS_GTE) out->claim_req_gte[c * K + k] = sg[c * K + k];
+      if (f & SF_HAS_LTE) out->claim_req_lte[c * K + k] = sl[c * K + k];
+      if (woff[k + 1] > woff[k]) out->claim_req_mask[c * MW + woff[k]] = sm[c * K + k];
+    }
+  // topology counters, non-hostname groups (regular then inverse == creation order of the reference's two maps)
+  HostTables& t = h->host;
+  std::vector<int32_t> cnt((size_t)std::max(t.G, 1) * 64);
+  CK(cudaMemcpy(cnt.data(), d.dom_cnt, cnt.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> off{0}, flat;
+  for (int g = 0; g < t.G; g++) {
+    int key = t.groups[g].key;
+    if (key != t.hostname_key) {
+      int nv = h->key_nvalues[key];
+      for (int v = 0; v < nv; v++) flat.push_back(cnt[(size_t)g * 64 + v]);
+    }
+    off.push_back((int32_t)flat.size());
+  }
+  out->n_groups = t.G;
+  out->n_domain_slots = (int32_t)flat.size();
+  out->group_domain_off = (int32_t*)malloc(off.size() * 4);
+  memcpy(out->group_domain_off, off.data(), off.size() * 4);
+  out->domain_counts = (int32_t*)malloc((flat.size() ? flat.size() : 1) * 4);
+  if (!flat.empty()) memcpy(out->domain_counts, flat.data(), flat.size() * 4);
+  out->n_existing_evals = counters[0];
+  out->n_inflight_evals = counters[1];
+  out->n_template_evals = counters[2];
+  out->n_commits = counters[3];
+  out->solve_ms = h->stats.solve_ms;
+  h->stats.bytes_d2h = P * 5 + C * (8 + (size_t)R * 8 + (size_t)ITW * 8 + (size_t)K * 25) + cnt.size() * 4;
+  auto t1 = std::chrono::steady_clock::now();
+  h->stats.download_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  return KP_OK;
+}
+
+int kp_solve_resident(kp_handle* h, int64_t deadline_ms, kp_result* out) {
+  (void)deadline_ms;
+  if (!h->resident) return h->err = "kp_upload has not been called", KP_ERR_INVALID;
+  int rc = run_solve(h);
+  if (rc != KP_OK) return rc;
+  int32_t status = 0;
+  CK(cudaMemcpy(&status, h->dev.status, 4, cudaMemcpyDeviceToHost));
+  if (status != KP_OK) return h->err = "claim capacity exceeded", status;
+  return download(h, out);
+}
+
+int kp_solve(kp_handle* h, const kp_problem* p, int64_t deadline_ms, kp_result* out) {
+  int64_t cmax = std::min<int64_t>(p->n_pods, std::max<int64_t>(4096, p->n_pods / 8));
+  for (;;) {
+    int rc = do_upload(h, p, (int)std::max<int64_t>(cmax, 1));
+    if (rc != KP_OK) return rc;
+    rc = kp_solve_resident(h, deadline_ms, out);
+    if (rc == KP_ERR_CAPACITY && cmax < p->n_pods) {  // more NodeClaims than provisioned: grow and redo
+      cmax = std::min<int64_t>(p->n_pods, cmax * 4);
+      continue;
+    }
+    return rc;
+  }
+}
+
+void kp_result_free(kp_result* r) {
+  free(r->pod_target);
+  free(r->pod_error);
+  free(r->claim_template);
+  free(r->claim_npods);
+  free(r->claim_rank);
+  free(r->claim_requests);
+  free(r->claim_its);
+  free(r->claim_req_flags);
+  free(r->claim_req_gte);
+  free(r->claim_req_lte);
+  free(r->claim_req_mask);
+  free(r->group_domain_off);
+  free(r->domain_counts);
+  memset(r, 0, sizeof(*r));
+}
+
+int kp_feasibility(kp_handle* h, const kp_problem* p, uint64_t* out_bits, int32_t* out_it_words) {
+  int rc = do_upload(h, p, 1);
+  if (rc != KP_OK) return rc;
+  KpDev& d = h->dev;
+  *out_it_words = d.ITW;
+  size_t n = (size_t)d.X * d.N * d.ITW;
+  uint64_t* dout;
+  CK(cudaMalloc(&dout, std::max<size_t>(n, 1) * 8));
+  if (d.N > 0) k_feasibility<<<(d.N * 32 + 255) / 256, 256, 0, h->stream>>>(d, nullptr, 1);
+  CK(cudaEventRecord(h->ev0, h->stream));
+  if (d.N > 0 && d.X > 0) {
+    int blocks = 148 * 8;
+    k_feasibility<<<blocks, 256, 0, h->stream>>>(d, dout, 0);
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.solve_ms = ms;
+  CK(cudaMemcpy(out_bits, dout, n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dout);
+  return KP_OK;
+}
+
+int kp_consolidate(kp_handle* h, const kp_problem* cluster, const kp_consol_input* in, int64_t deadline_ms,
+                   kp_consol_result* out) {
+  (void)deadline_ms;
+  return kp_consolidate_impl(h, cluster, in, out);
+}
+
+void kp_consol_result_free(kp_consol_result* r) {
+  free(r->decision);
+  free(r->replacement_its);
+  free(r->n_new_claims);
+  free(r->n_unscheduled);
+  memset(r, 0, sizeof(*r));
+}
+}
+
+static int kp_consolidate_impl(kp_handle* h, const kp_problem* cluster, const kp_consol_input* in,
+                               kp_consol_result* out) {
+  (void)cluster;
+  (void)in;
+  (void)out;
+  h->err = "consolidation kernel not built yet";
+  return KP_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,358 @@
+// kp_kernels.cuh -- device code of the solver (sm_100a).
+//
+//   k_feasibility  (K1)  class x template instance-type feasibility bitmaps: one warp per (class, template) pair,
+//                        bit-sliced mask ANDs -- filterInstanceTypesByRequirements (nodeclaim.go:412-480).
+//   k_solve        (K2/K3) the Scheduler.Solve loop (scheduler.go:381-684): one persistent CTA walks the sorted pod
+//                        queue; per pod a thread-per-candidate filter then a warp-per-candidate exact CanAdd
+//                        (existingnode.go:70-143, nodeclaim.go:114-202) with a ballot for the lowest feasible index,
+//                        and a one-warp commit (NodeClaim.Add / ExistingNode.Add / Topology.Record).
+//
+// Warp layout of an evaluation: lane k owns label key k (requirement slot), lane r owns resource r, lane w owns
+// instance-type bitmap word w.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/karpsolve.h"
+#include "kp_slot.hpp"
+
+#define FULL 0xffffffffu
+#define SOLVE_THREADS 1024
+#define SOLVE_WARPS (SOLVE_THREADS / 32)
+
+__device__ __forceinline__ KeyInfo key_info(const KpDev& d, int k) {
+  return KeyInfo{d.val_int + (size_t)k * 64, d.val_isint[k], d.key_univ[k]};
+}
+__device__ __forceinline__ Slot load_slot(const uint8_t* f, const uint64_t* m, const int64_t* g, const int64_t* l,
+                                          size_t i, int has_bounds) {
+  Slot s;
+  s.f = f[i];
+  s.m = m[i];
+  s.gte = has_bounds ? g[i] : 0;
+  s.lte = has_bounds ? l[i] : 0;
+  return s;
+}
+// Taints(taintset).Tolerates(tolset) (pkg/scheduling/taints.go:54-66), precomputed on the host
+__device__ __forceinline__ bool tolerated(const KpDev& d, int tolset, int taintset) {
+  if (taintset < 0 || d.n_taintsets == 0) return true;
+  return d.tol_ok[(size_t)(tolset + 1) * d.n_taintsets + taintset];
+}
+__device__ __forceinline__ Slot rs_slot(const KpDev& d, int rs, int k) {
+  return load_slot(d.rs_flags, d.rs_mask, d.rs_gte, d.rs_lte, (size_t)rs * d.K + k, d.has_bounds);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Instance-type filter on bit-sliced tables. `S` = the candidate's final requirement slots (one per key, readable by
+// every lane), q = total requests (lane r holds q[r]).  Lane w returns word w of
+//   compat & fits & hasOffering      (nodeclaim.go:434-445)
+// and *fits_word = word w of the resource-only test (used for the monotone "never fits again" marking).
+__device__ __forceinline__ uint64_t filter_its_word(const KpDev& d, const Slot* S, int64_t q_lane, int lane,
+                                                    uint64_t* fits_word) {
+  const int K = d.K, R = d.R, ITW = d.ITW;
+  // resources.Fits(total, allocatable) via ">= threshold" bitmaps: lane r ranks q[r]
+  int j = 0;
+  if (lane < R) {
+    const int64_t* vals = d.ge_vals + (size_t)lane * d.T;
+    int lo = 0, hi = d.ge_n[lane];
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (vals[mid] < q_lane)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    j = lo;
+  }
+  uint64_t fw = (lane < ITW) ? d.it_valid[lane] : 0ull;
+  for (int r = 0; r < R; r++) {
+    int jr = __shfl_sync(FULL, j, r);
+    if (lane < ITW) fw &= (jr < d.ge_n[r]) ? d.ge_bits[((size_t)r * d.T + jr) * ITW + lane] : 0ull;
+  }
+  *fits_word = fw;
+  // hasOffering: lane dd decides Compatible(S, offering set dd, AllowUndefinedWellKnownLabels)
+  bool off_ok = false;
+  if (lane < d.D) {
+    int rs = d.offset_rs[lane];
+    uint32_t keys = d.rs_keys[rs];
+    off_ok = true;
+    while (keys) {
+      int k = __ffs(keys) - 1;
+      keys &= keys - 1;
+      if (!slot_compatible(key_info(d, k), S[k], rs_slot(d, rs, k), d.key_wellknown[k], true)) off_ok = false;
+    }
+  }
+  uint32_t off_mask = __ballot_sync(FULL, off_ok);
+  uint64_t ow = 0, cw = ~0ull;
+  if (lane < ITW) {
+    while (off_mask) {
+      int dd = __ffs(off_mask) - 1;
+      off_mask &= off_mask - 1;
+      ow |= d.offset_bits[(size_t)dd * ITW + lane];
+    }
+    // compatible(): InstanceType.Requirements.Intersects(S) -- shared keys only (requirements.go:254-274)
+    for (int k = 0; k < K; k++) {
+      Slot s = S[k];
+      if (!slot_present(s)) continue;
+      KeyInfo ki = key_info(d, k);
+      uint64_t allowed = slot_allowed(ki, s);
+      uint64_t bw = d.it_nokey[(size_t)k * ITW + lane];
+      if (allowed == ki.univ) {
+        bw |= d.it_nonempty[(size_t)k * ITW + lane];
+      } else {
+        while (allowed) {
+          int v = __ffsll((long long)allowed) - 1;
+          allowed &= allowed - 1;
+          bw |= d.itv[((size_t)k * 64 + v) * ITW + lane];
+        }
+      }
+      if (op_is_negative(slot_op(s))) bw |= d.it_dne[(size_t)k * ITW + lane];
+      cw &= bw;
+    }
+  } else {
+    cw = 0;
+  }
+  return cw & fw & ow;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TopologyGroup.Get for a non-hostname key (topologygroup.go:226-428). Runs on the lane that owns the key.
+// Returns the `domains` requirement; an empty concrete set means "no eligible domain".
+__device__ __forceinline__ Slot topo_domains(const KpDev& d, int g, const KpGroup& G, bool self, const Slot& pod_d,
+                                             const Slot& node_d, uint64_t reg, uint64_t pop) {
+  KeyInfo ki = key_info(d, G.key);
+  const int32_t* cnt = d.dom_cnt + G.dom_off;
+  uint64_t pod_allowed = slot_allowed(ki, pod_d);
+  uint64_t node_allowed = slot_allowed(ki, node_d);
+  bool node_in = slot_present(node_d) && slot_op(node_d) == OP_IN;
+  Slot out;
+  out.f = SF_PRESENT;
+  out.m = 0;
+  out.gte = 0;
+  out.lte = 0;
+  if (G.type == KP_TOPO_SPREAD) {
+    // domainMinCount (topologygroup.go:289-310)
+    uint64_t sup = reg & pod_allowed;
+    long long mn = 2147483647LL;
+    int nsup = __popcll(sup);
+    for (uint64_t s = sup; s;) {
+      int v = __ffsll((long long)s) - 1;
+      s &= s - 1;
+      if (cnt[v] < mn) mn = cnt[v];
+    }
+    if (G.min_domains >= 0 && nsup < G.min_domains) mn = 0;
+    uint64_t cand = node_in ? (node_d.m & reg) : (reg & node_allowed);
+    long long best_c = 2147483647LL;
+    int best = -1;
+    while (cand) {  // ascending value id == the canonical iteration order
+      int v = __ffsll((long long)cand) - 1;
+      cand &= cand - 1;
+      long long c = (long long)cnt[v] + (self ? 1 : 0);
+      if (c - mn <= (long long)G.max_skew && c < best_c) {
+        best = v;
+        best_c = c;
+      }
+    }
+    if (best >= 0) out.m = 1ull << best;
+    return out;
+  }
+  if (G.type == KP_TOPO_AFFINITY) {
+    uint64_t opts = node_in ? (node_d.m & pod_allowed & reg & pop) : (reg & pod_allowed & pop & node_allowed);
+    if (opts) {
+      out.m = opts;
+      return out;
+    }
+    bool none_populated = (reg & pop) == 0;
+    bool any_compat = (reg & pop & pod_allowed) != 0;
+    if (self && (none_populated || !any_compat)) {
+      Slot pd = slot_present(pod_d) ? pod_d : slot_exists();
+      Slot nd = slot_present(node_d) ? node_d : slot_exists();
+      Slot inter = slot_intersection(ki, pd, nd);
+      uint64_t a = reg & slot_allowed(ki, inter);
+      if (a) out.m |= a & (~a + 1);  // lowest id == the canonical "first random domain"
+      uint64_t b = reg & pod_allowed;
+      if (b) out.m |= b & (~b + 1);
+    }
+    return out;
+  }
+  // anti-affinity: empty domains only
+  out.m = reg & ~pop & node_allowed & pod_allowed;
+  return out;
+}
+
+// One evaluated candidate, kept in the evaluating warp's registers until the winner commits.
+struct Eval {
+  bool ok;
+  bool res_dead;   // no remaining instance type can ever hold these requests again (monotone)
+  Slot F;          // lane k: final requirement slot of key k
+  int64_t q;       // lane r: total requests (claims)
+  uint64_t its;    // lane w: surviving instance-type word (claims)
+};
+
+// Exact CanAdd of pod class X on one candidate (NodeClaim.CanAdd nodeclaim.go:114-202 when is_claim, else
+// ExistingNode.CanAdd existingnode.go:70-143 after the taint / Fits checks of phase 1).
+//   base       lane k: the candidate's current requirement slot
+//   host       index of the candidate's hostname domain in host_cnt
+//   scratch    per-warp shared memory, KP_MAXK slots
+__device__ __forceinline__ Eval eval_candidate(const KpDev& d, int X, bool is_claim, const Slot& base, int64_t base_q,
+                                               uint64_t base_its, int host, Slot* scratch, int lane) {
+  Eval ev;
+  ev.ok = false;
+  ev.res_dead = false;
+  const int K = d.K;
+  const bool allow_undef = is_claim;  // ExistingNode.CanAdd passes no compatibility options
+  const bool wk = lane < K ? d.key_wellknown[lane] : false;
+  KeyInfo ki = lane < K ? key_info(d, lane) : KeyInfo{d.val_int, 0ull, 0ull};
+  Slot pod = lane < K ? rs_slot(d, d.cls_rs[X], lane) : slot_absent();
+  // requirements.Compatible(pod requirements) then Add
+  bool bad = lane < K && !slot_compatible(ki, base, pod, wk, allow_undef);
+  if (__any_sync(FULL, bad)) return ev;
+  Slot M = lane < K ? slot_add(ki, base, pod) : slot_absent();
+  // Topology.AddRequirements (topology.go:226-248)
+  Slot Tt = M;
+  bool fail = false;
+  int moff = d.cls_match_off[X], mend = d.cls_match_off[X + 1];
+  if (mend > moff) {
+    Slot strict = lane < K ? rs_slot(d, d.cls_strict_rs[X], lane) : slot_absent();
+    for (int i = moff; i < mend; i++) {
+      int e = d.cls_match[i];
+      int g = e & 0x3fffffff;
+      bool self = (e >> 30) & 1;
+      KpGroup G = d.groups[g];
+      if (G.key == d.hostname_key) {
+        if (lane == 0) {  // candidates carry exactly one hostname: the fast paths of topologygroup.go:235-247,317-333,402-408
+          int cnt = d.host_cnt[(size_t)G.host_row * d.H + host];
+          bool ok;
+          if (G.type == KP_TOPO_SPREAD)
+            ok = cnt + (self ? 1 : 0) <= G.max_skew;
+          else if (G.type == KP_TOPO_AFFINITY)
+            ok = cnt > 0 || (self && (d.g_ndomains[g] - d.g_nempty[g]) == 0);
+          else
+            ok = cnt == 0;
+          if (!ok) fail = true;
+        }
+      } else if (lane == G.key) {
+        Slot dm = topo_domains(d, g, G, self, strict, M, d.dom_reg[g], d.dom_pop[g]);
+        if (dm.m == 0)
+          fail = true;  // topologyError: domains.Len() == 0
+        else
+          Tt = slot_add(ki, Tt, dm);
+      }
+    }
+    if (__any_sync(FULL, fail)) return ev;
+    bad = lane < K && !slot_compatible(ki, M, Tt, wk, allow_undef);
+    if (__any_sync(FULL, bad)) return ev;
+    M = lane < K ? slot_add(ki, M, Tt) : slot_absent();
+  }
+  ev.F = M;
+  if (!is_claim) {
+    ev.ok = true;
+    return ev;
+  }
+  // resources.Merge + filterInstanceTypesByRequirements
+  if (lane < K) scratch[lane] = M;
+  __syncwarp();
+  int64_t q = base_q + (lane < d.R ? d.cls_req[(size_t)X * d.R + lane] : 0);
+  uint64_t fw;
+  uint64_t w = filter_its_word(d, scratch, q, lane, &fw) & base_its;
+  __syncwarp();
+  ev.q = q;
+  ev.its = w;
+  ev.ok = __any_sync(FULL, w != 0);
+  ev.res_dead = !__any_sync(FULL, (fw & base_its) != 0);
+  return ev;
+}
+
+// Topology.Record (topology.go:197-220) for the committed placement; executed by one warp.
+__device__ __forceinline__ void topo_record(const KpDev& d, int X, const Slot& F, int taintset, int host,
+                                            bool allow_undef, int lane) {
+  const int K = d.K;
+  (void)allow_undef;  // TopologyNodeFilter.Matches never forwards the options (topologynodefilter.go:68-85)
+  for (int i = d.cls_rec_off[X]; i < d.cls_rec_off[X + 1]; i++) {
+    int g = d.cls_rec[i];
+    KpGroup G = d.groups[g];
+    bool counts = true;
+    if (!G.inverse) {
+      if (G.affinity_policy == 1 && G.filter_n > 0) {
+        bool any_alt = false;
+        for (int a = 0; a < G.filter_n; a++) {
+          int rs = d.filter_rs[G.filter_off + a];
+          bool bad = lane < K &&
+                     !slot_compatible(key_info(d, lane), F, rs_slot(d, rs, lane), d.key_wellknown[lane], false);
+          if (!__any_sync(FULL, bad)) {
+            any_alt = true;
+            break;
+          }
+        }
+        counts = any_alt;
+      }
+      if (counts && G.taint_policy == 1) {
+        counts = tolerated(d, G.tolset, taintset);
+      }
+    }
+    if (!counts) continue;
+    if (G.key == d.hostname_key) {
+      if (lane == 0) {
+        int32_t* c = d.host_cnt + (size_t)G.host_row * d.H + host;
+        if (*c == 0) d.g_nempty[g]--;
+        (*c)++;
+      }
+    } else {
+      uint32_t ff = __shfl_sync(FULL, F.f, G.key);
+      uint64_t mm = __shfl_sync(FULL, F.m, G.key);
+      if (lane == 0 && (ff & SF_PRESENT)) {
+        uint64_t rec = 0;
+        if (G.inverse || G.type == KP_TOPO_ANTI_AFFINITY)
+          rec = mm;  // every value the node may still take
+        else if (!(ff & SF_COMPLEMENT) && __popcll(mm) == 1)
+          rec = mm;
+        uint64_t bits = rec;
+        while (bits) {
+          int v = __ffsll((long long)bits) - 1;
+          bits &= bits - 1;
+          d.dom_cnt[G.dom_off + v]++;
+        }
+        d.dom_reg[g] |= rec;
+        d.dom_pop[g] |= rec;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1: feasibility of (class, template) pairs without topology. grid-stride over pairs, one warp each.
+__global__ void __launch_bounds__(256) k_feasibility(KpDev d, uint64_t* out, int prefilter_only) {
+  __shared__ Slot scratch_all[8][KP_MAXK];
+  int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  Slot* scratch = scratch_all[wib];
+  int warps = (gridDim.x * blockDim.x) >> 5;
+  int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int npairs = prefilter_only ? d.N : d.X * d.N;
+  for (int pair = gw; pair < npairs; pair += warps) {
+    int X = prefilter_only ? -1 : pair / d.N, n = prefilter_only ? pair : pair % d.N;
+    Slot base = lane < d.K ? rs_slot(d, d.tmpl_rs[n], lane) : slot_absent();
+    uint64_t its = lane < d.ITW ? (prefilter_only ? d.tmpl_its_raw : d.tmpl_its)[(size_t)n * d.ITW + lane] : 0ull;
+    uint64_t w = 0;
+    if (prefilter_only) {  // scheduler.go:147: filter by the template requirements alone, zero requests
+      if (lane < d.K) scratch[lane] = base;
+      __syncwarp();
+      uint64_t fw;
+      w = filter_its_word(d, scratch, 0, lane, &fw) & its;
+      __syncwarp();
+      if (lane < d.ITW) d.tmpl_its[(size_t)n * d.ITW + lane] = w;
+    } else {
+      bool tol_ok = tolerated(d, d.cls_tolset[X], d.tmpl_taintset[n]);
+      KeyInfo ki = lane < d.K ? key_info(d, lane) : KeyInfo{d.val_int, 0ull, 0ull};
+      Slot pod = lane < d.K ? rs_slot(d, d.cls_rs[X], lane) : slot_absent();
+      bool bad = lane < d.K && !slot_compatible(ki, base, pod, d.key_wellknown[lane], true);
+      bool any_bad = __any_sync(FULL, bad);
+      Slot M = lane < d.K ? slot_add(ki, base, pod) : slot_absent();
+      if (lane < d.K) scratch[lane] = M;
+      __syncwarp();
+      int64_t q = lane < d.R ? d.tmpl_daemon[(size_t)n * d.R + lane] + d.cls_req[(size_t)X * d.R + lane] : 0;
+      uint64_t fw;
+      w = filter_its_word(d, scratch, q, lane, &fw) & its;
+      __syncwarp();
+      if (any_bad || !tol_ok) w = 0;
+      if (lane < d.ITW) out[((size_t)X * d.N + n) * d.ITW + lane] = w;
+    }
+  }
+}

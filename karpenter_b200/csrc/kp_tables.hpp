@@ -1,0 +1,137 @@
+// kp_tables.hpp -- the HBM-resident layout of a scheduling problem (shared between host prep and the kernels).
+//
+// Requirements (pkg/scheduling/requirements.go:36) become fixed-width rows: one slot per label key, each slot a flag
+// byte + one 64-bit value mask (+ optional integer bounds).  Instance-type side data is bit-sliced: for every
+// (key, value) a bitmap over instance types, for every resource a table of ">= threshold" bitmaps, for every distinct
+// offering requirement set a bitmap of the types that sell it.  filterInstanceTypesByRequirements
+// (nodeclaim.go:412-480) then is a handful of coalesced 64-bit ANDs/ORs per instance-type word.
+#pragma once
+#include <cstdint>
+
+#define KP_MAXK 32          // label keys (one warp lane per key)
+#define KP_MAXR 8           // resources
+#define KP_MAX_ITW 32       // instance-type bitmap words (<= 2048 types, one lane per word)
+#define KP_MAX_OFFSETS 32   // distinct offering requirement sets
+
+// slot flags
+#define SF_COMPLEMENT 0x01u
+#define SF_HAS_GTE 0x02u
+#define SF_HAS_LTE 0x04u
+#define SF_PRESENT 0x10u
+
+// operators of a slot (requirement.go:282-293)
+#define OP_IN 0
+#define OP_NOT_IN 1
+#define OP_EXISTS 2
+#define OP_DNE 3
+
+struct KpGroup {
+  int32_t key;          // label key, or -1 for the hostname key
+  int32_t type;         // KP_TOPO_*
+  int32_t max_skew;
+  int32_t min_domains;  // -1 == nil
+  int32_t inverse;
+  int32_t dom_off;      // offset into dom_cnt (non-hostname groups); hostname groups: row in host_cnt
+  int32_t filter_off, filter_n;   // TopologyNodeFilter.Requirements alternatives (reqset ids)
+  int32_t taint_policy, affinity_policy;  // 0 ignore 1 honor 2 unset
+  int32_t tolset;
+  int32_t host_row;     // row index among hostname groups, -1 otherwise
+};
+
+// pointers into device memory; filled by the host, passed by value to kernels
+struct KpDev {
+  int K, R, T, ITW, N, X, G, GH, E, D;  // keys, resources, types, words, templates, classes, groups, hostname groups, nodes, offering sets
+  int n_reqsets, n_taintsets, n_tolsets;
+  int has_bounds;
+  int hostname_key;  // index in the ORIGINAL key numbering (slots use compact ids without hostname)
+  // key universe
+  const uint8_t* key_wellknown;   // [K]
+  const uint64_t* key_univ;       // [K] mask of valid value bits
+  const int64_t* val_int;         // [K*64]
+  const uint64_t* val_isint;      // [K] bitmask
+  // requirement sets as slot rows
+  const uint8_t* rs_flags;        // [n_reqsets*K]
+  const uint64_t* rs_mask;        // [n_reqsets*K]
+  const int64_t* rs_gte;          // [n_reqsets*K] (has_bounds)
+  const int64_t* rs_lte;
+  const uint32_t* rs_keys;        // [n_reqsets] bitmask of present keys
+  // taints
+  const uint8_t* tol_ok;          // [(n_tolsets+1) * n_taintsets], row tolset+1 (row 0 == no tolerations)
+  // instance types (bit-sliced)
+  const uint64_t* itv;            // [K*64*ITW] types whose In-set on key k contains value v
+  const uint64_t* it_nokey;       // [K*ITW] types that do not define key k
+  const uint64_t* it_dne;         // [K*ITW] types whose slot on k is the empty concrete set
+  const uint64_t* it_nonempty;    // [K*ITW] types with a non-empty In-set on k
+  const uint64_t* it_valid;       // [ITW] types without a negative allocatable entry
+  const int64_t* ge_vals;         // [R*T] ascending distinct allocatable values per resource
+  const int32_t* ge_n;            // [R] number of distinct values
+  const uint64_t* ge_bits;        // [R*T*ITW] ge_bits[r][j] = types with alloc[r] >= ge_vals[r][j]
+  const int32_t* offset_rs;       // [D] distinct offering requirement sets
+  const uint64_t* offset_bits;    // [D*ITW] types with an AVAILABLE offering of that set
+  const int64_t* it_capacity;     // [T*R] (limits)
+  // templates
+  const int32_t* tmpl_rs;         // [N]
+  const int32_t* tmpl_taintset;   // [N]
+  const uint64_t* tmpl_its_raw;   // [N*ITW] instanceTypes[np] before the prefilter
+  uint64_t* tmpl_its;             // [N*ITW] after the NewScheduler prefilter (scheduler.go:147)
+  const int64_t* tmpl_daemon;     // [N*R]
+  int64_t* tmpl_remaining;        // [N*R] remainingResources (limits)
+  const uint32_t* tmpl_limit_present;  // [N]
+  int nodes_res;
+  // classes
+  const int64_t* cls_req;         // [X*R]
+  const int32_t* cls_rs;          // [X]
+  const int32_t* cls_strict_rs;   // [X]
+  const int32_t* cls_tolset;      // [X]
+  const int32_t* cls_rv;          // [X] id of the distinct request vector
+  int n_rv;
+  const int32_t* cls_match_off;   // [X+1] groups that constrain the class (owned + inverse selecting it); bit 30 = selects(pod)
+  const int32_t* cls_match;       //
+  const int32_t* cls_rec_off;     // [X+1] groups that may count the class on Record (select it / inverse owned)
+  const int32_t* cls_rec;
+  // topology groups
+  const KpGroup* groups;          // [G]
+  const int32_t* filter_rs;       // filter alternatives
+  int32_t* dom_cnt;               // [sum over non-hostname groups of 64]
+  uint64_t* dom_reg;              // [G] registered-domain mask (t.domains keys)
+  uint64_t* dom_pop;              // [G] domains with count > 0 (complement of t.emptyDomains within dom_reg)
+  int32_t* g_ndomains;            // [G] hostname groups: len(t.domains)
+  int32_t* g_nempty;              // [G] hostname groups: len(t.emptyDomains)
+  int32_t* host_cnt;              // [GH * H] per hostname group x host (existing nodes then claims)
+  int H;                          // E + claim capacity
+  // existing nodes (dynamic)
+  const int32_t* node_taintset;   // [E]
+  const uint8_t* node_flags;      // [E] KP_NODE_*
+  int64_t* node_rem;              // [E*R]
+  uint32_t* node_rem_present;     // [E]
+  uint8_t* node_sflags;           // [E*K]
+  uint64_t* node_smask;           // [E*K]
+  int64_t* node_sgte;             // [E*K]
+  int64_t* node_slte;
+  int32_t* node_npods;            // [E]
+  // claims (dynamic)
+  int Cmax;
+  int32_t* c_tmpl;                // [Cmax]
+  int32_t* c_npods;
+  int64_t* c_req;                 // [Cmax*R]
+  uint8_t* c_sflags;              // [Cmax*K]
+  uint64_t* c_smask;
+  int64_t* c_sgte;
+  int64_t* c_slte;
+  uint64_t* c_its;                // [Cmax*ITW]
+  int32_t* order;                 // [Cmax] s.newNodeClaims as claim ids
+  int32_t* cnt_at;                // [Cmax] len(Pods) by position
+  uint32_t* rdead;                // [n_rv * ceil(Cmax/32)] claim can never again fit this request vector
+  // pods
+  int64_t P;
+  const int32_t* pod_class;       // [P]
+  int32_t* queue;                 // [P+1] circular queue of pod rows, initially byCPUAndMemoryDescending
+  int32_t* last_len;              // [P]
+  int32_t* pod_target;            // [P]
+  uint8_t* pod_error;             // [P]
+  // scalars out
+  int32_t* n_claims;              // [1]
+  int64_t* counters;              // [8] existing evals, inflight evals, template evals, commits, slow sorts, ...
+  int32_t* status;                // [1] 0 ok, 4 capacity
+  int stable_order;
+};

@@ -1,0 +1,533 @@
+"""Interning of the object model (model.py) into the flat ``kp_problem`` of include/karpsolve.h.
+
+This is the caller-side step the cgo shim performs inside ``Provisioner.NewScheduler`` in the reference
+(pkg/controllers/provisioning/provisioner.go:238-307): strings -> integer ids, corev1 objects -> CSR tables.
+It applies only representation changes that the reference's own constructors define:
+
+* ``NewRequirementWithFlexibility`` operator canonicalisation (pkg/scheduling/requirement.go:48-102) and label
+  normalisation (pkg/apis/v1/labels.go:117-123);
+* ``NewPodRequirements`` / ``NewStrictPodRequirements`` (pkg/scheduling/requirements.go:90-110): node selector +
+  first required node-affinity term (preferred terms are a "next" row);
+* ``MakeTopologyNodeFilter`` requirement alternatives (topologynodefilter.go:38-64);
+* ``OrderByWeight`` (pkg/utils/nodepool/nodepool.go:161-171) and ``sortExistingNodes`` (scheduler.go:738-751);
+* key pruning: label keys that only instance types / node labels mention can never take part in a decision
+  (``Intersects`` looks at shared keys only, requirements.go:237-274), so they are dropped from the universe.
+
+Label values are interned in lexicographic order per key, which makes "ascending id" the canonical replacement for
+Go's random map iteration order.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi
+from .model import (HOSTNAME_LABEL, NODEPOOL_LABEL, NORMALIZED_LABELS, WELL_KNOWN_LABELS, InstanceType, LabelSelector,
+                    NodePool, NodeSelectorRequirement, Pod, StateNode, Taint, Toleration, quantity_units)
+
+EFFECTS = {"": 0, "NoSchedule": 1, "PreferNoSchedule": 2, "NoExecute": 3}
+TOL_OPS = {"": 0, "Equal": 0, "Exists": 1, "Lt": 2, "Gt": 3}
+SEL_OPS = {"In": 0, "NotIn": 1, "Exists": 2, "DoesNotExist": 3}
+INT64_MAX = (1 << 63) - 1
+
+
+def go_atoi(s: str) -> Optional[int]:
+    """strconv.Atoi: optional sign + decimal digits, must fit in int64."""
+    t = s[1:] if s[:1] in "+-" else s
+    if not t or not t.isdigit() or not t.isascii():
+        return None
+    v = int(s)
+    if v < -(1 << 63) or v > INT64_MAX:
+        return None
+    return v
+
+
+def canonical_requirement(r: NodeSelectorRequirement):
+    """NewRequirementWithFlexibility (requirement.go:48-102) -> (key, complement, values, gte, lte, min_values)."""
+    key = NORMALIZED_LABELS.get(r.key, r.key)
+    op = r.operator
+    mv = r.min_values
+    if op == "In":
+        return (key, False, tuple(sorted(set(r.values))), None, None, mv)
+    complement = op not in ("In", "DoesNotExist")
+    values = tuple(sorted(set(r.values))) if op == "NotIn" else ()
+    gte = lte = None
+    if op == "Gt":
+        v = int(r.values[0])
+        if v == INT64_MAX:
+            return (key, False, (), None, None, None)  # Gt MaxInt matches nothing: DoesNotExist
+        gte = v + 1
+    elif op == "Lt":
+        lte = int(r.values[0]) - 1
+    elif op == "Gte":
+        gte = int(r.values[0])
+    elif op == "Lte":
+        lte = int(r.values[0])
+    return (key, complement, values, gte, lte, mv)
+
+
+def label_requirements(labels: Dict[str, str]):
+    """NewLabelRequirements (requirements.go:64-70)."""
+    return [canonical_requirement(NodeSelectorRequirement(k, "In", (v,))) for k, v in sorted(labels.items())]
+
+
+def pod_requirements(pod: Pod):
+    """NewStrictPodRequirements == NewPodRequirements when no preferred node affinity exists (requirements.go:90-110)."""
+    reqs = label_requirements(pod.node_selector)
+    if pod.node_affinity_required:
+        reqs += [canonical_requirement(r) for r in pod.node_affinity_required[0]]
+    return reqs
+
+
+def pod_filter_requirements(pod: Pod):
+    """MakeTopologyNodeFilter (topologynodefilter.go:38-64): one alternative per required node-affinity term."""
+    base = label_requirements(pod.node_selector)
+    if not pod.node_affinity_required:
+        return [base]
+    return [base + [canonical_requirement(r) for r in term] for term in pod.node_affinity_required]
+
+
+class _Csr:
+    def __init__(self):
+        self.off = [0]
+        self.items: List[int] = []
+
+    def add(self, row: Iterable[int]) -> int:
+        self.items.extend(row)
+        self.off.append(len(self.items))
+        return len(self.off) - 2
+
+
+class _Dedup:
+    def __init__(self):
+        self.ids: Dict[object, int] = {}
+        self.rows: List[object] = []
+
+    def get(self, key) -> int:
+        i = self.ids.get(key)
+        if i is None:
+            i = len(self.rows)
+            self.ids[key] = i
+            self.rows.append(key)
+        return i
+
+
+class ProblemBuilder:
+    """Two-phase builder: collect symbolic rows, then `build()` interns strings and emits numpy arrays."""
+
+    def __init__(self, resources: Sequence[str] = ("cpu", "memory", "pods", "ephemeral-storage")):
+        self.resources = list(resources)
+        self.reqsets = _Dedup()      # tuple of canonical requirement tuples
+        self.taintsets = _Dedup()    # tuple of Taint
+        self.tolsets = _Dedup()      # tuple of Toleration
+        self.labelsets = _Dedup()    # tuple of (k, v)
+        self.selectors = _Dedup()    # LabelSelector
+        self.nssets = _Dedup()       # tuple of namespace strings
+        self.namespaces = _Dedup()
+        self.classes = _Dedup()      # class key -> id
+        self.class_rows: List[dict] = []
+        self.its: List[dict] = []
+        self.it_index: Dict[str, int] = {}
+        self.templates: List[dict] = []
+        self.nodes: List[dict] = []
+        self.pods: List[Tuple[int, int, int]] = []  # (class, creation, uid)
+        self.running: List[Tuple[int, int]] = []
+        self.extra_keys = set()
+        self.claim_order_mode = 0
+        self.pod_arrays = None
+
+    # ---- resources ----
+    def res_index(self, name: str) -> int:
+        if name not in self.resources:
+            self.resources.append(name)
+        return self.resources.index(name)
+
+    def res_vector(self, d: Dict[str, object]):
+        pairs = [(self.res_index(k), quantity_units(k, v)) for k, v in d.items()]
+        return pairs
+
+    # ---- symbolic rows ----
+    def reqset(self, reqs) -> int:
+        return self.reqsets.get(tuple(reqs))
+
+    def taintset(self, taints: Sequence[Taint]) -> int:
+        return self.taintsets.get(tuple(taints))
+
+    def tolset(self, tols: Sequence[Toleration]) -> int:
+        return self.tolsets.get(tuple(tols))
+
+    def add_instance_type(self, it: InstanceType) -> int:
+        row = dict(
+            name=it.name, reqset=self.reqset([canonical_requirement(r) for r in it.requirements]),
+            capacity=self.res_vector(it.capacity), overhead=self.res_vector(it.overhead),
+            offerings=[(self.reqset([canonical_requirement(r) for r in o.requirements]), float(o.price),
+                        bool(o.available)) for o in it.offerings])
+        self.it_index.setdefault(it.name, len(self.its))  # names may repeat (the AWS catalog lists linux + windows rows)
+        self.its.append(row)
+        return len(self.its) - 1
+
+    def add_nodepool(self, np_: NodePool, instance_types: Sequence[str], daemon: Optional[Dict[str, object]] = None):
+        """NewNodeClaimTemplate (nodeclaimtemplate.go:57-79): requirements + labels + nodepool/nodeclass labels."""
+        reqs = [canonical_requirement(r) for r in np_.requirements]
+        labels = dict(np_.labels)
+        labels[NODEPOOL_LABEL] = np_.name
+        labels["karpenter.kwok.sh/kwoknodeclass"] = np_.node_class
+        reqs += label_requirements(labels)
+        self.templates.append(dict(
+            name=np_.name, weight=np_.weight, reqset=self.reqset(reqs), taintset=self.taintset(np_.taints),
+            its=[n if isinstance(n, int) else self.it_index[n] for n in instance_types],
+            daemon=self.res_vector(daemon or {}),
+            limits=self.res_vector(np_.limits)))
+
+    def pod_class(self, pod: Pod) -> int:
+        tscs = []
+        for t in pod.topology_spread_constraints:
+            if t.when_unsatisfiable != "DoNotSchedule":
+                continue  # ScheduleAnyway is a preference: relaxation is a "next" row
+            sel = t.label_selector
+            if sel is not None and t.match_label_keys:  # topology.go:434-442
+                extra = tuple((k, "In", (pod.labels[k],)) for k in t.match_label_keys if k in pod.labels)
+                sel = LabelSelector(sel.match_labels, sel.match_expressions + extra)
+            tscs.append((0, t.topology_key, sel, (pod.namespace,), t.max_skew,
+                         -1 if t.min_domains is None else t.min_domains, t.node_taints_policy == "Honor",
+                         t.node_affinity_policy != "Ignore"))
+        for kind, terms in ((1, pod.pod_affinity), (2, pod.pod_anti_affinity)):
+            for t in terms:
+                ns = tuple(t.namespaces) if t.namespaces else (pod.namespace,)  # topology.go:503-526
+                tscs.append((kind, t.topology_key, t.label_selector, ns, 0, -1, False, False))
+        reqs = pod_requirements(pod)
+        key = (tuple(sorted((k, quantity_units(k, v)) for k, v in pod.requests.items())), tuple(reqs),
+               tuple(pod.tolerations), pod.namespace, tuple(sorted(pod.labels.items())), tuple(tscs),
+               tuple(tuple(a) for a in pod_filter_requirements(pod)) if tscs else ())
+        n_before = len(self.classes.rows)
+        cid = self.classes.get(key)
+        if cid == n_before:
+            requests = dict(pod.requests)
+            vec = self.res_vector(requests)
+            vec.append((self.res_index("pods"), 1))  # RequestsForPods adds pods: 1 (resources.go:37)
+            row = dict(requests=vec, reqset=self.reqset(reqs), strict=self.reqset(reqs),
+                       tolset=self.tolset(pod.tolerations), namespace=self.namespaces.get(pod.namespace),
+                       labelset=self.labelsets.get(tuple(sorted(pod.labels.items()))),
+                       filters=[self.reqset(a) for a in pod_filter_requirements(pod)] if tscs else [],
+                       tscs=[])
+            for (kind, tkey, sel, ns, skew, mind, tp, ap) in tscs:
+                for n in ns:
+                    self.namespaces.get(n)
+                row["tscs"].append(dict(type=kind, key=NORMALIZED_LABELS.get(tkey, tkey),
+                                        selector=-1 if sel is None else self.selectors.get(sel),
+                                        nsset=self.nssets.get(tuple(ns)), max_skew=skew, min_domains=mind,
+                                        taint_policy=int(tp), affinity_policy=int(ap)))
+                self.extra_keys.add(NORMALIZED_LABELS.get(tkey, tkey))
+            self.class_rows.append(row)
+        return cid
+
+    def add_pod(self, pod: Pod) -> int:
+        self.pods.append((self.pod_class(pod), pod.creation_timestamp, pod.uid))
+        return len(self.pods) - 1
+
+    def set_pod_arrays(self, pod_class, creation, uid_hi, uid_lo):
+        """Bulk path for the big synthetic configs: numpy arrays of per-pod rows (classes registered via pod_class())."""
+        self.pod_arrays = (np.asarray(pod_class, np.int32), np.asarray(creation, np.int64),
+                           np.asarray(uid_hi, np.uint64), np.asarray(uid_lo, np.uint64))
+
+    def add_running(self, pod: Pod, node: int):
+        """A pod already bound to cluster node `node` (index returned by add_node): only counted by the topology."""
+        self.running.append((self.pod_class(pod), node))
+
+    def add_node(self, n: StateNode) -> int:
+        template_index = {t["name"]: i for i, t in enumerate(self.templates)}
+        labels = {k: v for k, v in n.labels.items() if k != HOSTNAME_LABEL}
+        row = dict(name=n.name, hostname=n.labels.get(HOSTNAME_LABEL, n.name), reqset=self.reqset(label_requirements(labels)),
+                   taintset=self.taintset(n.taints), available=self.res_vector(n.available),
+                   capacity=self.res_vector(n.capacity),
+                   flags=(1 if n.schedulable else 0) | (2 if n.initialized else 0) | (4 if n.managed else 0),
+                   template=template_index.get(n.nodepool, -1) if n.nodepool else -1,
+                   instance_type=n.instance_type, labels=labels)
+        self.nodes.append(row)
+        return len(self.nodes) - 1
+
+    # ---- build ----
+    def build(self) -> "EncodedProblem":
+        R = len(self.resources)
+        # active keys
+        active = set(self.extra_keys) | {HOSTNAME_LABEL}
+        off_reqsets = {o[0] for it in self.its for o in it["offerings"]}
+        seeds = {t["reqset"] for t in self.templates} | off_reqsets
+        for c in self.class_rows:
+            seeds |= {c["reqset"], c["strict"], *c["filters"]}
+        for s in seeds:
+            for r in self.reqsets.rows[s]:
+                active.add(r[0])
+        keys = sorted(active)
+        key_id = {k: i for i, k in enumerate(keys)}
+        values: Dict[str, set] = {k: set() for k in keys}
+        for rows in self.reqsets.rows:
+            for r in rows:
+                if r[0] in values:
+                    values[r[0]].update(r[2])
+        for n in self.nodes:
+            values[HOSTNAME_LABEL].add(n["hostname"])
+        value_id = {k: {v: i for i, v in enumerate(sorted(vs))} for k, vs in values.items()}
+        key_value_off = [0]
+        value_int, value_is_int = [], []
+        for k in keys:
+            for v in sorted(values[k]):
+                a = go_atoi(v)
+                value_int.append(a if a is not None else 0)
+                value_is_int.append(0 if a is None else 1)
+            key_value_off.append(len(value_int))
+        P = _abi.Problem()
+        P.set("n_keys", len(keys))
+        P.set("key_flags", [(1 if k in WELL_KNOWN_LABELS else 0) | (2 if k == HOSTNAME_LABEL else 0) for k in keys])
+        P.set("key_value_off", key_value_off)
+        P.set("value_int", value_int)
+        P.set("value_is_int", value_is_int)
+        # requirement sets (pruned to active keys)
+        rs_off, rq_key, rq_flags, rq_gte, rq_lte, rq_min, rv_off, rvals = [0], [], [], [], [], [], [0], []
+        for rows in self.reqsets.rows:
+            for (k, comp, vals, gte, lte, mv) in rows:
+                if k not in key_id:
+                    continue
+                rq_key.append(key_id[k])
+                rq_flags.append((1 if comp else 0) | (2 if gte is not None else 0) | (4 if lte is not None else 0) |
+                                (8 if mv is not None else 0))
+                rq_gte.append(gte or 0)
+                rq_lte.append(lte or 0)
+                rq_min.append(mv or 0)
+                rvals.extend(value_id[k][v] for v in vals)
+                rv_off.append(len(rvals))
+            rs_off.append(len(rq_key))
+        P.set("n_reqsets", len(self.reqsets.rows))
+        P.set("reqset_off", rs_off)
+        P.set("n_reqs", len(rq_key))
+        for name, arr in (("req_key", rq_key), ("req_flags", rq_flags), ("req_gte", rq_gte), ("req_lte", rq_lte),
+                          ("req_min_values", rq_min), ("req_val_off", rv_off), ("req_vals", rvals)):
+            P.set(name, arr)
+        # resources
+        P.set("n_resources", R)
+        flags = []
+        for r in self.resources:
+            flags.append((1 if r == "cpu" else 0) | (2 if r == "memory" else 0) | (4 if r.startswith("hugepages-") else 0) |
+                         (8 if r == "nodes" else 0))
+        P.set("res_flags", flags)
+
+        def dense(pairs_list):
+            m = np.zeros((len(pairs_list), R), np.int64)
+            present = np.zeros(len(pairs_list), np.uint32)
+            for i, pairs in enumerate(pairs_list):
+                for r, v in pairs:
+                    m[i, r] += v
+                    present[i] |= np.uint32(1 << r)
+            return m, present
+
+        # taints / tolerations
+        tt = _Dedup()
+        tt.get("")
+        taints = _Dedup()
+        ts_csr = _Csr()
+        for rows in self.taintsets.rows:
+            ts_csr.add(taints.get((tt.get(t.key), tt.get(t.value), EFFECTS[t.effect])) for t in rows)
+        tols = _Dedup()
+        tl_csr = _Csr()
+        for rows in self.tolsets.rows:
+            tl_csr.add(tols.get((tt.get(t.key), TOL_OPS[t.operator], tt.get(t.value), EFFECTS[t.effect])) for t in rows)
+        tti = [go_atoi(s) for s in tt.rows]
+        P.set("n_tt_strings", len(tt.rows))
+        P.set("tt_int", [a or 0 for a in tti])
+        P.set("tt_is_int", [0 if a is None else 1 for a in tti])
+        P.set("n_taints", len(taints.rows))
+        P.set("taint_key", [t[0] for t in taints.rows])
+        P.set("taint_value", [t[1] for t in taints.rows])
+        P.set("taint_effect", [t[2] for t in taints.rows])
+        P.set("n_taintsets", len(self.taintsets.rows))
+        P.set("taintset_off", ts_csr.off)
+        P.set("taintset_ids", ts_csr.items)
+        P.set("n_tolerations", len(tols.rows))
+        P.set("tol_key", [t[0] for t in tols.rows])
+        P.set("tol_op", [t[1] for t in tols.rows])
+        P.set("tol_value", [t[2] for t in tols.rows])
+        P.set("tol_effect", [t[3] for t in tols.rows])
+        P.set("n_tolsets", len(self.tolsets.rows))
+        P.set("tolset_off", tl_csr.off)
+        P.set("tolset_ids", tl_csr.items)
+        # instance types
+        cap, capp = dense([it["capacity"] for it in self.its])
+        ovh, _ = dense([it["overhead"] for it in self.its])
+        P.set("n_its", len(self.its))
+        P.set("it_reqset", [it["reqset"] for it in self.its])
+        P.set("it_capacity", cap)
+        P.set("it_cap_present", capp)
+        P.set("it_overhead", ovh)
+        oo, orq, opr, oav = [0], [], [], []
+        for it in self.its:
+            for (rs, price, av) in it["offerings"]:
+                orq.append(rs)
+                opr.append(price)
+                oav.append(1 if av else 0)
+            oo.append(len(orq))
+        P.set("it_off_off", oo)
+        P.set("off_reqset", orq)
+        P.set("off_price", opr)
+        P.set("off_available", oav)
+        # templates in OrderByWeight order: weight desc, name desc
+        order = sorted(range(len(self.templates)), key=lambda i: (-self.templates[i]["weight"],
+                                                                     _neg_str(self.templates[i]["name"])))
+        tmpls = [self.templates[i] for i in order]
+        tmpl_index = {t["name"]: i for i, t in enumerate(tmpls)}
+        P.set("n_templates", len(tmpls))
+        P.set("tmpl_reqset", [t["reqset"] for t in tmpls])
+        P.set("tmpl_taintset", [t["taintset"] for t in tmpls])
+        tio, tits = [0], []
+        for t in tmpls:
+            tits.extend(t["its"])
+            tio.append(len(tits))
+        P.set("tmpl_it_off", tio)
+        P.set("tmpl_its", tits)
+        dm, _ = dense([t["daemon"] for t in tmpls])
+        lm, lp = dense([t["limits"] for t in tmpls])
+        P.set("tmpl_daemon", dm)
+        P.set("tmpl_limits", lm)
+        P.set("tmpl_limit_present", lp)
+        # labels / selectors / namespaces
+        lab = _Dedup()
+        ls_off, lk, lv = [0], [], []
+        for rows in self.labelsets.rows:
+            for (k, v) in rows:
+                lk.append(lab.get(("k", k)))
+                lv.append(lab.get(("v", v)))
+            ls_off.append(len(lk))
+        P.set("n_labelsets", len(self.labelsets.rows))
+        P.set("labelset_off", ls_off)
+        P.set("label_key", lk)
+        P.set("label_val", lv)
+        so, sk, sop, svo, sv = [0], [], [], [0], []
+        for sel in self.selectors.rows:
+            exprs = [(k, "In", (v,)) for k, v in sel.match_labels] + list(sel.match_expressions)
+            for (k, op, vs) in exprs:
+                sk.append(lab.get(("k", k)))
+                sop.append(SEL_OPS[op])
+                sv.extend(lab.get(("v", v)) for v in vs)
+                svo.append(len(sv))
+            so.append(len(sk))
+        P.set("n_selectors", len(self.selectors.rows))
+        P.set("selector_off", so)
+        P.set("selx_key", sk)
+        P.set("selx_op", sop)
+        P.set("selx_val_off", svo)
+        P.set("selx_vals", sv)
+        ns_csr = _Csr()
+        for rows in self.nssets.rows:
+            ns_csr.add(self.namespaces.get(n) for n in rows)
+        P.set("n_nssets", len(self.nssets.rows))
+        P.set("nsset_off", ns_csr.off)
+        P.set("nsset_ids", ns_csr.items)
+        # classes
+        creq, _ = dense([c["requests"] for c in self.class_rows])
+        P.set("n_classes", len(self.class_rows))
+        P.set("class_requests", creq)
+        P.set("class_reqset", [c["reqset"] for c in self.class_rows])
+        P.set("class_strict_reqset", [c["strict"] for c in self.class_rows])
+        P.set("class_tolset", [c["tolset"] for c in self.class_rows])
+        P.set("class_namespace", [c["namespace"] for c in self.class_rows])
+        P.set("class_labelset", [c["labelset"] for c in self.class_rows])
+        fo, fr, to = [0], [], [0]
+        cols = {k: [] for k in ("type", "key", "selector", "nsset", "max_skew", "min_domains", "taint_policy",
+                                "affinity_policy")}
+        for c in self.class_rows:
+            fr.extend(c["filters"])
+            fo.append(len(fr))
+            for t in c["tscs"]:
+                for k in cols:
+                    cols[k].append(key_id[t["key"]] if k == "key" else t[k])
+            to.append(len(cols["type"]))
+        P.set("class_filter_off", fo)
+        P.set("class_filter_reqsets", fr)
+        P.set("class_tsc_off", to)
+        for k, arr in cols.items():
+            P.set("tsc_" + k, arr)
+        # pods
+        if self.pod_arrays is not None:
+            pc, cr, hi, lo = self.pod_arrays
+        else:
+            pc = np.array([p[0] for p in self.pods], np.int32)
+            cr = np.array([p[1] for p in self.pods], np.int64)
+            hi = np.array([(p[2] >> 64) & 0xFFFFFFFFFFFFFFFF for p in self.pods], np.uint64)
+            lo = np.array([p[2] & 0xFFFFFFFFFFFFFFFF for p in self.pods], np.uint64)
+        P.set("n_pods", len(pc))
+        P.set("pod_class", pc)
+        P.set("pod_creation", cr)
+        P.set("pod_uid_hi", hi)
+        P.set("pod_uid_lo", lo)
+        # nodes: sortExistingNodes == initialized first, then name (stable)
+        norder = sorted(range(len(self.nodes)), key=lambda i: (0 if self.nodes[i]["flags"] & 2 else 1,
+                                                                 self.nodes[i]["name"]))
+        nodes = [self.nodes[i] for i in norder]
+        node_pos = {old: new for new, old in enumerate(norder)}
+        av, avp = dense([n["available"] for n in nodes])
+        cp, _ = dense([n["capacity"] for n in nodes])
+        P.set("n_nodes", len(nodes))
+        P.set("node_flags", [n["flags"] for n in nodes])
+        P.set("node_reqset", [n["reqset"] for n in nodes])
+        P.set("node_hostname", [value_id[HOSTNAME_LABEL][n["hostname"]] for n in nodes])
+        P.set("node_taintset", [n["taintset"] for n in nodes])
+        P.set("node_available", av)
+        P.set("node_avail_present", avp)
+        P.set("node_capacity", cp)
+        P.set("node_template", [tmpl_index.get(self.templates[n["template"]]["name"], -1) if n["template"] >= 0 else -1
+                                for n in nodes])
+        P.set("n_running", len(self.running))
+        P.set("run_class", [r[0] for r in self.running])
+        P.set("run_node", [node_pos[r[1]] for r in self.running])
+        P.set("min_values_best_effort", 0)
+        P.set("claim_order_mode", self.claim_order_mode)
+        return EncodedProblem(P, keys, {k: sorted(values[k]) for k in keys}, list(self.resources),
+                              [it["name"] for it in self.its], [t["name"] for t in tmpls], [n["name"] for n in nodes],
+                              node_pos, nodes)
+
+
+def _neg_str(s: str):
+    # descending string order as a sort key
+    return tuple(-ord(c) for c in s) + (1,)
+
+
+class EncodedProblem:
+    """A kp_problem plus the string tables needed to decode results."""
+
+    def __init__(self, problem, keys, values, resources, it_names, tmpl_names, node_names, node_pos, node_rows):
+        self.problem = problem
+        self.keys = keys
+        self.values = values
+        self.resources = resources
+        self.it_names = it_names
+        self.tmpl_names = tmpl_names
+        self.node_names = node_names
+        self.node_pos = node_pos
+        self.node_rows = node_rows
+
+    def key_id(self, key: str) -> int:
+        return self.keys.index(key) if key in self.keys else -1
+
+    def value_id(self, key: str, value: str) -> int:
+        vs = self.values.get(key, [])
+        return vs.index(value) if value in vs else -1
+
+    def decode_requirements(self, res: dict, claim: int) -> Dict[str, dict]:
+        out = {}
+        woff = 0
+        for k, key in enumerate(self.keys):
+            nv = len(self.values[key])
+            words = 0 if key == HOSTNAME_LABEL else (nv + 63) // 64
+            f = int(res["claim_req_flags"][claim, k])
+            if f & _abi.KP_SLOT_PRESENT:
+                vals = [self.values[key][v] for v in range(nv)
+                        if int(res["claim_req_mask"][claim, woff + (v >> 6)]) >> (v & 63) & 1]
+                out[key] = dict(complement=bool(f & 1), values=vals,
+                                gte=int(res["claim_req_gte"][claim, k]) if f & 2 else None,
+                                lte=int(res["claim_req_lte"][claim, k]) if f & 4 else None)
+            woff += words
+        return out
+
+    def decode_its(self, res: dict, claim: int) -> List[str]:
+        row = res["claim_its"][claim]
+        return [n for i, n in enumerate(self.it_names) if int(row[i >> 6]) >> (i & 63) & 1]

@@ -1,0 +1,209 @@
+"""Host-side mirror of the reference's object model for the provisioning hot path.
+
+These are plain data holders named after the Go types the reference's callers hand to
+``scheduling.NewScheduler`` / ``Scheduler.Solve`` (pkg/controllers/provisioning/scheduling/scheduler.go:116-129,381)
+and the plugin types of pkg/cloudprovider/types.go:122-138,372-379.  They carry strings; `encode.py` interns them into
+the flat ``kp_problem`` of include/karpsolve.h.  No scheduling logic lives here.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from fractions import Fraction
+from typing import Dict, List, Optional, Sequence, Tuple
+
+# pkg/apis/v1/labels.go:69-78,117-123 and k8s.io/api well-known label names
+NODEPOOL_LABEL = "karpenter.sh/nodepool"
+CAPACITY_TYPE_LABEL = "karpenter.sh/capacity-type"
+ZONE_LABEL = "topology.kubernetes.io/zone"
+REGION_LABEL = "topology.kubernetes.io/region"
+INSTANCE_TYPE_LABEL = "node.kubernetes.io/instance-type"
+ARCH_LABEL = "kubernetes.io/arch"
+OS_LABEL = "kubernetes.io/os"
+WINDOWS_BUILD_LABEL = "node.kubernetes.io/windows-build"
+HOSTNAME_LABEL = "kubernetes.io/hostname"
+
+WELL_KNOWN_LABELS = {
+    NODEPOOL_LABEL, ZONE_LABEL, REGION_LABEL, INSTANCE_TYPE_LABEL, ARCH_LABEL, OS_LABEL, CAPACITY_TYPE_LABEL,
+    WINDOWS_BUILD_LABEL,
+}
+NORMALIZED_LABELS = {
+    "failure-domain.beta.kubernetes.io/zone": ZONE_LABEL,
+    "beta.kubernetes.io/arch": ARCH_LABEL,
+    "beta.kubernetes.io/os": OS_LABEL,
+    "beta.kubernetes.io/instance-type": INSTANCE_TYPE_LABEL,
+    "failure-domain.beta.kubernetes.io/region": REGION_LABEL,
+}
+
+CAPACITY_TYPE_SPOT = "spot"
+CAPACITY_TYPE_ON_DEMAND = "on-demand"
+CAPACITY_TYPE_RESERVED = "reserved"
+
+_SUFFIX = {
+    "n": Fraction(1, 10**9), "u": Fraction(1, 10**6), "m": Fraction(1, 1000), "": Fraction(1),
+    "k": Fraction(10**3), "M": Fraction(10**6), "G": Fraction(10**9), "T": Fraction(10**12),
+    "P": Fraction(10**15), "E": Fraction(10**18),
+    "Ki": Fraction(2**10), "Mi": Fraction(2**20), "Gi": Fraction(2**30), "Ti": Fraction(2**40),
+    "Pi": Fraction(2**50), "Ei": Fraction(2**60),
+}
+
+
+def parse_quantity(q) -> Fraction:
+    """resource.MustParse (k8s.io/apimachinery/pkg/api/resource) for the decimal/binary-SI forms the reference uses."""
+    if isinstance(q, (int, Fraction)):
+        return Fraction(q)
+    s = str(q).strip()
+    for suf in sorted(_SUFFIX, key=len, reverse=True):
+        if suf and s.endswith(suf):
+            return Fraction(s[: -len(suf)]) * _SUFFIX[suf]
+    if "e" in s or "E" in s:
+        mant, exp = s.replace("E", "e").split("e")
+        return Fraction(mant) * Fraction(10) ** int(exp)
+    return Fraction(s)
+
+
+def quantity_units(name: str, q) -> int:
+    """Exact integer in the resource's unit: milli for cpu, base units (bytes / count) otherwise."""
+    f = parse_quantity(q)
+    if name == "cpu":
+        f = f * 1000
+    if f.denominator != 1:
+        raise ValueError(f"quantity {q!r} of {name} is not integral in the solver's unit")
+    return int(f)
+
+
+@dataclass(frozen=True)
+class NodeSelectorRequirement:
+    """corev1.NodeSelectorRequirement / v1.NodeSelectorRequirementWithMinValues."""
+    key: str
+    operator: str  # In NotIn Exists DoesNotExist Gt Lt Gte Lte
+    values: Tuple[str, ...] = ()
+    min_values: Optional[int] = None
+
+    def __post_init__(self):
+        object.__setattr__(self, "values", tuple(self.values))
+
+
+@dataclass(frozen=True)
+class Taint:
+    key: str
+    value: str = ""
+    effect: str = "NoSchedule"
+
+
+@dataclass(frozen=True)
+class Toleration:
+    key: str = ""
+    operator: str = "Equal"  # "" == Equal
+    value: str = ""
+    effect: str = ""
+
+
+@dataclass(frozen=True)
+class LabelSelector:
+    match_labels: Tuple[Tuple[str, str], ...] = ()
+    match_expressions: Tuple[Tuple[str, str, Tuple[str, ...]], ...] = ()  # (key, In|NotIn|Exists|DoesNotExist, values)
+
+    @staticmethod
+    def of(match_labels: Optional[Dict[str, str]] = None, match_expressions=()):
+        ml = tuple(sorted((match_labels or {}).items()))
+        me = tuple((k, op, tuple(vs)) for k, op, vs in match_expressions)
+        return LabelSelector(ml, me)
+
+
+@dataclass(frozen=True)
+class TopologySpreadConstraint:
+    max_skew: int
+    topology_key: str
+    label_selector: Optional[LabelSelector]
+    when_unsatisfiable: str = "DoNotSchedule"
+    min_domains: Optional[int] = None
+    node_taints_policy: Optional[str] = None    # Honor | Ignore (default Ignore)
+    node_affinity_policy: Optional[str] = None  # Honor | Ignore (default Honor)
+    match_label_keys: Tuple[str, ...] = ()
+
+
+@dataclass(frozen=True)
+class PodAffinityTerm:
+    label_selector: Optional[LabelSelector]
+    topology_key: str
+    namespaces: Tuple[str, ...] = ()
+
+
+@dataclass
+class Pod:
+    name: str = ""
+    namespace: str = "default"
+    uid: int = 0  # 128-bit integer; ordered like the canonical UUID string
+    labels: Dict[str, str] = field(default_factory=dict)
+    requests: Dict[str, object] = field(default_factory=dict)  # resource name -> quantity (str|int)
+    node_selector: Dict[str, str] = field(default_factory=dict)
+    node_affinity_required: List[List[NodeSelectorRequirement]] = field(default_factory=list)  # OR of terms
+    tolerations: List[Toleration] = field(default_factory=list)
+    topology_spread_constraints: List[TopologySpreadConstraint] = field(default_factory=list)
+    pod_affinity: List[PodAffinityTerm] = field(default_factory=list)       # required terms
+    pod_anti_affinity: List[PodAffinityTerm] = field(default_factory=list)  # required terms
+    creation_timestamp: int = 0
+
+
+@dataclass
+class Offering:
+    requirements: List[NodeSelectorRequirement]
+    price: float
+    available: bool = True
+
+
+@dataclass
+class InstanceType:
+    name: str
+    requirements: List[NodeSelectorRequirement]
+    offerings: List[Offering]
+    capacity: Dict[str, object]
+    overhead: Dict[str, object] = field(default_factory=dict)  # Overhead.Total()
+
+
+@dataclass
+class NodePool:
+    name: str
+    weight: int = 0
+    requirements: List[NodeSelectorRequirement] = field(default_factory=list)
+    labels: Dict[str, str] = field(default_factory=dict)
+    taints: List[Taint] = field(default_factory=list)
+    limits: Dict[str, object] = field(default_factory=dict)
+    node_class: str = "default"
+
+
+@dataclass
+class StateNode:
+    """state.StateNode as read by NewExistingNode (existingnode.go:40-66) and the disruption Candidate (types.go:74-82)."""
+    name: str
+    labels: Dict[str, str] = field(default_factory=dict)
+    taints: List[Taint] = field(default_factory=list)
+    available: Dict[str, object] = field(default_factory=dict)  # Allocatable - pod requests (- remaining daemons)
+    capacity: Dict[str, object] = field(default_factory=dict)
+    initialized: bool = True
+    managed: bool = True
+    schedulable: bool = True
+    nodepool: Optional[str] = None
+    instance_type: Optional[str] = None
+    pods: List[Pod] = field(default_factory=list)          # reschedulable pods bound to the node (consolidation)
+    running_pods: List[Pod] = field(default_factory=list)  # other bound pods, only counted by the topology
+
+
+@dataclass
+class NodeClaimResult:
+    """scheduling.NodeClaim as callers read it (nodeclaim.go:40-60): template, pods, instance type options, requirements."""
+    nodepool: str
+    pods: List[Pod]
+    instance_type_options: List[str]
+    requirements: Dict[str, dict]
+    requests: Dict[str, int]
+    rank: int
+
+
+@dataclass
+class Results:
+    """scheduling.Results (scheduler.go:237-241)."""
+    new_node_claims: List[NodeClaimResult]
+    existing_nodes: Dict[str, List[Pod]]
+    pod_errors: Dict[int, str]  # id(pod) -> reason
+    raw: object = None

@@ -1,0 +1,282 @@
+"""Synthetic KWOK workloads C1..C5 of BASELINE.json / SURVEY.md section 8(d).
+
+Deterministic: every random draw comes from splitmix64 seeded with 42 (mirroring the reference benchmark's
+`rand.New(rand.NewSource(42))`, scheduling_benchmark_test.go:62) and the pod request mix is the reference's
+randomCPU / randomMemory (scheduling_benchmark_test.go:446-454).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+from . import kwok
+from .encode import EncodedProblem, ProblemBuilder
+from .model import (ARCH_LABEL, CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, NODEPOOL_LABEL, OS_LABEL, ZONE_LABEL, LabelSelector,
+                    NodePool, NodeSelectorRequirement, Pod, PodAffinityTerm, StateNode, Taint, Toleration,
+                    TopologySpreadConstraint)
+
+SEED = 42
+CPU_MILLI = [100, 250, 500, 1000, 1500]
+MEM_MI = [100, 256, 512, 1024, 2048, 4096]
+_G = np.uint64(0x9E3779B97F4A7C15)
+
+
+def splitmix64(seed: int, idx: np.ndarray) -> np.ndarray:
+    """splitmix64 output number `idx` (0-based) of the stream started at `seed`."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + (idx.astype(np.uint64) + np.uint64(1)) * _G
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def draws(n: int, width: int, seed: int = SEED) -> np.ndarray:
+    """[n, width] table of uint64 draws; row i uses stream positions i*width .. i*width+width-1."""
+    idx = np.arange(n * width, dtype=np.uint64)
+    return splitmix64(seed, idx).reshape(n, width)
+
+
+def default_nodepool(name="default", taints=(), zones=None, limits=None, weight=0) -> NodePool:
+    """test/pkg/environment/common/default_nodepool.yaml (os In [linux], capacity-type In [on-demand])."""
+    reqs = [NodeSelectorRequirement(OS_LABEL, "In", ("linux",)),
+            NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "In", ("on-demand",))]
+    if zones:
+        reqs.append(NodeSelectorRequirement(ZONE_LABEL, "In", tuple(zones)))
+    return NodePool(name=name, weight=weight, requirements=reqs, taints=list(taints), limits=dict(limits or {}))
+
+
+def _requests(ci: int, mi: int) -> Dict[str, str]:
+    return {"cpu": f"{CPU_MILLI[ci]}m", "memory": f"{MEM_MI[mi]}Mi"}
+
+
+def config_c1(n_pods=1000, n_its=50) -> EncodedProblem:
+    """C1: cpu/mem-only pods, first 50 generic KWOK types, one NodePool."""
+    b = ProblemBuilder()
+    its = kwok.generic_instance_types()[:n_its]
+    for it in its:
+        b.add_instance_type(it)
+    b.add_nodepool(default_nodepool(), list(range(len(its))))
+    d = draws(n_pods, 4)
+    ci, mi = (d[:, 0] % np.uint64(5)).astype(int), (d[:, 1] % np.uint64(6)).astype(int)
+    table = np.zeros((5, 6), np.int32)
+    for c in range(5):
+        for m in range(6):
+            table[c, m] = b.pod_class(Pod(requests=_requests(c, m)))
+    b.set_pod_arrays(table[ci, mi], np.zeros(n_pods, np.int64), d[:, 2], d[:, 3])
+    return b.build()
+
+
+def config_c2(n_pods=100_000, n_its=500, nodepool="default") -> EncodedProblem:
+    """C2: zone / arch node selectors + tolerations against a tainted NodePool, first 500 AWS-KWOK types."""
+    b = ProblemBuilder()
+    its = kwok.aws_instance_types(n_its)
+    for it in its:
+        b.add_instance_type(it)
+    taint = Taint("bench/dedicated", "true", "NoSchedule")
+    b.add_nodepool(default_nodepool(nodepool, taints=[taint]), list(range(len(its))))
+    cls, uid_hi, _ = _c2_pods(b, n_pods, None)
+    uid_lo = splitmix64(SEED + 2, np.arange(n_pods, dtype=np.uint64))
+    b.set_pod_arrays(cls, np.zeros(n_pods, np.int64), uid_hi, uid_lo)
+    return b.build()
+
+
+def _c2_pods(b: ProblemBuilder, n_pods: int, nodepool_pin, seed=SEED, pools=None):
+    zones = kwok.AWS_ZONES
+    archs = ["x86_64", "arm64"]
+    d = draws(n_pods, 8, seed)
+    ci, mi = (d[:, 0] % np.uint64(5)).astype(int), (d[:, 1] % np.uint64(6)).astype(int)
+    zsel = np.where(d[:, 2] % np.uint64(2) == 0, (d[:, 3] % np.uint64(4)).astype(int), -1)  # 50 % pick a zone
+    asel = np.where(d[:, 4] % np.uint64(4) == 0, (d[:, 5] % np.uint64(2)).astype(int), -1)  # 25 % pick an arch
+    t = (d[:, 6] % np.uint64(40)).astype(int)
+    tol = np.where(t < 2, 0, np.where(t % 2 == 0, 1, 2))  # 5 % none, else half Equal / half Exists
+    npools = 1 if pools is None else len(pools)
+    pool = np.arange(n_pods) % npools
+    table = np.zeros((5, 6, 5, 3, 3, npools), np.int32)
+    for c in range(5):
+        for m in range(6):
+            for z in range(-1, 4):
+                for a in range(-1, 2):
+                    for k in range(3):
+                        for pl in range(npools):
+                            sel = {}
+                            if z >= 0:
+                                sel[ZONE_LABEL] = zones[z]
+                            if a >= 0:
+                                sel[ARCH_LABEL] = archs[a]
+                            tols = []
+                            key = "bench/dedicated" if pools is None else f"bench/{pools[pl]}"
+                            if pools is not None:
+                                sel[NODEPOOL_LABEL] = pools[pl]
+                            if k == 1:
+                                tols = [Toleration(key, "Equal", "true", "NoSchedule")]
+                            elif k == 2:
+                                tols = [Toleration(key, "Exists", "", "")]
+                            table[c, m, z + 1, a + 1, k, pl] = b.pod_class(
+                                Pod(requests=_requests(c, m), node_selector=sel, tolerations=tols))
+    return table[ci, mi, zsel + 1, asel + 1, tol, pool], d[:, 7], pool
+
+
+def config_c3(n_apps=1000, replicas=1000, n_its=1000, zones=3) -> EncodedProblem:
+    """C3: apps x replicas, zonal topology spread (maxSkew 1) + hostname anti-affinity per app."""
+    b = ProblemBuilder()
+    its = kwok.aws_instance_types(n_its)
+    for it in its:
+        b.add_instance_type(it)
+    b.add_nodepool(default_nodepool(zones=kwok.AWS_ZONES[:zones]), list(range(len(its))))
+    n_pods = n_apps * replicas
+    d = draws(n_pods, 4)
+    ci, mi = (d[:, 0] % np.uint64(5)).astype(int), (d[:, 1] % np.uint64(6)).astype(int)
+    app = np.arange(n_pods) // replicas
+    table = _app_classes(b, n_apps)
+    b.set_pod_arrays(table[app, ci, mi], np.zeros(n_pods, np.int64), d[:, 2], d[:, 3])
+    return b.build()
+
+
+def _app_classes(b: ProblemBuilder, n_apps: int, extra_selector=None, tolerations=(), prefix="app"):
+    table = np.zeros((n_apps, 5, 6), np.int32)
+    for a in range(n_apps):
+        labels = {"app": f"{prefix}-{a:05d}"}
+        sel = LabelSelector.of(labels)
+        tsc = [TopologySpreadConstraint(1, ZONE_LABEL, sel)]
+        anti = [PodAffinityTerm(sel, HOSTNAME_LABEL)]
+        for c in range(5):
+            for m in range(6):
+                table[a, c, m] = b.pod_class(Pod(labels=labels, requests=_requests(c, m),
+                                                 node_selector=dict(extra_selector or {}),
+                                                 tolerations=list(tolerations), topology_spread_constraints=tsc,
+                                                 pod_anti_affinity=anti))
+    return table
+
+
+def config_c5(n_pods=10_000_000, n_pools=8, n_its=1000, app_replicas=1000, pools_subset=None) -> EncodedProblem:
+    """C5: pods pinned to one of `n_pools` NodePools (selector + toleration of the pool's taint); half the pods carry
+    the C2 constraint mix, half the C3 mix (apps never span pools).  `pools_subset` keeps only the pods (and pools) of
+    the given pool indices -- the shard one rank owns when the job is split by NodePool."""
+    b = ProblemBuilder()
+    its = kwok.aws_instance_types(n_its)
+    for it in its:
+        b.add_instance_type(it)
+    pools = [f"pool-{i}" for i in range(n_pools)]
+    keep = list(range(n_pools)) if pools_subset is None else list(pools_subset)
+    for i in keep:
+        b.add_nodepool(default_nodepool(pools[i], taints=[Taint(f"bench/{pools[i]}", "true", "NoSchedule")],
+                                        zones=kwok.AWS_ZONES[:3]), list(range(len(its))))
+    half = n_pods // 2
+    cls_a, uid_a, pool_a = _c2_pods(b, half, None, SEED, pools)
+    n_b = n_pods - half
+    per_pool = n_b // n_pools
+    n_apps_pool = max(1, per_pool // app_replicas)
+    d = draws(n_b, 4, SEED + 1)
+    ci, mi = (d[:, 0] % np.uint64(5)).astype(int), (d[:, 1] % np.uint64(6)).astype(int)
+    pool_b = np.arange(n_b) % n_pools
+    app_b = (np.arange(n_b) // n_pools) // app_replicas
+    app_b = np.minimum(app_b, n_apps_pool - 1)
+    cls_b = np.zeros(n_b, np.int32)
+    for pl in range(n_pools):
+        if pl not in keep:
+            continue
+        tbl = _app_classes(b, n_apps_pool, {NODEPOOL_LABEL: pools[pl]},
+                           [Toleration(f"bench/{pools[pl]}", "Exists", "", "")], prefix=f"p{pl}-app")
+        m = pool_b == pl
+        cls_b[m] = tbl[app_b[m], ci[m], mi[m]]
+    cls = np.concatenate([cls_a, cls_b])
+    uid_hi = np.concatenate([uid_a, d[:, 2]])
+    uid_lo = np.concatenate([splitmix64(SEED + 2, np.arange(half, dtype=np.uint64)), d[:, 3]])
+    pool = np.concatenate([pool_a, pool_b])
+    m = np.isin(pool, keep)
+    b.set_pod_arrays(cls[m], np.zeros(int(m.sum()), np.int64), uid_hi[m], uid_lo[m])
+    return b.build()
+
+
+def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_its=50):
+    """C4: a cluster of existing KWOK nodes full of running pods + the removal subsets to evaluate.
+
+    Returns (EncodedProblem, ConsolInput-kwargs dict).  Nodes draw their instance type uniformly from the linux /
+    on-demand members of C1's catalog and a zone uniformly; pods are dealt first-fit round-robin so the state is
+    consistent (available = allocatable - bound requests >= 0).  Candidates are the `n_candidates` nodes with the
+    lowest disruption cost == fewest pods (utils/disruption/disruption.go:71-77 with default pod costs), and every
+    subset of size 1..max_subset of them is one computeConsolidation call (100 + 4950 + 161700 = 166750).
+    """
+    b = ProblemBuilder()
+    its = kwok.generic_instance_types()[:n_its]
+    for it in its:
+        b.add_instance_type(it)
+    b.add_nodepool(default_nodepool(), list(range(len(its))))
+    linux = [i for i, it in enumerate(its) if it.name.endswith("-linux")]
+    dn = draws(n_nodes, 2, SEED + 10)
+    node_it = np.array(linux)[(dn[:, 0] % np.uint64(len(linux))).astype(int)]
+    node_zone = (dn[:, 1] % np.uint64(4)).astype(int)
+    from .model import quantity_units
+    R = ["cpu", "memory", "pods", "ephemeral-storage"]
+    alloc = np.zeros((n_nodes, 4), np.int64)
+    for n in range(n_nodes):
+        it = its[node_it[n]]
+        for r, name in enumerate(R):
+            alloc[n, r] = quantity_units(name, it.capacity[name]) - quantity_units(name, it.overhead.get(name, 0))
+    dp = draws(n_pods, 4, SEED + 11)
+    ci, mi = (dp[:, 0] % np.uint64(5)).astype(int), (dp[:, 1] % np.uint64(6)).astype(int)
+    req = np.stack([np.array(CPU_MILLI)[ci], np.array(MEM_MI)[mi] * (1 << 20), np.ones(n_pods, np.int64),
+                    np.zeros(n_pods, np.int64)], axis=1).astype(np.int64)
+    used = np.zeros((n_nodes, 4), np.int64)
+    pod_node = np.full(n_pods, -1, np.int64)
+    for i in range(n_pods):
+        n = i % n_nodes
+        for _ in range(n_nodes):
+            if np.all(used[n] + req[i] <= alloc[n]):
+                break
+            n = (n + 1) % n_nodes
+        else:
+            continue  # cluster full: drop the pod
+        used[n] += req[i]
+        pod_node[i] = n
+    table = np.zeros((5, 6), np.int32)
+    for c in range(5):
+        for m in range(6):
+            table[c, m] = b.pod_class(Pod(requests=_requests(c, m)))
+    for n in range(n_nodes):
+        it = its[node_it[n]]
+        zone = kwok.KWOK_ZONES[node_zone[n]]
+        labels = {HOSTNAME_LABEL: f"node-{n:05d}", ZONE_LABEL: zone, CAPACITY_TYPE_LABEL: "on-demand",
+                  OS_LABEL: "linux", ARCH_LABEL: it.name.split("-")[2], NODEPOOL_LABEL: "default",
+                  "node.kubernetes.io/instance-type": it.name}
+        avail = {name: int(alloc[n, r] - used[n, r]) for r, name in enumerate(R)}
+        avail["cpu"] = f"{avail['cpu']}m"
+        cap = dict(it.capacity)
+        cap["nodes"] = 1
+        b.add_node(StateNode(name=f"node-{n:05d}", labels=labels, available=avail, capacity=cap, nodepool="default",
+                             instance_type=it.name))
+    # pod rows grouped by node (kp_consol_input.node_pod_off); node order == name order == index order here
+    keep = pod_node >= 0
+    order = np.argsort(pod_node[keep], kind="stable")
+    rows_cls = table[ci[keep], mi[keep]][order]
+    rows_node = pod_node[keep][order]
+    b.set_pod_arrays(rows_cls, np.zeros(len(rows_cls), np.int64), dp[keep][order, 2], dp[keep][order, 3])
+    enc = b.build()
+    counts = np.bincount(rows_node, minlength=n_nodes)
+    node_pod_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    # candidates: non-empty nodes sorted by disruption cost (== pod count), ties by index (stable canon)
+    nonempty = np.nonzero(counts > 0)[0]
+    cand = nonempty[np.argsort(counts[nonempty], kind="stable")][:n_candidates]
+    subsets: List[Tuple[int, ...]] = []
+    k = len(cand)
+    for i in range(k):
+        subsets.append((i,))
+    if max_subset >= 2:
+        for i in range(k):
+            for j in range(i + 1, k):
+                subsets.append((i, j))
+    if max_subset >= 3:
+        for i in range(k):
+            for j in range(i + 1, k):
+                for l in range(j + 1, k):
+                    subsets.append((i, j, l))
+    sub_off = np.concatenate([[0], np.cumsum([len(s) for s in subsets])]).astype(np.int32)
+    sub_nodes = np.array([cand[i] for s in subsets for i in s], np.int32)
+    consol = dict(node_pod_off=node_pod_off, node_it=node_it.astype(np.int32), node_is_spot=np.zeros(n_nodes, np.uint8),
+                  n_subsets=len(subsets), subset_off=sub_off, subset_nodes=sub_nodes, spot_to_spot_enabled=0,
+                  capacity_type_key=enc.key_id(CAPACITY_TYPE_LABEL),
+                  ct_reserved=enc.value_id(CAPACITY_TYPE_LABEL, "reserved"),
+                  ct_spot=enc.value_id(CAPACITY_TYPE_LABEL, "spot"),
+                  ct_on_demand=enc.value_id(CAPACITY_TYPE_LABEL, "on-demand"))
+    return enc, consol
