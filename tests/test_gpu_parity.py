@@ -43,3 +43,14 @@ def test_c2_parity(handle, n_pods):
 def test_c3_parity(handle, apps, replicas):
     enc = workloads.config_c3(n_apps=apps, replicas=replicas, n_its=300)
     assert_same(handle.solve(enc.problem), oracle_lib.solve(enc.problem), f"C3[{apps}x{replicas}] ")
+
+
+def test_c2_full_size_parity(handle):
+    """BASELINE configs[1] at full size: 100k pods x 500 instance types, bit-identical to the oracle."""
+    enc = workloads.config_c2()
+    assert_same(handle.solve(enc.problem), oracle_lib.solve(enc.problem), "C2[100k] ")
+
+
+def test_c3_medium_parity(handle):
+    enc = workloads.config_c3(n_apps=200, replicas=200, n_its=1000)
+    assert_same(handle.solve(enc.problem), oracle_lib.solve(enc.problem), "C3[200x200] ")
