@@ -217,6 +217,50 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(up(h, &d.cls_match, t.cls_match));
   CK(up(h, &d.cls_rec_off, t.cls_rec_off));
   CK(up(h, &d.cls_rec, t.cls_rec));
+  {  // class rows (one indirection less on the per-pod path)
+    std::vector<int32_t> hdr((size_t)std::max(t.X, 1) * 6, 0);
+    std::vector<uint64_t> tok(std::max(t.X, 1), 0);
+    size_t XK = (size_t)std::max(t.X, 1) * t.K;
+    std::vector<uint8_t> pf(XK, 0), sf(XK, 0);
+    std::vector<uint64_t> pm(XK, 0), sm(XK, 0);
+    std::vector<int64_t> pg(XK, 0), pl(XK, 0), sg(XK, 0), sl(XK, 0);
+    if (t.N > 64) return h->err = "more than 64 NodePools", KP_ERR_CAPACITY;
+    for (int x = 0; x < t.X; x++) {
+      int32_t* hh = &hdr[(size_t)x * 6];
+      hh[0] = t.cls_tolset[x];
+      hh[1] = t.cls_rv[x];
+      hh[2] = t.cls_match_off[x];
+      hh[3] = t.cls_match_off[x + 1];
+      hh[4] = t.cls_rec_off[x];
+      hh[5] = t.cls_rec_off[x + 1];
+      for (int n = 0; n < t.N; n++) {
+        int ts = t.tmpl_taintset[n];
+        bool ok = ts < 0 || t.n_taintsets == 0 || t.tol_ok[(size_t)(t.cls_tolset[x] + 1) * t.n_taintsets + ts];
+        if (ok) tok[x] |= 1ull << n;
+      }
+      for (int k = 0; k < t.K; k++) {
+        size_t a = (size_t)t.cls_rs[x] * t.K + k, b = (size_t)t.cls_strict_rs[x] * t.K + k, o = (size_t)x * t.K + k;
+        pf[o] = t.rs_flags[a];
+        pm[o] = t.rs_mask[a];
+        pg[o] = t.rs_gte[a];
+        pl[o] = t.rs_lte[a];
+        sf[o] = t.rs_flags[b];
+        sm[o] = t.rs_mask[b];
+        sg[o] = t.rs_gte[b];
+        sl[o] = t.rs_lte[b];
+      }
+    }
+    CK(up(h, &d.cr_hdr, hdr));
+    CK(up(h, &d.cr_tmplok, tok));
+    CK(up(h, &d.cp_f, pf));
+    CK(up(h, &d.cp_m, pm));
+    CK(up(h, &d.cp_g, pg));
+    CK(up(h, &d.cp_l, pl));
+    CK(up(h, &d.cs_f, sf));
+    CK(up(h, &d.cs_m, sm));
+    CK(up(h, &d.cs_g, sg));
+    CK(up(h, &d.cs_l, sl));
+  }
   CK(up(h, &d.groups, t.groups));
   CK(up(h, &d.filter_rs, t.filter_rs));
   CK(up_mut(h, &d.dom_cnt, t.dom_cnt));
@@ -346,6 +390,7 @@ static int do_upload(kp_handle* h, const kp_problem* p, int cmax) {
   }
   CK(up_raw(h, &h->d_class_rank, rank.data(), rank.size()));
   CK(zeros(h, &d.queue, P + 1));
+  CK(zeros(h, &d.qcls, P + 1));
   CK(zeros(h, &d.last_len, P));
   CK(zeros(h, &d.pod_target, P));
   CK(zeros(h, &d.pod_error, P));
@@ -394,15 +439,21 @@ static int run_solve(kp_handle* h) {
     k_sort_keys<<<nb, 256, 0, h->stream>>>(d.pod_class, h->d_class_rank, d.queue, P, keys);
     thrust::stable_sort_by_key(pol, k64, k64 + P, perm);
     CK(cudaFreeAsync(keys, h->stream));
+    k_gather<<<nb, 256, 0, h->stream>>>(d.pod_class, d.queue, P, d.qcls);
     k_fill_i32<<<nb, 256, 0, h->stream>>>(d.pod_target, P, KP_TARGET_UNSCHEDULED);
-    h->stats.kernel_launches += 5;
+    h->stats.kernel_launches += 6;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveShared));
-    attr_set = true;
-  }
-  k_solve<<<1, SOLVE_THREADS, sizeof(SolveShared), h->stream>>>(d);
+  // shared-memory budget of the solve CTA: fixed part + mirrors of the first CS claims + dead bits
+  const size_t fixed = (sizeof(SolveShared) + 15) & ~(size_t)15;
+  const size_t budget = 200 * 1024;
+  int CS = d.Cmax;
+  auto need = [&](int cs) { return fixed + (size_t)cs * 12 + (size_t)d.n_rv * ((cs + 31) / 32) * 4 + 64; };
+  while (CS > 32 && need(CS) > budget) CS = (CS * 3 / 4) & ~31;
+  if (need(CS) > budget) return h->err = "shared-memory budget exceeded (too many distinct request vectors)", KP_ERR_CAPACITY;
+  d.CS = CS;
+  size_t smem = need(CS);
+  CK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_solve<<<1, SOLVE_THREADS, smem, h->stream>>>(d);
   h->stats.kernel_launches++;
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));

@@ -16,7 +16,7 @@
 #include "kp_slot.hpp"
 
 #define FULL 0xffffffffu
-#define SOLVE_THREADS 1024
+#define SOLVE_THREADS 512
 #define SOLVE_WARPS (SOLVE_THREADS / 32)
 
 __device__ __forceinline__ KeyInfo key_info(const KpDev& d, int k) {
@@ -187,13 +187,23 @@ struct Eval {
   uint64_t its;    // lane w: surviving instance-type word (claims)
 };
 
-// Exact CanAdd of pod class X on one candidate (NodeClaim.CanAdd nodeclaim.go:114-202 when is_claim, else
+// The pod being placed, staged once per pod in shared memory (class row of the problem + its requirement slots).
+struct PodCtx {
+  int pod, cls, tolset, rv;
+  int moff, mend, roff, rend;
+  unsigned long long tmpl_ok;  // bit n: template n's taints are tolerated (taints.go:49-66)
+  int64_t req[KP_MAXR];
+  Slot pod_slot[KP_MAXK];
+  Slot strict_slot[KP_MAXK];
+};
+
+// Exact CanAdd of the staged pod on one candidate (NodeClaim.CanAdd nodeclaim.go:114-202 when is_claim, else
 // ExistingNode.CanAdd existingnode.go:70-143 after the taint / Fits checks of phase 1).
 //   base       lane k: the candidate's current requirement slot
 //   host       index of the candidate's hostname domain in host_cnt
 //   scratch    per-warp shared memory, KP_MAXK slots
-__device__ __forceinline__ Eval eval_candidate(const KpDev& d, int X, bool is_claim, const Slot& base, int64_t base_q,
-                                               uint64_t base_its, int host, Slot* scratch, int lane) {
+__device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px, bool is_claim, const Slot& base,
+                                               int64_t base_q, uint64_t base_its, int host, Slot* scratch, int lane) {
   Eval ev;
   ev.ok = false;
   ev.res_dead = false;
@@ -201,17 +211,17 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, int X, bool is_cl
   const bool allow_undef = is_claim;  // ExistingNode.CanAdd passes no compatibility options
   const bool wk = lane < K ? d.key_wellknown[lane] : false;
   KeyInfo ki = lane < K ? key_info(d, lane) : KeyInfo{d.val_int, 0ull, 0ull};
-  Slot pod = lane < K ? rs_slot(d, d.cls_rs[X], lane) : slot_absent();
+  Slot pod = lane < K ? px.pod_slot[lane] : slot_absent();
   // requirements.Compatible(pod requirements) then Add
   bool bad = lane < K && !slot_compatible(ki, base, pod, wk, allow_undef);
   if (__any_sync(FULL, bad)) return ev;
   Slot M = lane < K ? slot_add(ki, base, pod) : slot_absent();
   // Topology.AddRequirements (topology.go:226-248)
-  Slot Tt = M;
-  bool fail = false;
-  int moff = d.cls_match_off[X], mend = d.cls_match_off[X + 1];
+  const int moff = px.moff, mend = px.mend;
   if (mend > moff) {
-    Slot strict = lane < K ? rs_slot(d, d.cls_strict_rs[X], lane) : slot_absent();
+    Slot Tt = M;
+    bool fail = false;
+    Slot strict = lane < K ? px.strict_slot[lane] : slot_absent();
     for (int i = moff; i < mend; i++) {
       int e = d.cls_match[i];
       int g = e & 0x3fffffff;
@@ -250,7 +260,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, int X, bool is_cl
   // resources.Merge + filterInstanceTypesByRequirements
   if (lane < K) scratch[lane] = M;
   __syncwarp();
-  int64_t q = base_q + (lane < d.R ? d.cls_req[(size_t)X * d.R + lane] : 0);
+  int64_t q = base_q + (lane < d.R ? px.req[lane] : 0);
   uint64_t fw;
   uint64_t w = filter_its_word(d, scratch, q, lane, &fw) & base_its;
   __syncwarp();
@@ -261,12 +271,54 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, int X, bool is_cl
   return ev;
 }
 
+// A class row in flight between global memory and the shared PodCtx (one warp; lane k: key k, lane r: resource r,
+// lane i < 8: header word i).
+struct ClassRegs {
+  int hdr;                // lanes 0..7: tolset, rv, moff, mend, roff, rend, class, pod
+  unsigned long long tmpl_ok;
+  int64_t req;
+  Slot pod, strict;
+};
+__device__ __forceinline__ ClassRegs load_class_regs(const KpDev& d, int X, int pod, int lane) {
+  ClassRegs c;
+  c.hdr = lane < 6 ? d.cr_hdr[(size_t)X * 6 + lane] : (lane == 6 ? X : pod);
+  c.tmpl_ok = lane == 0 ? d.cr_tmplok[X] : 0ull;
+  c.req = lane < d.R ? d.cls_req[(size_t)X * d.R + lane] : 0;
+  if (lane < d.K) {
+    size_t i = (size_t)X * d.K + lane;
+    c.pod = load_slot(d.cp_f, d.cp_m, d.cp_g, d.cp_l, i, d.has_bounds);
+    c.strict = load_slot(d.cs_f, d.cs_m, d.cs_g, d.cs_l, i, d.has_bounds);
+  } else {
+    c.pod = slot_absent();
+    c.strict = slot_absent();
+  }
+  return c;
+}
+__device__ __forceinline__ void store_class_regs(const KpDev& d, PodCtx& px, const ClassRegs& c, int lane) {
+  int* hdr = &px.tolset;  // tolset, rv, moff, mend, roff, rend are consecutive ints
+  if (lane == 0) px.tolset = c.hdr;
+  if (lane == 1) px.rv = c.hdr;
+  if (lane == 2) px.moff = c.hdr;
+  if (lane == 3) px.mend = c.hdr;
+  if (lane == 4) px.roff = c.hdr;
+  if (lane == 5) px.rend = c.hdr;
+  if (lane == 6) px.cls = c.hdr;
+  if (lane == 7) px.pod = c.hdr;
+  (void)hdr;
+  if (lane == 0) px.tmpl_ok = c.tmpl_ok;
+  if (lane < d.R) px.req[lane] = c.req;
+  if (lane < d.K) {
+    px.pod_slot[lane] = c.pod;
+    px.strict_slot[lane] = c.strict;
+  }
+}
+
 // Topology.Record (topology.go:197-220) for the committed placement; executed by one warp.
-__device__ __forceinline__ void topo_record(const KpDev& d, int X, const Slot& F, int taintset, int host,
+__device__ __forceinline__ void topo_record(const KpDev& d, const PodCtx& px, const Slot& F, int taintset, int host,
                                             bool allow_undef, int lane) {
   const int K = d.K;
   (void)allow_undef;  // TopologyNodeFilter.Matches never forwards the options (topologynodefilter.go:68-85)
-  for (int i = d.cls_rec_off[X]; i < d.cls_rec_off[X + 1]; i++) {
+  for (int i = px.roff; i < px.rend; i++) {
     int g = d.cls_rec[i];
     KpGroup G = d.groups[g];
     bool counts = true;

@@ -200,48 +200,65 @@ struct DevSorter {
   }
 };
 
+
 enum { PERT_NONE = 0, PERT_INC = 1, PERT_APPEND = 2 };
 
+// Everything the per-pod critical path touches lives in shared memory: the claim order (s.newNodeClaims as ids +
+// pod counts), per-claim template ids, the "can never fit again" bits, the allocatable thresholds and the staged pod.
 struct SolveShared {
-  int head, tail, cap;     // circular pod queue
-  int pod, cls, done;
+  int head, tail, cap;
+  int done, found;
   int n_claims;
-  int pert_kind, pert_pos; // the one out-of-order element left behind by the previous commit
+  int pert_kind, pert_pos;
   int rot_from, rot_to, rot_mode;
-  int warp_cnt[SOLVE_WARPS];
-  int cand_n;
-  int cand[SOLVE_THREADS];     // candidates of the current chunk, in scan order
+  int ctx_idx[2];  // queue index whose class row sits in ctx[i]
+  int alive_tmpl;
+  unsigned warp_mask[SOLVE_WARPS];
   int ok[SOLVE_WARPS];
-  int winner;
-  int found;
-  int active_before;           // existing-node evaluation counter helper
+  PodCtx ctx[2];
   Slot scratch[SOLVE_WARPS][KP_MAXK];
 };
 
-// block-wide ordered compaction of a predicate into sh.cand (returns count via sh.cand_n)
-__device__ __forceinline__ void compact(SolveShared& sh, bool pass, int value) {
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned m = __ballot_sync(FULL, pass);
-  if (lane == 0) sh.warp_cnt[w] = __popc(m);
-  __syncthreads();
-  int base = 0, total = 0;
-  for (int i = 0; i < SOLVE_WARPS; i++) {
-    int c = sh.warp_cnt[i];
-    if (i < w) base += c;
-    total += c;
+// n-th set bit over the per-warp ballot masks of a chunk (-1 if fewer); *total = number of set bits
+__device__ __forceinline__ int nth_candidate(const unsigned* masks, int n, int* total) {
+  int acc = 0, found = -1;
+#pragma unroll
+  for (int w = 0; w < SOLVE_WARPS; w++) {
+    unsigned m = masks[w];
+    int c = __popc(m);
+    if (found < 0 && n < acc + c) found = w * 32 + (__fns(m, 0, n - acc + 1));
+    acc += c;
   }
-  if (pass) sh.cand[base + __popc(m & ((1u << lane) - 1))] = value;
-  if (threadIdx.x == 0) sh.cand_n = total;
-  __syncthreads();
+  *total = acc;
+  return found;
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SolveShared& sh = *reinterpret_cast<SolveShared*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int K = d.K, R = d.R, ITW = d.ITW, E = d.E;
-  int* order = d.order;
-  int* cnt_at = d.cnt_at;
+  const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, CS = d.CS;
+  // shared mirrors (write-through) of the first CS claim positions / ids
+  int* order_s = reinterpret_cast<int*>(smem_raw + ((sizeof(SolveShared) + 15) & ~15));
+  int* cnt_s = order_s + CS;
+  int* tmpl_s = cnt_s + CS;
+  uint32_t* rdead_s = reinterpret_cast<uint32_t*>(tmpl_s + CS);  // [n_rv * RWS]
+  const int RW = (d.Cmax + 31) >> 5, RWS = (CS + 31) >> 5;
+  auto ord = [&](int pos) { return pos < CS ? order_s[pos] : d.order[pos]; };
+  auto cnt = [&](int pos) { return pos < CS ? cnt_s[pos] : d.cnt_at[pos]; };
+  auto set_ord = [&](int pos, int c, int n) {
+    d.order[pos] = c;
+    d.cnt_at[pos] = n;
+    if (pos < CS) {
+      order_s[pos] = c;
+      cnt_s[pos] = n;
+    }
+  };
+  auto claim_tmpl = [&](int c) { return c < CS ? tmpl_s[c] : d.c_tmpl[c]; };
+  auto is_rdead = [&](int rv, int c) {
+    uint32_t w = c < CS ? rdead_s[rv * RWS + (c >> 5)] : d.rdead[(size_t)rv * RW + (c >> 5)];
+    return (w >> (c & 31)) & 1u;
+  };
   if (tid == 0) {
     sh.head = 0;
     sh.tail = (int)d.P;
@@ -249,45 +266,86 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
     sh.n_claims = 0;
     sh.pert_kind = PERT_NONE;
     sh.done = 0;
+    sh.ctx_idx[0] = sh.ctx_idx[1] = -1;
+    int alive = 0;
+    for (int n = 0; n < d.N; n++) {
+      bool any = false;
+      for (int w = 0; w < ITW; w++) any |= d.tmpl_its[(size_t)n * ITW + w] != 0;
+      alive += any;
+    }
+    sh.alive_tmpl = alive;
   }
-  __syncthreads();
+  for (int i = tid; i < d.n_rv * RWS; i += SOLVE_THREADS) rdead_s[i] = 0;
   long long ev_existing = 0, ev_inflight = 0, ev_tmpl = 0, commits = 0, slow_sorts = 0;  // thread 0 only
   int n_active_nodes = 0;
   for (int n = tid; n < E; n += SOLVE_THREADS) n_active_nodes += (d.node_flags[n] & KP_NODE_SCHEDULABLE) ? 1 : 0;
-  // (block reduce once)
   {
     for (int o = 16; o; o >>= 1) n_active_nodes += __shfl_xor_sync(FULL, n_active_nodes, o);
-    if (lane == 0) sh.warp_cnt[warp] = n_active_nodes;
+    __syncthreads();
+    if (lane == 0) sh.ok[warp] = n_active_nodes;
     __syncthreads();
     n_active_nodes = 0;
-    for (int i = 0; i < SOLVE_WARPS; i++) n_active_nodes += sh.warp_cnt[i];
-    __syncthreads();
+    for (int i = 0; i < SOLVE_WARPS; i++) n_active_nodes += sh.ok[i];
   }
+  // class prefetch pipeline of the last warp: pf_cls = class of queue index pf_idx (loaded one iteration earlier)
+  int a_idx = -1, a_val = -1;
 
+  long long watchdog = 0;
   for (;;) {
-    __syncthreads();  // everyone has read sh.found / sh.done of the previous pod
+    __syncthreads();  // (S0) previous pod fully committed; prefetched rows visible
+    const int h = sh.head;
+    if (++watchdog > 4 * (long long)d.P + 1024) {  // cannot happen: every requeue cycle needs progress (queue.go:54-58)
+      if (tid == 0) *d.status = KP_ERR_INVALID;
+      break;
+    }
     // ---- Queue.Pop (queue.go:46-60)
     if (tid == 0) {
-      int len = sh.tail - sh.head;
+      int len = sh.tail - h;
       if (len == 0) {
         sh.done = 1;
-      } else {
-        int pod = d.queue[sh.head % sh.cap];
-        if (d.last_len[pod] == len) {
-          sh.done = 1;
-        } else {
-          sh.head++;
-          sh.pod = pod;
-          sh.cls = d.pod_class[pod];
-        }
+      } else if (h >= (int)d.P && d.last_len[d.queue[h % sh.cap]] == len) {
+        sh.done = 1;  // a full cycle without progress
       }
       sh.found = 0;
     }
-    __syncthreads();
+    // stage the pod's class row unless the prefetcher already did
+    const bool have_ctx = sh.ctx_idx[h & 1] == h;
+    const int pert = sh.pert_kind;  // read between S0 and S1: commits write it before S0, the sort stage after S1
+    __syncthreads();  // (S1)
     if (sh.done) break;
-    const int X = sh.cls, pod = sh.pod;
-    const int tolset = d.cls_tolset[X];
-    const int rv = d.cls_rv[X];
+    if (!have_ctx) {
+      if (warp == 0) {
+        ClassRegs cr = load_class_regs(d, d.qcls[h % sh.cap], d.queue[h % sh.cap], lane);
+        store_class_regs(d, sh.ctx[h & 1], cr, lane);
+        if (lane == 0) sh.ctx_idx[h & 1] = h;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) sh.head = h + 1;
+    // ---- software-pipelined staging of upcoming pods by the last warp: stage A (previous iteration) fetched
+    // (class, pod) of queue index h+1 into registers; stage B issues that pod's class-row loads now and parks them
+    // in registers until the end of this iteration, so no warp ever waits on them.
+    int b_idx = -1;
+    ClassRegs br;
+    if (warp == SOLVE_WARPS - 1) {
+      if (a_idx == h + 1) {
+        int X = __shfl_sync(FULL, a_val, 0);
+        int podn = __shfl_sync(FULL, a_val, 1);
+        b_idx = a_idx;
+        br = load_class_regs(d, X, podn, lane);
+      }
+      a_idx = -1;
+      int nxt = h + 2;
+      if (nxt < sh.tail) {
+        a_idx = nxt;
+        if (lane == 0) a_val = d.qcls[nxt % sh.cap];
+        if (lane == 1) a_val = d.queue[nxt % sh.cap];
+      }
+    }
+    const PodCtx& px = sh.ctx[h & 1];
+    const int pod = px.pod;
+    const int tolset = px.tolset, rv = px.rv;
+    do {
 
     // ================= addToExistingNode (scheduler.go:520-555) =================
     for (int base = 0; base < E && !sh.found; base += SOLVE_THREADS) {
@@ -301,35 +359,34 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
             int64_t rem = d.node_rem[(size_t)n * R + r];
             bool present = pr >> r & 1;
             if (present && rem < 0) pass = false;
-            if (d.cls_req[(size_t)X * R + r] > (present ? rem : 0)) pass = false;
+            if (px.req[r] > (present ? rem : 0)) pass = false;
           }
         }
       }
-      compact(sh, pass, n);
-      int ncand = sh.cand_n;
-      for (int g0 = 0; g0 < ncand && !sh.found; g0 += SOLVE_WARPS) {
-        int ci = g0 + warp;
+      unsigned m = __ballot_sync(FULL, pass);
+      if (lane == 0) sh.warp_mask[warp] = m;
+      __syncthreads();
+      int total;
+      for (int g0 = 0;; g0 += SOLVE_WARPS) {
+        int off = nth_candidate(sh.warp_mask, g0 + warp, &total);
+        if (g0 >= total) break;
         Eval ev;
         ev.ok = false;
         int node = -1;
-        if (ci < ncand) {
-          node = sh.cand[ci];
+        if (off >= 0) {
+          node = base + off;
           Slot b = lane < K ? load_slot(d.node_sflags, d.node_smask, d.node_sgte, d.node_slte, (size_t)node * K + lane,
                                          d.has_bounds)
                             : slot_absent();
-          ev = eval_candidate(d, X, false, b, 0, 0, node, sh.scratch[warp], lane);
+          ev = eval_candidate(d, px, false, b, 0, 0, node, sh.scratch[warp], lane);
         }
         if (lane == 0) sh.ok[warp] = ev.ok;
         __syncthreads();
-        if (tid == 0) {
-          int w = -1;
-          for (int i = 0; i < SOLVE_WARPS && w < 0; i++)
-            if (sh.ok[i]) w = i;
-          sh.winner = w;
-          if (w >= 0) sh.found = 1;
-        }
-        __syncthreads();
-        if (sh.winner == warp) {  // ExistingNode.Add (existingnode.go:147-155)
+        int winner = -1;
+#pragma unroll
+        for (int i = SOLVE_WARPS - 1; i >= 0; i--)
+          if (sh.ok[i]) winner = i;
+        if (winner == warp) {  // ExistingNode.Add (existingnode.go:147-155)
           if (lane < K) {
             size_t i = (size_t)node * K + lane;
             d.node_sflags[i] = (uint8_t)ev.F.f;
@@ -339,62 +396,67 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
               d.node_slte[i] = ev.F.lte;
             }
           }
-          if (lane < R) d.node_rem[(size_t)node * R + lane] -= d.cls_req[(size_t)X * R + lane];
+          if (lane < R) d.node_rem[(size_t)node * R + lane] -= px.req[lane];
           if (lane == 0) {
             d.node_rem_present[node] |= (1u << R) - 1;
             d.node_npods[node]++;
             d.pod_target[pod] = node;
             d.pod_error[pod] = KP_PODERR_NONE;
-            d.counters[0] += node + 1;  // nodes 0..node were evaluated by the reference
+            d.counters[0] += node + 1;
+            sh.found = 1;
           }
-          topo_record(d, X, ev.F, d.node_taintset[node], node, false, lane);
+          topo_record(d, px, ev.F, d.node_taintset[node], node, false, lane);
         }
         __syncthreads();
+        if (winner >= 0) break;
       }
+      __syncthreads();  // the next chunk rewrites warp_mask
     }
     if (tid == 0) {
-      // the reference evaluates every existing node up to the winner (or all of them)
-      ev_existing += sh.found ? 0 : n_active_nodes;  // (winner-prefix counts are added by the host from pod_target)
-      if (sh.found) commits++;
+      if (sh.found)
+        commits++;
+      else
+        ev_existing += n_active_nodes;
     }
-    if (sh.found) continue;
+    if (sh.found) break;
 
     // ================= sort.Slice(newNodeClaims, len(Pods) asc) (scheduler.go:504) =================
     const int nC = sh.n_claims;
-    if (sh.pert_kind != PERT_NONE) {
+    if (pert != PERT_NONE) {
       if (tid == 0) {
         int p = sh.pert_pos;
-        bool inversion = sh.pert_kind == PERT_INC ? (p + 1 < nC && cnt_at[p + 1] < cnt_at[p])
-                                                  : (nC >= 2 && cnt_at[nC - 1] < cnt_at[nC - 2]);
+        bool inversion = sh.pert_kind == PERT_INC ? (p + 1 < nC && cnt(p + 1) < cnt(p))
+                                                  : (nC >= 2 && cnt(nC - 1) < cnt(nC - 2));
         sh.rot_mode = 0;
         if (inversion) {
           bool stable = d.stable_order || nC <= 12;
+          bool in_smem = nC <= CS;
           if (!stable && nC >= 50) {
-            DevSorter s{cnt_at, order};
+            DevSorter s{in_smem ? cnt_s : d.cnt_at, in_smem ? order_s : d.order};
             int hint;
             s.choose_pivot(0, nC, &hint);
             stable = hint == 1;  // partialInsertionSort repairs a single inversion == stable move
           }
           if (stable) {
             if (sh.pert_kind == PERT_INC) {
-              int c = cnt_at[p];  // elevated count; move right past every smaller element
+              int c = cnt(p);  // elevated count; move right past every smaller element
               int lo = p + 1, hi = nC;
               while (lo < hi) {
                 int mid = (lo + hi) >> 1;
-                if (cnt_at[mid] < c)
+                if (cnt(mid) < c)
                   lo = mid + 1;
                 else
                   hi = mid;
               }
               sh.rot_from = p;
-              sh.rot_to = lo - 1;  // new position of the elevated element
+              sh.rot_to = lo - 1;
               sh.rot_mode = 1;
             } else {
-              int c = cnt_at[nC - 1];  // new claim: move left past every larger element
+              int c = cnt(nC - 1);  // new claim: move left past every larger element
               int lo = 0, hi = nC - 1;
               while (lo < hi) {
                 int mid = (lo + hi) >> 1;
-                if (cnt_at[mid] <= c)
+                if (cnt(mid) <= c)
                   lo = mid + 1;
                 else
                   hi = mid;
@@ -404,8 +466,25 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
               sh.rot_mode = 2;
             }
           } else {
-            DevSorter s{cnt_at, order};
+            // exact pdqsort emulation by one thread (rare: ties scrambled by Go's unstable partition)
+            DevSorter s{in_smem ? cnt_s : d.cnt_at, in_smem ? order_s : d.order};
+            if (!in_smem)
+              for (int i = 0; i < CS; i++) {  // global arrays are the source of truth beyond CS
+                d.cnt_at[i] = cnt_s[i];
+                d.order[i] = order_s[i];
+              }
             s.pdqsort(0, nC, DevSorter::bits_len((unsigned long long)nC));
+            if (in_smem) {
+              for (int i = 0; i < nC; i++) {
+                d.cnt_at[i] = cnt_s[i];
+                d.order[i] = order_s[i];
+              }
+            } else {
+              for (int i = 0; i < CS; i++) {
+                cnt_s[i] = d.cnt_at[i];
+                order_s[i] = d.order[i];
+              }
+            }
             slow_sorts++;
           }
         }
@@ -414,91 +493,78 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
       __syncthreads();
       if (sh.rot_mode == 1) {  // rotate [from, to] left by one
         int from = sh.rot_from, to = sh.rot_to;
-        int eo = order[from], ec = cnt_at[from];
+        int eo = ord(from), ec = cnt(from);
         for (int b0 = from; b0 < to; b0 += SOLVE_THREADS) {
           int i = b0 + tid;
           int vo = 0, vc = 0;
           if (i < to) {
-            vo = order[i + 1];
-            vc = cnt_at[i + 1];
+            vo = ord(i + 1);
+            vc = cnt(i + 1);
           }
           __syncthreads();
-          if (i < to) {
-            order[i] = vo;
-            cnt_at[i] = vc;
-          }
+          if (i < to) set_ord(i, vo, vc);
           __syncthreads();
         }
-        if (tid == 0) {
-          order[to] = eo;
-          cnt_at[to] = ec;
-        }
+        if (tid == 0) set_ord(to, eo, ec);
         __syncthreads();
       } else if (sh.rot_mode == 2) {  // rotate [to, from] right by one
         int from = sh.rot_from, to = sh.rot_to;
-        int eo = order[from], ec = cnt_at[from];
+        int eo = ord(from), ec = cnt(from);
         for (int b0 = from; b0 > to; b0 -= SOLVE_THREADS) {
           int i = b0 - tid;
           int vo = 0, vc = 0;
           if (i > to) {
-            vo = order[i - 1];
-            vc = cnt_at[i - 1];
+            vo = ord(i - 1);
+            vc = cnt(i - 1);
           }
           __syncthreads();
-          if (i > to) {
-            order[i] = vo;
-            cnt_at[i] = vc;
-          }
+          if (i > to) set_ord(i, vo, vc);
           __syncthreads();
         }
-        if (tid == 0) {
-          order[to] = eo;
-          cnt_at[to] = ec;
-        }
+        if (tid == 0) set_ord(to, eo, ec);
         __syncthreads();
       }
     }
 
     // ================= addToInflightNode (scheduler.go:557-589) =================
-    const int rdw = (d.Cmax + 31) >> 5;
     for (int base = 0; base < nC && !sh.found; base += SOLVE_THREADS) {
       int pos = base + tid;
       bool pass = false;
-      int c = -1;
       if (pos < nC) {
-        c = order[pos];
-        pass = !(d.rdead[(size_t)rv * rdw + (c >> 5)] >> (c & 31) & 1);
-        if (pass) pass = tolerated(d, tolset, d.tmpl_taintset[d.c_tmpl[c]]);
+        int c = ord(pos);
+        pass = !is_rdead(rv, c) && ((px.tmpl_ok >> claim_tmpl(c)) & 1ull);
       }
-      compact(sh, pass, pos);
-      int ncand = sh.cand_n;
-      for (int g0 = 0; g0 < ncand && !sh.found; g0 += SOLVE_WARPS) {
-        int ci = g0 + warp;
+      unsigned m = __ballot_sync(FULL, pass);
+      if (lane == 0) sh.warp_mask[warp] = m;
+      __syncthreads();
+      int total;
+      for (int g0 = 0;; g0 += SOLVE_WARPS) {
+        int off = nth_candidate(sh.warp_mask, g0 + warp, &total);
+        if (g0 >= total) break;
         Eval ev;
         ev.ok = false;
         ev.res_dead = false;
         int cpos = -1, cc = -1;
-        if (ci < ncand) {
-          cpos = sh.cand[ci];
-          cc = order[cpos];
+        if (off >= 0) {
+          cpos = base + off;
+          cc = ord(cpos);
           Slot b = lane < K ? load_slot(d.c_sflags, d.c_smask, d.c_sgte, d.c_slte, (size_t)cc * K + lane, d.has_bounds)
                             : slot_absent();
           int64_t bq = lane < R ? d.c_req[(size_t)cc * R + lane] : 0;
           uint64_t bi = lane < ITW ? d.c_its[(size_t)cc * ITW + lane] : 0ull;
-          ev = eval_candidate(d, X, true, b, bq, bi, E + cc, sh.scratch[warp], lane);
-          if (ev.res_dead && lane == 0) atomicOr(&d.rdead[(size_t)rv * rdw + (cc >> 5)], 1u << (cc & 31));
+          ev = eval_candidate(d, px, true, b, bq, bi, E + cc, sh.scratch[warp], lane);
+          if (ev.res_dead && lane == 0) {
+            atomicOr(&d.rdead[(size_t)rv * RW + (cc >> 5)], 1u << (cc & 31));
+            if (cc < CS) atomicOr(&rdead_s[rv * RWS + (cc >> 5)], 1u << (cc & 31));
+          }
         }
         if (lane == 0) sh.ok[warp] = ev.ok;
         __syncthreads();
-        if (tid == 0) {
-          int w = -1;
-          for (int i = 0; i < SOLVE_WARPS && w < 0; i++)
-            if (sh.ok[i]) w = i;
-          sh.winner = w;
-          if (w >= 0) sh.found = 1;
-        }
-        __syncthreads();
-        if (sh.winner == warp) {  // NodeClaim.Add (nodeclaim.go:207-219)
+        int winner = -1;
+#pragma unroll
+        for (int i = SOLVE_WARPS - 1; i >= 0; i--)
+          if (sh.ok[i]) winner = i;
+        if (winner == warp) {  // NodeClaim.Add (nodeclaim.go:207-219)
           if (lane < K) {
             size_t i = (size_t)cc * K + lane;
             d.c_sflags[i] = (uint8_t)ev.F.f;
@@ -512,17 +578,20 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
           if (lane < ITW) d.c_its[(size_t)cc * ITW + lane] = ev.its;
           if (lane == 0) {
             d.c_npods[cc]++;
-            cnt_at[cpos]++;
+            set_ord(cpos, cc, cnt(cpos) + 1);
             d.pod_target[pod] = KP_TARGET_CLAIM(cc);
             d.pod_error[pod] = KP_PODERR_NONE;
             sh.pert_kind = PERT_INC;
             sh.pert_pos = cpos;
+            sh.found = 1;
+            d.counters[1] += cpos + 1;  // claims 0..cpos were evaluated by the reference
           }
-          topo_record(d, X, ev.F, d.tmpl_taintset[d.c_tmpl[cc]], E + cc, true, lane);
-          if (lane == 0) d.counters[1] += cpos + 1;  // claims 0..cpos were evaluated by the reference
+          topo_record(d, px, ev.F, d.tmpl_taintset[claim_tmpl(cc)], E + cc, true, lane);
         }
         __syncthreads();
+        if (winner >= 0) break;
       }
+      __syncthreads();  // the next chunk rewrites warp_mask
     }
     if (tid == 0) {
       if (sh.found)
@@ -530,18 +599,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
       else
         ev_inflight += nC;
     }
-    if (sh.found) continue;
+    if (sh.found) break;
 
     // ================= addToNewNodeClaim (scheduler.go:592-684) =================
-    int err = KP_PODERR_NO_TEMPLATES;
+    int err = sh.alive_tmpl ? KP_PODERR_INCOMPATIBLE : KP_PODERR_NO_TEMPLATES;
     for (int n = 0; n < d.N && !sh.found; n++) {
-      // template alive? (NewScheduler drops templates whose prefilter is empty, scheduler.go:148-157)
-      uint64_t tw = (warp == 0 && lane < ITW) ? d.tmpl_its[(size_t)n * ITW + lane] : 0ull;
-      bool alive = false;
       Eval ev;
       ev.ok = false;
       if (warp == 0) {
-        alive = __any_sync(FULL, tw != 0);
+        uint64_t tw = lane < ITW ? d.tmpl_its[(size_t)n * ITW + lane] : 0ull;
+        bool alive = __any_sync(FULL, tw != 0);  // NewScheduler drops templates whose prefilter is empty
         bool skip = !alive;
         uint32_t lp = d.tmpl_limit_present[n];
         if (alive && lp) {  // limits: scheduler.go:605-623, filterByRemainingResources :860-876
@@ -561,15 +628,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
           }
           if (!skip && !__any_sync(FULL, tw != 0)) skip = true;
         }
-        if (lane == 0) sh.ok[1] = alive;
+        if (alive && lane == 0) ev_tmpl++;
         if (!skip) {
           int cnew = sh.n_claims;
           if (cnew >= d.Cmax) {
             if (lane == 0) *d.status = KP_ERR_CAPACITY;
-          } else if (tolerated(d, tolset, d.tmpl_taintset[n])) {
+          } else if ((px.tmpl_ok >> n) & 1ull) {
             Slot b = lane < K ? rs_slot(d, d.tmpl_rs[n], lane) : slot_absent();
             int64_t bq = lane < R ? d.tmpl_daemon[(size_t)n * R + lane] : 0;
-            ev = eval_candidate(d, X, true, b, bq, tw, E + cnew, sh.scratch[0], lane);
+            ev = eval_candidate(d, px, true, b, bq, tw, E + cnew, sh.scratch[0], lane);
           }
         }
         if (lane == 0) sh.ok[0] = ev.ok;
@@ -579,10 +646,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
         if (tid == 0) sh.done = 1;
         __syncthreads();
         break;
-      }
-      if (sh.ok[1]) {
-        err = KP_PODERR_INCOMPATIBLE;
-        if (tid == 0) ev_tmpl++;
       }
       if (sh.ok[0]) {
         const int cnew = sh.n_claims;
@@ -600,9 +663,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
           if (lane < ITW) d.c_its[(size_t)cnew * ITW + lane] = ev.its;
           if (lane == 0) {
             d.c_tmpl[cnew] = n;
+            if (cnew < CS) tmpl_s[cnew] = n;
             d.c_npods[cnew] = 1;
-            order[cnew] = cnew;
-            cnt_at[cnew] = 1;
+            set_ord(cnew, cnew, 1);
             d.pod_target[pod] = KP_TARGET_CLAIM(cnew);
             d.pod_error[pod] = KP_PODERR_NONE;
           }
@@ -628,13 +691,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
           }
         }
         // Topology.Register(hostname) (nodeclaim.go:213): every hostname group learns the new, empty domain
-        for (int g = tid; g < d.G; g += SOLVE_THREADS)
-          if (d.groups[g].key == d.hostname_key) {
-            d.g_ndomains[g]++;
-            d.g_nempty[g]++;
-          }
-        __syncthreads();
-        if (warp == 0) topo_record(d, X, ev.F, d.tmpl_taintset[n], E + cnew, true, lane);
+        if (d.GH > 0) {
+          for (int g = tid; g < d.G; g += SOLVE_THREADS)
+            if (d.groups[g].key == d.hostname_key) {
+              d.g_ndomains[g]++;
+              d.g_nempty[g]++;
+            }
+          __syncthreads();
+        }
+        if (warp == 0) topo_record(d, px, ev.F, d.tmpl_taintset[n], E + cnew, true, lane);
         if (tid == 0) {
           sh.n_claims = cnew + 1;
           sh.pert_kind = PERT_APPEND;
@@ -644,16 +709,23 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
         }
         __syncthreads();
       }
+      __syncthreads();  // sh.ok[0] is rewritten by the next template
     }
     if (sh.done) break;
     if (!sh.found && tid == 0) {  // scheduler.go:415-421: record the error and requeue
       d.pod_error[pod] = (uint8_t)err;
       d.pod_target[pod] = KP_TARGET_UNSCHEDULED;
       d.queue[sh.tail % sh.cap] = pod;
+      d.qcls[sh.tail % sh.cap] = px.cls;
       sh.tail++;
       d.last_len[pod] = sh.tail - sh.head;
     }
-    __syncthreads();
+    } while (0);
+    if (sh.done) break;
+    if (b_idx >= 0) {  // last warp only: park the staged class row for the next iteration
+      store_class_regs(d, sh.ctx[b_idx & 1], br, lane);
+      if (lane == 0) sh.ctx_idx[b_idx & 1] = b_idx;
+    }
   }
   if (tid == 0) {
     *d.n_claims = sh.n_claims;

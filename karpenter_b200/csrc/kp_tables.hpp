@@ -89,6 +89,17 @@ struct KpDev {
   const int32_t* cls_match;       //
   const int32_t* cls_rec_off;     // [X+1] groups that may count the class on Record (select it / inverse owned)
   const int32_t* cls_rec;
+  // class rows, one level of indirection for the per-pod staging (header: tolset, rv, match/record list ranges)
+  const int32_t* cr_hdr;          // [X*6]
+  const uint64_t* cr_tmplok;      // [X] bit n: template n tolerated
+  const uint8_t* cp_f;            // [X*K] PodData.Requirements slots
+  const uint64_t* cp_m;
+  const int64_t* cp_g;
+  const int64_t* cp_l;
+  const uint8_t* cs_f;            // [X*K] PodData.StrictRequirements slots
+  const uint64_t* cs_m;
+  const int64_t* cs_g;
+  const int64_t* cs_l;
   // topology groups
   const KpGroup* groups;          // [G]
   const int32_t* filter_rs;       // filter alternatives
@@ -111,6 +122,7 @@ struct KpDev {
   int32_t* node_npods;            // [E]
   // claims (dynamic)
   int Cmax;
+  int CS;                         // claim positions / ids mirrored in shared memory
   int32_t* c_tmpl;                // [Cmax]
   int32_t* c_npods;
   int64_t* c_req;                 // [Cmax*R]
@@ -126,6 +138,7 @@ struct KpDev {
   int64_t P;
   const int32_t* pod_class;       // [P]
   int32_t* queue;                 // [P+1] circular queue of pod rows, initially byCPUAndMemoryDescending
+  int32_t* qcls;                  // [P+1] class of queue[i]
   int32_t* last_len;              // [P]
   int32_t* pod_target;            // [P]
   uint8_t* pod_error;             // [P]
