@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -190,15 +191,17 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(up(h, &d.rs_lte, t.rs_lte));
   CK(up(h, &d.rs_keys, t.rs_keys));
   CK(up(h, &d.tol_ok, t.tol_ok));
+  CK(up(h, &d.itv_off, t.itv_off));
   CK(up(h, &d.itv, t.itv));
   CK(up(h, &d.it_nokey, t.it_nokey));
   CK(up(h, &d.it_dne, t.it_dne));
   CK(up(h, &d.it_nonempty, t.it_nonempty));
   CK(up(h, &d.it_valid, t.it_valid));
+  CK(up(h, &d.ge_off, t.ge_off));
   CK(up(h, &d.ge_vals, t.ge_vals));
-  CK(up(h, &d.ge_n, t.ge_n));
   CK(up(h, &d.ge_bits, t.ge_bits));
-  CK(up(h, &d.offset_rs, t.offset_rs));
+  CK(up(h, &d.off_slots, t.off_slots));
+  CK(up(h, &d.off_keys, t.off_keys));
   CK(up(h, &d.offset_bits, t.offset_bits));
   CK(up(h, &d.it_capacity, t.it_capacity));
   CK(up(h, &d.tmpl_rs, t.tmpl_rs));
@@ -218,7 +221,8 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(up(h, &d.cls_rec_off, t.cls_rec_off));
   CK(up(h, &d.cls_rec, t.cls_rec));
   {  // class rows (one indirection less on the per-pod path)
-    std::vector<int32_t> hdr((size_t)std::max(t.X, 1) * 6, 0);
+    std::vector<int32_t> hdr((size_t)std::max(t.X, 1) * 7, 0);
+    std::map<std::pair<int, int>, int> sigs;
     std::vector<uint64_t> tok(std::max(t.X, 1), 0);
     size_t XK = (size_t)std::max(t.X, 1) * t.K;
     std::vector<uint8_t> pf(XK, 0), sf(XK, 0);
@@ -226,13 +230,20 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
     std::vector<int64_t> pg(XK, 0), pl(XK, 0), sg(XK, 0), sl(XK, 0);
     if (t.N > 64) return h->err = "more than 64 NodePools", KP_ERR_CAPACITY;
     for (int x = 0; x < t.X; x++) {
-      int32_t* hh = &hdr[(size_t)x * 6];
+      int32_t* hh = &hdr[(size_t)x * 7];
       hh[0] = t.cls_tolset[x];
       hh[1] = t.cls_rv[x];
       hh[2] = t.cls_match_off[x];
       hh[3] = t.cls_match_off[x + 1];
       hh[4] = t.cls_rec_off[x];
       hh[5] = t.cls_rec_off[x + 1];
+      hh[6] = -1;
+      if (t.cls_match_off[x + 1] == t.cls_match_off[x]) {  // topology-free: CanAdd is a pure function of the claim
+        auto key = std::make_pair(t.cls_rs[x], t.cls_rv[x]);
+        auto it = sigs.find(key);
+        if (it == sigs.end()) it = sigs.emplace(key, (int)sigs.size()).first;
+        hh[6] = it->second;
+      }
       for (int n = 0; n < t.N; n++) {
         int ts = t.tmpl_taintset[n];
         bool ok = ts < 0 || t.n_taintsets == 0 || t.tol_ok[(size_t)(t.cls_tolset[x] + 1) * t.n_taintsets + ts];
@@ -249,6 +260,11 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
         sg[o] = t.rs_gte[b];
         sl[o] = t.rs_lte[b];
       }
+    }
+    d.n_sig = (int)sigs.size();
+    if ((size_t)d.n_sig * (size_t)cmax_hint > (1ull << 28)) {  // cache would not fit comfortably: run without it
+      for (int x = 0; x < t.X; x++) hdr[(size_t)x * 7 + 6] = -1;
+      d.n_sig = 0;
     }
     CK(up(h, &d.cr_hdr, hdr));
     CK(up(h, &d.cr_tmplok, tok));
@@ -291,6 +307,8 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(zeros(h, &d.order, C));
   CK(zeros(h, &d.cnt_at, C));
   CK(zeros(h, &d.rdead, (size_t)t.n_rv * ((C + 31) / 32)));
+  CK(zeros(h, &d.fver, (size_t)std::max(d.n_sig, 1) * C));
+  CK(zeros(h, &d.cver, C));
   d.H = t.E + d.Cmax;
   CK(zeros(h, &d.host_cnt, (size_t)std::max(t.GH, 1) * d.H));
   for (int g = 0; g < t.GH; g++)
@@ -298,7 +316,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
       CK(cudaMemcpyAsync(d.host_cnt + (size_t)g * d.H, t.host_cnt_nodes.data() + (size_t)g * t.E,
                          (size_t)t.E * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   CK(zeros(h, &d.n_claims, 1));
-  CK(zeros(h, &d.counters, 8));
+  CK(zeros(h, &d.counters, 16));
   CK(zeros(h, &d.status, 1));
   return KP_OK;
 }
@@ -326,13 +344,15 @@ static int reset_dynamic(kp_handle* h) {
   size_t C = (size_t)d.Cmax;
   CK(cudaMemsetAsync(d.c_npods, 0, C * 4, h->stream));
   CK(cudaMemsetAsync(d.rdead, 0, (size_t)t.n_rv * ((C + 31) / 32) * 4, h->stream));
+  CK(cudaMemsetAsync(d.fver, 0, (size_t)std::max(d.n_sig, 1) * C * 4, h->stream));
+  CK(cudaMemsetAsync(d.cver, 0, C * 4, h->stream));
   CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)std::max(t.GH, 1) * d.H * 4, h->stream));
   for (int g = 0; g < t.GH; g++)
     if (t.E)
       CK(cudaMemcpyAsync(d.host_cnt + (size_t)g * d.H, t.host_cnt_nodes.data() + (size_t)g * t.E,
                          (size_t)t.E * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(d.n_claims, 0, 4, h->stream));
-  CK(cudaMemsetAsync(d.counters, 0, 64, h->stream));
+  CK(cudaMemsetAsync(d.counters, 0, 128, h->stream));
   CK(cudaMemsetAsync(d.status, 0, 4, h->stream));
   CK(cudaMemsetAsync(d.last_len, 0, (size_t)std::max<int64_t>(h->P, 1) * 4, h->stream));
   return KP_OK;
@@ -444,8 +464,12 @@ static int run_solve(kp_handle* h) {
     h->stats.kernel_launches += 6;
   }
   // shared-memory budget of the solve CTA: fixed part + mirrors of the first CS claims + dead bits
-  const size_t fixed = (sizeof(SolveShared) + 15) & ~(size_t)15;
-  const size_t budget = 200 * 1024;
+  d.n_ge = (int)h->host.ge_vals.size();
+  d.n_itv = std::max(h->host.itv_off[d.K], 1);
+  size_t tb = kp_tab_bytes(d);
+  d.tab_bytes = tb <= 110 * 1024 ? (int)tb : 0;  // too big: leave the tables in global memory (L2)
+  const size_t fixed = KP_ALIGN16(sizeof(SolveShared)) + (size_t)d.tab_bytes;
+  const size_t budget = 220 * 1024;
   int CS = d.Cmax;
   auto need = [&](int cs) { return fixed + (size_t)cs * 12 + (size_t)d.n_rv * ((cs + 31) / 32) * 4 + 64; };
   while (CS > 32 && need(CS) > budget) CS = (CS * 3 / 4) & ~31;
@@ -469,9 +493,13 @@ static int download(kp_handle* h, kp_result* out) {
   auto t0 = std::chrono::steady_clock::now();
   memset(out, 0, sizeof(*out));
   int32_t nclaims = 0;
-  int64_t counters[8];
+  int64_t counters[16];
   CK(cudaMemcpy(&nclaims, d.n_claims, 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(counters, d.counters, 64, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counters, d.counters, 128, cudaMemcpyDeviceToHost));
+  if (getenv("KP_DEBUG"))
+    fprintf(stderr, "[kp] slow_sorts=%lld cyc pop=%lld sort=%lld inflight=%lld rounds=%lld ctx_miss=%lld iters=%lld\n",
+            (long long)counters[4], (long long)counters[5], (long long)counters[6], (long long)counters[7],
+            (long long)counters[9], (long long)counters[10], (long long)counters[11]);
   int64_t P = h->P;
   int K = h->n_keys, R = h->n_resources, ITW = (h->n_its + 63) / 64;
   size_t C = (size_t)nclaims, c1 = C ? C : 1;

@@ -51,33 +51,32 @@ __device__ __forceinline__ uint64_t filter_its_word(const KpDev& d, const Slot* 
   // resources.Fits(total, allocatable) via ">= threshold" bitmaps: lane r ranks q[r]
   int j = 0;
   if (lane < R) {
-    const int64_t* vals = d.ge_vals + (size_t)lane * d.T;
-    int lo = 0, hi = d.ge_n[lane];
+    int lo = d.ge_off[lane], hi = d.ge_off[lane + 1];
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
-      if (vals[mid] < q_lane)
+      if (d.ge_vals[mid] < q_lane)
         lo = mid + 1;
       else
         hi = mid;
     }
-    j = lo;
+    j = lo == d.ge_off[lane + 1] ? -1 : lo;  // -1: the request exceeds every instance type
   }
   uint64_t fw = (lane < ITW) ? d.it_valid[lane] : 0ull;
   for (int r = 0; r < R; r++) {
     int jr = __shfl_sync(FULL, j, r);
-    if (lane < ITW) fw &= (jr < d.ge_n[r]) ? d.ge_bits[((size_t)r * d.T + jr) * ITW + lane] : 0ull;
+    if (lane < ITW) fw &= jr >= 0 ? d.ge_bits[(size_t)jr * ITW + lane] : 0ull;
   }
   *fits_word = fw;
   // hasOffering: lane dd decides Compatible(S, offering set dd, AllowUndefinedWellKnownLabels)
   bool off_ok = false;
   if (lane < d.D) {
-    int rs = d.offset_rs[lane];
-    uint32_t keys = d.rs_keys[rs];
+    uint32_t keys = d.off_keys[lane];
     off_ok = true;
     while (keys) {
       int k = __ffs(keys) - 1;
       keys &= keys - 1;
-      if (!slot_compatible(key_info(d, k), S[k], rs_slot(d, rs, k), d.key_wellknown[k], true)) off_ok = false;
+      if (!slot_compatible(key_info(d, k), S[k], d.off_slots[(size_t)lane * K + k], d.key_wellknown[k], true))
+        off_ok = false;
     }
   }
   uint32_t off_mask = __ballot_sync(FULL, off_ok);
@@ -101,7 +100,7 @@ __device__ __forceinline__ uint64_t filter_its_word(const KpDev& d, const Slot* 
         while (allowed) {
           int v = __ffsll((long long)allowed) - 1;
           allowed &= allowed - 1;
-          bw |= d.itv[((size_t)k * 64 + v) * ITW + lane];
+          bw |= d.itv[((size_t)d.itv_off[k] + v) * ITW + lane];
         }
       }
       if (op_is_negative(slot_op(s))) bw |= d.it_dne[(size_t)k * ITW + lane];
@@ -190,7 +189,7 @@ struct Eval {
 // The pod being placed, staged once per pod in shared memory (class row of the problem + its requirement slots).
 struct PodCtx {
   int pod, cls, tolset, rv;
-  int moff, mend, roff, rend;
+  int moff, mend, roff, rend, sig;
   unsigned long long tmpl_ok;  // bit n: template n's taints are tolerated (taints.go:49-66)
   int64_t req[KP_MAXR];
   Slot pod_slot[KP_MAXK];
@@ -274,14 +273,14 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
 // A class row in flight between global memory and the shared PodCtx (one warp; lane k: key k, lane r: resource r,
 // lane i < 8: header word i).
 struct ClassRegs {
-  int hdr;                // lanes 0..7: tolset, rv, moff, mend, roff, rend, class, pod
+  int hdr;                // lanes 0..8: tolset, rv, moff, mend, roff, rend, sig, class, pod
   unsigned long long tmpl_ok;
   int64_t req;
   Slot pod, strict;
 };
 __device__ __forceinline__ ClassRegs load_class_regs(const KpDev& d, int X, int pod, int lane) {
   ClassRegs c;
-  c.hdr = lane < 6 ? d.cr_hdr[(size_t)X * 6 + lane] : (lane == 6 ? X : pod);
+  c.hdr = lane < 7 ? d.cr_hdr[(size_t)X * 7 + lane] : (lane == 7 ? X : pod);
   c.tmpl_ok = lane == 0 ? d.cr_tmplok[X] : 0ull;
   c.req = lane < d.R ? d.cls_req[(size_t)X * d.R + lane] : 0;
   if (lane < d.K) {
@@ -295,16 +294,15 @@ __device__ __forceinline__ ClassRegs load_class_regs(const KpDev& d, int X, int 
   return c;
 }
 __device__ __forceinline__ void store_class_regs(const KpDev& d, PodCtx& px, const ClassRegs& c, int lane) {
-  int* hdr = &px.tolset;  // tolset, rv, moff, mend, roff, rend are consecutive ints
   if (lane == 0) px.tolset = c.hdr;
   if (lane == 1) px.rv = c.hdr;
   if (lane == 2) px.moff = c.hdr;
   if (lane == 3) px.mend = c.hdr;
   if (lane == 4) px.roff = c.hdr;
   if (lane == 5) px.rend = c.hdr;
-  if (lane == 6) px.cls = c.hdr;
-  if (lane == 7) px.pod = c.hdr;
-  (void)hdr;
+  if (lane == 6) px.sig = c.hdr;
+  if (lane == 7) px.cls = c.hdr;
+  if (lane == 8) px.pod = c.hdr;
   if (lane == 0) px.tmpl_ok = c.tmpl_ok;
   if (lane < d.R) px.req[lane] = c.req;
   if (lane < d.K) {

@@ -180,7 +180,10 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   for (int a = -1; a < p->n_tolsets; a++)
     for (int b = 0; b < p->n_taintsets; b++) h.tol_ok[(size_t)(a + 1) * p->n_taintsets + b] = c.tolerates(b, a);
   // ---- instance types ----
-  h.itv.assign((size_t)K * 64 * ITW, 0);
+  h.itv_off.assign(K + 1, 0);
+  for (int k = 0; k < K; k++)
+    h.itv_off[k + 1] = h.itv_off[k] + (k == h.hostname_key ? 0 : p->key_value_off[k + 1] - p->key_value_off[k]);
+  h.itv.assign((size_t)std::max(h.itv_off[K], 1) * ITW, 0);
   h.it_nokey.assign((size_t)K * ITW, 0);
   h.it_dne.assign((size_t)K * ITW, 0);
   h.it_nonempty.assign((size_t)K * ITW, 0);
@@ -205,7 +208,7 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
       }
       h.it_nonempty[(size_t)k * ITW + w] |= bit;
       for (int v = 0; v < 64; v++)
-        if (s.m >> v & 1) h.itv[((size_t)k * 64 + v) * ITW + w] |= bit;
+        if (s.m >> v & 1) h.itv[((size_t)h.itv_off[k] + v) * ITW + w] |= bit;
     }
     // Allocatable (types.go:198-216)
     uint32_t cp = p->it_cap_present ? p->it_cap_present[t] : ((1u << R) - 1);
@@ -227,22 +230,27 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
     }
     if (!neg) h.it_valid[w] |= bit;
   }
-  // ">= threshold" tables per resource
-  h.ge_vals.assign((size_t)R * std::max(T, 1), 0);
-  h.ge_n.assign(R, 0);
-  h.ge_bits.assign((size_t)R * std::max(T, 1) * std::max(ITW, 1), 0);
+  // ">= threshold" tables per resource (rows of all resources concatenated)
+  h.ge_off.assign(R + 1, 0);
+  h.ge_vals.clear();
+  h.ge_bits.clear();
   for (int r = 0; r < R; r++) {
     std::vector<int64_t> vals;
     for (int t = 0; t < T; t++) vals.push_back(h.it_alloc[(size_t)t * R + r]);
     std::sort(vals.begin(), vals.end());
     vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
-    h.ge_n[r] = (int)vals.size();
     for (size_t j = 0; j < vals.size(); j++) {
-      h.ge_vals[(size_t)r * T + j] = vals[j];
-      uint64_t* row = h.ge_bits.data() + ((size_t)r * T + j) * ITW;
+      h.ge_vals.push_back(vals[j]);
+      size_t base = h.ge_bits.size();
+      h.ge_bits.resize(base + ITW, 0);
       for (int t = 0; t < T; t++)
-        if (h.it_alloc[(size_t)t * R + r] >= vals[j]) row[t >> 6] |= 1ull << (t & 63);
+        if (h.it_alloc[(size_t)t * R + r] >= vals[j]) h.ge_bits[base + (t >> 6)] |= 1ull << (t & 63);
     }
+    h.ge_off[r + 1] = (int)h.ge_vals.size();
+  }
+  if (h.ge_vals.empty()) {
+    h.ge_vals.push_back(0);
+    h.ge_bits.assign(std::max(ITW, 1), 0);
   }
   // distinct offering requirement sets (by content of their slot rows)
   {
@@ -271,6 +279,12 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
     if (h.offset_rs.empty()) {
       h.offset_rs.push_back(0);
       h.offset_bits.assign(std::max(ITW, 1), 0);
+    }
+    h.off_slots.assign((size_t)std::max(h.D, 1) * K, Slot{0u, 0ull, 0, 0});
+    h.off_keys.assign(std::max(h.D, 1), 0);
+    for (int dd = 0; dd < h.D; dd++) {
+      h.off_keys[dd] = h.rs_keys[h.offset_rs[dd]];
+      for (int k = 0; k < K; k++) h.off_slots[(size_t)dd * K + k] = c.rs_slot(h.offset_rs[dd], k);
     }
   }
   // ---- templates ----

@@ -29,7 +29,9 @@ struct HostTables {
   std::vector<uint8_t> tol_ok;
   std::vector<uint64_t> itv, it_nokey, it_dne, it_nonempty, it_valid;
   std::vector<int64_t> ge_vals;
-  std::vector<int32_t> ge_n;
+  std::vector<int32_t> ge_off, itv_off;
+  std::vector<Slot> off_slots;
+  std::vector<uint32_t> off_keys;
   std::vector<uint64_t> ge_bits;
   std::vector<int32_t> offset_rs;
   std::vector<uint64_t> offset_bits;

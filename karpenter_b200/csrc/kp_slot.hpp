@@ -13,11 +13,6 @@
 #define KP_HD inline
 #endif
 
-struct Slot {
-  uint32_t f;   // SF_*
-  uint64_t m;   // values
-  int64_t gte, lte;
-};
 
 struct KeyInfo {  // integer reading of a key's values (strconv.Atoi, requirement.go:326-342)
   const int64_t* val_int;  // [64]

@@ -217,7 +217,22 @@ struct SolveShared {
   int ok[SOLVE_WARPS];
   PodCtx ctx[2];
   Slot scratch[SOLVE_WARPS][KP_MAXK];
+  KpDev ds;  // the table pointers, patched to the shared-memory copies of the small read-only tables
 };
+
+#define KP_ALIGN16(x) (((x) + 15) & ~(size_t)15)
+// bytes of the read-only tables k_solve stages in shared memory (same formula on host and device)
+__host__ __device__ inline size_t kp_tab_bytes(const KpDev& d) {
+  size_t K = d.K, R = d.R, ITW = d.ITW, D = d.D > 0 ? d.D : 1, N = d.N > 0 ? d.N : 1;
+  size_t b = 0;
+  b += KP_ALIGN16(K) + 2 * KP_ALIGN16(8 * K);                    // key_wellknown, key_univ, val_isint
+  b += KP_ALIGN16(4 * (R + 1)) + KP_ALIGN16(8 * (size_t)d.n_ge) + KP_ALIGN16(8 * (size_t)d.n_ge * ITW);
+  b += KP_ALIGN16(4 * (K + 1)) + KP_ALIGN16(8 * (size_t)d.n_itv * ITW);
+  b += 3 * KP_ALIGN16(8 * K * ITW) + KP_ALIGN16(8 * ITW);        // it_nokey, it_dne, it_nonempty, it_valid
+  b += KP_ALIGN16(sizeof(Slot) * D * K) + KP_ALIGN16(4 * D) + KP_ALIGN16(8 * D * ITW);
+  b += KP_ALIGN16(4 * N);
+  return b;
+}
 
 // n-th set bit over the per-warp ballot masks of a chunk (-1 if fewer); *total = number of set bits
 __device__ __forceinline__ int nth_candidate(const unsigned* masks, int n, int* total) {
@@ -233,13 +248,54 @@ __device__ __forceinline__ int nth_candidate(const unsigned* masks, int n, int* 
   return found;
 }
 
-__global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(const __grid_constant__ KpDev d_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SolveShared& sh = *reinterpret_cast<SolveShared*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- stage the small read-only tables (key universe, thresholds, bit-sliced instance-type rows, offering sets)
+  // in shared memory and keep a patched copy of the pointer block next to them
+  {
+    const int* src = reinterpret_cast<const int*>(&d_in);
+    int* dst = reinterpret_cast<int*>(&sh.ds);
+    for (int i = tid; i < (int)(sizeof(KpDev) / 4); i += SOLVE_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  unsigned char* tab = smem_raw + KP_ALIGN16(sizeof(SolveShared));
+  if (d_in.tab_bytes > 0) {
+    size_t off = 0;
+#define KP_STAGE(field, type, count)                                                            \
+  {                                                                                             \
+    size_t n_ = (size_t)(count);                                                                \
+    type* dst_ = reinterpret_cast<type*>(tab + off);                                            \
+    const type* src_ = d_in.field;                                                              \
+    for (size_t i_ = tid; i_ < n_; i_ += SOLVE_THREADS) dst_[i_] = src_[i_];                    \
+    if (tid == 0) sh.ds.field = dst_;                                                           \
+    off += KP_ALIGN16(sizeof(type) * n_);                                                       \
+  }
+    const size_t K_ = d_in.K, R_ = d_in.R, W_ = d_in.ITW, D_ = d_in.D > 0 ? d_in.D : 1, N_ = d_in.N > 0 ? d_in.N : 1;
+    KP_STAGE(key_wellknown, uint8_t, K_)
+    KP_STAGE(key_univ, uint64_t, K_)
+    KP_STAGE(val_isint, uint64_t, K_)
+    KP_STAGE(ge_off, int32_t, R_ + 1)
+    KP_STAGE(ge_vals, int64_t, d_in.n_ge)
+    KP_STAGE(ge_bits, uint64_t, (size_t)d_in.n_ge * W_)
+    KP_STAGE(itv_off, int32_t, K_ + 1)
+    KP_STAGE(itv, uint64_t, (size_t)d_in.n_itv * W_)
+    KP_STAGE(it_nokey, uint64_t, K_ * W_)
+    KP_STAGE(it_dne, uint64_t, K_ * W_)
+    KP_STAGE(it_nonempty, uint64_t, K_ * W_)
+    KP_STAGE(it_valid, uint64_t, W_)
+    KP_STAGE(off_slots, Slot, D_ * K_)
+    KP_STAGE(off_keys, uint32_t, D_)
+    KP_STAGE(offset_bits, uint64_t, D_ * W_)
+    KP_STAGE(tmpl_taintset, int32_t, N_)
+#undef KP_STAGE
+  }
+  __syncthreads();
+  const KpDev& d = sh.ds;
   const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, CS = d.CS;
   // shared mirrors (write-through) of the first CS claim positions / ids
-  int* order_s = reinterpret_cast<int*>(smem_raw + ((sizeof(SolveShared) + 15) & ~15));
+  int* order_s = reinterpret_cast<int*>(tab + d_in.tab_bytes);
   int* cnt_s = order_s + CS;
   int* tmpl_s = cnt_s + CS;
   uint32_t* rdead_s = reinterpret_cast<uint32_t*>(tmpl_s + CS);  // [n_rv * RWS]
@@ -291,9 +347,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
   int a_idx = -1, a_val = -1;
 
   long long watchdog = 0;
+  long long t_sort = 0, t_inflight = 0, t_new = 0, n_rounds = 0, n_ctx_miss = 0, t_pop = 0, t_mark = 0;
   for (;;) {
     __syncthreads();  // (S0) previous pod fully committed; prefetched rows visible
     const int h = sh.head;
+    t_mark = clock64();
     if (++watchdog > 4 * (long long)d.P + 1024) {  // cannot happen: every requeue cycle needs progress (queue.go:54-58)
       if (tid == 0) *d.status = KP_ERR_INVALID;
       break;
@@ -314,6 +372,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
     __syncthreads();  // (S1)
     if (sh.done) break;
     if (!have_ctx) {
+      n_ctx_miss++;
       if (warp == 0) {
         ClassRegs cr = load_class_regs(d, d.qcls[h % sh.cap], d.queue[h % sh.cap], lane);
         store_class_regs(d, sh.ctx[h & 1], cr, lane);
@@ -344,7 +403,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
     }
     const PodCtx& px = sh.ctx[h & 1];
     const int pod = px.pod;
-    const int tolset = px.tolset, rv = px.rv;
+    const int tolset = px.tolset, rv = px.rv, sig = px.sig;
     do {
 
     // ================= addToExistingNode (scheduler.go:520-555) =================
@@ -421,6 +480,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
     if (sh.found) break;
 
     // ================= sort.Slice(newNodeClaims, len(Pods) asc) (scheduler.go:504) =================
+    t_pop += clock64() - t_mark;
+    t_mark = clock64();
     const int nC = sh.n_claims;
     if (pert != PERT_NONE) {
       if (tid == 0) {
@@ -527,12 +588,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
     }
 
     // ================= addToInflightNode (scheduler.go:557-589) =================
+    t_sort += clock64() - t_mark;
+    t_mark = clock64();
     for (int base = 0; base < nC && !sh.found; base += SOLVE_THREADS) {
       int pos = base + tid;
       bool pass = false;
       if (pos < nC) {
         int c = ord(pos);
         pass = !is_rdead(rv, c) && ((px.tmpl_ok >> claim_tmpl(c)) & 1ull);
+        if (pass && sig >= 0) pass = d.fver[(size_t)sig * d.Cmax + c] != d.cver[c] + 1;  // known failure, claim unchanged
       }
       unsigned m = __ballot_sync(FULL, pass);
       if (lane == 0) sh.warp_mask[warp] = m;
@@ -544,6 +608,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
         Eval ev;
         ev.ok = false;
         ev.res_dead = false;
+        n_rounds++;
         int cpos = -1, cc = -1;
         if (off >= 0) {
           cpos = base + off;
@@ -557,6 +622,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
             atomicOr(&d.rdead[(size_t)rv * RW + (cc >> 5)], 1u << (cc & 31));
             if (cc < CS) atomicOr(&rdead_s[rv * RWS + (cc >> 5)], 1u << (cc & 31));
           }
+          if (!ev.ok && sig >= 0 && lane == 0) d.fver[(size_t)sig * d.Cmax + cc] = d.cver[cc] + 1;
         }
         if (lane == 0) sh.ok[warp] = ev.ok;
         __syncthreads();
@@ -578,6 +644,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
           if (lane < ITW) d.c_its[(size_t)cc * ITW + lane] = ev.its;
           if (lane == 0) {
             d.c_npods[cc]++;
+            d.cver[cc]++;
             set_ord(cpos, cc, cnt(cpos) + 1);
             d.pod_target[pod] = KP_TARGET_CLAIM(cc);
             d.pod_error[pod] = KP_PODERR_NONE;
@@ -599,9 +666,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
       else
         ev_inflight += nC;
     }
-    if (sh.found) break;
+    if (sh.found) {
+      t_inflight += clock64() - t_mark;
+      break;
+    }
 
     // ================= addToNewNodeClaim (scheduler.go:592-684) =================
+    t_inflight += clock64() - t_mark;
+    t_mark = clock64();
     int err = sh.alive_tmpl ? KP_PODERR_INCOMPATIBLE : KP_PODERR_NO_TEMPLATES;
     for (int n = 0; n < d.N && !sh.found; n++) {
       Eval ev;
@@ -734,5 +806,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(KpDev d) {
     d.counters[2] += ev_tmpl;
     d.counters[3] += commits;
     d.counters[4] += slow_sorts;
+    d.counters[5] = t_pop;
+    d.counters[6] = t_sort;
+    d.counters[7] = t_inflight;
+    d.counters[8] = t_new + (clock64() - t_mark) * 0;
+    d.counters[9] = n_rounds;
+    d.counters[10] = n_ctx_miss;
+    d.counters[11] = watchdog;
   }
 }

@@ -25,6 +25,13 @@
 #define OP_EXISTS 2
 #define OP_DNE 3
 
+// one scheduling.Requirement on a 64-value universe: {complement, values, gte, lte} (requirement.go:36-43)
+struct Slot {
+  uint32_t f;   // SF_*
+  uint64_t m;   // values
+  int64_t gte, lte;
+};
+
 struct KpGroup {
   int32_t key;          // label key, or -1 for the hostname key
   int32_t type;         // KP_TOPO_*
@@ -58,16 +65,20 @@ struct KpDev {
   // taints
   const uint8_t* tol_ok;          // [(n_tolsets+1) * n_taintsets], row tolset+1 (row 0 == no tolerations)
   // instance types (bit-sliced)
-  const uint64_t* itv;            // [K*64*ITW] types whose In-set on key k contains value v
+  const int32_t* itv_off;         // [K+1] prefix of value counts: row of (k, v) is itv_off[k] + v
+  const uint64_t* itv;            // [itv_off[K]*ITW] types whose In-set on key k contains value v
   const uint64_t* it_nokey;       // [K*ITW] types that do not define key k
   const uint64_t* it_dne;         // [K*ITW] types whose slot on k is the empty concrete set
   const uint64_t* it_nonempty;    // [K*ITW] types with a non-empty In-set on k
   const uint64_t* it_valid;       // [ITW] types without a negative allocatable entry
-  const int64_t* ge_vals;         // [R*T] ascending distinct allocatable values per resource
-  const int32_t* ge_n;            // [R] number of distinct values
-  const uint64_t* ge_bits;        // [R*T*ITW] ge_bits[r][j] = types with alloc[r] >= ge_vals[r][j]
-  const int32_t* offset_rs;       // [D] distinct offering requirement sets
+  const int32_t* ge_off;          // [R+1] rows of resource r are ge_off[r] .. ge_off[r+1]
+  const int64_t* ge_vals;         // [ge_off[R]] ascending distinct allocatable values per resource
+  const uint64_t* ge_bits;        // [ge_off[R]*ITW] row j = types with alloc[r] >= ge_vals[j]
+  const Slot* off_slots;          // [D*K] requirement slots of the distinct offering requirement sets
+  const uint32_t* off_keys;       // [D] keys present in each set
   const uint64_t* offset_bits;    // [D*ITW] types with an AVAILABLE offering of that set
+  int tab_bytes;                  // shared-memory bytes of the staged read-only tables (k_solve); 0 = not staged
+  int n_ge, n_itv;                // rows of ge_vals / itv
   const int64_t* it_capacity;     // [T*R] (limits)
   // templates
   const int32_t* tmpl_rs;         // [N]
@@ -90,7 +101,7 @@ struct KpDev {
   const int32_t* cls_rec_off;     // [X+1] groups that may count the class on Record (select it / inverse owned)
   const int32_t* cls_rec;
   // class rows, one level of indirection for the per-pod staging (header: tolset, rv, match/record list ranges)
-  const int32_t* cr_hdr;          // [X*6]
+  const int32_t* cr_hdr;          // [X*7] tolset, rv, moff, mend, roff, rend, sig
   const uint64_t* cr_tmplok;      // [X] bit n: template n tolerated
   const uint8_t* cp_f;            // [X*K] PodData.Requirements slots
   const uint64_t* cp_m;
@@ -134,6 +145,11 @@ struct KpDev {
   int32_t* order;                 // [Cmax] s.newNodeClaims as claim ids
   int32_t* cnt_at;                // [Cmax] len(Pods) by position
   uint32_t* rdead;                // [n_rv * ceil(Cmax/32)] claim can never again fit this request vector
+  // exact failure cache: CanAdd of a topology-free class on a NodeClaim is a pure function of (class requirements,
+  // class requests, claim state); a recorded failure stays valid until the claim changes (its version moves on)
+  int n_sig;
+  uint32_t* fver;                 // [n_sig * Cmax] claim version + 1 at which the signature failed (0 = never)
+  uint32_t* cver;                 // [Cmax] claim version: number of pods committed to it
   // pods
   int64_t P;
   const int32_t* pod_class;       // [P]
