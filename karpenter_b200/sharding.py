@@ -1,0 +1,83 @@
+"""NodePool sharding of a provisioning job across ranks.
+
+The reference's Solve shards exactly when (i) every pod is compatible with exactly one NodePool and (ii) no topology
+group's selected pods span two pools (scheduler.go:565,602; topology.go:53,58).  Then rank r owns the pods, the template
+and the NodeClaims of its pools and runs an ordinary, independent Scheduler.Solve; the only exchange is one all-reduce
+(sum, int32) of the topology-domain counter table so that every rank ends with the global counters the next
+provisioning round starts from.  No collective sits on the data path.
+
+Sharding is bit-exact against the un-sharded solve under the *stable* claim order (`claim_order_mode = 1`): a stable
+sort of the whole NodeClaim list restricted to one pool's claims is the stable sort of that pool's claims alone.  Go's
+unstable `sort.Slice` (mode 0) permutes ties depending on the entire slice, so there a shard is defined as "the
+reference run on that pool's pods" -- each shard is still bit-identical to the reference solver on its own input.
+
+This module is plain host logic (numpy + torch.distributed); it is exercised on CPU with the gloo backend
+(tests/test_sharding_gloo.py) and on GPUs with NCCL by bench.py.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import numpy as np
+
+
+def pools_of_rank(n_pools: int, rank: int, world: int) -> List[int]:
+    """Round-robin NodePool -> rank map (pool i lives on rank i mod world)."""
+    return [i for i in range(n_pools) if i % world == rank]
+
+
+def counter_layout(group_sizes_per_rank: Sequence[Sequence[int]]):
+    """Global layout of the [G x D] domain-counter table: the per-rank tables concatenated in rank order.
+    Returns (offset of every rank's slice, total length)."""
+    offs, total = [], 0
+    for sizes in group_sizes_per_rank:
+        offs.append(total)
+        total += int(sum(sizes))
+    return offs, total
+
+
+def allreduce_domain_counts(result: dict, rank: int, world: int, dist=None, device=None) -> np.ndarray:
+    """The single collective of the sharded job: every rank contributes its shard's domain counters (zeros elsewhere)
+    and receives the global table.  `result` is the dict of one shard's kp_solve (karpenter_b200/_abi.py)."""
+    import torch
+    local = np.ascontiguousarray(result["domain_counts"], dtype=np.int32)
+    if world == 1 or dist is None:
+        return local.copy()
+    # slice sizes differ by rank: exchange them first (tiny all-gather), then one sum all-reduce of the table
+    n = torch.tensor([local.size], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    offs, total = counter_layout([[s] for s in sizes])
+    table = torch.zeros(max(total, 1), dtype=torch.int32, device=device)
+    if local.size:
+        table[offs[rank]:offs[rank] + local.size] = torch.from_numpy(local).to(table.device)
+    dist.all_reduce(table, op=dist.ReduceOp.SUM)
+    return table[:total].cpu().numpy()
+
+
+def merge_shards(shards: Sequence[dict], pod_index: Sequence[np.ndarray], n_pods: int,
+                 template_index: Sequence[Sequence[int]]) -> Dict[str, np.ndarray]:
+    """Host-side concat of per-shard results into the global NodeClaim set (what a gather to rank 0 produces).
+    pod_index[r][i] = global row of shard r's pod i; template_index[r][n] = global NodePool index of shard r's template n.
+    NodeClaims are renumbered shard by shard (claim k of shard r -> base_r + k)."""
+    target = np.full(n_pods, -1, np.int32)
+    error = np.zeros(n_pods, np.uint8)
+    tmpl, npods, reqs, its = [], [], [], []
+    base = 0
+    for r, res in enumerate(shards):
+        t = res["pod_target"].copy()
+        is_claim = t <= -2
+        t[is_claim] -= base
+        target[pod_index[r]] = t
+        error[pod_index[r]] = res["pod_error"]
+        tmpl.append(np.asarray(template_index[r], np.int32)[res["claim_template"]])
+        npods.append(res["claim_npods"])
+        reqs.append(res["claim_requests"])
+        its.append(res["claim_its"])
+        base += int(res["n_claims"])
+    return {"pod_target": target, "pod_error": error, "n_claims": base,
+            "claim_template": np.concatenate(tmpl) if tmpl else np.zeros(0, np.int32),
+            "claim_npods": np.concatenate(npods) if npods else np.zeros(0, np.int32),
+            "claim_requests": np.concatenate(reqs) if reqs else np.zeros((0, 0), np.int64),
+            "claim_its": np.concatenate(its) if its else np.zeros((0, 0), np.uint64)}
