@@ -15,7 +15,6 @@
 
 #include "kp_consolidate.cuh"
 #include "kp_prep.hpp"
-#include "kp_solve.cuh"
 
 #define CK(call)                                                                                     \
   do {                                                                                               \
@@ -64,6 +63,9 @@ struct kp_handle {
   int64_t* d_pod_creation = nullptr;
   uint64_t *d_uid_hi = nullptr, *d_uid_lo = nullptr;
   int64_t* d_class_rank = nullptr;
+  int32_t *d_nsig_rs = nullptr, *d_nsig_tolset = nullptr;
+  int64_t* d_rv_req = nullptr;
+  int strict_undefined = 0;
   kp_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -119,6 +121,8 @@ __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
+
+static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_consol_input* in, kp_consol_result* out);
 
 extern "C" {
 
@@ -221,16 +225,38 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(up(h, &d.cls_rec_off, t.cls_rec_off));
   CK(up(h, &d.cls_rec, t.cls_rec));
   {  // class rows (one indirection less on the per-pod path)
-    std::vector<int32_t> hdr((size_t)std::max(t.X, 1) * 7, 0);
-    std::map<std::pair<int, int>, int> sigs;
+    std::vector<int32_t> hdr((size_t)std::max(t.X, 1) * KP_HDR, 0);
+    std::map<std::pair<int, int>, int> fsigs, nsigs;
+    std::vector<int32_t> nsig_rs, nsig_tolset;
+    std::vector<int4> hchk;
     std::vector<uint64_t> tok(std::max(t.X, 1), 0);
     size_t XK = (size_t)std::max(t.X, 1) * t.K;
     std::vector<uint8_t> pf(XK, 0), sf(XK, 0);
     std::vector<uint64_t> pm(XK, 0), sm(XK, 0);
     std::vector<int64_t> pg(XK, 0), pl(XK, 0), sg(XK, 0), sl(XK, 0);
     if (t.N > 64) return h->err = "more than 64 NodePools", KP_ERR_CAPACITY;
+    // A key a NodeClaim does not define makes Compatible fail (requirements.go:181-197) until some pod with a NotIn /
+    // DoesNotExist requirement defines it -- the one way CanAdd can flip from false to true for a topology-free pod.
+    // It cannot happen for a row whose positive keys are all well-known (AllowUndefinedWellKnownLabels) or defined by
+    // every NodePool template; only such rows get a permanent failure bit.
+    auto row_monotone = [&](int rs) {
+      for (int k = 0; k < t.K; k++) {
+        size_t i = (size_t)rs * t.K + k;
+        Slot sl_{t.rs_flags[i], t.rs_mask[i], t.rs_gte[i], t.rs_lte[i]};
+        if (!slot_present(sl_) || op_is_negative(slot_op(sl_)) || t.key_wellknown[k]) continue;
+        for (int n = 0; n < t.N; n++)
+          if (!(t.rs_flags[(size_t)t.tmpl_rs[n] * t.K + k] & SF_PRESENT)) return false;
+      }
+      return true;
+    };
+    bool offerings_monotone = true;
+    for (int dd = 0; dd < t.D; dd++) offerings_monotone = offerings_monotone && row_monotone(t.offset_rs[dd]);
+    // can a pod ever define a new key on an existing node? (negative requirement on an undefined key, or a topology
+    // domain choice) -- if not, an undefined key fails the strict Compatible of existingnode.go:89 forever
+    bool nodes_gain_keys = false;
+    for (int g = 0; g < t.G; g++) nodes_gain_keys = nodes_gain_keys || t.groups[g].key != t.hostname_key;
     for (int x = 0; x < t.X; x++) {
-      int32_t* hh = &hdr[(size_t)x * 7];
+      int32_t* hh = &hdr[(size_t)x * KP_HDR];
       hh[0] = t.cls_tolset[x];
       hh[1] = t.cls_rv[x];
       hh[2] = t.cls_match_off[x];
@@ -238,11 +264,33 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
       hh[4] = t.cls_rec_off[x];
       hh[5] = t.cls_rec_off[x + 1];
       hh[6] = -1;
-      if (t.cls_match_off[x + 1] == t.cls_match_off[x]) {  // topology-free: CanAdd is a pure function of the claim
+      if (t.cls_match_off[x + 1] == t.cls_match_off[x] && offerings_monotone && row_monotone(t.cls_rs[x])) {
         auto key = std::make_pair(t.cls_rs[x], t.cls_rv[x]);
-        auto it = sigs.find(key);
-        if (it == sigs.end()) it = sigs.emplace(key, (int)sigs.size()).first;
+        auto it = fsigs.find(key);
+        if (it == fsigs.end()) it = fsigs.emplace(key, (int)fsigs.size()).first;
         hh[6] = it->second;
+      }
+      {
+        auto key = std::make_pair(t.cls_rs[x], t.cls_tolset[x]);
+        auto it = nsigs.find(key);
+        if (it == nsigs.end()) {
+          it = nsigs.emplace(key, (int)nsigs.size()).first;
+          nsig_rs.push_back(t.cls_rs[x]);
+          nsig_tolset.push_back(t.cls_tolset[x]);
+        }
+        hh[7] = it->second;
+      }
+      hh[8] = (int)hchk.size();
+      for (int i = t.cls_match_off[x]; i < t.cls_match_off[x + 1]; i++) {
+        int e = t.cls_match[i], g = e & 0x3fffffff, self = (e >> 30) & 1;
+        const KpGroup& G = t.groups[g];
+        if (G.key == t.hostname_key) hchk.push_back(int4{G.host_row, G.type | (self << 8), G.max_skew, g});
+      }
+      hh[9] = (int)hchk.size();
+      for (int k = 0; k < t.K; k++) {
+        size_t i = (size_t)t.cls_rs[x] * t.K + k;
+        Slot sl_{t.rs_flags[i], t.rs_mask[i], t.rs_gte[i], t.rs_lte[i]};
+        if (slot_present(sl_) && op_is_negative(slot_op(sl_))) nodes_gain_keys = true;
       }
       for (int n = 0; n < t.N; n++) {
         int ts = t.tmpl_taintset[n];
@@ -261,11 +309,35 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
         sl[o] = t.rs_lte[b];
       }
     }
-    d.n_sig = (int)sigs.size();
-    if ((size_t)d.n_sig * (size_t)cmax_hint > (1ull << 28)) {  // cache would not fit comfortably: run without it
-      for (int x = 0; x < t.X; x++) hdr[(size_t)x * 7 + 6] = -1;
-      d.n_sig = 0;
+    d.n_fsig = (int)fsigs.size();
+    d.n_nsig = (int)nsigs.size();
+    d.EW = (t.E + 31) / 32;
+    h->strict_undefined = nodes_gain_keys ? 0 : 1;
+    if (hchk.empty()) hchk.push_back(int4{0, 0, 0, 0});
+    if (nsig_rs.empty()) {
+      nsig_rs.push_back(0);
+      nsig_tolset.push_back(-1);
     }
+    std::vector<int64_t> rv_req((size_t)std::max(t.n_rv, 1) * t.R, 0);
+    for (int x = 0; x < t.X; x++)
+      for (int r = 0; r < t.R; r++) rv_req[(size_t)t.cls_rv[x] * t.R + r] = t.cls_req[(size_t)x * t.R + r];
+    {
+      const int32_t *a_, *b_;
+      const int64_t* c_;
+      CK(up(h, &a_, nsig_rs));
+      CK(up(h, &b_, nsig_tolset));
+      CK(up(h, &c_, rv_req));
+      h->d_nsig_rs = const_cast<int32_t*>(a_);
+      h->d_nsig_tolset = const_cast<int32_t*>(b_);
+      h->d_rv_req = const_cast<int64_t*>(c_);
+    }
+    CK(up(h, &d.cls_hchk, hchk));
+    std::vector<uint32_t> nact(std::max(d.EW, 1), 0);
+    for (int n = 0; n < t.E; n++)
+      if (t.node_flags[n] & KP_NODE_SCHEDULABLE) nact[n >> 5] |= 1u << (n & 31);
+    CK(up_mut(h, &d.nactive, nact));
+    CK(zeros(h, &d.nfit, (size_t)std::max(t.n_rv, 1) * std::max(d.EW, 1)));
+    CK(zeros(h, &d.nstat, (size_t)std::max(d.n_nsig, 1) * std::max(d.EW, 1)));
     CK(up(h, &d.cr_hdr, hdr));
     CK(up(h, &d.cr_tmplok, tok));
     CK(up(h, &d.cp_f, pf));
@@ -307,8 +379,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(zeros(h, &d.order, C));
   CK(zeros(h, &d.cnt_at, C));
   CK(zeros(h, &d.rdead, (size_t)t.n_rv * ((C + 31) / 32)));
-  CK(zeros(h, &d.fver, (size_t)std::max(d.n_sig, 1) * C));
-  CK(zeros(h, &d.cver, C));
+  CK(zeros(h, &d.fail, (size_t)std::max(d.n_fsig, 1) * ((C + 31) / 32)));
   d.H = t.E + d.Cmax;
   CK(zeros(h, &d.host_cnt, (size_t)std::max(t.GH, 1) * d.H));
   for (int g = 0; g < t.GH; g++)
@@ -344,8 +415,7 @@ static int reset_dynamic(kp_handle* h) {
   size_t C = (size_t)d.Cmax;
   CK(cudaMemsetAsync(d.c_npods, 0, C * 4, h->stream));
   CK(cudaMemsetAsync(d.rdead, 0, (size_t)t.n_rv * ((C + 31) / 32) * 4, h->stream));
-  CK(cudaMemsetAsync(d.fver, 0, (size_t)std::max(d.n_sig, 1) * C * 4, h->stream));
-  CK(cudaMemsetAsync(d.cver, 0, C * 4, h->stream));
+  CK(cudaMemsetAsync(d.fail, 0, (size_t)std::max(d.n_fsig, 1) * ((C + 31) / 32) * 4, h->stream));
   CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)std::max(t.GH, 1) * d.H * 4, h->stream));
   for (int g = 0; g < t.GH; g++)
     if (t.E)
@@ -427,6 +497,53 @@ int kp_upload(kp_handle* h, const kp_problem* p) {
   return do_upload(h, p, (int)std::max<int64_t>(guess, 1));
 }
 
+// NewQueue: sort pods cpu desc, mem desc, creation asc, uid asc (queue.go:37-43) into d.queue / d.qcls.
+// Four LSD passes of a stable radix sort (cub), each on a gathered 64-bit key.
+static int sort_queue(kp_handle* h) {
+  KpDev& d = h->dev;
+  const int64_t P = h->P;
+  if (P <= 0) return KP_OK;
+  auto pol = thrust::cuda::par.on(h->stream);
+  thrust::device_ptr<int32_t> perm(d.queue);
+  thrust::sequence(pol, perm, perm + P);
+  int64_t* keys;
+  CK(cudaMallocAsync(&keys, P * 8, h->stream));
+  thrust::device_ptr<int64_t> k64(keys);
+  thrust::device_ptr<uint64_t> ku64((uint64_t*)keys);
+  int nb = (int)((P + 255) / 256);
+  k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_lo, d.queue, P, (uint64_t*)keys);
+  thrust::stable_sort_by_key(pol, ku64, ku64 + P, perm);
+  k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_hi, d.queue, P, (uint64_t*)keys);
+  thrust::stable_sort_by_key(pol, ku64, ku64 + P, perm);
+  k_gather<<<nb, 256, 0, h->stream>>>(h->d_pod_creation, d.queue, P, keys);
+  thrust::stable_sort_by_key(pol, k64, k64 + P, perm);
+  k_sort_keys<<<nb, 256, 0, h->stream>>>(d.pod_class, h->d_class_rank, d.queue, P, keys);
+  thrust::stable_sort_by_key(pol, k64, k64 + P, perm);
+  CK(cudaFreeAsync(keys, h->stream));
+  k_gather<<<nb, 256, 0, h->stream>>>(d.pod_class, d.queue, P, d.qcls);
+  h->stats.kernel_launches += 5;
+  return KP_OK;
+}
+
+// shared-memory plan of a kernel that stages the read-only tables: returns the table bytes to stage (0 = leave in L2)
+static size_t plan_tables(kp_handle* h, size_t fixed, size_t budget) {
+  KpDev& d = h->dev;
+  d.n_ge = (int)h->host.ge_vals.size();
+  d.n_itv = std::max(h->host.itv_off[d.K], 1);
+  size_t tb = kp_tab_bytes(d);
+  d.tab_bytes = (fixed + tb <= budget && tb <= 110 * 1024) ? (int)tb : 0;
+  return (size_t)d.tab_bytes;
+}
+
+static int launch_node_cand(kp_handle* h) {
+  KpDev& d = h->dev;
+  if (d.E <= 0) return KP_OK;
+  dim3 grid((d.E + 255) / 256, d.n_nsig + d.n_rv);
+  k_node_cand<<<grid, 256, 0, h->stream>>>(d, h->d_nsig_rs, h->d_nsig_tolset, h->d_rv_req, h->strict_undefined);
+  h->stats.kernel_launches++;
+  return KP_OK;
+}
+
 static int run_solve(kp_handle* h) {
   KpDev& d = h->dev;
   cudaSetDevice(h->device);
@@ -440,44 +557,25 @@ static int run_solve(kp_handle* h) {
     k_feasibility<<<(d.N * 32 + 255) / 256, 256, 0, h->stream>>>(d, nullptr, 1);
     h->stats.kernel_launches++;
   }
-  // NewQueue: sort pods cpu desc, mem desc, creation asc, uid asc (queue.go:37-43). LSD passes of a stable sort.
+  rc = sort_queue(h);
+  if (rc != KP_OK) return rc;
   if (P > 0) {
-    auto pol = thrust::cuda::par.on(h->stream);
-    thrust::device_ptr<int32_t> perm(d.queue);
-    thrust::sequence(pol, perm, perm + P);
-    int64_t* keys;
-    CK(cudaMallocAsync(&keys, P * 8, h->stream));
-    thrust::device_ptr<int64_t> k64(keys);
-    thrust::device_ptr<uint64_t> ku64((uint64_t*)keys);
-    int nb = (int)((P + 255) / 256);
-    k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_lo, d.queue, P, (uint64_t*)keys);
-    thrust::stable_sort_by_key(pol, ku64, ku64 + P, perm);
-    k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_hi, d.queue, P, (uint64_t*)keys);
-    thrust::stable_sort_by_key(pol, ku64, ku64 + P, perm);
-    k_gather<<<nb, 256, 0, h->stream>>>(h->d_pod_creation, d.queue, P, keys);
-    thrust::stable_sort_by_key(pol, k64, k64 + P, perm);
-    k_sort_keys<<<nb, 256, 0, h->stream>>>(d.pod_class, h->d_class_rank, d.queue, P, keys);
-    thrust::stable_sort_by_key(pol, k64, k64 + P, perm);
-    CK(cudaFreeAsync(keys, h->stream));
-    k_gather<<<nb, 256, 0, h->stream>>>(d.pod_class, d.queue, P, d.qcls);
-    k_fill_i32<<<nb, 256, 0, h->stream>>>(d.pod_target, P, KP_TARGET_UNSCHEDULED);
-    h->stats.kernel_launches += 6;
+    k_fill_i32<<<(int)((P + 255) / 256), 256, 0, h->stream>>>(d.pod_target, P, KP_TARGET_UNSCHEDULED);
+    h->stats.kernel_launches++;
   }
-  // shared-memory budget of the solve CTA: fixed part + mirrors of the first CS claims + dead bits
-  d.n_ge = (int)h->host.ge_vals.size();
-  d.n_itv = std::max(h->host.itv_off[d.K], 1);
-  size_t tb = kp_tab_bytes(d);
-  d.tab_bytes = tb <= 110 * 1024 ? (int)tb : 0;  // too big: leave the tables in global memory (L2)
-  const size_t fixed = KP_ALIGN16(sizeof(SolveShared)) + (size_t)d.tab_bytes;
-  const size_t budget = 220 * 1024;
-  int CS = d.Cmax;
-  auto need = [&](int cs) { return fixed + (size_t)cs * 12 + (size_t)d.n_rv * ((cs + 31) / 32) * 4 + 64; };
-  while (CS > 32 && need(CS) > budget) CS = (CS * 3 / 4) & ~31;
-  if (need(CS) > budget) return h->err = "shared-memory budget exceeded (too many distinct request vectors)", KP_ERR_CAPACITY;
-  d.CS = CS;
-  size_t smem = need(CS);
-  CK(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_solve<<<1, SOLVE_THREADS, smem, h->stream>>>(d);
+  rc = launch_node_cand(h);
+  if (rc != KP_OK) return rc;
+  // shared memory of the solve CTA: pointer block + staged tables + (when they fit) claim order, template ids and
+  // the failure bitmaps
+  const size_t budget = 224 * 1024;
+  const size_t fixed = KP_ALIGN16(sizeof(WSolveShared));
+  size_t tb = plan_tables(h, fixed, budget);
+  const size_t RW = ((size_t)d.Cmax + 31) / 32;
+  const size_t small = (size_t)d.Cmax * 12 + ((size_t)d.n_rv + (size_t)std::max(d.n_fsig, 1)) * RW * 4;
+  int small_in_smem = fixed + tb + small + 64 <= budget;
+  size_t smem = fixed + tb + (small_in_smem ? small : 0) + 64;
+  CK(cudaFuncSetAttribute(k_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_wsolve<<<1, 32, smem, h->stream>>>(d, small_in_smem);
   h->stats.kernel_launches++;
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -496,10 +594,7 @@ static int download(kp_handle* h, kp_result* out) {
   int64_t counters[16];
   CK(cudaMemcpy(&nclaims, d.n_claims, 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(counters, d.counters, 128, cudaMemcpyDeviceToHost));
-  if (getenv("KP_DEBUG"))
-    fprintf(stderr, "[kp] slow_sorts=%lld cyc pop=%lld sort=%lld inflight=%lld rounds=%lld ctx_miss=%lld iters=%lld\n",
-            (long long)counters[4], (long long)counters[5], (long long)counters[6], (long long)counters[7],
-            (long long)counters[9], (long long)counters[10], (long long)counters[11]);
+  if (getenv("KP_DEBUG")) fprintf(stderr, "[kp] slow_sorts=%lld\n", (long long)counters[4]);
   int64_t P = h->P;
   int K = h->n_keys, R = h->n_resources, ITW = (h->n_its + 63) / 64;
   size_t C = (size_t)nclaims, c1 = C ? C : 1;
@@ -663,11 +758,214 @@ void kp_consol_result_free(kp_consol_result* r) {
 }
 }
 
-static int kp_consolidate_impl(kp_handle* h, const kp_problem* cluster, const kp_consol_input* in,
-                               kp_consol_result* out) {
-  (void)cluster;
-  (void)in;
-  (void)out;
-  h->err = "consolidation kernel not built yet";
-  return KP_ERR_UNSUPPORTED;
+__global__ void k_scatter_rank(const int32_t* perm, int64_t n, int32_t* rank) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) rank[perm[i]] = (int32_t)i;
+}
+
+// kp_consolidate: every subset is one SimulateScheduling + computeConsolidation (helpers.go:51-142,
+// consolidation.go:136-229); they are independent, so each runs as its own solver instance on its own warp.
+static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_consol_input* in, kp_consol_result* out) {
+  memset(out, 0, sizeof(*out));
+  const int S = in->n_subsets;
+  int rc = do_upload(h, p, 1);  // the cluster's pod table doubles as the "pods" of the problem (rows by node)
+  if (rc != KP_OK) return rc;
+  HostTables& t = h->host;
+  KpDev& d = h->dev;
+  if (t.G > 0) return h->err = "consolidation with topology constraints is not built yet", KP_ERR_UNSUPPORTED;
+  const int K = t.K, R = t.R, ITW = t.ITW, E = t.E, N = t.N, T = t.T;
+  auto t_begin = std::chrono::steady_clock::now();
+  // ---- host-side constants of the decision step
+  auto ki = [&](int k) { return KeyInfo{t.val_int.data() + (size_t)k * 64, t.val_isint[k], t.key_univ[k]}; };
+  auto rs_slot_h = [&](int rs, int k) {
+    size_t i = (size_t)rs * K + k;
+    return Slot{t.rs_flags[i], t.rs_mask[i], t.rs_gte[i], t.rs_lte[i]};
+  };
+  std::vector<double> node_price(std::max(E, 1), -1.0);  // getCandidatePrices (consolidation.go:319-337)
+  for (int n = 0; n < E; n++) {
+    int it = in->node_it[n];
+    if (it < 0) continue;
+    bool any = false;
+    double best = 0;
+    for (int o = p->it_off_off[it]; o < p->it_off_off[it + 1]; o++) {
+      bool ok = true;
+      for (int k = 0; k < K && ok; k++)
+        ok = slot_compatible(ki(k), rs_slot_h(p->node_reqset[n], k), rs_slot_h(p->off_reqset[o], k), t.key_wellknown[k], true);
+      if (!ok) continue;
+      if (!any || p->off_price[o] < best) best = p->off_price[o];
+      any = true;
+    }
+    if (any) node_price[n] = best;
+  }
+  const int ct_order[3] = {in->ct_reserved, in->ct_spot, in->ct_on_demand};
+  int ct_valid = 0;
+  std::vector<uint8_t> ctmask(std::max(t.D, 1), 0);
+  for (int i = 0; i < 3; i++) {
+    if (in->capacity_type_key < 0 || ct_order[i] < 0) continue;
+    ct_valid |= 1 << i;
+    for (int dd = 0; dd < t.D; dd++) {
+      bool ok = true;
+      for (int k = 0; k < K && ok; k++) {
+        Slot ex = k == in->capacity_type_key ? Slot{SF_PRESENT, 1ull << ct_order[i], 0, 0} : Slot{0u, 0ull, 0, 0};
+        ok = slot_compatible(ki(k), ex, t.off_slots[(size_t)dd * K + k], t.key_wellknown[k], true);
+      }
+      if (ok) ctmask[dd] |= 1 << i;
+    }
+  }
+  int capq = 1;
+  for (int s = 0; s < S; s++) {
+    int n = 0;
+    for (int i = in->subset_off[s]; i < in->subset_off[s + 1]; i++) {
+      int node = in->subset_nodes[i];
+      if (node < 0 || node >= E) return h->err = "subset node out of range", KP_ERR_INVALID;
+      n += in->node_pod_off[node + 1] - in->node_pod_off[node];
+    }
+    capq = std::max(capq, n);
+  }
+  // ---- device inputs
+  KpConsol q;
+  memset(&q, 0, sizeof(q));
+  q.n_subsets = S;
+  q.capq = capq;
+  q.ct_key = in->capacity_type_key;
+  q.ct_spot = in->ct_spot;
+  q.ct_order_valid = ct_valid;
+  q.spot_to_spot_enabled = in->spot_to_spot_enabled;
+  int n_sub_nodes = S ? in->subset_off[S] : 0;
+  int n_off = T ? p->it_off_off[T] : 0;
+  int32_t* tmp32;
+  CK(up_raw(h, &tmp32, in->subset_off, (size_t)S + 1));
+  q.subset_off = tmp32;
+  CK(up_raw(h, &tmp32, in->subset_nodes, (size_t)n_sub_nodes));
+  q.subset_nodes = tmp32;
+  CK(up_raw(h, &tmp32, in->node_pod_off, (size_t)E + 1));
+  q.node_pod_off = tmp32;
+  q.pod_class = h->d_pod_class;
+  CK(zeros(h, &tmp32, (size_t)std::max<int64_t>(h->P, 1)));
+  int32_t* d_rank = tmp32;
+  q.pod_rank = d_rank;
+  CK(up(h, &q.node_price, node_price));
+  {
+    uint8_t* u8;
+    CK(up_raw(h, &u8, in->node_is_spot, (size_t)E));
+    q.node_is_spot = u8;
+    std::vector<int32_t> ntm(std::max(E, 1), -1);
+    std::vector<int64_t> ncap((size_t)std::max(E, 1) * R, 0);
+    for (int n = 0; n < E; n++) {
+      ntm[n] = p->node_template ? p->node_template[n] : -1;
+      if (p->node_capacity)
+        for (int r = 0; r < R; r++) ncap[(size_t)n * R + r] = p->node_capacity[(size_t)n * R + r];
+    }
+    CK(up(h, &q.node_tmpl, ntm));
+    CK(up(h, &q.node_capacity, ncap));
+    CK(up(h, &q.tmpl_remaining0, t.tmpl_remaining));
+    CK(up_raw(h, &tmp32, p->it_off_off, (size_t)T + 1));
+    q.it_off_off = tmp32;
+    CK(up(h, &q.off_set, t.off_set));
+    double* dd_;
+    CK(up_raw(h, &dd_, p->off_price, (size_t)n_off));
+    q.off_price = dd_;
+    CK(up_raw(h, &u8, p->off_available, (size_t)n_off));
+    q.off_available = u8;
+    CK(up(h, &q.offset_ctmask, ctmask));
+  }
+  // ---- launch geometry: as many resident warps as the GPU holds, each with a private scratch slot
+  const size_t budget = 200 * 1024;
+  const size_t fixed = KP_ALIGN16(sizeof(ConsolShared));
+  size_t tb = plan_tables(h, fixed, budget);
+  size_t smem = fixed + tb + 64;
+  CK(cudaFuncSetAttribute(k_consolidate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1, n_sm = 148;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_consolidate, CONSOL_WARPS * 32, smem);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+  per_sm = std::max(per_sm, 1);
+  int grid = std::min(n_sm * per_sm, std::max(1, (S + CONSOL_WARPS - 1) / CONSOL_WARPS));
+  const size_t slots = (size_t)grid * CONSOL_WARPS, cq = (size_t)capq, RWc = (cq + 31) / 32;
+  CK(zeros(h, &q.queue, slots * (cq + 1)));
+  CK(zeros(h, &q.qcls, slots * (cq + 1)));
+  CK(zeros(h, &q.last_len, slots * cq));
+  CK(zeros(h, &q.clsl, slots * cq));
+  CK(zeros(h, &q.rk, slots * cq));
+  CK(zeros(h, &q.c_tmpl, slots * cq));
+  CK(zeros(h, &q.c_npods, slots * cq));
+  CK(zeros(h, &q.order, slots * cq));
+  CK(zeros(h, &q.cnt_at, slots * cq));
+  CK(zeros(h, &q.c_req, slots * cq * R));
+  CK(zeros(h, &q.c_sflags, slots * cq * K));
+  CK(zeros(h, &q.c_smask, slots * cq * K));
+  CK(zeros(h, &q.c_its, slots * cq * ITW));
+  CK(zeros(h, &q.rdead, slots * (size_t)std::max(t.n_rv, 1) * RWc));
+  CK(zeros(h, &q.fail, slots * (size_t)std::max(d.n_fsig, 1) * RWc));
+  CK(zeros(h, &q.tmpl_remaining, slots * (size_t)std::max(N, 1) * R));
+  CK(zeros(h, &q.ov_node, slots * cq));
+  CK(zeros(h, &q.ov_rem, slots * cq * R));
+  CK(zeros(h, &q.ov_present, slots * cq));
+  CK(zeros(h, &q.ov_sflags, slots * cq * K));
+  CK(zeros(h, &q.ov_smask, slots * cq * K));
+  if (t.has_bounds) {
+    CK(zeros(h, &q.c_sgte, slots * cq * K));
+    CK(zeros(h, &q.c_slte, slots * cq * K));
+    CK(zeros(h, &q.ov_sgte, slots * cq * K));
+    CK(zeros(h, &q.ov_slte, slots * cq * K));
+  }
+  CK(zeros(h, &q.decision, (size_t)std::max(S, 1)));
+  CK(zeros(h, &q.replacement_its, (size_t)std::max(S, 1) * std::max(ITW, 1)));
+  CK(zeros(h, &q.n_new_claims, (size_t)std::max(S, 1)));
+  CK(zeros(h, &q.n_unscheduled, (size_t)std::max(S, 1)));
+  CK(zeros(h, &q.next, 1));
+  CK(zeros(h, &q.status, 1));
+  rc = reset_dynamic(h);
+  if (rc != KP_OK) return rc;
+  auto t_up = std::chrono::steady_clock::now();
+  h->stats.upload_ms += std::chrono::duration<double, std::milli>(t_up - t_begin).count();
+  // ---- kernels
+  CK(cudaEventRecord(h->ev0, h->stream));
+  h->stats.kernel_launches = 0;
+  if (d.N > 0) {
+    k_feasibility<<<(d.N * 32 + 255) / 256, 256, 0, h->stream>>>(d, nullptr, 1);
+    h->stats.kernel_launches++;
+  }
+  rc = sort_queue(h);  // byCPUAndMemoryDescending over every pod row; a subset's queue is its rows in rank order
+  if (rc != KP_OK) return rc;
+  if (h->P > 0) {
+    k_scatter_rank<<<(int)((h->P + 255) / 256), 256, 0, h->stream>>>(d.queue, h->P, d_rank);
+    h->stats.kernel_launches++;
+  }
+  rc = launch_node_cand(h);
+  if (rc != KP_OK) return rc;
+  if (S > 0) {
+    k_consolidate<<<grid, CONSOL_WARPS * 32, smem, h->stream>>>(d, q);
+    h->stats.kernel_launches++;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats.solve_ms = ms;
+  int32_t status = 0;
+  CK(cudaMemcpy(&status, q.status, 4, cudaMemcpyDeviceToHost));
+  if (status != KP_OK) return h->err = "consolidation instance failed (capacity or invalid state)", status;
+  // ---- results
+  auto t0 = std::chrono::steady_clock::now();
+  out->n_subsets = S;
+  out->it_words = ITW;
+  out->decision = (uint8_t*)calloc(S ? S : 1, 1);
+  out->replacement_its = (uint64_t*)calloc((size_t)(S ? S : 1) * (ITW ? ITW : 1), sizeof(uint64_t));
+  out->n_new_claims = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
+  out->n_unscheduled = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
+  CK(cudaMemcpy(out->decision, q.decision, (size_t)S, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out->replacement_its, q.replacement_its, (size_t)S * ITW * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out->n_new_claims, q.n_new_claims, (size_t)S * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out->n_unscheduled, q.n_unscheduled, (size_t)S * 4, cudaMemcpyDeviceToHost));
+  out->solve_ms = ms;
+  h->stats.bytes_d2h = (size_t)S * (9 + (size_t)ITW * 8);
+  h->stats.download_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  for (int s = 0; s < S; s++)
+    if (out->decision[s] == 255) {
+      kp_consol_result_free(out);
+      return h->err = "a replacement needs price-ordered truncation (> 600 instance types) or spot-to-spot rules: not built yet",
+             KP_ERR_UNSUPPORTED;
+    }
+  return KP_OK;
 }

@@ -1,6 +1,470 @@
-// kp_consolidate.cuh -- multi-node consolidation search (filled in below kp_api.cu's handle definition)
+// kp_consolidate.cuh -- launchable kernels around the warp solver (kp_wsolve.cuh):
+//
+//   k_node_cand     existing-node candidate bitmaps: for every (class signature | request vector) x node one bit.
+//                   Streams the node table once per signature tile -- the HBM-bound, embarrassingly parallel part.
+//   k_wsolve        Scheduler.Solve: one instance, one CTA; order / failure bitmaps / staged tables in shared memory.
+//   k_consolidate   disruption.SimulateScheduling + computeConsolidation (helpers.go:51-142, consolidation.go:136-229)
+//                   for every candidate subset: one warp per subset pulled from a global counter, 8 warps per CTA, all
+//                   SMs busy; the cluster's node table is shared read-only, each warp keeps the nodes its simulation
+//                   touched in a private overlay.
 #pragma once
-#include "kp_solve.cuh"
-struct kp_handle;
-static int kp_consolidate_impl(kp_handle* h, const kp_problem* cluster, const kp_consol_input* in,
-                               kp_consol_result* out);
+#include "kp_wsolve.cuh"
+
+#define KP_ALIGN16(x) (((x) + 15) & ~(size_t)15)
+
+// bytes of the read-only tables staged in shared memory (same formula on host and device)
+__host__ __device__ inline size_t kp_tab_bytes(const KpDev& d) {
+  size_t K = d.K, R = d.R, ITW = d.ITW, D = d.D > 0 ? d.D : 1, N = d.N > 0 ? d.N : 1;
+  size_t b = 0;
+  b += KP_ALIGN16(K) + 2 * KP_ALIGN16(8 * K);                    // key_wellknown, key_univ, val_isint
+  b += KP_ALIGN16(4 * (R + 1)) + KP_ALIGN16(8 * (size_t)d.n_ge) + KP_ALIGN16(8 * (size_t)d.n_ge * ITW);
+  b += KP_ALIGN16(4 * (K + 1)) + KP_ALIGN16(8 * (size_t)d.n_itv * ITW);
+  b += 3 * KP_ALIGN16(8 * K * ITW) + KP_ALIGN16(8 * ITW);        // it_nokey, it_dne, it_nonempty, it_valid
+  b += KP_ALIGN16(sizeof(Slot) * D * K) + KP_ALIGN16(4 * D) + KP_ALIGN16(8 * D * ITW);
+  b += KP_ALIGN16(4 * N);
+  return b;
+}
+
+// Copy the pointer block to shared memory and, when they fit, the small read-only tables next to it (key universe,
+// allocatable thresholds, bit-sliced instance-type rows, offering sets); patches the pointers. All threads of the CTA.
+__device__ __forceinline__ void stage_tables(const KpDev& d_in, KpDev* ds, unsigned char* tab) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  {
+    const int* src = reinterpret_cast<const int*>(&d_in);
+    int* dst = reinterpret_cast<int*>(ds);
+    for (int i = tid; i < (int)(sizeof(KpDev) / 4); i += nt) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (d_in.tab_bytes > 0) {
+    size_t off = 0;
+#define KP_STAGE(field, type, count)                                     \
+  {                                                                      \
+    size_t n_ = (size_t)(count);                                         \
+    type* dst_ = reinterpret_cast<type*>(tab + off);                     \
+    const type* src_ = d_in.field;                                       \
+    for (size_t i_ = tid; i_ < n_; i_ += nt) dst_[i_] = src_[i_];        \
+    if (tid == 0) ds->field = dst_;                                      \
+    off += KP_ALIGN16(sizeof(type) * n_);                                \
+  }
+    const size_t K_ = d_in.K, R_ = d_in.R, W_ = d_in.ITW, D_ = d_in.D > 0 ? d_in.D : 1, N_ = d_in.N > 0 ? d_in.N : 1;
+    KP_STAGE(key_wellknown, uint8_t, K_)
+    KP_STAGE(key_univ, uint64_t, K_)
+    KP_STAGE(val_isint, uint64_t, K_)
+    KP_STAGE(ge_off, int32_t, R_ + 1)
+    KP_STAGE(ge_vals, int64_t, d_in.n_ge)
+    KP_STAGE(ge_bits, uint64_t, (size_t)d_in.n_ge * W_)
+    KP_STAGE(itv_off, int32_t, K_ + 1)
+    KP_STAGE(itv, uint64_t, (size_t)d_in.n_itv * W_)
+    KP_STAGE(it_nokey, uint64_t, K_ * W_)
+    KP_STAGE(it_dne, uint64_t, K_ * W_)
+    KP_STAGE(it_nonempty, uint64_t, K_ * W_)
+    KP_STAGE(it_valid, uint64_t, W_)
+    KP_STAGE(off_slots, Slot, D_ * K_)
+    KP_STAGE(off_keys, uint32_t, D_)
+    KP_STAGE(offset_bits, uint64_t, D_ * W_)
+    KP_STAGE(tmpl_taintset, int32_t, N_)
+#undef KP_STAGE
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Candidate bitmaps over existing nodes.  Row y < n_nsig: class signature (requirements, tolerations) -- taints
+// tolerated (taints.go:49-66) and no key the node defines has an empty intersection with the pod's requirement
+// (requirements.go:254-274); an undefined key passes unless `strict_undefined` (no pod can ever define a key on a
+// node, so the strict Compatible of existingnode.go:89 would fail forever).  Row n_nsig + rv: resources.Fits of the
+// request vector (resources.go:150-163).  Both are monotone supersets of "CanAdd succeeds".
+__global__ void __launch_bounds__(256) k_node_cand(KpDev d, const int32_t* nsig_rs, const int32_t* nsig_tolset,
+                                                    const int64_t* rv_req, int strict_undefined) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y, lane = threadIdx.x & 31;
+  bool bit = false;
+  if (n < d.E) {
+    if (row < d.n_nsig) {
+      bit = tolerated(d, nsig_tolset[row], d.node_taintset[n]);
+      const int rs = nsig_rs[row];
+      for (int k = 0; k < d.K && bit; k++) {
+        Slot pod = rs_slot(d, rs, k);
+        if (!slot_present(pod)) continue;
+        Slot nd = load_slot(d.node_sflags, d.node_smask, d.node_sgte, d.node_slte, (size_t)n * d.K + k, d.has_bounds);
+        if (!slot_present(nd)) {
+          if (strict_undefined && !op_is_negative(slot_op(pod))) bit = false;
+        } else if (!slot_has_intersection(key_info(d, k), nd, pod) &&
+                   !(op_is_negative(slot_op(pod)) && op_is_negative(slot_op(nd)))) {
+          bit = false;
+        }
+      }
+    } else {
+      const int rv = row - d.n_nsig;
+      const uint32_t pr = d.node_rem_present[n];
+      bit = true;
+      for (int r = 0; r < d.R; r++) {
+        const int64_t rem = d.node_rem[(size_t)n * d.R + r];
+        const bool present = (pr >> r) & 1;
+        if (present && rem < 0) bit = false;
+        if (rv_req[(size_t)rv * d.R + r] > (present ? rem : 0)) bit = false;
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(FULL, bit);
+  const int w = n >> 5;
+  if (lane == 0 && w < d.EW) {
+    if (row < d.n_nsig)
+      d.nstat[(size_t)row * d.EW + w] = m;
+    else
+      d.nfit[(size_t)(row - d.n_nsig) * d.EW + w] = m;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Scheduler.Solve, one instance.
+struct WSolveShared {
+  KpDev ds;
+  WInst inst;
+  PodCtx ctx;
+  Slot scratch[KP_MAXK];
+};
+
+__global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev d_in, int small_in_smem) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WSolveShared& sh = *reinterpret_cast<WSolveShared*>(smem_raw);
+  const int lane = threadIdx.x;
+  unsigned char* tab = smem_raw + KP_ALIGN16(sizeof(WSolveShared));
+  stage_tables(d_in, &sh.ds, tab);
+  const KpDev& d = sh.ds;
+  WInst& I = sh.inst;
+  const int Cmax = d.Cmax, RW = (Cmax + 31) >> 5;
+  if (lane == 0) {
+    I.P = (int)d.P;
+    I.queue = d.queue;
+    I.qcls = d.qcls;
+    I.last_len = d.last_len;
+    I.pod_target = d.pod_target;
+    I.pod_error = d.pod_error;
+    I.Cmax = Cmax;
+    I.c_tmpl = d.c_tmpl;
+    I.c_npods = d.c_npods;
+    I.c_req = d.c_req;
+    I.c_sflags = d.c_sflags;
+    I.c_smask = d.c_smask;
+    I.c_sgte = d.c_sgte;
+    I.c_slte = d.c_slte;
+    I.c_its = d.c_its;
+    I.order = d.order;
+    I.cnt_at = d.cnt_at;
+    I.rdead = d.rdead;
+    I.fail = d.fail;
+    I.RW = RW;
+    I.tmpl_remaining = d.tmpl_remaining;
+    I.node_rem = d.node_rem;
+    I.node_rem_present = d.node_rem_present;
+    I.node_sflags = d.node_sflags;
+    I.node_smask = d.node_smask;
+    I.node_sgte = d.node_sgte;
+    I.node_slte = d.node_slte;
+    I.node_npods = d.node_npods;
+    I.nfit = d.nfit;
+    I.nstat = d.nstat;
+    I.nactive = d.nactive;
+    I.n_removed = 0;
+    I.removed = nullptr;
+    I.ov_cap = 0;
+    I.n_ov = 0;
+    if (small_in_smem) {  // claim order, template ids and the failure bitmaps live in shared memory
+      unsigned char* p = tab + d_in.tab_bytes;
+      I.order = reinterpret_cast<int32_t*>(p);
+      p += (size_t)Cmax * 4;
+      I.cnt_at = reinterpret_cast<int32_t*>(p);
+      p += (size_t)Cmax * 4;
+      I.c_tmpl = reinterpret_cast<int32_t*>(p);
+      p += (size_t)Cmax * 4;
+      I.rdead = reinterpret_cast<uint32_t*>(p);
+      p += (size_t)d.n_rv * RW * 4;
+      I.fail = reinterpret_cast<uint32_t*>(p);
+    }
+  }
+  __syncwarp();
+  if (small_in_smem) {
+    for (int i = lane; i < d.n_rv * RW; i += 32) I.rdead[i] = 0;
+    for (int i = lane; i < d.n_fsig * RW; i += 32) I.fail[i] = 0;
+    __syncwarp();
+  }
+  wsolve_run<false>(d, I, sh.ctx, sh.scratch, lane);
+  const int nC = I.n_claims;
+  if (small_in_smem) {  // the host reads the final order (claim_rank) and template ids from global memory
+    for (int i = lane; i < nC; i += 32) {
+      d_in.order[i] = I.order[i];
+      d_in.cnt_at[i] = I.cnt_at[i];
+      d_in.c_tmpl[i] = I.c_tmpl[i];
+    }
+  }
+  if (lane == 0) {
+    *d.n_claims = nC;
+    *d.status = I.status;
+    d.counters[0] = I.ev_existing;
+    d.counters[1] = I.ev_inflight;
+    d.counters[2] = I.ev_tmpl;
+    d.counters[3] = I.commits;
+    d.counters[4] = I.slow_sorts;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Consolidation.
+struct KpConsol {
+  // inputs
+  int n_subsets;
+  const int32_t* subset_off;
+  const int32_t* subset_nodes;
+  const int32_t* node_pod_off;   // [E+1] rows of the cluster's pod table bound to node i
+  const int32_t* pod_class;      // [rows]
+  const int32_t* pod_rank;       // [rows] position in byCPUAndMemoryDescending order over all rows
+  const double* node_price;      // [E] cheapest compatible offering of the node's instance type, < 0: none
+  const uint8_t* node_is_spot;   // [E]
+  const int32_t* node_tmpl;      // [E] NodePool of the node, -1 unmanaged
+  const int64_t* node_capacity;  // [E*R]
+  const int64_t* tmpl_remaining0;// [N*R] limits minus capacity of ALL nodes
+  const int32_t* it_off_off;     // [T+1]
+  const int32_t* off_set;        // [offerings] distinct offering requirement set
+  const double* off_price;
+  const uint8_t* off_available;
+  const uint8_t* offset_ctmask;  // [D] bit i: set compatible with capacity type ct_order[i] (reserved, spot, on-demand)
+  int ct_key, ct_spot, ct_order_valid;  // bit i of ct_order_valid: ct_order[i] is interned
+  int spot_to_spot_enabled;
+  // per warp slot scratch
+  int capq;                      // pods / claims / overlay entries an instance can hold
+  int32_t *queue, *qcls, *last_len, *clsl, *rk;
+  int32_t *c_tmpl, *c_npods, *order, *cnt_at;
+  int64_t* c_req;
+  uint8_t* c_sflags;
+  uint64_t* c_smask;
+  int64_t *c_sgte, *c_slte;
+  uint64_t* c_its;
+  uint32_t *rdead, *fail;
+  int64_t* tmpl_remaining;
+  int32_t* ov_node;
+  int64_t* ov_rem;
+  uint32_t* ov_present;
+  uint8_t* ov_sflags;
+  uint64_t* ov_smask;
+  int64_t *ov_sgte, *ov_slte;
+  // outputs
+  uint8_t* decision;             // [n_subsets] KP_DECISION_*, 255 = needs a feature that is not built
+  uint64_t* replacement_its;     // [n_subsets * ITW]
+  int32_t* n_new_claims;
+  int32_t* n_unscheduled;
+  int32_t* next;                 // work counter
+  int32_t* status;
+};
+
+#define CONSOL_WARPS 8
+struct ConsolWarp {
+  WInst inst;
+  PodCtx ctx;
+  Slot scratch[KP_MAXK];
+};
+struct ConsolShared {
+  KpDev ds;
+  ConsolWarp w[CONSOL_WARPS];
+};
+
+__global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_constant__ KpDev d_in,
+                                                                    const __grid_constant__ KpConsol q) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ConsolShared& sh = *reinterpret_cast<ConsolShared*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  stage_tables(d_in, &sh.ds, smem_raw + KP_ALIGN16(sizeof(ConsolShared)));
+  const KpDev& d = sh.ds;
+  ConsolWarp& W = sh.w[warp];
+  WInst& I = W.inst;
+  const int K = d.K, R = d.R, ITW = d.ITW, N = d.N;
+  const size_t slot = (size_t)blockIdx.x * CONSOL_WARPS + warp;
+  const int capq = q.capq, RW = (capq + 31) >> 5;
+  if (lane == 0) {
+    I.queue = q.queue + slot * (capq + 1);
+    I.qcls = q.qcls + slot * (capq + 1);
+    I.last_len = q.last_len + slot * capq;
+    I.pod_target = nullptr;
+    I.pod_error = nullptr;
+    I.Cmax = capq;
+    I.c_tmpl = q.c_tmpl + slot * capq;
+    I.c_npods = q.c_npods + slot * capq;
+    I.c_req = q.c_req + slot * capq * R;
+    I.c_sflags = q.c_sflags + slot * capq * K;
+    I.c_smask = q.c_smask + slot * capq * K;
+    I.c_sgte = q.c_sgte ? q.c_sgte + slot * capq * K : nullptr;
+    I.c_slte = q.c_slte ? q.c_slte + slot * capq * K : nullptr;
+    I.c_its = q.c_its + slot * capq * ITW;
+    I.order = q.order + slot * capq;
+    I.cnt_at = q.cnt_at + slot * capq;
+    I.rdead = q.rdead + slot * (size_t)d.n_rv * RW;
+    I.fail = q.fail + slot * (size_t)(d.n_fsig > 0 ? d.n_fsig : 1) * RW;
+    I.RW = RW;
+    I.tmpl_remaining = q.tmpl_remaining + slot * (size_t)(N > 0 ? N : 1) * R;
+    I.node_rem = d.node_rem;  // shared base, read-only here
+    I.node_rem_present = d.node_rem_present;
+    I.node_sflags = d.node_sflags;
+    I.node_smask = d.node_smask;
+    I.node_sgte = d.node_sgte;
+    I.node_slte = d.node_slte;
+    I.node_npods = nullptr;
+    I.nfit = d.nfit;
+    I.nstat = d.nstat;
+    I.nactive = d.nactive;
+    I.ov_cap = capq;
+    I.ov_node = q.ov_node + slot * capq;
+    I.ov_rem = q.ov_rem + slot * capq * R;
+    I.ov_present = q.ov_present + slot * capq;
+    I.ov_sflags = q.ov_sflags + slot * capq * K;
+    I.ov_smask = q.ov_smask + slot * capq * K;
+    I.ov_sgte = q.ov_sgte ? q.ov_sgte + slot * capq * K : nullptr;
+    I.ov_slte = q.ov_slte ? q.ov_slte + slot * capq * K : nullptr;
+  }
+  __syncwarp();
+  int32_t* clsl = q.clsl + slot * capq;
+  int32_t* rk = q.rk + slot * capq;
+
+  for (;;) {
+    int s = 0;
+    if (lane == 0) s = atomicAdd(q.next, 1);
+    s = __shfl_sync(FULL, s, 0);
+    if (s >= q.n_subsets) break;
+    const int so = q.subset_off[s], sn = q.subset_off[s + 1] - so;
+    const int32_t* snodes = q.subset_nodes + so;
+    // ---- pods = the candidates' reschedulable pods (helpers.go:60-75), sorted like NewQueue (queue.go:37-43)
+    int n = 0;
+    for (int i = 0; i < sn; i++) {
+      const int node = snodes[i];
+      const int a = q.node_pod_off[node], b = q.node_pod_off[node + 1];
+      for (int j = a + lane; j < b; j += 32) {
+        const int o = n + (j - a);
+        if (o < capq) {
+          clsl[o] = q.pod_class[j];
+          rk[o] = q.pod_rank[j];
+        }
+      }
+      n += b - a;
+    }
+    if (n > capq) {
+      if (lane == 0) *q.status = KP_ERR_CAPACITY;
+      break;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const int my = rk[i];
+      int pos = 0;
+      for (int j = 0; j < n; j++) pos += rk[j] < my ? 1 : 0;
+      I.queue[pos] = i;
+      I.qcls[pos] = clsl[i];
+    }
+    // ---- per-instance state
+    if (lane == 0) {
+      I.P = n;
+      I.n_ov = 0;
+      I.n_removed = sn;
+      I.removed = snodes;
+    }
+    for (int i = lane; i < N * R; i += 32) {  // updateRemainingResources over stateNodes minus candidates
+      const int t = i / R, r = i % R;
+      int64_t rem = q.tmpl_remaining0[i];
+      if ((d.tmpl_limit_present[t] >> r) & 1)
+        for (int c = 0; c < sn; c++)
+          if (q.node_tmpl[snodes[c]] == t) rem += q.node_capacity[(size_t)snodes[c] * R + r];
+      I.tmpl_remaining[i] = rem;
+    }
+    __syncwarp();
+    wsolve_run<true>(d, I, W.ctx, W.scratch, lane);
+    if (I.status != KP_OK) {
+      if (lane == 0) *q.status = I.status;
+      break;
+    }
+    // ---- computeConsolidation (consolidation.go:136-229)
+    const int unscheduled = I.n_unsched + I.n_uninit;
+    const int n_new = I.n_claims;
+    int decision = KP_DECISION_NOOP;
+    uint64_t rep = 0;  // lane w: word w of the replacement instance types
+    if (!unscheduled) {
+      if (n_new == 0) {
+        decision = KP_DECISION_DELETE;
+      } else if (n_new == 1) {
+        // the single new NodeClaim: requirements (hostname already dropped), instance types
+        Slot S = lane < K ? load_slot(I.c_sflags, I.c_smask, I.c_sgte, I.c_slte, (size_t)lane, d.has_bounds) : slot_absent();
+        const uint64_t its = lane < ITW ? I.c_its[lane] : 0ull;
+        int n_its = lane < ITW ? __popcll(its) : 0;
+        for (int o = 16; o; o >>= 1) n_its += __shfl_xor_sync(FULL, n_its, o);
+        // getCandidatePrices (consolidation.go:319-337)
+        double price = 0;
+        bool zero = false, all_spot = true;
+        for (int i = 0; i < sn; i++) {
+          const double np = q.node_price[snodes[i]];
+          if (np < 0) zero = true;
+          price += np;
+          if (!q.node_is_spot[snodes[i]]) all_spot = false;
+        }
+        if (zero) price = 0.0;
+        bool spot_ok = false;
+        if (q.ct_key >= 0 && q.ct_spot >= 0) {
+          const uint32_t f = __shfl_sync(FULL, S.f, q.ct_key);
+          const uint64_t m = __shfl_sync(FULL, S.m, q.ct_key);
+          const int64_t g = __shfl_sync(FULL, S.gte, q.ct_key), l = __shfl_sync(FULL, S.lte, q.ct_key);
+          spot_ok = slot_has(key_info(d, q.ct_key), Slot{f, m, g, l}, q.ct_spot);
+        }
+        if (n_its > 600) {
+          decision = 255;  // TruncateInstanceTypes by price order (scheduler.go:361-379) is not built on the device
+        } else if (all_spot && spot_ok) {
+          decision = q.spot_to_spot_enabled ? 255 : KP_DECISION_NOOP;  // computeSpotToSpotConsolidation :236-316
+        } else {
+          // RemoveInstanceTypeOptionsByPriceAndMinValues (nodeclaim.go:309-318): keep WorstLaunchPrice < price
+          if (lane < K) W.scratch[lane] = S;
+          __syncwarp();
+          bool off_ok = false;
+          if (lane < d.D) {
+            uint32_t keys = d.off_keys[lane];
+            off_ok = true;
+            while (keys) {
+              const int k = __ffs(keys) - 1;
+              keys &= keys - 1;
+              if (!slot_compatible(key_info(d, k), W.scratch[k], d.off_slots[(size_t)lane * K + k], d.key_wellknown[k], true))
+                off_ok = false;
+            }
+          }
+          const unsigned okmask = __ballot_sync(FULL, off_ok);
+          __syncwarp();
+          if (lane < ITW) {
+            for (uint64_t bits = its; bits;) {
+              const int b = __ffsll((long long)bits) - 1;
+              bits &= bits - 1;
+              const int t = lane * 64 + b;
+              double worst = 1.7976931348623157e308;
+              for (int ci = 0; ci < 3; ci++) {  // reserved -> spot -> on-demand (types.go:480-491)
+                if (q.ct_key < 0 || !((q.ct_order_valid >> ci) & 1)) continue;
+                bool any = false;
+                double mx = 0;
+                for (int o = q.it_off_off[t]; o < q.it_off_off[t + 1]; o++) {
+                  if (!q.off_available[o]) continue;
+                  const int dd = q.off_set[o];
+                  if (!((okmask >> dd) & 1u) || !((q.offset_ctmask[dd] >> ci) & 1)) continue;
+                  if (!any || q.off_price[o] > mx) mx = q.off_price[o];
+                  any = true;
+                }
+                if (any) {
+                  worst = mx;
+                  break;
+                }
+              }
+              if (worst < price) rep |= 1ull << b;
+            }
+          }
+          if (__any_sync(FULL, rep != 0)) decision = KP_DECISION_REPLACE;
+        }
+      }
+    }
+    if (decision != KP_DECISION_REPLACE) rep = 0;
+    if (lane < ITW) q.replacement_its[(size_t)s * ITW + lane] = rep;
+    if (lane == 0) {
+      q.decision[s] = (uint8_t)decision;
+      q.n_new_claims[s] = n_new;
+      q.n_unscheduled[s] = unscheduled;
+    }
+    __syncwarp();
+  }
+}

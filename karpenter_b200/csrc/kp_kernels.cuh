@@ -2,10 +2,8 @@
 //
 //   k_feasibility  (K1)  class x template instance-type feasibility bitmaps: one warp per (class, template) pair,
 //                        bit-sliced mask ANDs -- filterInstanceTypesByRequirements (nodeclaim.go:412-480).
-//   k_solve        (K2/K3) the Scheduler.Solve loop (scheduler.go:381-684): one persistent CTA walks the sorted pod
-//                        queue; per pod a thread-per-candidate filter then a warp-per-candidate exact CanAdd
-//                        (existingnode.go:70-143, nodeclaim.go:114-202) with a ballot for the lowest feasible index,
-//                        and a one-warp commit (NodeClaim.Add / ExistingNode.Add / Topology.Record).
+//   eval_candidate / topo_record  the exact CanAdd (existingnode.go:70-143, nodeclaim.go:114-202) and Topology.Record
+//                        of one pod on one candidate, executed by one warp (used by kp_wsolve.cuh).
 //
 // Warp layout of an evaluation: lane k owns label key k (requirement slot), lane r owns resource r, lane w owns
 // instance-type bitmap word w.
@@ -16,8 +14,6 @@
 #include "kp_slot.hpp"
 
 #define FULL 0xffffffffu
-#define SOLVE_THREADS 512
-#define SOLVE_WARPS (SOLVE_THREADS / 32)
 
 __device__ __forceinline__ KeyInfo key_info(const KpDev& d, int k) {
   return KeyInfo{d.val_int + (size_t)k * 64, d.val_isint[k], d.key_univ[k]};
@@ -41,17 +37,17 @@ __device__ __forceinline__ Slot rs_slot(const KpDev& d, int rs, int k) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Instance-type filter on bit-sliced tables. `S` = the candidate's final requirement slots (one per key, readable by
-// every lane), q = total requests (lane r holds q[r]).  Lane w returns word w of
-//   compat & fits & hasOffering      (nodeclaim.go:434-445)
-// and *fits_word = word w of the resource-only test (used for the monotone "never fits again" marking).
-__device__ __forceinline__ uint64_t filter_its_word(const KpDev& d, const Slot* S, int64_t q_lane, int lane,
-                                                    uint64_t* fits_word) {
-  const int K = d.K, R = d.R, ITW = d.ITW;
-  // resources.Fits(total, allocatable) via ">= threshold" bitmaps: lane r ranks q[r]
+// Instance-type filter on bit-sliced tables (filterInstanceTypesByRequirements, nodeclaim.go:412-480), one warp:
+// lane w owns instance-type bitmap word w, lane r resource r.
+//
+// fits_word: resources.Fits(total, allocatable) via ">= threshold" bitmaps: lane r ranks q[r] in the sorted distinct
+// allocatable values of resource r, the answer is the AND of the R selected rows.
+__device__ __forceinline__ uint64_t fits_word(const KpDev& d, int64_t q_lane, int lane) {
+  const int R = d.R, ITW = d.ITW;
   int j = 0;
   if (lane < R) {
     int lo = d.ge_off[lane], hi = d.ge_off[lane + 1];
+    const int end = hi;
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
       if (d.ge_vals[mid] < q_lane)
@@ -59,14 +55,18 @@ __device__ __forceinline__ uint64_t filter_its_word(const KpDev& d, const Slot* 
       else
         hi = mid;
     }
-    j = lo == d.ge_off[lane + 1] ? -1 : lo;  // -1: the request exceeds every instance type
+    j = lo == end ? -1 : lo;  // -1: the request exceeds every instance type
   }
   uint64_t fw = (lane < ITW) ? d.it_valid[lane] : 0ull;
   for (int r = 0; r < R; r++) {
     int jr = __shfl_sync(FULL, j, r);
     if (lane < ITW) fw &= jr >= 0 ? d.ge_bits[(size_t)jr * ITW + lane] : 0ull;
   }
-  *fits_word = fw;
+  return fw;
+}
+// compat_off_word: word w of compatible(it, S) & hasOffering(it, S) for the requirement slots S (readable by every lane)
+__device__ __forceinline__ uint64_t compat_off_word(const KpDev& d, const Slot* S, int lane) {
+  const int K = d.K, ITW = d.ITW;
   // hasOffering: lane dd decides Compatible(S, offering set dd, AllowUndefinedWellKnownLabels)
   bool off_ok = false;
   if (lane < d.D) {
@@ -109,7 +109,14 @@ __device__ __forceinline__ uint64_t filter_its_word(const KpDev& d, const Slot* 
   } else {
     cw = 0;
   }
-  return cw & fw & ow;
+  return cw & ow;
+}
+// word w of compat & fits & hasOffering (nodeclaim.go:434-445); *fits_out = the resource-only word
+__device__ __forceinline__ uint64_t filter_its_word(const KpDev& d, const Slot* S, int64_t q_lane, int lane,
+                                                    uint64_t* fits_out) {
+  uint64_t fw = fits_word(d, q_lane, lane);
+  *fits_out = fw;
+  return compat_off_word(d, S, lane) & fw;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -181,6 +188,7 @@ __device__ __forceinline__ Slot topo_domains(const KpDev& d, int g, const KpGrou
 struct Eval {
   bool ok;
   bool res_dead;   // no remaining instance type can ever hold these requests again (monotone)
+  bool changed;    // the pod tightened at least one requirement slot of the candidate
   Slot F;          // lane k: final requirement slot of key k
   int64_t q;       // lane r: total requests (claims)
   uint64_t its;    // lane w: surviving instance-type word (claims)
@@ -189,7 +197,7 @@ struct Eval {
 // The pod being placed, staged once per pod in shared memory (class row of the problem + its requirement slots).
 struct PodCtx {
   int pod, cls, tolset, rv;
-  int moff, mend, roff, rend, sig;
+  int moff, mend, roff, rend, fsig, nsig, hoff, hend;
   unsigned long long tmpl_ok;  // bit n: template n's taints are tolerated (taints.go:49-66)
   int64_t req[KP_MAXR];
   Slot pod_slot[KP_MAXK];
@@ -206,6 +214,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   Eval ev;
   ev.ok = false;
   ev.res_dead = false;
+  ev.changed = false;
   const int K = d.K;
   const bool allow_undef = is_claim;  // ExistingNode.CanAdd passes no compatibility options
   const bool wk = lane < K ? d.key_wellknown[lane] : false;
@@ -253,34 +262,43 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   }
   ev.F = M;
   if (!is_claim) {
+    ev.changed = __any_sync(FULL, lane < K && !slot_eq(M, base));
     ev.ok = true;
     return ev;
   }
-  // resources.Merge + filterInstanceTypesByRequirements
-  if (lane < K) scratch[lane] = M;
-  __syncwarp();
+  // resources.Merge + filterInstanceTypesByRequirements.  base_its already went through the filter with the
+  // candidate's current requirements (every NodeClaim.Add stores the filtered list, nodeclaim.go:209; a fresh claim
+  // starts from the NewScheduler prefilter, scheduler.go:147), so when the pod leaves every slot unchanged only the
+  // resource test can remove instance types.
+  const bool changed = __any_sync(FULL, lane < K && !slot_eq(M, base));
+  ev.changed = changed;
   int64_t q = base_q + (lane < d.R ? px.req[lane] : 0);
-  uint64_t fw;
-  uint64_t w = filter_its_word(d, scratch, q, lane, &fw) & base_its;
-  __syncwarp();
+  uint64_t fw = fits_word(d, q, lane) & base_its;
+  uint64_t w = fw;
+  if (changed) {
+    if (lane < K) scratch[lane] = M;
+    __syncwarp();
+    w &= compat_off_word(d, scratch, lane);
+    __syncwarp();
+  }
   ev.q = q;
   ev.its = w;
   ev.ok = __any_sync(FULL, w != 0);
-  ev.res_dead = !__any_sync(FULL, (fw & base_its) != 0);
+  ev.res_dead = !__any_sync(FULL, fw != 0);
   return ev;
 }
 
 // A class row in flight between global memory and the shared PodCtx (one warp; lane k: key k, lane r: resource r,
-// lane i < 8: header word i).
+// lane i < KP_HDR: header word i).
 struct ClassRegs {
-  int hdr;                // lanes 0..8: tolset, rv, moff, mend, roff, rend, sig, class, pod
+  int hdr;                // lanes 0..KP_HDR+1: tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend, class, pod
   unsigned long long tmpl_ok;
   int64_t req;
   Slot pod, strict;
 };
 __device__ __forceinline__ ClassRegs load_class_regs(const KpDev& d, int X, int pod, int lane) {
   ClassRegs c;
-  c.hdr = lane < 7 ? d.cr_hdr[(size_t)X * 7 + lane] : (lane == 7 ? X : pod);
+  c.hdr = lane < KP_HDR ? d.cr_hdr[(size_t)X * KP_HDR + lane] : (lane == KP_HDR ? X : pod);
   c.tmpl_ok = lane == 0 ? d.cr_tmplok[X] : 0ull;
   c.req = lane < d.R ? d.cls_req[(size_t)X * d.R + lane] : 0;
   if (lane < d.K) {
@@ -300,9 +318,12 @@ __device__ __forceinline__ void store_class_regs(const KpDev& d, PodCtx& px, con
   if (lane == 3) px.mend = c.hdr;
   if (lane == 4) px.roff = c.hdr;
   if (lane == 5) px.rend = c.hdr;
-  if (lane == 6) px.sig = c.hdr;
-  if (lane == 7) px.cls = c.hdr;
-  if (lane == 8) px.pod = c.hdr;
+  if (lane == 6) px.fsig = c.hdr;
+  if (lane == 7) px.nsig = c.hdr;
+  if (lane == 8) px.hoff = c.hdr;
+  if (lane == 9) px.hend = c.hdr;
+  if (lane == 10) px.cls = c.hdr;
+  if (lane == 11) px.pod = c.hdr;
   if (lane == 0) px.tmpl_ok = c.tmpl_ok;
   if (lane < d.R) px.req[lane] = c.req;
   if (lane < d.K) {

@@ -273,9 +273,12 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
         } else {
           d = it->second;
         }
+        if ((int)h.off_set.size() <= o) h.off_set.resize(o + 1, 0);
+        h.off_set[o] = d;
         if (p->off_available[o]) h.offset_bits[(size_t)d * ITW + (t >> 6)] |= 1ull << (t & 63);
       }
     h.D = (int)h.offset_rs.size();
+    if (h.off_set.empty()) h.off_set.push_back(0);
     if (h.offset_rs.empty()) {
       h.offset_rs.push_back(0);
       h.offset_bits.assign(std::max(ITW, 1), 0);

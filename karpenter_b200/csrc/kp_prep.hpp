@@ -34,6 +34,7 @@ struct HostTables {
   std::vector<uint32_t> off_keys;
   std::vector<uint64_t> ge_bits;
   std::vector<int32_t> offset_rs;
+  std::vector<int32_t> off_set;  // [offerings] index of the offering's distinct requirement set
   std::vector<uint64_t> offset_bits;
   std::vector<int64_t> it_capacity, it_alloc;
   std::vector<int32_t> tmpl_rs, tmpl_taintset;

@@ -24,6 +24,13 @@ KP_HD Slot slot_absent() { return Slot{0u, 0ull, 0, 0}; }
 KP_HD Slot slot_exists() { return Slot{SF_PRESENT | SF_COMPLEMENT, 0ull, 0, 0}; }
 KP_HD bool slot_present(const Slot& s) { return s.f & SF_PRESENT; }
 
+KP_HD bool slot_eq(const Slot& a, const Slot& b) {
+  if (a.f != b.f || a.m != b.m) return false;
+  if ((a.f & SF_HAS_GTE) && a.gte != b.gte) return false;
+  if ((a.f & SF_HAS_LTE) && a.lte != b.lte) return false;
+  return true;
+}
+
 // requirement.go:282-293 Operator()
 KP_HD int slot_op(const Slot& s) {
   if (s.f & SF_COMPLEMENT) return s.m ? OP_NOT_IN : OP_EXISTS;

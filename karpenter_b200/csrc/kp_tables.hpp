@@ -7,11 +7,15 @@
 // (nodeclaim.go:412-480) then is a handful of coalesced 64-bit ANDs/ORs per instance-type word.
 #pragma once
 #include <cstdint>
+#ifndef __CUDACC__
+struct int4 { int x, y, z, w; };
+#endif
 
 #define KP_MAXK 32          // label keys (one warp lane per key)
 #define KP_MAXR 8           // resources
 #define KP_MAX_ITW 32       // instance-type bitmap words (<= 2048 types, one lane per word)
 #define KP_MAX_OFFSETS 32   // distinct offering requirement sets
+#define KP_HDR 10            // ints per class header row (cr_hdr)
 
 // slot flags
 #define SF_COMPLEMENT 0x01u
@@ -101,7 +105,8 @@ struct KpDev {
   const int32_t* cls_rec_off;     // [X+1] groups that may count the class on Record (select it / inverse owned)
   const int32_t* cls_rec;
   // class rows, one level of indirection for the per-pod staging (header: tolset, rv, match/record list ranges)
-  const int32_t* cr_hdr;          // [X*7] tolset, rv, moff, mend, roff, rend, sig
+  const int32_t* cr_hdr;          // [X*KP_HDR] tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend
+  const int4* cls_hchk;           // hostname-group checks of a class {host_row, type | self << 8, max_skew, group}
   const uint64_t* cr_tmplok;      // [X] bit n: template n tolerated
   const uint8_t* cp_f;            // [X*K] PodData.Requirements slots
   const uint64_t* cp_m;
@@ -145,11 +150,15 @@ struct KpDev {
   int32_t* order;                 // [Cmax] s.newNodeClaims as claim ids
   int32_t* cnt_at;                // [Cmax] len(Pods) by position
   uint32_t* rdead;                // [n_rv * ceil(Cmax/32)] claim can never again fit this request vector
-  // exact failure cache: CanAdd of a topology-free class on a NodeClaim is a pure function of (class requirements,
-  // class requests, claim state); a recorded failure stays valid until the claim changes (its version moves on)
-  int n_sig;
-  uint32_t* fver;                 // [n_sig * Cmax] claim version + 1 at which the signature failed (0 = never)
-  uint32_t* cver;                 // [Cmax] claim version: number of pods committed to it
+  // monotone failure cache: for a topology-free class whose keys can never be "undefined" on a NodeClaim, CanAdd only
+  // ever flips from true to false (requirements tighten, requests grow, instance types shrink: nodeclaim.go:207-219)
+  int n_fsig;                     // distinct (requirements, requests) signatures of such classes
+  uint32_t* fail;                 // [n_fsig * ceil(Cmax/32)] claim rejected this signature once
+  // existing-node candidate bitmaps (supersets; the exact CanAdd runs on every candidate)
+  int n_nsig, EW;                 // distinct (requirements, tolerations) signatures; words per row = ceil(E/32)
+  uint32_t* nfit;                 // [n_rv * EW] resources.Fits(request vector, remaining) held when last checked
+  uint32_t* nstat;                // [n_nsig * EW] taints tolerated and no defined key has an empty intersection
+  uint32_t* nactive;              // [EW] schedulable nodes
   // pods
   int64_t P;
   const int32_t* pod_class;       // [P]

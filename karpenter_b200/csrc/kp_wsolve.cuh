@@ -1,0 +1,567 @@
+// kp_wsolve.cuh -- the Scheduler.Solve loop (scheduler.go:381-684) executed by ONE WARP per Scheduler instance.
+//
+// First-fit-decreasing with the reference's "fewest pods first" claim order is a serial chain: pod i's placement
+// decides the state pod i+1 sees.  A CTA-wide design spends its time in barriers around one working warp (ncu:
+// profiles/r1_v3_*), so the chain runs inside a single warp with no block-level synchronisation at all:
+//
+//   lane k  owns label key k      (requirement slot algebra: Compatible / Add)
+//   lane r  owns resource r       (requests, Fits)
+//   lane w  owns word w of the instance-type bitmap
+//   lane i  owns candidate base+i while scanning the claim order / node bitmaps (ballot -> lowest index wins)
+//
+// The same routine serves the provisioning solve (one instance, k_wsolve) and the consolidation search (one instance
+// per removal subset, thousands of warps in flight, k_consolidate): an instance is a WInst, a block of pointers to
+// its private mutable state.  Existing nodes are found through per-class candidate bitmaps (supersets computed once
+// by k_node_cand) and every candidate is re-checked exactly; the consolidation instances share the cluster's base node
+// table read-only and keep their few modified nodes in a private overlay.
+#pragma once
+#include "kp_gosort.cuh"
+#include "kp_kernels.cuh"
+
+enum { PERT_NONE = 0, PERT_INC = 1, PERT_APPEND = 2 };
+
+struct WInst {
+  // pods: local ids 0..P-1
+  int P;
+  int32_t* queue;       // [P+1] circular queue of local pod ids, initially byCPUAndMemoryDescending (queue.go:72-108)
+  int32_t* qcls;        // [P+1] class of queue[i]
+  int32_t* last_len;    // [P]
+  int32_t* pod_target;  // [P] or null
+  uint8_t* pod_error;   // [P] or null
+  // NodeClaims
+  int Cmax;
+  int32_t *c_tmpl, *c_npods;
+  int64_t* c_req;
+  uint8_t* c_sflags;
+  uint64_t* c_smask;
+  int64_t *c_sgte, *c_slte;
+  uint64_t* c_its;
+  int32_t *order, *cnt_at;  // s.newNodeClaims: claim id / len(Pods) by position
+  uint32_t *rdead, *fail;
+  int RW;                   // words per rdead / fail row
+  int64_t* tmpl_remaining;  // [N*R]
+  // existing nodes
+  int64_t* node_rem;
+  uint32_t* node_rem_present;
+  uint8_t* node_sflags;
+  uint64_t* node_smask;
+  int64_t *node_sgte, *node_slte;
+  int32_t* node_npods;      // direct mode only
+  uint32_t *nfit, *nstat;
+  const uint32_t* nactive;
+  int n_removed;
+  const int32_t* removed;   // overlay mode: nodes taken out of the cluster (the consolidation candidates)
+  // overlay (consolidation): entry i shadows node ov_node[i]
+  int ov_cap, n_ov;
+  int32_t* ov_node;
+  int64_t* ov_rem;
+  uint32_t* ov_present;
+  uint8_t* ov_sflags;
+  uint64_t* ov_smask;
+  int64_t *ov_sgte, *ov_slte;
+  // results
+  int n_claims, n_unsched, n_uninit, status;
+  long long ev_existing, ev_inflight, ev_tmpl, commits, slow_sorts;
+};
+
+// index of `node` in the overlay, -1 if it is untouched (warp-uniform result)
+__device__ __forceinline__ int ov_find(const WInst& I, int node, int lane) {
+  for (int b = 0; b < I.n_ov; b += 32) {
+    int i = b + lane;
+    unsigned m = __ballot_sync(FULL, i < I.n_ov && I.ov_node[i] == node);
+    if (m) return b + __ffs(m) - 1;
+  }
+  return -1;
+}
+
+// One Scheduler.Solve over the instance's queue.  OVERLAY: existing-node state = shared base + private overlay.
+template <bool OVERLAY>
+__device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch, const int lane) {
+  const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, EW = d.EW, RW = I.RW;
+  int head = 0, tail = I.P;
+  const int cap = I.P + 1;
+  int nC = 0;
+  int pert = PERT_NONE, pert_pos = 0;
+  long long ev_existing = 0, ev_inflight = 0, ev_tmpl = 0, commits = 0, slow_sorts = 0;
+  int n_unsched = 0, n_uninit = 0, status = KP_OK;
+  int32_t* const ord = I.order;
+  int32_t* const cnt = I.cnt_at;
+  // templates NewScheduler kept (scheduler.go:147-160)
+  int alive_tmpl = 0;
+  for (int n = 0; n < d.N; n++) {
+    uint64_t w = lane < ITW ? d.tmpl_its[(size_t)n * ITW + lane] : 0ull;
+    alive_tmpl += __any_sync(FULL, w != 0) ? 1 : 0;
+  }
+  int n_active_nodes = 0;
+  for (int w = lane; w < EW; w += 32) n_active_nodes += __popc(I.nactive[w]);
+  for (int o = 16; o; o >>= 1) n_active_nodes += __shfl_xor_sync(FULL, n_active_nodes, o);
+  if (OVERLAY) n_active_nodes -= I.n_removed;
+
+  // software pipeline of the class-row staging: `pf` holds the class row of queue index pf_idx (loads issued one
+  // iteration ahead), `ids` the (class, pod) of queue index ids_idx (two iterations ahead)
+  ClassRegs pf;
+  int pf_idx = -1, ids_idx = -1, ids_cls = 0, ids_pod = 0;
+  pf.hdr = 0;
+  pf.tmpl_ok = 0;
+  pf.req = 0;
+  pf.pod = slot_absent();
+  pf.strict = slot_absent();
+
+  long long watchdog = 0;
+  for (;;) {
+    // ---- Queue.Pop (queue.go:46-60)
+    const int len = tail - head;
+    if (len == 0) break;
+    if (++watchdog > 4ll * I.P + 1024) {  // cannot happen: every requeue cycle needs progress (queue.go:54-58)
+      status = KP_ERR_INVALID;
+      break;
+    }
+    const int h = head;
+    int li, X;
+    if (ids_idx == h) {
+      li = ids_pod;
+      X = ids_cls;
+    } else {
+      li = I.queue[h % cap];
+      X = I.qcls[h % cap];
+    }
+    if (h >= I.P && I.last_len[li] == len) break;  // a full cycle without progress
+    head = h + 1;
+    {
+      ClassRegs cur = pf_idx == h ? pf : load_class_regs(d, X, li, lane);
+      __syncwarp();
+      store_class_regs(d, ctx, cur, lane);
+      __syncwarp();
+    }
+    // issue the loads for the next two pods; nothing below waits on them
+    pf_idx = -1;
+    if (h + 1 < tail) {
+      int nli, nX;
+      if (ids_idx == h + 1) {
+        nli = ids_pod;
+        nX = ids_cls;
+      } else {
+        nli = I.queue[(h + 1) % cap];
+        nX = I.qcls[(h + 1) % cap];
+      }
+      pf = load_class_regs(d, nX, nli, lane);
+      pf_idx = h + 1;
+    }
+    ids_idx = -1;
+    if (h + 2 < tail) {
+      ids_pod = I.queue[(h + 2) % cap];
+      ids_cls = I.qcls[(h + 2) % cap];
+      ids_idx = h + 2;
+    }
+    const PodCtx& px = ctx;
+    const int rv = px.rv, fsig = px.fsig;
+    bool found = false;
+
+    // ================= addToExistingNode (scheduler.go:520-555) =================
+    if (E > 0 && px.nsig >= 0) {
+      const uint32_t* fitrow = I.nfit + (size_t)rv * EW;
+      const uint32_t* strow = I.nstat + (size_t)px.nsig * EW;
+      int seen = 0;
+      for (int w0 = 0; w0 < EW && !found; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t bits = w < EW ? (fitrow[w] & strow[w] & I.nactive[w]) : 0u;
+        if (OVERLAY)
+          for (int i = 0; i < I.n_removed; i++)
+            if ((I.removed[i] >> 5) == w) bits &= ~(1u << (I.removed[i] & 31));
+        unsigned has = __ballot_sync(FULL, bits != 0);
+        while (has && !found) {
+          const int src = __ffs(has) - 1;
+          has &= has - 1;
+          uint32_t bw = __shfl_sync(FULL, bits, src);
+          while (bw && !found) {
+            const int b = __ffs(bw) - 1;
+            bw &= bw - 1;
+            const int node = (w0 + src) * 32 + b;
+            seen++;
+            // current state of the node
+            int oi = -1;
+            if (OVERLAY) oi = ov_find(I, node, lane);
+            Slot nb = slot_absent();
+            int64_t rem = 0;
+            uint32_t pr;
+            if (OVERLAY && oi >= 0) {
+              if (lane < K) nb = load_slot(I.ov_sflags, I.ov_smask, I.ov_sgte, I.ov_slte, (size_t)oi * K + lane, d.has_bounds);
+              if (lane < R) rem = I.ov_rem[(size_t)oi * R + lane];
+              pr = I.ov_present[oi];
+            } else {
+              if (lane < K)
+                nb = load_slot(I.node_sflags, I.node_smask, I.node_sgte, I.node_slte, (size_t)node * K + lane, d.has_bounds);
+              if (lane < R) rem = I.node_rem[(size_t)node * R + lane];
+              pr = I.node_rem_present[node];
+            }
+            // resources.Fits(pod requests, remaining) (resources.go:150-163)
+            bool bad = false;
+            if (lane < R) {
+              const bool present = (pr >> lane) & 1;
+              if (present && rem < 0) bad = true;
+              if (px.req[lane] > (present ? rem : 0)) bad = true;
+            }
+            if (__any_sync(FULL, bad)) {
+              if (!OVERLAY && lane == 0) I.nfit[(size_t)rv * EW + (node >> 5)] &= ~(1u << (node & 31));  // monotone
+              continue;
+            }
+            Eval ev = eval_candidate(d, px, false, nb, 0, 0, node, scratch, lane);
+            if (!ev.ok) continue;
+            // ExistingNode.Add (existingnode.go:147-155)
+            if (OVERLAY) {
+              if (oi < 0) {
+                oi = I.n_ov;
+                if (oi >= I.ov_cap) {
+                  status = KP_ERR_CAPACITY;
+                  break;
+                }
+                if (lane == 0) {
+                  I.ov_node[oi] = node;
+                  I.n_ov = oi + 1;
+                }
+              }
+              if (lane < K) {
+                const size_t i = (size_t)oi * K + lane;
+                I.ov_sflags[i] = (uint8_t)ev.F.f;
+                I.ov_smask[i] = ev.F.m;
+                if (d.has_bounds) {
+                  I.ov_sgte[i] = ev.F.gte;
+                  I.ov_slte[i] = ev.F.lte;
+                }
+              }
+              if (lane < R) I.ov_rem[(size_t)oi * R + lane] = rem - px.req[lane];
+              if (lane == 0) I.ov_present[oi] = pr | ((1u << R) - 1);
+              __syncwarp();
+            } else {
+              if (ev.changed && lane < K) {
+                const size_t i = (size_t)node * K + lane;
+                I.node_sflags[i] = (uint8_t)ev.F.f;
+                I.node_smask[i] = ev.F.m;
+                if (d.has_bounds) {
+                  I.node_sgte[i] = ev.F.gte;
+                  I.node_slte[i] = ev.F.lte;
+                }
+              }
+              if (lane < R) I.node_rem[(size_t)node * R + lane] = rem - px.req[lane];
+              if (lane == 0) {
+                I.node_rem_present[node] = pr | ((1u << R) - 1);
+                I.node_npods[node]++;
+              }
+            }
+            if (lane == 0) {
+              if (I.pod_target) {
+                I.pod_target[li] = node;
+                I.pod_error[li] = KP_PODERR_NONE;
+              }
+            }
+            if (!(d.node_flags[node] & KP_NODE_INITIALIZED)) n_uninit++;  // helpers.go:121-140
+            topo_record(d, px, ev.F, d.node_taintset[node], node, false, lane);
+            ev_existing += node + 1;
+            found = true;
+          }
+          if (status != KP_OK) break;
+        }
+        if (status != KP_OK) break;
+      }
+      if (status != KP_OK) break;
+      if (found) {
+        commits++;
+        continue;
+      }
+      ev_existing += n_active_nodes;
+    } else if (E > 0) {
+      ev_existing += n_active_nodes;
+    }
+
+    // ================= sort.Slice(newNodeClaims, len(Pods) asc) (scheduler.go:504) =================
+    if (pert != PERT_NONE) {
+      const int p = pert_pos;
+      const bool inversion = pert == PERT_INC ? (p + 1 < nC && cnt[p + 1] < cnt[p]) : (nC >= 2 && cnt[nC - 1] < cnt[nC - 2]);
+      if (inversion) {
+        bool stable = d.stable_order || nC <= 12;
+        if (!stable && nC >= 50) {
+          DevSorter s{cnt, ord};
+          int hint;
+          s.choose_pivot(0, nC, &hint);
+          stable = hint == 1;  // partialInsertionSort repairs a single inversion == stable move
+        }
+        if (stable) {
+          if (pert == PERT_INC) {  // elevated count: move right past every smaller element
+            const int c = cnt[p];
+            int lo = p + 1, hi = nC;
+            while (lo < hi) {
+              int mid = (lo + hi) >> 1;
+              if (cnt[mid] < c)
+                lo = mid + 1;
+              else
+                hi = mid;
+            }
+            const int from = p, to = lo - 1;
+            const int eo = ord[from], ec = cnt[from];
+            for (int b0 = from; b0 < to; b0 += 32) {
+              const int i = b0 + lane;
+              int vo = 0, vc = 0;
+              if (i < to) {
+                vo = ord[i + 1];
+                vc = cnt[i + 1];
+              }
+              __syncwarp();
+              if (i < to) {
+                ord[i] = vo;
+                cnt[i] = vc;
+              }
+              __syncwarp();
+            }
+            if (lane == 0) {
+              ord[to] = eo;
+              cnt[to] = ec;
+            }
+          } else {  // new claim appended: move left past every larger element
+            const int c = cnt[nC - 1];
+            int lo = 0, hi = nC - 1;
+            while (lo < hi) {
+              int mid = (lo + hi) >> 1;
+              if (cnt[mid] <= c)
+                lo = mid + 1;
+              else
+                hi = mid;
+            }
+            const int from = nC - 1, to = lo;
+            const int eo = ord[from], ec = cnt[from];
+            for (int b0 = from; b0 > to; b0 -= 32) {
+              const int i = b0 - lane;
+              int vo = 0, vc = 0;
+              if (i > to) {
+                vo = ord[i - 1];
+                vc = cnt[i - 1];
+              }
+              __syncwarp();
+              if (i > to) {
+                ord[i] = vo;
+                cnt[i] = vc;
+              }
+              __syncwarp();
+            }
+            if (lane == 0) {
+              ord[to] = eo;
+              cnt[to] = ec;
+            }
+          }
+        } else {
+          // exact pdqsort emulation by one lane (rare: ties scrambled by Go's unstable partition)
+          if (lane == 0) {
+            DevSorter s{cnt, ord};
+            s.pdqsort(0, nC, DevSorter::bits_len((unsigned long long)nC));
+          }
+          slow_sorts++;
+        }
+        __syncwarp();
+      }
+      pert = PERT_NONE;
+    }
+
+    // ================= addToInflightNode (scheduler.go:557-589) =================
+    {
+      const uint32_t* rdrow = I.rdead + (size_t)rv * RW;
+      const uint32_t* flrow = fsig >= 0 ? I.fail + (size_t)fsig * RW : nullptr;
+      for (int base = 0; base < nC && !found; base += 32) {
+        const int pos = base + lane;
+        bool pass = false;
+        int c = -1;
+        if (pos < nC) {
+          c = ord[pos];
+          pass = !((rdrow[c >> 5] >> (c & 31)) & 1u) && ((px.tmpl_ok >> I.c_tmpl[c]) & 1ull);
+          if (pass && flrow) pass = !((flrow[c >> 5] >> (c & 31)) & 1u);
+          // hostname groups: a NodeClaim is exactly one hostname domain (topologygroup.go:235-247,317-333,402-408)
+          for (int i = px.hoff; pass && i < px.hend; i++) {
+            const int4 hc = d.cls_hchk[i];
+            const int hcnt = d.host_cnt[(size_t)hc.x * d.H + E + c];
+            const int type = hc.y & 0xff, self = hc.y >> 8;
+            if (type == KP_TOPO_SPREAD)
+              pass = hcnt + self <= hc.z;
+            else if (type == KP_TOPO_AFFINITY)
+              pass = hcnt > 0 || (self && (d.g_ndomains[hc.w] - d.g_nempty[hc.w]) == 0);
+            else
+              pass = hcnt == 0;
+          }
+        }
+        unsigned m = __ballot_sync(FULL, pass);
+        while (m && !found) {
+          const int l = __ffs(m) - 1;
+          m &= m - 1;
+          const int cpos = base + l;
+          const int cc = __shfl_sync(FULL, c, l);
+          Slot b = lane < K ? load_slot(I.c_sflags, I.c_smask, I.c_sgte, I.c_slte, (size_t)cc * K + lane, d.has_bounds)
+                            : slot_absent();
+          const int64_t bq = lane < R ? I.c_req[(size_t)cc * R + lane] : 0;
+          const uint64_t bi = lane < ITW ? I.c_its[(size_t)cc * ITW + lane] : 0ull;
+          Eval ev = eval_candidate(d, px, true, b, bq, bi, E + cc, scratch, lane);
+          if (!ev.ok) {
+            if (lane == 0) {
+              if (ev.res_dead) I.rdead[(size_t)rv * RW + (cc >> 5)] |= 1u << (cc & 31);
+              if (fsig >= 0) I.fail[(size_t)fsig * RW + (cc >> 5)] |= 1u << (cc & 31);
+            }
+            __syncwarp();
+            continue;
+          }
+          // NodeClaim.Add (nodeclaim.go:207-219)
+          if (ev.changed && lane < K) {
+            const size_t i = (size_t)cc * K + lane;
+            I.c_sflags[i] = (uint8_t)ev.F.f;
+            I.c_smask[i] = ev.F.m;
+            if (d.has_bounds) {
+              I.c_sgte[i] = ev.F.gte;
+              I.c_slte[i] = ev.F.lte;
+            }
+          }
+          if (lane < R) I.c_req[(size_t)cc * R + lane] = ev.q;
+          if (lane < ITW) I.c_its[(size_t)cc * ITW + lane] = ev.its;
+          if (lane == 0) {
+            I.c_npods[cc]++;
+            cnt[cpos]++;
+            if (I.pod_target) {
+              I.pod_target[li] = KP_TARGET_CLAIM(cc);
+              I.pod_error[li] = KP_PODERR_NONE;
+            }
+          }
+          topo_record(d, px, ev.F, d.tmpl_taintset[I.c_tmpl[cc]], E + cc, true, lane);
+          __syncwarp();
+          pert = PERT_INC;
+          pert_pos = cpos;
+          ev_inflight += cpos + 1;  // claims 0..cpos were evaluated by the reference
+          found = true;
+        }
+      }
+      if (found) {
+        commits++;
+        continue;
+      }
+      ev_inflight += nC;
+    }
+
+    // ================= addToNewNodeClaim (scheduler.go:592-684) =================
+    int err = alive_tmpl ? KP_PODERR_INCOMPATIBLE : KP_PODERR_NO_TEMPLATES;
+    for (int n = 0; n < d.N && !found; n++) {
+      uint64_t tw = lane < ITW ? d.tmpl_its[(size_t)n * ITW + lane] : 0ull;
+      const bool alive = __any_sync(FULL, tw != 0);  // NewScheduler drops templates whose prefilter is empty
+      if (!alive) continue;
+      ev_tmpl++;
+      const uint32_t lp = d.tmpl_limit_present[n];
+      if (lp) {  // limits: scheduler.go:605-623, filterByRemainingResources :860-876
+        if (d.nodes_res >= 0 && (lp >> d.nodes_res & 1) && I.tmpl_remaining[(size_t)n * R + d.nodes_res] == 0) continue;
+        if (lane < ITW) {
+          uint64_t keep = 0;
+          for (uint64_t bits = tw; bits;) {
+            const int b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            const int t = lane * 64 + b;
+            bool viable = true;
+            for (int r = 0; r < R; r++)
+              if ((lp >> r & 1) && d.it_capacity[(size_t)t * R + r] > I.tmpl_remaining[(size_t)n * R + r]) viable = false;
+            if (viable) keep |= 1ull << b;
+          }
+          tw = keep;
+        }
+        if (!__any_sync(FULL, tw != 0)) continue;
+      }
+      const int cnew = nC;
+      if (cnew >= I.Cmax) {
+        status = KP_ERR_CAPACITY;
+        break;
+      }
+      if (!((px.tmpl_ok >> n) & 1ull)) continue;
+      Slot b = lane < K ? rs_slot(d, d.tmpl_rs[n], lane) : slot_absent();
+      const int64_t bq = lane < R ? d.tmpl_daemon[(size_t)n * R + lane] : 0;
+      Eval ev = eval_candidate(d, px, true, b, bq, tw, E + cnew, scratch, lane);
+      if (!ev.ok) continue;
+      // NewNodeClaim + Add
+      if (lane < K) {
+        const size_t i = (size_t)cnew * K + lane;
+        I.c_sflags[i] = (uint8_t)ev.F.f;
+        I.c_smask[i] = ev.F.m;
+        if (d.has_bounds) {
+          I.c_sgte[i] = ev.F.gte;
+          I.c_slte[i] = ev.F.lte;
+        }
+      }
+      if (lane < R) I.c_req[(size_t)cnew * R + lane] = ev.q;
+      if (lane < ITW) I.c_its[(size_t)cnew * ITW + lane] = ev.its;
+      if (lane == 0) {
+        I.c_tmpl[cnew] = n;
+        I.c_npods[cnew] = 1;
+        ord[cnew] = cnew;
+        cnt[cnew] = 1;
+        if (I.pod_target) {
+          I.pod_target[li] = KP_TARGET_CLAIM(cnew);
+          I.pod_error[li] = KP_PODERR_NONE;
+        }
+      }
+      // a recycled instance must not inherit failure bits of an earlier claim with this id
+      for (int s = lane; s < d.n_rv; s += 32) I.rdead[(size_t)s * RW + (cnew >> 5)] &= ~(1u << (cnew & 31));
+      for (int s = lane; s < d.n_fsig; s += 32) I.fail[(size_t)s * RW + (cnew >> 5)] &= ~(1u << (cnew & 31));
+      // subtractMax (scheduler.go:840-857): remaining -= max capacity over the claim's instance types
+      if (lp) {
+        for (int r = 0; r < R; r++) {
+          if (!(lp >> r & 1)) continue;
+          long long mx = 0;
+          if (lane < ITW)
+            for (uint64_t bits = ev.its; bits;) {
+              const int bb = __ffsll((long long)bits) - 1;
+              bits &= bits - 1;
+              const long long capv = d.it_capacity[(size_t)(lane * 64 + bb) * R + r];
+              if (capv > mx) mx = capv;
+            }
+          for (int o = 16; o; o >>= 1) {
+            const long long other = __shfl_xor_sync(FULL, mx, o);
+            if (other > mx) mx = other;
+          }
+          if (lane == 0) I.tmpl_remaining[(size_t)n * R + r] -= mx;
+        }
+      }
+      // Topology.Register(hostname) (nodeclaim.go:213): every hostname group learns the new, empty domain
+      if (d.GH > 0) {
+        for (int g = lane; g < d.G; g += 32)
+          if (d.groups[g].key == d.hostname_key) {
+            d.g_ndomains[g]++;
+            d.g_nempty[g]++;
+          }
+        __syncwarp();
+      }
+      topo_record(d, px, ev.F, d.tmpl_taintset[n], E + cnew, true, lane);
+      __syncwarp();
+      nC = cnew + 1;
+      pert = PERT_APPEND;
+      pert_pos = cnew;
+      found = true;
+      commits++;
+    }
+    if (status != KP_OK) break;
+    if (!found) {  // scheduler.go:415-421: record the error and requeue
+      if (lane == 0) {
+        if (I.pod_target) {
+          I.pod_error[li] = (uint8_t)err;
+          I.pod_target[li] = KP_TARGET_UNSCHEDULED;
+        }
+        I.queue[tail % cap] = li;
+        I.qcls[tail % cap] = X;
+        I.last_len[li] = tail + 1 - head;
+      }
+      tail++;
+      __syncwarp();
+    }
+  }
+  // pods still queued when the loop ends are the PodErrors (scheduler.go:415-423)
+  n_unsched = tail - head;
+  if (lane == 0) {
+    I.n_claims = nC;
+    I.n_unsched = n_unsched;
+    I.n_uninit = n_uninit;
+    I.status = status;
+    I.ev_existing = ev_existing;
+    I.ev_inflight = ev_inflight;
+    I.ev_tmpl = ev_tmpl;
+    I.commits = commits;
+    I.slow_sorts = slow_sorts;
+  }
+  __syncwarp();
+}

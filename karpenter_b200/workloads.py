@@ -280,3 +280,59 @@ def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_
                   ct_spot=enc.value_id(CAPACITY_TYPE_LABEL, "spot"),
                   ct_on_demand=enc.value_id(CAPACITY_TYPE_LABEL, "on-demand"))
     return enc, consol
+
+
+def config_existing(n_nodes=200, n_pods=3000, n_its=50, fill=0.6, limits=None) -> EncodedProblem:
+    """Provisioning against a live cluster: `n_nodes` existing KWOK nodes (zone / arch / capacity-type labels, a third
+    of them tainted, `fill` of their allocatable already used) + pending pods with zone / arch selectors and
+    tolerations.  Exercises addToExistingNode (scheduler.go:520-555) before the NodeClaim stages."""
+    from .model import quantity_units
+    b = ProblemBuilder()
+    its = kwok.generic_instance_types()[:n_its]
+    for it in its:
+        b.add_instance_type(it)
+    b.add_nodepool(default_nodepool(limits=limits), list(range(len(its))))
+    linux = [i for i, it in enumerate(its) if it.name.endswith("-linux")]
+    dn = draws(n_nodes, 4, SEED + 20)
+    node_it = np.array(linux)[(dn[:, 0] % np.uint64(len(linux))).astype(int)]
+    R = ["cpu", "memory", "pods", "ephemeral-storage"]
+    taint = Taint("bench/dedicated", "true", "NoSchedule")
+    for n in range(n_nodes):
+        it = its[node_it[n]]
+        zone = kwok.KWOK_ZONES[int(dn[n, 1] % np.uint64(4))]
+        labels = {HOSTNAME_LABEL: f"node-{n:05d}", ZONE_LABEL: zone, CAPACITY_TYPE_LABEL: "on-demand",
+                  OS_LABEL: "linux", ARCH_LABEL: it.name.split("-")[2], NODEPOOL_LABEL: "default",
+                  "node.kubernetes.io/instance-type": it.name}
+        avail = {}
+        for name in R:
+            a = quantity_units(name, it.capacity[name]) - quantity_units(name, it.overhead.get(name, 0))
+            frac = 1.0 - fill * (int(dn[n, 2] % np.uint64(100)) / 100.0)
+            avail[name] = int(a * frac)
+        avail["cpu"] = f"{avail['cpu']}m"
+        cap = dict(it.capacity)
+        cap["nodes"] = 1
+        b.add_node(StateNode(name=f"node-{n:05d}", labels=labels, available=avail, capacity=cap, nodepool="default",
+                             instance_type=it.name, taints=[taint] if int(dn[n, 3] % np.uint64(3)) == 0 else []))
+    d = draws(n_pods, 8, SEED + 21)
+    ci, mi = (d[:, 0] % np.uint64(5)).astype(int), (d[:, 1] % np.uint64(6)).astype(int)
+    zsel = np.where(d[:, 2] % np.uint64(2) == 0, (d[:, 3] % np.uint64(4)).astype(int), -1)
+    asel = np.where(d[:, 4] % np.uint64(4) == 0, (d[:, 5] % np.uint64(2)).astype(int), -1)
+    tol = (d[:, 6] % np.uint64(2)).astype(int)
+    archs = ["amd64", "arm64"]
+    table = np.zeros((5, 6, 5, 3, 2), np.int32)
+    for c in range(5):
+        for m in range(6):
+            for z in range(-1, 4):
+                for a in range(-1, 2):
+                    for k in range(2):
+                        sel = {}
+                        if z >= 0:
+                            sel[ZONE_LABEL] = kwok.KWOK_ZONES[z]
+                        if a >= 0:
+                            sel[ARCH_LABEL] = archs[a]
+                        tols = [Toleration("bench/dedicated", "Exists", "", "")] if k else []
+                        table[c, m, z + 1, a + 1, k] = b.pod_class(
+                            Pod(requests=_requests(c, m), node_selector=sel, tolerations=tols))
+    b.set_pod_arrays(table[ci, mi, zsel + 1, asel + 1, tol], np.zeros(n_pods, np.int64), d[:, 7],
+                     splitmix64(SEED + 22, np.arange(n_pods, dtype=np.uint64)))
+    return b.build()

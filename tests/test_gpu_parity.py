@@ -54,3 +54,40 @@ def test_c2_full_size_parity(handle):
 def test_c3_medium_parity(handle):
     enc = workloads.config_c3(n_apps=200, replicas=200, n_its=1000)
     assert_same(handle.solve(enc.problem), oracle_lib.solve(enc.problem), "C3[200x200] ")
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(n_nodes=50, n_pods=1500), dict(n_nodes=400, n_pods=2500, fill=0.9),
+                                dict(limits={"cpu": "3000"}), dict(limits={"cpu": "200"})])
+def test_existing_nodes_parity(handle, kw):
+    """addToExistingNode through the candidate bitmaps (k_node_cand) + exact re-check, then claims, with limits."""
+    enc = workloads.config_existing(**kw)
+    assert_same(handle.solve(enc.problem), oracle_lib.solve(enc.problem), f"existing{kw} ")
+
+
+def _consol_same(gpu, orc, what):
+    for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+        assert np.array_equal(gpu[k], orc[k]), f"{what}{k}: {np.argwhere(gpu[k] != orc[k])[:5].tolist()}"
+
+
+@pytest.mark.parametrize("n_nodes,n_pods,n_cand", [(300, 1500, 12), (200, 2500, 10), (1000, 12000, 14)])
+def test_c4_consolidation_parity(handle, n_nodes, n_pods, n_cand):
+    """Every <=3-node removal subset: decision, replacement instance types, claim / unscheduled counts."""
+    from karpenter_b200 import _abi
+    enc, consol = workloads.config_c4(n_nodes=n_nodes, n_pods=n_pods, n_candidates=n_cand, max_subset=3)
+    ci = _abi.ConsolInput(**consol)
+    _consol_same(handle.consolidate(enc.problem, ci), oracle_lib.consolidate(enc.problem, ci), f"C4[{n_nodes}] ")
+
+
+def test_c4_consolidation_uninitialized_and_price(handle):
+    """Uninitialized targets count as unscheduled (helpers.go:121-140); a candidate without a known instance type
+    zeroes the candidate price (consolidation.go:323-326)."""
+    from karpenter_b200 import _abi
+    enc, consol = workloads.config_c4(n_nodes=300, n_pods=1500, n_candidates=12, max_subset=2)
+    flags = enc.problem.get("node_flags").copy()
+    flags[::7] &= ~np.uint8(2)  # clear KP_NODE_INITIALIZED on every 7th node
+    enc.problem.set("node_flags", flags)
+    node_it = consol["node_it"].copy()
+    node_it[consol["subset_nodes"][0]] = -1
+    consol["node_it"] = node_it
+    ci = _abi.ConsolInput(**consol)
+    _consol_same(handle.consolidate(enc.problem, ci), oracle_lib.consolidate(enc.problem, ci), "C4 uninit ")
