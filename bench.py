@@ -113,6 +113,62 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_consolidation(args, h, rank, world, dist, torch):
+    """C4: every <=3-node removal subset of the 100 cheapest-to-disrupt nodes of a 10k-node cluster (166 750
+    computeConsolidation calls).  Each rank evaluates the subsets s with s % world == rank; no collective on the data
+    path, decisions would be gathered on rank 0."""
+    from karpenter_b200 import _abi, workloads
+    enc, consol = workloads.config_c4(n_nodes=args.consol_nodes, n_pods=args.consol_pods)
+    S = consol["n_subsets"]
+    mine = np.arange(rank, S, world)
+    off, nodes = consol["subset_off"], consol["subset_nodes"]
+    sizes = (off[1:] - off[:-1])[mine]
+    sub_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    sub_nodes = np.concatenate([nodes[off[i]:off[i + 1]] for i in mine]).astype(np.int32) if len(mine) else nodes[:0]
+    shard = dict(consol, n_subsets=len(mine), subset_off=sub_off, subset_nodes=sub_nodes)
+    ci = _abi.ConsolInput(**shard)
+    dev_ms, e2e_ms = [], []
+    res = None
+    for i in range(1 + max(1, min(args.steps, 3))):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        res = h.consolidate(enc.problem, ci)  # host buffers in, decisions out: upload + kernels + download
+        torch.cuda.synchronize()
+        if i >= 1:
+            e2e_ms.append(1000 * (time.perf_counter() - t0))
+            dev_ms.append(res["solve_ms"])
+    ms, e2e = float(np.mean(dev_ms)), float(np.mean(e2e_ms))
+    if dist is not None:
+        t = torch.tensor([ms, e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e = t.tolist()
+    if rank != 0:
+        return None
+    E = args.consol_nodes
+    pods_per = (consol["node_pod_off"][1:] - consol["node_pod_off"][:-1])
+    pods_s = sum(int(pods_per[nodes[off[i]:off[i + 1]]].sum()) for i in range(0, S, max(1, S // 2000))) * max(1, S // 2000)
+    balg = pods_s * B_POD + sum(E - int(off[i + 1] - off[i]) for i in range(S)) * B_CLAIM  # SURVEY.md 8(d)
+    out = {"metric": "consolidation candidates/sec", "value": S / (ms / 1000), "unit": "subsets/s", "ms": ms,
+           "n_subsets": int(S), "nodes": int(E), "running_pods": int(enc.problem.get("n_pods")),
+           "decisions": np.bincount(res["decision"], minlength=3).tolist(),
+           "e2e": {"value": S / (e2e / 1000), "unit": "subsets/s", "ms": e2e},
+           "roofline": {"bound": "hbm", "algorithmic_bytes": int(balg), "achieved": balg / (ms / 1000) / 1e9,
+                        "unit": "GB/s", "note": "reference algorithm re-reads every node row per pod per subset; "
+                        "k_consolidate reads per-class candidate bitmaps instead (L2 resident)"}}
+    if not args.no_cpu_baseline and world == 1:
+        from tests import oracle_lib
+        n = min(S, 400)
+        smp = dict(consol, n_subsets=n, subset_off=off[:n + 1], subset_nodes=nodes[:off[n]])
+        t0 = time.perf_counter()
+        oracle_lib.consolidate(enc.problem, _abi.ConsolInput(**smp))
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n / dt, "unit": "subsets/s", "cores": 1, "kind": "port",
+                               "sample": f"first {n} subsets, single thread of {os.cpu_count()} host cores"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -121,6 +177,9 @@ def main():
     ap.add_argument("--impl", default="karpsolve")
     ap.add_argument("--pods", type=int, default=N_PODS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-consolidation", action="store_true")
+    ap.add_argument("--consol-nodes", type=int, default=10_000)
+    ap.add_argument("--consol-pods", type=int, default=200_000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -207,9 +266,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_solve", "peak_source": "measured" if peaks else "fallback",
+                         "kernel": "k_wsolve", "peak_source": "measured" if peaks else "fallback",
                          "algorithmic_bytes": int(balg),
-                         "note": "k_solve is a latency-bound serial first-fit walk (one CTA); see DESIGN.md"},
+                         "note": "k_wsolve is a latency-bound serial first-fit chain (one warp per Scheduler); see DESIGN.md"},
             "clocks": sampler.summary(),
             "unscheduled": int((res["pod_target"] == -1).sum()), "node_claims": int(res["n_claims"]),
             "wall_s_timed_region": wall,
@@ -224,6 +283,13 @@ def main():
             line["cpu_baseline"] = {"value": CPU_SAMPLE_PODS / dt, "unit": "pods/s", "cores": 1, "kind": "port",
                                     "sample": f"first {CPU_SAMPLE_PODS} pods of the workload, one full Solve, single "
                                               f"thread of {os.cpu_count()} host cores"}
+    # ---- second headline metric: consolidation candidates/sec (C4), subsets sharded round-robin across ranks
+    consol = None
+    if not args.no_consolidation:
+        consol = run_consolidation(args, h, rank, world, dist if world > 1 else None, torch)
+    if rank == 0:
+        if consol is not None:
+            line["consolidation"] = consol
         print(json.dumps(line))
     h.close()
     if world > 1:

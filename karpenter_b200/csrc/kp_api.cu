@@ -265,7 +265,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
       hh[5] = t.cls_rec_off[x + 1];
       hh[6] = -1;
       if (t.cls_match_off[x + 1] == t.cls_match_off[x] && offerings_monotone && row_monotone(t.cls_rs[x])) {
-        auto key = std::make_pair(t.cls_rs[x], t.cls_rv[x]);
+        auto key = std::make_pair(t.cls_rs[x], 0);  // failure bits record requirement incompatibility only
         auto it = fsigs.find(key);
         if (it == fsigs.end()) it = fsigs.emplace(key, (int)fsigs.size()).first;
         hh[6] = it->second;
@@ -376,6 +376,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(zeros(h, &d.c_sgte, C * t.K));
   CK(zeros(h, &d.c_slte, C * t.K));
   CK(zeros(h, &d.c_its, C * t.ITW));
+  CK(zeros(h, &d.c_j, C * t.R));
   CK(zeros(h, &d.order, C));
   CK(zeros(h, &d.cnt_at, C));
   CK(zeros(h, &d.rdead, (size_t)t.n_rv * ((C + 31) / 32)));
@@ -894,6 +895,7 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   CK(zeros(h, &q.c_sflags, slots * cq * K));
   CK(zeros(h, &q.c_smask, slots * cq * K));
   CK(zeros(h, &q.c_its, slots * cq * ITW));
+  CK(zeros(h, &q.c_j, slots * cq * R));
   CK(zeros(h, &q.rdead, slots * (size_t)std::max(t.n_rv, 1) * RWc));
   CK(zeros(h, &q.fail, slots * (size_t)std::max(d.n_fsig, 1) * RWc));
   CK(zeros(h, &q.tmpl_remaining, slots * (size_t)std::max(N, 1) * R));

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev 
     I.c_sgte = d.c_sgte;
     I.c_slte = d.c_slte;
     I.c_its = d.c_its;
+    I.c_j = d.c_j;
     I.order = d.order;
     I.cnt_at = d.cnt_at;
     I.rdead = d.rdead;
@@ -239,6 +240,7 @@ struct KpConsol {
   uint64_t* c_smask;
   int64_t *c_sgte, *c_slte;
   uint64_t* c_its;
+  int32_t* c_j;
   uint32_t *rdead, *fail;
   int64_t* tmpl_remaining;
   int32_t* ov_node;
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
     I.c_sgte = q.c_sgte ? q.c_sgte + slot * capq * K : nullptr;
     I.c_slte = q.c_slte ? q.c_slte + slot * capq * K : nullptr;
     I.c_its = q.c_its + slot * capq * ITW;
+    I.c_j = q.c_j + slot * capq * R;
     I.order = q.order + slot * capq;
     I.cnt_at = q.cnt_at + slot * capq;
     I.rdead = q.rdead + slot * (size_t)d.n_rv * RW;

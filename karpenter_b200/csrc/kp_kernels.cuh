@@ -42,20 +42,18 @@ __device__ __forceinline__ Slot rs_slot(const KpDev& d, int rs, int k) {
 //
 // fits_word: resources.Fits(total, allocatable) via ">= threshold" bitmaps: lane r ranks q[r] in the sorted distinct
 // allocatable values of resource r, the answer is the AND of the R selected rows.
-__device__ __forceinline__ uint64_t fits_word(const KpDev& d, int64_t q_lane, int lane) {
+// `j_lane` (lane r): in/out threshold row of resource r.  Requests of a candidate only grow, so the row found for the
+// previous total is a valid starting point and the search usually advances by zero or one step.
+__device__ __forceinline__ uint64_t fits_word(const KpDev& d, int64_t q_lane, int lane, int* j_lane) {
   const int R = d.R, ITW = d.ITW;
   int j = 0;
   if (lane < R) {
-    int lo = d.ge_off[lane], hi = d.ge_off[lane + 1];
-    const int end = hi;
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (d.ge_vals[mid] < q_lane)
-        lo = mid + 1;
-      else
-        hi = mid;
-    }
+    const int end = d.ge_off[lane + 1];
+    int lo = *j_lane;
+    if (lo < d.ge_off[lane]) lo = d.ge_off[lane];
+    while (lo < end && d.ge_vals[lo] < q_lane) lo++;
     j = lo == end ? -1 : lo;  // -1: the request exceeds every instance type
+    *j_lane = lo;
   }
   uint64_t fw = (lane < ITW) ? d.it_valid[lane] : 0ull;
   for (int r = 0; r < R; r++) {
@@ -114,7 +112,8 @@ __device__ __forceinline__ uint64_t compat_off_word(const KpDev& d, const Slot* 
 // word w of compat & fits & hasOffering (nodeclaim.go:434-445); *fits_out = the resource-only word
 __device__ __forceinline__ uint64_t filter_its_word(const KpDev& d, const Slot* S, int64_t q_lane, int lane,
                                                     uint64_t* fits_out) {
-  uint64_t fw = fits_word(d, q_lane, lane);
+  int j0 = 0;
+  uint64_t fw = fits_word(d, q_lane, lane, &j0);
   *fits_out = fw;
   return compat_off_word(d, S, lane) & fw;
 }
@@ -189,6 +188,8 @@ struct Eval {
   bool ok;
   bool res_dead;   // no remaining instance type can ever hold these requests again (monotone)
   bool changed;    // the pod tightened at least one requirement slot of the candidate
+  bool compat_fail;  // rejected by Requirements.Compatible(pod requirements) alone: independent of requests
+  int j;           // lane r: threshold row of the total requests (fits_word)
   Slot F;          // lane k: final requirement slot of key k
   int64_t q;       // lane r: total requests (claims)
   uint64_t its;    // lane w: surviving instance-type word (claims)
@@ -196,8 +197,12 @@ struct Eval {
 
 // The pod being placed, staged once per pod in shared memory (class row of the problem + its requirement slots).
 struct PodCtx {
-  int pod, cls, tolset, rv;
-  int moff, mend, roff, rend, fsig, nsig, hoff, hend;
+  union {
+    struct {
+      int tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend, cls, pod;
+    };
+    int hdr[KP_HDR + 2];  // same order as a cr_hdr row, then class id and pod id
+  };
   unsigned long long tmpl_ok;  // bit n: template n's taints are tolerated (taints.go:49-66)
   int64_t req[KP_MAXR];
   Slot pod_slot[KP_MAXK];
@@ -210,11 +215,14 @@ struct PodCtx {
 //   host       index of the candidate's hostname domain in host_cnt
 //   scratch    per-warp shared memory, KP_MAXK slots
 __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px, bool is_claim, const Slot& base,
-                                               int64_t base_q, uint64_t base_its, int host, Slot* scratch, int lane) {
+                                               int64_t base_q, uint64_t base_its, int base_j, int host, Slot* scratch,
+                                               int lane) {
   Eval ev;
   ev.ok = false;
   ev.res_dead = false;
   ev.changed = false;
+  ev.compat_fail = false;
+  ev.j = 0;
   const int K = d.K;
   const bool allow_undef = is_claim;  // ExistingNode.CanAdd passes no compatibility options
   const bool wk = lane < K ? d.key_wellknown[lane] : false;
@@ -222,7 +230,10 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   Slot pod = lane < K ? px.pod_slot[lane] : slot_absent();
   // requirements.Compatible(pod requirements) then Add
   bool bad = lane < K && !slot_compatible(ki, base, pod, wk, allow_undef);
-  if (__any_sync(FULL, bad)) return ev;
+  if (__any_sync(FULL, bad)) {
+    ev.compat_fail = true;
+    return ev;
+  }
   Slot M = lane < K ? slot_add(ki, base, pod) : slot_absent();
   // Topology.AddRequirements (topology.go:226-248)
   const int moff = px.moff, mend = px.mend;
@@ -273,7 +284,8 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   const bool changed = __any_sync(FULL, lane < K && !slot_eq(M, base));
   ev.changed = changed;
   int64_t q = base_q + (lane < d.R ? px.req[lane] : 0);
-  uint64_t fw = fits_word(d, q, lane) & base_its;
+  ev.j = base_j;
+  uint64_t fw = fits_word(d, q, lane, &ev.j) & base_its;
   uint64_t w = fw;
   if (changed) {
     if (lane < K) scratch[lane] = M;
@@ -312,18 +324,7 @@ __device__ __forceinline__ ClassRegs load_class_regs(const KpDev& d, int X, int 
   return c;
 }
 __device__ __forceinline__ void store_class_regs(const KpDev& d, PodCtx& px, const ClassRegs& c, int lane) {
-  if (lane == 0) px.tolset = c.hdr;
-  if (lane == 1) px.rv = c.hdr;
-  if (lane == 2) px.moff = c.hdr;
-  if (lane == 3) px.mend = c.hdr;
-  if (lane == 4) px.roff = c.hdr;
-  if (lane == 5) px.rend = c.hdr;
-  if (lane == 6) px.fsig = c.hdr;
-  if (lane == 7) px.nsig = c.hdr;
-  if (lane == 8) px.hoff = c.hdr;
-  if (lane == 9) px.hend = c.hdr;
-  if (lane == 10) px.cls = c.hdr;
-  if (lane == 11) px.pod = c.hdr;
+  if (lane < KP_HDR + 2) px.hdr[lane] = c.hdr;
   if (lane == 0) px.tmpl_ok = c.tmpl_ok;
   if (lane < d.R) px.req[lane] = c.req;
   if (lane < d.K) {

@@ -147,12 +147,13 @@ struct KpDev {
   int64_t* c_sgte;
   int64_t* c_slte;
   uint64_t* c_its;                // [Cmax*ITW]
+  int32_t* c_j;                   // [Cmax*R] threshold rows of the claim's requests (fits_word)
   int32_t* order;                 // [Cmax] s.newNodeClaims as claim ids
   int32_t* cnt_at;                // [Cmax] len(Pods) by position
   uint32_t* rdead;                // [n_rv * ceil(Cmax/32)] claim can never again fit this request vector
   // monotone failure cache: for a topology-free class whose keys can never be "undefined" on a NodeClaim, CanAdd only
   // ever flips from true to false (requirements tighten, requests grow, instance types shrink: nodeclaim.go:207-219)
-  int n_fsig;                     // distinct (requirements, requests) signatures of such classes
+  int n_fsig;                     // distinct requirement sets of such classes
   uint32_t* fail;                 // [n_fsig * ceil(Cmax/32)] claim rejected this signature once
   // existing-node candidate bitmaps (supersets; the exact CanAdd runs on every candidate)
   int n_nsig, EW;                 // distinct (requirements, tolerations) signatures; words per row = ceil(E/32)

@@ -36,6 +36,7 @@ struct WInst {
   uint64_t* c_smask;
   int64_t *c_sgte, *c_slte;
   uint64_t* c_its;
+  int32_t* c_j;             // [Cmax*R] threshold row of the claim's requests per resource (fits_word)
   int32_t *order, *cnt_at;  // s.newNodeClaims: claim id / len(Pods) by position
   uint32_t *rdead, *fail;
   int RW;                   // words per rdead / fail row
@@ -205,7 +206,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
               if (!OVERLAY && lane == 0) I.nfit[(size_t)rv * EW + (node >> 5)] &= ~(1u << (node & 31));  // monotone
               continue;
             }
-            Eval ev = eval_candidate(d, px, false, nb, 0, 0, node, scratch, lane);
+            Eval ev = eval_candidate(d, px, false, nb, 0, 0, 0, node, scratch, lane);
             if (!ev.ok) continue;
             // ExistingNode.Add (existingnode.go:147-155)
             if (OVERLAY) {
@@ -395,11 +396,12 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
                             : slot_absent();
           const int64_t bq = lane < R ? I.c_req[(size_t)cc * R + lane] : 0;
           const uint64_t bi = lane < ITW ? I.c_its[(size_t)cc * ITW + lane] : 0ull;
-          Eval ev = eval_candidate(d, px, true, b, bq, bi, E + cc, scratch, lane);
+          const int bj = lane < R ? I.c_j[(size_t)cc * R + lane] : 0;
+          Eval ev = eval_candidate(d, px, true, b, bq, bi, bj, E + cc, scratch, lane);
           if (!ev.ok) {
             if (lane == 0) {
               if (ev.res_dead) I.rdead[(size_t)rv * RW + (cc >> 5)] |= 1u << (cc & 31);
-              if (fsig >= 0) I.fail[(size_t)fsig * RW + (cc >> 5)] |= 1u << (cc & 31);
+              if (fsig >= 0 && ev.compat_fail) I.fail[(size_t)fsig * RW + (cc >> 5)] |= 1u << (cc & 31);
             }
             __syncwarp();
             continue;
@@ -414,7 +416,10 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
               I.c_slte[i] = ev.F.lte;
             }
           }
-          if (lane < R) I.c_req[(size_t)cc * R + lane] = ev.q;
+          if (lane < R) {
+            I.c_req[(size_t)cc * R + lane] = ev.q;
+            I.c_j[(size_t)cc * R + lane] = ev.j;
+          }
           if (lane < ITW) I.c_its[(size_t)cc * ITW + lane] = ev.its;
           if (lane == 0) {
             I.c_npods[cc]++;
@@ -472,7 +477,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       if (!((px.tmpl_ok >> n) & 1ull)) continue;
       Slot b = lane < K ? rs_slot(d, d.tmpl_rs[n], lane) : slot_absent();
       const int64_t bq = lane < R ? d.tmpl_daemon[(size_t)n * R + lane] : 0;
-      Eval ev = eval_candidate(d, px, true, b, bq, tw, E + cnew, scratch, lane);
+      Eval ev = eval_candidate(d, px, true, b, bq, tw, 0, E + cnew, scratch, lane);
       if (!ev.ok) continue;
       // NewNodeClaim + Add
       if (lane < K) {
@@ -484,7 +489,10 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           I.c_slte[i] = ev.F.lte;
         }
       }
-      if (lane < R) I.c_req[(size_t)cnew * R + lane] = ev.q;
+      if (lane < R) {
+        I.c_req[(size_t)cnew * R + lane] = ev.q;
+        I.c_j[(size_t)cnew * R + lane] = ev.j;
+      }
       if (lane < ITW) I.c_its[(size_t)cnew * ITW + lane] = ev.its;
       if (lane == 0) {
         I.c_tmpl[cnew] = n;

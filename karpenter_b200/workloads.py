@@ -220,14 +220,18 @@ def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_
                     np.zeros(n_pods, np.int64)], axis=1).astype(np.int64)
     used = np.zeros((n_nodes, 4), np.int64)
     pod_node = np.full(n_pods, -1, np.int64)
+    hopeless = np.zeros((5, 6), bool)  # request mixes that already failed a full scan (usage only grows)
     for i in range(n_pods):
         n = i % n_nodes
-        for _ in range(n_nodes):
-            if np.all(used[n] + req[i] <= alloc[n]):
-                break
-            n = (n + 1) % n_nodes
-        else:
-            continue  # cluster full: drop the pod
+        if not np.all(used[n] + req[i] <= alloc[n]):
+            if hopeless[ci[i], mi[i]]:
+                continue
+            ok = np.nonzero(np.all(used + req[i] <= alloc, axis=1))[0]  # first fit, cyclically from n
+            if ok.size == 0:
+                hopeless[ci[i], mi[i]] = True
+                continue  # cluster full: drop the pod
+            j = np.searchsorted(ok, n)
+            n = int(ok[j]) if j < ok.size else int(ok[0])
         used[n] += req[i]
         pod_node[i] = n
     table = np.zeros((5, 6), np.int32)
