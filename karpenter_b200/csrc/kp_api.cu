@@ -571,12 +571,25 @@ static int run_solve(kp_handle* h) {
   const size_t budget = 224 * 1024;
   const size_t fixed = KP_ALIGN16(sizeof(WSolveShared));
   size_t tb = plan_tables(h, fixed, budget);
-  const size_t RW = ((size_t)d.Cmax + 31) / 32;
-  const size_t small = (size_t)d.Cmax * 12 + ((size_t)d.n_rv + (size_t)std::max(d.n_fsig, 1)) * RW * 4;
-  int small_in_smem = fixed + tb + small + 64 <= budget;
-  size_t smem = fixed + tb + (small_in_smem ? small : 0) + 64;
+  const size_t rows = (size_t)d.n_rv + (size_t)std::max(d.n_fsig, 1);
+  auto small_bytes = [&](int cs) { return (size_t)cs * 12 + rows * (((size_t)cs + 31) / 32) * 4; };
+  int CS = 0;
+  if (fixed + tb + small_bytes(64) + 64 <= budget) {  // the largest multiple of 32 that fits, capped at Cmax
+    int lo = 64, hi = ((d.Cmax + 31) / 32) * 32;
+    while (lo < hi) {
+      int mid = ((lo + hi + 32) / 64) * 32;
+      if (mid <= lo) mid = lo + 32;
+      if (fixed + tb + small_bytes(mid) + 64 <= budget)
+        lo = mid;
+      else
+        hi = mid - 32;
+    }
+    CS = lo;
+  }
+  if (const char* lim = getenv("KP_CS_LIMIT")) CS = std::min(CS, std::max(0, atoi(lim)) / 32 * 32);  // test knob
+  size_t smem = fixed + tb + (CS ? small_bytes(CS) : 0) + 64;
   CK(cudaFuncSetAttribute(k_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_wsolve<<<1, 32, smem, h->stream>>>(d, small_in_smem);
+  k_wsolve<<<1, 32, smem, h->stream>>>(d, CS);
   h->stats.kernel_launches++;
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));

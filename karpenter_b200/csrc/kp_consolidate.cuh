@@ -124,7 +124,7 @@ struct WSolveShared {
   Slot scratch[KP_MAXK];
 };
 
-__global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev d_in, int small_in_smem) {
+__global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WSolveShared& sh = *reinterpret_cast<WSolveShared*>(smem_raw);
   const int lane = threadIdx.x;
@@ -170,28 +170,38 @@ __global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev 
     I.removed = nullptr;
     I.ov_cap = 0;
     I.n_ov = 0;
-    if (small_in_smem) {  // claim order, template ids and the failure bitmaps live in shared memory
+    I.CS = 0;
+    I.g_order = d.order;
+    I.g_cnt_at = d.cnt_at;
+    I.g_c_tmpl = d.c_tmpl;
+    I.g_rdead = d.rdead;
+    I.g_fail = d.fail;
+    I.g_RW = RW;
+    if (CS > 0) {  // claim order, template ids and the failure bitmaps of the first CS claims live in shared memory
+      const int RWs = (CS + 31) >> 5;
       unsigned char* p = tab + d_in.tab_bytes;
       I.order = reinterpret_cast<int32_t*>(p);
-      p += (size_t)Cmax * 4;
+      p += (size_t)CS * 4;
       I.cnt_at = reinterpret_cast<int32_t*>(p);
-      p += (size_t)Cmax * 4;
+      p += (size_t)CS * 4;
       I.c_tmpl = reinterpret_cast<int32_t*>(p);
-      p += (size_t)Cmax * 4;
+      p += (size_t)CS * 4;
       I.rdead = reinterpret_cast<uint32_t*>(p);
-      p += (size_t)d.n_rv * RW * 4;
+      p += (size_t)d.n_rv * RWs * 4;
       I.fail = reinterpret_cast<uint32_t*>(p);
+      I.RW = RWs;
+      I.CS = CS;
     }
   }
   __syncwarp();
-  if (small_in_smem) {
-    for (int i = lane; i < d.n_rv * RW; i += 32) I.rdead[i] = 0;
-    for (int i = lane; i < d.n_fsig * RW; i += 32) I.fail[i] = 0;
+  if (CS > 0) {
+    for (int i = lane; i < d.n_rv * I.RW; i += 32) I.rdead[i] = 0;
+    for (int i = lane; i < d.n_fsig * I.RW; i += 32) I.fail[i] = 0;
     __syncwarp();
   }
   wsolve_run<false>(d, I, sh.ctx, sh.scratch, lane);
   const int nC = I.n_claims;
-  if (small_in_smem) {  // the host reads the final order (claim_rank) and template ids from global memory
+  if (I.CS > 0) {  // the host reads the final order (claim_rank) and template ids from global memory
     for (int i = lane; i < nC; i += 32) {
       d_in.order[i] = I.order[i];
       d_in.cnt_at[i] = I.cnt_at[i];
@@ -313,6 +323,7 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
     I.nfit = d.nfit;
     I.nstat = d.nstat;
     I.nactive = d.nactive;
+    I.CS = 0;
     I.ov_cap = capq;
     I.ov_node = q.ov_node + slot * capq;
     I.ov_rem = q.ov_rem + slot * capq * R;

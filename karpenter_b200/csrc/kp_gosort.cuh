@@ -1,25 +1,136 @@
-// kp_gosort.cuh -- Go's sort.Slice (pdqsort_func of package sort, go1.26) on the claim-order arrays, device side.
+// kp_gosort.cuh -- Go's sort.Slice (pdqsort_func of package sort, go1.26) on the claim-order arrays, executed by one
+// warp.
+//
+// Emulated exactly because the permutation it leaves among claims with EQUAL pod counts decides first-fit
+// (scheduler.go:504).  key = len(Pods) by position, val = claim id by position.  The control flow is Go's, statement
+// for statement, and is warp-uniform; what the warp parallelises are the linear scans inside it (the two-pointer
+// partition loops, the "first inversion" search of partialInsertionSort, the element shifts, insertion sort of <= 12
+// elements as a stable rank computation), each a 32-wide compare + ballot instead of a scalar loop.
 #pragma once
 #include <cuda_runtime.h>
 
-// ---- Go's sort.Slice (pdqsort_func, package sort of go1.26) on the claim-order arrays -------------------------
-// Emulated exactly because the permutation it leaves among claims with EQUAL pod counts decides first-fit
-// (scheduler.go:504).  key = len(Pods) by position, val = claim id by position.
-struct DevSorter {
+#ifndef FULL
+#define FULL 0xffffffffu
+#endif
+
+struct WarpSorter {
   int* key;
   int* val;
+  int lane;
+
   __device__ bool less(int i, int j) const { return key[i] < key[j]; }
   __device__ void swap(int i, int j) {
-    int t = key[i];
-    key[i] = key[j];
-    key[j] = t;
-    t = val[i];
-    val[i] = val[j];
-    val[j] = t;
+    if (lane == 0) {
+      int t = key[i];
+      key[i] = key[j];
+      key[j] = t;
+      t = val[i];
+      val[i] = val[j];
+      val[j] = t;
+    }
+    __syncwarp();
   }
+  // smallest idx in [i, j] whose key is NOT < pv (j + 1 if none):   for i <= j && less(i, a) { i++ }
+  __device__ int first_not_less(int i, int j, int pv) const {
+    for (int b = i; b <= j; b += 32) {
+      int idx = b + lane;
+      unsigned m = __ballot_sync(FULL, idx <= j && !(key[idx] < pv));
+      if (m) return b + __ffs(m) - 1;
+    }
+    return j + 1;
+  }
+  // largest idx in [i, j] whose key IS < pv (i - 1 if none):        for i <= j && !less(j, a) { j-- }
+  __device__ int last_less(int i, int j, int pv) const {
+    for (int b = j; b >= i; b -= 32) {
+      int idx = b - lane;
+      unsigned m = __ballot_sync(FULL, idx >= i && key[idx] < pv);
+      if (m) return b - (__ffs(m) - 1);
+    }
+    return i - 1;
+  }
+  // smallest idx in [i, j] with pv < key[idx] (j + 1 if none):      for i <= j && !less(a, i) { i++ }
+  __device__ int first_greater(int i, int j, int pv) const {
+    for (int b = i; b <= j; b += 32) {
+      int idx = b + lane;
+      unsigned m = __ballot_sync(FULL, idx <= j && pv < key[idx]);
+      if (m) return b + __ffs(m) - 1;
+    }
+    return j + 1;
+  }
+  // largest idx in [i, j] with !(pv < key[idx]) (i - 1 if none):    for i <= j && less(a, j) { j-- }
+  __device__ int last_not_greater(int i, int j, int pv) const {
+    for (int b = j; b >= i; b -= 32) {
+      int idx = b - lane;
+      unsigned m = __ballot_sync(FULL, idx >= i && !(pv < key[idx]));
+      if (m) return b - (__ffs(m) - 1);
+    }
+    return i - 1;
+  }
+  // move element `from` to position `to` (to < from), shifting [to, from) right by one
+  __device__ void rotate_right(int to, int from) {
+    const int ek = key[from], ev = val[from];
+    for (int b0 = from; b0 > to; b0 -= 32) {
+      const int i = b0 - lane;
+      int vk = 0, vv = 0;
+      if (i > to) {
+        vk = key[i - 1];
+        vv = val[i - 1];
+      }
+      __syncwarp();
+      if (i > to) {
+        key[i] = vk;
+        val[i] = vv;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      key[to] = ek;
+      val[to] = ev;
+    }
+    __syncwarp();
+  }
+  // move element `from` to position `to` (to > from), shifting (from, to] left by one
+  __device__ void rotate_left(int from, int to) {
+    const int ek = key[from], ev = val[from];
+    for (int b0 = from; b0 < to; b0 += 32) {
+      const int i = b0 + lane;
+      int vk = 0, vv = 0;
+      if (i < to) {
+        vk = key[i + 1];
+        vv = val[i + 1];
+      }
+      __syncwarp();
+      if (i < to) {
+        key[i] = vk;
+        val[i] = vv;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      key[to] = ek;
+      val[to] = ev;
+    }
+    __syncwarp();
+  }
+  // insertionSortCmpFunc on [a, b), b - a <= 32: insertion sort is stable, so the result is the stable rank order
   __device__ void insertion_sort(int a, int b) {
-    for (int i = a + 1; i < b; i++)
-      for (int j = i; j > a && less(j, j - 1); j--) swap(j, j - 1);
+    const int n = b - a;
+    int k = 0, v = 0;
+    if (lane < n) {
+      k = key[a + lane];
+      v = val[a + lane];
+    }
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+      const int kj = __shfl_sync(FULL, k, j);
+      rank += (kj < k || (kj == k && j < lane)) ? 1 : 0;
+    }
+    __syncwarp();
+    if (lane < n) {
+      key[a + rank] = k;
+      val[a + rank] = v;
+    }
+    __syncwarp();
   }
   __device__ void sift_down(int lo, int hi, int first) {
     int root = lo;
@@ -42,9 +153,10 @@ struct DevSorter {
   }
   __device__ int partition(int a, int b, int pivot, bool* already) {
     swap(a, pivot);
+    const int pv = key[a];
     int i = a + 1, j = b - 1;
-    while (i <= j && less(i, a)) i++;
-    while (i <= j && !less(j, a)) j--;
+    i = first_not_less(i, j, pv);
+    j = last_less(i, j, pv);
     if (i > j) {
       swap(j, a);
       *already = true;
@@ -54,8 +166,8 @@ struct DevSorter {
     i++;
     j--;
     for (;;) {
-      while (i <= j && less(i, a)) i++;
-      while (i <= j && !less(j, a)) j--;
+      i = first_not_less(i, j, pv);
+      j = last_less(i, j, pv);
       if (i > j) break;
       swap(i, j);
       i++;
@@ -67,10 +179,11 @@ struct DevSorter {
   }
   __device__ int partition_equal(int a, int b, int pivot) {
     swap(a, pivot);
+    const int pv = key[a];
     int i = a + 1, j = b - 1;
     for (;;) {
-      while (i <= j && !less(a, i)) i++;
-      while (i <= j && less(a, j)) j--;
+      i = first_greater(i, j, pv);
+      j = last_not_greater(i, j, pv);
       if (i > j) break;
       swap(i, j);
       i++;
@@ -81,22 +194,50 @@ struct DevSorter {
   __device__ bool partial_insertion_sort(int a, int b) {
     int i = a + 1;
     for (int j = 0; j < 5; j++) {
-      while (i < b && !less(i, i - 1)) i++;
+      {  // for i < b && !less(i, i-1) { i++ }
+        int found = b;
+        for (int b0 = i; b0 < b; b0 += 32) {
+          int idx = b0 + lane;
+          unsigned m = __ballot_sync(FULL, idx < b && key[idx] < key[idx - 1]);
+          if (m) {
+            found = b0 + __ffs(m) - 1;
+            break;
+          }
+        }
+        i = found;
+      }
       if (i == b) return true;
       if (b - a < 50) return false;
       swap(i, i - 1);
-      if (i - a >= 2)
-        for (int k = i - 1; k >= 1; k--) {
-          if (!less(k, k - 1)) break;
-          swap(k, k - 1);
+      if (i - a >= 2) {  // shift the smaller one to the left:  for j := i-1; j >= 1; j-- { if !less(j, j-1) break; swap }
+        const int x = key[i - 1];
+        int stop = last_not_greater_from(i - 2, x);  // largest m in [0, i-2] with key[m] <= x, else -1
+        if (stop + 1 < i - 1) rotate_right(stop + 1, i - 1);
+      }
+      if (b - i >= 2) {  // shift the greater one to the right: for j := i+1; j < b; j++ { if !less(j, j-1) break; swap }
+        const int x = key[i];
+        int stop = b;  // smallest m in [i+1, b) with !(key[m] < x), else b
+        for (int b0 = i + 1; b0 < b; b0 += 32) {
+          int idx = b0 + lane;
+          unsigned m = __ballot_sync(FULL, idx < b && !(key[idx] < x));
+          if (m) {
+            stop = b0 + __ffs(m) - 1;
+            break;
+          }
         }
-      if (b - i >= 2)
-        for (int k = i + 1; k < b; k++) {
-          if (!less(k, k - 1)) break;
-          swap(k, k - 1);
-        }
+        if (stop - 1 > i) rotate_left(i, stop - 1);
+      }
     }
     return false;
+  }
+  // largest m in [0, hi] with key[m] <= x, else -1
+  __device__ int last_not_greater_from(int hi, int x) const {
+    for (int b = hi; b >= 0; b -= 32) {
+      int idx = b - lane;
+      unsigned m = __ballot_sync(FULL, idx >= 0 && !(x < key[idx]));
+      if (m) return b - (__ffs(m) - 1);
+    }
+    return -1;
   }
   __device__ static int bits_len(unsigned long long x) { return x ? 64 - __clzll((long long)x) : 0; }
   __device__ void break_patterns(int a, int b) {
@@ -145,12 +286,19 @@ struct DevSorter {
     return j;
   }
   __device__ void reverse_range(int a, int b) {
-    int i = a, j = b - 1;
-    while (i < j) {
-      swap(i, j);
-      i++;
-      j--;
+    const int n = b - a;
+    for (int b0 = 0; b0 < n / 2; b0 += 32) {
+      const int t = b0 + lane;
+      if (t < n / 2) {
+        const int i = a + t, j = b - 1 - t;
+        int tk = key[i], tv = val[i];
+        key[i] = key[j];
+        val[i] = val[j];
+        key[j] = tk;
+        val[j] = tv;
+      }
     }
+    __syncwarp();
   }
   __device__ void pdqsort(int a, int b, int limit) {
     bool wasBalanced = true, wasPartitioned = true;
@@ -199,5 +347,3 @@ struct DevSorter {
     }
   }
 };
-
-

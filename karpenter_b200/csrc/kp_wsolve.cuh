@@ -40,6 +40,12 @@ struct WInst {
   int32_t *order, *cnt_at;  // s.newNodeClaims: claim id / len(Pods) by position
   uint32_t *rdead, *fail;
   int RW;                   // words per rdead / fail row
+  // While the claim order, template ids and failure bitmaps fit, they live in shared memory (CS = claims the shared
+  // copies can hold, 0 = not in use); the moment a claim id reaches CS everything migrates to the global arrays below.
+  int CS;
+  int32_t *g_order, *g_cnt_at, *g_c_tmpl;
+  uint32_t *g_rdead, *g_fail;
+  int g_RW;
   int64_t* tmpl_remaining;  // [N*R]
   // existing nodes
   int64_t* node_rem;
@@ -75,18 +81,44 @@ __device__ __forceinline__ int ov_find(const WInst& I, int node, int lane) {
   return -1;
 }
 
+// shared -> global migration of the small per-claim arrays (see WInst::CS); executed once, by the whole warp
+__device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, int lane) {
+  for (int i = lane; i < nC; i += 32) {
+    I.g_order[i] = I.order[i];
+    I.g_cnt_at[i] = I.cnt_at[i];
+    I.g_c_tmpl[i] = I.c_tmpl[i];
+  }
+  const int RWs = I.RW, RWg = I.g_RW;
+  for (int r = 0; r < d.n_rv; r++)
+    for (int w = lane; w < RWg; w += 32) I.g_rdead[(size_t)r * RWg + w] = w < RWs ? I.rdead[(size_t)r * RWs + w] : 0u;
+  for (int r = 0; r < d.n_fsig; r++)
+    for (int w = lane; w < RWg; w += 32) I.g_fail[(size_t)r * RWg + w] = w < RWs ? I.fail[(size_t)r * RWs + w] : 0u;
+  __syncwarp();
+  if (lane == 0) {
+    I.order = I.g_order;
+    I.cnt_at = I.g_cnt_at;
+    I.c_tmpl = I.g_c_tmpl;
+    I.rdead = I.g_rdead;
+    I.fail = I.g_fail;
+    I.RW = I.g_RW;
+    I.CS = 0;
+  }
+  __syncwarp();
+}
+
 // One Scheduler.Solve over the instance's queue.  OVERLAY: existing-node state = shared base + private overlay.
 template <bool OVERLAY>
 __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch, const int lane) {
-  const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, EW = d.EW, RW = I.RW;
+  const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, EW = d.EW;
+  int RW = I.RW;
   int head = 0, tail = I.P;
   const int cap = I.P + 1;
   int nC = 0;
   int pert = PERT_NONE, pert_pos = 0;
   long long ev_existing = 0, ev_inflight = 0, ev_tmpl = 0, commits = 0, slow_sorts = 0;
   int n_unsched = 0, n_uninit = 0, status = KP_OK;
-  int32_t* const ord = I.order;
-  int32_t* const cnt = I.cnt_at;
+  int32_t* ord = I.order;
+  int32_t* cnt = I.cnt_at;
   // templates NewScheduler kept (scheduler.go:147-160)
   int alive_tmpl = 0;
   for (int n = 0; n < d.N; n++) {
@@ -281,7 +313,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       if (inversion) {
         bool stable = d.stable_order || nC <= 12;
         if (!stable && nC >= 50) {
-          DevSorter s{cnt, ord};
+          WarpSorter s{cnt, ord, lane};
           int hint;
           s.choose_pivot(0, nC, &hint);
           stable = hint == 1;  // partialInsertionSort repairs a single inversion == stable move
@@ -349,11 +381,9 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             }
           }
         } else {
-          // exact pdqsort emulation by one lane (rare: ties scrambled by Go's unstable partition)
-          if (lane == 0) {
-            DevSorter s{cnt, ord};
-            s.pdqsort(0, nC, DevSorter::bits_len((unsigned long long)nC));
-          }
+          // exact pdqsort emulation (rare: ties scrambled by Go's unstable partition), warp-cooperative
+          WarpSorter s{cnt, ord, lane};
+          s.pdqsort(0, nC, WarpSorter::bits_len((unsigned long long)nC));
           slow_sorts++;
         }
         __syncwarp();
@@ -475,6 +505,12 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         break;
       }
       if (!((px.tmpl_ok >> n) & 1ull)) continue;
+      if (I.CS && cnew >= I.CS) {  // the shared-memory copies are full: continue on the global arrays
+        migrate_small(d, I, nC, lane);
+        ord = I.order;
+        cnt = I.cnt_at;
+        RW = I.RW;
+      }
       Slot b = lane < K ? rs_slot(d, d.tmpl_rs[n], lane) : slot_absent();
       const int64_t bq = lane < R ? d.tmpl_daemon[(size_t)n * R + lane] : 0;
       Eval ev = eval_candidate(d, px, true, b, bq, tw, 0, E + cnew, scratch, lane);

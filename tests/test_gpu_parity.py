@@ -91,3 +91,42 @@ def test_c4_consolidation_uninitialized_and_price(handle):
     consol["node_it"] = node_it
     ci = _abi.ConsolInput(**consol)
     _consol_same(handle.consolidate(enc.problem, ci), oracle_lib.consolidate(enc.problem, ci), "C4 uninit ")
+
+
+def test_c4_full_size_sampled_parity(handle):
+    """BASELINE configs[3] at full size (10k nodes, all 166 750 <=3-node subsets of the 100 candidates) on the GPU;
+    the oracle re-simulates a seeded sample of 300 subsets and every one must agree bit for bit.  Size-independent
+    properties checked on all subsets: a delete decision has no new claim, a replace exactly one, and a subset whose
+    superset... (monotonicity does not hold in general, so only the per-subset invariants are asserted)."""
+    from karpenter_b200 import _abi
+    enc, consol = workloads.config_c4()
+    gpu = handle.consolidate(enc.problem, _abi.ConsolInput(**consol))
+    S = consol["n_subsets"]
+    assert S == 166750 and len(gpu["decision"]) == S
+    dec, nnew, uns = gpu["decision"], gpu["n_new_claims"], gpu["n_unscheduled"]
+    assert np.all(nnew[dec == 1] == 0) and np.all(nnew[dec == 2] == 1) and np.all(uns[dec != 0] == 0)
+    assert np.all(gpu["replacement_its"][dec != 2] == 0) and np.all(gpu["replacement_its"][dec == 2].any(axis=1))
+    rng = np.random.default_rng(7)
+    pick = np.sort(rng.choice(S, 300, replace=False))
+    off, nodes = consol["subset_off"], consol["subset_nodes"]
+    sizes = (off[1:] - off[:-1])[pick]
+    smp = dict(consol, n_subsets=len(pick), subset_off=np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32),
+               subset_nodes=np.concatenate([nodes[off[i]:off[i + 1]] for i in pick]).astype(np.int32))
+    orc = oracle_lib.consolidate(enc.problem, _abi.ConsolInput(**smp))
+    for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+        assert np.array_equal(gpu[k][pick], orc[k]), k
+
+
+def test_shared_to_global_migration(monkeypatch):
+    """Claims outgrow the shared-memory copies of the claim order / failure bitmaps (forced early with KP_CS_LIMIT):
+    the solver migrates them to HBM mid-run and the result must not change."""
+    monkeypatch.setenv("KP_CS_LIMIT", "64")
+    h = _native.Handle()
+    try:
+        for enc, what in ((workloads.config_c2(n_pods=30000, n_its=500), "C2 migrate "),
+                          (workloads.config_c3(n_apps=40, replicas=120, n_its=300), "C3 migrate ")):
+            res = h.solve(enc.problem)
+            assert res["n_claims"] > 64
+            assert_same(res, oracle_lib.solve(enc.problem), what)
+    finally:
+        h.close()
