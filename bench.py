@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 N_PODS = 100_000
 N_ITS = 500
 CPU_SAMPLE_PODS = 25_000
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_wsolve launch on this workload (ncu --set full capture,
+# profiles/r1_v5_k_metrics.csv); static: a number measured under a profiler is evidence, not a bench value
+NCU_TRAFFIC_BYTES = 1_721_344 + 3_584
 # packed row sizes of SURVEY.md section 8(d)
 B_POD, B_CLAIM, B_IT = 128, 256, 192
 
@@ -87,7 +90,12 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     oracle_lib.build()
-    enc = build_problem(0, CPU_SAMPLE_PODS, N_ITS)
+    # the reference algorithm is super-linear in the batch (every pod scans every open claim): time it on the FULL
+    # workload when the requested K + W solves fit in a few minutes (17.5 s each on this class of host), else on the
+    # largest prefix that does, and say which
+    total = args.steps + args.warmup
+    sample_pods = N_PODS if total <= 8 else (50_000 if total <= 30 else CPU_SAMPLE_PODS)
+    enc = build_problem(0, sample_pods, N_ITS)
     times = []
     res = None
     for i in range(args.warmup + args.steps):
@@ -97,7 +105,7 @@ def run_reference(args, rank, world):
         if i >= args.warmup:
             times.append(dt)
     ms = 1000 * sum(times) / len(times)
-    value = CPU_SAMPLE_PODS / (ms / 1000)
+    value = sample_pods / (ms / 1000)
     line = {
         "impl": "reference", "metric": "pods scheduled/sec", "value": value, "unit": "pods/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -105,8 +113,9 @@ def run_reference(args, rank, world):
         "config": {"workload": "C2: pods with zone/arch nodeSelector + tolerations, first 500 AWS-KWOK instance "
                                "types, 1 NodePool", "n_pods": N_PODS, "n_instance_types": N_ITS},
         "cpu_baseline": {"value": value, "unit": "pods/s", "cores": 1, "kind": "port",
-                         "sample": f"first {CPU_SAMPLE_PODS} pods of the workload (same generator, same seed), "
-                                   f"full Solve, single thread; host has {os.cpu_count()} cores"},
+                         "sample": f"first {sample_pods} of {N_PODS} pods of the workload (same generator, same seed), "
+                                   f"one full Solve per step, single thread (the reference's default "
+                                   f"parallelizeUntil width is 1); host has {os.cpu_count()} cores"},
         "e2e": {"value": value, "unit": "pods/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "unscheduled": int((res["pod_target"] == -1).sum()), "node_claims": int(res["n_claims"]),
     }
@@ -265,7 +274,7 @@ def main():
                     "host_prep_ms": st["prep_ms"]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
                          "kernel": "k_wsolve", "peak_source": "measured" if peaks else "fallback",
                          "algorithmic_bytes": int(balg),
                          "note": "k_wsolve is a latency-bound serial first-fit chain (one warp per Scheduler); see DESIGN.md"},

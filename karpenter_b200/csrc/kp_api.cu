@@ -338,6 +338,25 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
     CK(up_mut(h, &d.nactive, nact));
     CK(zeros(h, &d.nfit, (size_t)std::max(t.n_rv, 1) * std::max(d.EW, 1)));
     CK(zeros(h, &d.nstat, (size_t)std::max(d.n_nsig, 1) * std::max(d.EW, 1)));
+    {
+      std::vector<ClsLane> rows((size_t)std::max(t.X, 1) * 32);
+      memset(rows.data(), 0, rows.size() * sizeof(ClsLane));
+      for (int x = 0; x < t.X; x++)
+        for (int l = 0; l < 32; l++) {
+          ClsLane& c = rows[(size_t)x * 32 + l];
+          if (l < t.K) {
+            c.pod_m = pm[(size_t)x * t.K + l];
+            c.strict_m = sm[(size_t)x * t.K + l];
+            c.pod_f = pf[(size_t)x * t.K + l];
+            c.strict_f = sf[(size_t)x * t.K + l];
+          }
+          if (l < t.R) c.req = t.cls_req[(size_t)x * t.R + l];
+          if (l < KP_HDR) c.hdr = hdr[(size_t)x * KP_HDR + l];
+          if (l == KP_HDR + 2) c.hdr = (int32_t)(tok[x] & 0xffffffffull);
+          if (l == KP_HDR + 3) c.hdr = (int32_t)(tok[x] >> 32);
+        }
+      CK(up(h, &d.cls_lane, rows));
+    }
     CK(up(h, &d.cr_hdr, hdr));
     CK(up(h, &d.cr_tmplok, tok));
     CK(up(h, &d.cp_f, pf));
@@ -379,8 +398,8 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(zeros(h, &d.c_j, C * t.R));
   CK(zeros(h, &d.order, C));
   CK(zeros(h, &d.cnt_at, C));
-  CK(zeros(h, &d.rdead, (size_t)t.n_rv * ((C + 31) / 32)));
-  CK(zeros(h, &d.fail, (size_t)std::max(d.n_fsig, 1) * ((C + 31) / 32)));
+  CK(zeros(h, &d.cmask, C));
+  d.tmpl_all = t.N >= 64 ? ~0ull : ((1ull << t.N) - 1);
   d.H = t.E + d.Cmax;
   CK(zeros(h, &d.host_cnt, (size_t)std::max(t.GH, 1) * d.H));
   for (int g = 0; g < t.GH; g++)
@@ -415,8 +434,7 @@ static int reset_dynamic(kp_handle* h) {
   CK(cudaMemsetAsync(d.node_npods, 0, (size_t)std::max(t.E, 1) * 4, h->stream));
   size_t C = (size_t)d.Cmax;
   CK(cudaMemsetAsync(d.c_npods, 0, C * 4, h->stream));
-  CK(cudaMemsetAsync(d.rdead, 0, (size_t)t.n_rv * ((C + 31) / 32) * 4, h->stream));
-  CK(cudaMemsetAsync(d.fail, 0, (size_t)std::max(d.n_fsig, 1) * ((C + 31) / 32) * 4, h->stream));
+  CK(cudaMemsetAsync(d.cmask, 0, C * sizeof(ulonglong2), h->stream));
   CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)std::max(t.GH, 1) * d.H * 4, h->stream));
   for (int g = 0; g < t.GH; g++)
     if (t.E)
@@ -571,8 +589,18 @@ static int run_solve(kp_handle* h) {
   const size_t budget = 224 * 1024;
   const size_t fixed = KP_ALIGN16(sizeof(WSolveShared));
   size_t tb = plan_tables(h, fixed, budget);
-  const size_t rows = (size_t)d.n_rv + (size_t)std::max(d.n_fsig, 1);
-  auto small_bytes = [&](int cs) { return (size_t)cs * 12 + rows * (((size_t)cs + 31) / 32) * 4; };
+  // rows of the first CR claims (requirement slots, requests, threshold rows, instance-type words) ...
+  auto row_bytes = [&](int cr) {
+    return KP_ALIGN16((size_t)cr * d.K * 8) + KP_ALIGN16((size_t)cr * d.R * 8) + KP_ALIGN16((size_t)cr * d.ITW * 8) +
+           KP_ALIGN16((size_t)cr * d.R * 4) + KP_ALIGN16((size_t)cr * d.K);
+  };
+  int CR = std::min(d.Cmax, 512);
+  while (CR > 0 && fixed + tb + row_bytes(CR) > budget / 2) CR -= 32;
+  CR = std::max(CR, 0);
+  if (getenv("KP_CS_LIMIT")) CR = std::min(CR, 32);
+  tb += CR ? row_bytes(CR) : 0;  // from here on `tb` is everything in front of the small arrays
+  // ... and claim order / failure masks of the first CS claims
+  auto small_bytes = [&](int cs) { return (size_t)cs * 28; };  // cmask 16 B + order, count, template id
   int CS = 0;
   if (fixed + tb + small_bytes(64) + 64 <= budget) {  // the largest multiple of 32 that fits, capped at Cmax
     int lo = 64, hi = ((d.Cmax + 31) / 32) * 32;
@@ -589,7 +617,7 @@ static int run_solve(kp_handle* h) {
   if (const char* lim = getenv("KP_CS_LIMIT")) CS = std::min(CS, std::max(0, atoi(lim)) / 32 * 32);  // test knob
   size_t smem = fixed + tb + (CS ? small_bytes(CS) : 0) + 64;
   CK(cudaFuncSetAttribute(k_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_wsolve<<<1, 32, smem, h->stream>>>(d, CS);
+  k_wsolve<<<1, 32, smem, h->stream>>>(d, CS, CR);
   h->stats.kernel_launches++;
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -894,7 +922,7 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
   per_sm = std::max(per_sm, 1);
   int grid = std::min(n_sm * per_sm, std::max(1, (S + CONSOL_WARPS - 1) / CONSOL_WARPS));
-  const size_t slots = (size_t)grid * CONSOL_WARPS, cq = (size_t)capq, RWc = (cq + 31) / 32;
+  const size_t slots = (size_t)grid * CONSOL_WARPS, cq = (size_t)capq;
   CK(zeros(h, &q.queue, slots * (cq + 1)));
   CK(zeros(h, &q.qcls, slots * (cq + 1)));
   CK(zeros(h, &q.last_len, slots * cq));
@@ -909,8 +937,7 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   CK(zeros(h, &q.c_smask, slots * cq * K));
   CK(zeros(h, &q.c_its, slots * cq * ITW));
   CK(zeros(h, &q.c_j, slots * cq * R));
-  CK(zeros(h, &q.rdead, slots * (size_t)std::max(t.n_rv, 1) * RWc));
-  CK(zeros(h, &q.fail, slots * (size_t)std::max(d.n_fsig, 1) * RWc));
+  CK(zeros(h, &q.cmask, slots * cq));
   CK(zeros(h, &q.tmpl_remaining, slots * (size_t)std::max(N, 1) * R));
   CK(zeros(h, &q.ov_node, slots * cq));
   CK(zeros(h, &q.ov_rem, slots * cq * R));

@@ -124,7 +124,7 @@ struct WSolveShared {
   Slot scratch[KP_MAXK];
 };
 
-__global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS) {
+__global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS, int CR) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WSolveShared& sh = *reinterpret_cast<WSolveShared*>(smem_raw);
   const int lane = threadIdx.x;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev 
   stage_tables(d_in, &sh.ds, tab);
   const KpDev& d = sh.ds;
   WInst& I = sh.inst;
-  const int Cmax = d.Cmax, RW = (Cmax + 31) >> 5;
+  const int Cmax = d.Cmax;
   if (lane == 0) {
     I.P = (int)d.P;
     I.queue = d.queue;
@@ -152,9 +152,7 @@ __global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev 
     I.c_j = d.c_j;
     I.order = d.order;
     I.cnt_at = d.cnt_at;
-    I.rdead = d.rdead;
-    I.fail = d.fail;
-    I.RW = RW;
+    I.cmask = d.cmask;
     I.tmpl_remaining = d.tmpl_remaining;
     I.node_rem = d.node_rem;
     I.node_rem_present = d.node_rem_present;
@@ -174,33 +172,37 @@ __global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev 
     I.g_order = d.order;
     I.g_cnt_at = d.cnt_at;
     I.g_c_tmpl = d.c_tmpl;
-    I.g_rdead = d.rdead;
-    I.g_fail = d.fail;
-    I.g_RW = RW;
-    if (CS > 0) {  // claim order, template ids and the failure bitmaps of the first CS claims live in shared memory
-      const int RWs = (CS + 31) >> 5;
-      unsigned char* p = tab + d_in.tab_bytes;
+    I.g_cmask = d.cmask;
+    I.CR = 0;
+    unsigned char* p = tab + d_in.tab_bytes;
+    if (CR > 0) {  // rows of the first CR claims
+      I.s_smask = reinterpret_cast<uint64_t*>(p);
+      p += KP_ALIGN16((size_t)CR * d.K * 8);
+      I.s_req = reinterpret_cast<int64_t*>(p);
+      p += KP_ALIGN16((size_t)CR * d.R * 8);
+      I.s_its = reinterpret_cast<uint64_t*>(p);
+      p += KP_ALIGN16((size_t)CR * d.ITW * 8);
+      I.s_j = reinterpret_cast<int32_t*>(p);
+      p += KP_ALIGN16((size_t)CR * d.R * 4);
+      I.s_sflags = reinterpret_cast<uint8_t*>(p);
+      p += KP_ALIGN16((size_t)CR * d.K);
+      I.CR = CR;
+    }
+    if (CS > 0) {  // claim order, template ids and the failure masks of the first CS claims live in shared memory
+      I.cmask = reinterpret_cast<ulonglong2*>(p);
+      p += (size_t)CS * 16;
       I.order = reinterpret_cast<int32_t*>(p);
       p += (size_t)CS * 4;
       I.cnt_at = reinterpret_cast<int32_t*>(p);
       p += (size_t)CS * 4;
       I.c_tmpl = reinterpret_cast<int32_t*>(p);
-      p += (size_t)CS * 4;
-      I.rdead = reinterpret_cast<uint32_t*>(p);
-      p += (size_t)d.n_rv * RWs * 4;
-      I.fail = reinterpret_cast<uint32_t*>(p);
-      I.RW = RWs;
       I.CS = CS;
     }
   }
   __syncwarp();
-  if (CS > 0) {
-    for (int i = lane; i < d.n_rv * I.RW; i += 32) I.rdead[i] = 0;
-    for (int i = lane; i < d.n_fsig * I.RW; i += 32) I.fail[i] = 0;
-    __syncwarp();
-  }
   wsolve_run<false>(d, I, sh.ctx, sh.scratch, lane);
   const int nC = I.n_claims;
+  claim_rows_flush(d, I, nC, lane);
   if (I.CS > 0) {  // the host reads the final order (claim_rank) and template ids from global memory
     for (int i = lane; i < nC; i += 32) {
       d_in.order[i] = I.order[i];
@@ -251,7 +253,7 @@ struct KpConsol {
   int64_t *c_sgte, *c_slte;
   uint64_t* c_its;
   int32_t* c_j;
-  uint32_t *rdead, *fail;
+  ulonglong2* cmask;
   int64_t* tmpl_remaining;
   int32_t* ov_node;
   int64_t* ov_rem;
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
   WInst& I = W.inst;
   const int K = d.K, R = d.R, ITW = d.ITW, N = d.N;
   const size_t slot = (size_t)blockIdx.x * CONSOL_WARPS + warp;
-  const int capq = q.capq, RW = (capq + 31) >> 5;
+  const int capq = q.capq;
   if (lane == 0) {
     I.queue = q.queue + slot * (capq + 1);
     I.qcls = q.qcls + slot * (capq + 1);
@@ -309,9 +311,7 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
     I.c_j = q.c_j + slot * capq * R;
     I.order = q.order + slot * capq;
     I.cnt_at = q.cnt_at + slot * capq;
-    I.rdead = q.rdead + slot * (size_t)d.n_rv * RW;
-    I.fail = q.fail + slot * (size_t)(d.n_fsig > 0 ? d.n_fsig : 1) * RW;
-    I.RW = RW;
+    I.cmask = q.cmask + slot * capq;
     I.tmpl_remaining = q.tmpl_remaining + slot * (size_t)(N > 0 ? N : 1) * R;
     I.node_rem = d.node_rem;  // shared base, read-only here
     I.node_rem_present = d.node_rem_present;
@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
     I.nstat = d.nstat;
     I.nactive = d.nactive;
     I.CS = 0;
+    I.CR = 0;
     I.ov_cap = capq;
     I.ov_node = q.ov_node + slot * capq;
     I.ov_rem = q.ov_rem + slot * capq * R;

@@ -42,22 +42,32 @@ __device__ __forceinline__ Slot rs_slot(const KpDev& d, int rs, int k) {
 //
 // fits_word: resources.Fits(total, allocatable) via ">= threshold" bitmaps: lane r ranks q[r] in the sorted distinct
 // allocatable values of resource r, the answer is the AND of the R selected rows.
-// `j_lane` (lane r): in/out threshold row of resource r.  Requests of a candidate only grow, so the row found for the
-// previous total is a valid starting point and the search usually advances by zero or one step.
-__device__ __forceinline__ uint64_t fits_word(const KpDev& d, int64_t q_lane, int lane, int* j_lane) {
+// `j_lane` (lane r): in/out threshold row of resource r (-1: none yet).  Requests of a candidate only grow, so the row
+// found for the previous total is a valid starting point and the search usually advances by zero or one step; and
+// because `its` already passed the rows of the previous total, only rows that ADVANCED can remove instance types.
+// Returns its & Fits.
+__device__ __forceinline__ uint64_t fits_word(const KpDev& d, int64_t q_lane, int lane, int* j_lane, uint64_t its) {
   const int R = d.R, ITW = d.ITW;
   int j = 0;
+  bool adv = false, fresh = false;
   if (lane < R) {
     const int end = d.ge_off[lane + 1];
     int lo = *j_lane;
-    if (lo < d.ge_off[lane]) lo = d.ge_off[lane];
+    fresh = lo < d.ge_off[lane];
+    if (fresh) lo = d.ge_off[lane];
+    const int start = lo;
     while (lo < end && d.ge_vals[lo] < q_lane) lo++;
+    adv = fresh || lo != start;
     j = lo == end ? -1 : lo;  // -1: the request exceeds every instance type
     *j_lane = lo;
   }
-  uint64_t fw = (lane < ITW) ? d.it_valid[lane] : 0ull;
-  for (int r = 0; r < R; r++) {
-    int jr = __shfl_sync(FULL, j, r);
+  unsigned advm = __ballot_sync(FULL, adv);
+  uint64_t fw = its;
+  if (__any_sync(FULL, fresh)) fw &= (lane < ITW) ? d.it_valid[lane] : 0ull;
+  while (advm) {
+    const int r = __ffs(advm) - 1;
+    advm &= advm - 1;
+    const int jr = __shfl_sync(FULL, j, r);
     if (lane < ITW) fw &= jr >= 0 ? d.ge_bits[(size_t)jr * ITW + lane] : 0ull;
   }
   return fw;
@@ -112,8 +122,8 @@ __device__ __forceinline__ uint64_t compat_off_word(const KpDev& d, const Slot* 
 // word w of compat & fits & hasOffering (nodeclaim.go:434-445); *fits_out = the resource-only word
 __device__ __forceinline__ uint64_t filter_its_word(const KpDev& d, const Slot* S, int64_t q_lane, int lane,
                                                     uint64_t* fits_out) {
-  int j0 = 0;
-  uint64_t fw = fits_word(d, q_lane, lane, &j0);
+  int j0 = -1;
+  uint64_t fw = fits_word(d, q_lane, lane, &j0, ~0ull);
   *fits_out = fw;
   return compat_off_word(d, S, lane) & fw;
 }
@@ -200,10 +210,10 @@ struct PodCtx {
   union {
     struct {
       int tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend, cls, pod;
+      unsigned long long tmpl_ok;  // bit n: template n's taints are tolerated (taints.go:49-66)
     };
-    int hdr[KP_HDR + 2];  // same order as a cr_hdr row, then class id and pod id
+    int hdr[KP_HDR + 4];  // a cr_hdr row, then class id, pod id, tmpl_ok (lo, hi)
   };
-  unsigned long long tmpl_ok;  // bit n: template n's taints are tolerated (taints.go:49-66)
   int64_t req[KP_MAXR];
   Slot pod_slot[KP_MAXK];
   Slot strict_slot[KP_MAXK];
@@ -229,12 +239,13 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   KeyInfo ki = lane < K ? key_info(d, lane) : KeyInfo{d.val_int, 0ull, 0ull};
   Slot pod = lane < K ? px.pod_slot[lane] : slot_absent();
   // requirements.Compatible(pod requirements) then Add
-  bool bad = lane < K && !slot_compatible(ki, base, pod, wk, allow_undef);
+  const bool nb = !d.has_bounds;
+  bool bad = lane < K && !(nb ? slot_compatible_nb(base, pod, wk, allow_undef) : slot_compatible(ki, base, pod, wk, allow_undef));
   if (__any_sync(FULL, bad)) {
     ev.compat_fail = true;
     return ev;
   }
-  Slot M = lane < K ? slot_add(ki, base, pod) : slot_absent();
+  Slot M = lane < K ? (nb ? slot_add_nb(base, pod) : slot_add(ki, base, pod)) : slot_absent();
   // Topology.AddRequirements (topology.go:226-248)
   const int moff = px.moff, mend = px.mend;
   if (mend > moff) {
@@ -285,7 +296,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   ev.changed = changed;
   int64_t q = base_q + (lane < d.R ? px.req[lane] : 0);
   ev.j = base_j;
-  uint64_t fw = fits_word(d, q, lane, &ev.j) & base_its;
+  uint64_t fw = fits_word(d, q, lane, &ev.j, base_its);
   uint64_t w = fw;
   if (changed) {
     if (lane < K) scratch[lane] = M;
@@ -303,29 +314,32 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
 // A class row in flight between global memory and the shared PodCtx (one warp; lane k: key k, lane r: resource r,
 // lane i < KP_HDR: header word i).
 struct ClassRegs {
-  int hdr;                // lanes 0..KP_HDR+1: tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend, class, pod
-  unsigned long long tmpl_ok;
+  int hdr;                // lanes 0..KP_HDR+3: header row, class, pod, tmpl_ok lo / hi
   int64_t req;
   Slot pod, strict;
 };
 __device__ __forceinline__ ClassRegs load_class_regs(const KpDev& d, int X, int pod, int lane) {
   ClassRegs c;
-  c.hdr = lane < KP_HDR ? d.cr_hdr[(size_t)X * KP_HDR + lane] : (lane == KP_HDR ? X : pod);
-  c.tmpl_ok = lane == 0 ? d.cr_tmplok[X] : 0ull;
-  c.req = lane < d.R ? d.cls_req[(size_t)X * d.R + lane] : 0;
-  if (lane < d.K) {
-    size_t i = (size_t)X * d.K + lane;
-    c.pod = load_slot(d.cp_f, d.cp_m, d.cp_g, d.cp_l, i, d.has_bounds);
-    c.strict = load_slot(d.cs_f, d.cs_m, d.cs_g, d.cs_l, i, d.has_bounds);
-  } else {
-    c.pod = slot_absent();
-    c.strict = slot_absent();
+  const uint4* p = reinterpret_cast<const uint4*>(d.cls_lane + ((size_t)X * 32 + lane));
+  const uint4 a = p[0], b = p[1];
+  c.pod.m = (uint64_t)a.x | ((uint64_t)a.y << 32);
+  c.strict.m = (uint64_t)a.z | ((uint64_t)a.w << 32);
+  c.req = (int64_t)((uint64_t)b.x | ((uint64_t)b.y << 32));
+  c.hdr = lane == KP_HDR ? X : (lane == KP_HDR + 1 ? pod : (int)b.z);
+  c.pod.f = b.w & 0xffu;
+  c.strict.f = (b.w >> 8) & 0xffu;
+  c.pod.gte = c.pod.lte = c.strict.gte = c.strict.lte = 0;
+  if (d.has_bounds && lane < d.K) {
+    const size_t i = (size_t)X * d.K + lane;
+    c.pod.gte = d.cp_g[i];
+    c.pod.lte = d.cp_l[i];
+    c.strict.gte = d.cs_g[i];
+    c.strict.lte = d.cs_l[i];
   }
   return c;
 }
 __device__ __forceinline__ void store_class_regs(const KpDev& d, PodCtx& px, const ClassRegs& c, int lane) {
-  if (lane < KP_HDR + 2) px.hdr[lane] = c.hdr;
-  if (lane == 0) px.tmpl_ok = c.tmpl_ok;
+  if (lane < KP_HDR + 4) px.hdr[lane] = c.hdr;
   if (lane < d.R) px.req[lane] = c.req;
   if (lane < d.K) {
     px.pod_slot[lane] = c.pod;

@@ -168,3 +168,40 @@ KP_HD bool slot_intersects(const KeyInfo& ki, const Slot& existing, const Slot& 
   if (slot_has_intersection(ki, existing, incoming)) return true;
   return op_is_negative(slot_op(incoming)) && op_is_negative(slot_op(existing));
 }
+
+
+// ---- the same algebra when no requirement in the problem carries Gt / Lt bounds (has_bounds == 0): flags + mask only
+KP_HD bool slot_neg_nb(const Slot& s) { return ((s.f & SF_COMPLEMENT) != 0) == (s.m != 0); }  // NotIn or DoesNotExist
+KP_HD bool slot_compatible_nb(const Slot& existing, const Slot& incoming, bool well_known, bool allow_undefined) {
+  if (!(incoming.f & SF_PRESENT)) return true;
+  if (!(existing.f & SF_PRESENT)) return (allow_undefined && well_known) || slot_neg_nb(incoming);
+  const bool ac = existing.f & SF_COMPLEMENT, bc = incoming.f & SF_COMPLEMENT;
+  bool inter;
+  if (ac && bc)
+    inter = true;
+  else if (ac)
+    inter = (incoming.m & ~existing.m) != 0;
+  else if (bc)
+    inter = (existing.m & ~incoming.m) != 0;
+  else
+    inter = (existing.m & incoming.m) != 0;
+  return inter || (slot_neg_nb(incoming) && slot_neg_nb(existing));
+}
+KP_HD Slot slot_add_nb(const Slot& existing, const Slot& incoming) {
+  if (!(incoming.f & SF_PRESENT)) return existing;
+  if (!(existing.f & SF_PRESENT)) return incoming;
+  const bool ac = incoming.f & SF_COMPLEMENT, bc = existing.f & SF_COMPLEMENT;
+  Slot o;
+  o.gte = 0;
+  o.lte = 0;
+  o.f = SF_PRESENT | ((ac && bc) ? SF_COMPLEMENT : 0u);
+  if (ac && bc)
+    o.m = incoming.m | existing.m;
+  else if (ac)
+    o.m = existing.m & ~incoming.m;
+  else if (bc)
+    o.m = incoming.m & ~existing.m;
+  else
+    o.m = incoming.m & existing.m;
+  return o;
+}

@@ -9,6 +9,7 @@
 #include <cstdint>
 #ifndef __CUDACC__
 struct int4 { int x, y, z, w; };
+struct ulonglong2 { unsigned long long x, y; };
 #endif
 
 #define KP_MAXK 32          // label keys (one warp lane per key)
@@ -35,6 +36,17 @@ struct Slot {
   uint64_t m;   // values
   int64_t gte, lte;
 };
+
+// One lane's share of a class row: lane k carries the class's requirement slots on key k, lane r its request for
+// resource r, lane i < KP_HDR header word i (lanes KP_HDR+2, +3: the tolerated-template mask).  32 bytes, so staging a
+// pod is two 16-byte loads per lane.
+struct ClsLane {
+  uint64_t pod_m, strict_m;
+  int64_t req;
+  int32_t hdr;
+  uint8_t pod_f, strict_f, pad[2];
+};
+static_assert(sizeof(ClsLane) == 32, "ClsLane is loaded as two 16-byte vectors");
 
 struct KpGroup {
   int32_t key;          // label key, or -1 for the hostname key
@@ -105,6 +117,7 @@ struct KpDev {
   const int32_t* cls_rec_off;     // [X+1] groups that may count the class on Record (select it / inverse owned)
   const int32_t* cls_rec;
   // class rows, one level of indirection for the per-pod staging (header: tolset, rv, match/record list ranges)
+  const ClsLane* cls_lane;        // [X*32] class rows, lane-major (see ClsLane)
   const int32_t* cr_hdr;          // [X*KP_HDR] tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend
   const int4* cls_hchk;           // hostname-group checks of a class {host_row, type | self << 8, max_skew, group}
   const uint64_t* cr_tmplok;      // [X] bit n: template n tolerated
@@ -150,11 +163,12 @@ struct KpDev {
   int32_t* c_j;                   // [Cmax*R] threshold rows of the claim's requests (fits_word)
   int32_t* order;                 // [Cmax] s.newNodeClaims as claim ids
   int32_t* cnt_at;                // [Cmax] len(Pods) by position
-  uint32_t* rdead;                // [n_rv * ceil(Cmax/32)] claim can never again fit this request vector
   // monotone failure cache: for a topology-free class whose keys can never be "undefined" on a NodeClaim, CanAdd only
   // ever flips from true to false (requirements tighten, requests grow, instance types shrink: nodeclaim.go:207-219)
   int n_fsig;                     // distinct requirement sets of such classes
-  uint32_t* fail;                 // [n_fsig * ceil(Cmax/32)] claim rejected this signature once
+  ulonglong2* cmask;              // [Cmax] per claim: x = rejected requirement signatures, y = request vectors that can
+                                  // never fit again (bit index = signature / vector id, ids >= 64 are not cached)
+  unsigned long long tmpl_all;    // bit n: template n survived the NewScheduler prefilter input (n < N)
   // existing-node candidate bitmaps (supersets; the exact CanAdd runs on every candidate)
   int n_nsig, EW;                 // distinct (requirements, tolerations) signatures; words per row = ceil(E/32)
   uint32_t* nfit;                 // [n_rv * EW] resources.Fits(request vector, remaining) held when last checked

@@ -37,15 +37,23 @@ struct WInst {
   int64_t *c_sgte, *c_slte;
   uint64_t* c_its;
   int32_t* c_j;             // [Cmax*R] threshold row of the claim's requests per resource (fits_word)
+  // rows of the first CR claims are kept in shared memory (0 = none); copied out when the solve ends
+  int CR;
+  uint8_t* s_sflags;
+  uint64_t* s_smask;
+  int64_t* s_req;
+  int32_t* s_j;
+  uint64_t* s_its;
   int32_t *order, *cnt_at;  // s.newNodeClaims: claim id / len(Pods) by position
-  uint32_t *rdead, *fail;
-  int RW;                   // words per rdead / fail row
-  // While the claim order, template ids and failure bitmaps fit, they live in shared memory (CS = claims the shared
+  // monotone failure cache, one 16-byte entry per claim: x = bit f set when requirement signature f was rejected by
+  // Requirements.Compatible, y = bit rv set when no remaining instance type can hold the claim's requests plus request
+  // vector rv.  Signatures / vectors with an index >= 64 are simply not cached (exact either way).
+  ulonglong2* cmask;
+  // While the claim order, template ids and failure masks fit, they live in shared memory (CS = claims the shared
   // copies can hold, 0 = not in use); the moment a claim id reaches CS everything migrates to the global arrays below.
   int CS;
   int32_t *g_order, *g_cnt_at, *g_c_tmpl;
-  uint32_t *g_rdead, *g_fail;
-  int g_RW;
+  ulonglong2* g_cmask;
   int64_t* tmpl_remaining;  // [N*R]
   // existing nodes
   int64_t* node_rem;
@@ -81,26 +89,97 @@ __device__ __forceinline__ int ov_find(const WInst& I, int node, int lane) {
   return -1;
 }
 
+// a NodeClaim's row: requirement slot of key `lane`, requests / threshold row of resource `lane`, instance-type word `lane`
+__device__ __forceinline__ void claim_load(const KpDev& d, const WInst& I, int c, int lane, Slot* b, int64_t* q,
+                                           uint64_t* its, int* j) {
+  const int K = d.K, R = d.R, ITW = d.ITW;
+  *b = slot_absent();
+  *q = 0;
+  *its = 0;
+  *j = 0;
+  if (c < I.CR) {
+    if (lane < K) {
+      b->f = I.s_sflags[c * K + lane];
+      b->m = I.s_smask[c * K + lane];
+    }
+    if (lane < R) {
+      *q = I.s_req[c * R + lane];
+      *j = I.s_j[c * R + lane];
+    }
+    if (lane < ITW) *its = I.s_its[c * ITW + lane];
+  } else {
+    if (lane < K) {
+      b->f = I.c_sflags[(size_t)c * K + lane];
+      b->m = I.c_smask[(size_t)c * K + lane];
+    }
+    if (lane < R) {
+      *q = I.c_req[(size_t)c * R + lane];
+      *j = I.c_j[(size_t)c * R + lane];
+    }
+    if (lane < ITW) *its = I.c_its[(size_t)c * ITW + lane];
+  }
+  if (d.has_bounds && lane < K) {
+    b->gte = I.c_sgte[(size_t)c * K + lane];
+    b->lte = I.c_slte[(size_t)c * K + lane];
+  }
+}
+__device__ __forceinline__ void claim_store(const KpDev& d, WInst& I, int c, int lane, const Eval& ev, bool slots) {
+  const int K = d.K, R = d.R, ITW = d.ITW;
+  if (c < I.CR) {
+    if (slots && lane < K) {
+      I.s_sflags[c * K + lane] = (uint8_t)ev.F.f;
+      I.s_smask[c * K + lane] = ev.F.m;
+    }
+    if (lane < R) {
+      I.s_req[c * R + lane] = ev.q;
+      I.s_j[c * R + lane] = ev.j;
+    }
+    if (lane < ITW) I.s_its[c * ITW + lane] = ev.its;
+  } else {
+    if (slots && lane < K) {
+      I.c_sflags[(size_t)c * K + lane] = (uint8_t)ev.F.f;
+      I.c_smask[(size_t)c * K + lane] = ev.F.m;
+    }
+    if (lane < R) {
+      I.c_req[(size_t)c * R + lane] = ev.q;
+      I.c_j[(size_t)c * R + lane] = ev.j;
+    }
+    if (lane < ITW) I.c_its[(size_t)c * ITW + lane] = ev.its;
+  }
+  if (slots && d.has_bounds && lane < K) {
+    I.c_sgte[(size_t)c * K + lane] = ev.F.gte;
+    I.c_slte[(size_t)c * K + lane] = ev.F.lte;
+  }
+}
+// copy the shared-memory claim rows to their global arrays (end of the solve)
+__device__ __forceinline__ void claim_rows_flush(const KpDev& d, WInst& I, int nC, int lane) {
+  const int n = nC < I.CR ? nC : I.CR;
+  for (int i = lane; i < n * d.K; i += 32) {
+    I.c_sflags[i] = I.s_sflags[i];
+    I.c_smask[i] = I.s_smask[i];
+  }
+  for (int i = lane; i < n * d.R; i += 32) {
+    I.c_req[i] = I.s_req[i];
+    I.c_j[i] = I.s_j[i];
+  }
+  for (int i = lane; i < n * d.ITW; i += 32) I.c_its[i] = I.s_its[i];
+  __syncwarp();
+}
+
 // shared -> global migration of the small per-claim arrays (see WInst::CS); executed once, by the whole warp
 __device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, int lane) {
   for (int i = lane; i < nC; i += 32) {
     I.g_order[i] = I.order[i];
     I.g_cnt_at[i] = I.cnt_at[i];
     I.g_c_tmpl[i] = I.c_tmpl[i];
+    I.g_cmask[i] = I.cmask[i];
   }
-  const int RWs = I.RW, RWg = I.g_RW;
-  for (int r = 0; r < d.n_rv; r++)
-    for (int w = lane; w < RWg; w += 32) I.g_rdead[(size_t)r * RWg + w] = w < RWs ? I.rdead[(size_t)r * RWs + w] : 0u;
-  for (int r = 0; r < d.n_fsig; r++)
-    for (int w = lane; w < RWg; w += 32) I.g_fail[(size_t)r * RWg + w] = w < RWs ? I.fail[(size_t)r * RWs + w] : 0u;
   __syncwarp();
   if (lane == 0) {
     I.order = I.g_order;
     I.cnt_at = I.g_cnt_at;
     I.c_tmpl = I.g_c_tmpl;
-    I.rdead = I.g_rdead;
-    I.fail = I.g_fail;
-    I.RW = I.g_RW;
+    I.cmask = I.g_cmask;
     I.CS = 0;
   }
   __syncwarp();
@@ -110,7 +189,6 @@ __device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, 
 template <bool OVERLAY>
 __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch, const int lane) {
   const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, EW = d.EW;
-  int RW = I.RW;
   int head = 0, tail = I.P;
   const int cap = I.P + 1;
   int nC = 0;
@@ -135,7 +213,6 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
   ClassRegs pf;
   int pf_idx = -1, ids_idx = -1, ids_cls = 0, ids_pod = 0;
   pf.hdr = 0;
-  pf.tmpl_ok = 0;
   pf.req = 0;
   pf.pod = slot_absent();
   pf.strict = slot_absent();
@@ -393,18 +470,25 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
 
     // ================= addToInflightNode (scheduler.go:557-589) =================
     {
-      const uint32_t* rdrow = I.rdead + (size_t)rv * RW;
-      const uint32_t* flrow = fsig >= 0 ? I.fail + (size_t)fsig * RW : nullptr;
-      for (int base = 0; base < nC && !found; base += 32) {
+      // loop invariants of the scan, in registers: the failure bits to test, the tolerated templates, hostname checks
+      const unsigned long long fbit = (fsig >= 0 && fsig < 64) ? 1ull << fsig : 0ull;
+      const unsigned long long rbit = rv < 64 ? 1ull << rv : 0ull;
+      const unsigned long long tok = px.tmpl_ok;
+      const bool all_tmpl = (tok & d.tmpl_all) == d.tmpl_all;
+      const int hoff = px.hoff, hend = px.hend;
+      const ulonglong2* cm = I.cmask;
+      const int32_t* ctm = I.c_tmpl;
+      for (int base = 0; base < nC && !found && (tok & d.tmpl_all); base += 32) {
         const int pos = base + lane;
         bool pass = false;
         int c = -1;
         if (pos < nC) {
           c = ord[pos];
-          pass = !((rdrow[c >> 5] >> (c & 31)) & 1u) && ((px.tmpl_ok >> I.c_tmpl[c]) & 1ull);
-          if (pass && flrow) pass = !((flrow[c >> 5] >> (c & 31)) & 1u);
+          const ulonglong2 mk = cm[c];
+          pass = !(mk.x & fbit) && !(mk.y & rbit);
+          if (pass && !all_tmpl) pass = (tok >> ctm[c]) & 1ull;
           // hostname groups: a NodeClaim is exactly one hostname domain (topologygroup.go:235-247,317-333,402-408)
-          for (int i = px.hoff; pass && i < px.hend; i++) {
+          for (int i = hoff; pass && i < hend; i++) {
             const int4 hc = d.cls_hchk[i];
             const int hcnt = d.host_cnt[(size_t)hc.x * d.H + E + c];
             const int type = hc.y & 0xff, self = hc.y >> 8;
@@ -422,35 +506,24 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           m &= m - 1;
           const int cpos = base + l;
           const int cc = __shfl_sync(FULL, c, l);
-          Slot b = lane < K ? load_slot(I.c_sflags, I.c_smask, I.c_sgte, I.c_slte, (size_t)cc * K + lane, d.has_bounds)
-                            : slot_absent();
-          const int64_t bq = lane < R ? I.c_req[(size_t)cc * R + lane] : 0;
-          const uint64_t bi = lane < ITW ? I.c_its[(size_t)cc * ITW + lane] : 0ull;
-          const int bj = lane < R ? I.c_j[(size_t)cc * R + lane] : 0;
+          Slot b;
+          int64_t bq;
+          uint64_t bi;
+          int bj;
+          claim_load(d, I, cc, lane, &b, &bq, &bi, &bj);
           Eval ev = eval_candidate(d, px, true, b, bq, bi, bj, E + cc, scratch, lane);
           if (!ev.ok) {
             if (lane == 0) {
-              if (ev.res_dead) I.rdead[(size_t)rv * RW + (cc >> 5)] |= 1u << (cc & 31);
-              if (fsig >= 0 && ev.compat_fail) I.fail[(size_t)fsig * RW + (cc >> 5)] |= 1u << (cc & 31);
+              ulonglong2 mk = I.cmask[cc];
+              if (ev.res_dead) mk.y |= rbit;
+              if (ev.compat_fail) mk.x |= fbit;
+              I.cmask[cc] = mk;
             }
             __syncwarp();
             continue;
           }
           // NodeClaim.Add (nodeclaim.go:207-219)
-          if (ev.changed && lane < K) {
-            const size_t i = (size_t)cc * K + lane;
-            I.c_sflags[i] = (uint8_t)ev.F.f;
-            I.c_smask[i] = ev.F.m;
-            if (d.has_bounds) {
-              I.c_sgte[i] = ev.F.gte;
-              I.c_slte[i] = ev.F.lte;
-            }
-          }
-          if (lane < R) {
-            I.c_req[(size_t)cc * R + lane] = ev.q;
-            I.c_j[(size_t)cc * R + lane] = ev.j;
-          }
-          if (lane < ITW) I.c_its[(size_t)cc * ITW + lane] = ev.its;
+          claim_store(d, I, cc, lane, ev, ev.changed);
           if (lane == 0) {
             I.c_npods[cc]++;
             cnt[cpos]++;
@@ -509,27 +582,13 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         migrate_small(d, I, nC, lane);
         ord = I.order;
         cnt = I.cnt_at;
-        RW = I.RW;
       }
       Slot b = lane < K ? rs_slot(d, d.tmpl_rs[n], lane) : slot_absent();
       const int64_t bq = lane < R ? d.tmpl_daemon[(size_t)n * R + lane] : 0;
-      Eval ev = eval_candidate(d, px, true, b, bq, tw, 0, E + cnew, scratch, lane);
+      Eval ev = eval_candidate(d, px, true, b, bq, tw, -1, E + cnew, scratch, lane);
       if (!ev.ok) continue;
       // NewNodeClaim + Add
-      if (lane < K) {
-        const size_t i = (size_t)cnew * K + lane;
-        I.c_sflags[i] = (uint8_t)ev.F.f;
-        I.c_smask[i] = ev.F.m;
-        if (d.has_bounds) {
-          I.c_sgte[i] = ev.F.gte;
-          I.c_slte[i] = ev.F.lte;
-        }
-      }
-      if (lane < R) {
-        I.c_req[(size_t)cnew * R + lane] = ev.q;
-        I.c_j[(size_t)cnew * R + lane] = ev.j;
-      }
-      if (lane < ITW) I.c_its[(size_t)cnew * ITW + lane] = ev.its;
+      claim_store(d, I, cnew, lane, ev, true);
       if (lane == 0) {
         I.c_tmpl[cnew] = n;
         I.c_npods[cnew] = 1;
@@ -541,8 +600,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         }
       }
       // a recycled instance must not inherit failure bits of an earlier claim with this id
-      for (int s = lane; s < d.n_rv; s += 32) I.rdead[(size_t)s * RW + (cnew >> 5)] &= ~(1u << (cnew & 31));
-      for (int s = lane; s < d.n_fsig; s += 32) I.fail[(size_t)s * RW + (cnew >> 5)] &= ~(1u << (cnew & 31));
+      if (lane == 0) I.cmask[cnew] = make_ulonglong2(0ull, 0ull);
       // subtractMax (scheduler.go:840-857): remaining -= max capacity over the claim's instance types
       if (lp) {
         for (int r = 0; r < R; r++) {
