@@ -271,7 +271,8 @@ def main():
                        "timing": "CUDA events on the library stream around sort+solve kernels, max over ranks"},
             "e2e": {"value": total_pods / (e2e_ms / 1000), "unit": "pods/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(st["bytes_h2d"]), "d2h_bytes_per_step": int(st["bytes_d2h"]),
-                    "host_prep_ms": st["prep_ms"]},
+                    "host_prep_ms": st["prep_ms"], "upload_ms": st["upload_ms"], "kernels_ms": st["solve_ms"],
+                    "download_ms": st["download_ms"]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,

@@ -25,23 +25,45 @@
     }                                                                                                \
   } while (0)
 
-struct Arena {  // every device allocation of one upload; freed together
-  std::vector<void*> ptrs;
-  size_t bytes = 0;
+struct Arena {  // device allocations of one upload, bump-allocated from chunks that survive across uploads
+  struct Chunk {
+    char* base;
+    size_t cap, used;
+  };
+  std::vector<Chunk> chunks;
+  size_t bytes = 0;  // requested by the current upload
   template <class T>
   cudaError_t alloc(T** out, size_t n) {
+    size_t need = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
+    bytes += need;
+    for (auto& c : chunks)
+      if (c.cap - c.used >= need) {
+        *out = (T*)(c.base + c.used);
+        c.used += need;
+        return cudaSuccess;
+      }
+    size_t cap = std::max<size_t>(need, (size_t)32 << 20);
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    cudaError_t e = cudaMalloc(&p, cap);
     if (e != cudaSuccess) return e;
-    ptrs.push_back(p);
-    bytes += n * sizeof(T);
+    chunks.push_back(Chunk{(char*)p, cap, need});
     *out = (T*)p;
     return cudaSuccess;
   }
-  void release() {
-    for (void* p : ptrs) cudaFree(p);
-    ptrs.clear();
+  // start a new upload: keep the memory; if the last upload needed several chunks, replace them by one that fits
+  void reset() {
+    if (chunks.size() > 1) {
+      size_t total = bytes + bytes / 4;
+      destroy();
+      void* p = nullptr;
+      if (cudaMalloc(&p, total) == cudaSuccess) chunks.push_back(Chunk{(char*)p, total, 0});
+    }
+    for (auto& c : chunks) c.used = 0;
     bytes = 0;
+  }
+  void destroy() {
+    for (auto& c : chunks) cudaFree(c.base);
+    chunks.clear();
   }
 };
 
@@ -149,7 +171,7 @@ int kp_create(int device, kp_handle** out) {
 void kp_destroy(kp_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  h->arena.release();
+  h->arena.destroy();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -449,7 +471,8 @@ static int reset_dynamic(kp_handle* h) {
 
 static int do_upload(kp_handle* h, const kp_problem* p, int cmax) {
   cudaSetDevice(h->device);
-  h->arena.release();
+  cudaStreamSynchronize(h->stream);
+  h->arena.reset();
   h->resident = false;
   h->stats = kp_stats{};
   auto t0 = std::chrono::steady_clock::now();

@@ -189,8 +189,11 @@ __device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, 
 template <bool OVERLAY>
 __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch, const int lane) {
   const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, EW = d.EW;
-  int head = 0, tail = I.P;
-  const int cap = I.P + 1;
+  const int P = I.P;
+  int head = 0, tail = P;
+  const int cap = P + 1;
+  int hq = 0, tq = P;  // head / tail modulo cap (cap > P, so the initial tail index is P)
+  const long long watchdog_limit = 4ll * P + 1024;
   int nC = 0;
   int pert = PERT_NONE, pert_pos = 0;
   long long ev_existing = 0, ev_inflight = 0, ev_tmpl = 0, commits = 0, slow_sorts = 0;
@@ -217,26 +220,31 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
   pf.pod = slot_absent();
   pf.strict = slot_absent();
 
+  // lb0 / lb1 (lane f): every claim at a position below this bound has rejected requirement signature f (resp. f+32)
+  // for good, so the in-flight scan of a pod with that signature starts there.  Maintained under every reordering.
+  int lb0 = 0, lb1 = 0;
   long long watchdog = 0;
   for (;;) {
     // ---- Queue.Pop (queue.go:46-60)
     const int len = tail - head;
     if (len == 0) break;
-    if (++watchdog > 4ll * I.P + 1024) {  // cannot happen: every requeue cycle needs progress (queue.go:54-58)
+    if (++watchdog > watchdog_limit) {  // cannot happen: every requeue cycle needs progress (queue.go:54-58)
       status = KP_ERR_INVALID;
       break;
     }
     const int h = head;
+    const int hq1 = hq + 1 >= cap ? hq + 1 - cap : hq + 1, hq2 = hq1 + 1 >= cap ? hq1 + 1 - cap : hq1 + 1;
     int li, X;
     if (ids_idx == h) {
       li = ids_pod;
       X = ids_cls;
     } else {
-      li = I.queue[h % cap];
-      X = I.qcls[h % cap];
+      li = I.queue[hq];
+      X = I.qcls[hq];
     }
-    if (h >= I.P && I.last_len[li] == len) break;  // a full cycle without progress
+    if (h >= P && I.last_len[li] == len) break;  // a full cycle without progress
     head = h + 1;
+    hq = hq1;
     {
       ClassRegs cur = pf_idx == h ? pf : load_class_regs(d, X, li, lane);
       __syncwarp();
@@ -251,16 +259,16 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         nli = ids_pod;
         nX = ids_cls;
       } else {
-        nli = I.queue[(h + 1) % cap];
-        nX = I.qcls[(h + 1) % cap];
+        nli = I.queue[hq1];
+        nX = I.qcls[hq1];
       }
       pf = load_class_regs(d, nX, nli, lane);
       pf_idx = h + 1;
     }
     ids_idx = -1;
     if (h + 2 < tail) {
-      ids_pod = I.queue[(h + 2) % cap];
-      ids_cls = I.qcls[(h + 2) % cap];
+      ids_pod = I.queue[hq2];
+      ids_cls = I.qcls[hq2];
       ids_idx = h + 2;
     }
     const PodCtx& px = ctx;
@@ -388,82 +396,80 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       const int p = pert_pos;
       const bool inversion = pert == PERT_INC ? (p + 1 < nC && cnt[p + 1] < cnt[p]) : (nC >= 2 && cnt[nC - 1] < cnt[nC - 2]);
       if (inversion) {
+        // When does Go's pdqsort leave the stable result?  n <= 12: insertion sort (stable).  n >= 50: choosePivot
+        // samples the triples around n/4, n/2, 3n/4; the slice is sorted except for the one pair (p, p+1), so it
+        // reports "increasing" -- and partialInsertionSort then repairs the pair by shifting the elevated element
+        // right, i.e. the stable move -- exactly when p is not the first or middle element of a sampled triple.  (An
+        // appended claim sits at n-1, never sampled.)  Everything else runs the real pdqsort.
         bool stable = d.stable_order || nC <= 12;
         if (!stable && nC >= 50) {
-          WarpSorter s{cnt, ord, lane};
-          int hint;
-          s.choose_pivot(0, nC, &hint);
-          stable = hint == 1;  // partialInsertionSort repairs a single inversion == stable move
+          const int q4 = nC / 4;
+          stable = pert == PERT_APPEND || !(p == q4 - 1 || p == q4 || p == 2 * q4 - 1 || p == 2 * q4 || p == 3 * q4 - 1 || p == 3 * q4);
         }
         if (stable) {
-          if (pert == PERT_INC) {  // elevated count: move right past every smaller element
-            const int c = cnt[p];
-            int lo = p + 1, hi = nC;
-            while (lo < hi) {
-              int mid = (lo + hi) >> 1;
-              if (cnt[mid] < c)
-                lo = mid + 1;
-              else
-                hi = mid;
-            }
-            const int from = p, to = lo - 1;
-            const int eo = ord[from], ec = cnt[from];
-            for (int b0 = from; b0 < to; b0 += 32) {
-              const int i = b0 + lane;
-              int vo = 0, vc = 0;
-              if (i < to) {
-                vo = ord[i + 1];
-                vc = cnt[i + 1];
-              }
+          if (pert == PERT_INC) {  // elevated count: shift smaller successors left until one is not smaller
+            const int ec = cnt[p], eo = ord[p];
+            int i0 = p;
+            for (;;) {
+              const int i = i0 + lane;
+              const bool in = i + 1 < nC;
+              const int vc = in ? cnt[i + 1] : 0x7fffffff, vo = in ? ord[i + 1] : 0;
+              const unsigned stop = __ballot_sync(FULL, vc >= ec);
+              const int nmove = stop ? __ffs(stop) - 1 : 32;
               __syncwarp();
-              if (i < to) {
-                ord[i] = vo;
+              if (lane < nmove) {
                 cnt[i] = vc;
+                ord[i] = vo;
               }
               __syncwarp();
+              i0 += nmove;
+              if (nmove < 32) break;
             }
             if (lane == 0) {
-              ord[to] = eo;
-              cnt[to] = ec;
+              cnt[i0] = ec;
+              ord[i0] = eo;
             }
-          } else {  // new claim appended: move left past every larger element
-            const int c = cnt[nC - 1];
-            int lo = 0, hi = nC - 1;
-            while (lo < hi) {
-              int mid = (lo + hi) >> 1;
-              if (cnt[mid] <= c)
-                lo = mid + 1;
-              else
-                hi = mid;
-            }
-            const int from = nC - 1, to = lo;
-            const int eo = ord[from], ec = cnt[from];
-            for (int b0 = from; b0 > to; b0 -= 32) {
-              const int i = b0 - lane;
-              int vo = 0, vc = 0;
-              if (i > to) {
-                vo = ord[i - 1];
-                vc = cnt[i - 1];
-              }
+            // positions (p, i0] moved one to the left: a bound inside that range follows its elements
+            if (p < lb0 && lb0 <= i0) lb0--;
+            if (p < lb1 && lb1 <= i0) lb1--;
+          } else {  // new claim appended: shift larger predecessors right until one is not larger
+            const int ec = cnt[nC - 1], eo = ord[nC - 1];
+            int i0 = nC - 1;
+            for (;;) {
+              const int i = i0 - lane;
+              const bool in = i - 1 >= 0;
+              const int vc = in ? cnt[i - 1] : -0x7fffffff, vo = in ? ord[i - 1] : 0;
+              const unsigned stop = __ballot_sync(FULL, vc <= ec);
+              const int nmove = stop ? __ffs(stop) - 1 : 32;
               __syncwarp();
-              if (i > to) {
-                ord[i] = vo;
+              if (lane < nmove) {
                 cnt[i] = vc;
+                ord[i] = vo;
               }
               __syncwarp();
+              i0 -= nmove;
+              if (nmove < 32) break;
             }
             if (lane == 0) {
-              ord[to] = eo;
-              cnt[to] = ec;
+              cnt[i0] = ec;
+              ord[i0] = eo;
             }
+            // the new claim (untested by every signature) now sits at i0
+            if (lb0 > i0) lb0 = i0;
+            if (lb1 > i0) lb1 = i0;
           }
         } else {
           // exact pdqsort emulation (rare: ties scrambled by Go's unstable partition), warp-cooperative
           WarpSorter s{cnt, ord, lane};
           s.pdqsort(0, nC, WarpSorter::bits_len((unsigned long long)nC));
           slow_sorts++;
+          lb0 = 0;  // ties were permuted arbitrarily: the bounds restart
+          lb1 = 0;
         }
         __syncwarp();
+      } else if (pert == PERT_APPEND) {  // the new claim stays last
+        if (lb0 > nC - 1) lb0 = nC - 1;
+        if (lb1 > nC - 1) lb1 = nC - 1;
       }
       pert = PERT_NONE;
     }
@@ -478,14 +484,17 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       const int hoff = px.hoff, hend = px.hend;
       const ulonglong2* cm = I.cmask;
       const int32_t* ctm = I.c_tmpl;
-      for (int base = 0; base < nC && !found && (tok & d.tmpl_all); base += 32) {
+      int lb = 0, first_clear = -1;
+      if (fbit) lb = __shfl_sync(FULL, fsig < 32 ? lb0 : lb1, fsig & 31);
+      for (int base = lb & ~31; base < nC && !found && (tok & d.tmpl_all); base += 32) {
         const int pos = base + lane;
-        bool pass = false;
+        bool pass = false, fclear = false;
         int c = -1;
-        if (pos < nC) {
+        if (pos < nC && pos >= lb) {
           c = ord[pos];
           const ulonglong2 mk = cm[c];
-          pass = !(mk.x & fbit) && !(mk.y & rbit);
+          fclear = !(mk.x & fbit);
+          pass = fclear && !(mk.y & rbit);
           if (pass && !all_tmpl) pass = (tok >> ctm[c]) & 1ull;
           // hostname groups: a NodeClaim is exactly one hostname domain (topologygroup.go:235-247,317-333,402-408)
           for (int i = hoff; pass && i < hend; i++) {
@@ -501,6 +510,10 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           }
         }
         unsigned m = __ballot_sync(FULL, pass);
+        if (fbit && first_clear < 0) {
+          const unsigned fm = __ballot_sync(FULL, fclear);
+          if (fm) first_clear = base + __ffs(fm) - 1;
+        }
         while (m && !found) {
           const int l = __ffs(m) - 1;
           m &= m - 1;
@@ -538,6 +551,15 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           pert_pos = cpos;
           ev_inflight += cpos + 1;  // claims 0..cpos were evaluated by the reference
           found = true;
+        }
+      }
+      if (fbit && (tok & d.tmpl_all)) {  // every position below the first clear bit rejected this signature for good
+        const int nb = first_clear >= 0 ? first_clear : nC;
+        if (lane == (fsig & 31)) {
+          if (fsig < 32)
+            lb0 = nb;
+          else
+            lb1 = nb;
         }
       }
       if (found) {
@@ -644,11 +666,12 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           I.pod_error[li] = (uint8_t)err;
           I.pod_target[li] = KP_TARGET_UNSCHEDULED;
         }
-        I.queue[tail % cap] = li;
-        I.qcls[tail % cap] = X;
+        I.queue[tq] = li;
+        I.qcls[tq] = X;
         I.last_len[li] = tail + 1 - head;
       }
       tail++;
+      tq = tq + 1 >= cap ? tq + 1 - cap : tq + 1;
       __syncwarp();
     }
   }
