@@ -223,6 +223,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
   // lb0 / lb1 (lane f): every claim at a position below this bound has rejected requirement signature f (resp. f+32)
   // for good, so the in-flight scan of a pod with that signature starts there.  Maintained under every reordering.
   int lb0 = 0, lb1 = 0;
+  // lr0 / lr1 (lane v): the same for request vector v (resp. v+32): every claim below can never fit it again
+  int lr0 = 0, lr1 = 0;
   long long watchdog = 0;
   for (;;) {
     // ---- Queue.Pop (queue.go:46-60)
@@ -432,6 +434,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             // positions (p, i0] moved one to the left: a bound inside that range follows its elements
             if (p < lb0 && lb0 <= i0) lb0--;
             if (p < lb1 && lb1 <= i0) lb1--;
+            if (p < lr0 && lr0 <= i0) lr0--;
+            if (p < lr1 && lr1 <= i0) lr1--;
           } else {  // new claim appended: shift larger predecessors right until one is not larger
             const int ec = cnt[nC - 1], eo = ord[nC - 1];
             int i0 = nC - 1;
@@ -457,6 +461,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             // the new claim (untested by every signature) now sits at i0
             if (lb0 > i0) lb0 = i0;
             if (lb1 > i0) lb1 = i0;
+            if (lr0 > i0) lr0 = i0;
+            if (lr1 > i0) lr1 = i0;
           }
         } else {
           // exact pdqsort emulation (rare: ties scrambled by Go's unstable partition), warp-cooperative
@@ -465,11 +471,15 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           slow_sorts++;
           lb0 = 0;  // ties were permuted arbitrarily: the bounds restart
           lb1 = 0;
+          lr0 = 0;
+          lr1 = 0;
         }
         __syncwarp();
       } else if (pert == PERT_APPEND) {  // the new claim stays last
         if (lb0 > nC - 1) lb0 = nC - 1;
         if (lb1 > nC - 1) lb1 = nC - 1;
+        if (lr0 > nC - 1) lr0 = nC - 1;
+        if (lr1 > nC - 1) lr1 = nC - 1;
       }
       pert = PERT_NONE;
     }
@@ -484,17 +494,20 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       const int hoff = px.hoff, hend = px.hend;
       const ulonglong2* cm = I.cmask;
       const int32_t* ctm = I.c_tmpl;
-      int lb = 0, first_clear = -1;
-      if (fbit) lb = __shfl_sync(FULL, fsig < 32 ? lb0 : lb1, fsig & 31);
+      int lbf = 0, lbr = 0, first_clear = -1, first_rclear = -1;
+      if (fbit) lbf = __shfl_sync(FULL, fsig < 32 ? lb0 : lb1, fsig & 31);
+      if (rbit) lbr = __shfl_sync(FULL, rv < 32 ? lr0 : lr1, rv & 31);
+      const int lb = lbf > lbr ? lbf : lbr;  // below either bound a claim fails for one of the two reasons
       for (int base = lb & ~31; base < nC && !found && (tok & d.tmpl_all); base += 32) {
         const int pos = base + lane;
-        bool pass = false, fclear = false;
+        bool pass = false, fclear = false, rclear = false;
         int c = -1;
         if (pos < nC && pos >= lb) {
           c = ord[pos];
           const ulonglong2 mk = cm[c];
           fclear = !(mk.x & fbit);
-          pass = fclear && !(mk.y & rbit);
+          rclear = !(mk.y & rbit);
+          pass = fclear && rclear;
           if (pass && !all_tmpl) pass = (tok >> ctm[c]) & 1ull;
           // hostname groups: a NodeClaim is exactly one hostname domain (topologygroup.go:235-247,317-333,402-408)
           for (int i = hoff; pass && i < hend; i++) {
@@ -513,6 +526,10 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         if (fbit && first_clear < 0) {
           const unsigned fm = __ballot_sync(FULL, fclear);
           if (fm) first_clear = base + __ffs(fm) - 1;
+        }
+        if (rbit && first_rclear < 0) {
+          const unsigned rm = __ballot_sync(FULL, rclear);
+          if (rm) first_rclear = base + __ffs(rm) - 1;
         }
         while (m && !found) {
           const int l = __ffs(m) - 1;
@@ -553,13 +570,23 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           found = true;
         }
       }
-      if (fbit && (tok & d.tmpl_all)) {  // every position below the first clear bit rejected this signature for good
+      // a bound may only advance when the scan really started at it (positions below `lb` were not looked at)
+      if (fbit && (tok & d.tmpl_all) && lbf == lb) {  // all positions below the first clear bit rejected the signature
         const int nb = first_clear >= 0 ? first_clear : nC;
         if (lane == (fsig & 31)) {
           if (fsig < 32)
             lb0 = nb;
           else
             lb1 = nb;
+        }
+      }
+      if (rbit && (tok & d.tmpl_all) && lbr == lb) {
+        const int nb = first_rclear >= 0 ? first_rclear : nC;
+        if (lane == (rv & 31)) {
+          if (rv < 32)
+            lr0 = nb;
+          else
+            lr1 = nb;
         }
       }
       if (found) {
