@@ -640,7 +640,7 @@ static int run_solve(kp_handle* h) {
   if (const char* lim = getenv("KP_CS_LIMIT")) CS = std::min(CS, std::max(0, atoi(lim)) / 32 * 32);  // test knob
   size_t smem = fixed + tb + (CS ? small_bytes(CS) : 0) + 64;
   CK(cudaFuncSetAttribute(k_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_wsolve<<<1, 32, smem, h->stream>>>(d, CS, CR);
+  k_wsolve<<<1, 64, smem, h->stream>>>(d, CS, CR);
   h->stats.kernel_launches++;
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -659,7 +659,9 @@ static int download(kp_handle* h, kp_result* out) {
   int64_t counters[16];
   CK(cudaMemcpy(&nclaims, d.n_claims, 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(counters, d.counters, 128, cudaMemcpyDeviceToHost));
-  if (getenv("KP_DEBUG")) fprintf(stderr, "[kp] slow_sorts=%lld\n", (long long)counters[4]);
+  if (getenv("KP_DEBUG"))
+    fprintf(stderr, "[kp] slow_sorts=%lld scan_chunks=%lld evals=%lld commits=%lld\n", (long long)counters[4],
+            (long long)counters[5], (long long)counters[6], (long long)counters[3]);
   int64_t P = h->P;
   int K = h->n_keys, R = h->n_resources, ITW = (h->n_its + 63) / 64;
   size_t C = (size_t)nclaims, c1 = C ? C : 1;

@@ -120,20 +120,25 @@ __global__ void __launch_bounds__(256) k_node_cand(KpDev d, const int32_t* nsig_
 struct WSolveShared {
   KpDev ds;
   WInst inst;
-  PodCtx ctx;
+  StageRing ring;
   Slot scratch[KP_MAXK];
 };
 
-__global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS, int CR) {
+// warp 0: the solver; warp 1: the pod stager (see StageRing)
+__global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS, int CR) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WSolveShared& sh = *reinterpret_cast<WSolveShared*>(smem_raw);
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* tab = smem_raw + KP_ALIGN16(sizeof(WSolveShared));
   stage_tables(d_in, &sh.ds, tab);
   const KpDev& d = sh.ds;
   WInst& I = sh.inst;
   const int Cmax = d.Cmax;
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
+    sh.ring.produced = 0;
+    sh.ring.consumed = 0;
+    sh.ring.tail_pub = (int)d.P;
+    sh.ring.done = 0;
     I.P = (int)d.P;
     I.queue = d.queue;
     I.qcls = d.qcls;
@@ -199,8 +204,12 @@ __global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev 
       I.CS = CS;
     }
   }
-  __syncwarp();
-  wsolve_run<false>(d, I, sh.ctx, sh.scratch, lane);
+  __syncthreads();
+  if (warp == 1) {
+    stager_run(d, I, &sh.ring, lane);
+    return;
+  }
+  wsolve_run<false, true>(d, I, sh.ring.slot[0], sh.scratch, lane, &sh.ring);
   const int nC = I.n_claims;
   claim_rows_flush(d, I, nC, lane);
   if (I.CS > 0) {  // the host reads the final order (claim_rank) and template ids from global memory
@@ -218,6 +227,8 @@ __global__ void __launch_bounds__(32, 1) k_wsolve(const __grid_constant__ KpDev 
     d.counters[2] = I.ev_tmpl;
     d.counters[3] = I.commits;
     d.counters[4] = I.slow_sorts;
+    d.counters[5] = I.scan_chunks;
+    d.counters[6] = I.evals;
   }
 }
 
@@ -387,7 +398,7 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
       I.tmpl_remaining[i] = rem;
     }
     __syncwarp();
-    wsolve_run<true>(d, I, W.ctx, W.scratch, lane);
+    wsolve_run<true, false>(d, I, W.ctx, W.scratch, lane);
     if (I.status != KP_OK) {
       if (lane == 0) *q.status = I.status;
       break;

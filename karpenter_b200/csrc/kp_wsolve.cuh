@@ -76,7 +76,7 @@ struct WInst {
   int64_t *ov_sgte, *ov_slte;
   // results
   int n_claims, n_unsched, n_uninit, status;
-  long long ev_existing, ev_inflight, ev_tmpl, commits, slow_sorts;
+  long long ev_existing, ev_inflight, ev_tmpl, commits, slow_sorts, scan_chunks, evals;
 };
 
 // index of `node` in the overlay, -1 if it is untouched (warp-uniform result)
@@ -185,9 +185,42 @@ __device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, 
   __syncwarp();
 }
 
+// Pod staging ring between a stager warp and the solver warp of one CTA (k_wsolve): the stager walks the queue a few
+// pods ahead and parks each pod's class row (header, requests, requirement slots) in shared memory, so the solver's
+// dependence chain never waits on -- or spends instructions for -- the L2 loads of the next pod.
+#define KP_RING 8
+struct StageRing {
+  volatile int produced;  // pods staged so far (stager)
+  volatile int consumed;  // pods the solver is done with (solver)
+  volatile int tail_pub;  // queue entries below this index are valid (solver; grows with every requeue)
+  volatile int done;
+  PodCtx slot[KP_RING];
+};
+
+__device__ void stager_run(const KpDev& d, const WInst& I, StageRing* ring, const int lane) {
+  const int cap = I.P + 1;
+  int qi = 0;
+  for (int idx = 0;; idx++) {
+    for (;;) {
+      if (ring->done) return;
+      if (idx < ring->tail_pub && idx - ring->consumed < KP_RING) break;
+      __nanosleep(64);
+    }
+    __threadfence_block();
+    const int li = __ldcg(I.queue + qi), X = __ldcg(I.qcls + qi);
+    qi = qi + 1 >= cap ? 0 : qi + 1;
+    ClassRegs c = load_class_regs(d, X, li, lane);
+    store_class_regs(d, ring->slot[idx & (KP_RING - 1)], c, lane);
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) ring->produced = idx + 1;
+  }
+}
+
 // One Scheduler.Solve over the instance's queue.  OVERLAY: existing-node state = shared base + private overlay.
-template <bool OVERLAY>
-__device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch, const int lane) {
+// STAGED: pods arrive through a StageRing filled by a second warp instead of being staged inline.
+template <bool OVERLAY, bool STAGED>
+__device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch, const int lane, StageRing* ring = nullptr) {
   const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, EW = d.EW;
   const int P = I.P;
   int head = 0, tail = P;
@@ -196,7 +229,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
   const long long watchdog_limit = 4ll * P + 1024;
   int nC = 0;
   int pert = PERT_NONE, pert_pos = 0;
-  long long ev_existing = 0, ev_inflight = 0, ev_tmpl = 0, commits = 0, slow_sorts = 0;
+  long long ev_existing = 0, ev_inflight = 0, ev_tmpl = 0, commits = 0, slow_sorts = 0, scan_chunks = 0, evals = 0;
   int n_unsched = 0, n_uninit = 0, status = KP_OK;
   int32_t* ord = I.order;
   int32_t* cnt = I.cnt_at;
@@ -237,7 +270,16 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
     const int h = head;
     const int hq1 = hq + 1 >= cap ? hq + 1 - cap : hq + 1, hq2 = hq1 + 1 >= cap ? hq1 + 1 - cap : hq1 + 1;
     int li, X;
-    if (ids_idx == h) {
+    if (STAGED) {
+      if (lane == 0) ring->consumed = h;  // every slot below h is free again
+      while (ring->produced <= h) {
+      }
+      __threadfence_block();
+      __syncwarp();
+      const PodCtx& sx = ring->slot[h & (KP_RING - 1)];
+      li = sx.pod;
+      X = sx.cls;
+    } else if (ids_idx == h) {
       li = ids_pod;
       X = ids_cls;
     } else {
@@ -247,33 +289,35 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
     if (h >= P && I.last_len[li] == len) break;  // a full cycle without progress
     head = h + 1;
     hq = hq1;
-    {
-      ClassRegs cur = pf_idx == h ? pf : load_class_regs(d, X, li, lane);
-      __syncwarp();
-      store_class_regs(d, ctx, cur, lane);
-      __syncwarp();
-    }
-    // issue the loads for the next two pods; nothing below waits on them
-    pf_idx = -1;
-    if (h + 1 < tail) {
-      int nli, nX;
-      if (ids_idx == h + 1) {
-        nli = ids_pod;
-        nX = ids_cls;
-      } else {
-        nli = I.queue[hq1];
-        nX = I.qcls[hq1];
+    if (!STAGED) {
+      {
+        ClassRegs cur = pf_idx == h ? pf : load_class_regs(d, X, li, lane);
+        __syncwarp();
+        store_class_regs(d, ctx, cur, lane);
+        __syncwarp();
       }
-      pf = load_class_regs(d, nX, nli, lane);
-      pf_idx = h + 1;
+      // issue the loads for the next two pods; nothing below waits on them
+      pf_idx = -1;
+      if (h + 1 < tail) {
+        int nli, nX;
+        if (ids_idx == h + 1) {
+          nli = ids_pod;
+          nX = ids_cls;
+        } else {
+          nli = I.queue[hq1];
+          nX = I.qcls[hq1];
+        }
+        pf = load_class_regs(d, nX, nli, lane);
+        pf_idx = h + 1;
+      }
+      ids_idx = -1;
+      if (h + 2 < tail) {
+        ids_pod = I.queue[hq2];
+        ids_cls = I.qcls[hq2];
+        ids_idx = h + 2;
+      }
     }
-    ids_idx = -1;
-    if (h + 2 < tail) {
-      ids_pod = I.queue[hq2];
-      ids_cls = I.qcls[hq2];
-      ids_idx = h + 2;
-    }
-    const PodCtx& px = ctx;
+    const PodCtx& px = STAGED ? ring->slot[h & (KP_RING - 1)] : ctx;
     const int rv = px.rv, fsig = px.fsig;
     bool found = false;
 
@@ -500,6 +544,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       const int lb = lbf > lbr ? lbf : lbr;  // below either bound a claim fails for one of the two reasons
       for (int base = lb & ~31; base < nC && !found && (tok & d.tmpl_all); base += 32) {
         const int pos = base + lane;
+        scan_chunks++;
         bool pass = false, fclear = false, rclear = false;
         int c = -1;
         if (pos < nC && pos >= lb) {
@@ -541,6 +586,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           uint64_t bi;
           int bj;
           claim_load(d, I, cc, lane, &b, &bq, &bi, &bj);
+          evals++;
           Eval ev = eval_candidate(d, px, true, b, bq, bi, bj, E + cc, scratch, lane);
           if (!ev.ok) {
             if (lane == 0) {
@@ -699,8 +745,16 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       }
       tail++;
       tq = tq + 1 >= cap ? tq + 1 - cap : tq + 1;
+      if (STAGED) {
+        __threadfence_block();
+        if (lane == 0) ring->tail_pub = tail;
+      }
       __syncwarp();
     }
+  }
+  if (STAGED) {
+    __syncwarp();
+    if (lane == 0) ring->done = 1;
   }
   // pods still queued when the loop ends are the PodErrors (scheduler.go:415-423)
   n_unsched = tail - head;
@@ -714,6 +768,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
     I.ev_tmpl = ev_tmpl;
     I.commits = commits;
     I.slow_sorts = slow_sorts;
+    I.scan_chunks = scan_chunks;
+    I.evals = evals;
   }
   __syncwarp();
 }
