@@ -421,6 +421,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(zeros(h, &d.order, C));
   CK(zeros(h, &d.cnt_at, C));
   CK(zeros(h, &d.cmask, C));
+  CK(zeros(h, &d.amask, C));
   d.tmpl_all = t.N >= 64 ? ~0ull : ((1ull << t.N) - 1);
   d.H = t.E + d.Cmax;
   CK(zeros(h, &d.host_cnt, (size_t)std::max(t.GH, 1) * d.H));
@@ -457,6 +458,7 @@ static int reset_dynamic(kp_handle* h) {
   size_t C = (size_t)d.Cmax;
   CK(cudaMemsetAsync(d.c_npods, 0, C * 4, h->stream));
   CK(cudaMemsetAsync(d.cmask, 0, C * sizeof(ulonglong2), h->stream));
+  CK(cudaMemsetAsync(d.amask, 0, C * 8, h->stream));
   CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)std::max(t.GH, 1) * d.H * 4, h->stream));
   for (int g = 0; g < t.GH; g++)
     if (t.E)
@@ -623,7 +625,7 @@ static int run_solve(kp_handle* h) {
   if (getenv("KP_CS_LIMIT")) CR = std::min(CR, 32);
   tb += CR ? row_bytes(CR) : 0;  // from here on `tb` is everything in front of the small arrays
   // ... and claim order / failure masks of the first CS claims
-  auto small_bytes = [&](int cs) { return (size_t)cs * 28; };  // cmask 16 B + order, count, template id
+  auto small_bytes = [&](int cs) { return (size_t)cs * 36; };  // cmask 16 B + amask 8 B + order, count, template id
   int CS = 0;
   if (fixed + tb + small_bytes(64) + 64 <= budget) {  // the largest multiple of 32 that fits, capped at Cmax
     int lo = 64, hi = ((d.Cmax + 31) / 32) * 32;
@@ -963,6 +965,7 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   CK(zeros(h, &q.c_its, slots * cq * ITW));
   CK(zeros(h, &q.c_j, slots * cq * R));
   CK(zeros(h, &q.cmask, slots * cq));
+  CK(zeros(h, &q.amask, slots * cq));
   CK(zeros(h, &q.tmpl_remaining, slots * (size_t)std::max(N, 1) * R));
   CK(zeros(h, &q.ov_node, slots * cq));
   CK(zeros(h, &q.ov_rem, slots * cq * R));

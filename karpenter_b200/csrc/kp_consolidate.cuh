@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev 
     I.order = d.order;
     I.cnt_at = d.cnt_at;
     I.cmask = d.cmask;
+    I.amask = d.amask;
     I.tmpl_remaining = d.tmpl_remaining;
     I.node_rem = d.node_rem;
     I.node_rem_present = d.node_rem_present;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev 
     I.g_cnt_at = d.cnt_at;
     I.g_c_tmpl = d.c_tmpl;
     I.g_cmask = d.cmask;
+    I.g_amask = d.amask;
     I.CR = 0;
     unsigned char* p = tab + d_in.tab_bytes;
     if (CR > 0) {  // rows of the first CR claims
@@ -196,6 +198,8 @@ __global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev 
     if (CS > 0) {  // claim order, template ids and the failure masks of the first CS claims live in shared memory
       I.cmask = reinterpret_cast<ulonglong2*>(p);
       p += (size_t)CS * 16;
+      I.amask = reinterpret_cast<unsigned long long*>(p);
+      p += (size_t)CS * 8;
       I.order = reinterpret_cast<int32_t*>(p);
       p += (size_t)CS * 4;
       I.cnt_at = reinterpret_cast<int32_t*>(p);
@@ -265,6 +269,7 @@ struct KpConsol {
   uint64_t* c_its;
   int32_t* c_j;
   ulonglong2* cmask;
+  unsigned long long* amask;
   int64_t* tmpl_remaining;
   int32_t* ov_node;
   int64_t* ov_rem;
@@ -323,6 +328,7 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
     I.order = q.order + slot * capq;
     I.cnt_at = q.cnt_at + slot * capq;
     I.cmask = q.cmask + slot * capq;
+    I.amask = q.amask + slot * capq;
     I.tmpl_remaining = q.tmpl_remaining + slot * (size_t)(N > 0 ? N : 1) * R;
     I.node_rem = d.node_rem;  // shared base, read-only here
     I.node_rem_present = d.node_rem_present;

@@ -168,6 +168,7 @@ struct KpDev {
   int n_fsig;                     // distinct requirement sets of such classes
   ulonglong2* cmask;              // [Cmax] per claim: x = rejected requirement signatures, y = request vectors that can
                                   // never fit again (bit index = signature / vector id, ids >= 64 are not cached)
+  unsigned long long* amask;      // [Cmax] per claim: signatures that add nothing to the claim's requirements
   unsigned long long tmpl_all;    // bit n: template n survived the NewScheduler prefilter input (n < N)
   // existing-node candidate bitmaps (supersets; the exact CanAdd runs on every candidate)
   int n_nsig, EW;                 // distinct (requirements, tolerations) signatures; words per row = ceil(E/32)

@@ -49,6 +49,11 @@ struct WInst {
   // Requirements.Compatible, y = bit rv set when no remaining instance type can hold the claim's requests plus request
   // vector rv.  Signatures / vectors with an index >= 64 are simply not cached (exact either way).
   ulonglong2* cmask;
+  // amask[c] bit f: requirement signature f adds nothing to claim c's requirements.  Stable for the claim's lifetime
+  // (the claim's value sets only shrink, so they stay inside the pod's), which reduces CanAdd for such a pair to the
+  // resource test.
+  unsigned long long* amask;
+  unsigned long long* g_amask;
   // While the claim order, template ids and failure masks fit, they live in shared memory (CS = claims the shared
   // copies can hold, 0 = not in use); the moment a claim id reaches CS everything migrates to the global arrays below.
   int CS;
@@ -151,6 +156,40 @@ __device__ __forceinline__ void claim_store(const KpDev& d, WInst& I, int c, int
     I.c_slte[(size_t)c * K + lane] = ev.F.lte;
   }
 }
+// requests / threshold rows only (lane r), and the instance-type words only (lane w)
+__device__ __forceinline__ void claim_load_rq(const KpDev& d, const WInst& I, int c, int lane, int64_t* q, int* j) {
+  *q = 0;
+  *j = 0;
+  if (lane < d.R) {
+    if (c < I.CR) {
+      *q = I.s_req[c * d.R + lane];
+      *j = I.s_j[c * d.R + lane];
+    } else {
+      *q = I.c_req[(size_t)c * d.R + lane];
+      *j = I.c_j[(size_t)c * d.R + lane];
+    }
+  }
+}
+__device__ __forceinline__ uint64_t claim_load_its(const KpDev& d, const WInst& I, int c, int lane) {
+  if (lane >= d.ITW) return 0ull;
+  return c < I.CR ? I.s_its[c * d.ITW + lane] : I.c_its[(size_t)c * d.ITW + lane];
+}
+__device__ __forceinline__ void claim_store_rq(const KpDev& d, WInst& I, int c, int lane, int64_t q, int j, bool with_its,
+                                               uint64_t its) {
+  if (c < I.CR) {
+    if (lane < d.R) {
+      I.s_req[c * d.R + lane] = q;
+      I.s_j[c * d.R + lane] = j;
+    }
+    if (with_its && lane < d.ITW) I.s_its[c * d.ITW + lane] = its;
+  } else {
+    if (lane < d.R) {
+      I.c_req[(size_t)c * d.R + lane] = q;
+      I.c_j[(size_t)c * d.R + lane] = j;
+    }
+    if (with_its && lane < d.ITW) I.c_its[(size_t)c * d.ITW + lane] = its;
+  }
+}
 // copy the shared-memory claim rows to their global arrays (end of the solve)
 __device__ __forceinline__ void claim_rows_flush(const KpDev& d, WInst& I, int nC, int lane) {
   const int n = nC < I.CR ? nC : I.CR;
@@ -173,6 +212,7 @@ __device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, 
     I.g_cnt_at[i] = I.cnt_at[i];
     I.g_c_tmpl[i] = I.c_tmpl[i];
     I.g_cmask[i] = I.cmask[i];
+    I.g_amask[i] = I.amask[i];
   }
   __syncwarp();
   if (lane == 0) {
@@ -180,6 +220,7 @@ __device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, 
     I.cnt_at = I.g_cnt_at;
     I.c_tmpl = I.g_c_tmpl;
     I.cmask = I.g_cmask;
+    I.amask = I.g_amask;
     I.CS = 0;
   }
   __syncwarp();
@@ -319,6 +360,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
     }
     const PodCtx& px = STAGED ? ring->slot[h & (KP_RING - 1)] : ctx;
     const int rv = px.rv, fsig = px.fsig;
+    const unsigned long long fbit = (fsig >= 0 && fsig < 64) ? 1ull << fsig : 0ull;
+    const unsigned long long rbit = rv < 64 ? 1ull << rv : 0ull;
     bool found = false;
 
     // ================= addToExistingNode (scheduler.go:520-555) =================
@@ -531,13 +574,12 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
     // ================= addToInflightNode (scheduler.go:557-589) =================
     {
       // loop invariants of the scan, in registers: the failure bits to test, the tolerated templates, hostname checks
-      const unsigned long long fbit = (fsig >= 0 && fsig < 64) ? 1ull << fsig : 0ull;
-      const unsigned long long rbit = rv < 64 ? 1ull << rv : 0ull;
       const unsigned long long tok = px.tmpl_ok;
       const bool all_tmpl = (tok & d.tmpl_all) == d.tmpl_all;
       const int hoff = px.hoff, hend = px.hend;
       const ulonglong2* cm = I.cmask;
       const int32_t* ctm = I.c_tmpl;
+      const bool fast_ok = fbit != 0 && px.roff == px.rend;  // topology-free and counted by no topology group
       int lbf = 0, lbr = 0, first_clear = -1, first_rclear = -1;
       if (fbit) lbf = __shfl_sync(FULL, fsig < 32 ? lb0 : lb1, fsig & 31);
       if (rbit) lbr = __shfl_sync(FULL, rv < 32 ? lr0 : lr1, rv & 31);
@@ -581,6 +623,57 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           m &= m - 1;
           const int cpos = base + l;
           const int cc = __shfl_sync(FULL, c, l);
+          if (fast_ok && (I.amask[cc] & fbit)) {
+            // ---- the pod's requirements are already implied by the claim's: CanAdd == "do the merged requests still
+            // fit a remaining instance type", and the stored list only changes when a threshold row advances
+            int64_t q;
+            int j;
+            claim_load_rq(d, I, cc, lane, &q, &j);
+            evals++;
+            int lo = j;
+            bool adv = false;
+            if (lane < R) {
+              q += px.req[lane];
+              const int end = d.ge_off[lane + 1];
+              while (lo < end && d.ge_vals[lo] < q) lo++;
+              adv = lo != j;
+            }
+            unsigned advm = __ballot_sync(FULL, adv);
+            const bool any_adv = advm != 0;
+            uint64_t its = 0;
+            bool ok = true;
+            if (any_adv) {
+              its = claim_load_its(d, I, cc, lane);
+              const int jj = (lane < R && lo == d.ge_off[lane + 1]) ? -1 : lo;
+              while (advm) {
+                const int r = __ffs(advm) - 1;
+                advm &= advm - 1;
+                const int jr = __shfl_sync(FULL, jj, r);
+                if (lane < ITW) its &= jr >= 0 ? d.ge_bits[(size_t)jr * ITW + lane] : 0ull;
+              }
+              ok = __any_sync(FULL, its != 0);
+            }
+            if (!ok) {  // nothing left that holds the merged requests: permanent for this request vector
+              if (lane == 0) I.cmask[cc].y |= rbit;
+              __syncwarp();
+              continue;
+            }
+            claim_store_rq(d, I, cc, lane, q, lo, any_adv, its);
+            if (lane == 0) {
+              I.c_npods[cc]++;
+              cnt[cpos]++;
+              if (I.pod_target) {
+                I.pod_target[li] = KP_TARGET_CLAIM(cc);
+                I.pod_error[li] = KP_PODERR_NONE;
+              }
+            }
+            __syncwarp();
+            pert = PERT_INC;
+            pert_pos = cpos;
+            ev_inflight += cpos + 1;
+            found = true;
+            continue;
+          }
           Slot b;
           int64_t bq;
           uint64_t bi;
@@ -588,6 +681,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           claim_load(d, I, cc, lane, &b, &bq, &bi, &bj);
           evals++;
           Eval ev = eval_candidate(d, px, true, b, bq, bi, bj, E + cc, scratch, lane);
+          if (fbit && !ev.compat_fail && !ev.changed && lane == 0) I.amask[cc] |= fbit;
           if (!ev.ok) {
             if (lane == 0) {
               ulonglong2 mk = I.cmask[cc];
@@ -695,7 +789,10 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         }
       }
       // a recycled instance must not inherit failure bits of an earlier claim with this id
-      if (lane == 0) I.cmask[cnew] = make_ulonglong2(0ull, 0ull);
+      if (lane == 0) {
+        I.cmask[cnew] = make_ulonglong2(0ull, 0ull);
+        I.amask[cnew] = (fbit && !ev.changed) ? fbit : 0ull;
+      }
       // subtractMax (scheduler.go:840-857): remaining -= max capacity over the claim's instance types
       if (lp) {
         for (int r = 0; r < R; r++) {
