@@ -130,3 +130,17 @@ def test_shared_to_global_migration(monkeypatch):
             assert_same(res, oracle_lib.solve(enc.problem), what)
     finally:
         h.close()
+
+
+def test_c3_100k_parity(handle):
+    """C3 shape at 100 000 pods (100 apps x 1000 replicas, 1000 instance types): zonal spread + hostname anti-affinity,
+    1000 NodeClaims, bit-identical to the oracle."""
+    enc = workloads.config_c3(n_apps=100, replicas=1000, n_its=1000)
+    res = handle.solve(enc.problem)
+    assert_same(res, oracle_lib.solve(enc.problem), "C3[100x1000] ")
+    # size-independent properties of the domain: one pod of an app per NodeClaim, zonal skew <= 1 per app
+    tgt = res["pod_target"]
+    assert np.all(tgt <= -2)
+    claim = -2 - tgt
+    app = np.arange(len(tgt)) // 1000
+    assert len(set(zip(app.tolist(), claim.tolist()))) == len(tgt)
