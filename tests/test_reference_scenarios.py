@@ -1,0 +1,302 @@
+"""Scenarios of the reference's own scheduling test-suite, replayed with the reference's fake cloud-provider catalog.
+
+Each case restates one `It(...)` of pkg/controllers/provisioning/scheduling/{suite_test.go,topology_test.go} with the
+expected outcome the reference asserts (instance type picked, number of nodes, zonal skew, unschedulable pods).  They
+pin the ORACLE (oracle/) to reference behaviour beyond the requirement-algebra known-answer tables: the CPU tier runs
+the scenarios through the oracle, the GPU tier runs the same scenarios through the CUDA path and additionally demands
+bit-identical results.  The fake provider launches the cheapest instance type of a NodeClaim's options
+(fake/cloudprovider.go Create), which is what `cheapest()` evaluates.
+"""
+from collections import Counter
+
+import pytest
+
+from karpenter_b200 import fake
+from karpenter_b200.model import (ARCH_LABEL, CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, ZONE_LABEL, LabelSelector, NodePool,
+                                  NodeSelectorRequirement, Pod, PodAffinityTerm, TopologySpreadConstraint)
+from karpenter_b200.scheduler import Scheduler
+from tests import oracle_lib
+
+PRICE = {it.name: fake.price_from_resources(it.capacity) for it in fake.default_instance_types()}
+
+
+def nodepool(**kw):
+    """suite_test.go:135-149: capacity-type In [spot, on-demand, reserved]; test.NodePool() default limit cpu 2000."""
+    reqs = [NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "In", ("spot", "on-demand", "reserved"))]
+    reqs += kw.pop("requirements", [])
+    return NodePool(name="default", requirements=reqs, limits={"cpu": "2000"}, **kw)
+
+
+def pods(n, uid0=1, **kw):
+    return [Pod(name=f"p{uid0 + i}", uid=uid0 + i, **kw) for i in range(n)]
+
+
+def cheapest(claim):
+    return min(claim.instance_type_options, key=lambda n: (PRICE[n], n))
+
+
+def zone_of(claim):
+    z = claim.requirements[ZONE_LABEL]
+    assert not z["complement"] and len(z["values"]) == 1, z
+    return z["values"][0]
+
+
+def solve(backend, pod_list, np_=None, its=None):
+    np_ = np_ or nodepool()
+    its = its or fake.default_instance_types()
+    s = Scheduler([np_], {np_.name: its}, backend=backend)
+    try:
+        return s.solve(pod_list)
+    finally:
+        s.close()
+
+
+def gpu_and_oracle(pod_list, np_=None, its=None):
+    """CUDA path result, checked bit for bit against the oracle on the same encoding."""
+    from tests.parity import assert_same
+    gpu = solve(None, pod_list, np_, its)
+    orc = solve(oracle_lib.solve, pod_list, np_, its)
+    assert_same(gpu.raw, orc.raw, "scenario ")
+    return gpu
+
+
+BACKENDS = [pytest.param("oracle", id="oracle"), pytest.param("gpu", id="gpu", marks=pytest.mark.gpu)]
+
+
+def run(which, pod_list, np_=None, its=None):
+    return solve(oracle_lib.solve, pod_list, np_, its) if which == "oracle" else gpu_and_oracle(pod_list, np_, its)
+
+
+# ---- Binpacking (suite_test.go:1520-1836) -------------------------------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_small_pod_on_smallest_instance(which):  # suite_test.go:1521-1533
+    r = run(which, pods(1, requests={"memory": "100M"}))
+    assert len(r.new_node_claims) == 1 and not r.pod_errors
+    assert cheapest(r.new_node_claims[0]) == "small-instance-type"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_small_pod_on_smallest_possible_instance(which):  # suite_test.go:1534-1546
+    r = run(which, pods(1, requests={"memory": "2000M"}))
+    assert cheapest(r.new_node_claims[0]) == "small-instance-type"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_multiple_small_pods_share_one_small_node(which):  # suite_test.go:1573-1592
+    r = run(which, pods(5, requests={"memory": "10M"}))
+    assert len(r.new_node_claims) == 1 and len(r.new_node_claims[0].pods) == 5
+    assert cheapest(r.new_node_claims[0]) == "small-instance-type"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_new_nodes_when_at_capacity(which):  # suite_test.go:1593-1611: 40 x 1.8G on 4Gi types -> 20 nodes
+    r = run(which, pods(40, requests={"memory": "1.8G"}, node_selector={ARCH_LABEL: "amd64"}))
+    assert len(r.new_node_claims) == 20 and not r.pod_errors
+    assert all(cheapest(c) == "default-instance-type" and len(c.pods) == 2 for c in r.new_node_claims)
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_pack_small_and_large_together(which):  # suite_test.go:1612-1643: 40 large + 20 small -> still 20 nodes
+    sel = {ARCH_LABEL: "amd64"}
+    pl = pods(40, requests={"memory": "1.8G"}, node_selector=sel) + pods(20, uid0=100, requests={"memory": "400M"},
+                                                                          node_selector=sel)
+    r = run(which, pl)
+    assert len(r.new_node_claims) == 20 and not r.pod_errors
+    assert all(cheapest(c) == "default-instance-type" for c in r.new_node_claims)
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_zero_quantity_unknown_resource_schedules(which):  # suite_test.go:1670-1681
+    r = run(which, pods(1, requests={"foo.com/weird-resources": "0"}))
+    assert len(r.new_node_claims) == 1 and not r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_pod_exceeding_every_instance_type(which):  # suite_test.go:1682-1692
+    p = pods(1, requests={"memory": "2Ti"})
+    r = run(which, p)
+    assert not r.new_node_claims and id(p[0]) in r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_pod_limit_per_node(which):  # suite_test.go:1693-1714: 25 tiny pods, 5 pods per node -> 5 small nodes
+    # the reference asks for memory "1m" (a milli-byte); the encoder's exact unit for memory is the byte, so "1" here
+    r = run(which, pods(25, requests={"memory": "1", "cpu": "1m"}, node_selector={ARCH_LABEL: "amd64"}))
+    assert len(r.new_node_claims) == 5 and all(len(c.pods) == 5 for c in r.new_node_claims)
+    assert all(cheapest(c) == "small-instance-type" for c in r.new_node_claims)
+
+
+# ---- Topology (topology_test.go:107-651) ---------------------------------------------------------------------------
+LABELS = {"test": "test"}
+
+
+def topo_nodepool(requirements=()):
+    """topology_test.go:41-56: capacity-type Exists (so the domain universe is what the instance types offer)."""
+    return NodePool(name="default", requirements=[NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "Exists")] +
+                    list(requirements), limits={"cpu": "2000"})
+
+
+def spread(key=ZONE_LABEL, max_skew=1, selector=None):
+    return [TopologySpreadConstraint(max_skew, key, selector or LabelSelector.of(LABELS))]
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_zonal_balance_match_labels(which):  # topology_test.go:108-121: 4 pods over 3 zones -> skew (1, 1, 2)
+    r = run(which, pods(4, labels=LABELS, topology_spread_constraints=spread()), topo_nodepool())
+    skew = Counter(zone_of(c) for c in r.new_node_claims for _ in c.pods)
+    assert sorted(skew.values()) == [1, 1, 2] and not r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_zonal_balance_match_expressions(which):  # topology_test.go:122-143
+    sel = LabelSelector.of(None, [("test", "In", ("test",))])
+    r = run(which, pods(4, labels=LABELS, topology_spread_constraints=spread(selector=sel)), topo_nodepool())
+    skew = Counter(zone_of(c) for c in r.new_node_claims for _ in c.pods)
+    assert sorted(skew.values()) == [1, 1, 2]
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_zonal_respects_nodepool_subset(which):  # topology_test.go:160-176: two zones allowed -> (2, 2)
+    np_ = topo_nodepool([NodeSelectorRequirement(ZONE_LABEL, "In", ("test-zone-1", "test-zone-2"))])
+    r = run(which, pods(4, labels=LABELS, topology_spread_constraints=spread()), np_)
+    skew = Counter(zone_of(c) for c in r.new_node_claims for _ in c.pods)
+    assert sorted(skew.values()) == [2, 2]
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_hostname_spread_one_pod_per_node(which):  # topology_test.go:544-557: hostname spread maxSkew 1 -> (1, 1, 1, 1)
+    r = run(which, pods(4, labels=LABELS, topology_spread_constraints=spread(key=HOSTNAME_LABEL)), topo_nodepool())
+    assert sorted(len(c.pods) for c in r.new_node_claims) == [1, 1, 1, 1]
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_hostname_anti_affinity_separates_pods(which):  # topology_test.go:2240-2260 (anti-affinity on hostname)
+    anti = [PodAffinityTerm(LabelSelector.of(LABELS), HOSTNAME_LABEL)]
+    r = run(which, pods(3, labels=LABELS, pod_anti_affinity=anti), topo_nodepool())
+    assert sorted(len(c.pods) for c in r.new_node_claims) == [1, 1, 1] and not r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_capacity_type_spread(which):  # topology_test.go:652-666: spread over capacity types -> (2, 2)
+    r = run(which, pods(4, labels=LABELS, topology_spread_constraints=spread(key=CAPACITY_TYPE_LABEL)), topo_nodepool())
+    skew = Counter()
+    for c in r.new_node_claims:
+        ct = c.requirements[CAPACITY_TYPE_LABEL]
+        assert len(ct["values"]) == 1
+        skew[ct["values"][0]] += len(c.pods)
+    assert sorted(skew.values()) == [2, 2]
+
+
+# ---- Custom constraints / well-known labels / operators (suite_test.go:152-420) -----------------------------------
+def req(key, op, *values):
+    return NodeSelectorRequirement(key, op, tuple(values))
+
+
+def scheduled_label(r, key):
+    assert len(r.new_node_claims) == 1 and not r.pod_errors
+    v = r.new_node_claims[0].requirements[key]
+    assert not v["complement"] and len(v["values"]) == 1
+    return v["values"][0]
+
+
+def int_label_of_cheapest(claim):
+    """the integer label of the instance type the fake provider would launch"""
+    its = {it.name: it for it in fake.default_instance_types()}
+    r = [x for x in its[cheapest(claim)].requirements if x.key == fake.INTEGER_INSTANCE_LABEL][0]
+    return r.values[0]
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_nodepool_labels_unconstrained_pod(which):  # suite_test.go:154-161
+    r = run(which, pods(1), nodepool(labels={"test-key": "test-value"}))
+    assert scheduled_label(r, "test-key") == "test-value"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_conflicting_node_selector(which):  # suite_test.go:162-170
+    p = pods(1, node_selector={"test-key": "different-value"})
+    r = run(which, p, nodepool(labels={"test-key": "test-value"}))
+    assert not r.new_node_claims and id(p[0]) in r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_node_selector_with_undefined_key(which):  # suite_test.go:171-178
+    p = pods(1, node_selector={"test-key": "test-value"})
+    r = run(which, p)
+    assert not r.new_node_claims and id(p[0]) in r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_matching_requirements(which):  # suite_test.go:179-190
+    r = run(which, pods(1, node_affinity_required=[[req("test-key", "In", "test-value", "another-value")]]),
+            nodepool(labels={"test-key": "test-value"}))
+    assert scheduled_label(r, "test-key") == "test-value"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_conflicting_requirements(which):  # suite_test.go:191-201
+    p = pods(1, node_affinity_required=[[req("test-key", "In", "another-value")]])
+    r = run(which, p, nodepool(labels={"test-key": "test-value"}))
+    assert not r.new_node_claims and id(p[0]) in r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_nodepool_zone_constraint(which):  # suite_test.go:204-212
+    r = run(which, pods(1), nodepool(requirements=[req(ZONE_LABEL, "In", "test-zone-2")]))
+    assert scheduled_label(r, ZONE_LABEL) == "test-zone-2"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_node_selector_zone(which):  # suite_test.go:213-223
+    r = run(which, pods(1, node_selector={ZONE_LABEL: "test-zone-2"}),
+            nodepool(requirements=[req(ZONE_LABEL, "In", "test-zone-1", "test-zone-2")]))
+    assert scheduled_label(r, ZONE_LABEL) == "test-zone-2"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+@pytest.mark.parametrize("zone", ["unknown", "test-zone-2"])
+def test_node_selector_outside_nodepool(which, zone):  # suite_test.go:232-251
+    p = pods(1, node_selector={ZONE_LABEL: zone})
+    r = run(which, p, nodepool(requirements=[req(ZONE_LABEL, "In", "test-zone-1")]))
+    assert not r.new_node_claims and id(p[0]) in r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_requirement_operator_in(which):  # suite_test.go:252-262
+    r = run(which, pods(1, node_affinity_required=[[req(ZONE_LABEL, "In", "test-zone-3")]]))
+    assert scheduled_label(r, ZONE_LABEL) == "test-zone-3"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+@pytest.mark.parametrize("op,operand,expect", [("Gt", "8", "16"), ("Lt", "8", "2"), ("Gte", "16", "16"), ("Lte", "2", "2")])
+def test_requirement_integer_operators(which, op, operand, expect):  # suite_test.go:263-298
+    r = run(which, pods(1), nodepool(requirements=[req(fake.INTEGER_INSTANCE_LABEL, op, operand)]))
+    assert len(r.new_node_claims) == 1 and not r.pod_errors
+    assert int_label_of_cheapest(r.new_node_claims[0]) == expect
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_requirement_operator_not_in(which):  # suite_test.go:309-319
+    r = run(which, pods(1, node_affinity_required=[[req(ZONE_LABEL, "NotIn", "test-zone-1", "test-zone-2", "unknown")]]))
+    assert len(r.new_node_claims) == 1 and not r.pod_errors
+    z = r.new_node_claims[0].requirements[ZONE_LABEL]  # the NodeClaim keeps NotIn [...]; only test-zone-3 offerings remain
+    assert z["complement"] and {"test-zone-1", "test-zone-2"} <= set(z["values"]) and "test-zone-3" not in z["values"]
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_incompatible_requirements_in(which):  # suite_test.go:299-308
+    p = pods(1, node_affinity_required=[[req(ZONE_LABEL, "In", "unknown")]])
+    r = run(which, p)
+    assert not r.new_node_claims and id(p[0]) in r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_compatible_pods_share_a_node_incompatible_do_not(which):  # suite_test.go:625-664
+    a = pods(1, node_affinity_required=[[req(ZONE_LABEL, "In", "test-zone-1", "test-zone-2")]])
+    b = pods(1, uid0=2, node_affinity_required=[[req(ZONE_LABEL, "In", "test-zone-2", "test-zone-3")]])
+    r = run(which, a + b)
+    assert len(r.new_node_claims) == 1 and scheduled_label(r, ZONE_LABEL) == "test-zone-2"
+    c = pods(1, uid0=3, node_affinity_required=[[req(ZONE_LABEL, "In", "test-zone-1")]])
+    d = pods(1, uid0=4, node_affinity_required=[[req(ZONE_LABEL, "In", "test-zone-3")]])
+    r = run(which, c + d)
+    assert len(r.new_node_claims) == 2
