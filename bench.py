@@ -220,6 +220,7 @@ def main():
     dev_ms, wall = [], None
     for i in range(args.warmup + args.steps):
         flush.zero_()  # evict the previous step's working set from L2
+        torch.cuda.synchronize()  # the solve runs on the library's own stream: nothing of torch's may overlap it
         if i == args.warmup:
             barrier()
             sampler.start()
@@ -228,6 +229,7 @@ def main():
         if world > 1:  # global topology-domain counters: the one collective of the sharded job
             counters = torch.from_numpy(np.concatenate([res["domain_counts"], [res["n_claims"]]]).astype(np.int32)).cuda()
             dist.all_reduce(counters)
+            torch.cuda.synchronize()  # a rank that finishes early must not spin in NCCL underneath its next solve
         if i >= args.warmup:
             dev_ms.append(h.stats()["solve_ms"])
     barrier()
