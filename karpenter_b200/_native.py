@@ -84,9 +84,14 @@ class Handle:
             raise SolverError(rc, lib().kp_last_error(self._h).decode())
 
     def solve(self, problem: _abi.Problem, deadline_ms: int = 0) -> dict:
+        """kp_solve.  On KP_DEADLINE the partial result is returned with out["deadline"] = True (the reference returns
+        partial Results plus ctx.Err(), scheduler.go:411-414)."""
         r = _abi.kp_result()
-        self._check(lib().kp_solve(self._h, problem.ref(), deadline_ms, C.byref(r)))
+        rc = lib().kp_solve(self._h, problem.ref(), deadline_ms, C.byref(r))
+        if rc != 1:
+            self._check(rc)
         out = _abi.result_to_dict(r, problem.n_resources)
+        out["deadline"] = rc == 1
         lib().kp_result_free(C.byref(r))
         return out
 

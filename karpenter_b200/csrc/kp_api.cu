@@ -746,12 +746,16 @@ static int download(kp_handle* h, kp_result* out) {
 }
 
 int kp_solve_resident(kp_handle* h, int64_t deadline_ms, kp_result* out) {
-  (void)deadline_ms;
+  h->dev.deadline_ns = deadline_ms > 0 ? deadline_ms * 1000000ll : 0;
   if (!h->resident) return h->err = "kp_upload has not been called", KP_ERR_INVALID;
   int rc = run_solve(h);
   if (rc != KP_OK) return rc;
   int32_t status = 0;
   CK(cudaMemcpy(&status, h->dev.status, 4, cudaMemcpyDeviceToHost));
+  if (status == KP_DEADLINE) {  // partial results are valid (scheduler.go:411-414)
+    rc = download(h, out);
+    return rc == KP_OK ? KP_DEADLINE : rc;
+  }
   if (status != KP_OK) return h->err = "claim capacity exceeded", status;
   return download(h, out);
 }

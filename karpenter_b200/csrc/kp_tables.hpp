@@ -188,4 +188,5 @@ struct KpDev {
   int64_t* counters;              // [8] existing evals, inflight evals, template evals, commits, slow sorts, ...
   int32_t* status;                // [1] 0 ok, 4 capacity
   int stable_order;
+  long long deadline_ns;          // 0 = none; the solve stops with KP_DEADLINE once this much device time has passed
 };

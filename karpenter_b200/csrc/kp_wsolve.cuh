@@ -300,10 +300,21 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
   // lr0 / lr1 (lane v): the same for request vector v (resp. v+32): every claim below can never fit it again
   int lr0 = 0, lr1 = 0;
   long long watchdog = 0;
+  unsigned long long t_start = 0;
+  if (d.deadline_ns > 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   for (;;) {
     // ---- Queue.Pop (queue.go:46-60)
     const int len = tail - head;
     if (len == 0) break;
+    if (d.deadline_ns > 0 && (watchdog & 63) == 0) {  // context deadline (scheduler.go:411-414): partial results stay valid
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      now = __shfl_sync(FULL, now, 0);
+      if ((long long)(now - t_start) > d.deadline_ns) {
+        status = KP_DEADLINE;
+        break;
+      }
+    }
     if (++watchdog > watchdog_limit) {  // cannot happen: every requeue cycle needs progress (queue.go:54-58)
       status = KP_ERR_INVALID;
       break;

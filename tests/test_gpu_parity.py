@@ -144,3 +144,15 @@ def test_c3_100k_parity(handle):
     claim = -2 - tgt
     app = np.arange(len(tgt)) // 1000
     assert len(set(zip(app.tolist(), claim.tolist()))) == len(tgt)
+
+
+def test_deadline_returns_partial_results(handle):
+    """KP_DEADLINE: the solve stops early, what was placed so far is exactly what the full solve places."""
+    enc = workloads.config_c2(n_pods=60000, n_its=500)
+    full = handle.solve(enc.problem)
+    assert not full["deadline"]
+    part = handle.solve(enc.problem, deadline_ms=20)
+    assert part["deadline"]
+    placed = part["pod_target"] != -1
+    assert 0 < placed.sum() < (full["pod_target"] != -1).sum()
+    assert np.array_equal(part["pod_target"][placed], full["pod_target"][placed])
