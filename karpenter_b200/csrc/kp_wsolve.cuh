@@ -205,6 +205,74 @@ __device__ __forceinline__ void claim_rows_flush(const KpDev& d, WInst& I, int n
   __syncwarp();
 }
 
+// ---- in-flight scan: the next position >= `from` in the claim order whose claim can still pass the cheap tests
+struct ScanCtx {
+  unsigned long long fbit, rbit, tok;  // failure bits to test, tolerated templates
+  bool all_tmpl;
+  int hoff, hend;                      // hostname-group checks of the class
+  int first_clear, first_rclear;       // first position (>= the scan start) whose signature / request-vector bit is clear
+};
+// U sub-chunks of 32 positions per step: their loads are independent, so a step costs one memory latency, not U.
+template <int U>
+__device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, const int32_t* ord, int nC, int from,
+                                              ScanCtx& sc, int lane, int E, int* cc_out) {
+  const ulonglong2* cm = I.cmask;
+  for (int base = from & ~31; base < nC; base += 32 * U) {
+    bool pass[U], fclear[U], rclear[U];
+    int c[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int pos = base + u * 32 + lane;
+      c[u] = -1;
+      pass[u] = fclear[u] = rclear[u] = false;
+      if (pos < nC && pos >= from) {
+        c[u] = ord[pos];
+        const ulonglong2 mk = cm[c[u]];
+        fclear[u] = !(mk.x & sc.fbit);
+        rclear[u] = !(mk.y & sc.rbit);
+        pass[u] = fclear[u] && rclear[u];
+        if (pass[u] && !sc.all_tmpl) pass[u] = (sc.tok >> I.c_tmpl[c[u]]) & 1ull;
+      }
+    }
+    // hostname groups: a NodeClaim is exactly one hostname domain (topologygroup.go:235-247,317-333,402-408)
+    for (int i = sc.hoff; i < sc.hend; i++) {
+      const int4 hc = d.cls_hchk[i];
+      const int type = hc.y & 0xff, self = hc.y >> 8;
+      int hcnt[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) hcnt[u] = pass[u] ? d.host_cnt[(size_t)hc.x * d.H + E + c[u]] : 0;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (!pass[u]) continue;
+        if (type == KP_TOPO_SPREAD)
+          pass[u] = hcnt[u] + self <= hc.z;
+        else if (type == KP_TOPO_AFFINITY)
+          pass[u] = hcnt[u] > 0 || (self && (d.g_ndomains[hc.w] - d.g_nempty[hc.w]) == 0);
+        else
+          pass[u] = hcnt[u] == 0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (sc.fbit && sc.first_clear < 0) {
+        const unsigned fm = __ballot_sync(FULL, fclear[u]);
+        if (fm) sc.first_clear = base + u * 32 + __ffs(fm) - 1;
+      }
+      if (sc.rbit && sc.first_rclear < 0) {
+        const unsigned rm = __ballot_sync(FULL, rclear[u]);
+        if (rm) sc.first_rclear = base + u * 32 + __ffs(rm) - 1;
+      }
+      const unsigned m = __ballot_sync(FULL, pass[u]);
+      if (m) {
+        const int l = __ffs(m) - 1;
+        *cc_out = __shfl_sync(FULL, c[u], l);
+        return base + u * 32 + l;
+      }
+    }
+  }
+  return -1;
+}
+
 // shared -> global migration of the small per-claim arrays (see WInst::CS); executed once, by the whole warp
 __device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, int lane) {
   for (int i = lane; i < nC; i += 32) {
@@ -584,56 +652,30 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
 
     // ================= addToInflightNode (scheduler.go:557-589) =================
     {
-      // loop invariants of the scan, in registers: the failure bits to test, the tolerated templates, hostname checks
-      const unsigned long long tok = px.tmpl_ok;
-      const bool all_tmpl = (tok & d.tmpl_all) == d.tmpl_all;
-      const int hoff = px.hoff, hend = px.hend;
-      const ulonglong2* cm = I.cmask;
-      const int32_t* ctm = I.c_tmpl;
+      ScanCtx sc;
+      sc.fbit = fbit;
+      sc.rbit = rbit;
+      sc.tok = px.tmpl_ok;
+      sc.all_tmpl = (sc.tok & d.tmpl_all) == d.tmpl_all;
+      sc.hoff = px.hoff;
+      sc.hend = px.hend;
+      sc.first_clear = -1;
+      sc.first_rclear = -1;
       const bool fast_ok = fbit != 0 && px.roff == px.rend;  // topology-free and counted by no topology group
-      int lbf = 0, lbr = 0, first_clear = -1, first_rclear = -1;
+      int lbf = 0, lbr = 0;
       if (fbit) lbf = __shfl_sync(FULL, fsig < 32 ? lb0 : lb1, fsig & 31);
       if (rbit) lbr = __shfl_sync(FULL, rv < 32 ? lr0 : lr1, rv & 31);
       const int lb = lbf > lbr ? lbf : lbr;  // below either bound a claim fails for one of the two reasons
-      for (int base = lb & ~31; base < nC && !found && (tok & d.tmpl_all); base += 32) {
-        const int pos = base + lane;
-        scan_chunks++;
-        bool pass = false, fclear = false, rclear = false;
-        int c = -1;
-        if (pos < nC && pos >= lb) {
-          c = ord[pos];
-          const ulonglong2 mk = cm[c];
-          fclear = !(mk.x & fbit);
-          rclear = !(mk.y & rbit);
-          pass = fclear && rclear;
-          if (pass && !all_tmpl) pass = (tok >> ctm[c]) & 1ull;
-          // hostname groups: a NodeClaim is exactly one hostname domain (topologygroup.go:235-247,317-333,402-408)
-          for (int i = hoff; pass && i < hend; i++) {
-            const int4 hc = d.cls_hchk[i];
-            const int hcnt = d.host_cnt[(size_t)hc.x * d.H + E + c];
-            const int type = hc.y & 0xff, self = hc.y >> 8;
-            if (type == KP_TOPO_SPREAD)
-              pass = hcnt + self <= hc.z;
-            else if (type == KP_TOPO_AFFINITY)
-              pass = hcnt > 0 || (self && (d.g_ndomains[hc.w] - d.g_nempty[hc.w]) == 0);
-            else
-              pass = hcnt == 0;
-          }
-        }
-        unsigned m = __ballot_sync(FULL, pass);
-        if (fbit && first_clear < 0) {
-          const unsigned fm = __ballot_sync(FULL, fclear);
-          if (fm) first_clear = base + __ffs(fm) - 1;
-        }
-        if (rbit && first_rclear < 0) {
-          const unsigned rm = __ballot_sync(FULL, rclear);
-          if (rm) first_rclear = base + __ffs(rm) - 1;
-        }
-        while (m && !found) {
-          const int l = __ffs(m) - 1;
-          m &= m - 1;
-          const int cpos = base + l;
-          const int cc = __shfl_sync(FULL, c, l);
+      const bool scanned = (sc.tok & d.tmpl_all) != 0;
+      int from = lb;
+      while (scanned && !found) {
+        int cc;
+        // classes with hostname checks read one counter per candidate from HBM/L2: scan 128 positions per step there
+        const int cpos = sc.hend > sc.hoff ? next_candidate<4>(d, I, ord, nC, from, sc, lane, E, &cc)
+                                           : next_candidate<1>(d, I, ord, nC, from, sc, lane, E, &cc);
+        if (cpos < 0) break;
+        from = cpos + 1;
+        {
           if (fast_ok && (I.amask[cc] & fbit)) {
             // ---- the pod's requirements are already implied by the claim's: CanAdd == "do the merged requests still
             // fit a remaining instance type", and the stored list only changes when a threshold row advances
@@ -722,8 +764,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         }
       }
       // a bound may only advance when the scan really started at it (positions below `lb` were not looked at)
-      if (fbit && (tok & d.tmpl_all) && lbf == lb) {  // all positions below the first clear bit rejected the signature
-        const int nb = first_clear >= 0 ? first_clear : nC;
+      if (fbit && scanned && lbf == lb) {  // all positions below the first clear bit rejected the signature
+        const int nb = sc.first_clear >= 0 ? sc.first_clear : nC;
         if (lane == (fsig & 31)) {
           if (fsig < 32)
             lb0 = nb;
@@ -731,8 +773,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             lb1 = nb;
         }
       }
-      if (rbit && (tok & d.tmpl_all) && lbr == lb) {
-        const int nb = first_rclear >= 0 ? first_rclear : nC;
+      if (rbit && scanned && lbr == lb) {
+        const int nb = sc.first_rclear >= 0 ? sc.first_rclear : nC;
         if (lane == (rv & 31)) {
           if (rv < 32)
             lr0 = nb;
