@@ -713,7 +713,6 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             }
             claim_store_rq(d, I, cc, lane, q, lo, any_adv, its);
             if (lane == 0) {
-              I.c_npods[cc]++;
               cnt[cpos]++;
               if (I.pod_target) {
                 I.pod_target[li] = KP_TARGET_CLAIM(cc);
@@ -748,7 +747,6 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           // NodeClaim.Add (nodeclaim.go:207-219)
           claim_store(d, I, cc, lane, ev, ev.changed);
           if (lane == 0) {
-            I.c_npods[cc]++;
             cnt[cpos]++;
             if (I.pod_target) {
               I.pod_target[li] = KP_TARGET_CLAIM(cc);
@@ -833,7 +831,6 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       claim_store(d, I, cnew, lane, ev, true);
       if (lane == 0) {
         I.c_tmpl[cnew] = n;
-        I.c_npods[cnew] = 1;
         ord[cnew] = cnew;
         cnt[cnew] = 1;
         if (I.pod_target) {
@@ -906,6 +903,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
     __syncwarp();
     if (lane == 0) ring->done = 1;
   }
+  // len(Pods) of every claim is the count stored next to it in the claim order
+  for (int i = lane; i < nC; i += 32) I.c_npods[ord[i]] = cnt[i];
   // pods still queued when the loop ends are the PodErrors (scheduler.go:415-423)
   n_unsched = tail - head;
   if (lane == 0) {
