@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 N_PODS = 100_000
 N_ITS = 500
-CPU_SAMPLE_PODS = 25_000
+CPU_SAMPLE_PODS = 100_000  # the whole workload: ~17 s of CPU work, inside the 10-30 s the contract asks for
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_wsolve launch on this workload (ncu --set full capture,
 # profiles/r1_v5_k_metrics.csv); static: a number measured under a profiler is evidence, not a bench value
 NCU_TRAFFIC_BYTES = 1_721_344 + 3_584
@@ -94,7 +94,7 @@ def run_reference(args, rank, world):
     # workload when the requested K + W solves fit in a few minutes (17.5 s each on this class of host), else on the
     # largest prefix that does, and say which
     total = args.steps + args.warmup
-    sample_pods = N_PODS if total <= 8 else (50_000 if total <= 30 else CPU_SAMPLE_PODS)
+    sample_pods = N_PODS if total <= 8 else (50_000 if total <= 30 else 25_000)
     enc = build_problem(0, sample_pods, N_ITS)
     times = []
     res = None
@@ -293,8 +293,8 @@ def main():
             oracle_lib.solve(sample.problem)
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": CPU_SAMPLE_PODS / dt, "unit": "pods/s", "cores": 1, "kind": "port",
-                                    "sample": f"first {CPU_SAMPLE_PODS} pods of the workload, one full Solve, single "
-                                              f"thread of {os.cpu_count()} host cores"}
+                                    "sample": f"the full workload ({CPU_SAMPLE_PODS} pods), one Solve, single thread of "
+                                              f"{os.cpu_count()} host cores (the reference's default parallelizeUntil width is 1)"}
     # ---- second headline metric: consolidation candidates/sec (C4), subsets sharded round-robin across ranks
     consol = None
     if not args.no_consolidation:
