@@ -211,38 +211,7 @@ struct ScanCtx {
   bool all_tmpl;
   int hoff, hend;                      // hostname-group checks of the class
   int first_clear, first_rclear;       // first position (>= the scan start) whose signature / request-vector bit is clear
-  // topology-spread prefilter: for up to two of the class's spread groups on a label key, the domains that satisfy the
-  // skew right now (registered, count + self - min <= maxSkew).  A claim whose requirement on that key allows none of
-  // them cannot pass Topology.AddRequirements (topologygroup.go:226-287) -- a necessary condition, the exact test
-  // still runs on every candidate.
-  int nz;
-  int zkey[2];
-  unsigned long long zmask[2];
 };
-
-// domains of spread group g that a pod of the staged class may take right now (see ScanCtx::zmask)
-__device__ __forceinline__ unsigned long long spread_eligible(const KpDev& d, const KpGroup& G, int g, bool self,
-                                                              const Slot& pod_d) {
-  KeyInfo ki = key_info(d, G.key);
-  const int32_t* cnt = d.dom_cnt + G.dom_off;
-  const unsigned long long reg = d.dom_reg[g];
-  const unsigned long long sup = reg & slot_allowed(ki, pod_d);
-  long long mn = 2147483647LL;
-  const int nsup = __popcll(sup);
-  for (unsigned long long s = sup; s;) {
-    const int v = __ffsll((long long)s) - 1;
-    s &= s - 1;
-    if (cnt[v] < mn) mn = cnt[v];
-  }
-  if (G.min_domains >= 0 && nsup < G.min_domains) mn = 0;
-  unsigned long long out = 0;
-  for (unsigned long long s = reg; s;) {
-    const int v = __ffsll((long long)s) - 1;
-    s &= s - 1;
-    if ((long long)cnt[v] + (self ? 1 : 0) - mn <= (long long)G.max_skew) out |= 1ull << v;
-  }
-  return out;
-}
 // U sub-chunks of 32 positions per step: their loads are independent, so a step costs one memory latency, not U.
 template <int U>
 __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, const int32_t* ord, int nC, int from,
@@ -263,26 +232,6 @@ __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, co
         rclear[u] = !(mk.y & sc.rbit);
         pass[u] = fclear[u] && rclear[u];
         if (pass[u] && !sc.all_tmpl) pass[u] = (sc.tok >> I.c_tmpl[c[u]]) & 1ull;
-      }
-    }
-    for (int z = 0; z < sc.nz; z++) {
-      const int k = sc.zkey[z];
-      const unsigned long long univ = d.key_univ[k];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (!pass[u]) continue;
-        const int cc = c[u];
-        unsigned f;
-        unsigned long long m;
-        if (cc < I.CR) {
-          f = I.s_sflags[cc * d.K + k];
-          m = I.s_smask[cc * d.K + k];
-        } else {
-          f = I.c_sflags[(size_t)cc * d.K + k];
-          m = I.c_smask[(size_t)cc * d.K + k];
-        }
-        const unsigned long long allowed = !(f & SF_PRESENT) ? univ : (((f & SF_COMPLEMENT) ? ~m : m) & univ);
-        pass[u] = (allowed & sc.zmask[z]) != 0;
       }
     }
     // hostname groups: a NodeClaim is exactly one hostname domain (topologygroup.go:235-247,317-333,402-408)
@@ -712,16 +661,6 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       sc.hend = px.hend;
       sc.first_clear = -1;
       sc.first_rclear = -1;
-      sc.nz = 0;
-      if (!d.has_bounds)
-        for (int i = px.moff; i < px.mend && sc.nz < 2; i++) {
-          const int e = d.cls_match[i], g = e & 0x3fffffff;
-          const KpGroup G = d.groups[g];
-          if (G.type != KP_TOPO_SPREAD || G.key == d.hostname_key) continue;
-          sc.zkey[sc.nz] = G.key;
-          sc.zmask[sc.nz] = spread_eligible(d, G, g, (e >> 30) & 1, px.strict_slot[G.key]);
-          sc.nz++;
-        }
       const bool fast_ok = fbit != 0 && px.roff == px.rend;  // topology-free and counted by no topology group
       int lbf = 0, lbr = 0;
       if (fbit) lbf = __shfl_sync(FULL, fsig < 32 ? lb0 : lb1, fsig & 31);
