@@ -13,7 +13,10 @@
 // (tests/golden/requirement_kats.json, extracted from pkg/scheduling/requirement_test.go and requirements_test.go);
 // solver-level behaviour is pinned by the reference's aggregate assertions restated in tests/test_oracle_*.py.
 // Go's sort.Slice tie order (orc_gosort.hpp) and Go map iteration order are UNPINNED by construction.
+#include <atomic>
 #include <chrono>
+#include <functional>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -46,6 +49,44 @@ struct Counters {
   int64_t existing = 0, inflight = 0, tmpl = 0, commits = 0;
 };
 
+// parallelizeUntil (scheduler.go:757-779): W workers pull candidate indices from a shared counter; the lowest index
+// that succeeds wins and every index below it has been evaluated.  Persistent spinning workers, one job at a time.
+struct WorkerPool {
+  int W;
+  std::vector<std::thread> threads;
+  std::atomic<uint64_t> epoch{0};
+  std::atomic<int> finished{0};
+  std::atomic<bool> quit{false};
+  std::function<void(int)> job;
+  explicit WorkerPool(int w) : W(w) {
+    for (int i = 1; i < W; i++)
+      threads.emplace_back([this, i] {
+        uint64_t seen = 0;
+        for (;;) {
+          uint64_t e;
+          while ((e = epoch.load(std::memory_order_acquire)) == seen && !quit.load(std::memory_order_relaxed)) {
+          }
+          if (quit.load(std::memory_order_relaxed)) return;
+          seen = e;
+          job(i);
+          finished.fetch_add(1, std::memory_order_release);
+        }
+      });
+  }
+  ~WorkerPool() {
+    quit.store(true);
+    for (auto& t : threads) t.join();
+  }
+  void run(const std::function<void(int)>& f) {
+    job = f;
+    finished.store(0, std::memory_order_relaxed);
+    epoch.fetch_add(1, std::memory_order_release);
+    f(0);
+    while (finished.load(std::memory_order_acquire) != W - 1) {
+    }
+  }
+};
+
 struct Scheduler {
   const Prob& P;
   const kp_problem* p;
@@ -59,6 +100,7 @@ struct Scheduler {
   int64_t hostname_seq = 0;
   Counters ctr;
   bool stable_order;
+  WorkerPool* pool = nullptr;  // null: evaluate candidates serially
 
   Scheduler(const Prob& prob) : P(prob), p(prob.p), topo(prob), stable_order(prob.p->claim_order_mode == 1) {}
 
@@ -195,8 +237,53 @@ struct Scheduler {
     }
   }
 
+  // scheduler.go:557-589 with parallelizeUntil: same result as the serial scan (lowest succeeding index)
+  bool add_to_inflight_parallel(int64_t pod, int cls, int* target) {
+    const int n = (int)new_claims.size();
+    std::atomic<int> next{0}, best{INT32_MAX};
+    struct Slot_ {
+      int idx = INT32_MAX;
+      Requirements r;
+      std::vector<int> its;
+    };
+    std::vector<Slot_> slots(pool->W);
+    pool->run([&](int w) {
+      for (;;) {
+        int i = next.fetch_add(1, std::memory_order_relaxed);
+        if (i >= n || i > best.load(std::memory_order_relaxed)) return;
+        Requirements r;
+        std::vector<int> its;
+        if (claim_can_add(*new_claims[i], cls, &r, &its)) {
+          if (i < slots[w].idx) {
+            slots[w].idx = i;
+            slots[w].r = std::move(r);
+            slots[w].its = std::move(its);
+          }
+          int cur = best.load();
+          while (i < cur && !best.compare_exchange_weak(cur, i)) {
+          }
+          return;
+        }
+      }
+    });
+    int b = best.load();
+    if (b == INT32_MAX) {
+      ctr.inflight += n;
+      return false;
+    }
+    ctr.inflight += b + 1;
+    for (auto& sl : slots)
+      if (sl.idx == b) {
+        claim_add(*new_claims[b], pod, cls, sl.r, sl.its);
+        *target = KP_TARGET_CLAIM(new_claims[b]->created);
+        return true;
+      }
+    return false;
+  }
+
   // scheduler.go:557-589
   bool add_to_inflight(int64_t pod, int cls, int* target) {
+    if (pool && new_claims.size() >= 32) return add_to_inflight_parallel(pod, cls, target);
     for (size_t i = 0; i < new_claims.size(); i++) {
       Requirements r;
       std::vector<int> its;
@@ -492,11 +579,20 @@ extern "C" {
 
 int orc_version(void) { return KP_ABI_VERSION; }
 
-int orc_solve(const kp_problem* p, kp_result* out) {
+int orc_solve_mt(const kp_problem* p, kp_result* out, int threads);
+int orc_solve(const kp_problem* p, kp_result* out) { return orc_solve_mt(p, out, 1); }
+
+// threads > 1: in-flight candidates are evaluated by a worker pool like the reference's parallelizeUntil
+int orc_solve_mt(const kp_problem* p, kp_result* out, int threads) {
   if (has_min_values(p)) return KP_ERR_UNSUPPORTED;
   if (p->n_resources > KP_MAX_RESOURCES) return KP_ERR_CAPACITY;
   Prob P(p);
   Scheduler s(P);
+  std::unique_ptr<WorkerPool> pool;
+  if (threads > 1) {
+    pool.reset(new WorkerPool(threads));
+    s.pool = pool.get();
+  }
   std::vector<uint8_t> active(p->n_nodes, 0);
   for (int i = 0; i < p->n_nodes; i++) active[i] = (p->node_flags[i] & KP_NODE_SCHEDULABLE) != 0;
   std::vector<std::pair<int, int>> bound;

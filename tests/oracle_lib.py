@@ -24,14 +24,16 @@ def lib():
             build()
         _LIB = C.CDLL(path)
         _LIB.orc_solve.argtypes = [C.c_void_p, C.c_void_p]
+        _LIB.orc_solve_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _LIB.orc_consolidate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _LIB.orc_feasibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     return _LIB
 
 
-def solve(problem) -> dict:
+def solve(problem, threads: int = 1) -> dict:
+    """threads > 1: candidates are evaluated by a worker pool like the reference's parallelizeUntil (same result)."""
     r = _abi.kp_result()
-    rc = lib().orc_solve(problem.ref(), C.byref(r))
+    rc = lib().orc_solve_mt(problem.ref(), C.byref(r), int(threads))
     if rc != 0:
         raise RuntimeError(f"orc_solve failed: {rc}")
     out = _abi.result_to_dict(r, problem.n_resources)
