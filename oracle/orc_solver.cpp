@@ -656,7 +656,12 @@ int orc_feasibility(const kp_problem* p, uint64_t* out_bits, int32_t* out_it_wor
 }
 
 // disruption/helpers.go:51-142 + consolidation.go:136-229, one call per subset
+int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol_result* out, int threads);
 int orc_consolidate(const kp_problem* p, const kp_consol_input* in, kp_consol_result* out) {
+  return orc_consolidate_mt(p, in, out, 1);
+}
+// subsets are independent simulations: `threads` workers take them round-robin
+int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol_result* out, int threads) {
   if (has_min_values(p)) return KP_ERR_UNSUPPORTED;
   Prob P(p);
   Pricing pr(P);
@@ -671,7 +676,7 @@ int orc_consolidate(const kp_problem* p, const kp_consol_input* in, kp_consol_re
   out->n_unscheduled = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
   const int ct_order[3] = {in->ct_reserved, in->ct_spot, in->ct_on_demand};
   auto t0 = std::chrono::steady_clock::now();
-  for (int s_i = 0; s_i < S; s_i++) {
+  auto one_subset = [&](int s_i) {
     std::vector<uint8_t> active(p->n_nodes, 0), is_cand(p->n_nodes, 0);
     for (int i = in->subset_off[s_i]; i < in->subset_off[s_i + 1]; i++) is_cand[in->subset_nodes[i]] = 1;
     for (int i = 0; i < p->n_nodes; i++) active[i] = (p->node_flags[i] & KP_NODE_SCHEDULABLE) && !is_cand[i];
@@ -773,6 +778,16 @@ int orc_consolidate(const kp_problem* p, const kp_consol_input* in, kp_consol_re
       for (int it : kept) rep[it >> 6] |= 1ull << (it & 63);
     } while (0);
     out->decision[s_i] = decision;
+  };
+  if (threads <= 1) {
+    for (int s_i = 0; s_i < S; s_i++) one_subset(s_i);
+  } else {
+    std::vector<std::thread> pool;
+    for (int w = 0; w < threads; w++)
+      pool.emplace_back([&, w] {
+        for (int s_i = w; s_i < S; s_i += threads) one_subset(s_i);
+      });
+    for (auto& t : pool) t.join();
   }
   auto t1 = std::chrono::steady_clock::now();
   out->solve_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();

@@ -26,6 +26,7 @@ def lib():
         _LIB.orc_solve.argtypes = [C.c_void_p, C.c_void_p]
         _LIB.orc_solve_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _LIB.orc_consolidate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _LIB.orc_consolidate_mt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _LIB.orc_feasibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     return _LIB
 
@@ -41,9 +42,9 @@ def solve(problem, threads: int = 1) -> dict:
     return out
 
 
-def consolidate(problem, consol) -> dict:
+def consolidate(problem, consol, threads: int = 1) -> dict:
     r = _abi.kp_consol_result()
-    rc = lib().orc_consolidate(problem.ref(), consol.ref(), C.byref(r))
+    rc = lib().orc_consolidate_mt(problem.ref(), consol.ref(), C.byref(r), int(threads))
     if rc != 0:
         raise RuntimeError(f"orc_consolidate failed: {rc}")
     out = _abi.consol_result_to_dict(r)
