@@ -41,7 +41,9 @@ def algorithmic_bytes(res, n_pods, n_its, n_groups=0, domains=4):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """SM clock and throttle reasons while the timed region runs (B200_PROFILING.md).  Sampled through NVML in-process:
+    spawning `nvidia-smi` five times a second stalls a one-warp kernel for hundreds of milliseconds at a time (measured:
+    individual steps went from 189 ms to 0.5 - 1.4 s), an NVML query does not.  Falls back to nvidia-smi at 1 Hz."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -50,28 +52,58 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.stop_flag = False
         self.max_mhz = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        for name, bit in (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown),
+                          ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown),
+                          ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)):
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                              str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        self.samples.append(float(f[0]))
+        self.max_mhz = float(f[1])
+        for n, v in zip(names, f[2:]):
+            if v.lower().startswith("active"):
+                self.reasons.add(n)
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                f = [x.strip() for x in out.split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(float(os.environ.get("KP_SAMPLE_S", "0.2")) if self.nvml is not None else 1.0)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons)}
+                "sm_min_mhz": float(np.min(self.samples)) if self.samples else None,
+                "reasons": sorted(self.reasons), "source": "nvml" if self.nvml is not None else "nvidia-smi",
+                "samples": len(self.samples)}
 
 
 def build_problem(rank, n_pods, n_its):
@@ -245,7 +277,8 @@ def main():
         torch.cuda.synchronize()  # the solve runs on the library's own stream: nothing of torch's may overlap it
         if i == args.warmup:
             barrier()
-            sampler.start()
+            if not os.environ.get("KP_NO_SAMPLER"):
+                sampler.start()
             wall = time.perf_counter()
         res = h.solve_resident()
         if world > 1:  # global topology-domain counters: the one collective of the sharded job
@@ -259,6 +292,7 @@ def main():
     sampler.stop_flag = True
     launches = h.stats()["kernel_launches"] * args.steps
     ms = float(np.mean(dev_ms))
+    ms_all = [round(float(x), 3) for x in dev_ms]
     # ---- end to end through kp_solve with host buffers
     e2e_t = []
     for i in range(2 + args.steps):
@@ -305,7 +339,7 @@ def main():
                          "note": "k_wsolve is a latency-bound serial first-fit chain (one warp per Scheduler); see DESIGN.md"},
             "clocks": sampler.summary(),
             "unscheduled": int((res["pod_target"] == -1).sum()), "node_claims": int(res["n_claims"]),
-            "wall_s_timed_region": wall,
+            "wall_s_timed_region": wall, "ms_per_step_all": ms_all,
         }
         if not args.no_cpu_baseline and world == 1:
             from tests import oracle_lib

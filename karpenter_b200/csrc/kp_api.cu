@@ -1,10 +1,6 @@
 // kp_api.cu -- the C ABI of include/karpsolve.h: device memory, transfers, kernel launches, result assembly.
 #include <cuda_runtime.h>
-#include <thrust/device_ptr.h>
-#include <thrust/execution_policy.h>
-#include <thrust/gather.h>
-#include <thrust/sequence.h>
-#include <thrust/sort.h>
+#include <cub/cub.cuh>
 
 #include <chrono>
 #include <cstdio>
@@ -89,7 +85,21 @@ struct kp_handle {
   int64_t* d_rv_req = nullptr;
   int strict_undefined = 0;
   kp_stats stats{};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  float wsolve_ms = 0;
+  // state the solve mutates: pristine device copies, restored device-to-device before every solve (no host memory,
+  // no allocation and no synchronisation sits between the first and the last kernel of a solve)
+  struct Reset {
+    void* dst;
+    const void* src;
+    size_t bytes;
+  };
+  std::vector<Reset> resets;
+  const int32_t* d_host_cnt_nodes = nullptr;
+  // NewQueue radix sort buffers
+  void *sort_keys_a = nullptr, *sort_keys_b = nullptr, *sort_tmp = nullptr;
+  int32_t* sort_perm_b = nullptr;
+  size_t sort_tmp_bytes = 0;
 };
 
 template <class T>
@@ -102,12 +112,18 @@ static cudaError_t up(kp_handle* h, const T** dst, const std::vector<T>& v) {
   *dst = p;
   return e;
 }
+// a table the solve mutates: the upload goes to a pristine copy, the working copy is restored from it per solve
 template <class T>
 static cudaError_t up_mut(kp_handle* h, T** dst, const std::vector<T>& v) {
-  const T* p;
-  cudaError_t e = up(h, &p, v);
-  *dst = const_cast<T*>(p);
-  return e;
+  const T* init;
+  cudaError_t e = up(h, &init, v);
+  if (e != cudaSuccess) return e;
+  T* work;
+  e = h->arena.alloc(&work, v.size());
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) h->resets.push_back({work, init, v.size() * sizeof(T)});
+  *dst = work;
+  return cudaSuccess;
 }
 template <class T>
 static cudaError_t up_raw(kp_handle* h, T** dst, const T* src, size_t n) {
@@ -163,6 +179,7 @@ int kp_create(int device, kp_handle** out) {
   }
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
+  cudaEventCreate(&h->ev2);
   cudaDeviceSetLimit(cudaLimitStackSize, 16384);  // pdqsort emulation recurses (log n deep)
   *out = h;
   return KP_OK;
@@ -425,10 +442,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   d.tmpl_all = t.N >= 64 ? ~0ull : ((1ull << t.N) - 1);
   d.H = t.E + d.Cmax;
   CK(zeros(h, &d.host_cnt, (size_t)std::max(t.GH, 1) * d.H));
-  for (int g = 0; g < t.GH; g++)
-    if (t.E)
-      CK(cudaMemcpyAsync(d.host_cnt + (size_t)g * d.H, t.host_cnt_nodes.data() + (size_t)g * t.E,
-                         (size_t)t.E * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  CK(up(h, &h->d_host_cnt_nodes, t.host_cnt_nodes));
   CK(zeros(h, &d.n_claims, 1));
   CK(zeros(h, &d.counters, 16));
   CK(zeros(h, &d.status, 1));
@@ -439,31 +453,16 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
 static int reset_dynamic(kp_handle* h) {
   HostTables& t = h->host;
   KpDev& d = h->dev;
-  auto cp = [&](void* dst, const void* src, size_t n) {
-    return n ? cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
-  };
-  CK(cp(d.tmpl_remaining, t.tmpl_remaining.data(), t.tmpl_remaining.size() * 8));
-  CK(cp(d.dom_cnt, t.dom_cnt.data(), t.dom_cnt.size() * 4));
-  CK(cp(d.dom_reg, t.dom_reg.data(), t.dom_reg.size() * 8));
-  CK(cp(d.dom_pop, t.dom_pop.data(), t.dom_pop.size() * 8));
-  CK(cp(d.g_ndomains, t.g_ndomains.data(), t.g_ndomains.size() * 4));
-  CK(cp(d.g_nempty, t.g_nempty.data(), t.g_nempty.size() * 4));
-  CK(cp(d.node_rem, t.node_rem.data(), t.node_rem.size() * 8));
-  CK(cp(d.node_rem_present, t.node_rem_present.data(), t.node_rem_present.size() * 4));
-  CK(cp(d.node_sflags, t.node_sflags.data(), t.node_sflags.size()));
-  CK(cp(d.node_smask, t.node_smask.data(), t.node_smask.size() * 8));
-  CK(cp(d.node_sgte, t.node_sgte.data(), t.node_sgte.size() * 8));
-  CK(cp(d.node_slte, t.node_slte.data(), t.node_slte.size() * 8));
+  for (auto& r : h->resets) CK(cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemsetAsync(d.node_npods, 0, (size_t)std::max(t.E, 1) * 4, h->stream));
   size_t C = (size_t)d.Cmax;
   CK(cudaMemsetAsync(d.c_npods, 0, C * 4, h->stream));
   CK(cudaMemsetAsync(d.cmask, 0, C * sizeof(ulonglong2), h->stream));
   CK(cudaMemsetAsync(d.amask, 0, C * 8, h->stream));
   CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)std::max(t.GH, 1) * d.H * 4, h->stream));
-  for (int g = 0; g < t.GH; g++)
-    if (t.E)
-      CK(cudaMemcpyAsync(d.host_cnt + (size_t)g * d.H, t.host_cnt_nodes.data() + (size_t)g * t.E,
-                         (size_t)t.E * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  if (t.E && t.GH)  // initial hostname-group counts of the existing nodes: rows of E ints into rows of H ints
+    CK(cudaMemcpy2DAsync(d.host_cnt, (size_t)d.H * 4, h->d_host_cnt_nodes, (size_t)t.E * 4, (size_t)t.E * 4, t.GH,
+                         cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemsetAsync(d.n_claims, 0, 4, h->stream));
   CK(cudaMemsetAsync(d.counters, 0, 128, h->stream));
   CK(cudaMemsetAsync(d.status, 0, 4, h->stream));
@@ -475,6 +474,7 @@ static int do_upload(kp_handle* h, const kp_problem* p, int cmax) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   h->arena.reset();
+  h->resets.clear();
   h->resident = false;
   h->stats = kp_stats{};
   auto t0 = std::chrono::steady_clock::now();
@@ -523,6 +523,24 @@ static int do_upload(kp_handle* h, const kp_problem* p, int cmax) {
     }
   }
   CK(up_raw(h, &h->d_class_rank, rank.data(), rank.size()));
+  {  // NewQueue sort: key / permutation ping-pong buffers and cub's scratch, sized once per upload
+    int64_t* ka;
+    int64_t* kb;
+    CK(h->arena.alloc(&ka, P));
+    CK(h->arena.alloc(&kb, P));
+    CK(h->arena.alloc(&h->sort_perm_b, P));
+    h->sort_keys_a = ka;
+    h->sort_keys_b = kb;
+    size_t n1 = 0, n2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, n1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)std::max<size_t>(P, 1));
+    cub::DeviceRadixSort::SortPairs(nullptr, n2, (const int64_t*)nullptr, (int64_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)std::max<size_t>(P, 1));
+    h->sort_tmp_bytes = std::max(n1, n2);
+    char* tmp;
+    CK(h->arena.alloc(&tmp, h->sort_tmp_bytes));
+    h->sort_tmp = tmp;
+  }
   CK(zeros(h, &d.queue, P + 1));
   CK(zeros(h, &d.qcls, P + 1));
   CK(zeros(h, &d.last_len, P));
@@ -543,29 +561,32 @@ int kp_upload(kp_handle* h, const kp_problem* p) {
 
 // NewQueue: sort pods cpu desc, mem desc, creation asc, uid asc (queue.go:37-43) into d.queue / d.qcls.
 // Four LSD passes of a stable radix sort (cub), each on a gathered 64-bit key.
+__global__ void k_iota(int32_t* p, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
+}
+
 static int sort_queue(kp_handle* h) {
   KpDev& d = h->dev;
   const int64_t P = h->P;
   if (P <= 0) return KP_OK;
-  auto pol = thrust::cuda::par.on(h->stream);
-  thrust::device_ptr<int32_t> perm(d.queue);
-  thrust::sequence(pol, perm, perm + P);
-  int64_t* keys;
-  CK(cudaMallocAsync(&keys, P * 8, h->stream));
-  thrust::device_ptr<int64_t> k64(keys);
-  thrust::device_ptr<uint64_t> ku64((uint64_t*)keys);
-  int nb = (int)((P + 255) / 256);
-  k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_lo, d.queue, P, (uint64_t*)keys);
-  thrust::stable_sort_by_key(pol, ku64, ku64 + P, perm);
-  k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_hi, d.queue, P, (uint64_t*)keys);
-  thrust::stable_sort_by_key(pol, ku64, ku64 + P, perm);
-  k_gather<<<nb, 256, 0, h->stream>>>(h->d_pod_creation, d.queue, P, keys);
-  thrust::stable_sort_by_key(pol, k64, k64 + P, perm);
-  k_sort_keys<<<nb, 256, 0, h->stream>>>(d.pod_class, h->d_class_rank, d.queue, P, keys);
-  thrust::stable_sort_by_key(pol, k64, k64 + P, perm);
-  CK(cudaFreeAsync(keys, h->stream));
+  const int nb = (int)((P + 255) / 256), n = (int)P;
+  int32_t* perm_a = d.queue;  // passes ping-pong a -> b -> a -> b -> a: the result lands in d.queue
+  int32_t* perm_b = h->sort_perm_b;
+  uint64_t *ua = (uint64_t*)h->sort_keys_a, *ub = (uint64_t*)h->sort_keys_b;
+  int64_t *sa = (int64_t*)h->sort_keys_a, *sb = (int64_t*)h->sort_keys_b;
+  size_t tb = h->sort_tmp_bytes;
+  k_iota<<<nb, 256, 0, h->stream>>>(perm_a, P);
+  k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_lo, perm_a, P, ua);
+  CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, tb, ua, ub, perm_a, perm_b, n, 0, 64, h->stream));
+  k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_hi, perm_b, P, ua);
+  CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, tb, ua, ub, perm_b, perm_a, n, 0, 64, h->stream));
+  k_gather<<<nb, 256, 0, h->stream>>>(h->d_pod_creation, perm_a, P, sa);
+  CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, tb, sa, sb, perm_a, perm_b, n, 0, 64, h->stream));
+  k_sort_keys<<<nb, 256, 0, h->stream>>>(d.pod_class, h->d_class_rank, perm_b, P, sa);
+  CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, tb, sa, sb, perm_b, perm_a, n, 0, 64, h->stream));
   k_gather<<<nb, 256, 0, h->stream>>>(d.pod_class, d.queue, P, d.qcls);
-  h->stats.kernel_launches += 5;
+  h->stats.kernel_launches += 6;
   return KP_OK;
 }
 
@@ -642,6 +663,7 @@ static int run_solve(kp_handle* h) {
   if (const char* lim = getenv("KP_CS_LIMIT")) CS = std::min(CS, std::max(0, atoi(lim)) / 32 * 32);  // test knob
   size_t smem = fixed + tb + (CS ? small_bytes(CS) : 0) + 64;
   CK(cudaFuncSetAttribute(k_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaEventRecord(h->ev2, h->stream));
   k_wsolve<<<1, 64, smem, h->stream>>>(d, CS, CR);
   h->stats.kernel_launches++;
   CK(cudaEventRecord(h->ev1, h->stream));
@@ -650,6 +672,8 @@ static int run_solve(kp_handle* h) {
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->stats.solve_ms = ms;
+  cudaEventElapsedTime(&h->wsolve_ms, h->ev2, h->ev1);
+  if (getenv("KP_DEBUG")) fprintf(stderr, "[kp] step %.3f ms, k_wsolve %.3f ms\n", ms, h->wsolve_ms);
   return KP_OK;
 }
 
