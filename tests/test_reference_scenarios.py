@@ -300,3 +300,114 @@ def test_compatible_pods_share_a_node_incompatible_do_not(which):  # suite_test.
     d = pods(1, uid0=4, node_affinity_required=[[req(ZONE_LABEL, "In", "test-zone-3")]])
     r = run(which, c + d)
     assert len(r.new_node_claims) == 2
+
+
+# ---- Consolidation (pkg/controllers/disruption/consolidation_test.go) ----------------------------------------------
+def _node(name, it, zone="test-zone-1", ct="on-demand", pod_list=(), initialized=True):
+    """A managed, initialized node of instance type `it` holding `pod_list` (StateNode.Available = allocatable - requests)."""
+    from karpenter_b200.model import INSTANCE_TYPE_LABEL, NODEPOOL_LABEL, OS_LABEL, StateNode, quantity_units
+    res = ["cpu", "memory", "pods"]
+    used = {r: 0 for r in res}
+    for p in pod_list:
+        for r in res:
+            used[r] += quantity_units(r, p.requests.get(r, 0)) if r != "pods" else 1
+    avail = {}
+    for r in res:
+        a = quantity_units(r, it.capacity[r]) - quantity_units(r, it.overhead.get(r, 0)) - used[r]
+        avail[r] = f"{a}m" if r == "cpu" else a
+    arch = [x for x in it.requirements if x.key == ARCH_LABEL][0].values[0]
+    labels = {HOSTNAME_LABEL: name, ZONE_LABEL: zone, CAPACITY_TYPE_LABEL: ct, OS_LABEL: "linux", ARCH_LABEL: arch,
+              NODEPOOL_LABEL: "default", INSTANCE_TYPE_LABEL: it.name}
+    cap = dict(it.capacity)
+    cap["nodes"] = 1
+    return StateNode(name=name, labels=labels, available=avail, capacity=cap, nodepool="default", instance_type=it.name,
+                     pods=list(pod_list), initialized=initialized)
+
+
+def consolidate(which, nodes, candidate_sets, its=None):
+    from karpenter_b200.disruption import Consolidation
+    import numpy as np
+    its = its or fake.default_instance_types()
+    np_ = nodepool()
+    orc = Consolidation([np_], {np_.name: its}, nodes, backend=oracle_lib.consolidate)
+    cmds = orc.compute(candidate_sets)
+    if which == "gpu":
+        gpu = Consolidation([np_], {np_.name: its}, nodes)
+        try:
+            got = gpu.compute(candidate_sets)
+        finally:
+            gpu.close()
+        for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+            assert np.array_equal(gpu.raw[k], orc.raw[k]), k
+        return got
+    return cmds
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_consolidation_can_delete_nodes(which):  # consolidation_test.go:2407-2447: the lone pod fits on the other node
+    its = {it.name: it for it in fake.default_instance_types()}
+    d = its["default-instance-type"]
+    p = pods(3, requests={"cpu": "1"})
+    nodes = [_node("node-1", d, pod_list=p[:2]), _node("node-2", d, pod_list=p[2:])]
+    (cmd,) = consolidate(which, nodes, [["node-2"]])
+    assert cmd.decision == "delete" and cmd.n_new_node_claims == 0 and cmd.n_unscheduled == 0
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_consolidation_replaces_with_cheaper_node(which):  # consolidation_test.go "can replace node" (977-1032 family)
+    its = {it.name: it for it in fake.default_instance_types()}
+    big = its["arm-instance-type"]  # 16 cpu / 128Gi: price 0.1*16 + 0.1*137.4 = 15.3
+    p = pods(1, requests={"cpu": "1"}, node_selector={ARCH_LABEL: "amd64"})
+    # an amd64 pod cannot really sit on the arm node; what matters is the simulation: it needs one new, cheaper amd64 node
+    nodes = [_node("node-1", big, pod_list=p)]
+    (cmd,) = consolidate(which, nodes, [["node-1"]])
+    assert cmd.decision == "replace" and cmd.n_new_node_claims == 1
+    assert "small-instance-type" in cmd.replacement_instance_types
+    assert "arm-instance-type" not in cmd.replacement_instance_types
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_consolidation_wont_replace_with_more_expensive(which):  # consolidation_test.go:2283-2406
+    def it(name, offerings):
+        return fake.new_instance_type(name, offerings=[
+            __import__("karpenter_b200.model", fromlist=["Offering"]).Offering(
+                [req(CAPACITY_TYPE_LABEL, "In", ct), req(ZONE_LABEL, "In", z)], price, avail) for ct, z, price, avail in offerings])
+    current = it("current-on-demand", [("on-demand", "test-zone-1a", 0.5, False)])
+    replacement = it("on-demand-replacement", [("on-demand", "test-zone-1a", 0.6, True), ("on-demand", "test-zone-1b", 0.6, True),
+                                               ("spot", "test-zone-1b", 0.2, True), ("spot", "test-zone-1c", 0.3, True)])
+    p = pods(1, requests={"cpu": "1"})
+    nodes = [_node("node-1", current, zone="test-zone-1a", pod_list=p)]
+    # the reference pins the NodePool to on-demand for this test (consolidation_test.go:2335-2345)
+    from karpenter_b200.disruption import Consolidation
+    np_ = NodePool(name="default", requirements=[req(CAPACITY_TYPE_LABEL, "In", "on-demand")], limits={"cpu": "2000"})
+    c = Consolidation([np_], {"default": [current, replacement]}, nodes, backend=oracle_lib.consolidate)
+    (cmd,) = c.compute([["node-1"]])
+    assert cmd.decision == "noop" and cmd.n_new_node_claims == 1  # 0.6 is not cheaper than 0.5
+    if which == "gpu":
+        g = Consolidation([np_], {"default": [current, replacement]}, nodes)
+        try:
+            (gc,) = g.compute([["node-1"]])
+        finally:
+            g.close()
+        assert gc == cmd
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_consolidation_wont_delete_onto_uninitialized_node(which):  # consolidation_test.go:2990-3035
+    its = {it.name: it for it in fake.default_instance_types()}
+    d = its["default-instance-type"]
+    p = pods(3, requests={"cpu": "1"})
+    nodes = [_node("node-1", d, pod_list=p[:2], initialized=False), _node("node-2", d, pod_list=p[2:])]
+    (cmd,) = consolidate(which, nodes, [["node-2"]])
+    assert cmd.decision == "noop" and cmd.n_unscheduled == 1
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_consolidation_merges_three_nodes_into_one(which):  # consolidation_test.go:3823 family: 3 nodes -> 1 replacement
+    its = {it.name: it for it in fake.default_instance_types()}
+    d = its["default-instance-type"]
+    p = pods(3, requests={"cpu": "1"})
+    nodes = [_node(f"node-{i+1}", d, pod_list=p[i:i + 1]) for i in range(3)]
+    cmds = consolidate(which, nodes, [["node-1", "node-2", "node-3"], ["node-1"], ["node-1", "node-2"]])
+    assert cmds[0].decision == "replace" and cmds[0].n_new_node_claims == 1  # three 0.83-priced nodes -> one of them
+    assert cmds[1].decision == "delete" and cmds[2].decision == "delete"    # the others still have room
