@@ -232,7 +232,6 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(up(h, &d.rs_mask, t.rs_mask));
   CK(up(h, &d.rs_gte, t.rs_gte));
   CK(up(h, &d.rs_lte, t.rs_lte));
-  CK(up(h, &d.rs_keys, t.rs_keys));
   CK(up(h, &d.tol_ok, t.tol_ok));
   CK(up(h, &d.itv_off, t.itv_off));
   CK(up(h, &d.itv, t.itv));
@@ -256,12 +255,8 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(up(h, &d.tmpl_limit_present, t.tmpl_limit_present));
   CK(up(h, &d.cls_req, t.cls_req));
   CK(up(h, &d.cls_rs, t.cls_rs));
-  CK(up(h, &d.cls_strict_rs, t.cls_strict_rs));
   CK(up(h, &d.cls_tolset, t.cls_tolset));
-  CK(up(h, &d.cls_rv, t.cls_rv));
-  CK(up(h, &d.cls_match_off, t.cls_match_off));
   CK(up(h, &d.cls_match, t.cls_match));
-  CK(up(h, &d.cls_rec_off, t.cls_rec_off));
   CK(up(h, &d.cls_rec, t.cls_rec));
   {  // class rows (one indirection less on the per-pod path)
     std::vector<int32_t> hdr((size_t)std::max(t.X, 1) * KP_HDR, 0);
@@ -396,14 +391,8 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
         }
       CK(up(h, &d.cls_lane, rows));
     }
-    CK(up(h, &d.cr_hdr, hdr));
-    CK(up(h, &d.cr_tmplok, tok));
-    CK(up(h, &d.cp_f, pf));
-    CK(up(h, &d.cp_m, pm));
     CK(up(h, &d.cp_g, pg));
     CK(up(h, &d.cp_l, pl));
-    CK(up(h, &d.cs_f, sf));
-    CK(up(h, &d.cs_m, sm));
     CK(up(h, &d.cs_g, sg));
     CK(up(h, &d.cs_l, sl));
   }

@@ -212,7 +212,7 @@ struct PodCtx {
       int tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend, cls, pod;
       unsigned long long tmpl_ok;  // bit n: template n's taints are tolerated (taints.go:49-66)
     };
-    int hdr[KP_HDR + 4];  // a cr_hdr row, then class id, pod id, tmpl_ok (lo, hi)
+    int hdr[KP_HDR + 4];  // the class header, then class id, pod id, tmpl_ok (lo, hi)
   };
   int64_t req[KP_MAXR];
   Slot pod_slot[KP_MAXK];

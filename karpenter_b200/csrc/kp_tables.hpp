@@ -16,7 +16,7 @@ struct ulonglong2 { unsigned long long x, y; };
 #define KP_MAXR 8           // resources
 #define KP_MAX_ITW 32       // instance-type bitmap words (<= 2048 types, one lane per word)
 #define KP_MAX_OFFSETS 32   // distinct offering requirement sets
-#define KP_HDR 10            // ints per class header row (cr_hdr)
+#define KP_HDR 10            // ints of a class header: tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend
 
 // slot flags
 #define SF_COMPLEMENT 0x01u
@@ -77,7 +77,6 @@ struct KpDev {
   const uint64_t* rs_mask;        // [n_reqsets*K]
   const int64_t* rs_gte;          // [n_reqsets*K] (has_bounds)
   const int64_t* rs_lte;
-  const uint32_t* rs_keys;        // [n_reqsets] bitmask of present keys
   // taints
   const uint8_t* tol_ok;          // [(n_tolsets+1) * n_taintsets], row tolset+1 (row 0 == no tolerations)
   // instance types (bit-sliced)
@@ -108,26 +107,15 @@ struct KpDev {
   // classes
   const int64_t* cls_req;         // [X*R]
   const int32_t* cls_rs;          // [X]
-  const int32_t* cls_strict_rs;   // [X]
   const int32_t* cls_tolset;      // [X]
-  const int32_t* cls_rv;          // [X] id of the distinct request vector
   int n_rv;
-  const int32_t* cls_match_off;   // [X+1] groups that constrain the class (owned + inverse selecting it); bit 30 = selects(pod)
-  const int32_t* cls_match;       //
-  const int32_t* cls_rec_off;     // [X+1] groups that may count the class on Record (select it / inverse owned)
-  const int32_t* cls_rec;
-  // class rows, one level of indirection for the per-pod staging (header: tolset, rv, match/record list ranges)
-  const ClsLane* cls_lane;        // [X*32] class rows, lane-major (see ClsLane)
-  const int32_t* cr_hdr;          // [X*KP_HDR] tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend
+  const int32_t* cls_match;       // groups that constrain a class (owned + inverse selecting it); bit 30 = selects(pod)
+  const int32_t* cls_rec;         // groups that may count a class on Record (select it / inverse owned)
+  const ClsLane* cls_lane;        // [X*32] class rows, lane-major (see ClsLane): header, requests, requirement slots
   const int4* cls_hchk;           // hostname-group checks of a class {host_row, type | self << 8, max_skew, group}
-  const uint64_t* cr_tmplok;      // [X] bit n: template n tolerated
-  const uint8_t* cp_f;            // [X*K] PodData.Requirements slots
-  const uint64_t* cp_m;
-  const int64_t* cp_g;
+  const int64_t* cp_g;            // [X*K] Gt / Lt bounds of PodData.Requirements (has_bounds only)
   const int64_t* cp_l;
-  const uint8_t* cs_f;            // [X*K] PodData.StrictRequirements slots
-  const uint64_t* cs_m;
-  const int64_t* cs_g;
+  const int64_t* cs_g;            // [X*K] ... of PodData.StrictRequirements
   const int64_t* cs_l;
   // topology groups
   const KpGroup* groups;          // [G]
