@@ -1,0 +1,129 @@
+"""Differential fuzzing: random scheduling problems (tests/fuzz.py) solved by the CUDA path and by the oracle must agree
+bit for bit.  The CPU tier only checks that the generator produces well-formed, varied problems the oracle accepts."""
+import collections
+
+import numpy as np
+import pytest
+
+from karpenter_b200 import _native
+from karpenter_b200.scheduler import Scheduler
+from tests import fuzz, oracle_lib
+from tests.parity import assert_same
+
+SEEDS = list(range(120))
+
+
+def encode(seed):
+    pools, per_pool, nodes, pl = fuzz.problem(seed)
+    s = Scheduler(pools, per_pool, nodes, claim_order="go" if seed % 3 else "stable")
+    return s.encode(pl)
+
+
+def test_generator_is_wellformed_and_varied():
+    stats = collections.Counter()
+    for seed in SEEDS:
+        enc = encode(seed)
+        try:
+            res = oracle_lib.solve(enc.problem)
+        except RuntimeError:
+            stats["rejected"] += 1
+            continue
+        t = res["pod_target"]
+        stats["solved"] += 1
+        stats["on_nodes"] += int((t >= 0).sum() > 0)
+        stats["claims"] += int(res["n_claims"] > 0)
+        stats["unsched"] += int((t == -1).sum() > 0)
+        stats["multi_claim"] += int(res["n_claims"] > 3)
+        stats["groups"] += int(res["n_groups"] > 0)
+    assert stats["solved"] >= 100, stats
+    for k in ("on_nodes", "claims", "unsched", "multi_claim", "groups"):
+        assert stats[k] >= 10, stats
+
+
+@pytest.mark.gpu
+def test_fuzz_parity_gpu():
+    h = _native.Handle()
+    bad, ran = [], 0
+    try:
+        for seed in SEEDS:
+            enc = encode(seed)
+            try:
+                orc = oracle_lib.solve(enc.problem)
+            except RuntimeError:
+                continue  # unsupported feature combination: both sides refuse (checked below)
+            try:
+                gpu = h.solve(enc.problem)
+            except _native.SolverError as e:
+                bad.append((seed, f"gpu refused: {e}"))
+                continue
+            ran += 1
+            try:
+                assert_same(gpu, orc, f"seed {seed} ")
+            except AssertionError as e:
+                bad.append((seed, str(e)[:200]))
+    finally:
+        h.close()
+    assert ran >= 100
+    assert not bad, bad[:10]
+
+
+def consolidation_case(seed):
+    """A random small cluster (topology-free pods bound to nodes) and random candidate sets of 1-3 nodes."""
+    import random
+    from karpenter_b200.disruption import Consolidation
+    rng = random.Random(10_000 + seed)
+    its = fuzz.instance_types(rng)
+    pools = fuzz.node_pools(rng)
+    per_pool = {p.name: its for p in pools}
+    nodes = fuzz.state_nodes(rng, its, pools, rng.randint(3, 14), [])
+    for n in nodes:
+        n.running_pods = []
+        k = rng.randint(0, 4)
+        plain = [p for p in fuzz.pods(rng, 12) if not (p.topology_spread_constraints or p.pod_affinity or p.pod_anti_affinity)]
+        n.pods = plain[:k]
+    names = [n.name for n in nodes]
+    sets = [rng.sample(names, rng.randint(1, min(3, len(names)))) for _ in range(rng.randint(1, 12))]
+    return pools, per_pool, nodes, sets
+
+
+@pytest.mark.gpu
+def test_fuzz_consolidation_parity_gpu():
+    from karpenter_b200.disruption import Consolidation
+    bad, ran = [], 0
+    for seed in range(60):
+        pools, per_pool, nodes, sets = consolidation_case(seed)
+        orc = Consolidation(pools, per_pool, nodes, backend=oracle_lib.consolidate)
+        try:
+            orc.compute(sets)
+        except RuntimeError:
+            continue
+        gpu = Consolidation(pools, per_pool, nodes)
+        try:
+            gpu.compute(sets)
+        except _native.SolverError as e:
+            if e.code == 5:  # KP_ERR_UNSUPPORTED: > 600 types / spot-to-spot / topology on the evicted pods
+                continue
+            bad.append((seed, str(e)))
+            continue
+        finally:
+            gpu.close()
+        ran += 1
+        for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+            if not np.array_equal(gpu.raw[k], orc.raw[k]):
+                bad.append((seed, k, gpu.raw[k].tolist()[:8], orc.raw[k].tolist()[:8]))
+                break
+    assert ran >= 40
+    assert not bad, bad[:6]
+
+
+def test_consolidation_generator_on_oracle():
+    from karpenter_b200.disruption import Consolidation
+    decisions = collections.Counter()
+    for seed in range(60):
+        pools, per_pool, nodes, sets = consolidation_case(seed)
+        try:
+            for c in Consolidation(pools, per_pool, nodes, backend=oracle_lib.consolidate).compute(sets):
+                decisions[c.decision] += 1
+        except RuntimeError:
+            decisions["rejected"] += 1
+    assert decisions["delete"] >= 5 and decisions["noop"] >= 5 and decisions["replace"] >= 5, decisions
