@@ -157,7 +157,7 @@ def problem(seed: int, n_pods=None, with_nodes=True):
     its = instance_types(rng)
     pools = node_pools(rng)
     per_pool = {p.name: (its if rng.random() < 0.7 else rng.sample(its, max(1, len(its) // 2))) for p in pools}
-    n = n_pods if n_pods is not None else rng.choice([5, 20, 60, 150])
+    n = n_pods if n_pods is not None else rng.choice([5, 20, 60, 150, 400])
     pl = pods(rng, n)
     nodes = []
     if with_nodes and rng.random() < 0.6:

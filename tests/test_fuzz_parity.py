@@ -10,7 +10,7 @@ from karpenter_b200.scheduler import Scheduler
 from tests import fuzz, oracle_lib
 from tests.parity import assert_same
 
-SEEDS = list(range(120))
+SEEDS = list(range(400))
 
 
 def encode(seed):
@@ -35,7 +35,7 @@ def test_generator_is_wellformed_and_varied():
         stats["unsched"] += int((t == -1).sum() > 0)
         stats["multi_claim"] += int(res["n_claims"] > 3)
         stats["groups"] += int(res["n_groups"] > 0)
-    assert stats["solved"] >= 100, stats
+    assert stats["solved"] >= 300, stats
     for k in ("on_nodes", "claims", "unsched", "multi_claim", "groups"):
         assert stats[k] >= 10, stats
 
@@ -63,7 +63,7 @@ def test_fuzz_parity_gpu():
                 bad.append((seed, str(e)[:200]))
     finally:
         h.close()
-    assert ran >= 100
+    assert ran >= 300
     assert not bad, bad[:10]
 
 
@@ -90,7 +90,7 @@ def consolidation_case(seed):
 def test_fuzz_consolidation_parity_gpu():
     from karpenter_b200.disruption import Consolidation
     bad, ran = [], 0
-    for seed in range(60):
+    for seed in range(200):
         pools, per_pool, nodes, sets = consolidation_case(seed)
         orc = Consolidation(pools, per_pool, nodes, backend=oracle_lib.consolidate)
         try:
@@ -112,7 +112,7 @@ def test_fuzz_consolidation_parity_gpu():
             if not np.array_equal(gpu.raw[k], orc.raw[k]):
                 bad.append((seed, k, gpu.raw[k].tolist()[:8], orc.raw[k].tolist()[:8]))
                 break
-    assert ran >= 40
+    assert ran >= 120
     assert not bad, bad[:6]
 
 
