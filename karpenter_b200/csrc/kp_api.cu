@@ -370,6 +370,9 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
     for (int n = 0; n < t.E; n++)
       if (t.node_flags[n] & KP_NODE_SCHEDULABLE) nact[n >> 5] |= 1u << (n & 31);
     CK(up_mut(h, &d.nactive, nact));
+    d.ESW = (d.EW + 31) / 32;
+    CK(zeros(h, &d.nfit_sum, (size_t)std::max(t.n_rv, 1) * std::max(d.ESW, 1)));
+    CK(zeros(h, &d.nstat_sum, (size_t)std::max(d.n_nsig, 1) * std::max(d.ESW, 1)));
     CK(zeros(h, &d.nfit, (size_t)std::max(t.n_rv, 1) * std::max(d.EW, 1)));
     CK(zeros(h, &d.nstat, (size_t)std::max(d.n_nsig, 1) * std::max(d.EW, 1)));
     {
@@ -594,7 +597,9 @@ static int launch_node_cand(kp_handle* h) {
   if (d.E <= 0) return KP_OK;
   dim3 grid((d.E + 255) / 256, d.n_nsig + d.n_rv);
   k_node_cand<<<grid, 256, 0, h->stream>>>(d, h->d_nsig_rs, h->d_nsig_tolset, h->d_rv_req, h->strict_undefined);
-  h->stats.kernel_launches++;
+  const int nsum = (d.n_rv + d.n_nsig) * d.ESW;
+  k_node_sum<<<(nsum + 255) / 256, 256, 0, h->stream>>>(d);
+  h->stats.kernel_launches += 2;
   return KP_OK;
 }
 
@@ -918,7 +923,6 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   q.ct_order_valid = ct_valid;
   q.spot_to_spot_enabled = in->spot_to_spot_enabled;
   int n_sub_nodes = S ? in->subset_off[S] : 0;
-  int n_off = T ? p->it_off_off[T] : 0;
   int32_t* tmp32;
   CK(up_raw(h, &tmp32, in->subset_off, (size_t)S + 1));
   q.subset_off = tmp32;
@@ -945,15 +949,30 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
     CK(up(h, &q.node_tmpl, ntm));
     CK(up(h, &q.node_capacity, ncap));
     CK(up(h, &q.tmpl_remaining0, t.tmpl_remaining));
-    CK(up_raw(h, &tmp32, p->it_off_off, (size_t)T + 1));
-    q.it_off_off = tmp32;
-    CK(up(h, &q.off_set, t.off_set));
-    double* dd_;
-    CK(up_raw(h, &dd_, p->off_price, (size_t)n_off));
-    q.off_price = dd_;
-    CK(up_raw(h, &u8, p->off_available, (size_t)n_off));
-    q.off_available = u8;
-    CK(up(h, &q.offset_ctmask, ctmask));
+    // WorstLaunchPrice lists (see KpConsol)
+    std::vector<int32_t> wl_off((size_t)T * 3 + 1, 0), wl_set;
+    std::vector<double> wl_price;
+    for (int ti = 0; ti < T; ti++)
+      for (int ci = 0; ci < 3; ci++) {
+        std::vector<std::pair<double, int>> ent;
+        for (int o = p->it_off_off[ti]; o < p->it_off_off[ti + 1]; o++)
+          if (p->off_available[o] && ((ctmask[t.off_set[o]] >> ci) & 1)) ent.push_back({p->off_price[o], t.off_set[o]});
+        std::stable_sort(ent.begin(), ent.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
+          return a.first > b.first;
+        });
+        for (auto& e : ent) {
+          wl_price.push_back(e.first);
+          wl_set.push_back(e.second);
+        }
+        wl_off[(size_t)ti * 3 + ci + 1] = (int32_t)wl_set.size();
+      }
+    if (wl_set.empty()) {
+      wl_set.push_back(0);
+      wl_price.push_back(0);
+    }
+    CK(up(h, &q.wl_off, wl_off));
+    CK(up(h, &q.wl_set, wl_set));
+    CK(up(h, &q.wl_price, wl_price));
   }
   // ---- launch geometry: as many resident warps as the GPU holds, each with a private scratch slot
   const size_t budget = 200 * 1024;

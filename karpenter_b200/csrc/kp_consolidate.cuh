@@ -115,6 +115,24 @@ __global__ void __launch_bounds__(256) k_node_cand(KpDev d, const int32_t* nsig_
   }
 }
 
+// word-level summaries of the candidate bitmaps: bit w of summary word s <=> bitmap word 32*s+w (masked by nactive for
+// the Fits rows) is non-zero.  One thread per summary word.
+__global__ void __launch_bounds__(256) k_node_sum(KpDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, rows = d.n_rv + d.n_nsig;
+  if (i >= rows * d.ESW) return;
+  const int row = i / d.ESW, s = i % d.ESW;
+  const uint32_t* src = row < d.n_rv ? d.nfit + (size_t)row * d.EW : d.nstat + (size_t)(row - d.n_rv) * d.EW;
+  uint32_t out = 0;
+  for (int w = 0; w < 32; w++) {
+    const int idx = s * 32 + w;
+    if (idx < d.EW && (src[idx] & d.nactive[idx])) out |= 1u << w;
+  }
+  if (row < d.n_rv)
+    d.nfit_sum[(size_t)row * d.ESW + s] = out;
+  else
+    d.nstat_sum[(size_t)(row - d.n_rv) * d.ESW + s] = out;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Scheduler.Solve, one instance.
 struct WSolveShared {
@@ -170,6 +188,8 @@ __global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev 
     I.nfit = d.nfit;
     I.nstat = d.nstat;
     I.nactive = d.nactive;
+    I.nfit_sum = d.nfit_sum;
+    I.nstat_sum = d.nstat_sum;
     I.n_removed = 0;
     I.removed = nullptr;
     I.ov_cap = 0;
@@ -251,11 +271,12 @@ struct KpConsol {
   const int32_t* node_tmpl;      // [E] NodePool of the node, -1 unmanaged
   const int64_t* node_capacity;  // [E*R]
   const int64_t* tmpl_remaining0;// [N*R] limits minus capacity of ALL nodes
-  const int32_t* it_off_off;     // [T+1]
-  const int32_t* off_set;        // [offerings] distinct offering requirement set
-  const double* off_price;
-  const uint8_t* off_available;
-  const uint8_t* offset_ctmask;  // [D] bit i: set compatible with capacity type ct_order[i] (reserved, spot, on-demand)
+  // WorstLaunchPrice lists: for instance type t and capacity type i (reserved, spot, on-demand) the AVAILABLE offerings
+  // whose requirement set admits that capacity type, most expensive first -- the first entry whose set is compatible
+  // with the claim's requirements is the answer (types.go:480-491)
+  const int32_t* wl_off;         // [T*3+1]
+  const int32_t* wl_set;         // distinct offering requirement set of the entry
+  const double* wl_price;
   int ct_key, ct_spot, ct_order_valid;  // bit i of ct_order_valid: ct_order[i] is interned
   int spot_to_spot_enabled;
   // per warp slot scratch
@@ -340,6 +361,8 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
     I.nfit = d.nfit;
     I.nstat = d.nstat;
     I.nactive = d.nactive;
+    I.nfit_sum = d.nfit_sum;
+    I.nstat_sum = d.nstat_sum;
     I.CS = 0;
     I.CR = 0;
     I.ov_cap = capq;
@@ -467,21 +490,13 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
               bits &= bits - 1;
               const int t = lane * 64 + b;
               double worst = 1.7976931348623157e308;
-              for (int ci = 0; ci < 3; ci++) {  // reserved -> spot -> on-demand (types.go:480-491)
+              for (int ci = 0; ci < 3 && worst > 1e308; ci++) {  // reserved -> spot -> on-demand (types.go:480-491)
                 if (q.ct_key < 0 || !((q.ct_order_valid >> ci) & 1)) continue;
-                bool any = false;
-                double mx = 0;
-                for (int o = q.it_off_off[t]; o < q.it_off_off[t + 1]; o++) {
-                  if (!q.off_available[o]) continue;
-                  const int dd = q.off_set[o];
-                  if (!((okmask >> dd) & 1u) || !((q.offset_ctmask[dd] >> ci) & 1)) continue;
-                  if (!any || q.off_price[o] > mx) mx = q.off_price[o];
-                  any = true;
-                }
-                if (any) {
-                  worst = mx;
-                  break;
-                }
+                for (int e = q.wl_off[t * 3 + ci]; e < q.wl_off[t * 3 + ci + 1]; e++)
+                  if ((okmask >> q.wl_set[e]) & 1u) {
+                    worst = q.wl_price[e];
+                    break;
+                  }
               }
               if (worst < price) rep |= 1ull << b;
             }

@@ -163,6 +163,9 @@ struct KpDev {
   uint32_t* nfit;                 // [n_rv * EW] resources.Fits(request vector, remaining) held when last checked
   uint32_t* nstat;                // [n_nsig * EW] taints tolerated and no defined key has an empty intersection
   uint32_t* nactive;              // [EW] schedulable nodes
+  int ESW;                        // summary words per row = ceil(EW/32)
+  uint32_t* nfit_sum;             // [n_rv * ESW] bit w of word s: nfit word 32*s+w (and nactive) is non-zero
+  uint32_t* nstat_sum;            // [n_nsig * ESW] the same for nstat
   // pods
   int64_t P;
   const int32_t* pod_class;       // [P]

@@ -69,6 +69,7 @@ struct WInst {
   int32_t* node_npods;      // direct mode only
   uint32_t *nfit, *nstat;
   const uint32_t* nactive;
+  const uint32_t *nfit_sum, *nstat_sum;  // one bit per bitmap word: skip 1024-node chunks nothing can match in
   int n_removed;
   const int32_t* removed;   // overlay mode: nodes taken out of the cluster (the consolidation candidates)
   // overlay (consolidation): entry i shadows node ov_node[i]
@@ -448,7 +449,15 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       const uint32_t* fitrow = I.nfit + (size_t)rv * EW;
       const uint32_t* strow = I.nstat + (size_t)px.nsig * EW;
       int seen = 0;
+      // chunks of 32 bitmap words (1024 nodes) that can hold a candidate at all, from the word-level summaries: one
+      // parallel load for up to 32 chunks (32 768 nodes); clusters beyond that scan every chunk
+      unsigned live = 0xffffffffu;
+      if (d.ESW <= 32) {
+        const uint32_t sw = lane < d.ESW ? (I.nfit_sum[(size_t)rv * d.ESW + lane] & I.nstat_sum[(size_t)px.nsig * d.ESW + lane]) : 0u;
+        live = __ballot_sync(FULL, sw != 0);
+      }
       for (int w0 = 0; w0 < EW && !found; w0 += 32) {
+        if (d.ESW <= 32 && !((live >> (w0 >> 5)) & 1u)) continue;
         const int w = w0 + lane;
         uint32_t bits = w < EW ? (fitrow[w] & strow[w] & I.nactive[w]) : 0u;
         if (OVERLAY)
