@@ -411,3 +411,26 @@ def test_consolidation_merges_three_nodes_into_one(which):  # consolidation_test
     cmds = consolidate(which, nodes, [["node-1", "node-2", "node-3"], ["node-1"], ["node-1", "node-2"]])
     assert cmds[0].decision == "replace" and cmds[0].n_new_node_claims == 1  # three 0.83-priced nodes -> one of them
     assert cmds[1].decision == "delete" and cmds[2].decision == "delete"    # the others still have room
+
+
+# ---- edge cases: empty input, no usable NodePool ---------------------------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_empty_pod_list(which):
+    r = run(which, [])
+    assert not r.new_node_claims and not r.pod_errors and not r.existing_nodes
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_nodepool_requirements_filter_out_every_instance_type(which):  # scheduler.go:147-160, 510-512
+    p = pods(3, requests={"cpu": "1"})
+    r = run(which, p, nodepool(requirements=[req(ZONE_LABEL, "In", "no-such-zone")]))
+    assert not r.new_node_claims and len(r.pod_errors) == 3
+    assert all("filtered out all" in m for m in r.pod_errors.values())
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_mixed_schedulable_and_unschedulable(which):
+    ok = pods(4, requests={"cpu": "1"})
+    bad = pods(2, uid0=50, requests={"cpu": "100"})  # larger than every instance type
+    r = run(which, ok + bad)
+    assert {id(x) for x in bad} == set(r.pod_errors) and sum(len(c.pods) for c in r.new_node_claims) == 4
