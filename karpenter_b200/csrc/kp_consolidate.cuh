@@ -22,6 +22,7 @@ __host__ __device__ inline size_t kp_tab_bytes(const KpDev& d) {
   b += 3 * KP_ALIGN16(8 * K * ITW) + KP_ALIGN16(8 * ITW);        // it_nokey, it_dne, it_nonempty, it_valid
   b += KP_ALIGN16(sizeof(Slot) * D * K) + KP_ALIGN16(4 * D) + KP_ALIGN16(8 * D * ITW);
   b += KP_ALIGN16(4 * N);
+  b += KP_ALIGN16(4 * (size_t)d.n_rv * d.ESW) + KP_ALIGN16(4 * (size_t)d.n_nsig * d.ESW);  // candidate bitmap summaries
   return b;
 }
 
@@ -63,6 +64,8 @@ __device__ __forceinline__ void stage_tables(const KpDev& d_in, KpDev* ds, unsig
     KP_STAGE(off_keys, uint32_t, D_)
     KP_STAGE(offset_bits, uint64_t, D_ * W_)
     KP_STAGE(tmpl_taintset, int32_t, N_)
+    KP_STAGE(nfit_sum, uint32_t, (size_t)d_in.n_rv * d_in.ESW)
+    KP_STAGE(nstat_sum, uint32_t, (size_t)d_in.n_nsig * d_in.ESW)
 #undef KP_STAGE
   }
   __syncthreads();
