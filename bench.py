@@ -29,8 +29,8 @@ N_PODS = 100_000
 N_ITS = 500
 CPU_SAMPLE_PODS = 100_000  # the whole workload: ~17 s of CPU work, inside the 10-30 s the contract asks for
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_wsolve launch on this workload (ncu --set full capture,
-# profiles/r1_v5_k_metrics.csv); static: a number measured under a profiler is evidence, not a bench value
-NCU_TRAFFIC_BYTES = 1_721_344 + 3_584
+# profiles/r1_v9_k_metrics.csv); static: a number measured under a profiler is evidence, not a bench value
+NCU_TRAFFIC_BYTES = 2_666_496 + 0
 # packed row sizes of SURVEY.md section 8(d)
 B_POD, B_CLAIM, B_IT = 128, 256, 192
 
