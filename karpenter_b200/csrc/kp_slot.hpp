@@ -162,14 +162,6 @@ KP_HD bool slot_compatible(const KeyInfo& ki, const Slot& existing, const Slot& 
   if (slot_has_intersection(ki, existing, incoming)) return true;
   return op_is_negative(slot_op(incoming)) && op_is_negative(slot_op(existing));
 }
-// One key of Requirements.Intersects(existing, incoming) -- shared keys only
-KP_HD bool slot_intersects(const KeyInfo& ki, const Slot& existing, const Slot& incoming) {
-  if (!slot_present(incoming) || !slot_present(existing)) return true;
-  if (slot_has_intersection(ki, existing, incoming)) return true;
-  return op_is_negative(slot_op(incoming)) && op_is_negative(slot_op(existing));
-}
-
-
 // ---- the same algebra when no requirement in the problem carries Gt / Lt bounds (has_bounds == 0): flags + mask only
 KP_HD bool slot_neg_nb(const Slot& s) { return ((s.f & SF_COMPLEMENT) != 0) == (s.m != 0); }  // NotIn or DoesNotExist
 KP_HD bool slot_compatible_nb(const Slot& existing, const Slot& incoming, bool well_known, bool allow_undefined) {
