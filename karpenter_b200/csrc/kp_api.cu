@@ -970,6 +970,29 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
       wl_set.push_back(0);
       wl_price.push_back(0);
     }
+    // OrderByPrice lists: available offerings per instance type, cheapest first
+    std::vector<int32_t> ml_off((size_t)T + 1, 0), ml_set;
+    std::vector<double> ml_price;
+    for (int ti = 0; ti < T; ti++) {
+      std::vector<std::pair<double, int>> ent;
+      for (int o = p->it_off_off[ti]; o < p->it_off_off[ti + 1]; o++)
+        if (p->off_available[o]) ent.push_back({p->off_price[o], t.off_set[o]});
+      std::stable_sort(ent.begin(), ent.end(),
+                       [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });
+      for (auto& e : ent) {
+        ml_price.push_back(e.first);
+        ml_set.push_back(e.second);
+      }
+      ml_off[(size_t)ti + 1] = (int32_t)ml_set.size();
+    }
+    if (ml_set.empty()) {
+      ml_set.push_back(0);
+      ml_price.push_back(0);
+    }
+    CK(up(h, &q.ml_off, ml_off));
+    CK(up(h, &q.ml_set, ml_set));
+    CK(up(h, &q.ml_price, ml_price));
+    q.T = T;
     CK(up(h, &q.wl_off, wl_off));
     CK(up(h, &q.wl_set, wl_set));
     CK(up(h, &q.wl_price, wl_price));
@@ -1000,6 +1023,9 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   CK(zeros(h, &q.c_smask, slots * cq * K));
   CK(zeros(h, &q.c_its, slots * cq * ITW));
   CK(zeros(h, &q.c_j, slots * cq * R));
+  CK(zeros(h, &q.sort_key, slots * (size_t)std::max(T, 1)));
+  CK(zeros(h, &q.sort_val, slots * (size_t)std::max(T, 1)));
+  CK(zeros(h, &q.sort_bits, slots * (size_t)std::max(ITW, 1)));
   CK(zeros(h, &q.cmask, slots * cq));
   CK(zeros(h, &q.amask, slots * cq));
   CK(zeros(h, &q.tmpl_remaining, slots * (size_t)std::max(N, 1) * R));
@@ -1070,8 +1096,7 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   for (int s = 0; s < S; s++)
     if (out->decision[s] == 255) {
       kp_consol_result_free(out);
-      return h->err = "a replacement needs price-ordered truncation (> 600 instance types) or spot-to-spot rules: not built yet",
-             KP_ERR_UNSUPPORTED;
+      return h->err = "internal: unknown consolidation decision", KP_ERR_INVALID;
     }
   return KP_OK;
 }

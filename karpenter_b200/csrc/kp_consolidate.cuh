@@ -280,6 +280,16 @@ struct KpConsol {
   const int32_t* wl_off;         // [T*3+1]
   const int32_t* wl_set;         // distinct offering requirement set of the entry
   const double* wl_price;
+  // OrderByPrice lists (types.go:238-257): the AVAILABLE offerings of instance type t, cheapest first -- the first entry
+  // whose set is compatible with the requirements is the sort key
+  const int32_t* ml_off;         // [T+1]
+  const int32_t* ml_set;
+  const double* ml_price;
+  int T;
+  // per warp slot: instance types of the single new NodeClaim in price order (sort keys / ids), bitmap scratch
+  double* sort_key;              // [slots * T]
+  int32_t* sort_val;             // [slots * T]
+  unsigned long long* sort_bits; // [slots * ITW]
   int ct_key, ct_spot, ct_order_valid;  // bit i of ct_order_valid: ct_order[i] is interned
   int spot_to_spot_enabled;
   // per warp slot scratch
@@ -309,6 +319,21 @@ struct KpConsol {
   int32_t* next;                 // work counter
   int32_t* status;
 };
+
+// bit dd: Requirements.Compatible(S, offering requirement set dd, AllowUndefinedWellKnownLabels)
+__device__ __forceinline__ unsigned offering_ok_mask(const KpDev& d, const Slot* S, int lane) {
+  bool ok = false;
+  if (lane < d.D) {
+    uint32_t keys = d.off_keys[lane];
+    ok = true;
+    while (keys) {
+      const int k = __ffs(keys) - 1;
+      keys &= keys - 1;
+      if (!slot_compatible(key_info(d, k), S[k], d.off_slots[(size_t)lane * d.K + k], d.key_wellknown[k], true)) ok = false;
+    }
+  }
+  return __ballot_sync(FULL, ok);
+}
 
 #define CONSOL_WARPS 8
 struct ConsolWarp {
@@ -466,29 +491,77 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
           const int64_t g = __shfl_sync(FULL, S.gte, q.ct_key), l = __shfl_sync(FULL, S.lte, q.ct_key);
           spot_ok = slot_has(key_info(d, q.ct_key), Slot{f, m, g, l}, q.ct_spot);
         }
-        if (n_its > 600) {
-          decision = 255;  // TruncateInstanceTypes by price order (scheduler.go:361-379) is not built on the device
-        } else if (all_spot && spot_ok) {
-          decision = q.spot_to_spot_enabled ? 255 : KP_DECISION_NOOP;  // computeSpotToSpotConsolidation :236-316
-        } else {
-          // RemoveInstanceTypeOptionsByPriceAndMinValues (nodeclaim.go:309-318): keep WorstLaunchPrice < price
-          if (lane < K) W.scratch[lane] = S;
-          __syncwarp();
-          bool off_ok = false;
-          if (lane < d.D) {
-            uint32_t keys = d.off_keys[lane];
-            off_ok = true;
-            while (keys) {
-              const int k = __ffs(keys) - 1;
-              keys &= keys - 1;
-              if (!slot_compatible(key_info(d, k), W.scratch[k], d.off_slots[(size_t)lane * K + k], d.key_wellknown[k], true))
-                off_ok = false;
-            }
+        if (lane < K) W.scratch[lane] = S;
+        __syncwarp();
+        unsigned okmask = offering_ok_mask(d, W.scratch, lane);
+        const bool spot_path = all_spot && spot_ok;
+        uint64_t cur = its;  // lane w: word w of the NodeClaim's instance types as they go through the steps below
+        // ---- OrderByPrice + Truncate(600) (helpers.go:120, scheduler.go:361-379, types.go:238-257,339-351).  The order
+        // only matters when it truncates, or for the 15-cheapest rule of single-node spot-to-spot consolidation.
+        double* sk = q.sort_key + slot * (size_t)q.T;
+        int32_t* sv = q.sort_val + slot * (size_t)q.T;
+        unsigned long long* sb = q.sort_bits + slot * (size_t)ITW;
+        int n_ord = 0;
+        const bool need_order = n_its > 600 || (spot_path && q.spot_to_spot_enabled);
+        if (need_order) {
+          const int cw = lane < ITW ? __popcll(cur) : 0;
+          int pre = cw;
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, pre, o);
+            if (lane >= o) pre += t;
           }
-          const unsigned okmask = __ballot_sync(FULL, off_ok);
+          int at = pre - cw;  // provider order == ascending instance type index
+          for (uint64_t bits = lane < ITW ? cur : 0ull; bits;) {
+            const int b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            const int t = lane * 64 + b;
+            double mp = 1.7976931348623157e308;
+            for (int e = q.ml_off[t]; e < q.ml_off[t + 1]; e++)
+              if ((okmask >> q.ml_set[e]) & 1u) {
+                mp = q.ml_price[e];
+                break;
+              }
+            sk[at] = mp;
+            sv[at] = t;
+            at++;
+          }
+          n_ord = n_its;
           __syncwarp();
+          WarpSorterT<double> srt{sk, sv, lane};
+          srt.pdqsort(0, n_ord, WarpSorterT<double>::bits_len((unsigned long long)n_ord));
+          if (n_ord > 600) {
+            n_ord = 600;
+            if (lane < ITW) sb[lane] = 0ull;
+            __syncwarp();
+            for (int i = lane; i < n_ord; i += 32) atomicOr(&sb[sv[i] >> 6], 1ull << (sv[i] & 63));
+            __syncwarp();
+            cur = lane < ITW ? sb[lane] : 0ull;
+          }
+        }
+        if (spot_path && !q.spot_to_spot_enabled) {
+          decision = KP_DECISION_NOOP;  // computeSpotToSpotConsolidation needs the feature gate (consolidation.go:239)
+        } else {
+          if (spot_path) {  // restrict the claim to spot (consolidation.go:252-257) and drop types without such an offering
+            if (lane == q.ct_key)
+              W.scratch[lane] = slot_add(key_info(d, lane), W.scratch[lane], Slot{SF_PRESENT, 1ull << q.ct_spot, 0, 0});
+            __syncwarp();
+            okmask = offering_ok_mask(d, W.scratch, lane);
+            uint64_t keep = 0;
+            for (uint64_t bits = lane < ITW ? cur : 0ull; bits;) {
+              const int b = __ffsll((long long)bits) - 1;
+              bits &= bits - 1;
+              const int t = lane * 64 + b;
+              for (int e = q.ml_off[t]; e < q.ml_off[t + 1]; e++)
+                if ((okmask >> q.ml_set[e]) & 1u) {
+                  keep |= 1ull << b;
+                  break;
+                }
+            }
+            cur = keep;
+          }
+          // RemoveInstanceTypeOptionsByPriceAndMinValues (nodeclaim.go:309-318): keep WorstLaunchPrice < price
           if (lane < ITW) {
-            for (uint64_t bits = its; bits;) {
+            for (uint64_t bits = cur; bits;) {
               const int b = __ffsll((long long)bits) - 1;
               bits &= bits - 1;
               const int t = lane * 64 + b;
@@ -504,7 +577,35 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
               if (worst < price) rep |= 1ull << b;
             }
           }
-          if (__any_sync(FULL, rep != 0)) decision = KP_DECISION_REPLACE;
+          bool any = __any_sync(FULL, rep != 0);
+          if (any && spot_path && sn == 1) {
+            // single-node spot-to-spot: at least 15 cheaper types, and only the 15 cheapest go out (consolidation.go:283-312)
+            int total = lane < ITW ? __popcll(rep) : 0;
+            for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+            if (total < 15) {
+              any = false;
+            } else {
+              if (lane < ITW) sb[lane] = rep;
+              __syncwarp();
+              uint64_t first15 = 0;  // lane w collects its words' bits; walk the price order 32 entries at a time
+              int taken = 0;
+              for (int b0 = 0; b0 < n_ord && taken < 15; b0 += 32) {
+                const int i = b0 + lane;
+                const int t = i < n_ord ? sv[i] : 0;
+                const bool in = i < n_ord && ((sb[t >> 6] >> (t & 63)) & 1ull);
+                const unsigned m = __ballot_sync(FULL, in);
+                const int rank = taken + __popc(m & ((1u << lane) - 1));
+                const bool take = in && rank < 15;
+                for (int l = 0; l < 32; l++) {  // hand each taken type to the lane that owns its word
+                  const int tt = __shfl_sync(FULL, take ? t : -1, l);
+                  if (tt >= 0 && (tt >> 6) == lane) first15 |= 1ull << (tt & 63);
+                }
+                taken += __popc(m);
+              }
+              rep = first15;
+            }
+          }
+          if (any) decision = KP_DECISION_REPLACE;
         }
       }
     }

@@ -13,25 +13,26 @@
 #define FULL 0xffffffffu
 #endif
 
-struct WarpSorter {
-  int* key;
-  int* val;
+template <class K>
+struct WarpSorterT {
+  K* key;    // sort key by position (pod count of a claim; price of an instance type)
+  int* val;  // payload by position
   int lane;
 
   __device__ bool less(int i, int j) const { return key[i] < key[j]; }
   __device__ void swap(int i, int j) {
     if (lane == 0) {
-      int t = key[i];
+      K tk = key[i];
       key[i] = key[j];
-      key[j] = t;
-      t = val[i];
+      key[j] = tk;
+      int t = val[i];
       val[i] = val[j];
       val[j] = t;
     }
     __syncwarp();
   }
   // smallest idx in [i, j] whose key is NOT < pv (j + 1 if none):   for i <= j && less(i, a) { i++ }
-  __device__ int first_not_less(int i, int j, int pv) const {
+  __device__ int first_not_less(int i, int j, K pv) const {
     for (int b = i; b <= j; b += 32) {
       int idx = b + lane;
       unsigned m = __ballot_sync(FULL, idx <= j && !(key[idx] < pv));
@@ -40,7 +41,7 @@ struct WarpSorter {
     return j + 1;
   }
   // largest idx in [i, j] whose key IS < pv (i - 1 if none):        for i <= j && !less(j, a) { j-- }
-  __device__ int last_less(int i, int j, int pv) const {
+  __device__ int last_less(int i, int j, K pv) const {
     for (int b = j; b >= i; b -= 32) {
       int idx = b - lane;
       unsigned m = __ballot_sync(FULL, idx >= i && key[idx] < pv);
@@ -49,7 +50,7 @@ struct WarpSorter {
     return i - 1;
   }
   // smallest idx in [i, j] with pv < key[idx] (j + 1 if none):      for i <= j && !less(a, i) { i++ }
-  __device__ int first_greater(int i, int j, int pv) const {
+  __device__ int first_greater(int i, int j, K pv) const {
     for (int b = i; b <= j; b += 32) {
       int idx = b + lane;
       unsigned m = __ballot_sync(FULL, idx <= j && pv < key[idx]);
@@ -58,7 +59,7 @@ struct WarpSorter {
     return j + 1;
   }
   // largest idx in [i, j] with !(pv < key[idx]) (i - 1 if none):    for i <= j && less(a, j) { j-- }
-  __device__ int last_not_greater(int i, int j, int pv) const {
+  __device__ int last_not_greater(int i, int j, K pv) const {
     for (int b = j; b >= i; b -= 32) {
       int idx = b - lane;
       unsigned m = __ballot_sync(FULL, idx >= i && !(pv < key[idx]));
@@ -68,10 +69,12 @@ struct WarpSorter {
   }
   // move element `from` to position `to` (to < from), shifting [to, from) right by one
   __device__ void rotate_right(int to, int from) {
-    const int ek = key[from], ev = val[from];
+    const K ek = key[from];
+    const int ev = val[from];
     for (int b0 = from; b0 > to; b0 -= 32) {
       const int i = b0 - lane;
-      int vk = 0, vv = 0;
+      K vk = 0;
+      int vv = 0;
       if (i > to) {
         vk = key[i - 1];
         vv = val[i - 1];
@@ -91,10 +94,12 @@ struct WarpSorter {
   }
   // move element `from` to position `to` (to > from), shifting (from, to] left by one
   __device__ void rotate_left(int from, int to) {
-    const int ek = key[from], ev = val[from];
+    const K ek = key[from];
+    const int ev = val[from];
     for (int b0 = from; b0 < to; b0 += 32) {
       const int i = b0 + lane;
-      int vk = 0, vv = 0;
+      K vk = 0;
+      int vv = 0;
       if (i < to) {
         vk = key[i + 1];
         vv = val[i + 1];
@@ -115,14 +120,15 @@ struct WarpSorter {
   // insertionSortCmpFunc on [a, b), b - a <= 32: insertion sort is stable, so the result is the stable rank order
   __device__ void insertion_sort(int a, int b) {
     const int n = b - a;
-    int k = 0, v = 0;
+    K k = 0;
+    int v = 0;
     if (lane < n) {
       k = key[a + lane];
       v = val[a + lane];
     }
     int rank = 0;
     for (int j = 0; j < n; j++) {
-      const int kj = __shfl_sync(FULL, k, j);
+      const K kj = __shfl_sync(FULL, k, j);
       rank += (kj < k || (kj == k && j < lane)) ? 1 : 0;
     }
     __syncwarp();
@@ -153,7 +159,7 @@ struct WarpSorter {
   }
   __device__ int partition(int a, int b, int pivot, bool* already) {
     swap(a, pivot);
-    const int pv = key[a];
+    const K pv = key[a];
     int i = a + 1, j = b - 1;
     i = first_not_less(i, j, pv);
     j = last_less(i, j, pv);
@@ -179,7 +185,7 @@ struct WarpSorter {
   }
   __device__ int partition_equal(int a, int b, int pivot) {
     swap(a, pivot);
-    const int pv = key[a];
+    const K pv = key[a];
     int i = a + 1, j = b - 1;
     for (;;) {
       i = first_greater(i, j, pv);
@@ -210,12 +216,12 @@ struct WarpSorter {
       if (b - a < 50) return false;
       swap(i, i - 1);
       if (i - a >= 2) {  // shift the smaller one to the left:  for j := i-1; j >= 1; j-- { if !less(j, j-1) break; swap }
-        const int x = key[i - 1];
+        const K x = key[i - 1];
         int stop = last_not_greater_from(i - 2, x);  // largest m in [0, i-2] with key[m] <= x, else -1
         if (stop + 1 < i - 1) rotate_right(stop + 1, i - 1);
       }
       if (b - i >= 2) {  // shift the greater one to the right: for j := i+1; j < b; j++ { if !less(j, j-1) break; swap }
-        const int x = key[i];
+        const K x = key[i];
         int stop = b;  // smallest m in [i+1, b) with !(key[m] < x), else b
         for (int b0 = i + 1; b0 < b; b0 += 32) {
           int idx = b0 + lane;
@@ -231,7 +237,7 @@ struct WarpSorter {
     return false;
   }
   // largest m in [0, hi] with key[m] <= x, else -1
-  __device__ int last_not_greater_from(int hi, int x) const {
+  __device__ int last_not_greater_from(int hi, K x) const {
     for (int b = hi; b >= 0; b -= 32) {
       int idx = b - lane;
       unsigned m = __ballot_sync(FULL, idx >= 0 && !(x < key[idx]));
@@ -291,7 +297,8 @@ struct WarpSorter {
       const int t = b0 + lane;
       if (t < n / 2) {
         const int i = a + t, j = b - 1 - t;
-        int tk = key[i], tv = val[i];
+        K tk = key[i];
+        int tv = val[i];
         key[i] = key[j];
         val[i] = val[j];
         key[j] = tk;
@@ -347,3 +354,4 @@ struct WarpSorter {
     }
   }
 };
+using WarpSorter = WarpSorterT<int>;

@@ -189,7 +189,8 @@ def config_c5(n_pods=10_000_000, n_pools=8, n_its=1000, app_replicas=1000, pools
     return b.build()
 
 
-def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_its=50):
+def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_its=50, catalog="generic",
+              spot_fraction=0.0, spot_to_spot=False, node_cpu=(0, 16)):
     """C4: a cluster of existing KWOK nodes full of running pods + the removal subsets to evaluate.
 
     Returns (EncodedProblem, ConsolInput-kwargs dict).  Nodes draw their instance type uniformly from the linux /
@@ -197,16 +198,34 @@ def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_
     consistent (available = allocatable - bound requests >= 0).  Candidates are the `n_candidates` nodes with the
     lowest disruption cost == fewest pods (utils/disruption/disruption.go:71-77 with default pod costs), and every
     subset of size 1..max_subset of them is one computeConsolidation call (100 + 4950 + 161700 = 166750).
+
+    `catalog="aws"` draws the nodes from the AWS-KWOK catalog instead and lets the NodePool launch any OS and capacity type, so
+    a replacement NodeClaim can carry more than 600 instance types (the price-ordered truncation of
+    scheduler.go:361-379); `spot_fraction` of the nodes run on spot capacity (spot-to-spot rules, consolidation.go:236-316).
     """
     b = ProblemBuilder()
-    its = kwok.generic_instance_types()[:n_its]
+    aws = catalog == "aws"
+    its = kwok.aws_instance_types(n_its) if aws else kwok.generic_instance_types()[:n_its]
     for it in its:
         b.add_instance_type(it)
-    b.add_nodepool(default_nodepool(), list(range(len(its))))
-    linux = [i for i, it in enumerate(its) if it.name.endswith("-linux")]
+    if aws:
+        b.add_nodepool(NodePool(name="default", requirements=[
+            NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "In", ("on-demand", "spot"))]), list(range(len(its))))
+    else:
+        b.add_nodepool(default_nodepool(), list(range(len(its))))
+
+    def _os(it):
+        return [r.values[0] for r in it.requirements if r.key == OS_LABEL][0]
+
+    def _arch(it):
+        return [r.values[0] for r in it.requirements if r.key == ARCH_LABEL][0]
+    linux = [i for i, it in enumerate(its)
+             if _os(it) == "linux" and (not aws or node_cpu[0] <= int(it.capacity["cpu"]) <= node_cpu[1])]
+    zones = kwok.AWS_ZONES if aws else kwok.KWOK_ZONES
     dn = draws(n_nodes, 2, SEED + 10)
     node_it = np.array(linux)[(dn[:, 0] % np.uint64(len(linux))).astype(int)]
     node_zone = (dn[:, 1] % np.uint64(4)).astype(int)
+    node_spot = (draws(n_nodes, 1, SEED + 12)[:, 0] % np.uint64(1000)).astype(int) < int(1000 * spot_fraction)
     from .model import quantity_units
     R = ["cpu", "memory", "pods", "ephemeral-storage"]
     alloc = np.zeros((n_nodes, 4), np.int64)
@@ -240,9 +259,10 @@ def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_
             table[c, m] = b.pod_class(Pod(requests=_requests(c, m)))
     for n in range(n_nodes):
         it = its[node_it[n]]
-        zone = kwok.KWOK_ZONES[node_zone[n]]
-        labels = {HOSTNAME_LABEL: f"node-{n:05d}", ZONE_LABEL: zone, CAPACITY_TYPE_LABEL: "on-demand",
-                  OS_LABEL: "linux", ARCH_LABEL: it.name.split("-")[2], NODEPOOL_LABEL: "default",
+        zone = zones[node_zone[n]]
+        labels = {HOSTNAME_LABEL: f"node-{n:05d}", ZONE_LABEL: zone,
+                  CAPACITY_TYPE_LABEL: "spot" if node_spot[n] else "on-demand",
+                  OS_LABEL: "linux", ARCH_LABEL: _arch(it), NODEPOOL_LABEL: "default",
                   "node.kubernetes.io/instance-type": it.name}
         avail = {name: int(alloc[n, r] - used[n, r]) for r, name in enumerate(R)}
         avail["cpu"] = f"{avail['cpu']}m"
@@ -277,8 +297,9 @@ def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_
                     subsets.append((i, j, l))
     sub_off = np.concatenate([[0], np.cumsum([len(s) for s in subsets])]).astype(np.int32)
     sub_nodes = np.array([cand[i] for s in subsets for i in s], np.int32)
-    consol = dict(node_pod_off=node_pod_off, node_it=node_it.astype(np.int32), node_is_spot=np.zeros(n_nodes, np.uint8),
-                  n_subsets=len(subsets), subset_off=sub_off, subset_nodes=sub_nodes, spot_to_spot_enabled=0,
+    consol = dict(node_pod_off=node_pod_off, node_it=node_it.astype(np.int32), node_is_spot=node_spot.astype(np.uint8),
+                  n_subsets=len(subsets), subset_off=sub_off, subset_nodes=sub_nodes,
+                  spot_to_spot_enabled=int(spot_to_spot),
                   capacity_type_key=enc.key_id(CAPACITY_TYPE_LABEL),
                   ct_reserved=enc.value_id(CAPACITY_TYPE_LABEL, "reserved"),
                   ct_spot=enc.value_id(CAPACITY_TYPE_LABEL, "spot"),

@@ -83,7 +83,7 @@ def consolidation_case(seed):
         n.pods = plain[:k]
     names = [n.name for n in nodes]
     sets = [rng.sample(names, rng.randint(1, min(3, len(names)))) for _ in range(rng.randint(1, 12))]
-    return pools, per_pool, nodes, sets
+    return pools, per_pool, nodes, sets, rng.random() < 0.5  # ... and whether spot-to-spot consolidation is enabled
 
 
 @pytest.mark.gpu
@@ -91,17 +91,17 @@ def test_fuzz_consolidation_parity_gpu():
     from karpenter_b200.disruption import Consolidation
     bad, ran = [], 0
     for seed in range(200):
-        pools, per_pool, nodes, sets = consolidation_case(seed)
-        orc = Consolidation(pools, per_pool, nodes, backend=oracle_lib.consolidate)
+        pools, per_pool, nodes, sets, s2s = consolidation_case(seed)
+        orc = Consolidation(pools, per_pool, nodes, spot_to_spot=s2s, backend=oracle_lib.consolidate)
         try:
             orc.compute(sets)
         except RuntimeError:
             continue
-        gpu = Consolidation(pools, per_pool, nodes)
+        gpu = Consolidation(pools, per_pool, nodes, spot_to_spot=s2s)
         try:
             gpu.compute(sets)
         except _native.SolverError as e:
-            if e.code == 5:  # KP_ERR_UNSUPPORTED: > 600 types / spot-to-spot / topology on the evicted pods
+            if e.code == 5:  # KP_ERR_UNSUPPORTED: topology constraints on the evicted pods
                 continue
             bad.append((seed, str(e)))
             continue
@@ -120,9 +120,9 @@ def test_consolidation_generator_on_oracle():
     from karpenter_b200.disruption import Consolidation
     decisions = collections.Counter()
     for seed in range(60):
-        pools, per_pool, nodes, sets = consolidation_case(seed)
+        pools, per_pool, nodes, sets, s2s = consolidation_case(seed)
         try:
-            for c in Consolidation(pools, per_pool, nodes, backend=oracle_lib.consolidate).compute(sets):
+            for c in Consolidation(pools, per_pool, nodes, spot_to_spot=s2s, backend=oracle_lib.consolidate).compute(sets):
                 decisions[c.decision] += 1
         except RuntimeError:
             decisions["rejected"] += 1

@@ -156,3 +156,50 @@ def test_deadline_returns_partial_results(handle):
     placed = part["pod_target"] != -1
     assert 0 < placed.sum() < (full["pod_target"] != -1).sum()
     assert np.array_equal(part["pod_target"][placed], full["pod_target"][placed])
+
+
+def _expensive_cluster(spot: bool):
+    """Three full, expensive nodes of the AWS-KWOK catalog, one tiny pod each, a NodePool that may launch any of the
+    1000 catalog rows: the single replacement NodeClaim starts with > 600 instance types, so SimulateScheduling's
+    TruncateInstanceTypes (scheduler.go:361-379) cuts it to the 600 cheapest -- with price ties between the linux and
+    windows rows of the same type right at the cut."""
+    from karpenter_b200 import kwok
+    from karpenter_b200.disruption import Consolidation
+    from karpenter_b200.model import (ARCH_LABEL, CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, INSTANCE_TYPE_LABEL, NODEPOOL_LABEL,
+                                      OS_LABEL, ZONE_LABEL, NodePool, NodeSelectorRequirement, Pod, StateNode)
+    its = kwok.aws_instance_types(1000)
+    big = sorted((it for it in its if [r.values[0] for r in it.requirements if r.key == OS_LABEL][0] == "linux"),
+                 key=lambda it: -int(it.capacity["cpu"]))[:3]
+    pool = NodePool(name="default", requirements=[NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "In", ("on-demand", "spot"))])
+    nodes = []
+    for i, it in enumerate(big):
+        arch = [r.values[0] for r in it.requirements if r.key == ARCH_LABEL][0]
+        labels = {HOSTNAME_LABEL: f"node-{i}", ZONE_LABEL: kwok.AWS_ZONES[i % 4], OS_LABEL: "linux", ARCH_LABEL: arch,
+                  CAPACITY_TYPE_LABEL: "spot" if spot else "on-demand", NODEPOOL_LABEL: "default",
+                  INSTANCE_TYPE_LABEL: it.name}
+        cap = dict(it.capacity)
+        cap["nodes"] = 1
+        nodes.append(StateNode(name=f"node-{i}", labels=labels, available={"cpu": "0", "memory": 0, "pods": 0},
+                               capacity=cap, nodepool="default", instance_type=it.name,
+                               pods=[Pod(name=f"p{i}", uid=i + 1, requests={"cpu": "100m", "memory": "64Mi"})]))
+    sets = [["node-0"], ["node-1"], ["node-0", "node-1"], ["node-0", "node-1", "node-2"]]
+    return pool, its, nodes, sets, Consolidation
+
+
+@pytest.mark.parametrize("spot,enabled", [(False, False), (True, True), (True, False)])
+def test_consolidation_truncates_to_600_cheapest_types(spot, enabled):
+    pool, its, nodes, sets, Consolidation = _expensive_cluster(spot)
+    orc = Consolidation([pool], {"default": its}, nodes, spot_to_spot=enabled, backend=oracle_lib.consolidate)
+    want = orc.compute(sets)
+    gpu = Consolidation([pool], {"default": its}, nodes, spot_to_spot=enabled)
+    try:
+        got = gpu.compute(sets)
+    finally:
+        gpu.close()
+    for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+        assert np.array_equal(gpu.raw[k], orc.raw[k]), k
+    assert got == want
+    if not spot:
+        assert any(len(c.replacement_instance_types) == 600 for c in want)  # the cut really happened
+    elif enabled:
+        assert len(want[0].replacement_instance_types) == 15                # single-node spot-to-spot: 15 cheapest
