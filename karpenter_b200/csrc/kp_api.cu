@@ -863,8 +863,8 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   if (rc != KP_OK) return rc;
   HostTables& t = h->host;
   KpDev& d = h->dev;
-  if (t.G > 0) return h->err = "consolidation with topology constraints is not built yet", KP_ERR_UNSUPPORTED;
   const int K = t.K, R = t.R, ITW = t.ITW, E = t.E, N = t.N, T = t.T;
+  const bool general = t.G > 0;  // the evicted pods carry topology constraints: one full solve per candidate set
   auto t_begin = std::chrono::steady_clock::now();
   // ---- host-side constants of the decision step
   auto ki = [&](int k) { return KeyInfo{t.val_int.data() + (size_t)k * 64, t.val_isint[k], t.key_univ[k]}; };
@@ -903,6 +903,148 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
       if (ok) ctmask[dd] |= 1 << i;
     }
   }
+  // WorstLaunchPrice lists (see KpConsol)
+  std::vector<int32_t> wl_off((size_t)T * 3 + 1, 0), wl_set;
+  std::vector<double> wl_price;
+  for (int ti = 0; ti < T; ti++)
+    for (int ci = 0; ci < 3; ci++) {
+      std::vector<std::pair<double, int>> ent;
+      for (int o = p->it_off_off[ti]; o < p->it_off_off[ti + 1]; o++)
+        if (p->off_available[o] && ((ctmask[t.off_set[o]] >> ci) & 1)) ent.push_back({p->off_price[o], t.off_set[o]});
+      std::stable_sort(ent.begin(), ent.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
+        return a.first > b.first;
+      });
+      for (auto& e : ent) {
+        wl_price.push_back(e.first);
+        wl_set.push_back(e.second);
+      }
+      wl_off[(size_t)ti * 3 + ci + 1] = (int32_t)wl_set.size();
+    }
+  if (wl_set.empty()) {
+    wl_set.push_back(0);
+    wl_price.push_back(0);
+  }
+  // OrderByPrice lists: available offerings per instance type, cheapest first
+  std::vector<int32_t> ml_off((size_t)T + 1, 0), ml_set;
+  std::vector<double> ml_price;
+  for (int ti = 0; ti < T; ti++) {
+    std::vector<std::pair<double, int>> ent;
+    for (int o = p->it_off_off[ti]; o < p->it_off_off[ti + 1]; o++)
+      if (p->off_available[o]) ent.push_back({p->off_price[o], t.off_set[o]});
+    std::stable_sort(ent.begin(), ent.end(),
+                     [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });
+    for (auto& e : ent) {
+      ml_price.push_back(e.first);
+      ml_set.push_back(e.second);
+    }
+    ml_off[(size_t)ti + 1] = (int32_t)ml_set.size();
+  }
+  if (ml_set.empty()) {
+    ml_set.push_back(0);
+    ml_price.push_back(0);
+  }
+  // price tables and decision constants of the device side (both paths)
+  auto upload_prices = [&](KpConsol& q) -> int {
+    q.ct_key = in->capacity_type_key;
+    q.ct_spot = in->ct_spot;
+    q.ct_order_valid = ct_valid;
+    q.spot_to_spot_enabled = in->spot_to_spot_enabled;
+    q.T = T;
+    CK(up(h, &q.node_price, node_price));
+    uint8_t* u8;
+    CK(up_raw(h, &u8, in->node_is_spot, (size_t)E));
+    q.node_is_spot = u8;
+    CK(up(h, &q.ml_off, ml_off));
+    CK(up(h, &q.ml_set, ml_set));
+    CK(up(h, &q.ml_price, ml_price));
+    CK(up(h, &q.wl_off, wl_off));
+    CK(up(h, &q.wl_set, wl_set));
+    CK(up(h, &q.wl_price, wl_price));
+    CK(zeros(h, &q.sort_key, (size_t)std::max(T, 1)));  // one warp slot; the fast path re-allocates per slot below
+    CK(zeros(h, &q.sort_val, (size_t)std::max(T, 1)));
+    CK(zeros(h, &q.sort_bits, (size_t)std::max(ITW, 1)));
+    return KP_OK;
+  };
+  for (int s = 0; s < S; s++)
+    for (int i = in->subset_off[s]; i < in->subset_off[s + 1]; i++)
+      if (in->subset_nodes[i] < 0 || in->subset_nodes[i] >= E) return h->err = "subset node out of range", KP_ERR_INVALID;
+  if (general) {
+    // ---- general path: a candidate set is SimulateScheduling over its own stateNodes / bound pods / pending pods
+    // (helpers.go:51-142) -> a derived kp_problem -> an ordinary kp_solve on the device, then computeConsolidation
+    out->n_subsets = S;
+    out->it_words = ITW;
+    out->decision = (uint8_t*)calloc(S ? S : 1, 1);
+    out->replacement_its = (uint64_t*)calloc((size_t)(S ? S : 1) * (ITW ? ITW : 1), sizeof(uint64_t));
+    out->n_new_claims = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
+    out->n_unscheduled = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
+    double total_ms = 0;
+    std::vector<uint8_t> is_cand(std::max(E, 1), 0), flags(std::max(E, 1), 0);
+    for (int s = 0; s < S; s++) {
+      const int so = in->subset_off[s], sn = in->subset_off[s + 1] - so;
+      std::fill(is_cand.begin(), is_cand.end(), 0);
+      for (int i = 0; i < sn; i++) is_cand[in->subset_nodes[so + i]] = 1;
+      for (int n = 0; n < E; n++)
+        flags[n] = is_cand[n] ? (uint8_t)(p->node_flags[n] & ~KP_NODE_SCHEDULABLE) : p->node_flags[n];
+      std::vector<int32_t> pod_class, run_class(p->run_class, p->run_class + p->n_running),
+          run_node(p->run_node, p->run_node + p->n_running);
+      std::vector<int64_t> creation;
+      std::vector<uint64_t> uid_hi, uid_lo;
+      for (int n = 0; n < E; n++)
+        for (int j = in->node_pod_off[n]; j < in->node_pod_off[n + 1]; j++) {
+          if (is_cand[n]) {
+            pod_class.push_back(p->pod_class[j]);
+            creation.push_back(p->pod_creation ? p->pod_creation[j] : 0);
+            uid_hi.push_back(p->pod_uid_hi[j]);
+            uid_lo.push_back(p->pod_uid_lo[j]);
+          } else {  // still running where it is: counted by the topology
+            run_class.push_back(p->pod_class[j]);
+            run_node.push_back(n);
+          }
+        }
+      if (pod_class.empty()) {  // nothing to reschedule: every pod is "placed", no NodeClaim
+        out->decision[s] = KP_DECISION_DELETE;
+        continue;
+      }
+      kp_problem sp = *p;
+      sp.node_flags = flags.data();
+      sp.n_pods = (int64_t)pod_class.size();
+      sp.pod_class = pod_class.data();
+      sp.pod_creation = creation.data();
+      sp.pod_uid_hi = uid_hi.data();
+      sp.pod_uid_lo = uid_lo.data();
+      sp.n_running = (int64_t)run_class.size();
+      sp.run_class = run_class.data();
+      sp.run_node = run_node.data();
+      rc = do_upload(h, &sp, (int)std::max<int64_t>(sp.n_pods, 1));
+      if (rc != KP_OK) return rc;
+      KpConsol q;
+      memset(&q, 0, sizeof(q));
+      rc = upload_prices(q);
+      if (rc != KP_OK) return rc;
+      int32_t* d_snodes;
+      CK(up_raw(h, &d_snodes, in->subset_nodes + so, (size_t)sn));
+      CK(zeros(h, &q.decision, 1));
+      CK(zeros(h, &q.replacement_its, (size_t)std::max(ITW, 1)));
+      CK(zeros(h, &q.n_new_claims, 1));
+      CK(zeros(h, &q.n_unscheduled, 1));
+      rc = run_solve(h);
+      if (rc != KP_OK) return rc;
+      int32_t status = 0;
+      CK(cudaMemcpy(&status, h->dev.status, 4, cudaMemcpyDeviceToHost));
+      if (status != KP_OK) return h->err = "consolidation simulation failed", status;
+      total_ms += h->stats.solve_ms;
+      k_decide<<<1, 32, 0, h->stream>>>(h->dev, q, sn, d_snodes, 0);
+      CK(cudaStreamSynchronize(h->stream));
+      CK(cudaGetLastError());
+      CK(cudaMemcpy(out->decision + s, q.decision, 1, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(out->replacement_its + (size_t)s * ITW, q.replacement_its, (size_t)ITW * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(out->n_new_claims + s, q.n_new_claims, 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(out->n_unscheduled + s, q.n_unscheduled, 4, cudaMemcpyDeviceToHost));
+    }
+    out->solve_ms = total_ms;
+    h->stats.solve_ms = total_ms;
+    return KP_OK;
+  }
   int capq = 1;
   for (int s = 0; s < S; s++) {
     int n = 0;
@@ -918,10 +1060,6 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   memset(&q, 0, sizeof(q));
   q.n_subsets = S;
   q.capq = capq;
-  q.ct_key = in->capacity_type_key;
-  q.ct_spot = in->ct_spot;
-  q.ct_order_valid = ct_valid;
-  q.spot_to_spot_enabled = in->spot_to_spot_enabled;
   int n_sub_nodes = S ? in->subset_off[S] : 0;
   int32_t* tmp32;
   CK(up_raw(h, &tmp32, in->subset_off, (size_t)S + 1));
@@ -934,11 +1072,7 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   CK(zeros(h, &tmp32, (size_t)std::max<int64_t>(h->P, 1)));
   int32_t* d_rank = tmp32;
   q.pod_rank = d_rank;
-  CK(up(h, &q.node_price, node_price));
   {
-    uint8_t* u8;
-    CK(up_raw(h, &u8, in->node_is_spot, (size_t)E));
-    q.node_is_spot = u8;
     std::vector<int32_t> ntm(std::max(E, 1), -1);
     std::vector<int64_t> ncap((size_t)std::max(E, 1) * R, 0);
     for (int n = 0; n < E; n++) {
@@ -949,53 +1083,8 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
     CK(up(h, &q.node_tmpl, ntm));
     CK(up(h, &q.node_capacity, ncap));
     CK(up(h, &q.tmpl_remaining0, t.tmpl_remaining));
-    // WorstLaunchPrice lists (see KpConsol)
-    std::vector<int32_t> wl_off((size_t)T * 3 + 1, 0), wl_set;
-    std::vector<double> wl_price;
-    for (int ti = 0; ti < T; ti++)
-      for (int ci = 0; ci < 3; ci++) {
-        std::vector<std::pair<double, int>> ent;
-        for (int o = p->it_off_off[ti]; o < p->it_off_off[ti + 1]; o++)
-          if (p->off_available[o] && ((ctmask[t.off_set[o]] >> ci) & 1)) ent.push_back({p->off_price[o], t.off_set[o]});
-        std::stable_sort(ent.begin(), ent.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) {
-          return a.first > b.first;
-        });
-        for (auto& e : ent) {
-          wl_price.push_back(e.first);
-          wl_set.push_back(e.second);
-        }
-        wl_off[(size_t)ti * 3 + ci + 1] = (int32_t)wl_set.size();
-      }
-    if (wl_set.empty()) {
-      wl_set.push_back(0);
-      wl_price.push_back(0);
-    }
-    // OrderByPrice lists: available offerings per instance type, cheapest first
-    std::vector<int32_t> ml_off((size_t)T + 1, 0), ml_set;
-    std::vector<double> ml_price;
-    for (int ti = 0; ti < T; ti++) {
-      std::vector<std::pair<double, int>> ent;
-      for (int o = p->it_off_off[ti]; o < p->it_off_off[ti + 1]; o++)
-        if (p->off_available[o]) ent.push_back({p->off_price[o], t.off_set[o]});
-      std::stable_sort(ent.begin(), ent.end(),
-                       [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });
-      for (auto& e : ent) {
-        ml_price.push_back(e.first);
-        ml_set.push_back(e.second);
-      }
-      ml_off[(size_t)ti + 1] = (int32_t)ml_set.size();
-    }
-    if (ml_set.empty()) {
-      ml_set.push_back(0);
-      ml_price.push_back(0);
-    }
-    CK(up(h, &q.ml_off, ml_off));
-    CK(up(h, &q.ml_set, ml_set));
-    CK(up(h, &q.ml_price, ml_price));
-    q.T = T;
-    CK(up(h, &q.wl_off, wl_off));
-    CK(up(h, &q.wl_set, wl_set));
-    CK(up(h, &q.wl_price, wl_price));
+    rc = upload_prices(q);
+    if (rc != KP_OK) return rc;
   }
   // ---- launch geometry: as many resident warps as the GPU holds, each with a private scratch slot
   const size_t budget = 200 * 1024;

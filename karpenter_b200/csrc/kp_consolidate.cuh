@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev 
     d.counters[4] = I.slow_sorts;
     d.counters[5] = I.scan_chunks;
     d.counters[6] = I.evals;
+    d.counters[7] = I.n_unsched;
+    d.counters[8] = I.n_uninit;
   }
 }
 
@@ -333,6 +335,170 @@ __device__ __forceinline__ unsigned offering_ok_mask(const KpDev& d, const Slot*
     }
   }
   return __ballot_sync(FULL, ok);
+}
+
+// computeConsolidation (consolidation.go:136-229) for one simulated candidate set: `unscheduled` pods could not be
+// placed (or only on uninitialized nodes), `n_new` NodeClaims were opened; claim 0's row (requirement slots, instance
+// types) is read through the c_* pointers.  One warp; `slot` selects the warp's sort scratch in q; result row `s`.
+__device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q, size_t slot, Slot* scratch,
+                                              const uint8_t* c_sflags, const uint64_t* c_smask, const int64_t* c_sgte,
+                                              const int64_t* c_slte, const uint64_t* c_its, int sn, const int32_t* snodes,
+                                              int unscheduled, int n_new, int s, int lane) {
+  const int K = d.K, ITW = d.ITW;
+  int decision = KP_DECISION_NOOP;
+  uint64_t rep = 0;  // lane w: word w of the replacement instance types
+  if (!unscheduled) {
+    if (n_new == 0) {
+      decision = KP_DECISION_DELETE;
+    } else if (n_new == 1) {
+      // the single new NodeClaim: requirements (hostname already dropped), instance types
+      Slot S = lane < K ? load_slot(c_sflags, c_smask, c_sgte, c_slte, (size_t)lane, d.has_bounds) : slot_absent();
+      const uint64_t its = lane < ITW ? c_its[lane] : 0ull;
+      int n_its = lane < ITW ? __popcll(its) : 0;
+      for (int o = 16; o; o >>= 1) n_its += __shfl_xor_sync(FULL, n_its, o);
+      // getCandidatePrices (consolidation.go:319-337)
+      double price = 0;
+      bool zero = false, all_spot = true;
+      for (int i = 0; i < sn; i++) {
+        const double np = q.node_price[snodes[i]];
+        if (np < 0) zero = true;
+        price += np;
+        if (!q.node_is_spot[snodes[i]]) all_spot = false;
+      }
+      if (zero) price = 0.0;
+      bool spot_ok = false;
+      if (q.ct_key >= 0 && q.ct_spot >= 0) {
+        const uint32_t f = __shfl_sync(FULL, S.f, q.ct_key);
+        const uint64_t m = __shfl_sync(FULL, S.m, q.ct_key);
+        const int64_t g = __shfl_sync(FULL, S.gte, q.ct_key), l = __shfl_sync(FULL, S.lte, q.ct_key);
+        spot_ok = slot_has(key_info(d, q.ct_key), Slot{f, m, g, l}, q.ct_spot);
+      }
+      if (lane < K) scratch[lane] = S;
+      __syncwarp();
+      unsigned okmask = offering_ok_mask(d, scratch, lane);
+      const bool spot_path = all_spot && spot_ok;
+      uint64_t cur = its;  // lane w: word w of the NodeClaim's instance types as they go through the steps below
+      // ---- OrderByPrice + Truncate(600) (helpers.go:120, scheduler.go:361-379, types.go:238-257,339-351).  The order
+      // only matters when it truncates, or for the 15-cheapest rule of single-node spot-to-spot consolidation.
+      double* sk = q.sort_key + slot * (size_t)q.T;
+      int32_t* sv = q.sort_val + slot * (size_t)q.T;
+      unsigned long long* sb = q.sort_bits + slot * (size_t)ITW;
+      int n_ord = 0;
+      const bool need_order = n_its > 600 || (spot_path && q.spot_to_spot_enabled);
+      if (need_order) {
+        const int cw = lane < ITW ? __popcll(cur) : 0;
+        int pre = cw;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(FULL, pre, o);
+          if (lane >= o) pre += t;
+        }
+        int at = pre - cw;  // provider order == ascending instance type index
+        for (uint64_t bits = lane < ITW ? cur : 0ull; bits;) {
+          const int b = __ffsll((long long)bits) - 1;
+          bits &= bits - 1;
+          const int t = lane * 64 + b;
+          double mp = 1.7976931348623157e308;
+          for (int e = q.ml_off[t]; e < q.ml_off[t + 1]; e++)
+            if ((okmask >> q.ml_set[e]) & 1u) {
+              mp = q.ml_price[e];
+              break;
+            }
+          sk[at] = mp;
+          sv[at] = t;
+          at++;
+        }
+        n_ord = n_its;
+        __syncwarp();
+        WarpSorterT<double> srt{sk, sv, lane};
+        srt.pdqsort(0, n_ord, WarpSorterT<double>::bits_len((unsigned long long)n_ord));
+        if (n_ord > 600) {
+          n_ord = 600;
+          if (lane < ITW) sb[lane] = 0ull;
+          __syncwarp();
+          for (int i = lane; i < n_ord; i += 32) atomicOr(&sb[sv[i] >> 6], 1ull << (sv[i] & 63));
+          __syncwarp();
+          cur = lane < ITW ? sb[lane] : 0ull;
+        }
+      }
+      if (spot_path && !q.spot_to_spot_enabled) {
+        decision = KP_DECISION_NOOP;  // computeSpotToSpotConsolidation needs the feature gate (consolidation.go:239)
+      } else {
+        if (spot_path) {  // restrict the claim to spot (consolidation.go:252-257) and drop types without such an offering
+          if (lane == q.ct_key)
+            scratch[lane] = slot_add(key_info(d, lane), scratch[lane], Slot{SF_PRESENT, 1ull << q.ct_spot, 0, 0});
+          __syncwarp();
+          okmask = offering_ok_mask(d, scratch, lane);
+          uint64_t keep = 0;
+          for (uint64_t bits = lane < ITW ? cur : 0ull; bits;) {
+            const int b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            const int t = lane * 64 + b;
+            for (int e = q.ml_off[t]; e < q.ml_off[t + 1]; e++)
+              if ((okmask >> q.ml_set[e]) & 1u) {
+                keep |= 1ull << b;
+                break;
+              }
+          }
+          cur = keep;
+        }
+        // RemoveInstanceTypeOptionsByPriceAndMinValues (nodeclaim.go:309-318): keep WorstLaunchPrice < price
+        if (lane < ITW) {
+          for (uint64_t bits = cur; bits;) {
+            const int b = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            const int t = lane * 64 + b;
+            double worst = 1.7976931348623157e308;
+            for (int ci = 0; ci < 3 && worst > 1e308; ci++) {  // reserved -> spot -> on-demand (types.go:480-491)
+              if (q.ct_key < 0 || !((q.ct_order_valid >> ci) & 1)) continue;
+              for (int e = q.wl_off[t * 3 + ci]; e < q.wl_off[t * 3 + ci + 1]; e++)
+                if ((okmask >> q.wl_set[e]) & 1u) {
+                  worst = q.wl_price[e];
+                  break;
+                }
+            }
+            if (worst < price) rep |= 1ull << b;
+          }
+        }
+        bool any = __any_sync(FULL, rep != 0);
+        if (any && spot_path && sn == 1) {
+          // single-node spot-to-spot: at least 15 cheaper types, and only the 15 cheapest go out (consolidation.go:283-312)
+          int total = lane < ITW ? __popcll(rep) : 0;
+          for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+          if (total < 15) {
+            any = false;
+          } else {
+            if (lane < ITW) sb[lane] = rep;
+            __syncwarp();
+            uint64_t first15 = 0;  // lane w collects its words' bits; walk the price order 32 entries at a time
+            int taken = 0;
+            for (int b0 = 0; b0 < n_ord && taken < 15; b0 += 32) {
+              const int i = b0 + lane;
+              const int t = i < n_ord ? sv[i] : 0;
+              const bool in = i < n_ord && ((sb[t >> 6] >> (t & 63)) & 1ull);
+              const unsigned m = __ballot_sync(FULL, in);
+              const int rank = taken + __popc(m & ((1u << lane) - 1));
+              const bool take = in && rank < 15;
+              for (int l = 0; l < 32; l++) {  // hand each taken type to the lane that owns its word
+                const int tt = __shfl_sync(FULL, take ? t : -1, l);
+                if (tt >= 0 && (tt >> 6) == lane) first15 |= 1ull << (tt & 63);
+              }
+              taken += __popc(m);
+            }
+            rep = first15;
+          }
+        }
+        if (any) decision = KP_DECISION_REPLACE;
+      }
+    }
+  }
+  if (decision != KP_DECISION_REPLACE) rep = 0;
+  if (lane < ITW) q.replacement_its[(size_t)s * ITW + lane] = rep;
+  if (lane == 0) {
+    q.decision[s] = (uint8_t)decision;
+    q.n_new_claims[s] = n_new;
+    q.n_unscheduled[s] = unscheduled;
+  }
+  __syncwarp();
 }
 
 #define CONSOL_WARPS 8
@@ -461,161 +627,17 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_
       break;
     }
     // ---- computeConsolidation (consolidation.go:136-229)
-    const int unscheduled = I.n_unsched + I.n_uninit;
-    const int n_new = I.n_claims;
-    int decision = KP_DECISION_NOOP;
-    uint64_t rep = 0;  // lane w: word w of the replacement instance types
-    if (!unscheduled) {
-      if (n_new == 0) {
-        decision = KP_DECISION_DELETE;
-      } else if (n_new == 1) {
-        // the single new NodeClaim: requirements (hostname already dropped), instance types
-        Slot S = lane < K ? load_slot(I.c_sflags, I.c_smask, I.c_sgte, I.c_slte, (size_t)lane, d.has_bounds) : slot_absent();
-        const uint64_t its = lane < ITW ? I.c_its[lane] : 0ull;
-        int n_its = lane < ITW ? __popcll(its) : 0;
-        for (int o = 16; o; o >>= 1) n_its += __shfl_xor_sync(FULL, n_its, o);
-        // getCandidatePrices (consolidation.go:319-337)
-        double price = 0;
-        bool zero = false, all_spot = true;
-        for (int i = 0; i < sn; i++) {
-          const double np = q.node_price[snodes[i]];
-          if (np < 0) zero = true;
-          price += np;
-          if (!q.node_is_spot[snodes[i]]) all_spot = false;
-        }
-        if (zero) price = 0.0;
-        bool spot_ok = false;
-        if (q.ct_key >= 0 && q.ct_spot >= 0) {
-          const uint32_t f = __shfl_sync(FULL, S.f, q.ct_key);
-          const uint64_t m = __shfl_sync(FULL, S.m, q.ct_key);
-          const int64_t g = __shfl_sync(FULL, S.gte, q.ct_key), l = __shfl_sync(FULL, S.lte, q.ct_key);
-          spot_ok = slot_has(key_info(d, q.ct_key), Slot{f, m, g, l}, q.ct_spot);
-        }
-        if (lane < K) W.scratch[lane] = S;
-        __syncwarp();
-        unsigned okmask = offering_ok_mask(d, W.scratch, lane);
-        const bool spot_path = all_spot && spot_ok;
-        uint64_t cur = its;  // lane w: word w of the NodeClaim's instance types as they go through the steps below
-        // ---- OrderByPrice + Truncate(600) (helpers.go:120, scheduler.go:361-379, types.go:238-257,339-351).  The order
-        // only matters when it truncates, or for the 15-cheapest rule of single-node spot-to-spot consolidation.
-        double* sk = q.sort_key + slot * (size_t)q.T;
-        int32_t* sv = q.sort_val + slot * (size_t)q.T;
-        unsigned long long* sb = q.sort_bits + slot * (size_t)ITW;
-        int n_ord = 0;
-        const bool need_order = n_its > 600 || (spot_path && q.spot_to_spot_enabled);
-        if (need_order) {
-          const int cw = lane < ITW ? __popcll(cur) : 0;
-          int pre = cw;
-          for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, pre, o);
-            if (lane >= o) pre += t;
-          }
-          int at = pre - cw;  // provider order == ascending instance type index
-          for (uint64_t bits = lane < ITW ? cur : 0ull; bits;) {
-            const int b = __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            const int t = lane * 64 + b;
-            double mp = 1.7976931348623157e308;
-            for (int e = q.ml_off[t]; e < q.ml_off[t + 1]; e++)
-              if ((okmask >> q.ml_set[e]) & 1u) {
-                mp = q.ml_price[e];
-                break;
-              }
-            sk[at] = mp;
-            sv[at] = t;
-            at++;
-          }
-          n_ord = n_its;
-          __syncwarp();
-          WarpSorterT<double> srt{sk, sv, lane};
-          srt.pdqsort(0, n_ord, WarpSorterT<double>::bits_len((unsigned long long)n_ord));
-          if (n_ord > 600) {
-            n_ord = 600;
-            if (lane < ITW) sb[lane] = 0ull;
-            __syncwarp();
-            for (int i = lane; i < n_ord; i += 32) atomicOr(&sb[sv[i] >> 6], 1ull << (sv[i] & 63));
-            __syncwarp();
-            cur = lane < ITW ? sb[lane] : 0ull;
-          }
-        }
-        if (spot_path && !q.spot_to_spot_enabled) {
-          decision = KP_DECISION_NOOP;  // computeSpotToSpotConsolidation needs the feature gate (consolidation.go:239)
-        } else {
-          if (spot_path) {  // restrict the claim to spot (consolidation.go:252-257) and drop types without such an offering
-            if (lane == q.ct_key)
-              W.scratch[lane] = slot_add(key_info(d, lane), W.scratch[lane], Slot{SF_PRESENT, 1ull << q.ct_spot, 0, 0});
-            __syncwarp();
-            okmask = offering_ok_mask(d, W.scratch, lane);
-            uint64_t keep = 0;
-            for (uint64_t bits = lane < ITW ? cur : 0ull; bits;) {
-              const int b = __ffsll((long long)bits) - 1;
-              bits &= bits - 1;
-              const int t = lane * 64 + b;
-              for (int e = q.ml_off[t]; e < q.ml_off[t + 1]; e++)
-                if ((okmask >> q.ml_set[e]) & 1u) {
-                  keep |= 1ull << b;
-                  break;
-                }
-            }
-            cur = keep;
-          }
-          // RemoveInstanceTypeOptionsByPriceAndMinValues (nodeclaim.go:309-318): keep WorstLaunchPrice < price
-          if (lane < ITW) {
-            for (uint64_t bits = cur; bits;) {
-              const int b = __ffsll((long long)bits) - 1;
-              bits &= bits - 1;
-              const int t = lane * 64 + b;
-              double worst = 1.7976931348623157e308;
-              for (int ci = 0; ci < 3 && worst > 1e308; ci++) {  // reserved -> spot -> on-demand (types.go:480-491)
-                if (q.ct_key < 0 || !((q.ct_order_valid >> ci) & 1)) continue;
-                for (int e = q.wl_off[t * 3 + ci]; e < q.wl_off[t * 3 + ci + 1]; e++)
-                  if ((okmask >> q.wl_set[e]) & 1u) {
-                    worst = q.wl_price[e];
-                    break;
-                  }
-              }
-              if (worst < price) rep |= 1ull << b;
-            }
-          }
-          bool any = __any_sync(FULL, rep != 0);
-          if (any && spot_path && sn == 1) {
-            // single-node spot-to-spot: at least 15 cheaper types, and only the 15 cheapest go out (consolidation.go:283-312)
-            int total = lane < ITW ? __popcll(rep) : 0;
-            for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
-            if (total < 15) {
-              any = false;
-            } else {
-              if (lane < ITW) sb[lane] = rep;
-              __syncwarp();
-              uint64_t first15 = 0;  // lane w collects its words' bits; walk the price order 32 entries at a time
-              int taken = 0;
-              for (int b0 = 0; b0 < n_ord && taken < 15; b0 += 32) {
-                const int i = b0 + lane;
-                const int t = i < n_ord ? sv[i] : 0;
-                const bool in = i < n_ord && ((sb[t >> 6] >> (t & 63)) & 1ull);
-                const unsigned m = __ballot_sync(FULL, in);
-                const int rank = taken + __popc(m & ((1u << lane) - 1));
-                const bool take = in && rank < 15;
-                for (int l = 0; l < 32; l++) {  // hand each taken type to the lane that owns its word
-                  const int tt = __shfl_sync(FULL, take ? t : -1, l);
-                  if (tt >= 0 && (tt >> 6) == lane) first15 |= 1ull << (tt & 63);
-                }
-                taken += __popc(m);
-              }
-              rep = first15;
-            }
-          }
-          if (any) decision = KP_DECISION_REPLACE;
-        }
-      }
-    }
-    if (decision != KP_DECISION_REPLACE) rep = 0;
-    if (lane < ITW) q.replacement_its[(size_t)s * ITW + lane] = rep;
-    if (lane == 0) {
-      q.decision[s] = (uint8_t)decision;
-      q.n_new_claims[s] = n_new;
-      q.n_unscheduled[s] = unscheduled;
-    }
-    __syncwarp();
+    consol_decide(d, q, slot, W.scratch, I.c_sflags, I.c_smask, I.c_sgte, I.c_slte, I.c_its, sn, snodes,
+                  I.n_unsched + I.n_uninit, I.n_claims, s, lane);
   }
+}
+
+// The general consolidation path (evicted pods carry topology constraints): every candidate set is a full
+// Scheduler.Solve of its own (fresh NewTopology, k_wsolve); this kernel then applies computeConsolidation to it.
+__global__ void __launch_bounds__(32) k_decide(KpDev d, KpConsol q, int sn, const int32_t* snodes, int s) {
+  __shared__ Slot scratch[KP_MAXK];
+  const int lane = threadIdx.x;
+  const int unscheduled = (int)(d.counters[7] + d.counters[8]);
+  consol_decide(d, q, 0, scratch, d.c_sflags, d.c_smask, d.c_sgte, d.c_slte, d.c_its, sn, snodes, unscheduled, *d.n_claims, s,
+                lane);
 }

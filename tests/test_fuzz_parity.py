@@ -79,8 +79,10 @@ def consolidation_case(seed):
     for n in nodes:
         n.running_pods = []
         k = rng.randint(0, 4)
-        plain = [p for p in fuzz.pods(rng, 12) if not (p.topology_spread_constraints or p.pod_affinity or p.pod_anti_affinity)]
-        n.pods = plain[:k]
+        cand = fuzz.pods(rng, 12)
+        if seed % 4:  # three seeds of four stay topology-free (one warp per candidate set); the fourth takes the general path
+            cand = [p for p in cand if not (p.topology_spread_constraints or p.pod_affinity or p.pod_anti_affinity)]
+        n.pods = cand[:k]
     names = [n.name for n in nodes]
     sets = [rng.sample(names, rng.randint(1, min(3, len(names)))) for _ in range(rng.randint(1, 12))]
     return pools, per_pool, nodes, sets, rng.random() < 0.5  # ... and whether spot-to-spot consolidation is enabled

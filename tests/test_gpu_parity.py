@@ -203,3 +203,36 @@ def test_consolidation_truncates_to_600_cheapest_types(spot, enabled):
         assert any(len(c.replacement_instance_types) == 600 for c in want)  # the cut really happened
     elif enabled:
         assert len(want[0].replacement_instance_types) == 15                # single-node spot-to-spot: 15 cheapest
+
+
+def test_more_than_64_requirement_signatures_and_request_vectors(handle):
+    """The failure / acceptance masks cache 64 requirement signatures and 64 request vectors; classes beyond that run
+    uncached.  144 distinct node-affinity terms x 80 distinct request vectors must still match the oracle."""
+    import itertools
+    import random
+    from karpenter_b200 import kwok
+    from karpenter_b200.model import (ARCH_LABEL, CAPACITY_TYPE_LABEL, ZONE_LABEL, NodePool, NodeSelectorRequirement, Pod)
+    from karpenter_b200.scheduler import Scheduler
+    rng = random.Random(5)
+    its = kwok.aws_instance_types(300)
+    zones = kwok.AWS_ZONES
+    terms = []
+    for k in range(0, 4):
+        for zs in itertools.combinations(zones, k):
+            for arch in (None, "x86_64", "arm64"):
+                for ct in (None, "spot", "on-demand"):
+                    t = []
+                    if zs:
+                        t.append(NodeSelectorRequirement(ZONE_LABEL, "NotIn", zs))
+                    if arch:
+                        t.append(NodeSelectorRequirement(ARCH_LABEL, "In", (arch,)))
+                    if ct:
+                        t.append(NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "In", (ct,)))
+                    terms.append(t)
+    assert len(terms) > 64
+    reqs = [{"cpu": f"{100 + 50 * i}m", "memory": f"{128 + 64 * (i % 7)}Mi"} for i in range(80)]
+    pods = [Pod(name=f"p{i}", uid=rng.getrandbits(100), requests=rng.choice(reqs),
+                node_affinity_required=[t] if (t := rng.choice(terms)) else []) for i in range(6000)]
+    pool = NodePool(name="default", requirements=[NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "In", ("spot", "on-demand"))])
+    enc = Scheduler([pool], {"default": its}).encode(pods)
+    assert_same(handle.solve(enc.problem), oracle_lib.solve(enc.problem), "many signatures ")

@@ -434,3 +434,30 @@ def test_mixed_schedulable_and_unschedulable(which):
     bad = pods(2, uid0=50, requests={"cpu": "100"})  # larger than every instance type
     r = run(which, ok + bad)
     assert {id(x) for x in bad} == set(r.pod_errors) and sum(len(c.pods) for c in r.new_node_claims) == 4
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_consolidation_replace_keeps_zonal_spread(which):  # consolidation_test.go:4333-4406
+    its = {it.name: it for it in fake.default_instance_types()}
+    d = its["default-instance-type"]
+    tsc = spread()  # zone, maxSkew 1, selector LABELS
+    p = pods(3, labels=LABELS, requests={"cpu": "1"}, topology_spread_constraints=tsc)
+    nodes = [_node(f"node-{i+1}", d, zone=f"test-zone-{i+1}", pod_list=p[i:i + 1]) for i in range(3)]
+    (cmd,) = consolidate(which, nodes, [["node-3"]])
+    # the evicted pod may only land in test-zone-3 (the other zones would skew 2:1:0): not on node-1 / node-2, so a
+    # cheaper replacement in that zone is launched
+    assert cmd.decision == "replace" and cmd.n_new_node_claims == 1 and cmd.n_unscheduled == 0
+    assert "small-instance-type" in cmd.replacement_instance_types
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_consolidation_wont_delete_when_anti_affinity_forbids(which):  # consolidation_test.go:4407-4467
+    its = {it.name: it for it in fake.default_instance_types()}
+    small = its["small-instance-type"]
+    anti = [PodAffinityTerm(LabelSelector.of(LABELS), HOSTNAME_LABEL)]
+    p = pods(3, labels=LABELS, requests={"cpu": "1"}, pod_anti_affinity=anti)
+    nodes = [_node(f"node-{i+1}", small, pod_list=p[i:i + 1]) for i in range(3)]
+    cmds = consolidate(which, nodes, [["node-1"], ["node-1", "node-2"]])
+    # the pod cannot join its peers; a new node of the cheapest type is not cheaper than the one it leaves
+    assert cmds[0].decision == "noop" and cmds[0].n_new_node_claims == 1
+    assert cmds[1].decision == "noop" and cmds[1].n_new_node_claims == 2
