@@ -136,6 +136,7 @@ class ProblemBuilder:
         self.extra_keys = set()
         self.claim_order_mode = 0
         self.pod_arrays = None
+        self.max_values_per_key = 64  # width of the per-key value mask; wider keys go through value compaction
 
     # ---- resources ----
     def res_index(self, name: str) -> int:
@@ -268,7 +269,34 @@ class ProblemBuilder:
                     values[r[0]].update(r[2])
         for n in self.nodes:
             values[HOSTNAME_LABEL].add(n["hostname"])
+        # Value compaction.  A key carries one 64-bit value mask, but keys like node.kubernetes.io/instance-type have one
+        # value per instance type.  Values that no pod / NodePool / offering / topology-filter requirement MENTIONS are
+        # indistinguishable to the algorithm (they only ever occur as In{v} on an instance type or a node label and are
+        # compared with sets of mentioned values or complements of them), so they collapse into one OTHER value.  Not
+        # applicable when the key is a topology key (domain counts are per value) or carries Gt / Lt bounds.
+        self.OTHER = "\uffff<any unmentioned value>"
+        value_map: Dict[str, Dict[str, str]] = {}
+        topo_keys = {t["key"] for c in self.class_rows for t in c["tscs"]}
+        for k in keys:
+            if k == HOSTNAME_LABEL or len(values[k]) <= self.max_values_per_key:
+                continue
+            bounded = any(r[0] == k and (r[3] is not None or r[4] is not None) for rows in self.reqsets.rows for r in rows)
+            if k in topo_keys or bounded:
+                continue  # stays too wide: the library answers KP_ERR_CAPACITY
+            mentioned = set()
+            for sd in seeds:
+                for r in self.reqsets.rows[sd]:
+                    if r[0] == k:
+                        mentioned.update(r[2])
+            if len(mentioned) >= 64:
+                continue
+            value_map[k] = {v: (v if v in mentioned else self.OTHER) for v in values[k]}
+            values[k] = mentioned | {self.OTHER}
         value_id = {k: {v: i for i, v in enumerate(sorted(vs))} for k, vs in values.items()}
+        for k, m in value_map.items():
+            ids = value_id[k]
+            value_id[k] = {v: ids[m[v]] for v in m}
+            value_id[k][self.OTHER] = ids[self.OTHER]
         key_value_off = [0]
         value_int, value_is_int = [], []
         for k in keys:
@@ -295,7 +323,7 @@ class ProblemBuilder:
                 rq_gte.append(gte or 0)
                 rq_lte.append(lte or 0)
                 rq_min.append(mv or 0)
-                rvals.extend(value_id[k][v] for v in vals)
+                rvals.extend(sorted({value_id[k][v] for v in vals}))  # a set: compaction may merge values
                 rv_off.append(len(rvals))
             rs_off.append(len(rq_key))
         P.set("n_reqsets", len(self.reqsets.rows))
