@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KP_ABI_VERSION 1
+#define KP_ABI_VERSION 2
 
 typedef enum kp_status {
   KP_OK = 0,
@@ -37,7 +37,7 @@ typedef enum kp_status {
   KP_ERR_INVALID = 2,      /* malformed problem */
   KP_ERR_CUDA = 3,         /* device / driver failure; message via kp_last_error */
   KP_ERR_CAPACITY = 4,     /* a compiled limit was exceeded (e.g. > KP_MAX_RESOURCES) */
-  KP_ERR_UNSUPPORTED = 5   /* feature of the reference not built yet (minValues, reserved offerings, preferences) */
+  KP_ERR_UNSUPPORTED = 5   /* feature of the reference not built yet (minValues, reserved offerings, host ports) */
 } kp_status;
 
 /* ---- requirement encoding --------------------------------------------------------------------------------------
@@ -186,6 +186,14 @@ typedef struct kp_problem {
   const int32_t* tsc_min_domains;    /* -1 == nil */
   const uint8_t* tsc_taint_policy;   /* 1 == Honor */
   const uint8_t* tsc_affinity_policy;/* 1 == Honor */
+  const uint8_t* tsc_preferred;      /* may be NULL. 1 == a preferred (soft) pod affinity / anti-affinity term or a
+                                        ScheduleAnyway spread: enforced like a required one until relaxed away
+                                        (topology.go:428-499), but a preferred anti-affinity term registers no inverse
+                                        group (topology.go:297-322) */
+  /* Preferences.Relax (preferences.go:38-146, scheduler.go:438-469): class of the pod after ONE relaxation step, -1 when
+   * nothing is left to relax.  A pod that fails with class X is retried at once as class_relax_next[X], and so on; the
+   * queue keeps the original class.  May be NULL (no soft constraints anywhere). */
+  const int32_t* class_relax_next;   /* [n_classes] */
 
   /* ---- pods to schedule ---- */
   int64_t n_pods;

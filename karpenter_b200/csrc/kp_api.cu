@@ -256,6 +256,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(up(h, &d.cls_req, t.cls_req));
   CK(up(h, &d.cls_rs, t.cls_rs));
   CK(up(h, &d.cls_tolset, t.cls_tolset));
+  CK(up(h, &d.cls_relax, t.cls_relax));
   CK(up(h, &d.cls_match, t.cls_match));
   CK(up(h, &d.cls_rec, t.cls_rec));
   {  // class rows (one indirection less on the per-pod path)

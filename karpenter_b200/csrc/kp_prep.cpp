@@ -342,6 +342,9 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   h.cls_rs.assign(p->class_reqset, p->class_reqset + X);
   h.cls_strict_rs.assign(p->class_strict_reqset, p->class_strict_reqset + X);
   h.cls_tolset.assign(p->class_tolset, p->class_tolset + X);
+  h.cls_relax.assign(std::max(X, 1), -1);
+  if (p->class_relax_next)
+    for (int x = 0; x < X; x++) h.cls_relax[x] = p->class_relax_next[x];
   h.cls_rv.assign(std::max(X, 1), 0);
   h.cls_sort_cpu.assign(std::max(X, 1), 0);
   h.cls_sort_mem.assign(std::max(X, 1), 0);
@@ -525,6 +528,7 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   auto update_inverse = [&](int cls, int node) {
     for (int ci = p->class_tsc_off[cls]; ci < p->class_tsc_off[cls + 1]; ci++) {
       if (p->tsc_type[ci] != KP_TOPO_ANTI_AFFINITY) continue;
+      if (p->tsc_preferred && p->tsc_preferred[ci]) continue;  // required terms only (topology.go:297-322)
       HGroup g = make_group(cls, ci, true);
       std::string hk = hash_of(g);
       auto it = inv_index.find(hk);
@@ -546,11 +550,47 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   for (auto& bp : bound) update_inverse(bp.first, bp.second);
   // Update (topology.go:162-194) per pending pod, class-level (every pod of a class carries the same constraints)
   std::vector<uint8_t> seen_cls(std::max(X, 1), 0);
-  for (int cls : pending_classes) {
-    if (seen_cls[cls]) continue;
-    seen_cls[cls] = 1;
+  // A pod that fails is retried as its relaxed class (Preferences.Relax, preferences.go:38-57) after a Topology.Update
+  // of the relaxed pod.  The relaxed classes are made owners of their groups up front, behind the pending classes.
+  // That is the reference's behaviour as long as a relaxed pod only reuses groups some pending pod created at
+  // NewTopology time (dropping a preferred term, a ScheduleAnyway spread, a toleration).  A relaxation that changes a
+  // group's identity (dropping a required node-affinity term changes the node filter of an Honor spread) would have the
+  // reference create a fresh group in the middle of the solve, blind to the pods already placed: not built, refused.
+  std::vector<int32_t> pending_closure;
+  for (int cls0 : pending_classes)
+    if (!seen_cls[cls0]) {
+      seen_cls[cls0] = 1;
+      pending_closure.push_back(cls0);
+    }
+  const size_t n_direct = pending_closure.size();
+  if (p->class_relax_next)
+    for (int x = 0; x < X; x++)
+    {
+      int steps = 0;
+      for (int c = p->class_relax_next[x]; c >= 0; c = p->class_relax_next[c])
+        if (c >= X || ++steps > X) return err = "class_relax_next out of range or cyclic", KP_ERR_INVALID;
+    }
+  auto group_hashes = [&](int cls) {
+    std::set<std::string> out;
+    for (int ci = p->class_tsc_off[cls]; ci < p->class_tsc_off[cls + 1]; ci++) out.insert(hash_of(make_group(cls, ci, false)));
+    return out;
+  };
+  for (size_t i = 0; i < n_direct; i++)
+    for (int prev = pending_closure[i], c = p->class_relax_next ? p->class_relax_next[prev] : -1; c >= 0 && !seen_cls[c];
+         prev = c, c = p->class_relax_next[c]) {
+      const std::set<std::string> have = group_hashes(prev);
+      for (const std::string& hk : group_hashes(c))
+        if (!have.count(hk))
+          return err = "relaxing a pod would create a new topology group mid-solve (spread with nodeAffinityPolicy Honor "
+                       "and several required node-affinity terms): not supported yet",
+                 KP_ERR_UNSUPPORTED;
+      seen_cls[c] = 1;
+      pending_closure.push_back(c);
+    }
+  for (int cls : pending_closure) {
     bool anti = false;
-    for (int ci = p->class_tsc_off[cls]; ci < p->class_tsc_off[cls + 1]; ci++) anti |= p->tsc_type[ci] == KP_TOPO_ANTI_AFFINITY;
+    for (int ci = p->class_tsc_off[cls]; ci < p->class_tsc_off[cls + 1]; ci++)
+      anti |= p->tsc_type[ci] == KP_TOPO_ANTI_AFFINITY && !(p->tsc_preferred && p->tsc_preferred[ci]);
     if (anti) update_inverse(cls, -1);
     for (int ci = p->class_tsc_off[cls]; ci < p->class_tsc_off[cls + 1]; ci++) {
       HGroup g = make_group(cls, ci, false);

@@ -42,6 +42,7 @@ struct HostTables {
   std::vector<int64_t> tmpl_daemon, tmpl_remaining;
   std::vector<uint32_t> tmpl_limit_present;
   std::vector<int64_t> cls_req;
+  std::vector<int32_t> cls_relax;  // class after one Preferences.Relax step, -1: none
   std::vector<int32_t> cls_rs, cls_strict_rs, cls_tolset, cls_rv, cls_match_off, cls_match, cls_rec_off, cls_rec;
   std::vector<int64_t> cls_sort_cpu, cls_sort_mem;
   std::vector<KpGroup> groups;

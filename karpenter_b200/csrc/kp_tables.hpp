@@ -108,6 +108,7 @@ struct KpDev {
   const int64_t* cls_req;         // [X*R]
   const int32_t* cls_rs;          // [X]
   const int32_t* cls_tolset;      // [X]
+  const int32_t* cls_relax;       // [X] class after one Preferences.Relax step (preferences.go:38-57), -1: none
   int n_rv;
   const int32_t* cls_match;       // groups that constrain a class (owned + inverse selecting it); bit 30 = selects(pod)
   const int32_t* cls_rec;         // groups that may count a class on Record (select it / inverse owned)

@@ -438,7 +438,10 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         ids_idx = h + 2;
       }
     }
-    const PodCtx& px = STAGED ? ring->slot[h & (KP_RING - 1)] : ctx;
+    PodCtx& pxw = STAGED ? ring->slot[h & (KP_RING - 1)] : ctx;
+    int Xc = X;  // class the pod is tried as: X, then its relaxations (trySchedule, scheduler.go:438-469)
+  try_pod:
+    const PodCtx& px = pxw;
     const int rv = px.rv, fsig = px.fsig;
     const unsigned long long fbit = (fsig >= 0 && fsig < 64) ? 1ull << fsig : 0ull;
     const unsigned long long rbit = rv < 64 ? 1ull << rv : 0ull;
@@ -889,7 +892,17 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       commits++;
     }
     if (status != KP_OK) break;
-    if (!found) {  // scheduler.go:415-421: record the error and requeue
+    if (!found) {
+      const int nx = d.cls_relax[Xc];
+      if (nx >= 0) {  // Preferences.Relax dropped one soft constraint (preferences.go:38-57): same pod, next class row
+        Xc = nx;
+        ClassRegs cur = load_class_regs(d, Xc, li, lane);
+        __syncwarp();
+        store_class_regs(d, pxw, cur, lane);
+        __syncwarp();
+        goto try_pod;
+      }
+      // scheduler.go:415-421: record the error and requeue the ORIGINAL pod
       if (lane == 0) {
         if (I.pod_target) {
           I.pod_error[li] = (uint8_t)err;

@@ -18,6 +18,7 @@ Go's random map iteration order.
 """
 from __future__ import annotations
 
+from dataclasses import replace
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -72,12 +73,48 @@ def label_requirements(labels: Dict[str, str]):
     return [canonical_requirement(NodeSelectorRequirement(k, "In", (v,))) for k, v in sorted(labels.items())]
 
 
-def pod_requirements(pod: Pod):
-    """NewStrictPodRequirements == NewPodRequirements when no preferred node affinity exists (requirements.go:90-110)."""
+def pod_requirements(pod: Pod, strict: bool = False):
+    """NewPodRequirements / NewStrictPodRequirements (requirements.go:90-110): node selector, the heaviest preferred
+    node-affinity term (not when strict), the first required term.  (The reference picks the heaviest term with an
+    unstable sort; up to 12 terms that is the first of the heaviest, which is what this does.)"""
     reqs = label_requirements(pod.node_selector)
+    if not strict and pod.node_affinity_preferred:
+        heaviest = sorted(pod.node_affinity_preferred, key=lambda t: -t.weight)[0]
+        reqs += [canonical_requirement(r) for r in heaviest.match_expressions]
     if pod.node_affinity_required:
         reqs += [canonical_requirement(r) for r in pod.node_affinity_required[0]]
     return reqs
+
+
+PREFER_NO_SCHEDULE_TOLERATION = Toleration("", "Exists", "", "PreferNoSchedule")
+
+
+def _tolerates_all_prefer_no_schedule(t: Toleration) -> bool:
+    """corev1.Toleration.MatchToleration against {Operator: Exists, Effect: PreferNoSchedule} (preferences.go:133-146)."""
+    return t.key == "" and t.operator == "Exists" and t.effect == "PreferNoSchedule" and t.value == ""
+
+
+def relax(pod: Pod, tolerate_prefer_no_schedule: bool) -> Optional[Pod]:
+    """Preferences.Relax (preferences.go:38-57): the pod with ONE soft constraint dropped, None when nothing is left.
+
+    Order: the first required node-affinity term while several remain (they are alternatives) :74-88, the heaviest
+    preferred pod affinity term :102-115, the heaviest preferred pod anti-affinity term :117-130, the heaviest preferred
+    node-affinity term :59-72, the first ScheduleAnyway spread (the last constraint takes its place) :90-100, and -- only
+    if some NodePool carries a PreferNoSchedule taint -- a toleration for all such taints :132-146."""
+    if len(pod.node_affinity_required) > 1:
+        return replace(pod, node_affinity_required=list(pod.node_affinity_required[1:]))
+    for f in ("pod_affinity_preferred", "pod_anti_affinity_preferred", "node_affinity_preferred"):
+        terms = getattr(pod, f)
+        if terms:
+            return replace(pod, **{f: sorted(terms, key=lambda t: -t.weight)[1:]})  # sort.SliceStable, drop the head
+    for i, t in enumerate(pod.topology_spread_constraints):
+        if t.when_unsatisfiable == "ScheduleAnyway":
+            tscs = list(pod.topology_spread_constraints)
+            tscs[i] = tscs[-1]
+            return replace(pod, topology_spread_constraints=tscs[:-1])
+    if tolerate_prefer_no_schedule and not any(_tolerates_all_prefer_no_schedule(t) for t in pod.tolerations):
+        return replace(pod, tolerations=list(pod.tolerations) + [PREFER_NO_SCHEDULE_TOLERATION])
+    return None
 
 
 def pod_filter_requirements(pod: Pod):
@@ -137,6 +174,7 @@ class ProblemBuilder:
         self.claim_order_mode = 0
         self.pod_arrays = None
         self.max_values_per_key = 64  # width of the per-key value mask; wider keys go through value compaction
+        self.preference_policy = "Respect"  # or "Ignore": scheduler.IgnorePreferences (scheduler.go:81-101)
 
     # ---- resources ----
     def res_index(self, name: str) -> int:
@@ -182,43 +220,52 @@ class ProblemBuilder:
             limits=self.res_vector(np_.limits)))
 
     def pod_class(self, pod: Pod) -> int:
+        respect = self.preference_policy != "Ignore"
         tscs = []
         for t in pod.topology_spread_constraints:
-            if t.when_unsatisfiable != "DoNotSchedule":
-                continue  # ScheduleAnyway is a preference: relaxation is a "next" row
+            soft = t.when_unsatisfiable != "DoNotSchedule"
+            if soft and not respect:
+                continue  # PreferencePolicyIgnore (topology.go:431)
             sel = t.label_selector
             if sel is not None and t.match_label_keys:  # topology.go:434-442
                 extra = tuple((k, "In", (pod.labels[k],)) for k in t.match_label_keys if k in pod.labels)
                 sel = LabelSelector(sel.match_labels, sel.match_expressions + extra)
             tscs.append((0, t.topology_key, sel, (pod.namespace,), t.max_skew,
                          -1 if t.min_domains is None else t.min_domains, t.node_taints_policy == "Honor",
-                         t.node_affinity_policy != "Ignore"))
-        for kind, terms in ((1, pod.pod_affinity), (2, pod.pod_anti_affinity)):
-            for t in terms:
+                         t.node_affinity_policy != "Ignore", soft))
+        # required and -- unless preferences are ignored -- preferred terms alike (topology.go:460-499)
+        for kind, hard, pref in ((1, pod.pod_affinity, pod.pod_affinity_preferred),
+                                 (2, pod.pod_anti_affinity, pod.pod_anti_affinity_preferred)):
+            for t, soft in [(t, False) for t in hard] + [(w.term, True) for w in (pref if respect else [])]:
                 ns = tuple(t.namespaces) if t.namespaces else (pod.namespace,)  # topology.go:503-526
-                tscs.append((kind, t.topology_key, t.label_selector, ns, 0, -1, False, False))
-        reqs = pod_requirements(pod)
-        key = (tuple(sorted((k, quantity_units(k, v)) for k, v in pod.requests.items())), tuple(reqs),
+                tscs.append((kind, t.topology_key, t.label_selector, ns, 0, -1, False, False, soft))
+        strict_reqs = pod_requirements(pod, strict=True)
+        reqs = pod_requirements(pod, strict=not respect)  # scheduler.go:471-491 updateCachedPodData
+        # everything a scheduling decision or a later relaxation step can depend on
+        key = (tuple(sorted((k, quantity_units(k, v)) for k, v in pod.requests.items())), tuple(reqs), tuple(strict_reqs),
                tuple(pod.tolerations), pod.namespace, tuple(sorted(pod.labels.items())), tuple(tscs),
-               tuple(tuple(a) for a in pod_filter_requirements(pod)) if tscs else ())
+               tuple(tuple(a) for a in pod_filter_requirements(pod)),
+               tuple(pod.node_affinity_preferred) if respect else (),
+               tuple((w.weight for w in pod.pod_affinity_preferred)) if respect else (),
+               tuple((w.weight for w in pod.pod_anti_affinity_preferred)) if respect else ())
         n_before = len(self.classes.rows)
         cid = self.classes.get(key)
         if cid == n_before:
             requests = dict(pod.requests)
             vec = self.res_vector(requests)
             vec.append((self.res_index("pods"), 1))  # RequestsForPods adds pods: 1 (resources.go:37)
-            row = dict(requests=vec, reqset=self.reqset(reqs), strict=self.reqset(reqs),
+            row = dict(pod=pod, requests=vec, reqset=self.reqset(reqs), strict=self.reqset(strict_reqs),
                        tolset=self.tolset(pod.tolerations), namespace=self.namespaces.get(pod.namespace),
                        labelset=self.labelsets.get(tuple(sorted(pod.labels.items()))),
                        filters=[self.reqset(a) for a in pod_filter_requirements(pod)] if tscs else [],
                        tscs=[])
-            for (kind, tkey, sel, ns, skew, mind, tp, ap) in tscs:
+            for (kind, tkey, sel, ns, skew, mind, tp, ap, soft) in tscs:
                 for n in ns:
                     self.namespaces.get(n)
                 row["tscs"].append(dict(type=kind, key=NORMALIZED_LABELS.get(tkey, tkey),
                                         selector=-1 if sel is None else self.selectors.get(sel),
                                         nsset=self.nssets.get(tuple(ns)), max_skew=skew, min_domains=mind,
-                                        taint_policy=int(tp), affinity_policy=int(ap)))
+                                        taint_policy=int(tp), affinity_policy=int(ap), preferred=int(soft)))
                 self.extra_keys.add(NORMALIZED_LABELS.get(tkey, tkey))
             self.class_rows.append(row)
         return cid
@@ -249,7 +296,30 @@ class ProblemBuilder:
         return len(self.nodes) - 1
 
     # ---- build ----
+    def relax_chains(self) -> List[int]:
+        """class_relax_next: the class of each class's pods after one EFFECTIVE Preferences.Relax step.  Steps that leave
+        the class unchanged (a preference the policy already ignores) are skipped: retrying an identical pod fails
+        identically.  Relaxed classes are appended while walking, so the loop also covers them."""
+        # NewScheduler: tolerate PreferNoSchedule during relaxation iff some NodePool adds such a taint (scheduler.go:132-142)
+        tolerate = any(t.effect == "PreferNoSchedule" for tm in self.templates for t in self.taintsets.rows[tm["taintset"]])
+        nxt: List[int] = []
+        c = 0
+        while c < len(self.class_rows):
+            pod, n = self.class_rows[c]["pod"], -1
+            while True:
+                pod = relax(pod, tolerate)
+                if pod is None:
+                    break
+                n = self.pod_class(pod)
+                if n != c:
+                    break
+                n = -1
+            nxt.append(n)
+            c += 1
+        return nxt
+
     def build(self) -> "EncodedProblem":
+        relax_next = self.relax_chains()  # first: it may add classes
         R = len(self.resources)
         # active keys
         active = set(self.extra_keys) | {HOSTNAME_LABEL}
@@ -461,7 +531,7 @@ class ProblemBuilder:
         P.set("class_labelset", [c["labelset"] for c in self.class_rows])
         fo, fr, to = [0], [], [0]
         cols = {k: [] for k in ("type", "key", "selector", "nsset", "max_skew", "min_domains", "taint_policy",
-                                "affinity_policy")}
+                                "affinity_policy", "preferred")}
         for c in self.class_rows:
             fr.extend(c["filters"])
             fo.append(len(fr))
@@ -472,6 +542,7 @@ class ProblemBuilder:
         P.set("class_filter_off", fo)
         P.set("class_filter_reqsets", fr)
         P.set("class_tsc_off", to)
+        P.set("class_relax_next", relax_next)
         for k, arr in cols.items():
             P.set("tsc_" + k, arr)
         # pods

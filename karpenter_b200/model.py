@@ -129,6 +129,23 @@ class PodAffinityTerm:
     namespaces: Tuple[str, ...] = ()
 
 
+@dataclass(frozen=True)
+class PreferredSchedulingTerm:
+    """corev1.PreferredSchedulingTerm: a soft node-affinity term."""
+    weight: int
+    match_expressions: Tuple[NodeSelectorRequirement, ...] = ()
+
+    def __post_init__(self):
+        object.__setattr__(self, "match_expressions", tuple(self.match_expressions))
+
+
+@dataclass(frozen=True)
+class WeightedPodAffinityTerm:
+    """corev1.WeightedPodAffinityTerm: a soft pod affinity / anti-affinity term."""
+    weight: int
+    term: PodAffinityTerm
+
+
 @dataclass
 class Pod:
     name: str = ""
@@ -142,6 +159,10 @@ class Pod:
     topology_spread_constraints: List[TopologySpreadConstraint] = field(default_factory=list)
     pod_affinity: List[PodAffinityTerm] = field(default_factory=list)       # required terms
     pod_anti_affinity: List[PodAffinityTerm] = field(default_factory=list)  # required terms
+    # soft constraints: enforced until Preferences.Relax drops them one at a time (preferences.go:38-57)
+    node_affinity_preferred: List[PreferredSchedulingTerm] = field(default_factory=list)
+    pod_affinity_preferred: List[WeightedPodAffinityTerm] = field(default_factory=list)
+    pod_anti_affinity_preferred: List[WeightedPodAffinityTerm] = field(default_factory=list)
     creation_timestamp: int = 0
 
 

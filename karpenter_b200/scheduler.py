@@ -30,12 +30,14 @@ POD_ERRORS = {
 class Scheduler:
     def __init__(self, node_pools: Sequence[NodePool], instance_types: Dict[str, List[InstanceType]],
                  state_nodes: Sequence[StateNode] = (), daemon_overhead: Optional[Dict[str, dict]] = None,
-                 claim_order: str = "go", backend: Optional[Callable] = None, device: int = -1):
+                 claim_order: str = "go", backend: Optional[Callable] = None, device: int = -1,
+                 preference_policy: str = "Respect"):
         self.node_pools = list(node_pools)
         self.instance_types = instance_types
         self.state_nodes = list(state_nodes)
         self.daemon_overhead = daemon_overhead or {}
         self.claim_order = claim_order
+        self.preference_policy = preference_policy  # "Ignore" == scheduler.IgnorePreferences (scheduler.go:81-101)
         self._backend = backend
         self._device = device
         self._handle = None
@@ -44,6 +46,7 @@ class Scheduler:
     def _builder(self) -> ProblemBuilder:
         b = ProblemBuilder()
         b.claim_order_mode = 1 if self.claim_order == "stable" else 0
+        b.preference_policy = self.preference_policy
         index: Dict[int, int] = {}
         for np_ in self.node_pools:
             ids = []

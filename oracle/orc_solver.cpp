@@ -409,15 +409,27 @@ struct Scheduler {
       auto ll = last_len.find(pod);
       if (ll != last_len.end() && ll->second == len) break;  // queue.go:54-58: a full cycle without progress
       head++;
-      int cls = p->pod_class[pod];
+      const int cls0 = p->pod_class[pod];
+      int cls = cls0;
       int target = KP_TARGET_UNSCHEDULED;
       uint8_t err = KP_PODERR_NONE;
-      if (add(pod, cls, &target, &err)) {
+      bool placed = false;
+      for (;;) {  // trySchedule (scheduler.go:438-469): relax one soft constraint at a time until the pod fits
+        if (add(pod, cls, &target, &err)) {
+          placed = true;
+          break;
+        }
+        int nx = p->class_relax_next ? p->class_relax_next[cls] : -1;  // Preferences.Relax (preferences.go:38-57)
+        if (nx < 0) break;
+        cls = nx;
+        topo.update(cls);
+      }
+      if (placed) {
         (*targets)[slot[pod]] = target;
         (*errors)[slot[pod]] = KP_PODERR_NONE;
       } else {
         (*errors)[slot[pod]] = err;
-        topo.update(cls);
+        topo.update(cls0);  // the ORIGINAL pod goes back into the queue (scheduler.go:415-421)
         q.push_back(pod);  // queue.go:63-66 Push
         last_len[pod] = q.size() - head;
       }

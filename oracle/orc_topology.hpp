@@ -438,6 +438,7 @@ struct Topology {
     const kp_problem* p = P.p;
     for (int c = p->class_tsc_off[cls]; c < p->class_tsc_off[cls + 1]; c++) {
       if (p->tsc_type[c] != KP_TOPO_ANTI_AFFINITY) continue;
+      if (p->tsc_preferred && p->tsc_preferred[c]) continue;  // required terms only (topology.go:297-322)
       auto g = new_group(cls, c);
       g->inverse = true;
       std::string h = hash_of(*g);
@@ -467,7 +468,7 @@ struct Topology {
     updated.insert(cls);
     bool has_anti = false;
     for (int c = p->class_tsc_off[cls]; c < p->class_tsc_off[cls + 1]; c++)
-      if (p->tsc_type[c] == KP_TOPO_ANTI_AFFINITY) has_anti = true;
+      if (p->tsc_type[c] == KP_TOPO_ANTI_AFFINITY && !(p->tsc_preferred && p->tsc_preferred[c])) has_anti = true;
     if (has_anti) update_inverse_anti_affinity(cls, -1);
     for (int c = p->class_tsc_off[cls]; c < p->class_tsc_off[cls + 1]; c++) {
       auto g = new_group(cls, c);
@@ -491,6 +492,7 @@ struct Topology {
   void init(const std::vector<int>& pending_classes_in_pod_order) {
     build_domain_groups();
     for (auto& bp : bound_pods) update_inverse_anti_affinity(bp.first, bp.second);
+    // the groups of a relaxed pod are created when it is relaxed (Topology.Update in trySchedule, scheduler.go:462)
     for (int cls : pending_classes_in_pod_order) update(cls);
   }
 

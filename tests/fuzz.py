@@ -13,7 +13,8 @@ from typing import List
 from karpenter_b200 import fake
 from karpenter_b200.model import (ARCH_LABEL, CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, INSTANCE_TYPE_LABEL, NODEPOOL_LABEL,
                                   OS_LABEL, ZONE_LABEL, LabelSelector, NodePool, NodeSelectorRequirement, Offering, Pod,
-                                  PodAffinityTerm, StateNode, Taint, Toleration, TopologySpreadConstraint, quantity_units)
+                                  PodAffinityTerm, PreferredSchedulingTerm, StateNode, Taint, Toleration,
+                                  TopologySpreadConstraint, WeightedPodAffinityTerm, quantity_units)
 
 ZONES = ["test-zone-1", "test-zone-2", "test-zone-3"]
 CTS = ["spot", "on-demand"]
@@ -163,3 +164,52 @@ def problem(seed: int, n_pods=None, with_nodes=True):
     if with_nodes and rng.random() < 0.6:
         nodes = state_nodes(rng, its, pools, rng.randint(1, 12), pods(rng, rng.randint(0, 10), uid0=10_000))
     return pools, per_pool, nodes, pl
+
+
+def soften(seed: int, pools, pl: List[Pod]):
+    """Sprinkle soft constraints over a problem (own random stream, so `problem(seed)` itself is unchanged): preferred
+    node affinity with mixed weights, ScheduleAnyway spreads, preferred pod (anti-)affinity, alternative required
+    node-affinity terms, PreferNoSchedule taints on NodePools.  Pods of one deployment stay identical."""
+    rng = random.Random(77_000 + seed)
+    for pool in pools:
+        if rng.random() < 0.25:
+            pool.taints = list(pool.taints) + [Taint("soft", "x", "PreferNoSchedule")]
+    shapes = {}
+    for p in pl:
+        shapes.setdefault(id(p.tolerations), []).append(p)  # pods(): the kwargs of one deployment share their lists
+    for group in shapes.values():
+        kw = {}
+        if rng.random() < 0.4:
+            terms = []
+            for _ in range(rng.randint(1, 3)):
+                k = rng.choice([ZONE_LABEL, ZONE_LABEL, CAPACITY_TYPE_LABEL, fake.LABEL_INSTANCE_SIZE])
+                v = {ZONE_LABEL: ZONES + ["nowhere"], CAPACITY_TYPE_LABEL: CTS, fake.LABEL_INSTANCE_SIZE: ["small", "large", "huge"]}[k]
+                terms.append(PreferredSchedulingTerm(rng.choice([1, 1, 10, 50, 100]),
+                                                     (_req(k, rng.choice(["In", "In", "NotIn"]), rng.choice(v)),)))
+            kw["node_affinity_preferred"] = terms
+        tscs = list(group[0].topology_spread_constraints)
+        r = rng.random()
+        if tscs and r < 0.4:
+            t = tscs[0]
+            tscs[0] = TopologySpreadConstraint(t.max_skew, t.topology_key, t.label_selector, "ScheduleAnyway", t.min_domains,
+                                               t.node_taints_policy, t.node_affinity_policy)
+            kw["topology_spread_constraints"] = tscs
+        elif r < 0.55:
+            tscs.append(TopologySpreadConstraint(1, rng.choice([ZONE_LABEL, HOSTNAME_LABEL, CAPACITY_TYPE_LABEL]), _selector(rng),
+                                                 "ScheduleAnyway"))
+            kw["topology_spread_constraints"] = tscs
+        if rng.random() < 0.25:
+            kw["pod_anti_affinity_preferred"] = [
+                WeightedPodAffinityTerm(rng.choice([1, 50]), PodAffinityTerm(_selector(rng), rng.choice([HOSTNAME_LABEL, ZONE_LABEL])))
+                for _ in range(rng.randint(1, 2))]
+        if rng.random() < 0.2:
+            kw["pod_affinity_preferred"] = [
+                WeightedPodAffinityTerm(rng.choice([1, 50]), PodAffinityTerm(_selector(rng), rng.choice([HOSTNAME_LABEL, ZONE_LABEL])))]
+        if rng.random() < 0.15:  # alternatives: the first term is tried first, dropped when the pod does not fit
+            first = list(group[0].node_affinity_required[0]) if group[0].node_affinity_required else []
+            alt = [_req(ZONE_LABEL, "In", rng.choice(ZONES + ["nowhere"]))]
+            kw["node_affinity_required"] = [[_req(ZONE_LABEL, "In", rng.choice(["nowhere", ZONES[0]]))] + first, alt + first]
+        for p in group:
+            for k, v in kw.items():
+                setattr(p, k, v)
+    return pools, pl

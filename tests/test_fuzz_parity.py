@@ -40,13 +40,39 @@ def test_generator_is_wellformed_and_varied():
         assert stats[k] >= 10, stats
 
 
+def encode_soft(seed):
+    """the same problems with soft constraints sprinkled in (fuzz.soften); every fifth ignores preferences"""
+    pools, per_pool, nodes, pl = fuzz.problem(seed, n_pods=[5, 20, 60, 150][seed % 4])
+    fuzz.soften(seed, pools, pl)
+    s = Scheduler(pools, per_pool, nodes, claim_order="go" if seed % 3 else "stable",
+                  preference_policy="Ignore" if seed % 5 == 0 else "Respect")
+    return s.encode(pl)
+
+
+def test_soft_generator_relaxes():
+    stats = collections.Counter()
+    for seed in range(150):
+        enc = encode_soft(seed)
+        nxt = enc.problem.get("class_relax_next")
+        stats["chains"] += int((nxt >= 0).any())
+        try:
+            res = oracle_lib.solve(enc.problem)
+        except RuntimeError:
+            stats["rejected"] += 1
+            continue
+        stats["solved"] += 1
+        stats["unsched"] += int((res["pod_target"] == -1).sum() > 0)
+    assert stats["solved"] >= 100 and stats["chains"] >= 80, stats
+
+
 @pytest.mark.gpu
-def test_fuzz_parity_gpu():
+@pytest.mark.parametrize("soft", [False, True], ids=["hard", "soft"])
+def test_fuzz_parity_gpu(soft):
     h = _native.Handle()
     bad, ran = [], 0
     try:
-        for seed in SEEDS:
-            enc = encode(seed)
+        for seed in (range(300) if soft else SEEDS):
+            enc = encode_soft(seed) if soft else encode(seed)
             try:
                 orc = oracle_lib.solve(enc.problem)
             except RuntimeError:
@@ -54,7 +80,9 @@ def test_fuzz_parity_gpu():
             try:
                 gpu = h.solve(enc.problem)
             except _native.SolverError as e:
-                bad.append((seed, f"gpu refused: {e}"))
+                # relaxing a required node-affinity term under an Honor spread creates a topology group mid-solve
+                if not (soft and e.code == 5 and "mid-solve" in str(e)):
+                    bad.append((seed, f"gpu refused: {e}"))
                 continue
             ran += 1
             try:
@@ -63,7 +91,7 @@ def test_fuzz_parity_gpu():
                 bad.append((seed, str(e)[:200]))
     finally:
         h.close()
-    assert ran >= 300
+    assert ran >= (200 if soft else 300)
     assert not bad, bad[:10]
 
 
@@ -83,6 +111,8 @@ def consolidation_case(seed):
         if seed % 4:  # three seeds of four stay topology-free (one warp per candidate set); the fourth takes the general path
             cand = [p for p in cand if not (p.topology_spread_constraints or p.pod_affinity or p.pod_anti_affinity)]
         n.pods = cand[:k]
+    if seed % 3 == 0:  # soft constraints on the evicted pods: the simulation relaxes them like the provisioner does
+        fuzz.soften(seed, pools, [p for n in nodes for p in n.pods])
     names = [n.name for n in nodes]
     sets = [rng.sample(names, rng.randint(1, min(3, len(names)))) for _ in range(rng.randint(1, 12))]
     return pools, per_pool, nodes, sets, rng.random() < 0.5  # ... and whether spot-to-spot consolidation is enabled
@@ -103,7 +133,7 @@ def test_fuzz_consolidation_parity_gpu():
         try:
             gpu.compute(sets)
         except _native.SolverError as e:
-            if e.code == 5:  # KP_ERR_UNSUPPORTED: topology constraints on the evicted pods
+            if e.code == 5 and "mid-solve" in str(e):  # see test_fuzz_parity_gpu
                 continue
             bad.append((seed, str(e)))
             continue

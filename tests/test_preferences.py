@@ -1,0 +1,235 @@
+"""Preference relaxation (Preferences.Relax, preferences.go:38-146; trySchedule, scheduler.go:438-469).
+
+Restates the reference's "Preferential Fallback" cases (suite_test.go:1125-1245) and the soft topology cases of
+topology_test.go (ScheduleAnyway spreads, preferred pod affinity / anti-affinity) with the outcomes the reference
+asserts.  CPU tier: through the oracle.  GPU tier: through the CUDA path, bit-identical to the oracle.
+"""
+from collections import Counter
+
+import pytest
+
+from karpenter_b200 import encode, fake
+from karpenter_b200.model import (CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, INSTANCE_TYPE_LABEL, ZONE_LABEL, LabelSelector, NodePool,
+                                  NodeSelectorRequirement, Pod, PodAffinityTerm, PreferredSchedulingTerm, Taint, Toleration,
+                                  TopologySpreadConstraint, WeightedPodAffinityTerm)
+from tests.test_reference_scenarios import BACKENDS, nodepool, pods, req, run, zone_of
+
+LABELS = {"test": "test"}
+SEL = LabelSelector.of(LABELS)
+
+
+def pref(weight, *reqs):
+    return PreferredSchedulingTerm(weight, tuple(reqs))
+
+
+# ---- Preferences.Relax itself: order and stopping rule (preferences.go:38-57) ----------------------------------------
+def test_relax_order():
+    p = Pod(name="p", node_affinity_required=[[req(ZONE_LABEL, "In", "a")], [req(ZONE_LABEL, "In", "b")]],
+            node_affinity_preferred=[pref(1, req(ZONE_LABEL, "In", "c")), pref(5, req(ZONE_LABEL, "In", "d"))],
+            pod_affinity_preferred=[WeightedPodAffinityTerm(1, PodAffinityTerm(SEL, ZONE_LABEL))],
+            pod_anti_affinity_preferred=[WeightedPodAffinityTerm(1, PodAffinityTerm(SEL, HOSTNAME_LABEL))],
+            topology_spread_constraints=[TopologySpreadConstraint(1, ZONE_LABEL, SEL, "ScheduleAnyway"),
+                                         TopologySpreadConstraint(1, HOSTNAME_LABEL, SEL)])
+    steps = []
+    while p is not None:
+        steps.append((len(p.node_affinity_required), len(p.pod_affinity_preferred), len(p.pod_anti_affinity_preferred),
+                      [t.weight for t in p.node_affinity_preferred], len(p.topology_spread_constraints),
+                      len(p.tolerations)))
+        p = encode.relax(p, True)
+    assert steps == [(2, 1, 1, [1, 5], 2, 0), (1, 1, 1, [1, 5], 2, 0), (1, 0, 1, [1, 5], 2, 0), (1, 0, 0, [1, 5], 2, 0),
+                     (1, 0, 0, [1], 2, 0),  # the heaviest (5) goes first
+                     (1, 0, 0, [], 2, 0), (1, 0, 0, [], 1, 0), (1, 0, 0, [], 1, 1)]
+    # without a PreferNoSchedule taint on any NodePool no toleration is added
+    q = Pod(name="q")
+    assert encode.relax(q, False) is None
+    assert encode.relax(Pod(name="q", tolerations=[Toleration("", "Exists", "", "PreferNoSchedule")]), True) is None
+
+
+# ---- Required (suite_test.go:1126-1165) ------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_final_required_term_is_not_relaxed(which):  # suite_test.go:1127-1142
+    np_ = nodepool(requirements=[req(ZONE_LABEL, "In", "test-zone-1"), req(INSTANCE_TYPE_LABEL, "In", "default-instance-type")])
+    r = run(which, pods(1, node_affinity_required=[[req(ZONE_LABEL, "In", "invalid")]]), np_)
+    assert not r.new_node_claims and len(r.pod_errors) == 1
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_required_terms_relax_in_order(which):  # suite_test.go:1143-1165: invalid, invalid, zone-1, (zone-2 never reached)
+    terms = [[req(ZONE_LABEL, "In", "invalid")], [req(ZONE_LABEL, "In", "invalid")], [req(ZONE_LABEL, "In", "test-zone-1")],
+             [req(ZONE_LABEL, "In", "test-zone-2")]]
+    r = run(which, pods(1, node_affinity_required=terms))
+    assert not r.pod_errors and zone_of(r.new_node_claims[0]) == "test-zone-1"
+
+
+# ---- Preferred (suite_test.go:1166-1245) -----------------------------------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_all_preferred_terms_relax(which):  # suite_test.go:1167-1186
+    prefs = [pref(1, req(ZONE_LABEL, "In", "invalid")), pref(1, req(INSTANCE_TYPE_LABEL, "In", "invalid"))]
+    r = run(which, pods(1, node_affinity_preferred=prefs))
+    assert not r.pod_errors and len(r.new_node_claims) == 1
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_relax_to_lighter_weights(which):  # suite_test.go:1187-1212: weight 100 impossible, 50 -> zone-2, 1 never reached
+    np_ = nodepool(requirements=[req(ZONE_LABEL, "In", "test-zone-1", "test-zone-2")])
+    prefs = [pref(100, req(INSTANCE_TYPE_LABEL, "In", "test-zone-3")), pref(50, req(ZONE_LABEL, "In", "test-zone-2")),
+             pref(1, req(ZONE_LABEL, "In", "test-zone-1"))]
+    r = run(which, pods(1, node_affinity_preferred=prefs), np_)
+    assert not r.pod_errors and zone_of(r.new_node_claims[0]) == "test-zone-2"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_preference_conflicting_with_requirement(which):  # suite_test.go:1213-1233
+    r = run(which, pods(1, node_affinity_preferred=[pref(1, req(ZONE_LABEL, "NotIn", "test-zone-3"))],
+                        node_affinity_required=[[req(ZONE_LABEL, "In", "test-zone-3")]]))
+    assert not r.pod_errors and zone_of(r.new_node_claims[0]) == "test-zone-3"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_conflicting_preference_requirements(which):  # suite_test.go:1234-1243: In invalid AND NotIn invalid in one term
+    r = run(which, pods(1, node_affinity_preferred=[pref(1, req(ZONE_LABEL, "In", "invalid"), req(ZONE_LABEL, "NotIn", "invalid"))]))
+    assert not r.pod_errors and len(r.new_node_claims) == 1
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_satisfiable_preference_is_honoured(which):  # suite_test.go:335-349 family: a preference that CAN hold, holds
+    r = run(which, pods(3, node_affinity_preferred=[pref(1, req(ZONE_LABEL, "In", "test-zone-2"))]))
+    assert not r.pod_errors and {zone_of(c) for c in r.new_node_claims} == {"test-zone-2"}
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_failed_pod_requeues_with_its_preferences(which):  # scheduler.go:405-421: the ORIGINAL pod goes back into the queue
+    # the pod can never schedule (20 000 cpu); every requeue cycle starts again from the unrelaxed class, and ends
+    np_ = nodepool()
+    pl = pods(2, requests={"cpu": "20000"}, node_affinity_preferred=[pref(1, req(ZONE_LABEL, "In", "test-zone-2"))])
+    pl += pods(3, uid0=10, requests={"cpu": "1"})
+    r = run(which, pl, np_)
+    assert len(r.pod_errors) == 2 and sum(len(c.pods) for c in r.new_node_claims) == 3
+
+
+# ---- ScheduleAnyway spreads (topology_test.go:715-741, 1049-1085) ----------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_schedule_anyway_violates_max_skew(which):  # topology_test.go:715-741, second half: one pod already on spot
+    from tests.test_reference_scenarios import _node
+    tsc = [TopologySpreadConstraint(1, CAPACITY_TYPE_LABEL, SEL, "ScheduleAnyway")]
+    spot_pod = Pod(name="old", uid=999, labels=LABELS, requests={"cpu": "1.1"}, topology_spread_constraints=tsc)
+    its = fake.default_instance_types()
+    n = _node("n1", [i for i in its if i.name == "default-instance-type"][0], ct="spot")
+    n.running_pods = [spot_pod]
+    n.available = {"cpu": "0", "memory": "0", "pods": 0}  # full: the new pods need new nodes
+    np_ = nodepool()
+    np_.requirements = [req(CAPACITY_TYPE_LABEL, "In", "on-demand")]
+    from karpenter_b200.scheduler import Scheduler
+    from tests import oracle_lib
+    from tests.parity import assert_same
+    pl = pods(5, labels=LABELS, requests={"cpu": "1.1"}, topology_spread_constraints=tsc)
+
+    def go(backend):
+        s = Scheduler([np_], {np_.name: its}, state_nodes=[n], backend=backend)
+        try:
+            return s.solve(pl)
+        finally:
+            s.close()
+    r = go(oracle_lib.solve)
+    if which == "gpu":
+        g = go(None)
+        assert_same(g.raw, r.raw, "schedule-anyway ")
+        r = g
+    # on-demand ends up with all 5 pods although spot holds a single one
+    assert not r.pod_errors and sum(len(c.pods) for c in r.new_node_claims) == 5
+    assert all(c.requirements[CAPACITY_TYPE_LABEL]["values"] == ["on-demand"] for c in r.new_node_claims)
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_do_not_schedule_zone_with_schedule_anyway_hostname(which):  # topology_test.go:1049-1085
+    tscs = [TopologySpreadConstraint(1, ZONE_LABEL, SEL), TopologySpreadConstraint(1, HOSTNAME_LABEL, SEL, "ScheduleAnyway")]
+    np_ = nodepool(requirements=[req(ZONE_LABEL, "In", "test-zone-1", "test-zone-2")])
+    np_b = NodePool(name="b", requirements=[req(ZONE_LABEL, "In", "test-zone-3")], limits={"cpu": "0"})
+    from karpenter_b200.scheduler import Scheduler
+    from tests import oracle_lib
+    from tests.parity import assert_same
+    its = fake.default_instance_types()
+    pl = pods(10, labels=LABELS, topology_spread_constraints=tscs)
+
+    def go(backend):
+        s = Scheduler([np_, np_b], {np_.name: its, np_b.name: its}, backend=backend)
+        try:
+            return s.solve(pl)
+        finally:
+            s.close()
+    r = go(oracle_lib.solve)
+    if which == "gpu":
+        g = go(None)
+        assert_same(g.raw, r.raw, "both-constraints ")
+        r = g
+    # one pod per zone; zone 3 is only reachable through the disabled NodePool, so the zonal skew blocks the rest
+    zones = Counter(zone_of(c) for c in r.new_node_claims for _ in c.pods)
+    assert sorted(zones.values()) == [1, 1] and len(r.pod_errors) == 8
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_preferred_node_affinity_does_not_restrict_spread_domains(which):  # topology_test.go:1831-1852
+    tsc = [TopologySpreadConstraint(1, ZONE_LABEL, SEL)]
+    r = run(which, pods(6, labels=LABELS, topology_spread_constraints=tsc,
+                        node_affinity_preferred=[pref(1, req(ZONE_LABEL, "In", "test-zone-1", "test-zone-2"))]))
+    zones = Counter(zone_of(c) for c in r.new_node_claims for _ in c.pods)
+    assert not r.pod_errors and sorted(zones.values()) == [2, 2, 2]
+
+
+# ---- preferred pod affinity / anti-affinity (topology_test.go:2230-2300, 2630-2665) ---------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_preferred_pod_affinity_may_be_violated(which):  # topology_test.go:2230-2262
+    tsc = [TopologySpreadConstraint(1, HOSTNAME_LABEL, SEL)]
+    aff = Pod(name="aff", uid=500, pod_affinity_preferred=[
+        WeightedPodAffinityTerm(50, PodAffinityTerm(LabelSelector.of({"security": "s2"}), HOSTNAME_LABEL))])
+    r = run(which, pods(10, labels=LABELS, topology_spread_constraints=tsc) + [aff])
+    assert not r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_preferred_pod_anti_affinity_may_be_violated(which):  # topology_test.go:2263-2290
+    anti = [WeightedPodAffinityTerm(50, PodAffinityTerm(SEL, HOSTNAME_LABEL))]
+    # 10 pods that prefer to avoid each other but ALSO must all share one zone-1 node type... they still schedule
+    r = run(which, pods(10, labels=LABELS, pod_anti_affinity_preferred=anti))
+    assert not r.pod_errors
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_affinity_preference_conflicting_with_required_spread(which):  # topology_test.go:2630-2665
+    tsc = [TopologySpreadConstraint(1, HOSTNAME_LABEL, SEL)]
+    aff_labels = {"security": "s2"}
+    pl = pods(3, labels=LABELS, topology_spread_constraints=tsc, pod_affinity_preferred=[
+        WeightedPodAffinityTerm(50, PodAffinityTerm(LabelSelector.of(aff_labels), HOSTNAME_LABEL))])
+    pl += pods(1, uid0=100, labels=aff_labels)
+    r = run(which, pl)
+    assert not r.pod_errors
+    per_node = sorted(sum(1 for p in c.pods if p.labels == LABELS) for c in r.new_node_claims)
+    assert [n for n in per_node if n] == [1, 1, 1]  # three nodes due to the required hostname spread
+
+
+# ---- PreferNoSchedule (preferences.go:132-146, scheduler.go:132-142) ------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_prefer_no_schedule_taint_is_tolerated_after_relaxation(which):  # suite_test.go "PreferNoSchedule" family
+    np_ = nodepool(taints=[Taint("soft", "x", "PreferNoSchedule")])
+    r = run(which, pods(2, requests={"cpu": "1"}), np_)
+    assert not r.pod_errors and sum(len(c.pods) for c in r.new_node_claims) == 2
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_no_schedule_taint_is_never_relaxed(which):
+    np_ = nodepool(taints=[Taint("hard", "x", "NoSchedule"), Taint("soft", "x", "PreferNoSchedule")])
+    r = run(which, pods(1, requests={"cpu": "1"}), np_)
+    assert len(r.pod_errors) == 1
+
+
+# ---- PreferencePolicy Ignore (scheduler.go:81-101, topology.go:431,471,481) ----------------------------------------
+def test_preference_policy_ignore_drops_soft_constraints():
+    b = encode.ProblemBuilder()
+    b.preference_policy = "Ignore"
+    p = Pod(name="p", labels=LABELS, node_affinity_preferred=[pref(1, req(ZONE_LABEL, "In", "test-zone-2"))],
+            pod_anti_affinity_preferred=[WeightedPodAffinityTerm(1, PodAffinityTerm(SEL, HOSTNAME_LABEL))],
+            topology_spread_constraints=[TopologySpreadConstraint(1, ZONE_LABEL, SEL, "ScheduleAnyway")])
+    c = b.pod_class(p)
+    assert b.class_rows[c]["tscs"] == [] and b.class_rows[c]["reqset"] == b.class_rows[c]["strict"]
+    assert b.pod_class(Pod(name="q", labels=LABELS)) == c  # indistinguishable from the bare pod
+    assert b.relax_chains() == [-1]
