@@ -79,3 +79,9 @@ def default_instance_types() -> List[InstanceType]:
                           operating_systems=("ios", "linux", "windows", "darwin")),
         new_instance_type("single-pod-instance-type", {"pods": "1"}),
     ]
+
+
+def instance_types(total: int) -> List[InstanceType]:
+    """fake.InstanceTypes (fake/instancetype.go:200-213): fake-it-<i> with i+1 cpu, 2(i+1) Gi, 10(i+1) pods."""
+    return [new_instance_type(f"fake-it-{i}", {"cpu": str(i + 1), "memory": f"{(i + 1) * 2}Gi", "pods": str((i + 1) * 10)})
+            for i in range(total)]

@@ -91,8 +91,8 @@ def test_fuzz_parity_gpu(soft):
                 bad.append((seed, str(e)[:200]))
     finally:
         h.close()
-    assert ran >= (200 if soft else 300)
     assert not bad, bad[:10]
+    assert ran >= (270 if soft else 300), ran
 
 
 def consolidation_case(seed):

@@ -233,3 +233,40 @@ def test_preference_policy_ignore_drops_soft_constraints():
     assert b.class_rows[c]["tscs"] == [] and b.class_rows[c]["reqset"] == b.class_rows[c]["strict"]
     assert b.pod_class(Pod(name="q", labels=LABELS)) == c  # indistinguishable from the bare pod
     assert b.relax_chains() == [-1]
+
+
+# ---- BenchmarkRespectPreferences / BenchmarkIgnorePreferences (scheduling_benchmark_test.go:104-109, 217-256, 379-427) ---
+def preference_benchmark(n_pods, policy, backend):
+    from karpenter_b200.scheduler import Scheduler
+    np_ = NodePool(name="default", requirements=[req(CAPACITY_TYPE_LABEL, "In", "spot", "on-demand", "reserved")],
+                   limits={"cpu": "10000000", "memory": "10000000Gi"})
+    nginx = LabelSelector.of({"app": "nginx"})
+    pl = pods(n_pods, labels={"app": "nginx"}, requests={"cpu": "500m", "memory": "512Mi"},
+              node_affinity_preferred=[pref(1, req(ZONE_LABEL, "In", "test-zone-1"))],  # satisfiable
+              pod_anti_affinity_preferred=[WeightedPodAffinityTerm(10, PodAffinityTerm(nginx, ZONE_LABEL)),      # not satisfiable
+                                           WeightedPodAffinityTerm(1, PodAffinityTerm(nginx, HOSTNAME_LABEL))])  # satisfiable
+    s = Scheduler([np_], {np_.name: fake.instance_types(400)}, backend=backend, preference_policy=policy)
+    try:
+        return s.solve(pl)
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("policy", ["Respect", "Ignore"])
+@pytest.mark.parametrize("which", BACKENDS)
+def test_preference_benchmark_pods(which, policy):
+    from tests import oracle_lib
+    from tests.parity import assert_same
+    n = 400 if which == "oracle" else 4000
+    r = preference_benchmark(n, policy, oracle_lib.solve)
+    if which == "gpu":
+        g = preference_benchmark(n, policy, None)
+        assert_same(g.raw, r.raw, f"preference benchmark {policy} ")
+        r = g
+    assert not r.pod_errors  # the benchmark fails on any PodError (scheduling_benchmark_test.go:177-179)
+    if policy == "Respect":
+        # the zonal anti-affinity preference holds for the first pod only (one zone is preferred), the hostname one always:
+        # one pod per node, all in the preferred zone
+        assert len(r.new_node_claims) == n and all(zone_of(c) == "test-zone-1" for c in r.new_node_claims)
+    else:
+        assert len(r.new_node_claims) < n // 10
