@@ -241,6 +241,13 @@ class ProblemBuilder:
                 tscs.append((kind, t.topology_key, t.label_selector, ns, 0, -1, False, False, soft))
         strict_reqs = pod_requirements(pod, strict=True)
         reqs = pod_requirements(pod, strict=not respect)  # scheduler.go:471-491 updateCachedPodData
+        if pod.volume_requirements:
+            # CanAdd tries the volume alternatives in turn, each added to the NODE's requirements behind the pod's own and
+            # kept out of the strict requirements the topology sees (nodeclaim.go:136-176, existingnode.go:98-140).  With
+            # one alternative that is: requirements = pod AND volume, strict requirements = pod.
+            if len(pod.volume_requirements) > 1:
+                raise ValueError("several volume topology alternatives for one pod are not supported yet")
+            reqs = reqs + [canonical_requirement(r) for r in pod.volume_requirements[0]]
         # everything a scheduling decision or a later relaxation step can depend on
         key = (tuple(sorted((k, quantity_units(k, v)) for k, v in pod.requests.items())), tuple(reqs), tuple(strict_reqs),
                tuple(pod.tolerations), pod.namespace, tuple(sorted(pod.labels.items())), tuple(tscs),

@@ -163,6 +163,10 @@ class Pod:
     node_affinity_preferred: List[PreferredSchedulingTerm] = field(default_factory=list)
     pod_affinity_preferred: List[WeightedPodAffinityTerm] = field(default_factory=list)
     pod_anti_affinity_preferred: List[WeightedPodAffinityTerm] = field(default_factory=list)
+    # volumeReqsByPod[uid] (scheduler.go:127,489): alternatives of topology requirements of the pod's volumes, as
+    # VolumeTopology.GetRequirements derives them (volumetopology.go:44-89).  They constrain the node, never the pod's own
+    # topology domains (nodeclaim.go:136-176).  One alternative is supported (a bound PV / one storage class).
+    volume_requirements: List[List[NodeSelectorRequirement]] = field(default_factory=list)
     creation_timestamp: int = 0
 
 

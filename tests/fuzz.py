@@ -212,6 +212,8 @@ def soften(seed: int, pools, pl: List[Pod]):
             first = list(group[0].node_affinity_required[0]) if group[0].node_affinity_required else []
             alt = [_req(ZONE_LABEL, "In", rng.choice(ZONES + ["nowhere"]))]
             kw["node_affinity_required"] = [[_req(ZONE_LABEL, "In", rng.choice(["nowhere", ZONES[0]]))] + first, alt + first]
+        if rng.random() < 0.15:  # a volume bound in one zone, or a storage class spanning two
+            kw["volume_requirements"] = [[_req(ZONE_LABEL, "In", *rng.sample(ZONES, rng.choice([1, 1, 2])))]]
         for p in group:
             for k, v in kw.items():
                 setattr(p, k, v)

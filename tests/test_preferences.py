@@ -270,3 +270,43 @@ def test_preference_benchmark_pods(which, policy):
         assert len(r.new_node_claims) == n and all(zone_of(c) == "test-zone-1" for c in r.new_node_claims)
     else:
         assert len(r.new_node_claims) < n // 10
+
+
+# ---- Volume topology requirements (provisioning/suite_test.go:1852-2260; nodeclaim.go:136-176) ----------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_volume_zone_is_respected(which):  # provisioning/suite_test.go:2036-2046: PV bound in test-zone-3
+    r = run(which, pods(1, volume_requirements=[[req(ZONE_LABEL, "In", "test-zone-3")]]))
+    assert not r.pod_errors and zone_of(r.new_node_claims[0]) == "test-zone-3"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_volume_zone_incompatible_with_pod(which):  # provisioning/suite_test.go:2182-2194
+    r = run(which, pods(1, volume_requirements=[[req(ZONE_LABEL, "In", "test-zone-3")]],
+                        node_affinity_required=[[req(ZONE_LABEL, "In", "test-zone-1")]]))
+    assert len(r.pod_errors) == 1
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_storage_class_zones(which):  # provisioning/suite_test.go:1968-1980: storage class allows zones 2 and 3
+    r = run(which, pods(1, volume_requirements=[[req(ZONE_LABEL, "In", "test-zone-2", "test-zone-3")]]))
+    z = r.new_node_claims[0].requirements[ZONE_LABEL]
+    assert not r.pod_errors and sorted(z["values"]) == ["test-zone-2", "test-zone-3"] and not z["complement"]
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_volume_zone_survives_relaxation(which):  # provisioning/suite_test.go:2218-2258
+    terms = [[req("example.com/label", "In", "unsupported")], [req(CAPACITY_TYPE_LABEL, "In", "on-demand")]]
+    r = run(which, pods(1, volume_requirements=[[req(ZONE_LABEL, "In", "test-zone-3")]], node_affinity_required=terms))
+    assert not r.pod_errors and zone_of(r.new_node_claims[0]) == "test-zone-3"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_volume_zone_does_not_restrict_spread_domains(which):  # nodeclaim.go:160-176: the spread still sees three zones
+    tsc = [TopologySpreadConstraint(1, ZONE_LABEL, SEL)]
+    # all pods mount a zone-1 volume: the first lands in zone 1; the skew over zones 1, 2, 3 (0 pods in 2 and 3) then
+    # blocks the others, which a pod whose OWN requirement were zone 1 would not be
+    r = run(which, pods(3, labels=LABELS, topology_spread_constraints=tsc,
+                        volume_requirements=[[req(ZONE_LABEL, "In", "test-zone-1")]]))
+    assert len(r.pod_errors) == 2 and zone_of(r.new_node_claims[0]) == "test-zone-1"
+    r = run(which, pods(3, labels=LABELS, topology_spread_constraints=tsc, node_selector={ZONE_LABEL: "test-zone-1"}))
+    assert not r.pod_errors
