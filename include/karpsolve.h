@@ -37,7 +37,7 @@ typedef enum kp_status {
   KP_ERR_INVALID = 2,      /* malformed problem */
   KP_ERR_CUDA = 3,         /* device / driver failure; message via kp_last_error */
   KP_ERR_CAPACITY = 4,     /* a compiled limit was exceeded (e.g. > KP_MAX_RESOURCES) */
-  KP_ERR_UNSUPPORTED = 5   /* feature of the reference not built yet (minValues, reserved offerings, host ports) */
+  KP_ERR_UNSUPPORTED = 5   /* feature of the reference not built yet (reserved offerings, host ports, minValues in kp_consolidate) */
 } kp_status;
 
 /* ---- requirement encoding --------------------------------------------------------------------------------------
@@ -217,7 +217,21 @@ typedef struct kp_problem {
   const int32_t* run_class;
   const int32_t* run_node;
 
+  /* ---- minValues (InstanceTypes.SatisfiesMinValues, pkg/cloudprovider/types.go:301-337) ----
+   * For every key some requirement carries minValues on: the values instanceType.Requirements.Get(key).Values() of each
+   * instance type, as ids that only need to be distinct per key (the 64-value masks cannot serve: value compaction folds
+   * unmentioned values, and "how many different instance types / families are left" is exactly about those).
+   * All NULL / 0 when no requirement has minValues. */
+  int32_t n_minvalue_keys;           /* M */
+  const int32_t* minvalue_key;       /* [M] key index */
+  const int32_t* minvalue_it_off;    /* [M * n_its + 1] CSR over (m, instance type) */
+  const int32_t* minvalue_it_vals;   /* value ids */
+
   /* ---- options (scheduler.go:87-114) ---- */
+  /* MinValuesPolicy (scheduler.go:110-114): 0 = Strict: a NodeClaim whose remaining instance types offer fewer distinct
+   * values than minValues is refused (nodeclaim.go:464-475).  1 = BestEffort: minValues never refuses; the relaxed value
+   * the reference writes back (nodeclaim.go:186-191) is min(minValues, distinct values of the final claim_its), which the
+   * decoder derives from the result. */
   int32_t min_values_best_effort;
   int32_t claim_order_mode; /* 0 = Go sort.Slice (pdqsort_func) tie order, 1 = stable */
 } kp_problem;

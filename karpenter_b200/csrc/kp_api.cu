@@ -257,6 +257,12 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(up(h, &d.cls_rs, t.cls_rs));
   CK(up(h, &d.cls_tolset, t.cls_tolset));
   CK(up(h, &d.cls_relax, t.cls_relax));
+  d.mv_strict = t.min_values_strict ? 1 : 0;
+  CK(up(h, &d.tmpl_mv_off, t.tmpl_mv_off));
+  CK(up(h, &d.tmpl_mv_key, t.tmpl_mv_key));
+  CK(up(h, &d.tmpl_mv_need, t.tmpl_mv_need));
+  CK(up(h, &d.mv_val_off, t.mv_val_off));
+  CK(up(h, &d.mv_masks, t.mv_masks));
   CK(up(h, &d.cls_match, t.cls_match));
   CK(up(h, &d.cls_rec, t.cls_rec));
   {  // class rows (one indirection less on the per-pod path)
@@ -864,6 +870,10 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   if (rc != KP_OK) return rc;
   HostTables& t = h->host;
   KpDev& d = h->dev;
+  if (t.has_min_values) {  // RemoveInstanceTypeOptionsByPriceAndMinValues / Truncate with minValues (nodeclaim.go:309-318)
+    h->err = "consolidation with minValues on a NodePool is not supported yet";
+    return KP_ERR_UNSUPPORTED;
+  }
   const int K = t.K, R = t.R, ITW = t.ITW, E = t.E, N = t.N, T = t.T;
   const bool general = t.G > 0;  // the evicted pods carry topology constraints: one full solve per candidate set
   auto t_begin = std::chrono::steady_clock::now();

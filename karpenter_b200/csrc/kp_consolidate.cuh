@@ -512,7 +512,12 @@ struct ConsolShared {
   ConsolWarp w[CONSOL_WARPS];
 };
 
-__global__ void __launch_bounds__(CONSOL_WARPS * 32) k_consolidate(const __grid_constant__ KpDev d_in,
+// Two CTAs per SM (<= 128 registers, a few spills): the chain of one subset is latency-bound, so resident warps are what
+// fills the issue slots.  Pinned because ptxas otherwise flips between 128 and 248 registers on unrelated edits.
+#ifndef CONSOL_MIN_CTAS
+#define CONSOL_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolidate(const __grid_constant__ KpDev d_in,
                                                                     const __grid_constant__ KpConsol q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ConsolShared& sh = *reinterpret_cast<ConsolShared*>(smem_raw);

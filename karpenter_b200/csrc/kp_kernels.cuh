@@ -403,6 +403,22 @@ __device__ __forceinline__ void topo_record(const KpDev& d, const PodCtx& px, co
   }
 }
 
+// InstanceTypes.SatisfiesMinValues (cloudprovider/types.go:301-337) for a NodeClaim of template n whose remaining
+// instance types are `its` (word `lane` of the bitmap): every key with minValues must still see that many distinct values.
+// One ballot per value, stopping as soon as enough were seen.  Warp-uniform result.
+__device__ __forceinline__ bool min_values_ok(const KpDev& d, int n, uint64_t its, int lane) {
+  for (int e = d.tmpl_mv_off[n]; e < d.tmpl_mv_off[n + 1]; e++) {
+    const int m = d.tmpl_mv_key[e], need = d.tmpl_mv_need[e];
+    int seen = 0;
+    for (int v = d.mv_val_off[m]; v < d.mv_val_off[m + 1] && seen < need; v++) {
+      const bool hit = lane < d.ITW && (its & d.mv_masks[(size_t)v * d.ITW + lane]) != 0;
+      seen += __any_sync(FULL, hit) ? 1 : 0;
+    }
+    if (seen < need) return false;
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // K1: feasibility of (class, template) pairs without topology. grid-stride over pairs, one warp each.
 __global__ void __launch_bounds__(256) k_feasibility(KpDev d, uint64_t* out, int prefilter_only) {
@@ -423,6 +439,7 @@ __global__ void __launch_bounds__(256) k_feasibility(KpDev d, uint64_t* out, int
       uint64_t fw;
       w = filter_its_word(d, scratch, 0, lane, &fw) & its;
       __syncwarp();
+      if (d.mv_strict && !min_values_ok(d, n, w, lane)) w = 0;  // scheduler.go:147-156: the template is skipped
       if (lane < d.ITW) d.tmpl_its[(size_t)n * d.ITW + lane] = w;
     } else {
       bool tol_ok = tolerated(d, d.cls_tolset[X], d.tmpl_taintset[n]);

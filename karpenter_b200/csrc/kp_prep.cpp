@@ -153,7 +153,6 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
     for (int e = p->reqset_off[s]; e < p->reqset_off[s + 1]; e++) {
       int k = p->req_key[e];
       uint8_t f = p->req_flags[e];
-      if (f & KP_REQ_HAS_MINVALUES) return err = "minValues is not supported yet", KP_ERR_UNSUPPORTED;
       if (k == h.hostname_key) return err = "requirements on kubernetes.io/hostname are not supported yet", KP_ERR_UNSUPPORTED;
       Slot in;
       in.f = SF_PRESENT | ((f & KP_REQ_COMPLEMENT) ? SF_COMPLEMENT : 0) | ((f & KP_REQ_HAS_GTE) ? SF_HAS_GTE : 0) |
@@ -308,6 +307,66 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
     }
     h.tmpl_limit_present[n] = p->tmpl_limit_present ? p->tmpl_limit_present[n] : 0;
   }
+  // ---- minValues (cloudprovider/types.go:301-337) ----
+  // Only NodePool requirements can carry minValues (pods have none), and Requirements.Add keeps the larger one
+  // (requirement.go:180), so a NodeClaim's minValues are its template's.  Per key with minValues: one instance-type
+  // bitmap per distinct value; SatisfiesMinValues == "at least `need` of those bitmaps meet the remaining types".
+  h.tmpl_mv_off.assign(1, 0);
+  h.mv_val_off.assign(1, 0);
+  {
+    const int M = p->n_minvalue_keys;
+    for (int m = 0; m < M; m++) {
+      std::map<int32_t, int> dense;
+      size_t base = h.mv_masks.size();
+      for (int t = 0; t < T; t++) {
+        size_t row = (size_t)m * T + t;
+        for (int i = p->minvalue_it_off[row]; i < p->minvalue_it_off[row + 1]; i++) {
+          auto ins = dense.emplace(p->minvalue_it_vals[i], (int)dense.size());
+          if (ins.second) h.mv_masks.resize(h.mv_masks.size() + std::max(ITW, 1), 0);
+          h.mv_masks[base + (size_t)ins.first->second * ITW + (t >> 6)] |= 1ull << (t & 63);
+        }
+      }
+      h.mv_val_off.push_back(h.mv_val_off.back() + (int)dense.size());
+    }
+    for (int n = 0; n < N; n++) {
+      std::map<int, int> need;  // key -> minValues
+      int s = p->tmpl_reqset[n];
+      for (int e = p->reqset_off[s]; e < p->reqset_off[s + 1]; e++)
+        if (p->req_flags[e] & KP_REQ_HAS_MINVALUES) {
+          int& v = need[p->req_key[e]];
+          v = std::max(v, p->req_min_values[e]);
+        }
+      for (auto& kv : need) {
+        int m = -1;
+        for (int i = 0; i < M; i++)
+          if (p->minvalue_key[i] == kv.first) m = i;
+        if (m < 0) {  // no table for the key: no instance type offers a value (Get(key).Values() is empty everywhere)
+          if (kv.second > 0) m = M;  // sentinel: an empty value range, never satisfiable
+          else continue;
+        }
+        h.tmpl_mv_key.push_back(m);
+        h.tmpl_mv_need.push_back(kv.second);
+        h.has_min_values = true;
+      }
+      h.tmpl_mv_off.push_back((int)h.tmpl_mv_key.size());
+    }
+    h.mv_val_off.push_back(h.mv_val_off.back());  // the sentinel's empty range
+    if (h.mv_masks.empty()) h.mv_masks.assign(1, 0);
+    if (h.tmpl_mv_key.empty()) {
+      h.tmpl_mv_key.assign(1, 0);
+      h.tmpl_mv_need.assign(1, 0);
+    }
+    // minValues on any other requirement set (a pod, an instance type) has no meaning in the reference's API
+    for (int s = 0; s < p->n_reqsets; s++) {
+      bool is_tmpl = false;
+      for (int n = 0; n < N; n++) is_tmpl |= p->tmpl_reqset[n] == s;
+      if (is_tmpl) continue;
+      for (int e = p->reqset_off[s]; e < p->reqset_off[s + 1]; e++)
+        if (p->req_flags[e] & KP_REQ_HAS_MINVALUES)
+          return err = "minValues outside NodePool requirements", KP_ERR_INVALID;
+    }
+  }
+  h.min_values_strict = h.has_min_values && !p->min_values_best_effort;
   // ---- existing nodes ----
   h.node_taintset.assign(std::max(E, 1), -1);
   h.node_flags.assign(std::max(E, 1), 0);

@@ -43,6 +43,11 @@ struct HostTables {
   std::vector<uint32_t> tmpl_limit_present;
   std::vector<int64_t> cls_req;
   std::vector<int32_t> cls_relax;  // class after one Preferences.Relax step, -1: none
+  // minValues: per template a list of (table m, need); per table m the value range [mv_val_off[m], mv_val_off[m+1]) of
+  // instance-type bitmaps mv_masks[value * ITW ..]
+  bool has_min_values = false, min_values_strict = false;
+  std::vector<int32_t> tmpl_mv_off, tmpl_mv_key, tmpl_mv_need, mv_val_off;
+  std::vector<uint64_t> mv_masks;
   std::vector<int32_t> cls_rs, cls_strict_rs, cls_tolset, cls_rv, cls_match_off, cls_match, cls_rec_off, cls_rec;
   std::vector<int64_t> cls_sort_cpu, cls_sort_mem;
   std::vector<KpGroup> groups;

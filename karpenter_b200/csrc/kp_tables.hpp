@@ -109,6 +109,14 @@ struct KpDev {
   const int32_t* cls_rs;          // [X]
   const int32_t* cls_tolset;      // [X]
   const int32_t* cls_relax;       // [X] class after one Preferences.Relax step (preferences.go:38-57), -1: none
+  // minValues, Strict policy (cloudprovider/types.go:301-337): template n must keep, for each e in
+  // [tmpl_mv_off[n], tmpl_mv_off[n+1]), tmpl_mv_need[e] distinct values of table tmpl_mv_key[e]
+  int mv_strict;                  // 0: no template carries minValues (or BestEffort): nothing is checked
+  const int32_t* tmpl_mv_off;     // [N+1]
+  const int32_t* tmpl_mv_key;
+  const int32_t* tmpl_mv_need;
+  const int32_t* mv_val_off;      // [M+2]
+  const uint64_t* mv_masks;       // [values * ITW] instance types that offer the value
   int n_rv;
   const int32_t* cls_match;       // groups that constrain a class (owned + inverse selecting it); bit 30 = selects(pod)
   const int32_t* cls_rec;         // groups that may count a class on Record (select it / inverse owned)

@@ -673,7 +673,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       sc.hend = px.hend;
       sc.first_clear = -1;
       sc.first_rclear = -1;
-      const bool fast_ok = fbit != 0 && px.roff == px.rend;  // topology-free and counted by no topology group
+      // topology-free and counted by no topology group (and no minValues to re-check on the shrinking type list)
+      const bool fast_ok = fbit != 0 && px.roff == px.rend && !d.mv_strict;
       int lbf = 0, lbr = 0;
       if (fbit) lbf = __shfl_sync(FULL, fsig < 32 ? lb0 : lb1, fsig & 31);
       if (rbit) lbr = __shfl_sync(FULL, rv < 32 ? lr0 : lr1, rv & 31);
@@ -745,6 +746,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           claim_load(d, I, cc, lane, &b, &bq, &bi, &bj);
           evals++;
           Eval ev = eval_candidate(d, px, true, b, bq, bi, bj, E + cc, scratch, lane);
+          // Strict minValues (nodeclaim.go:464-475): the surviving types must still span enough distinct values
+          if (d.mv_strict && ev.ok && !min_values_ok(d, I.c_tmpl[cc], ev.its, lane)) ev.ok = false;
           if (fbit && !ev.compat_fail && !ev.changed && lane == 0) I.amask[cc] |= fbit;
           if (!ev.ok) {
             if (lane == 0) {
@@ -838,6 +841,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       Slot b = lane < K ? rs_slot(d, d.tmpl_rs[n], lane) : slot_absent();
       const int64_t bq = lane < R ? d.tmpl_daemon[(size_t)n * R + lane] : 0;
       Eval ev = eval_candidate(d, px, true, b, bq, tw, -1, E + cnew, scratch, lane);
+      if (d.mv_strict && ev.ok && !min_values_ok(d, n, ev.its, lane)) ev.ok = false;
       if (!ev.ok) continue;
       // NewNodeClaim + Add
       claim_store(d, I, cnew, lane, ev, true);

@@ -175,6 +175,7 @@ class ProblemBuilder:
         self.pod_arrays = None
         self.max_values_per_key = 64  # width of the per-key value mask; wider keys go through value compaction
         self.preference_policy = "Respect"  # or "Ignore": scheduler.IgnorePreferences (scheduler.go:81-101)
+        self.min_values_policy = "Strict"   # or "BestEffort": scheduler.MinValuesPolicy (scheduler.go:110-114)
 
     # ---- resources ----
     def res_index(self, name: str) -> int:
@@ -585,11 +586,39 @@ class ProblemBuilder:
         P.set("n_running", len(self.running))
         P.set("run_class", [r[0] for r in self.running])
         P.set("run_node", [node_pos[r[1]] for r in self.running])
-        P.set("min_values_best_effort", 0)
+        # minValues tables (cloudprovider/types.go:301-337): per key with minValues, the RAW values of every instance type
+        mv_keys = sorted({r[0] for t in self.templates for r in self.reqsets.rows[t["reqset"]] if r[5] is not None},
+                         key=lambda k: key_id[k])
+        mv_off, mv_vals = [0], []
+        for k in mv_keys:
+            ids: Dict[str, int] = {}
+            for it in self.its:
+                for r in self.reqsets.rows[it["reqset"]]:
+                    if r[0] == k:
+                        mv_vals.extend(ids.setdefault(v, len(ids)) for v in r[2])
+                mv_off.append(len(mv_vals))
+        P.set("n_minvalue_keys", len(mv_keys))
+        P.set("minvalue_key", [key_id[k] for k in mv_keys])
+        P.set("minvalue_it_off", mv_off)
+        P.set("minvalue_it_vals", mv_vals)
+        self.minvalue_keys = mv_keys
+        P.set("min_values_best_effort", 1 if self.min_values_policy == "BestEffort" else 0)
         P.set("claim_order_mode", self.claim_order_mode)
-        return EncodedProblem(P, keys, {k: sorted(values[k]) for k in keys}, list(self.resources),
-                              [it["name"] for it in self.its], [t["name"] for t in tmpls], [n["name"] for n in nodes],
-                              node_pos, nodes)
+        enc = EncodedProblem(P, keys, {k: sorted(values[k]) for k in keys}, list(self.resources),
+                             [it["name"] for it in self.its], [t["name"] for t in tmpls], [n["name"] for n in nodes],
+                             node_pos, nodes)
+        # what the decoder needs to report minValues per NodeClaim (nodeclaim.go:186-191)
+        enc.min_values_policy = self.min_values_policy
+        enc.tmpl_min_values = []
+        for t in tmpls:
+            need: Dict[str, int] = {}
+            for r in self.reqsets.rows[t["reqset"]]:
+                if r[5] is not None:
+                    need[r[0]] = max(need.get(r[0], 0), r[5])  # Requirements.Add keeps the larger (requirement.go:180)
+            enc.tmpl_min_values.append(need)
+        enc.it_min_value_sets = {k: [{v for r in self.reqsets.rows[it["reqset"]] if r[0] == k for v in r[2]} for it in self.its]
+                                 for k in mv_keys}
+        return enc
 
 
 def _neg_str(s: str):
@@ -632,6 +661,25 @@ class EncodedProblem:
                                 gte=int(res["claim_req_gte"][claim, k]) if f & 2 else None,
                                 lte=int(res["claim_req_lte"][claim, k]) if f & 4 else None)
             woff += words
+        return out
+
+    def decode_min_values(self, res: dict, claim: int) -> Dict[str, dict]:
+        """minValues of the NodeClaim's requirements.  Strict: the NodePool's.  BestEffort: lowered to the number of distinct
+        values the final instance-type options offer whenever that is less (nodeclaim.go:186-191, scheduler.go:658-667)."""
+        need = self.tmpl_min_values[int(res["claim_template"][claim])]
+        if not need:
+            return {}
+        out = {}
+        its = None
+        for key, n in need.items():
+            mv = n
+            if self.min_values_policy == "BestEffort":
+                if its is None:
+                    w = res["claim_its"][claim]
+                    its = [t for t in range(len(self.it_names)) if int(w[t >> 6]) >> (t & 63) & 1]
+                have = len(set().union(*[self.it_min_value_sets[key][t] for t in its])) if its else 0
+                mv = min(n, have)
+            out[key] = dict(min_values=mv, relaxed=mv < n)
         return out
 
     def decode_its(self, res: dict, claim: int) -> List[str]:

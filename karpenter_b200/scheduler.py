@@ -31,13 +31,14 @@ class Scheduler:
     def __init__(self, node_pools: Sequence[NodePool], instance_types: Dict[str, List[InstanceType]],
                  state_nodes: Sequence[StateNode] = (), daemon_overhead: Optional[Dict[str, dict]] = None,
                  claim_order: str = "go", backend: Optional[Callable] = None, device: int = -1,
-                 preference_policy: str = "Respect"):
+                 preference_policy: str = "Respect", min_values_policy: str = "Strict"):
         self.node_pools = list(node_pools)
         self.instance_types = instance_types
         self.state_nodes = list(state_nodes)
         self.daemon_overhead = daemon_overhead or {}
         self.claim_order = claim_order
         self.preference_policy = preference_policy  # "Ignore" == scheduler.IgnorePreferences (scheduler.go:81-101)
+        self.min_values_policy = min_values_policy  # "BestEffort" == MinValuesPolicyBestEffort (scheduler.go:110-114)
         self._backend = backend
         self._device = device
         self._handle = None
@@ -47,6 +48,7 @@ class Scheduler:
         b = ProblemBuilder()
         b.claim_order_mode = 1 if self.claim_order == "stable" else 0
         b.preference_policy = self.preference_policy
+        b.min_values_policy = self.min_values_policy
         index: Dict[int, int] = {}
         for np_ in self.node_pools:
             ids = []
@@ -97,9 +99,12 @@ class Scheduler:
             else:
                 by_claim.setdefault(-2 - t, []).append(p)
         for k in range(res["n_claims"]):
+            reqs = enc.decode_requirements(res, k)
+            for key, mv in enc.decode_min_values(res, k).items():
+                reqs.setdefault(key, dict(complement=True, values=[], gte=None, lte=None)).update(mv)
             claims.append(NodeClaimResult(
                 nodepool=enc.tmpl_names[int(res["claim_template"][k])], pods=by_claim.get(k, []),
-                instance_type_options=enc.decode_its(res, k), requirements=enc.decode_requirements(res, k),
+                instance_type_options=enc.decode_its(res, k), requirements=reqs,
                 requests={r: int(v) for r, v in zip(enc.resources, res["claim_requests"][k])},
                 rank=int(res["claim_rank"][k])))
         claims.sort(key=lambda c: c.rank)  # the order of Results.NewNodeClaims

@@ -110,7 +110,26 @@ struct Scheduler {
     return false;
   }
 
-  // nodeclaim.go:412-480 (minValues: KP_ERR_UNSUPPORTED is raised up front)
+  // InstanceTypes.SatisfiesMinValues (cloudprovider/types.go:301-337): for every requirement that carries minValues, the
+  // instance types together must offer at least that many distinct values of its key
+  bool satisfies_min_values(const std::vector<int>& its, const Requirements& reqs) const {
+    for (auto& kv : reqs.m) {
+      if (!kv.second.has_min) continue;
+      int m = -1;
+      for (int i = 0; i < p->n_minvalue_keys; i++)
+        if (p->minvalue_key[i] == kv.first) m = i;
+      std::set<int32_t> values;
+      if (m >= 0)
+        for (int it : its) {
+          size_t row = (size_t)m * p->n_its + it;
+          values.insert(p->minvalue_it_vals + p->minvalue_it_off[row], p->minvalue_it_vals + p->minvalue_it_off[row + 1]);
+        }
+      if ((int)values.size() < kv.second.min_values) return false;
+    }
+    return true;
+  }
+
+  // nodeclaim.go:412-480
   std::vector<int> filter_instance_types(const std::vector<int>& its, const Requirements& reqs, const Res& total) const {
     std::vector<int> remaining;
     for (int it : its) {
@@ -119,6 +138,8 @@ struct Scheduler {
       bool it_off = offering_compatible(reqs, it);
       if (it_compat && it_fits && it_off) remaining.push_back(it);
     }
+    // nodeclaim.go:464-475: Strict refuses the NodeClaim, BestEffort lowers minValues and carries on
+    if (!p->min_values_best_effort && reqs.has_min_values() && !satisfies_min_values(remaining, reqs)) remaining.clear();
     return remaining;
   }
 
@@ -596,7 +617,6 @@ int orc_solve(const kp_problem* p, kp_result* out) { return orc_solve_mt(p, out,
 
 // threads > 1: in-flight candidates are evaluated by a worker pool like the reference's parallelizeUntil
 int orc_solve_mt(const kp_problem* p, kp_result* out, int threads) {
-  if (has_min_values(p)) return KP_ERR_UNSUPPORTED;
   if (p->n_resources > KP_MAX_RESOURCES) return KP_ERR_CAPACITY;
   Prob P(p);
   Scheduler s(P);

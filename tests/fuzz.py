@@ -174,6 +174,10 @@ def soften(seed: int, pools, pl: List[Pod]):
     for pool in pools:
         if rng.random() < 0.25:
             pool.taints = list(pool.taints) + [Taint("soft", "x", "PreferNoSchedule")]
+        if rng.random() < 0.25:  # minValues: keep a NodeClaim flexible across instance types / sizes / architectures
+            k = rng.choice([INSTANCE_TYPE_LABEL, INSTANCE_TYPE_LABEL, fake.LABEL_INSTANCE_SIZE, ARCH_LABEL])
+            pool.requirements = list(pool.requirements) + [
+                NodeSelectorRequirement(k, "Exists", (), rng.choice([2, 3, 5]) if k == INSTANCE_TYPE_LABEL else 2)]
     shapes = {}
     for p in pl:
         shapes.setdefault(id(p.tolerations), []).append(p)  # pods(): the kwargs of one deployment share their lists

@@ -1,0 +1,12 @@
+"""C4 consolidation with the stock library (2 CTAs / SM) and with a -DCONSOL_MIN_CTAS=1 build: which occupancy wins."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from karpenter_b200 import _abi, _native, workloads
+if len(sys.argv) > 1:
+    _native.LIB_PATH = sys.argv[1]
+enc, consol = workloads.config_c4()
+h = _native.Handle()
+for _ in range(4):
+    res = h.consolidate(enc.problem, _abi.ConsolInput(**consol))
+    print(sys.argv[1:] or "stock", res["solve_ms"])
+h.close()
