@@ -411,6 +411,10 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(up_mut(h, &d.dom_cnt, t.dom_cnt));
   CK(up_mut(h, &d.dom_reg, t.dom_reg));
   CK(up_mut(h, &d.dom_pop, t.dom_pop));
+  CK(up_mut(h, &d.g_born, t.g_born));
+  CK(up_mut(h, &d.g_birth, t.g_birth));
+  CK(up(h, &d.cls_lazy_off, t.cls_lazy_off));
+  CK(up(h, &d.cls_lazy, t.cls_lazy));
   CK(up_mut(h, &d.g_ndomains, t.g_ndomains));
   CK(up_mut(h, &d.g_nempty, t.g_nempty));
   CK(up(h, &d.node_taintset, t.node_taintset));
@@ -744,8 +748,23 @@ static int download(kp_handle* h, kp_result* out) {
   HostTables& t = h->host;
   std::vector<int32_t> cnt((size_t)std::max(t.G, 1) * 64);
   CK(cudaMemcpy(cnt.data(), d.dom_cnt, cnt.size() * 4, cudaMemcpyDeviceToHost));
+  // order of the reference's maps: groups of NewTopology in creation order, then the groups relaxed pods created, in
+  // birth order (the ones never born do not exist), then the inverse groups
+  std::vector<int32_t> birth(std::max(t.G, 1));
+  CK(cudaMemcpy(birth.data(), d.g_birth, birth.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<int> gorder;
+  for (int g = 0; g < t.n_regular; g++)
+    if (!t.groups[g].lazy) gorder.push_back(g);
+  {
+    std::vector<std::pair<int, int>> born;
+    for (int g = 0; g < t.n_regular; g++)
+      if (t.groups[g].lazy && birth[g] >= 0) born.push_back({birth[g], g});
+    std::sort(born.begin(), born.end());
+    for (auto& b : born) gorder.push_back(b.second);
+  }
+  for (int g = t.n_regular; g < t.G; g++) gorder.push_back(g);
   std::vector<int32_t> off{0}, flat;
-  for (int g = 0; g < t.G; g++) {
+  for (int g : gorder) {
     int key = t.groups[g].key;
     if (key != t.hostname_key) {
       int nv = h->key_nvalues[key];
@@ -753,7 +772,7 @@ static int download(kp_handle* h, kp_result* out) {
     }
     off.push_back((int32_t)flat.size());
   }
-  out->n_groups = t.G;
+  out->n_groups = (int32_t)gorder.size();
   out->n_domain_slots = (int32_t)flat.size();
   out->group_domain_off = (int32_t*)malloc(off.size() * 4);
   memcpy(out->group_domain_off, off.data(), off.size() * 4);

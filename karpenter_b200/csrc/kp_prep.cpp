@@ -611,10 +611,10 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   std::vector<uint8_t> seen_cls(std::max(X, 1), 0);
   // A pod that fails is retried as its relaxed class (Preferences.Relax, preferences.go:38-57) after a Topology.Update
   // of the relaxed pod.  The relaxed classes are made owners of their groups up front, behind the pending classes.
-  // That is the reference's behaviour as long as a relaxed pod only reuses groups some pending pod created at
-  // NewTopology time (dropping a preferred term, a ScheduleAnyway spread, a toleration).  A relaxation that changes a
-  // group's identity (dropping a required node-affinity term changes the node filter of an Honor spread) would have the
-  // reference create a fresh group in the middle of the solve, blind to the pods already placed: not built, refused.
+  // A group only relaxed classes own is one the reference creates in the middle of the solve (the relaxation changed
+  // its identity: the node filter of a spread holds the pod's tolerations and required node-affinity terms,
+  // topologynodefilter.go:30-64): it is built here with its cluster counts and marked lazy; the solver gives birth to
+  // it when a pod is first tried as the relaxed class (KpDev::g_born).
   std::vector<int32_t> pending_closure;
   for (int cls0 : pending_classes)
     if (!seen_cls[cls0]) {
@@ -629,24 +629,15 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
       for (int c = p->class_relax_next[x]; c >= 0; c = p->class_relax_next[c])
         if (c >= X || ++steps > X) return err = "class_relax_next out of range or cyclic", KP_ERR_INVALID;
     }
-  auto group_hashes = [&](int cls) {
-    std::set<std::string> out;
-    for (int ci = p->class_tsc_off[cls]; ci < p->class_tsc_off[cls + 1]; ci++) out.insert(hash_of(make_group(cls, ci, false)));
-    return out;
-  };
   for (size_t i = 0; i < n_direct; i++)
-    for (int prev = pending_closure[i], c = p->class_relax_next ? p->class_relax_next[prev] : -1; c >= 0 && !seen_cls[c];
-         prev = c, c = p->class_relax_next[c]) {
-      const std::set<std::string> have = group_hashes(prev);
-      for (const std::string& hk : group_hashes(c))
-        if (!have.count(hk))
-          return err = "relaxing a pod would create a new topology group mid-solve (spread with nodeAffinityPolicy Honor "
-                       "and several required node-affinity terms): not supported yet",
-                 KP_ERR_UNSUPPORTED;
+    for (int c = p->class_relax_next ? p->class_relax_next[pending_closure[i]] : -1; c >= 0 && !seen_cls[c];
+         c = p->class_relax_next[c]) {
       seen_cls[c] = 1;
       pending_closure.push_back(c);
     }
-  for (int cls : pending_closure) {
+  std::vector<std::vector<int>> cls_lazy(std::max(X, 1));
+  for (size_t pi = 0; pi < pending_closure.size(); pi++) {
+    const int cls = pending_closure[pi];
     bool anti = false;
     for (int ci = p->class_tsc_off[cls]; ci < p->class_tsc_off[cls + 1]; ci++)
       anti |= p->tsc_type[ci] == KP_TOPO_ANTI_AFFINITY && !(p->tsc_preferred && p->tsc_preferred[ci]);
@@ -673,6 +664,7 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
           if (!filter_matches(g, p->node_taintset[node], [&](int k) { return node_slot(node, k); })) continue;
           group_record(g, d);
         }
+        g.g.lazy = pi >= n_direct ? 1 : 0;
         gi = (int)regular.size();
         reg_index[hk] = gi;
         regular.push_back(std::move(g));
@@ -680,14 +672,26 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
         gi = it->second;
       }
       regular[gi].owners.insert(cls);
+      if (regular[gi].g.lazy && std::find(cls_lazy[cls].begin(), cls_lazy[cls].end(), gi) == cls_lazy[cls].end())
+        cls_lazy[cls].push_back(gi);
     }
   }
-  // NewExistingNode registers every schedulable node's hostname in every hostname group (existingnode.go:64)
+  // NewExistingNode registers every schedulable node's hostname in every hostname group that exists when the
+  // Scheduler is built (existingnode.go:64); a group born later only knows the nodes countDomains registered
   for (auto* vec : {&regular, &inverse})
     for (auto& g : *vec)
-      if (g.g.key == h.hostname_key)
+      if (g.g.key == h.hostname_key && !g.g.lazy)
         for (int n = 0; n < E; n++)
           if (node_active[n]) g.host_reg.insert(n);
+  h.n_regular = (int)regular.size();
+  h.cls_lazy_off.assign(1, 0);
+  h.cls_lazy.clear();
+  for (int x = 0; x < X; x++) {
+    for (int gi : cls_lazy[x]) h.cls_lazy.push_back(gi);  // regular groups keep their index in the flattened table
+    h.cls_lazy_off.push_back((int)h.cls_lazy.size());
+  }
+  if (X == 0) h.cls_lazy_off.push_back(0);
+  if (h.cls_lazy.empty()) h.cls_lazy.push_back(0);
 
   // ---- flatten groups: regular first (creation order), then inverse ----
   int G = (int)(regular.size() + inverse.size());
@@ -731,9 +735,17 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   if (h.filter_rs.empty()) h.filter_rs.push_back(0);
   h.GH = GH;
   h.host_cnt_nodes.assign((size_t)std::max(GH, 1) * std::max(E, 1), 0);
-  for (int gi = 0; gi < G; gi++)
-    if (all[gi]->g.host_row >= 0)
-      for (auto& kv : all[gi]->host_cnt) h.host_cnt_nodes[(size_t)all[gi]->g.host_row * E + kv.first] = kv.second;
+  h.g_born.assign(std::max(G, 1), 1);
+  h.g_birth.assign(std::max(G, 1), -1);
+  for (int gi = 0; gi < G; gi++) {
+    if (all[gi]->g.lazy) h.g_born[gi] = 0;
+    if (all[gi]->g.host_row < 0) continue;
+    int32_t* row = h.host_cnt_nodes.data() + (size_t)all[gi]->g.host_row * E;
+    if (all[gi]->g.lazy)
+      for (int n = 0; n < E; n++)
+        if (!all[gi]->host_reg.count(n)) row[n] = KP_HOST_UNREG;
+    for (auto& kv : all[gi]->host_cnt) row[kv.first] = kv.second;
+  }
   // per-class lists. selects(group, class) only depends on (labelset, namespace): evaluate per distinct pair, and
   // use the first In-expression of a selector to enumerate candidate pairs instead of scanning all of them.
   std::map<std::pair<int, int>, int> pair_id;

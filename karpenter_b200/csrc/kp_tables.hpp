@@ -59,7 +59,12 @@ struct KpGroup {
   int32_t taint_policy, affinity_policy;  // 0 ignore 1 honor 2 unset
   int32_t tolset;
   int32_t host_row;     // row index among hostname groups, -1 otherwise
+  int32_t lazy;         // 1: only a RELAXED pod owns it: the reference creates it in the middle of the solve (see g_born)
 };
+
+// host_cnt entry of a hostname the group never registered (TopologyGroup.domains has no such key): a spread cannot pick
+// it (topologygroup.go:235-247) until a Record creates the entry with count 1 (topologygroup.go:133-141)
+#define KP_HOST_UNREG (-(1 << 30))
 
 // pointers into device memory; filled by the host, passed by value to kernels
 struct KpDev {
@@ -111,6 +116,14 @@ struct KpDev {
   const int32_t* cls_relax;       // [X] class after one Preferences.Relax step (preferences.go:38-57), -1: none
   // minValues, Strict policy (cloudprovider/types.go:301-337): template n must keep, for each e in
   // [tmpl_mv_off[n], tmpl_mv_off[n+1]), tmpl_mv_need[e] distinct values of table tmpl_mv_key[e]
+  // Topology groups the reference creates mid-solve (Topology.Update of a relaxed pod, topology.go:162-194, when the
+  // relaxation changed the group's identity: the node filter holds the pod's tolerations and node-affinity terms,
+  // topologynodefilter.go:30-64).  Until a pod is first tried as the relaxed class the group does not exist: it records
+  // nothing, and NodeClaims opened before its birth never register their hostname with it.
+  int32_t* g_born;                // [G] 1 once the group exists (all but lazy groups: from the start)
+  int32_t* g_birth;               // [G] birth order of lazy groups (-1: never born), for the result's group table
+  const int32_t* cls_lazy_off;    // [X+1] lazy groups of a class, in constraint order
+  const int32_t* cls_lazy;
   int mv_strict;                  // 0: no template carries minValues (or BestEffort): nothing is checked
   const int32_t* tmpl_mv_off;     // [N+1]
   const int32_t* tmpl_mv_key;

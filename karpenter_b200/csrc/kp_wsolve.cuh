@@ -340,7 +340,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
   int nC = 0;
   int pert = PERT_NONE, pert_pos = 0;
   long long ev_existing = 0, ev_inflight = 0, ev_tmpl = 0, commits = 0, slow_sorts = 0, scan_chunks = 0, evals = 0;
-  int n_unsched = 0, n_uninit = 0, status = KP_OK;
+  int n_unsched = 0, n_uninit = 0, status = KP_OK, n_born = 0;
   int32_t* ord = I.order;
   int32_t* cnt = I.cnt_at;
   // templates NewScheduler kept (scheduler.go:147-160)
@@ -900,6 +900,21 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       const int nx = d.cls_relax[Xc];
       if (nx >= 0) {  // Preferences.Relax dropped one soft constraint (preferences.go:38-57): same pod, next class row
         Xc = nx;
+        // Topology.Update of the relaxed pod (scheduler.go:462): groups only relaxed pods own come into being now
+        for (int i = d.cls_lazy_off[nx]; i < d.cls_lazy_off[nx + 1]; i++) {
+          const int g = d.cls_lazy[i];
+          if (d.g_born[g]) continue;
+          const int row = d.groups[g].host_row;
+          if (row >= 0)  // NodeClaims opened earlier never registered their hostname with it (topology.go:251-262)
+            for (int c = lane; c < nC; c += 32) d.host_cnt[(size_t)row * d.H + E + c] = KP_HOST_UNREG;
+          __syncwarp();
+          if (lane == 0) {
+            d.g_born[g] = 1;
+            d.g_birth[g] = n_born;
+          }
+          n_born++;
+          __syncwarp();
+        }
         ClassRegs cur = load_class_regs(d, Xc, li, lane);
         __syncwarp();
         store_class_regs(d, pxw, cur, lane);

@@ -209,10 +209,9 @@ def soften(seed: int, pools, pl: List[Pod]):
         if rng.random() < 0.2:
             kw["pod_affinity_preferred"] = [
                 WeightedPodAffinityTerm(rng.choice([1, 50]), PodAffinityTerm(_selector(rng), rng.choice([HOSTNAME_LABEL, ZONE_LABEL])))]
-        spread = any(t.node_affinity_policy != "Ignore" for t in kw.get("topology_spread_constraints", tscs))
-        # alternatives: the first term is tried first, dropped when the pod does not fit.  (Under a spread that honours
-        # node affinity the relaxation changes the spread's node filter: the case the CUDA path refuses -- kept rare.)
-        if rng.random() < (0.02 if spread else 0.2):
+        # alternatives: the first term is tried first, dropped when the pod does not fit.  (Under a spread the relaxation
+        # changes the spread's node filter, so the reference creates a fresh topology group mid-solve.)
+        if rng.random() < 0.2:
             first = list(group[0].node_affinity_required[0]) if group[0].node_affinity_required else []
             alt = [_req(ZONE_LABEL, "In", rng.choice(ZONES + ["nowhere"]))]
             kw["node_affinity_required"] = [[_req(ZONE_LABEL, "In", rng.choice(["nowhere", ZONES[0]]))] + first, alt + first]

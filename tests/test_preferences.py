@@ -310,3 +310,69 @@ def test_volume_zone_does_not_restrict_spread_domains(which):  # nodeclaim.go:16
     assert len(r.pod_errors) == 2 and zone_of(r.new_node_claims[0]) == "test-zone-1"
     r = run(which, pods(3, labels=LABELS, topology_spread_constraints=tsc, node_selector={ZONE_LABEL: "test-zone-1"}))
     assert not r.pod_errors
+
+
+# ---- topology groups born mid-solve (topology.go:162-194, topologygroup.go:186-202, topologynodefilter.go:30-64) ------
+def _two_pools(which, pod_list):
+    """pool a: untainted, room for a few pods only; pool b: PreferNoSchedule taint (pods reach it after relaxation)"""
+    from karpenter_b200.scheduler import Scheduler
+    from tests import oracle_lib
+    from tests.parity import assert_same
+    a = NodePool(name="a", weight=10, requirements=[req(CAPACITY_TYPE_LABEL, "In", "on-demand")], limits={"cpu": "8"})
+    b = NodePool(name="b", requirements=[req(CAPACITY_TYPE_LABEL, "In", "on-demand")],
+                 taints=[Taint("soft", "x", "PreferNoSchedule")], limits={"cpu": "2000"})
+    its = fake.default_instance_types()
+
+    def go(backend):
+        s = Scheduler([a, b], {"a": its, "b": its}, backend=backend)
+        try:
+            return s.solve(pod_list)
+        finally:
+            s.close()
+    r = go(oracle_lib.solve)
+    if which == "gpu":
+        g = go(None)
+        assert_same(g.raw, r.raw, "born mid-solve ")
+        r = g
+    return r
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_zone_spread_group_born_by_toleration_relaxation(which):
+    # the toleration is part of the spread's node filter, so the relaxed pods get a FRESH zonal spread group that never
+    # saw the pods placed through pool a: both generations are balanced on their own
+    tsc = [TopologySpreadConstraint(1, ZONE_LABEL, SEL)]
+    r = _two_pools(which, pods(12, labels=LABELS, requests={"cpu": "1500m"}, topology_spread_constraints=tsc))
+    assert not r.pod_errors
+    by_pool = {}
+    for c in r.new_node_claims:
+        by_pool.setdefault(c.nodepool, Counter())[zone_of(c)] += len(c.pods)
+    assert set(by_pool) == {"a", "b"}
+    for pool, zones in by_pool.items():
+        assert max(zones.values()) - min(zones.values()) <= 1 or len(zones) < 3, (pool, zones)
+    raw = r.raw
+    assert raw["n_groups"] == 2  # the NewTopology group and the one born when the first pod was relaxed
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_hostname_spread_group_born_by_toleration_relaxation(which):
+    # NodeClaims opened before the relaxed group existed never registered their hostname with it: relaxed pods cannot
+    # join them, whatever room they have
+    tsc = [TopologySpreadConstraint(2, HOSTNAME_LABEL, SEL)]
+    r = _two_pools(which, pods(10, labels=LABELS, requests={"cpu": "1500m"}, topology_spread_constraints=tsc))
+    assert not r.pod_errors
+    assert all(len(c.pods) <= 2 for c in r.new_node_claims)
+    assert {c.nodepool for c in r.new_node_claims} == {"a", "b"}
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_spread_group_born_by_dropping_a_required_term(which):
+    # two alternative node-affinity terms under a zonal spread: the terms are part of the spread's node filter, so the pod
+    # relaxed to its second alternative gets its own spread group
+    tsc = [TopologySpreadConstraint(1, ZONE_LABEL, SEL)]
+    terms = [[req(ZONE_LABEL, "In", "invalid")], [req(ZONE_LABEL, "In", "test-zone-2", "test-zone-3")]]
+    r = run(which, pods(5, labels=LABELS, topology_spread_constraints=tsc, node_affinity_required=terms))
+    zones = Counter(zone_of(c) for c in r.new_node_claims for _ in c.pods)
+    assert not r.pod_errors and sorted(zones.items()) in ([("test-zone-2", 2), ("test-zone-3", 3)],
+                                                          [("test-zone-2", 3), ("test-zone-3", 2)])
+    assert r.raw["n_groups"] == 2
