@@ -94,7 +94,10 @@ struct HGroup {
   int32_t cnt[64];
   std::map<int, int32_t> host_cnt;  // node index -> count (hostname groups)
   std::set<int> host_reg;           // registered hostname domains (node indices)
-  HGroup() { memset(cnt, 0, sizeof(cnt)); }
+  HGroup() {
+    memset(&g, 0, sizeof(g));
+    memset(cnt, 0, sizeof(cnt));
+  }
 };
 
 }  // namespace
