@@ -262,7 +262,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
           int cnt = d.host_cnt[(size_t)G.host_row * d.H + host];
           bool ok;
           if (G.type == KP_TOPO_SPREAD)
-            ok = cnt >= 0 && cnt + (self ? 1 : 0) <= G.max_skew;  // cnt < 0: KP_HOST_UNREG, not a domain of the group
+            ok = cnt + (self ? 1 : 0) <= G.max_skew;
           else if (G.type == KP_TOPO_AFFINITY)
             ok = cnt > 0 || (self && (d.g_ndomains[g] - d.g_nempty[g]) == 0);
           else
@@ -380,7 +380,7 @@ __device__ __forceinline__ void topo_record(const KpDev& d, const PodCtx& px, co
       if (lane == 0) {
         int32_t* c = d.host_cnt + (size_t)G.host_row * d.H + host;
         if (*c == 0) d.g_nempty[g]--;
-        *c = *c < 0 ? 1 : *c + 1;  // Record creates the entry of an unregistered hostname (topologygroup.go:133-141)
+        (*c)++;
       }
     } else {
       uint32_t ff = __shfl_sync(FULL, F.f, G.key);

@@ -744,9 +744,6 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
     if (all[gi]->g.lazy) h.g_born[gi] = 0;
     if (all[gi]->g.host_row < 0) continue;
     int32_t* row = h.host_cnt_nodes.data() + (size_t)all[gi]->g.host_row * E;
-    if (all[gi]->g.lazy)
-      for (int n = 0; n < E; n++)
-        if (!all[gi]->host_reg.count(n)) row[n] = KP_HOST_UNREG;
     for (auto& kv : all[gi]->host_cnt) row[kv.first] = kv.second;
   }
   // per-class lists. selects(group, class) only depends on (labelset, namespace): evaluate per distinct pair, and

@@ -62,9 +62,6 @@ struct KpGroup {
   int32_t lazy;         // 1: only a RELAXED pod owns it: the reference creates it in the middle of the solve (see g_born)
 };
 
-// host_cnt entry of a hostname the group never registered (TopologyGroup.domains has no such key): a spread cannot pick
-// it (topologygroup.go:235-247) until a Record creates the entry with count 1 (topologygroup.go:133-141)
-#define KP_HOST_UNREG (-(1 << 30))
 
 // pointers into device memory; filled by the host, passed by value to kernels
 struct KpDev {
@@ -119,7 +116,8 @@ struct KpDev {
   // Topology groups the reference creates mid-solve (Topology.Update of a relaxed pod, topology.go:162-194, when the
   // relaxation changed the group's identity: the node filter holds the pod's tolerations and node-affinity terms,
   // topologynodefilter.go:30-64).  Until a pod is first tried as the relaxed class the group does not exist: it records
-  // nothing, and NodeClaims opened before its birth never register their hostname with it.
+  // nothing.  (Only spreads can be lazy -- affinity groups have no node filter -- and a spread reads an unregistered
+  // hostname as count 0, topologygroup.go:235-247, so hostnames registered before the birth need no bookkeeping.)
   int32_t* g_born;                // [G] 1 once the group exists (all but lazy groups: from the start)
   int32_t* g_birth;               // [G] birth order of lazy groups (-1: never born), for the result's group table
   const int32_t* cls_lazy_off;    // [X+1] lazy groups of a class, in constraint order

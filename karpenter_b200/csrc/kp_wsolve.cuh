@@ -904,10 +904,6 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         for (int i = d.cls_lazy_off[nx]; i < d.cls_lazy_off[nx + 1]; i++) {
           const int g = d.cls_lazy[i];
           if (d.g_born[g]) continue;
-          const int row = d.groups[g].host_row;
-          if (row >= 0)  // NodeClaims opened earlier never registered their hostname with it (topology.go:251-262)
-            for (int c = lane; c < nC; c += 32) d.host_cnt[(size_t)row * d.H + E + c] = KP_HOST_UNREG;
-          __syncwarp();
           if (lane == 0) {
             d.g_born[g] = 1;
             d.g_birth[g] = n_born;

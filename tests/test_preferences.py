@@ -356,8 +356,7 @@ def test_zone_spread_group_born_by_toleration_relaxation(which):
 
 @pytest.mark.parametrize("which", BACKENDS)
 def test_hostname_spread_group_born_by_toleration_relaxation(which):
-    # NodeClaims opened before the relaxed group existed never registered their hostname with it: relaxed pods cannot
-    # join them, whatever room they have
+    # the relaxed pods count hostnames in their own, fresh group: NodeClaims opened earlier look empty to it
     tsc = [TopologySpreadConstraint(2, HOSTNAME_LABEL, SEL)]
     r = _two_pools(which, pods(10, labels=LABELS, requests={"cpu": "1500m"}, topology_spread_constraints=tsc))
     assert not r.pod_errors
