@@ -398,6 +398,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
           if (l < KP_HDR) c.hdr = hdr[(size_t)x * KP_HDR + l];
           if (l == KP_HDR + 2) c.hdr = (int32_t)(tok[x] & 0xffffffffull);
           if (l == KP_HDR + 3) c.hdr = (int32_t)(tok[x] >> 32);
+          if (l == KP_HDR + 4) c.hdr = t.cls_relax[x];
         }
       CK(up(h, &d.cls_lane, rows));
     }
@@ -411,6 +412,8 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(up_mut(h, &d.dom_cnt, t.dom_cnt));
   CK(up_mut(h, &d.dom_reg, t.dom_reg));
   CK(up_mut(h, &d.dom_pop, t.dom_pop));
+  d.n_lazy = 0;
+  for (int32_t b : t.g_born) d.n_lazy += b == 0;
   CK(up_mut(h, &d.g_born, t.g_born));
   CK(up_mut(h, &d.g_birth, t.g_birth));
   CK(up(h, &d.cls_lazy_off, t.cls_lazy_off));
@@ -754,11 +757,11 @@ static int download(kp_handle* h, kp_result* out) {
   CK(cudaMemcpy(birth.data(), d.g_birth, birth.size() * 4, cudaMemcpyDeviceToHost));
   std::vector<int> gorder;
   for (int g = 0; g < t.n_regular; g++)
-    if (!t.groups[g].lazy) gorder.push_back(g);
+    if (t.g_born[g]) gorder.push_back(g);
   {
     std::vector<std::pair<int, int>> born;
     for (int g = 0; g < t.n_regular; g++)
-      if (t.groups[g].lazy && birth[g] >= 0) born.push_back({birth[g], g});
+      if (!t.g_born[g] && birth[g] >= 0) born.push_back({birth[g], g});
     std::sort(born.begin(), born.end());
     for (auto& b : born) gorder.push_back(b.second);
   }

@@ -211,8 +211,9 @@ struct PodCtx {
     struct {
       int tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend, cls, pod;
       unsigned long long tmpl_ok;  // bit n: template n's taints are tolerated (taints.go:49-66)
+      int relax;                   // class after one Preferences.Relax step, -1: nothing left to relax
     };
-    int hdr[KP_HDR + 4];  // the class header, then class id, pod id, tmpl_ok (lo, hi)
+    int hdr[KP_HDR + 5];  // the class header, then class id, pod id, tmpl_ok (lo, hi), relax
   };
   int64_t req[KP_MAXR];
   Slot pod_slot[KP_MAXK];
@@ -314,7 +315,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
 // A class row in flight between global memory and the shared PodCtx (one warp; lane k: key k, lane r: resource r,
 // lane i < KP_HDR: header word i).
 struct ClassRegs {
-  int hdr;                // lanes 0..KP_HDR+3: header row, class, pod, tmpl_ok lo / hi
+  int hdr;                // lanes 0..KP_HDR+4: header row, class, pod, tmpl_ok lo / hi, relax
   int64_t req;
   Slot pod, strict;
 };
@@ -339,7 +340,7 @@ __device__ __forceinline__ ClassRegs load_class_regs(const KpDev& d, int X, int 
   return c;
 }
 __device__ __forceinline__ void store_class_regs(const KpDev& d, PodCtx& px, const ClassRegs& c, int lane) {
-  if (lane < KP_HDR + 4) px.hdr[lane] = c.hdr;
+  if (lane < KP_HDR + 5) px.hdr[lane] = c.hdr;
   if (lane < d.R) px.req[lane] = c.req;
   if (lane < d.K) {
     px.pod_slot[lane] = c.pod;
@@ -355,7 +356,7 @@ __device__ __forceinline__ void topo_record(const KpDev& d, const PodCtx& px, co
   for (int i = px.roff; i < px.rend; i++) {
     int g = d.cls_rec[i];
     KpGroup G = d.groups[g];
-    if (G.lazy && !d.g_born[g]) continue;  // the reference has not created this group yet
+    if (d.n_lazy && !d.g_born[g]) continue;  // the reference has not created this group yet
     bool counts = true;
     if (!G.inverse) {
       if (G.affinity_policy == 1 && G.filter_n > 0) {

@@ -87,6 +87,7 @@ struct Ctx {
 
 struct HGroup {
   KpGroup g;
+  bool lazy = false;  // only a relaxed class owns it: born mid-solve (KpDev::g_born)
   int nsset, selector;
   std::vector<int> filter;
   std::set<int> owners;
@@ -667,7 +668,7 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
           if (!filter_matches(g, p->node_taintset[node], [&](int k) { return node_slot(node, k); })) continue;
           group_record(g, d);
         }
-        g.g.lazy = pi >= n_direct ? 1 : 0;
+        g.lazy = pi >= n_direct;
         gi = (int)regular.size();
         reg_index[hk] = gi;
         regular.push_back(std::move(g));
@@ -675,7 +676,7 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
         gi = it->second;
       }
       regular[gi].owners.insert(cls);
-      if (regular[gi].g.lazy && std::find(cls_lazy[cls].begin(), cls_lazy[cls].end(), gi) == cls_lazy[cls].end())
+      if (regular[gi].lazy && std::find(cls_lazy[cls].begin(), cls_lazy[cls].end(), gi) == cls_lazy[cls].end())
         cls_lazy[cls].push_back(gi);
     }
   }
@@ -683,7 +684,7 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   // Scheduler is built (existingnode.go:64); a group born later only knows the nodes countDomains registered
   for (auto* vec : {&regular, &inverse})
     for (auto& g : *vec)
-      if (g.g.key == h.hostname_key && !g.g.lazy)
+      if (g.g.key == h.hostname_key && !g.lazy)
         for (int n = 0; n < E; n++)
           if (node_active[n]) g.host_reg.insert(n);
   h.n_regular = (int)regular.size();
@@ -741,7 +742,7 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   h.g_born.assign(std::max(G, 1), 1);
   h.g_birth.assign(std::max(G, 1), -1);
   for (int gi = 0; gi < G; gi++) {
-    if (all[gi]->g.lazy) h.g_born[gi] = 0;
+    if (all[gi]->lazy) h.g_born[gi] = 0;
     if (all[gi]->g.host_row < 0) continue;
     int32_t* row = h.host_cnt_nodes.data() + (size_t)all[gi]->g.host_row * E;
     for (auto& kv : all[gi]->host_cnt) row[kv.first] = kv.second;

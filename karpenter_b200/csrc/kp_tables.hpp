@@ -38,7 +38,7 @@ struct Slot {
 };
 
 // One lane's share of a class row: lane k carries the class's requirement slots on key k, lane r its request for
-// resource r, lane i < KP_HDR header word i (lanes KP_HDR+2, +3: the tolerated-template mask).  32 bytes, so staging a
+// resource r, lane i < KP_HDR header word i (lanes KP_HDR+2, +3: the tolerated-template mask, KP_HDR+4: cls_relax).  32 bytes, so staging a
 // pod is two 16-byte loads per lane.
 struct ClsLane {
   uint64_t pod_m, strict_m;
@@ -59,8 +59,8 @@ struct KpGroup {
   int32_t taint_policy, affinity_policy;  // 0 ignore 1 honor 2 unset
   int32_t tolset;
   int32_t host_row;     // row index among hostname groups, -1 otherwise
-  int32_t lazy;         // 1: only a RELAXED pod owns it: the reference creates it in the middle of the solve (see g_born)
 };
+static_assert(sizeof(KpGroup) == 48, "KpGroup is read by value on the solver's critical path: three 16-byte loads");
 
 
 // pointers into device memory; filled by the host, passed by value to kernels
@@ -118,6 +118,7 @@ struct KpDev {
   // topologynodefilter.go:30-64).  Until a pod is first tried as the relaxed class the group does not exist: it records
   // nothing.  (Only spreads can be lazy -- affinity groups have no node filter -- and a spread reads an unregistered
   // hostname as count 0, topologygroup.go:235-247, so hostnames registered before the birth need no bookkeeping.)
+  int n_lazy;                     // number of such groups (0: nothing below is ever read)
   int32_t* g_born;                // [G] 1 once the group exists (all but lazy groups: from the start)
   int32_t* g_birth;               // [G] birth order of lazy groups (-1: never born), for the result's group table
   const int32_t* cls_lazy_off;    // [X+1] lazy groups of a class, in constraint order

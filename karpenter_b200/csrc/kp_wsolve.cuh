@@ -897,7 +897,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
     }
     if (status != KP_OK) break;
     if (!found) {
-      const int nx = d.cls_relax[Xc];
+      const int nx = px.relax;  // staged with the class row: cls_relax[Xc]
       if (nx >= 0) {  // Preferences.Relax dropped one soft constraint (preferences.go:38-57): same pod, next class row
         Xc = nx;
         // Topology.Update of the relaxed pod (scheduler.go:462): groups only relaxed pods own come into being now
