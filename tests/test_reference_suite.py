@@ -1,0 +1,220 @@
+"""Further cases of the reference's scheduling suite (pkg/controllers/provisioning/scheduling/suite_test.go): instance
+type compatibility, bin-packing, in-flight / existing nodes across provisioning passes.  Same harness as
+test_reference_topology.py (`Cluster`); CPU tier through the oracle, GPU tier bit-identical to it.
+"""
+import random
+
+import pytest
+
+from karpenter_b200 import fake
+from karpenter_b200.model import (ARCH_LABEL, CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, INSTANCE_TYPE_LABEL, OS_LABEL, ZONE_LABEL,
+                                  LabelSelector, NodePool, Offering, Taint, Toleration)
+from tests.test_reference_scenarios import BACKENDS, req
+from tests.test_reference_topology import Cluster, spread, _pool
+
+GPU1, GPU2 = "karpenter.sh/super-great-gpu", "karpenter.sh/even-better-gpu"
+
+
+def nodes_of(c, pods_):
+    return {c.bound[id(p)] for p in pods_}
+
+
+# ---- Instance Type Compatibility (suite_test.go:1246-1519) -----------------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_more_resources_than_any_instance_type(which):  # suite_test.go:1247-1257
+    c = Cluster(which)
+    pl = c.pods(1, requests={"cpu": "512"})
+    c.provision(pl)
+    assert not c.scheduled(pl[0])
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_different_archs_on_different_instances(which):  # suite_test.go:1258-1282
+    c = Cluster(which, pools=[_pool(requirements=[req(ARCH_LABEL, "In", "arm64", "amd64")])])
+    pl = c.pods(1, node_selector={ARCH_LABEL: "amd64"}) + c.pods(1, node_selector={ARCH_LABEL: "arm64"})
+    c.provision(pl)
+    assert len(nodes_of(c, pl)) == 2
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_node_affinity_on_instance_type(which):  # suite_test.go:1283-1303
+    c = Cluster(which, pools=[_pool(requirements=[req(ARCH_LABEL, "In", "arm64", "amd64")])])
+    pl = c.pods(1, node_affinity_required=[[req(INSTANCE_TYPE_LABEL, "In", "arm-instance-type")]])
+    c.provision(pl)
+    assert c.node_of(pl[0]).labels[INSTANCE_TYPE_LABEL] == "arm-instance-type"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_node_affinity_on_operating_system(which):  # suite_test.go:1304-1325: only the arm type offers ios
+    c = Cluster(which, pools=[_pool(requirements=[req(ARCH_LABEL, "In", "arm64", "amd64")])])
+    pl = c.pods(1, node_affinity_required=[[req(OS_LABEL, "In", "ios")]])
+    c.provision(pl)
+    assert c.node_of(pl[0]).labels[INSTANCE_TYPE_LABEL] == "arm-instance-type"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_different_instance_type_selectors(which):  # suite_test.go:1366-1390
+    c = Cluster(which, pools=[_pool(requirements=[req(ARCH_LABEL, "In", "arm64", "amd64")])])
+    pl = c.pods(1, node_selector={INSTANCE_TYPE_LABEL: "small-instance-type"})
+    pl += c.pods(1, node_selector={INSTANCE_TYPE_LABEL: "default-instance-type"})
+    c.provision(pl)
+    assert {c.node_of(p).labels[INSTANCE_TYPE_LABEL] for p in pl} == {"small-instance-type", "default-instance-type"}
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_different_zone_selectors(which):  # suite_test.go:1391-1415
+    c = Cluster(which)
+    pl = c.pods(1, node_selector={ZONE_LABEL: "test-zone-1"}) + c.pods(1, node_selector={ZONE_LABEL: "test-zone-2"})
+    c.provision(pl)
+    assert [c.node_of(p).labels[ZONE_LABEL] for p in pl] == ["test-zone-1", "test-zone-2"]
+
+
+def _gpu_types():
+    its = fake.instance_types(5)
+    its[0].capacity[GPU1] = "25"
+    its[1].capacity[GPU2] = "25"
+    return its
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_resources_that_no_single_type_has(which):  # suite_test.go:1416-1462
+    c = Cluster(which, its=_gpu_types())
+    pl = c.pods(1, requests={GPU1: "1"}) + c.pods(1, requests={GPU2: "1"})
+    c.provision(pl)
+    assert len(nodes_of(c, pl)) == 2
+    both = c.pods(1, requests={GPU1: "1", GPU2: "1"})
+    c.provision(both)
+    assert not c.scheduled(both[0])
+
+
+# ---- Binpacking (suite_test.go:1644-1836) ----------------------------------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_pack_nodes_tightly(which):  # suite_test.go:1644-1669
+    c = Cluster(which, its=fake.instance_types(5))
+    pl = c.pods(1, requests={"cpu": "4.5"}) + c.pods(1, requests={"cpu": "1"})
+    c.provision(pl)
+    types = [c.node_of(p).labels[INSTANCE_TYPE_LABEL] for p in pl]
+    assert len(nodes_of(c, pl)) == 2 and types[0] != types[1]
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_valid_instance_types_regardless_of_price(which):  # suite_test.go:1762-1835
+    def it(name, cpu, price):
+        off = [Offering([req(CAPACITY_TYPE_LABEL, "In", "on-demand"), req(ZONE_LABEL, "In", "test-zone-1a")], price, True)]
+        return fake.new_instance_type(name, {"cpu": str(cpu), "memory": f"{cpu}Gi"}, offerings=off)
+    c = Cluster(which, its=[it("medium", 2, 3.0), it("small", 1, 2.0), it("large", 4, 1.0)])
+    pl = c.pods(1, requests={"cpu": "1m", "memory": "1Mi"})
+    r = c.provision(pl)
+    assert sorted(r.new_node_claims[0].instance_type_options) == ["large", "medium", "small"]
+
+
+# ---- In-Flight Nodes (suite_test.go:1837-2478) -----------------------------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_in_flight_node_takes_the_next_pod(which):  # suite_test.go:1838-1854
+    c = Cluster(which)
+    first = c.pods(1, requests={"cpu": "10m"})
+    c.provision(first)
+    second = c.pods(1, requests={"cpu": "10m"})
+    c.provision(second)
+    assert nodes_of(c, first) == nodes_of(c, second)
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_second_node_when_the_pod_does_not_fit(which):  # suite_test.go:1904-1922: the node has 2000m
+    c = Cluster(which)
+    first = c.pods(1, requests={"cpu": "1001m"})
+    c.provision(first)
+    second = c.pods(1, requests={"cpu": "1"})
+    c.provision(second)
+    assert nodes_of(c, first) != nodes_of(c, second)
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_second_node_when_the_selector_does_not_match(which):  # suite_test.go:1923-1939
+    c = Cluster(which, pools=[_pool(requirements=[req(ARCH_LABEL, "In", "arm64", "amd64")])])
+    first = c.pods(1, requests={"cpu": "10m"})
+    c.provision(first)
+    second = c.pods(1, node_selector={ARCH_LABEL: "arm64"})
+    c.provision(second)
+    assert nodes_of(c, first) != nodes_of(c, second)
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_zonal_balance_with_in_flight_nodes(which):  # suite_test.go:1967-1997
+    c = Cluster(which)
+    lab = {"foo": "bar"}
+    tsc = spread(ZONE_LABEL, 1, LabelSelector.of(lab))
+    c.provision(c.pods(4, labels=lab, topology_spread_constraints=tsc))
+    assert c.skew(ZONE_LABEL, LabelSelector.of(lab)) == [1, 1, 2]
+    n = len(c.nodes)
+    c.provision(c.pods(5, labels=lab, topology_spread_constraints=tsc))
+    assert c.skew(ZONE_LABEL, LabelSelector.of(lab)) == [3, 3, 3] and len(c.nodes) == n  # no new nodes
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_hostname_balance_with_in_flight_nodes(which):  # suite_test.go:1998-2023
+    c = Cluster(which)
+    lab = {"foo": "bar"}
+    tsc = spread(HOSTNAME_LABEL, 1, LabelSelector.of(lab))
+    c.provision(c.pods(4, labels=lab, topology_spread_constraints=tsc))
+    c.provision(c.pods(5, labels=lab, topology_spread_constraints=tsc))
+    assert c.skew(HOSTNAME_LABEL, LabelSelector.of(lab)) == [1] * 9  # new nodes although the old ones have room
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_pack_in_flight_nodes_before_launching_new_ones(which):  # suite_test.go:2375-2414
+    medium = fake.new_instance_type("medium", {"cpu": "4.25", "pods": "4"})
+    c = Cluster(which, its=[medium])
+    rng = random.Random(5)
+    for _ in range(10):
+        batch = c.pods(rng.randrange(10), requests={"cpu": "1"})
+        c.provision(batch)
+        assert all(c.scheduled(p) for p in batch)
+    free = sum(1 for n in c.nodes if int(str(n.available["cpu"]).rstrip("m")) >= 1000)
+    assert free <= 1
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_tainted_in_flight_node_is_not_assumed(which):  # suite_test.go:2086-2117
+    c = Cluster(which)
+    first = c.pods(1, requests={"cpu": "10m"})
+    c.provision(first)
+    c.node_of(first[0]).taints = [Taint("foo.com/taint", "tainted", "NoSchedule")]
+    second = c.pods(1, requests={"cpu": "10m"})
+    c.provision(second)
+    assert nodes_of(c, first) != nodes_of(c, second)
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_nodepool_taint_needs_a_toleration(which):  # topology_test.go:2991-3017
+    c = Cluster(which, pools=[_pool(taints=[Taint("test-key", "test-value", "NoSchedule")])])
+    ok = c.pods(1, tolerations=[Toleration("test-key", "Equal", "test-value", "NoSchedule")])
+    ok += c.pods(1, tolerations=[Toleration("test-key", "Exists", "", "NoSchedule")])
+    ok += c.pods(1, tolerations=[Toleration("test-key", "Exists", "", "")])
+    ok += c.pods(1, tolerations=[Toleration("", "Exists", "", "")])
+    bad = c.pods(1)
+    bad += c.pods(1, tolerations=[Toleration("invalid", "Exists", "", "")])
+    bad += c.pods(1, tolerations=[Toleration("test-key", "Equal", "other", "NoSchedule")])
+    c.provision(ok + bad)
+    assert all(c.scheduled(p) for p in ok) and not any(c.scheduled(p) for p in bad)
+
+
+# ---- Existing Nodes (suite_test.go:2479-2659) ------------------------------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_existing_node_not_owned_by_karpenter(which):  # suite_test.go:2480-2534
+    c = Cluster(which)
+    c.add_node("unowned", {ZONE_LABEL: "test-zone-1", ARCH_LABEL: "amd64", OS_LABEL: "linux"},
+               available={"cpu": "10", "memory": "10Gi", "pods": 110})
+    pl = c.pods(100, requests={"cpu": "10m"})
+    r = c.provision(pl)
+    assert not r.new_node_claims and nodes_of(c, pl) == {"unowned"}
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_pod_incompatible_with_the_existing_node_gets_a_new_one(which):  # suite_test.go:2568-2600
+    c = Cluster(which)
+    c.add_node("unowned", {ZONE_LABEL: "test-zone-1", ARCH_LABEL: "amd64", OS_LABEL: "linux"},
+               available={"cpu": "10", "memory": "10Gi", "pods": 110})
+    pl = c.pods(1, requests={"cpu": "10m"}, node_selector={ZONE_LABEL: "test-zone-2"})
+    r = c.provision(pl)
+    assert len(r.new_node_claims) == 1 and c.node_of(pl[0]).labels[ZONE_LABEL] == "test-zone-2"
