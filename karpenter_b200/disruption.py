@@ -35,18 +35,20 @@ class Command:
 class Consolidation:
     def __init__(self, node_pools: Sequence[NodePool], instance_types: Dict[str, List[InstanceType]],
                  state_nodes: Sequence[StateNode], spot_to_spot: bool = False, backend: Optional[Callable] = None,
-                 device: int = -1):
+                 device: int = -1, preference_policy: str = "Respect"):
         self.node_pools = list(node_pools)
         self.instance_types = instance_types
         # sortExistingNodes order (scheduler.go:738-751): initialized first, then by name
         self.state_nodes = sorted(state_nodes, key=lambda n: (not n.initialized, n.name))
         self.spot_to_spot = spot_to_spot
+        self.preference_policy = preference_policy  # SimulateScheduling forwards the policy (helpers.go:97-101)
         self._backend = backend
         self._device = device
         self._handle = None
 
     def _encode(self, candidate_sets):
         b = ProblemBuilder()
+        b.preference_policy = self.preference_policy
         index: Dict[int, int] = {}
         by_name: Dict[str, int] = {}
         for np_ in self.node_pools:

@@ -218,3 +218,85 @@ def test_pod_incompatible_with_the_existing_node_gets_a_new_one(which):  # suite
     pl = c.pods(1, requests={"cpu": "10m"}, node_selector={ZONE_LABEL: "test-zone-2"})
     r = c.provision(pl)
     assert len(r.new_node_claims) == 1 and c.node_of(pl[0]).labels[ZONE_LABEL] == "test-zone-2"
+
+
+# ---- consolidation (pkg/controllers/disruption/consolidation_test.go) ------------------------------------------------
+def _consolidate(which, nodes, sets, its=None, **kw):
+    import numpy as np
+    from karpenter_b200.disruption import Consolidation
+    from tests import oracle_lib
+    from tests.test_reference_scenarios import nodepool
+    its = its or fake.default_instance_types()
+    np_ = nodepool()
+    orc = Consolidation([np_], {np_.name: its}, nodes, backend=oracle_lib.consolidate, **kw)
+    cmds = orc.compute(sets)
+    if which == "gpu":
+        gpu = Consolidation([np_], {np_.name: its}, nodes, **kw)
+        try:
+            cmds = gpu.compute(sets)
+        finally:
+            gpu.close()
+        for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+            assert np.array_equal(gpu.raw[k], orc.raw[k]), k
+    return cmds
+
+
+def _its():
+    return {i.name: i for i in fake.default_instance_types()}
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+@pytest.mark.parametrize("policy,decision", [("Ignore", "delete"), ("Respect", "replace")])
+def test_consolidation_delete_with_preferred_anti_affinity(which, policy, decision):  # consolidation_test.go:4760-4824
+    from karpenter_b200.model import Pod, PodAffinityTerm, WeightedPodAffinityTerm
+    from tests.test_reference_scenarios import _node
+    foo = {"app": "foo"}
+    anti = [WeightedPodAffinityTerm(1, PodAffinityTerm(LabelSelector.of(foo), HOSTNAME_LABEL))]
+    p = [Pod(name=f"p{i}", uid=i + 1, labels=foo, requests={"cpu": "1"}, pod_anti_affinity_preferred=anti) for i in range(3)]
+    d = _its()["default-instance-type"]
+    nodes = [_node("node-1", d, pod_list=p[:2]), _node("node-2", d, pod_list=p[2:])]
+    (cmd,) = _consolidate(which, nodes, [["node-2"]], preference_policy=policy)
+    # ignoring the preference the pod simply moves next to the others; respecting it, a fresh (cheaper) node satisfies the
+    # preference before any relaxation is tried, so the command becomes a replacement
+    assert cmd.decision == decision and cmd.n_new_node_claims == (0 if decision == "delete" else 1)
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+@pytest.mark.parametrize("policy,decision", [("Ignore", "replace"), ("Respect", "noop")])
+def test_consolidation_replace_with_preferred_instance_type(which, policy, decision):  # consolidation_test.go:4825-4870
+    from karpenter_b200.model import Pod, PreferredSchedulingTerm
+    from tests.test_reference_scenarios import _node
+    its = _its()
+    exp = its["arm-instance-type"]  # the most expensive type of the fake catalog
+    p = [Pod(name="p", uid=1, labels={"app": "foo"}, requests={"cpu": "1"},
+             node_affinity_preferred=[PreferredSchedulingTerm(1, (req(INSTANCE_TYPE_LABEL, "In", exp.name),))])]
+    nodes = [_node("node-1", exp, pod_list=p)]
+    (cmd,) = _consolidate(which, nodes, [["node-1"]], preference_policy=policy)
+    assert cmd.decision == decision
+    if decision == "replace":
+        assert exp.name not in cmd.replacement_instance_types and cmd.replacement_instance_types
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_consolidation_delete_onto_unmanaged_capacity(which):  # consolidation_test.go:2525-2572
+    from karpenter_b200.model import StateNode
+    from tests.test_reference_scenarios import _node, pods
+    d = _its()["default-instance-type"]
+    managed = _node("node-1", d, pod_list=pods(3, requests={"cpu": "1"}))
+    unmanaged = StateNode(name="unmanaged", labels={HOSTNAME_LABEL: "unmanaged"}, available={"cpu": "32", "pods": 100},
+                          capacity={"cpu": "32", "pods": 100}, managed=False)
+    (cmd,) = _consolidate(which, [managed, unmanaged], [["node-1"]])
+    assert cmd.decision == "delete" and cmd.n_new_node_claims == 0
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_consolidation_would_make_a_pod_pending(which):  # consolidation_test.go:3235-3274
+    from tests.test_reference_scenarios import _node, pods
+    small = fake.new_instance_type("only", {"cpu": "32", "pods": "100"})
+    n1 = _node("node-1", small, pod_list=pods(2, requests={"cpu": "1"}, node_selector={"foo": "1"}))
+    n2 = _node("node-2", small, pod_list=pods(1, uid0=10, requests={"cpu": "1"}, node_selector={"foo": "2"}))
+    n1.labels["foo"], n2.labels["foo"] = "1", "2"
+    cmds = _consolidate(which, [n1, n2], [["node-1"], ["node-2"], ["node-1", "node-2"]], its=[small])
+    # the NodePool knows no label foo: a pod evicted from either node has nowhere to go
+    assert [c.decision for c in cmds] == ["noop", "noop", "noop"]
+    assert all(c.n_unscheduled > 0 for c in cmds)
