@@ -291,6 +291,11 @@ typedef struct kp_consol_input {
   int32_t spot_to_spot_enabled; /* FeatureGates.SpotToSpotConsolidation (consolidation.go:239) */
   int32_t capacity_type_key;    /* key id of karpenter.sh/capacity-type, -1 if not interned */
   int32_t ct_reserved, ct_spot, ct_on_demand; /* value ids in that key, -1 if not interned (types.go:45-47) */
+  /* MultiNodeConsolidation.firstNConsolidationOption (multinodeconsolidation.go:154-163): a Replace of two or more nodes
+   * goes through filterOutSameInstanceType (:189-226) -- if the replacement options contain a type that is being
+   * removed, only options cheaper than the cheapest such node stay; nothing left == not a valid command, reported as
+   * KP_DECISION_NOOP.  0 = plain computeConsolidation (single-node consolidation, or the caller filters itself). */
+  int32_t filter_same_instance_type;
 } kp_consol_input;
 
 typedef struct kp_consol_result {

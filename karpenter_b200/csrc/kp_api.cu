@@ -987,6 +987,10 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
     uint8_t* u8;
     CK(up_raw(h, &u8, in->node_is_spot, (size_t)E));
     q.node_is_spot = u8;
+    int32_t* nit = nullptr;
+    CK(up_raw(h, &nit, in->node_it, (size_t)E));
+    q.node_it = nit;
+    q.filter_same_type = in->filter_same_instance_type;
     CK(up(h, &q.ml_off, ml_off));
     CK(up(h, &q.ml_set, ml_set));
     CK(up(h, &q.ml_price, ml_price));

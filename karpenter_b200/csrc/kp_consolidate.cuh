@@ -273,6 +273,8 @@ struct KpConsol {
   const int32_t* pod_rank;       // [rows] position in byCPUAndMemoryDescending order over all rows
   const double* node_price;      // [E] cheapest compatible offering of the node's instance type, < 0: none
   const uint8_t* node_is_spot;   // [E]
+  const int32_t* node_it;        // [E] instance type of the node, -1 unknown
+  int filter_same_type;          // apply filterOutSameInstanceType to replacements of >= 2 nodes
   const int32_t* node_tmpl;      // [E] NodePool of the node, -1 unmanaged
   const int64_t* node_capacity;  // [E*R]
   const int64_t* tmpl_remaining0;// [N*R] limits minus capacity of ALL nodes
@@ -485,6 +487,44 @@ __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q,
               taken += __popc(m);
             }
             rep = first15;
+          }
+        }
+        if (any && q.filter_same_type && sn >= 2) {
+          // filterOutSameInstanceType (multinodeconsolidation.go:189-226): if an option is a type that is being removed,
+          // only options cheaper than the cheapest such node are worth a replacement
+          double max_price = 1.7976931348623157e308;
+          for (int i = 0; i < sn; i++) {
+            const int t = q.node_it[snodes[i]];
+            if (t < 0) continue;
+            const bool in_rep = (__shfl_sync(FULL, rep, t >> 6) >> (t & 63)) & 1ull;
+            if (!in_rep) continue;
+            double mine = 1.7976931348623157e308;  // cheapest removed node of this type; none priced: 0 (Go map miss)
+            for (int j = 0; j < sn; j++)
+              if (q.node_it[snodes[j]] == t && q.node_price[snodes[j]] >= 0 && q.node_price[snodes[j]] < mine)
+                mine = q.node_price[snodes[j]];
+            if (mine > 1e308) mine = 0.0;
+            if (mine < max_price) max_price = mine;
+          }
+          if (max_price < 1e308) {
+            uint64_t keep = 0;
+            if (lane < ITW)
+              for (uint64_t bits = rep; bits;) {
+                const int b = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                const int t = lane * 64 + b;
+                double worst = 1.7976931348623157e308;
+                for (int ci = 0; ci < 3 && worst > 1e308; ci++) {
+                  if (q.ct_key < 0 || !((q.ct_order_valid >> ci) & 1)) continue;
+                  for (int e = q.wl_off[t * 3 + ci]; e < q.wl_off[t * 3 + ci + 1]; e++)
+                    if ((okmask >> q.wl_set[e]) & 1u) {
+                      worst = q.wl_price[e];
+                      break;
+                    }
+                }
+                if (worst < max_price) keep |= 1ull << b;
+              }
+            rep = keep;
+            any = __any_sync(FULL, rep != 0);
           }
         }
         if (any) decision = KP_DECISION_REPLACE;

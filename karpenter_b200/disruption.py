@@ -35,13 +35,15 @@ class Command:
 class Consolidation:
     def __init__(self, node_pools: Sequence[NodePool], instance_types: Dict[str, List[InstanceType]],
                  state_nodes: Sequence[StateNode], spot_to_spot: bool = False, backend: Optional[Callable] = None,
-                 device: int = -1, preference_policy: str = "Respect"):
+                 device: int = -1, preference_policy: str = "Respect", filter_same_instance_type: bool = False):
         self.node_pools = list(node_pools)
         self.instance_types = instance_types
         # sortExistingNodes order (scheduler.go:738-751): initialized first, then by name
         self.state_nodes = sorted(state_nodes, key=lambda n: (not n.initialized, n.name))
         self.spot_to_spot = spot_to_spot
         self.preference_policy = preference_policy  # SimulateScheduling forwards the policy (helpers.go:97-101)
+        # MultiNodeConsolidation applies filterOutSameInstanceType to every Replace of >= 2 nodes (multinodeconsolidation.go:154-163)
+        self.filter_same_instance_type = filter_same_instance_type
         self._backend = backend
         self._device = device
         self._handle = None
@@ -80,7 +82,8 @@ class Consolidation:
             n_subsets=len(candidate_sets), subset_off=sub_off, subset_nodes=sub_nodes,
             spot_to_spot_enabled=int(self.spot_to_spot), capacity_type_key=enc.key_id(CAPACITY_TYPE_LABEL),
             ct_reserved=enc.value_id(CAPACITY_TYPE_LABEL, "reserved"), ct_spot=enc.value_id(CAPACITY_TYPE_LABEL, "spot"),
-            ct_on_demand=enc.value_id(CAPACITY_TYPE_LABEL, "on-demand"))
+            ct_on_demand=enc.value_id(CAPACITY_TYPE_LABEL, "on-demand"),
+            filter_same_instance_type=int(self.filter_same_instance_type))
         return enc, consol
 
     def compute(self, candidate_sets: Sequence[Sequence[str]]) -> List[Command]:

@@ -806,6 +806,39 @@ int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol
         if (kept.size() < 15) break;  // MinInstanceTypesForSpotToSpotConsolidation
         kept.resize(15);
       }
+      if (in->filter_same_instance_type && in->subset_off[s_i + 1] - in->subset_off[s_i] >= 2) {
+        // filterOutSameInstanceType (multinodeconsolidation.go:189-226)
+        std::map<int, double> price_by_type;  // cheapest node of each instance type that is being removed
+        std::set<int> existing;
+        for (int i = in->subset_off[s_i]; i < in->subset_off[s_i + 1]; i++) {
+          int node = in->subset_nodes[i], it = in->node_it[node];
+          if (it < 0) continue;
+          existing.insert(it);
+          const Requirements& labels = P.reqsets[p->node_reqset[node]];
+          bool any = false;
+          double cheapest = 0;
+          for (int o = p->it_off_off[it]; o < p->it_off_off[it + 1]; o++) {
+            if (!compatible(P, P, labels, P.reqsets[p->off_reqset[o]], true)) continue;
+            if (!any || p->off_price[o] < cheapest) cheapest = p->off_price[o];
+            any = true;
+          }
+          if (!any) continue;
+          auto f = price_by_type.find(it);
+          if (f == price_by_type.end() || cheapest < f->second) price_by_type[it] = cheapest;
+        }
+        double max_price = std::numeric_limits<double>::max();
+        for (int it : kept)
+          if (existing.count(it)) {
+            auto f = price_by_type.find(it);
+            double v = f == price_by_type.end() ? 0.0 : f->second;  // a Go map miss reads as 0
+            if (v < max_price) max_price = v;
+          }
+        std::vector<int> kept2;
+        for (int it : kept)
+          if (pr.worst_launch_price(it, c.reqs, in->capacity_type_key, ct_order) < max_price) kept2.push_back(it);
+        kept.swap(kept2);
+        if (kept.empty()) break;  // not a valid command for the binary search (multinodeconsolidation.go:157-163)
+      }
       decision = KP_DECISION_REPLACE;
       for (int it : kept) rep[it >> 6] |= 1ull << (it & 63);
     } while (0);

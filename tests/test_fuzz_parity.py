@@ -123,12 +123,13 @@ def test_fuzz_consolidation_parity_gpu():
     bad, ran = [], 0
     for seed in range(200):
         pools, per_pool, nodes, sets, s2s = consolidation_case(seed)
-        orc = Consolidation(pools, per_pool, nodes, spot_to_spot=s2s, backend=oracle_lib.consolidate)
+        kw = dict(spot_to_spot=s2s, filter_same_instance_type=seed % 2 == 1)
+        orc = Consolidation(pools, per_pool, nodes, backend=oracle_lib.consolidate, **kw)
         try:
             orc.compute(sets)
         except RuntimeError:
             continue
-        gpu = Consolidation(pools, per_pool, nodes, spot_to_spot=s2s)
+        gpu = Consolidation(pools, per_pool, nodes, **kw)
         try:
             gpu.compute(sets)
         except _native.SolverError as e:

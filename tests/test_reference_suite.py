@@ -300,3 +300,26 @@ def test_consolidation_would_make_a_pod_pending(which):  # consolidation_test.go
     # the NodePool knows no label foo: a pod evicted from either node has nowhere to go
     assert [c.decision for c in cmds] == ["noop", "noop", "noop"]
     assert all(c.n_unscheduled > 0 for c in cmds)
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_multi_node_replacement_by_one_of_the_removed_types(which):  # multinodeconsolidation.go:165-188 (the two examples)
+    from tests.test_reference_scenarios import _node, pods
+    its = _its()
+    d, small = its["default-instance-type"], its["small-instance-type"]
+    p = pods(3, requests={"cpu": "500m"})
+    # [default, default, small] -> the pods fit one small node, but a small node is being removed: that is a deletion of
+    # the two default nodes in disguise, not a replacement
+    nodes = [_node("n1", d, pod_list=p[:1]), _node("n2", d, pod_list=p[1:2]), _node("n3", small, pod_list=p[2:])]
+    sets = [["n1", "n2", "n3"]]
+    (plain,) = _consolidate(which, nodes, sets)
+    assert plain.decision == "replace" and "small-instance-type" in plain.replacement_instance_types
+    (multi,) = _consolidate(which, nodes, sets, filter_same_instance_type=True)
+    assert multi.decision == "noop"
+    # [default, default, default] -> options cheaper than a default node stay
+    nodes = [_node(f"n{i + 1}", d, pod_list=p[i:i + 1]) for i in range(3)]
+    (multi,) = _consolidate(which, nodes, sets, filter_same_instance_type=True)
+    assert multi.decision == "replace" and multi.replacement_instance_types == ["small-instance-type"]
+    # a single node is never filtered (firstNConsolidationOption only sees >= 2 candidates)
+    (single,) = _consolidate(which, nodes, [["n1"]], filter_same_instance_type=True)
+    assert single.decision == "delete"
