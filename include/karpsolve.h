@@ -141,6 +141,11 @@ typedef struct kp_problem {
   const int32_t* off_reqset;      /* [n_offerings] Offering.Requirements */
   const double* off_price;        /* [n_offerings] */
   const uint8_t* off_available;   /* [n_offerings] */
+  const uint8_t* off_reserved;    /* [n_offerings], may be NULL.  1 == Offering.CapacityType() is "reserved" AND the
+                                     ReservedCapacity feature gate is on, i.e. the reference would run the offering through
+                                     its ReservationManager (reservationmanager.go:28-110, nodeclaim.go:240-307).  That
+                                     bookkeeping is not built: a problem with an available reserved offering is refused
+                                     with KP_ERR_UNSUPPORTED rather than solved as if reservations were unlimited. */
 
   /* ---- NodeClaimTemplates, one per NodePool, already in OrderByWeight order (utils/nodepool/nodepool.go:161) ---- */
   int32_t n_templates;

@@ -112,6 +112,11 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   if (R > KP_MAXR || R < 1) return err = "resource count out of range", KP_ERR_CAPACITY;
   const int ITW = (T + 63) / 64;
   if (ITW > KP_MAX_ITW) return err = "more than 2048 instance types", KP_ERR_CAPACITY;
+  if (p->off_reserved)  // the ReservationManager (reservationmanager.go:28-110) is not built: refuse, never approximate
+    for (int t = 0; t < T; t++)
+      for (int o = p->it_off_off[t]; o < p->it_off_off[t + 1]; o++)
+        if (p->off_reserved[o] && p->off_available[o])
+          return err = "reserved-capacity offerings (ReservationManager) are not supported yet", KP_ERR_UNSUPPORTED;
   h.K = K;
   h.R = R;
   h.T = T;

@@ -24,7 +24,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _abi
-from .model import (HOSTNAME_LABEL, NODEPOOL_LABEL, NORMALIZED_LABELS, WELL_KNOWN_LABELS, InstanceType, LabelSelector,
+from .model import (CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, NODEPOOL_LABEL, NORMALIZED_LABELS, WELL_KNOWN_LABELS, InstanceType, LabelSelector,
                     NodePool, NodeSelectorRequirement, Pod, StateNode, Taint, Toleration, quantity_units)
 
 EFFECTS = {"": 0, "NoSchedule": 1, "PreferNoSchedule": 2, "NoExecute": 3}
@@ -176,6 +176,7 @@ class ProblemBuilder:
         self.max_values_per_key = 64  # width of the per-key value mask; wider keys go through value compaction
         self.preference_policy = "Respect"  # or "Ignore": scheduler.IgnorePreferences (scheduler.go:81-101)
         self.min_values_policy = "Strict"   # or "BestEffort": scheduler.MinValuesPolicy (scheduler.go:110-114)
+        self.reserved_capacity = True       # FeatureGates.ReservedCapacity (options.go:169-177, default on)
 
     # ---- resources ----
     def res_index(self, name: str) -> int:
@@ -465,13 +466,17 @@ class ProblemBuilder:
         P.set("it_capacity", cap)
         P.set("it_cap_present", capp)
         P.set("it_overhead", ovh)
-        oo, orq, opr, oav = [0], [], [], []
+        oo, orq, opr, oav, orsv = [0], [], [], [], []
         for it in self.its:
             for (rs, price, av) in it["offerings"]:
                 orq.append(rs)
                 opr.append(price)
                 oav.append(1 if av else 0)
+                # Offering.CapacityType() == reserved (types.go:385-387) while the ReservedCapacity gate is on
+                orsv.append(1 if self.reserved_capacity and any(
+                    r[0] == CAPACITY_TYPE_LABEL and not r[1] and tuple(r[2]) == ("reserved",) for r in self.reqsets.rows[rs]) else 0)
             oo.append(len(orq))
+        P.set("off_reserved", orsv)
         P.set("it_off_off", oo)
         P.set("off_reqset", orq)
         P.set("off_price", opr)

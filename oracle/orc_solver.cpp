@@ -532,6 +532,15 @@ static void export_requirements(const Prob& P, const Requirements& reqs, int mas
   }
 }
 
+// reserved-capacity offerings need the ReservationManager (reservationmanager.go:28-110): not restated, refused
+static bool has_reserved_offerings(const kp_problem* p) {
+  if (!p->off_reserved) return false;
+  for (int t = 0; t < p->n_its; t++)
+    for (int o = p->it_off_off[t]; o < p->it_off_off[t + 1]; o++)
+      if (p->off_reserved[o] && p->off_available[o]) return true;
+  return false;
+}
+
 static bool has_min_values(const kp_problem* p) {
   for (int e = 0; e < p->n_reqs; e++)
     if (p->req_flags[e] & KP_REQ_HAS_MINVALUES) return true;
@@ -617,6 +626,7 @@ int orc_solve(const kp_problem* p, kp_result* out) { return orc_solve_mt(p, out,
 
 // threads > 1: in-flight candidates are evaluated by a worker pool like the reference's parallelizeUntil
 int orc_solve_mt(const kp_problem* p, kp_result* out, int threads) {
+  if (has_reserved_offerings(p)) return KP_ERR_UNSUPPORTED;
   if (p->n_resources > KP_MAX_RESOURCES) return KP_ERR_CAPACITY;
   Prob P(p);
   Scheduler s(P);
@@ -694,7 +704,7 @@ int orc_consolidate(const kp_problem* p, const kp_consol_input* in, kp_consol_re
 }
 // subsets are independent simulations: `threads` workers take them round-robin
 int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol_result* out, int threads) {
-  if (has_min_values(p)) return KP_ERR_UNSUPPORTED;
+  if (has_min_values(p) || has_reserved_offerings(p)) return KP_ERR_UNSUPPORTED;
   Prob P(p);
   Pricing pr(P);
   int ITW = (p->n_its + 63) / 64;
