@@ -354,3 +354,156 @@ def test_library_refuses_reserved_capacity_offerings():
         assert e.value.code == 5 and "reserved" in str(e.value)
     finally:
         s.close()
+
+
+# ---- NodePool limits (provisioning/suite_test.go:742-935) -------------------------------------------------------------
+def _limited(which, **limits):
+    return Cluster(which, pools=[NodePool(name="default", requirements=[req(CAPACITY_TYPE_LABEL, "In", "spot", "on-demand", "reserved")],
+                                          limits=limits)])
+
+
+FOO = {"app": "foo"}
+
+
+def _anti_foo(c, n=1):
+    from karpenter_b200.model import PodAffinityTerm
+    return c.pods(n, labels=FOO, requests={"cpu": "1.5"},
+                  pod_anti_affinity=[PodAffinityTerm(LabelSelector.of(FOO), HOSTNAME_LABEL)])
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_limits_already_exceeded_by_existing_capacity(which):  # provisioning/suite_test.go:743-765
+    from karpenter_b200.model import StateNode
+    c = _limited(which, cpu="20")
+    c.nodes.append(StateNode(name="big", labels={HOSTNAME_LABEL: "big"}, available={"cpu": "0", "pods": 0},
+                             capacity={"cpu": "100"}, nodepool="default", initialized=True))
+    pl = c.pods(1)
+    c.provision(pl)
+    assert not c.scheduled(pl[0])
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+@pytest.mark.parametrize("cpu,ok", [("1.75", True), ("2.1", False)])
+def test_limits_would_be_met_or_exceeded(which, cpu, ok):  # provisioning/suite_test.go:766-782, 833-847
+    c = _limited(which, cpu="2")
+    pl = c.pods(1, requests={"cpu": cpu})
+    c.provision(pl)
+    assert c.scheduled(pl[0]) == ok
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_limits_partially_schedule(which):  # provisioning/suite_test.go:783-832: the first node eats the limit
+    c = _limited(which, cpu="3")
+    pl = _anti_foo(c, 2)
+    c.provision(pl)
+    assert sum(c.scheduled(p) for p in pl) == 1
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_limit_on_pods_blocks_every_instance_type(which):  # provisioning/suite_test.go:848-863
+    c = _limited(which, pods="1")
+    pl = c.pods(1, requests={fake.GPU_VENDOR_A: "1"})
+    c.provision(pl)
+    assert not c.scheduled(pl[0])
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_limits_across_scheduling_rounds(which):  # provisioning/suite_test.go:864-891
+    c = _limited(which, cpu="2")
+    first = c.pods(1, requests={"cpu": "1.75"})
+    c.provision(first)
+    second = c.pods(1, requests={"cpu": "1.75"})
+    c.provision(second)
+    assert c.scheduled(first[0]) and not c.scheduled(second[0])
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_limit_on_node_count(which):  # provisioning/suite_test.go:892-934
+    c = _limited(which, nodes="2")
+    placed = []
+    for _ in range(3):
+        p = _anti_foo(c)
+        c.provision(p)
+        placed.append(c.scheduled(p[0]))
+    assert placed == [True, True, False]
+
+
+# ---- Daemonsets (provisioning/suite_test.go:936-1057) ----------------------------------------------------------------
+@pytest.mark.parametrize("which", BACKENDS)
+def test_daemonset_overhead_moves_the_pod_to_a_bigger_node(which):  # provisioning/suite_test.go:936-956
+    c = Cluster(which, daemon_overhead={"default": {"cpu": "2", "memory": "1Gi"}})
+    pl = c.pods(1, requests={"cpu": "1", "memory": "1Gi"})
+    c.provision(pl)
+    assert c.node_of(pl[0]).labels[INSTANCE_TYPE_LABEL] == "default-instance-type"  # 4 cpu / 4Gi; the 2-cpu type is out
+    c2 = Cluster(which)
+    pl = c2.pods(1, requests={"cpu": "1", "memory": "1Gi"})
+    c2.provision(pl)
+    assert c2.node_of(pl[0]).labels[INSTANCE_TYPE_LABEL] == "small-instance-type"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_daemonset_overhead_too_large(which):  # provisioning/suite_test.go:1005-1014
+    c = Cluster(which, daemon_overhead={"default": {"cpu": "10000", "memory": "10000Gi"}})
+    pl = c.pods(1)
+    c.provision(pl)
+    assert not c.scheduled(pl[0])
+
+
+# ---- NodePool selection (provisioning/suite_test.go:2637-2711) -------------------------------------------------------
+def _pools(*specs):
+    return [NodePool(name=n, weight=w, requirements=[req(CAPACITY_TYPE_LABEL, "In", "spot", "on-demand", "reserved")],
+                     labels=dict(lab), taints=list(t), limits={"cpu": "2000"}) for n, w, lab, t in specs]
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_explicitly_selected_nodepool(which):  # provisioning/suite_test.go:2638-2645, 2696-2710
+    from karpenter_b200.model import NODEPOOL_LABEL
+    c = Cluster(which, pools=_pools(("target", 0, {}, ()), ("w20", 20, {}, ()), ("w100", 100, {}, ())))
+    pl = c.pods(1, node_selector={NODEPOOL_LABEL: "target"})
+    r = c.provision(pl)
+    assert r.new_node_claims[0].nodepool == "target"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_nodepool_by_labels(which):  # provisioning/suite_test.go:2646-2661
+    c = Cluster(which, pools=_pools(("plain", 0, {}, ()), ("labelled", 0, {"foo": "bar"}, ())))
+    r = c.provision(c.pods(1, node_selector={"foo": "bar"}))
+    assert r.new_node_claims[0].nodepool == "labelled"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_prefer_no_schedule_pool_is_avoided_when_another_matches(which):  # provisioning/suite_test.go:2662-2677
+    soft = Taint("foo", "bar", "PreferNoSchedule")
+    for order in (("soft", "plain"), ("plain", "soft")):  # whatever the name order (OrderByWeight ties break on names)
+        specs = [(n, 0, {}, (soft,) if n == "soft" else ()) for n in order]
+        c = Cluster(which, pools=_pools(*specs))
+        r = c.provision(c.pods(1))
+        assert r.new_node_claims[0].nodepool == "plain"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_highest_weight_nodepool_always(which):  # provisioning/suite_test.go:2680-2695
+    c = Cluster(which, pools=_pools(("w0", 0, {}, ()), ("w20", 20, {}, ()), ("w100", 100, {}, ())))
+    r = c.provision(c.pods(3))
+    assert {cl.nodepool for cl in r.new_node_claims} == {"w100"}
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_prefer_no_schedule_tolerated_after_affinity_terms_relaxed(which):  # provisioning/suite_test.go:2352-2378
+    from karpenter_b200.model import PreferredSchedulingTerm
+    c = Cluster(which, pools=_pools(("default", 0, {}, (Taint("foo", "bar", "PreferNoSchedule"),))))
+    pl = c.pods(1, node_affinity_preferred=[PreferredSchedulingTerm(1, (req(ZONE_LABEL, "In", "invalid"),)),
+                                            PreferredSchedulingTerm(1, (req(INSTANCE_TYPE_LABEL, "In", "invalid"),))])
+    c.provision(pl)
+    assert c.scheduled(pl[0]) and c.node_of(pl[0]).taints == [Taint("foo", "bar", "PreferNoSchedule")]
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_unsatisfiable_node_preference_is_dropped(which):  # provisioning/suite_test.go:2379-2424 (zone entry)
+    from karpenter_b200.model import PreferredSchedulingTerm
+    c = Cluster(which)
+    big = c.pods(1, labels={"app": "foo"}, requests={"cpu": "2"})
+    pref = c.pods(1, labels={"app": "baz"}, requests={"cpu": "1"},
+                  node_affinity_preferred=[PreferredSchedulingTerm(1, (req(ZONE_LABEL, "In", "value-1"),))])
+    c.provision(big + pref)
+    assert nodes_of(c, big) == nodes_of(c, pref)

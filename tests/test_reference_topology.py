@@ -26,8 +26,9 @@ RR = {"cpu": "1.1"}  # fills a 2-cpu small instance: the launched node cannot ta
 
 
 class Cluster:
-    def __init__(self, which, pools=None, its=None):
+    def __init__(self, which, pools=None, its=None, daemon_overhead=None):
         self.which = which
+        self.daemon_overhead = daemon_overhead
         self.pools = pools or [NodePool(name="default", requirements=[req(CAPACITY_TYPE_LABEL, "In", "spot", "on-demand", "reserved")],
                                         limits={"cpu": "2000"})]
         self.its = its or fake.default_instance_types()
@@ -56,7 +57,8 @@ class Cluster:
         return n
 
     def _solve(self, backend, pod_list):
-        s = Scheduler(self.pools, {p.name: self.its for p in self.pools}, state_nodes=self.nodes, backend=backend)
+        s = Scheduler(self.pools, {p.name: self.its for p in self.pools}, state_nodes=self.nodes, backend=backend,
+                      daemon_overhead=self.daemon_overhead)
         try:
             return s.solve(pod_list)
         finally:
