@@ -180,14 +180,10 @@ def run_consolidation(args, h, rank, world, dist, torch):
     path, decisions would be gathered on rank 0."""
     from karpenter_b200 import _abi, workloads
     enc, consol = workloads.config_c4(n_nodes=args.consol_nodes, n_pods=args.consol_pods)
+    from karpenter_b200 import sharding
     S = consol["n_subsets"]
-    mine = np.arange(rank, S, world)
     off, nodes = consol["subset_off"], consol["subset_nodes"]
-    sizes = (off[1:] - off[:-1])[mine]
-    sub_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
-    sub_nodes = np.concatenate([nodes[off[i]:off[i + 1]] for i in mine]).astype(np.int32) if len(mine) else nodes[:0]
-    shard = dict(consol, n_subsets=len(mine), subset_off=sub_off, subset_nodes=sub_nodes)
-    ci = _abi.ConsolInput(**shard)
+    ci = _abi.ConsolInput(**sharding.shard_subsets(consol, rank, world))
     dev_ms, e2e_ms = [], []
     res = None
     for i in range(1 + max(1, min(args.steps, 3))):

@@ -81,3 +81,30 @@ def merge_shards(shards: Sequence[dict], pod_index: Sequence[np.ndarray], n_pods
             "claim_npods": np.concatenate(npods) if npods else np.zeros(0, np.int32),
             "claim_requests": np.concatenate(reqs) if reqs else np.zeros((0, 0), np.int64),
             "claim_its": np.concatenate(its) if its else np.zeros((0, 0), np.uint64)}
+
+
+# ---- consolidation: candidate sets shard trivially ----------------------------------------------
+def shard_subsets(consol: dict, rank: int, world: int) -> dict:
+    """Rank r's share of a kp_consol_input: the candidate sets s with s % world == r (each one is an independent
+    computeConsolidation over read-only cluster state, helpers.go:55-59).  Tables are replicated, nothing is exchanged on
+    the data path; `gather_decisions` puts the per-rank answers back into candidate-set order."""
+    S = int(consol["n_subsets"])
+    off, nodes = np.asarray(consol["subset_off"]), np.asarray(consol["subset_nodes"])
+    mine = np.arange(rank, S, world)
+    sizes = (off[1:] - off[:-1])[mine]
+    sub_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    sub_nodes = (np.concatenate([nodes[off[i]:off[i + 1]] for i in mine]).astype(np.int32) if len(mine) else nodes[:0].astype(np.int32))
+    return dict(consol, n_subsets=len(mine), subset_off=sub_off, subset_nodes=sub_nodes)
+
+
+def gather_decisions(per_rank: Sequence[dict], n_subsets: int) -> Dict[str, np.ndarray]:
+    """Interleave the shard results (rank r holds sets r, r + world, ...) back into candidate-set order."""
+    world = len(per_rank)
+    out: Dict[str, np.ndarray] = {}
+    for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+        first = np.asarray(per_rank[0][k])
+        full = np.zeros((n_subsets,) + first.shape[1:], first.dtype)
+        for r, res in enumerate(per_rank):
+            full[r::world] = np.asarray(res[k])[:len(range(r, n_subsets, world))]
+        out[k] = full
+    return out
