@@ -56,3 +56,50 @@ def test_tainted_in_flight_node_with_a_toleration():  # suite_test.go:2086-2117,
     tol = c.pods(1, requests={"cpu": "10m"}, tolerations=[Toleration("foo.com/taint", "Exists", "", "")])
     c.provision(tol)
     assert c.bound[id(first[0])] == c.bound[id(tol[0])]
+
+
+# ---- spot-to-spot consolidation rules (consolidation_test.go:1033-1218, consolidation.go:236-316) ---------------------
+def _assorted(n):
+    """the first n of fake.InstanceTypesAssorted() (fake/instancetype.go:156-192): 1 cpu / 1 Gi in every combination of
+    zone x capacity type x os x arch, one offering each, all at the same price"""
+    from karpenter_b200 import fake
+    from karpenter_b200.model import Offering
+    out = []
+    for zone in ("test-zone-1", "test-zone-2", "test-zone-3"):
+        for ct in ("spot", "on-demand"):
+            for os_ in ("linux", "windows"):
+                for arch in ("amd64", "arm64"):
+                    res = {"cpu": "1", "memory": "1Gi"}
+                    off = [Offering([req(CAPACITY_TYPE_LABEL, "In", ct), req(ZONE_LABEL, "In", zone)],
+                                    fake.price_from_resources(res), True)]
+                    out.append(fake.new_instance_type(f"1-cpu-1-mem-{arch}-{os_}-{zone}-{ct}", res, architecture=arch,
+                                                      operating_systems=(os_,), offerings=off))
+    return out[:n]
+
+
+def _spot_case(n_types, spot_to_spot=True):
+    from karpenter_b200.disruption import Consolidation
+    from karpenter_b200.model import NodePool, Offering
+    from tests import oracle_lib
+    from tests.test_reference_scenarios import _node, pods
+    its = _assorted(n_types)
+    # the first type becomes a dirt-cheap spot offering: one option that is cheaper than the node
+    its[0].offerings = [Offering([req(CAPACITY_TYPE_LABEL, "In", "spot"), req(ZONE_LABEL, "In", "test-zone-1")], 0.001, True)]
+    spot = [i for i in its[1:] if i.offerings[0].requirements[0].values == ("spot",)]
+    node_it = spot[-1]
+    zone = node_it.offerings[0].requirements[1].values[0]
+    np_ = NodePool(name="default", requirements=[req(CAPACITY_TYPE_LABEL, "In", "spot", "on-demand"),
+                                                 req(ARCH_LABEL, "In", "amd64", "arm64")], limits={"cpu": "2000"})
+    n = _node("spot-node", node_it, zone=zone, ct="spot", pod_list=pods(1, requests={"cpu": "100m"}))
+    c = Consolidation([np_], {np_.name: its}, [n], spot_to_spot=spot_to_spot, backend=oracle_lib.consolidate)
+    return c.compute([["spot-node"]])[0]
+
+
+@pytest.mark.parametrize("n_types", [5, 20])
+def test_spot_to_spot_needs_fifteen_cheaper_types(n_types):  # consolidation_test.go:1033-1107, 1149-1218
+    cmd = _spot_case(n_types)
+    assert cmd.decision == "noop" and cmd.n_new_node_claims == 1  # a cheaper spot type exists, but only one of them
+
+
+def test_spot_to_spot_needs_the_feature_gate():  # consolidation_test.go:1108-1148
+    assert _spot_case(20, spot_to_spot=False).decision == "noop"
