@@ -331,6 +331,17 @@ void kp_result_free(kp_result* r);
 int kp_upload(kp_handle* h, const kp_problem* p);
 int kp_solve_resident(kp_handle* h, int64_t deadline_ms, kp_result* out);
 
+/* Many Scheduler instances at once -- one CTA (one SM) per instance, a single launch.  What it stands for in the
+ * reference: the Scheduler instances that run side by side there -- one NewScheduler + Solve per NodePool shard of a
+ * provisioning pass, one per SimulateScheduling of a disruption pass (helpers.go:51-142, one
+ * call per candidate set: multinodeconsolidation.go:118-171, singlenodeconsolidation.go:56-176), provisioner and
+ * disruption controller each inside their own Scheduler (provisioner.go:354-375).  Instances share nothing: outs[b] is
+ * exactly what kp_solve(problems[b]) returns (outs[b].solve_ms = device time of the whole batch).  Returns KP_DEADLINE
+ * if any instance hit the deadline (every outs[b] is valid, partial for the ones that did). */
+int kp_solve_batch(kp_handle* h, const kp_problem* const* problems, int32_t n, int64_t deadline_ms, kp_result* outs);
+int kp_upload_batch(kp_handle* h, const kp_problem* const* problems, int32_t n);
+int kp_solve_batch_resident(kp_handle* h, int64_t deadline_ms, kp_result* outs);
+
 int kp_consolidate(kp_handle* h, const kp_problem* cluster, const kp_consol_input* in, int64_t deadline_ms,
                    kp_consol_result* out);
 void kp_consol_result_free(kp_consol_result* r);

@@ -47,6 +47,9 @@ def lib():
         L.kp_upload.argtypes = [C.c_void_p, C.c_void_p]
         L.kp_solve_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.kp_result_free.argtypes = [C.c_void_p]
+        L.kp_solve_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
+        L.kp_upload_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.kp_solve_batch_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.kp_consolidate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.kp_consol_result_free.argtypes = [C.c_void_p]
         L.kp_feasibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -56,7 +59,8 @@ def lib():
 
 
 EXPORTS = ["kp_version", "kp_create", "kp_destroy", "kp_last_error", "kp_solve", "kp_result_free", "kp_upload",
-           "kp_solve_resident", "kp_consolidate", "kp_consol_result_free", "kp_feasibility", "kp_get_stats"]
+           "kp_solve_resident", "kp_consolidate", "kp_consol_result_free", "kp_feasibility", "kp_get_stats",
+           "kp_solve_batch", "kp_upload_batch", "kp_solve_batch_resident"]
 
 
 class Handle:
@@ -105,6 +109,41 @@ class Handle:
         out = _abi.result_to_dict(r, self._n_resources)
         lib().kp_result_free(C.byref(r))
         return out
+
+    @staticmethod
+    def _problem_array(problems):
+        arr = (C.c_void_p * len(problems))()
+        for i, p in enumerate(problems):
+            arr[i] = C.addressof(p.c)
+        return arr
+
+    def _batch_out(self, rc, results, n_resources):
+        if rc != 1:
+            self._check(rc)
+        outs = []
+        for r, nr in zip(results, n_resources):
+            o = _abi.result_to_dict(r, nr)
+            o["deadline"] = rc == 1
+            lib().kp_result_free(C.byref(r))
+            outs.append(o)
+        return outs
+
+    def solve_batch(self, problems, deadline_ms: int = 0) -> list:
+        """kp_solve_batch: independent Scheduler instances (NodePool shards, candidate sets), one CTA each."""
+        n = len(problems)
+        results = (_abi.kp_result * max(n, 1))()
+        rc = lib().kp_solve_batch(self._h, self._problem_array(problems), n, deadline_ms, results)
+        return self._batch_out(rc, results[:n], [p.n_resources for p in problems])
+
+    def upload_batch(self, problems):
+        self._batch_resources = [p.n_resources for p in problems]
+        self._check(lib().kp_upload_batch(self._h, self._problem_array(problems), len(problems)))
+
+    def solve_batch_resident(self, deadline_ms: int = 0) -> list:
+        n = len(self._batch_resources)
+        results = (_abi.kp_result * max(n, 1))()
+        rc = lib().kp_solve_batch_resident(self._h, deadline_ms, results)
+        return self._batch_out(rc, results[:n], self._batch_resources)
 
     def consolidate(self, problem: _abi.Problem, consol: _abi.ConsolInput, deadline_ms: int = 0) -> dict:
         r = _abi.kp_consol_result()

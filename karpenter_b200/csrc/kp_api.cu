@@ -63,11 +63,9 @@ struct Arena {  // device allocations of one upload, bump-allocated from chunks 
   }
 };
 
-struct kp_handle {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::string err;
-  Arena arena;
+// One uploaded problem == one Scheduler instance (scheduler.go:116-184): its tables in HBM and what the host needs to
+// assemble the result.  A handle owns one for kp_solve / kp_consolidate and a vector of them for kp_solve_batch.
+struct Instance {
   KpDev dev;
   HostTables host;
   bool resident = false;
@@ -84,8 +82,6 @@ struct kp_handle {
   int32_t *d_nsig_rs = nullptr, *d_nsig_tolset = nullptr;
   int64_t* d_rv_req = nullptr;
   int strict_undefined = 0;
-  kp_stats stats{};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   float wsolve_ms = 0;
   // state the solve mutates: pristine device copies, restored device-to-device before every solve (no host memory,
   // no allocation and no synchronisation sits between the first and the last kernel of a solve)
@@ -100,6 +96,23 @@ struct kp_handle {
   void *sort_keys_a = nullptr, *sort_keys_b = nullptr, *sort_tmp = nullptr;
   int32_t* sort_perm_b = nullptr;
   size_t sort_tmp_bytes = 0;
+  // shared-memory plan of the solve CTA (plan_solve)
+  int CS = 0, CR = 0;
+  size_t smem = 0;
+};
+
+struct kp_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  Arena arena;
+  Instance main;
+  std::vector<Instance*> batch;  // kp_upload_batch
+  Instance* cur = &main;          // the instance the helpers below work on
+  KpDev* d_batch_devs = nullptr;  // [batch] device copies of the instances' pointer blocks
+  int2* d_batch_plan = nullptr;   // [batch] {CS, CR}
+  kp_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 };
 
 template <class T>
@@ -121,7 +134,7 @@ static cudaError_t up_mut(kp_handle* h, T** dst, const std::vector<T>& v) {
   T* work;
   e = h->arena.alloc(&work, v.size());
   if (e != cudaSuccess) return e;
-  if (!v.empty()) h->resets.push_back({work, init, v.size() * sizeof(T)});
+  if (!v.empty()) h->cur->resets.push_back(Instance::Reset{work, init, v.size() * sizeof(T)});
   *dst = work;
   return cudaSuccess;
 }
@@ -161,6 +174,9 @@ __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
 }
 
 static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_consol_input* in, kp_consol_result* out);
+extern "C" {
+static void batch_clear(kp_handle* h);
+}
 
 extern "C" {
 
@@ -189,6 +205,7 @@ void kp_destroy(kp_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   h->arena.destroy();
+  for (Instance* b : h->batch) delete b;
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -203,8 +220,8 @@ int kp_get_stats(kp_handle* h, kp_stats* out) {
 }
 
 static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
-  HostTables& t = h->host;
-  KpDev& d = h->dev;
+  HostTables& t = h->cur->host;
+  KpDev& d = h->cur->dev;
   memset(&d, 0, sizeof(d));
   d.K = t.K;
   d.R = t.R;
@@ -353,7 +370,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
     d.n_fsig = (int)fsigs.size();
     d.n_nsig = (int)nsigs.size();
     d.EW = (t.E + 31) / 32;
-    h->strict_undefined = nodes_gain_keys ? 0 : 1;
+    h->cur->strict_undefined = nodes_gain_keys ? 0 : 1;
     if (hchk.empty()) hchk.push_back(int4{0, 0, 0, 0});
     if (nsig_rs.empty()) {
       nsig_rs.push_back(0);
@@ -368,9 +385,9 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
       CK(up(h, &a_, nsig_rs));
       CK(up(h, &b_, nsig_tolset));
       CK(up(h, &c_, rv_req));
-      h->d_nsig_rs = const_cast<int32_t*>(a_);
-      h->d_nsig_tolset = const_cast<int32_t*>(b_);
-      h->d_rv_req = const_cast<int64_t*>(c_);
+      h->cur->d_nsig_rs = const_cast<int32_t*>(a_);
+      h->cur->d_nsig_tolset = const_cast<int32_t*>(b_);
+      h->cur->d_rv_req = const_cast<int64_t*>(c_);
     }
     CK(up(h, &d.cls_hchk, hchk));
     std::vector<uint32_t> nact(std::max(d.EW, 1), 0);
@@ -448,7 +465,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   d.tmpl_all = t.N >= 64 ? ~0ull : ((1ull << t.N) - 1);
   d.H = t.E + d.Cmax;
   CK(zeros(h, &d.host_cnt, (size_t)std::max(t.GH, 1) * d.H));
-  CK(up(h, &h->d_host_cnt_nodes, t.host_cnt_nodes));
+  CK(up(h, &h->cur->d_host_cnt_nodes, t.host_cnt_nodes));
   CK(zeros(h, &d.n_claims, 1));
   CK(zeros(h, &d.counters, 16));
   CK(zeros(h, &d.status, 1));
@@ -457,9 +474,9 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
 
 // stack of state the solve mutates, so kp_solve_resident can be re-run on the same upload
 static int reset_dynamic(kp_handle* h) {
-  HostTables& t = h->host;
-  KpDev& d = h->dev;
-  for (auto& r : h->resets) CK(cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyDeviceToDevice, h->stream));
+  HostTables& t = h->cur->host;
+  KpDev& d = h->cur->dev;
+  for (auto& r : h->cur->resets) CK(cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemsetAsync(d.node_npods, 0, (size_t)std::max(t.E, 1) * 4, h->stream));
   size_t C = (size_t)d.Cmax;
   CK(cudaMemsetAsync(d.c_npods, 0, C * 4, h->stream));
@@ -467,60 +484,64 @@ static int reset_dynamic(kp_handle* h) {
   CK(cudaMemsetAsync(d.amask, 0, C * 8, h->stream));
   CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)std::max(t.GH, 1) * d.H * 4, h->stream));
   if (t.E && t.GH)  // initial hostname-group counts of the existing nodes: rows of E ints into rows of H ints
-    CK(cudaMemcpy2DAsync(d.host_cnt, (size_t)d.H * 4, h->d_host_cnt_nodes, (size_t)t.E * 4, (size_t)t.E * 4, t.GH,
+    CK(cudaMemcpy2DAsync(d.host_cnt, (size_t)d.H * 4, h->cur->d_host_cnt_nodes, (size_t)t.E * 4, (size_t)t.E * 4, t.GH,
                          cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemsetAsync(d.n_claims, 0, 4, h->stream));
   CK(cudaMemsetAsync(d.counters, 0, 128, h->stream));
   CK(cudaMemsetAsync(d.status, 0, 4, h->stream));
-  CK(cudaMemsetAsync(d.last_len, 0, (size_t)std::max<int64_t>(h->P, 1) * 4, h->stream));
+  CK(cudaMemsetAsync(d.last_len, 0, (size_t)std::max<int64_t>(h->cur->P, 1) * 4, h->stream));
   return KP_OK;
 }
 
-static int do_upload(kp_handle* h, const kp_problem* p, int cmax) {
+static int do_upload(kp_handle* h, const kp_problem* p, int cmax, bool fresh_arena = true) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  h->arena.reset();
-  h->resets.clear();
-  h->resident = false;
+  if (fresh_arena) {
+    if (h->cur == &h->main) batch_clear(h);  // the arena is shared: a fresh single upload invalidates every batch instance
+    h->main.resident = false;
+    h->arena.reset();
+  }
+  h->cur->resets.clear();
+  h->cur->resident = false;
   h->stats = kp_stats{};
   auto t0 = std::chrono::steady_clock::now();
-  h->host = HostTables();
+  h->cur->host = HostTables();
   std::vector<uint8_t> active(p->n_nodes, 0);
   for (int i = 0; i < p->n_nodes; i++) active[i] = (p->node_flags[i] & KP_NODE_SCHEDULABLE) != 0;
   std::vector<int32_t> pending(p->pod_class, p->pod_class + p->n_pods);
-  int rc = kp_prepare(p, active, {}, pending, h->host, h->err);
+  int rc = kp_prepare(p, active, {}, pending, h->cur->host, h->err);
   if (rc != KP_OK) return rc;
   auto t1 = std::chrono::steady_clock::now();
   h->stats.prep_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-  h->P = p->n_pods;
-  h->n_keys = p->n_keys;
-  h->n_resources = p->n_resources;
-  h->n_its = p->n_its;
-  h->n_nodes = p->n_nodes;
-  h->hostname_key = h->host.hostname_key;
-  h->key_nvalues.resize(p->n_keys);
-  for (int k = 0; k < p->n_keys; k++) h->key_nvalues[k] = p->key_value_off[k + 1] - p->key_value_off[k];
+  h->cur->P = p->n_pods;
+  h->cur->n_keys = p->n_keys;
+  h->cur->n_resources = p->n_resources;
+  h->cur->n_its = p->n_its;
+  h->cur->n_nodes = p->n_nodes;
+  h->cur->hostname_key = h->cur->host.hostname_key;
+  h->cur->key_nvalues.resize(p->n_keys);
+  for (int k = 0; k < p->n_keys; k++) h->cur->key_nvalues[k] = p->key_value_off[k + 1] - p->key_value_off[k];
   if (p->n_pods >= (1ll << 31) - 2) return h->err = "more than 2^31 pods", KP_ERR_CAPACITY;
   rc = upload_tables(h, p, cmax);
   if (rc != KP_OK) return rc;
-  KpDev& d = h->dev;
+  KpDev& d = h->cur->dev;
   d.P = p->n_pods;
   size_t P = (size_t)p->n_pods;
-  CK(up_raw(h, &h->d_pod_class, p->pod_class, P));
-  d.pod_class = h->d_pod_class;
+  CK(up_raw(h, &h->cur->d_pod_class, p->pod_class, P));
+  d.pod_class = h->cur->d_pod_class;
   if (p->pod_creation) {
-    CK(up_raw(h, &h->d_pod_creation, p->pod_creation, P));
+    CK(up_raw(h, &h->cur->d_pod_creation, p->pod_creation, P));
   } else {
-    CK(zeros(h, &h->d_pod_creation, P));
+    CK(zeros(h, &h->cur->d_pod_creation, P));
   }
-  CK(up_raw(h, &h->d_uid_hi, p->pod_uid_hi, P));
-  CK(up_raw(h, &h->d_uid_lo, p->pod_uid_lo, P));
+  CK(up_raw(h, &h->cur->d_uid_hi, p->pod_uid_hi, P));
+  CK(up_raw(h, &h->cur->d_uid_lo, p->pod_uid_lo, P));
   // class rank for byCPUAndMemoryDescending (queue.go:72-108): cpu desc, then memory desc
-  std::vector<int64_t> rank(std::max(h->host.X, 1), 0);
+  std::vector<int64_t> rank(std::max(h->cur->host.X, 1), 0);
   {
-    std::vector<int> idx(h->host.X);
-    for (int i = 0; i < h->host.X; i++) idx[i] = i;
-    auto key = [&](int x) { return std::make_pair(-h->host.cls_sort_cpu[x], -h->host.cls_sort_mem[x]); };
+    std::vector<int> idx(h->cur->host.X);
+    for (int i = 0; i < h->cur->host.X; i++) idx[i] = i;
+    auto key = [&](int x) { return std::make_pair(-h->cur->host.cls_sort_cpu[x], -h->cur->host.cls_sort_mem[x]); };
     std::sort(idx.begin(), idx.end(), [&](int a, int b) { return key(a) < key(b); });
     int64_t r = -1;
     for (size_t i = 0; i < idx.size(); i++) {
@@ -528,24 +549,24 @@ static int do_upload(kp_handle* h, const kp_problem* p, int cmax) {
       rank[idx[i]] = r;
     }
   }
-  CK(up_raw(h, &h->d_class_rank, rank.data(), rank.size()));
+  CK(up_raw(h, &h->cur->d_class_rank, rank.data(), rank.size()));
   {  // NewQueue sort: key / permutation ping-pong buffers and cub's scratch, sized once per upload
     int64_t* ka;
     int64_t* kb;
     CK(h->arena.alloc(&ka, P));
     CK(h->arena.alloc(&kb, P));
-    CK(h->arena.alloc(&h->sort_perm_b, P));
-    h->sort_keys_a = ka;
-    h->sort_keys_b = kb;
+    CK(h->arena.alloc(&h->cur->sort_perm_b, P));
+    h->cur->sort_keys_a = ka;
+    h->cur->sort_keys_b = kb;
     size_t n1 = 0, n2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, n1, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const int32_t*)nullptr,
                                     (int32_t*)nullptr, (int)std::max<size_t>(P, 1));
     cub::DeviceRadixSort::SortPairs(nullptr, n2, (const int64_t*)nullptr, (int64_t*)nullptr, (const int32_t*)nullptr,
                                     (int32_t*)nullptr, (int)std::max<size_t>(P, 1));
-    h->sort_tmp_bytes = std::max(n1, n2);
+    h->cur->sort_tmp_bytes = std::max(n1, n2);
     char* tmp;
-    CK(h->arena.alloc(&tmp, h->sort_tmp_bytes));
-    h->sort_tmp = tmp;
+    CK(h->arena.alloc(&tmp, h->cur->sort_tmp_bytes));
+    h->cur->sort_tmp = tmp;
   }
   CK(zeros(h, &d.queue, P + 1));
   CK(zeros(h, &d.qcls, P + 1));
@@ -555,7 +576,7 @@ static int do_upload(kp_handle* h, const kp_problem* p, int cmax) {
   CK(cudaStreamSynchronize(h->stream));
   auto t2 = std::chrono::steady_clock::now();
   h->stats.upload_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
-  h->resident = true;
+  h->cur->resident = true;
   return KP_OK;
 }
 
@@ -573,24 +594,24 @@ __global__ void k_iota(int32_t* p, int64_t n) {
 }
 
 static int sort_queue(kp_handle* h) {
-  KpDev& d = h->dev;
-  const int64_t P = h->P;
+  KpDev& d = h->cur->dev;
+  const int64_t P = h->cur->P;
   if (P <= 0) return KP_OK;
   const int nb = (int)((P + 255) / 256), n = (int)P;
   int32_t* perm_a = d.queue;  // passes ping-pong a -> b -> a -> b -> a: the result lands in d.queue
-  int32_t* perm_b = h->sort_perm_b;
-  uint64_t *ua = (uint64_t*)h->sort_keys_a, *ub = (uint64_t*)h->sort_keys_b;
-  int64_t *sa = (int64_t*)h->sort_keys_a, *sb = (int64_t*)h->sort_keys_b;
-  size_t tb = h->sort_tmp_bytes;
+  int32_t* perm_b = h->cur->sort_perm_b;
+  uint64_t *ua = (uint64_t*)h->cur->sort_keys_a, *ub = (uint64_t*)h->cur->sort_keys_b;
+  int64_t *sa = (int64_t*)h->cur->sort_keys_a, *sb = (int64_t*)h->cur->sort_keys_b;
+  size_t tb = h->cur->sort_tmp_bytes;
   k_iota<<<nb, 256, 0, h->stream>>>(perm_a, P);
-  k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_lo, perm_a, P, ua);
-  CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, tb, ua, ub, perm_a, perm_b, n, 0, 64, h->stream));
-  k_gather<<<nb, 256, 0, h->stream>>>(h->d_uid_hi, perm_b, P, ua);
-  CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, tb, ua, ub, perm_b, perm_a, n, 0, 64, h->stream));
-  k_gather<<<nb, 256, 0, h->stream>>>(h->d_pod_creation, perm_a, P, sa);
-  CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, tb, sa, sb, perm_a, perm_b, n, 0, 64, h->stream));
-  k_sort_keys<<<nb, 256, 0, h->stream>>>(d.pod_class, h->d_class_rank, perm_b, P, sa);
-  CK(cub::DeviceRadixSort::SortPairs(h->sort_tmp, tb, sa, sb, perm_b, perm_a, n, 0, 64, h->stream));
+  k_gather<<<nb, 256, 0, h->stream>>>(h->cur->d_uid_lo, perm_a, P, ua);
+  CK(cub::DeviceRadixSort::SortPairs(h->cur->sort_tmp, tb, ua, ub, perm_a, perm_b, n, 0, 64, h->stream));
+  k_gather<<<nb, 256, 0, h->stream>>>(h->cur->d_uid_hi, perm_b, P, ua);
+  CK(cub::DeviceRadixSort::SortPairs(h->cur->sort_tmp, tb, ua, ub, perm_b, perm_a, n, 0, 64, h->stream));
+  k_gather<<<nb, 256, 0, h->stream>>>(h->cur->d_pod_creation, perm_a, P, sa);
+  CK(cub::DeviceRadixSort::SortPairs(h->cur->sort_tmp, tb, sa, sb, perm_a, perm_b, n, 0, 64, h->stream));
+  k_sort_keys<<<nb, 256, 0, h->stream>>>(d.pod_class, h->cur->d_class_rank, perm_b, P, sa);
+  CK(cub::DeviceRadixSort::SortPairs(h->cur->sort_tmp, tb, sa, sb, perm_b, perm_a, n, 0, 64, h->stream));
   k_gather<<<nb, 256, 0, h->stream>>>(d.pod_class, d.queue, P, d.qcls);
   h->stats.kernel_launches += 6;
   return KP_OK;
@@ -598,33 +619,32 @@ static int sort_queue(kp_handle* h) {
 
 // shared-memory plan of a kernel that stages the read-only tables: returns the table bytes to stage (0 = leave in L2)
 static size_t plan_tables(kp_handle* h, size_t fixed, size_t budget) {
-  KpDev& d = h->dev;
-  d.n_ge = (int)h->host.ge_vals.size();
-  d.n_itv = std::max(h->host.itv_off[d.K], 1);
+  KpDev& d = h->cur->dev;
+  d.n_ge = (int)h->cur->host.ge_vals.size();
+  d.n_itv = std::max(h->cur->host.itv_off[d.K], 1);
   size_t tb = kp_tab_bytes(d);
   d.tab_bytes = (fixed + tb <= budget && tb <= 110 * 1024) ? (int)tb : 0;
   return (size_t)d.tab_bytes;
 }
 
 static int launch_node_cand(kp_handle* h) {
-  KpDev& d = h->dev;
+  KpDev& d = h->cur->dev;
   if (d.E <= 0) return KP_OK;
   dim3 grid((d.E + 255) / 256, d.n_nsig + d.n_rv);
-  k_node_cand<<<grid, 256, 0, h->stream>>>(d, h->d_nsig_rs, h->d_nsig_tolset, h->d_rv_req, h->strict_undefined);
+  k_node_cand<<<grid, 256, 0, h->stream>>>(d, h->cur->d_nsig_rs, h->cur->d_nsig_tolset, h->cur->d_rv_req, h->cur->strict_undefined);
   const int nsum = (d.n_rv + d.n_nsig) * d.ESW;
   k_node_sum<<<(nsum + 255) / 256, 256, 0, h->stream>>>(d);
   h->stats.kernel_launches += 2;
   return KP_OK;
 }
 
-static int run_solve(kp_handle* h) {
-  KpDev& d = h->dev;
-  cudaSetDevice(h->device);
-  int rc = reset_dynamic(h);
-  if (rc != KP_OK) return rc;
-  CK(cudaEventRecord(h->ev0, h->stream));
-  int64_t P = h->P;
-  h->stats.kernel_launches = 0;
+// Everything of a solve in front of the solver kernel (after reset_dynamic): NewScheduler prefilter, NewQueue,
+// existing-node candidate bitmaps, and the shared-memory plan of the solver CTA.  Asynchronous on the handle's stream.
+static int prep_solve(kp_handle* h) {
+  Instance& in = *h->cur;
+  KpDev& d = in.dev;
+  int rc;
+  int64_t P = in.P;
   // NewScheduler prefilter of template instance types (scheduler.go:147)
   if (d.N > 0) {
     k_feasibility<<<(d.N * 32 + 255) / 256, 256, 0, h->stream>>>(d, nullptr, 1);
@@ -669,10 +689,25 @@ static int run_solve(kp_handle* h) {
     CS = lo;
   }
   if (const char* lim = getenv("KP_CS_LIMIT")) CS = std::min(CS, std::max(0, atoi(lim)) / 32 * 32);  // test knob
-  size_t smem = fixed + tb + (CS ? small_bytes(CS) : 0) + 64;
-  CK(cudaFuncSetAttribute(k_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  in.CS = CS;
+  in.CR = CR;
+  in.smem = fixed + tb + (CS ? small_bytes(CS) : 0) + 64;
+  return KP_OK;
+}
+
+static int run_solve(kp_handle* h) {
+  Instance& in = *h->cur;
+  KpDev& d = in.dev;
+  cudaSetDevice(h->device);
+  int rc = reset_dynamic(h);
+  if (rc != KP_OK) return rc;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  h->stats.kernel_launches = 0;
+  rc = prep_solve(h);
+  if (rc != KP_OK) return rc;
+  CK(cudaFuncSetAttribute(k_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)in.smem));
   CK(cudaEventRecord(h->ev2, h->stream));
-  k_wsolve<<<1, 64, smem, h->stream>>>(d, CS, CR);
+  k_wsolve<<<1, 64, in.smem, h->stream>>>(d, in.CS, in.CR);
   h->stats.kernel_launches++;
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -680,13 +715,13 @@ static int run_solve(kp_handle* h) {
   float ms = 0;
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->stats.solve_ms = ms;
-  cudaEventElapsedTime(&h->wsolve_ms, h->ev2, h->ev1);
-  if (getenv("KP_DEBUG")) fprintf(stderr, "[kp] step %.3f ms, k_wsolve %.3f ms\n", ms, h->wsolve_ms);
+  cudaEventElapsedTime(&in.wsolve_ms, h->ev2, h->ev1);
+  if (getenv("KP_DEBUG")) fprintf(stderr, "[kp] step %.3f ms, k_wsolve %.3f ms\n", ms, in.wsolve_ms);
   return KP_OK;
 }
 
 static int download(kp_handle* h, kp_result* out) {
-  KpDev& d = h->dev;
+  KpDev& d = h->cur->dev;
   auto t0 = std::chrono::steady_clock::now();
   memset(out, 0, sizeof(*out));
   int32_t nclaims = 0;
@@ -696,8 +731,8 @@ static int download(kp_handle* h, kp_result* out) {
   if (getenv("KP_DEBUG"))
     fprintf(stderr, "[kp] slow_sorts=%lld scan_chunks=%lld evals=%lld commits=%lld\n", (long long)counters[4],
             (long long)counters[5], (long long)counters[6], (long long)counters[3]);
-  int64_t P = h->P;
-  int K = h->n_keys, R = h->n_resources, ITW = (h->n_its + 63) / 64;
+  int64_t P = h->cur->P;
+  int K = h->cur->n_keys, R = h->cur->n_resources, ITW = (h->cur->n_its + 63) / 64;
   size_t C = (size_t)nclaims, c1 = C ? C : 1;
   out->n_pods = P;
   out->pod_target = (int32_t*)malloc(sizeof(int32_t) * (P ? P : 1));
@@ -728,7 +763,7 @@ static int download(kp_handle* h, kp_result* out) {
   CK(cudaMemcpy(sg.data(), d.c_sgte, C * K * 8, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(sl.data(), d.c_slte, C * K * 8, cudaMemcpyDeviceToHost));
   std::vector<int> woff(K + 1, 0);
-  for (int k = 0; k < K; k++) woff[k + 1] = woff[k] + (k == h->hostname_key ? 0 : (h->key_nvalues[k] + 63) / 64);
+  for (int k = 0; k < K; k++) woff[k + 1] = woff[k] + (k == h->cur->hostname_key ? 0 : (h->cur->key_nvalues[k] + 63) / 64);
   int MW = woff[K];
   out->n_keys = K;
   out->mask_words = MW;
@@ -739,7 +774,7 @@ static int download(kp_handle* h, kp_result* out) {
   for (size_t c = 0; c < C; c++)
     for (int k = 0; k < K; k++) {
       uint8_t f = sf[c * K + k];
-      if (!(f & SF_PRESENT) || k == h->hostname_key) continue;
+      if (!(f & SF_PRESENT) || k == h->cur->hostname_key) continue;
       uint8_t of = KP_SLOT_PRESENT | ((f & SF_COMPLEMENT) ? KP_REQ_COMPLEMENT : 0) |
                    ((f & SF_HAS_GTE) ? KP_REQ_HAS_GTE : 0) | ((f & SF_HAS_LTE) ? KP_REQ_HAS_LTE : 0);
       out->claim_req_flags[c * K + k] = of;
@@ -748,7 +783,7 @@ static int download(kp_handle* h, kp_result* out) {
       if (woff[k + 1] > woff[k]) out->claim_req_mask[c * MW + woff[k]] = sm[c * K + k];
     }
   // topology counters, non-hostname groups (regular then inverse == creation order of the reference's two maps)
-  HostTables& t = h->host;
+  HostTables& t = h->cur->host;
   std::vector<int32_t> cnt((size_t)std::max(t.G, 1) * 64);
   CK(cudaMemcpy(cnt.data(), d.dom_cnt, cnt.size() * 4, cudaMemcpyDeviceToHost));
   // order of the reference's maps: groups of NewTopology in creation order, then the groups relaxed pods created, in
@@ -770,7 +805,7 @@ static int download(kp_handle* h, kp_result* out) {
   for (int g : gorder) {
     int key = t.groups[g].key;
     if (key != t.hostname_key) {
-      int nv = h->key_nvalues[key];
+      int nv = h->cur->key_nvalues[key];
       for (int v = 0; v < nv; v++) flat.push_back(cnt[(size_t)g * 64 + v]);
     }
     off.push_back((int32_t)flat.size());
@@ -793,12 +828,12 @@ static int download(kp_handle* h, kp_result* out) {
 }
 
 int kp_solve_resident(kp_handle* h, int64_t deadline_ms, kp_result* out) {
-  h->dev.deadline_ns = deadline_ms > 0 ? deadline_ms * 1000000ll : 0;
-  if (!h->resident) return h->err = "kp_upload has not been called", KP_ERR_INVALID;
+  h->cur->dev.deadline_ns = deadline_ms > 0 ? deadline_ms * 1000000ll : 0;
+  if (!h->cur->resident) return h->err = "kp_upload has not been called", KP_ERR_INVALID;
   int rc = run_solve(h);
   if (rc != KP_OK) return rc;
   int32_t status = 0;
-  CK(cudaMemcpy(&status, h->dev.status, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&status, h->cur->dev.status, 4, cudaMemcpyDeviceToHost));
   if (status == KP_DEADLINE) {  // partial results are valid (scheduler.go:411-414)
     rc = download(h, out);
     return rc == KP_OK ? KP_DEADLINE : rc;
@@ -818,6 +853,154 @@ int kp_solve(kp_handle* h, const kp_problem* p, int64_t deadline_ms, kp_result* 
       continue;
     }
     return rc;
+  }
+}
+
+// ---- kp_solve_batch: n independent Scheduler instances, one launch (one CTA per instance) ------------------------
+static void batch_clear(kp_handle* h) {
+  for (Instance* b : h->batch) delete b;
+  h->batch.clear();
+  h->cur = &h->main;
+}
+
+static int upload_batch(kp_handle* h, const kp_problem* const* problems, int n, const std::vector<int64_t>& cmax) {
+  batch_clear(h);
+  h->main.resident = false;
+  double prep = 0, upl = 0;
+  int64_t h2d = 0;
+  for (int b = 0; b < n; b++) {
+    h->batch.push_back(new Instance());
+    h->cur = h->batch.back();
+    int rc = do_upload(h, problems[b], (int)std::max<int64_t>(cmax[b], 1), b == 0);
+    prep += h->stats.prep_ms;
+    upl += h->stats.upload_ms;
+    h2d += h->stats.bytes_h2d;
+    if (rc != KP_OK) {
+      h->cur = &h->main;
+      return rc;
+    }
+  }
+  h->cur = &h->main;
+  h->stats.prep_ms = prep;
+  h->stats.upload_ms = upl;
+  h->stats.bytes_h2d = h2d;
+  CK(h->arena.alloc(&h->d_batch_devs, (size_t)std::max(n, 1)));
+  CK(h->arena.alloc(&h->d_batch_plan, (size_t)std::max(n, 1)));
+  return KP_OK;
+}
+
+static int64_t cmax_guess(const kp_problem* p) {
+  return std::min<int64_t>(p->n_pods, std::max<int64_t>(4096, p->n_pods / 8));
+}
+
+int kp_upload_batch(kp_handle* h, const kp_problem* const* problems, int32_t n) {
+  if (n < 0 || (n > 0 && !problems)) return h->err = "kp_upload_batch: bad arguments", KP_ERR_INVALID;
+  std::vector<int64_t> cmax(n);
+  for (int b = 0; b < n; b++) cmax[b] = cmax_guess(problems[b]);
+  return upload_batch(h, problems, n, cmax);
+}
+
+// statuses[b]: KP_OK / KP_DEADLINE / KP_ERR_CAPACITY of instance b
+static int run_batch(kp_handle* h, int64_t deadline_ms, std::vector<int32_t>& statuses) {
+  const int n = (int)h->batch.size();
+  statuses.assign(n, KP_OK);
+  if (n == 0) return KP_OK;
+  cudaSetDevice(h->device);
+  for (Instance* b : h->batch) {
+    if (!b->resident) return h->err = "kp_upload_batch has not been called", KP_ERR_INVALID;
+    b->dev.deadline_ns = deadline_ms > 0 ? deadline_ms * 1000000ll : 0;
+    h->cur = b;
+    int rc = reset_dynamic(h);
+    if (rc != KP_OK) return h->cur = &h->main, rc;
+  }
+  CK(cudaEventRecord(h->ev0, h->stream));
+  h->stats.kernel_launches = 0;
+  std::vector<KpDev> devs(n);
+  std::vector<int2> plan(n);
+  size_t smem = 0;
+  for (int b = 0; b < n; b++) {
+    h->cur = h->batch[b];
+    int rc = prep_solve(h);
+    if (rc != KP_OK) return h->cur = &h->main, rc;
+    devs[b] = h->cur->dev;
+    plan[b] = make_int2(h->cur->CS, h->cur->CR);
+    smem = std::max(smem, h->cur->smem);
+  }
+  h->cur = &h->main;
+  CK(cudaMemcpyAsync(h->d_batch_devs, devs.data(), sizeof(KpDev) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_batch_plan, plan.data(), sizeof(int2) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaFuncSetAttribute(k_wsolve_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaEventRecord(h->ev2, h->stream));
+  k_wsolve_batch<<<n, 64, smem, h->stream>>>(h->d_batch_devs, h->d_batch_plan);
+  h->stats.kernel_launches++;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // devs / plan are host vectors: the copies above must have completed
+  CK(cudaGetLastError());
+  float ms = 0, wms = 0;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  cudaEventElapsedTime(&wms, h->ev2, h->ev1);
+  h->stats.solve_ms = ms;
+  if (getenv("KP_DEBUG")) fprintf(stderr, "[kp] batch of %d: step %.3f ms, k_wsolve_batch %.3f ms\n", n, ms, wms);
+  for (int b = 0; b < n; b++) {
+    h->batch[b]->wsolve_ms = wms;
+    CK(cudaMemcpy(&statuses[b], h->batch[b]->dev.status, 4, cudaMemcpyDeviceToHost));
+  }
+  return KP_OK;
+}
+
+static int download_batch(kp_handle* h, const std::vector<int32_t>& statuses, kp_result* outs) {
+  int worst = KP_OK;
+  double dl = 0;
+  int64_t d2h = 0;
+  const double solve_ms = h->stats.solve_ms;
+  for (size_t b = 0; b < h->batch.size(); b++) {
+    h->cur = h->batch[b];
+    int rc = download(h, &outs[b]);
+    h->cur = &h->main;
+    if (rc != KP_OK) {
+      for (size_t i = 0; i < b; i++) kp_result_free(&outs[i]);
+      return rc;
+    }
+    outs[b].solve_ms = solve_ms;
+    dl += h->stats.download_ms;
+    d2h += h->stats.bytes_d2h;
+    if (statuses[b] == KP_DEADLINE) worst = KP_DEADLINE;
+  }
+  h->stats.download_ms = dl;
+  h->stats.bytes_d2h = d2h;
+  return worst;
+}
+
+int kp_solve_batch_resident(kp_handle* h, int64_t deadline_ms, kp_result* outs) {
+  std::vector<int32_t> st;
+  int rc = run_batch(h, deadline_ms, st);
+  if (rc != KP_OK) return rc;
+  for (int32_t s : st)
+    if (s != KP_OK && s != KP_DEADLINE) return h->err = "claim capacity exceeded in a batch instance", s;
+  return download_batch(h, st, outs);
+}
+
+int kp_solve_batch(kp_handle* h, const kp_problem* const* problems, int32_t n, int64_t deadline_ms, kp_result* outs) {
+  if (n < 0 || (n > 0 && (!problems || !outs))) return h->err = "kp_solve_batch: bad arguments", KP_ERR_INVALID;
+  std::vector<int64_t> cmax(n);
+  for (int b = 0; b < n; b++) cmax[b] = cmax_guess(problems[b]);
+  for (;;) {
+    int rc = upload_batch(h, problems, n, cmax);
+    if (rc != KP_OK) return rc;
+    std::vector<int32_t> st;
+    rc = run_batch(h, deadline_ms, st);
+    if (rc != KP_OK) return rc;
+    bool grow = false;
+    for (int b = 0; b < n; b++) {
+      if (st[b] == KP_ERR_CAPACITY && cmax[b] < problems[b]->n_pods) {  // more NodeClaims than provisioned: grow, redo
+        cmax[b] = std::min<int64_t>(problems[b]->n_pods, cmax[b] * 4);
+        grow = true;
+      } else if (st[b] != KP_OK && st[b] != KP_DEADLINE) {
+        return h->err = "batch instance failed", st[b];
+      }
+    }
+    if (grow) continue;
+    return download_batch(h, st, outs);
   }
 }
 
@@ -841,7 +1024,7 @@ void kp_result_free(kp_result* r) {
 int kp_feasibility(kp_handle* h, const kp_problem* p, uint64_t* out_bits, int32_t* out_it_words) {
   int rc = do_upload(h, p, 1);
   if (rc != KP_OK) return rc;
-  KpDev& d = h->dev;
+  KpDev& d = h->cur->dev;
   *out_it_words = d.ITW;
   size_t n = (size_t)d.X * d.N * d.ITW;
   uint64_t* dout;
@@ -890,8 +1073,8 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   const int S = in->n_subsets;
   int rc = do_upload(h, p, 1);  // the cluster's pod table doubles as the "pods" of the problem (rows by node)
   if (rc != KP_OK) return rc;
-  HostTables& t = h->host;
-  KpDev& d = h->dev;
+  HostTables& t = h->cur->host;
+  KpDev& d = h->cur->dev;
   if (t.has_min_values) {  // RemoveInstanceTypeOptionsByPriceAndMinValues / Truncate with minValues (nodeclaim.go:309-318)
     h->err = "consolidation with minValues on a NodePool is not supported yet";
     return KP_ERR_UNSUPPORTED;
@@ -1067,10 +1250,10 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
       rc = run_solve(h);
       if (rc != KP_OK) return rc;
       int32_t status = 0;
-      CK(cudaMemcpy(&status, h->dev.status, 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&status, h->cur->dev.status, 4, cudaMemcpyDeviceToHost));
       if (status != KP_OK) return h->err = "consolidation simulation failed", status;
       total_ms += h->stats.solve_ms;
-      k_decide<<<1, 32, 0, h->stream>>>(h->dev, q, sn, d_snodes, 0);
+      k_decide<<<1, 32, 0, h->stream>>>(h->cur->dev, q, sn, d_snodes, 0);
       CK(cudaStreamSynchronize(h->stream));
       CK(cudaGetLastError());
       CK(cudaMemcpy(out->decision + s, q.decision, 1, cudaMemcpyDeviceToHost));
@@ -1105,8 +1288,8 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   q.subset_nodes = tmp32;
   CK(up_raw(h, &tmp32, in->node_pod_off, (size_t)E + 1));
   q.node_pod_off = tmp32;
-  q.pod_class = h->d_pod_class;
-  CK(zeros(h, &tmp32, (size_t)std::max<int64_t>(h->P, 1)));
+  q.pod_class = h->cur->d_pod_class;
+  CK(zeros(h, &tmp32, (size_t)std::max<int64_t>(h->cur->P, 1)));
   int32_t* d_rank = tmp32;
   q.pod_rank = d_rank;
   {
@@ -1185,8 +1368,8 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   }
   rc = sort_queue(h);  // byCPUAndMemoryDescending over every pod row; a subset's queue is its rows in rank order
   if (rc != KP_OK) return rc;
-  if (h->P > 0) {
-    k_scatter_rank<<<(int)((h->P + 255) / 256), 256, 0, h->stream>>>(d.queue, h->P, d_rank);
+  if (h->cur->P > 0) {
+    k_scatter_rank<<<(int)((h->cur->P + 255) / 256), 256, 0, h->stream>>>(d.queue, h->cur->P, d_rank);
     h->stats.kernel_launches++;
   }
   rc = launch_node_cand(h);

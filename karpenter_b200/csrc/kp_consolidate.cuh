@@ -146,7 +146,7 @@ struct WSolveShared {
 };
 
 // warp 0: the solver; warp 1: the pod stager (see StageRing)
-__global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS, int CR) {
+__device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WSolveShared& sh = *reinterpret_cast<WSolveShared*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -259,6 +259,15 @@ __global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev 
     d.counters[7] = I.n_unsched;
     d.counters[8] = I.n_uninit;
   }
+}
+__global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS, int CR) {
+  wsolve_cta(d_in, CS, CR);
+}
+// Many Scheduler instances in one launch, one CTA (== one SM) each: NodePool shards of a provisioning pass, or the
+// candidate sets of a consolidation pass whose pods carry topology constraints (SimulateScheduling, helpers.go:51-142).
+// Instances share nothing but the device; plan[b] = {CS, CR} of instance b.
+__global__ void __launch_bounds__(64, 1) k_wsolve_batch(const KpDev* __restrict__ devs, const int2* __restrict__ plan) {
+  wsolve_cta(devs[blockIdx.x], plan[blockIdx.x].x, plan[blockIdx.x].y);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

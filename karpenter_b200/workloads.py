@@ -189,20 +189,34 @@ def config_c5(n_pods=10_000_000, n_pools=8, n_its=1000, app_replicas=1000, pools
     return b.build()
 
 
-def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_its=50, catalog="generic",
-              spot_fraction=0.0, spot_to_spot=False, node_cpu=(0, 16)):
-    """C4: a cluster of existing KWOK nodes full of running pods + the removal subsets to evaluate.
+def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_its=144, catalog="generic",
+              spot_fraction=0.0, spot_to_spot=False, node_cpus=(8, 16), window=4, slack_pods=20):
+    """C4: a cluster of existing KWOK nodes holding `n_pods` running pods + the removal subsets to evaluate.
 
-    Returns (EncodedProblem, ConsolInput-kwargs dict).  Nodes draw their instance type uniformly from the linux /
-    on-demand members of C1's catalog and a zone uniformly; pods are dealt first-fit round-robin so the state is
-    consistent (available = allocatable - bound requests >= 0).  Candidates are the `n_candidates` nodes with the
-    lowest disruption cost == fewest pods (utils/disruption/disruption.go:71-77 with default pod costs), and every
-    subset of size 1..max_subset of them is one computeConsolidation call (100 + 4950 + 161700 = 166750).
+    Returns (EncodedProblem, ConsolInput-kwargs dict).  BASELINE configs[3]: 10 000 nodes, 200 000 running pods, i.e.
+    20 pods per node on average.  C1's 50 smallest generic types cannot hold that (4.7 vCPU per node on average against
+    13.4 vCPU of requests), so the catalog is the whole generic KWOK table (144 types).  The cluster is what a bin-packing
+    provisioner leaves behind: the pod stream (reference request mix, seed 42) is dealt first-fit into the last
+    `window` nodes opened; when a pod fits none of them the next node is opened, with a size class from `node_cpus`
+    chosen by a feedback rule (pods left / nodes left against the expected pods per full node of each class) and,
+    inside the class, a uniformly drawn linux type (family c / s / m, amd64 / arm64) and zone.  With the defaults all
+    10 000 nodes are used, 99 % of the allocatable vCPU are requested, nodes hold 7 .. 41 pods -- and EVERY pod is
+    placed (asserted; nothing is dropped).  `slack_pods` extra pods are packed with the rest and have terminated since,
+    so exactly `n_pods` run and the cluster has a dozen pod-sized holes: the freed pods of a candidate set fit into
+    them only partly, which is what makes delete, replace and no-op all occur (one half-empty node anywhere would turn
+    every <=3-node set into a delete).
+    Candidates are the `n_candidates` non-empty nodes with the lowest DisruptionCost (multinodeconsolidation.go:87,
+    utils/disruption/disruption.go:71-77: with default pod deletion costs and no expiry the cost of a node is its pod
+    count; ties by node index), and every subset of size 1..max_subset of them is one computeConsolidation call
+    (100 + 4950 + 161700 = 166750).  A cluster with fewer pods than nodes x pods-per-node simply leaves the tail nodes
+    partly filled (the small test instances).
 
-    `catalog="aws"` draws the nodes from the AWS-KWOK catalog instead and lets the NodePool launch any OS and capacity type, so
-    a replacement NodeClaim can carry more than 600 instance types (the price-ordered truncation of
-    scheduler.go:361-379); `spot_fraction` of the nodes run on spot capacity (spot-to-spot rules, consolidation.go:236-316).
+    `catalog="aws"` draws the nodes from the AWS-KWOK catalog instead (size classes by vCPU) and lets the NodePool launch
+    any OS and capacity type, so a replacement NodeClaim can carry more than 600 instance types (the price-ordered
+    truncation of scheduler.go:361-379); `spot_fraction` of the nodes run on spot capacity (spot-to-spot rules,
+    consolidation.go:236-316).
     """
+    from .model import quantity_units
     b = ProblemBuilder()
     aws = catalog == "aws"
     its = kwok.aws_instance_types(n_its) if aws else kwok.generic_instance_types()[:n_its]
@@ -219,40 +233,69 @@ def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_
 
     def _arch(it):
         return [r.values[0] for r in it.requirements if r.key == ARCH_LABEL][0]
-    linux = [i for i, it in enumerate(its)
-             if _os(it) == "linux" and (not aws or node_cpu[0] <= int(it.capacity["cpu"]) <= node_cpu[1])]
+    classes = [[i for i, it in enumerate(its) if _os(it) == "linux" and int(it.capacity["cpu"]) == c] for c in node_cpus]
+    classes = [c for c in classes if c]
+    if not classes:
+        raise ValueError(f"no linux instance type with cpu in {node_cpus} among the first {n_its} of the {catalog} catalog")
     zones = kwok.AWS_ZONES if aws else kwok.KWOK_ZONES
     dn = draws(n_nodes, 2, SEED + 10)
-    node_it = np.array(linux)[(dn[:, 0] % np.uint64(len(linux))).astype(int)]
     node_zone = (dn[:, 1] % np.uint64(4)).astype(int)
     node_spot = (draws(n_nodes, 1, SEED + 12)[:, 0] % np.uint64(1000)).astype(int) < int(1000 * spot_fraction)
-    from .model import quantity_units
     R = ["cpu", "memory", "pods", "ephemeral-storage"]
-    alloc = np.zeros((n_nodes, 4), np.int64)
-    for n in range(n_nodes):
-        it = its[node_it[n]]
-        for r, name in enumerate(R):
-            alloc[n, r] = quantity_units(name, it.capacity[name]) - quantity_units(name, it.overhead.get(name, 0))
-    dp = draws(n_pods, 4, SEED + 11)
+    alloc_t = np.array([[quantity_units(name, it.capacity[name]) - quantity_units(name, it.overhead.get(name, 0))
+                         for name in R] for it in its], np.int64)
+    n_keep = n_pods
+    n_pods = n_keep + int(slack_pods)  # packed first, then `slack_pods` of them leave again (see below)
+    dp = draws(n_pods, 5, SEED + 11)
     ci, mi = (dp[:, 0] % np.uint64(5)).astype(int), (dp[:, 1] % np.uint64(6)).astype(int)
     req = np.stack([np.array(CPU_MILLI)[ci], np.array(MEM_MI)[mi] * (1 << 20), np.ones(n_pods, np.int64),
                     np.zeros(n_pods, np.int64)], axis=1).astype(np.int64)
+    per = [alloc_t[c[0], 0] / req[:, 0].mean() for c in classes]  # expected pods of a full node, per size class
+    node_it = np.zeros(n_nodes, np.int64)
+    alloc = np.zeros((n_nodes, 4), np.int64)
     used = np.zeros((n_nodes, 4), np.int64)
     pod_node = np.full(n_pods, -1, np.int64)
-    hopeless = np.zeros((5, 6), bool)  # request mixes that already failed a full scan (usage only grows)
+    nn = 0
     for i in range(n_pods):
-        n = i % n_nodes
-        if not np.all(used[n] + req[i] <= alloc[n]):
-            if hopeless[ci[i], mi[i]]:
+        r = req[i]
+        n = -1
+        for m in range(max(0, nn - window), nn):
+            if used[m, 0] + r[0] <= alloc[m, 0] and used[m, 1] + r[1] <= alloc[m, 1] and used[m, 2] + 1 <= alloc[m, 2]:
+                n = m
+                break
+        if n < 0:
+            if nn >= n_nodes:  # every node is open: the stragglers go first-fit into whatever crack holds them
+                ok = np.nonzero(np.all(used + r <= alloc, axis=1))[0]
+                if ok.size:
+                    used[ok[0]] += r
+                    pod_node[i] = ok[0]
                 continue
-            ok = np.nonzero(np.all(used + req[i] <= alloc, axis=1))[0]  # first fit, cyclically from n
-            if ok.size == 0:
-                hopeless[ci[i], mi[i]] = True
-                continue  # cluster full: drop the pod
-            j = np.searchsorted(ok, n)
-            n = int(ok[j]) if j < ok.size else int(ok[0])
-        used[n] += req[i]
+            want = (n_pods - i) / (n_nodes - nn)
+            k = 0
+            for kk in range(len(classes) - 1):
+                if want > 0.5 * (per[kk] + per[kk + 1]):
+                    k = kk + 1
+            node_it[nn] = classes[k][int(dn[nn, 0] % np.uint64(len(classes[k])))]
+            alloc[nn] = alloc_t[node_it[nn]]
+            n = nn
+            nn += 1
+        used[n] += r
         pod_node[i] = n
+    for n in range(nn, n_nodes):  # nodes the stream never reached stay empty (small test instances only)
+        node_it[n] = classes[0][int(dn[n, 0] % np.uint64(len(classes[0])))]
+        alloc[n] = alloc_t[node_it[n]]
+    # scale-down since the nodes were provisioned: `slack_pods` pods (lowest draw first; a pod the full cluster had no
+    # room for counts as gone already) have left again, which leaves exactly the requested number of running pods and
+    # a handful of holes scattered over the cluster
+    stay = pod_node >= 0
+    if stay.sum() < n_keep:
+        raise ValueError(f"C4: {n_nodes} nodes of {node_cpus} vCPU cannot hold {n_keep} pods ({stay.sum()} placed)")
+    placed = np.nonzero(stay)[0]
+    gone = placed[np.argsort(dp[placed, 4], kind="stable")[:len(placed) - n_keep]]
+    np.subtract.at(used, pod_node[gone], req[gone])
+    stay[gone] = False
+    assert stay.sum() == n_keep and (used <= alloc).all() and (used >= 0).all()
+    pod_node, ci, mi, dp, req, n_pods = pod_node[stay], ci[stay], mi[stay], dp[stay], req[stay], n_keep
     table = np.zeros((5, 6), np.int32)
     for c in range(5):
         for m in range(6):
@@ -271,11 +314,10 @@ def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_
         b.add_node(StateNode(name=f"node-{n:05d}", labels=labels, available=avail, capacity=cap, nodepool="default",
                              instance_type=it.name))
     # pod rows grouped by node (kp_consol_input.node_pod_off); node order == name order == index order here
-    keep = pod_node >= 0
-    order = np.argsort(pod_node[keep], kind="stable")
-    rows_cls = table[ci[keep], mi[keep]][order]
-    rows_node = pod_node[keep][order]
-    b.set_pod_arrays(rows_cls, np.zeros(len(rows_cls), np.int64), dp[keep][order, 2], dp[keep][order, 3])
+    order = np.argsort(pod_node, kind="stable")
+    rows_cls = table[ci, mi][order]
+    rows_node = pod_node[order]
+    b.set_pod_arrays(rows_cls, np.zeros(len(rows_cls), np.int64), dp[order, 2], dp[order, 3])
     enc = b.build()
     counts = np.bincount(rows_node, minlength=n_nodes)
     node_pod_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)

@@ -94,27 +94,76 @@ def test_c4_consolidation_uninitialized_and_price(handle):
 
 
 def test_c4_full_size_sampled_parity(handle):
-    """BASELINE configs[3] at full size (10k nodes, all 166 750 <=3-node subsets of the 100 candidates) on the GPU;
-    the oracle re-simulates a seeded sample of 300 subsets and every one must agree bit for bit.  Size-independent
-    properties checked on all subsets: a delete decision has no new claim, a replace exactly one, and a subset whose
-    superset... (monotonicity does not hold in general, so only the per-subset invariants are asserted)."""
+    """BASELINE configs[3] at full size (10 000 nodes holding 200 000 running pods, all 166 750 <=3-node subsets of the
+    100 cheapest candidates) on the GPU; the oracle re-simulates a seeded sample of 5 400 subsets stratified over subset
+    size AND over the GPU's decisions (every delete / no-op the GPU reports, up to 1 800 each, the rest replaces), and
+    every one must agree bit for bit.  Size-independent properties checked on all subsets: a delete decision has no
+    new claim, a replace exactly one, nothing is left unscheduled in either."""
     from karpenter_b200 import _abi
     enc, consol = workloads.config_c4()
+    assert enc.problem.n_nodes == 10000 and enc.problem.n_pods == 200000
     gpu = handle.consolidate(enc.problem, _abi.ConsolInput(**consol))
     S = consol["n_subsets"]
     assert S == 166750 and len(gpu["decision"]) == S
     dec, nnew, uns = gpu["decision"], gpu["n_new_claims"], gpu["n_unscheduled"]
     assert np.all(nnew[dec == 1] == 0) and np.all(nnew[dec == 2] == 1) and np.all(uns[dec != 0] == 0)
     assert np.all(gpu["replacement_its"][dec != 2] == 0) and np.all(gpu["replacement_its"][dec == 2].any(axis=1))
+    assert len(set(dec.tolist())) == 3, "the full-size instance exercises delete, replace and no-op"
     rng = np.random.default_rng(7)
-    pick = np.sort(rng.choice(S, 300, replace=False))
     off, nodes = consol["subset_off"], consol["subset_nodes"]
-    sizes = (off[1:] - off[:-1])[pick]
+    size = off[1:] - off[:-1]
+    pick = [np.nonzero(size == 1)[0]]
+    for k in (0, 1, 2):
+        idx = np.nonzero((dec == k) & (size > 1))[0]
+        pick.append(rng.choice(idx, min(len(idx), 1800), replace=False))
+    pick = np.unique(np.concatenate(pick))
+    assert len(pick) >= 5000
+    sizes = size[pick]
     smp = dict(consol, n_subsets=len(pick), subset_off=np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32),
                subset_nodes=np.concatenate([nodes[off[i]:off[i + 1]] for i in pick]).astype(np.int32))
-    orc = oracle_lib.consolidate(enc.problem, _abi.ConsolInput(**smp))
+    orc = oracle_lib.consolidate(enc.problem, _abi.ConsolInput(**smp), threads=8)
     for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
         assert np.array_equal(gpu[k][pick], orc[k]), k
+
+
+def test_solve_batch_matches_single_solves(handle):
+    """kp_solve_batch: one CTA per Scheduler instance, instances of different shapes in one launch; every result is
+    bit-identical to the oracle on that problem (and so to kp_solve)."""
+    encs = [workloads.config_c1(n_pods=300), workloads.config_c2(n_pods=4000, n_its=500),
+            workloads.config_c3(n_apps=12, replicas=40, n_its=300), workloads.config_existing(n_nodes=200, n_pods=1500),
+            workloads.config_c2(n_pods=1, n_its=50)]
+    outs = handle.solve_batch([e.problem for e in encs])
+    assert len(outs) == len(encs)
+    for i, (e, o) in enumerate(zip(encs, outs)):
+        assert_same(o, oracle_lib.solve(e.problem), f"batch[{i}] ")
+    # resident variant, twice (state restored between runs), and a single solve on the same handle afterwards
+    handle.upload_batch([e.problem for e in encs[:3]])
+    for _ in range(2):
+        outs = handle.solve_batch_resident()
+        for i, (e, o) in enumerate(zip(encs[:3], outs)):
+            assert_same(o, oracle_lib.solve(e.problem), f"batch resident[{i}] ")
+    assert_same(handle.solve(encs[1].problem), oracle_lib.solve(encs[1].problem), "single after batch ")
+    assert handle.solve_batch([]) == []
+
+
+def test_solve_batch_more_instances_than_sms(handle):
+    """200 instances > 148 SMs: the launch runs in waves; results are per-instance exact."""
+    encs = [workloads.config_c1(n_pods=20 + 3 * i) for i in range(200)]
+    outs = handle.solve_batch([e.problem for e in encs])
+    for i in (0, 57, 148, 199):
+        assert_same(outs[i], oracle_lib.solve(encs[i].problem), f"wave batch[{i}] ")
+
+
+def test_c5_pool_shards_as_one_batch(handle):
+    """BASELINE configs[4] shape, scaled down: 8 NodePools, C2 + C3 constraint mix, pods pinned to their pool.  The 8
+    pool shards solved as ONE batch on one GPU equal the 8 oracle solves of the shards."""
+    n_pods, pools = 24000, 8
+    shards = [workloads.config_c5(n_pods=n_pods, n_pools=pools, n_its=300, app_replicas=100, pools_subset=[r])
+              for r in range(pools)]
+    outs = handle.solve_batch([e.problem for e in shards])
+    for r, (e, o) in enumerate(zip(shards, outs)):
+        assert_same(o, oracle_lib.solve(e.problem), f"C5 shard {r} ")
+        assert o["n_domain_slots"] > 0  # the counter table a multi-GPU run all-reduces is not empty
 
 
 def test_shared_to_global_migration(monkeypatch):
