@@ -313,6 +313,69 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
     // domain choice) -- if not, an undefined key fails the strict Compatible of existingnode.go:89 forever
     bool nodes_gain_keys = false;
     for (int g = 0; g < t.G; g++) nodes_gain_keys = nodes_gain_keys || t.groups[g].key != t.hostname_key;
+    // ---- the domain fast path (kp_kernels.cuh domain_mask): topology key = the non-hostname key most groups sit on
+    std::vector<int32_t> tkinfo(std::max(t.X, 1), 0xff);
+    {
+      std::vector<int> per_key(std::max(t.K, 1), 0);
+      for (int g = 0; g < t.G; g++)
+        if (t.groups[g].key != t.hostname_key && t.groups[g].key >= 0) per_key[t.groups[g].key]++;
+      d.tk_key = -1;
+      for (int k = 0; k < t.K; k++)
+        if (per_key[k] > 0 && (d.tk_key < 0 || per_key[k] > per_key[d.tk_key])) d.tk_key = k;
+      bool lazy = false;
+      for (int32_t b : t.g_born) lazy = lazy || b == 0;
+      const bool fp_global = !t.has_bounds && !lazy && !t.min_values_strict && !getenv("KP_NO_DOMAIN_FP");
+      // set inclusion of requirement slots without bounds: values(a) within values(b)
+      auto slot_subset = [&](int rs_a, int rs_b, int k) {
+        const size_t ia = (size_t)rs_a * t.K + k, ib = (size_t)rs_b * t.K + k;
+        const bool ac = t.rs_flags[ia] & SF_COMPLEMENT, bc = t.rs_flags[ib] & SF_COMPLEMENT;
+        const uint64_t am = t.rs_mask[ia], bm = t.rs_mask[ib];
+        if (!ac && !bc) return (am & ~bm) == 0;
+        if (!ac && bc) return (am & bm) == 0;
+        if (ac && bc) return (bm & ~am) == 0;
+        return false;
+      };
+      // TopologyNodeFilter.Matches (topologynodefilter.go:68-97) holds for every claim whose requirements the class's
+      // own requirement set leaves unchanged: some alternative is empty, or constrains only keys the class constrains
+      // at least as tightly
+      auto filter_implied = [&](int x, const KpGroup& G) {
+        for (int a = 0; a < G.filter_n; a++) {
+          const int rs = t.filter_rs[G.filter_off + a];
+          bool ok = true;
+          for (int k = 0; k < t.K && ok; k++) {
+            if (!(t.rs_flags[(size_t)rs * t.K + k] & SF_PRESENT)) continue;
+            ok = (t.rs_flags[(size_t)t.cls_rs[x] * t.K + k] & SF_PRESENT) && slot_subset(t.cls_rs[x], rs, k);
+          }
+          if (ok) return true;
+        }
+        return false;
+      };
+      std::map<int, int> asigs;
+      for (int x = 0; x < t.X; x++) {
+        auto it = asigs.find(t.cls_rs[x]);
+        if (it == asigs.end()) it = asigs.emplace(t.cls_rs[x], (int)asigs.size()).first;
+        int info = it->second < 64 ? it->second : 0xff;
+        const int nm = t.cls_match_off[x + 1] - t.cls_match_off[x], nr = t.cls_rec_off[x + 1] - t.cls_rec_off[x];
+        bool fp = fp_global && nm + nr > 0 && nm <= KP_PG && nr <= KP_PG, has_tk = false;
+        for (int i = t.cls_match_off[x]; i < t.cls_match_off[x + 1] && fp; i++) {
+          const KpGroup& G = t.groups[t.cls_match[i] & 0x3fffffff];
+          if (G.key == d.tk_key)
+            has_tk = true;
+          else if (G.key != t.hostname_key)
+            fp = false;
+        }
+        for (int i = t.cls_rec_off[x]; i < t.cls_rec_off[x + 1] && fp; i++) {
+          const KpGroup& G = t.groups[t.cls_rec[i]];
+          if (G.key == d.tk_key)
+            has_tk = true;
+          else if (G.key != t.hostname_key)
+            fp = false;
+          if (fp && !G.inverse && G.affinity_policy == 1 && G.filter_n > 0 && !filter_implied(x, G)) fp = false;
+        }
+        if (fp) info |= TKI_FP | (has_tk ? TKI_TK : 0);
+        tkinfo[x] = info;
+      }
+    }
     for (int x = 0; x < t.X; x++) {
       int32_t* hh = &hdr[(size_t)x * KP_HDR];
       hh[0] = t.cls_tolset[x];
@@ -416,6 +479,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
           if (l == KP_HDR + 2) c.hdr = (int32_t)(tok[x] & 0xffffffffull);
           if (l == KP_HDR + 3) c.hdr = (int32_t)(tok[x] >> 32);
           if (l == KP_HDR + 4) c.hdr = t.cls_relax[x];
+          if (l == KP_HDR + 5) c.hdr = tkinfo[x];
         }
       CK(up(h, &d.cls_lane, rows));
     }
@@ -462,6 +526,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(zeros(h, &d.cnt_at, C));
   CK(zeros(h, &d.cmask, C));
   CK(zeros(h, &d.amask, C));
+  CK(zeros(h, &d.c_dom, C));
   d.tmpl_all = t.N >= 64 ? ~0ull : ((1ull << t.N) - 1);
   d.H = t.E + d.Cmax;
   CK(zeros(h, &d.host_cnt, (size_t)std::max(t.GH, 1) * d.H));
@@ -674,7 +739,7 @@ static int prep_solve(kp_handle* h) {
   if (getenv("KP_CS_LIMIT")) CR = std::min(CR, 32);
   tb += CR ? row_bytes(CR) : 0;  // from here on `tb` is everything in front of the small arrays
   // ... and claim order / failure masks of the first CS claims
-  auto small_bytes = [&](int cs) { return (size_t)cs * 36; };  // cmask 16 B + amask 8 B + order, count, template id
+  auto small_bytes = [&](int cs) { return (size_t)cs * 37; };  // cmask 16 B + amask 8 B + order, count, template id, c_dom
   int CS = 0;
   if (fixed + tb + small_bytes(64) + 64 <= budget) {  // the largest multiple of 32 that fits, capped at Cmax
     int lo = 64, hi = ((d.Cmax + 31) / 32) * 32;
@@ -729,8 +794,8 @@ static int download(kp_handle* h, kp_result* out) {
   CK(cudaMemcpy(&nclaims, d.n_claims, 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(counters, d.counters, 128, cudaMemcpyDeviceToHost));
   if (getenv("KP_DEBUG"))
-    fprintf(stderr, "[kp] slow_sorts=%lld scan_chunks=%lld evals=%lld commits=%lld\n", (long long)counters[4],
-            (long long)counters[5], (long long)counters[6], (long long)counters[3]);
+    fprintf(stderr, "[kp] slow_sorts=%lld evals=%lld commits=%lld fast_commits=%lld\n", (long long)counters[4],
+            (long long)counters[6], (long long)counters[3], (long long)counters[9]);
   int64_t P = h->cur->P;
   int K = h->cur->n_keys, R = h->cur->n_resources, ITW = (h->cur->n_its + 63) / 64;
   size_t C = (size_t)nclaims, c1 = C ? C : 1;

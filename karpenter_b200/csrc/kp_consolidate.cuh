@@ -203,6 +203,8 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     I.g_c_tmpl = d.c_tmpl;
     I.g_cmask = d.cmask;
     I.g_amask = d.amask;
+    I.c_dom = d.c_dom;
+    I.g_c_dom = d.c_dom;
     I.CR = 0;
     unsigned char* p = tab + d_in.tab_bytes;
     if (CR > 0) {  // rows of the first CR claims
@@ -228,6 +230,8 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
       I.cnt_at = reinterpret_cast<int32_t*>(p);
       p += (size_t)CS * 4;
       I.c_tmpl = reinterpret_cast<int32_t*>(p);
+      p += (size_t)CS * 4;
+      I.c_dom = reinterpret_cast<uint8_t*>(p);
       I.CS = CS;
     }
   }
@@ -258,6 +262,7 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     d.counters[6] = I.evals;
     d.counters[7] = I.n_unsched;
     d.counters[8] = I.n_uninit;
+    d.counters[9] = I.fast_commits;
   }
 }
 __global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS, int CR) {
@@ -613,6 +618,8 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolid
     I.nstat_sum = d.nstat_sum;
     I.CS = 0;
     I.CR = 0;
+    I.c_dom = nullptr;  // candidate sets with topology take the batch path (k_wsolve_batch)
+    I.g_c_dom = nullptr;
     I.ov_cap = capq;
     I.ov_node = q.ov_node + slot * capq;
     I.ov_rem = q.ov_rem + slot * capq * R;

@@ -199,26 +199,59 @@ struct Eval {
   bool res_dead;   // no remaining instance type can ever hold these requests again (monotone)
   bool changed;    // the pod tightened at least one requirement slot of the candidate
   bool compat_fail;  // rejected by Requirements.Compatible(pod requirements) alone: independent of requests
+  bool pod_noop;   // Compatible passed and the pod's own requirements left every slot of the candidate as it was
   int j;           // lane r: threshold row of the total requests (fits_word)
   Slot F;          // lane k: final requirement slot of key k
   int64_t q;       // lane r: total requests (claims)
   uint64_t its;    // lane w: surviving instance-type word (claims)
 };
 
-// The pod being placed, staged once per pod in shared memory (class row of the problem + its requirement slots).
+// The pod being placed, staged once per pod in shared memory (class row of the problem + its requirement slots + the
+// descriptors of the topology groups that constrain / count it, so the solver's chain never goes to HBM for them).
+#define KP_PG 6              // groups per list staged with the pod; a class with more reads them from HBM
+#define TKI_FP 0x100         // tkinfo: the class may take the domain fast path (see wsolve_run)
+#define TKI_TK 0x200         // ... and has at least one group on the topology key
+#define TKI_ASIG(t) ((t) & 0xff)  // requirement-set id for the "adds nothing" masks (amask), 0xff: none
 struct PodCtx {
   union {
     struct {
       int tolset, rv, moff, mend, roff, rend, fsig, nsig, hoff, hend, cls, pod;
       unsigned long long tmpl_ok;  // bit n: template n's taints are tolerated (taints.go:49-66)
       int relax;                   // class after one Preferences.Relax step, -1: nothing left to relax
+      int tkinfo;                  // TKI_*
     };
-    int hdr[KP_HDR + 5];  // the class header, then class id, pod id, tmpl_ok (lo, hi), relax
+    int hdr[KP_HDR + 6];  // the class header, then class id, pod id, tmpl_ok (lo, hi), relax, tkinfo
   };
   int64_t req[KP_MAXR];
   Slot pod_slot[KP_MAXK];
   Slot strict_slot[KP_MAXK];
+  int n_mg, n_rg;      // staged entries of cls_match / cls_rec, -1: not staged (more than KP_PG)
+  int m_e[KP_PG];      // cls_match entries (group | self << 30)
+  int r_g[KP_PG];      // cls_rec entries
+  KpGroup mg[KP_PG];
+  KpGroup rg[KP_PG];
+  int n_hc;            // hostname-group checks among the staged match groups (the scan's per-candidate tests)
+  int4 hc[KP_PG];      // {host_row, type | self << 8, max_skew, group}
 };
+// entry i of the pod's match / record list
+__device__ __forceinline__ void pod_match(const KpDev& d, const PodCtx& px, int i, int* e, KpGroup* G) {
+  if (px.n_mg >= 0) {
+    *e = px.m_e[i];
+    *G = px.mg[i];
+  } else {
+    *e = d.cls_match[px.moff + i];
+    *G = d.groups[*e & 0x3fffffff];
+  }
+}
+__device__ __forceinline__ void pod_rec(const KpDev& d, const PodCtx& px, int i, int* g, KpGroup* G) {
+  if (px.n_rg >= 0) {
+    *g = px.r_g[i];
+    *G = px.rg[i];
+  } else {
+    *g = d.cls_rec[px.roff + i];
+    *G = d.groups[*g];
+  }
+}
 
 // Exact CanAdd of the staged pod on one candidate (NodeClaim.CanAdd nodeclaim.go:114-202 when is_claim, else
 // ExistingNode.CanAdd existingnode.go:70-143 after the taint / Fits checks of phase 1).
@@ -233,6 +266,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   ev.res_dead = false;
   ev.changed = false;
   ev.compat_fail = false;
+  ev.pod_noop = false;
   ev.j = 0;
   const int K = d.K;
   const bool allow_undef = is_claim;  // ExistingNode.CanAdd passes no compatibility options
@@ -248,16 +282,18 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   }
   Slot M = lane < K ? (nb ? slot_add_nb(base, pod) : slot_add(ki, base, pod)) : slot_absent();
   // Topology.AddRequirements (topology.go:226-248)
-  const int moff = px.moff, mend = px.mend;
-  if (mend > moff) {
+  const int nm = px.mend - px.moff;
+  if (nm > 0) {
+    ev.pod_noop = !__any_sync(FULL, lane < K && !slot_eq(M, base));
     Slot Tt = M;
     bool fail = false;
     Slot strict = lane < K ? px.strict_slot[lane] : slot_absent();
-    for (int i = moff; i < mend; i++) {
-      int e = d.cls_match[i];
+    for (int i = 0; i < nm; i++) {
+      int e;
+      KpGroup G;
+      pod_match(d, px, i, &e, &G);
       int g = e & 0x3fffffff;
       bool self = (e >> 30) & 1;
-      KpGroup G = d.groups[g];
       if (G.key == d.hostname_key) {
         if (lane == 0) {  // candidates carry exactly one hostname: the fast paths of topologygroup.go:235-247,317-333,402-408
           int cnt = d.host_cnt[(size_t)G.host_row * d.H + host];
@@ -286,6 +322,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   ev.F = M;
   if (!is_claim) {
     ev.changed = __any_sync(FULL, lane < K && !slot_eq(M, base));
+    if (nm <= 0) ev.pod_noop = !ev.changed;
     ev.ok = true;
     return ev;
   }
@@ -295,6 +332,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   // resource test can remove instance types.
   const bool changed = __any_sync(FULL, lane < K && !slot_eq(M, base));
   ev.changed = changed;
+  if (nm <= 0) ev.pod_noop = !changed;
   int64_t q = base_q + (lane < d.R ? px.req[lane] : 0);
   ev.j = base_j;
   uint64_t fw = fits_word(d, q, lane, &ev.j, base_its);
@@ -315,7 +353,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
 // A class row in flight between global memory and the shared PodCtx (one warp; lane k: key k, lane r: resource r,
 // lane i < KP_HDR: header word i).
 struct ClassRegs {
-  int hdr;                // lanes 0..KP_HDR+4: header row, class, pod, tmpl_ok lo / hi, relax
+  int hdr;                // lanes 0..KP_HDR+5: header row, class, pod, tmpl_ok lo / hi, relax, tkinfo
   int64_t req;
   Slot pod, strict;
 };
@@ -340,12 +378,46 @@ __device__ __forceinline__ ClassRegs load_class_regs(const KpDev& d, int X, int 
   return c;
 }
 __device__ __forceinline__ void store_class_regs(const KpDev& d, PodCtx& px, const ClassRegs& c, int lane) {
-  if (lane < KP_HDR + 5) px.hdr[lane] = c.hdr;
+  if (lane < KP_HDR + 6) px.hdr[lane] = c.hdr;
   if (lane < d.R) px.req[lane] = c.req;
   if (lane < d.K) {
     px.pod_slot[lane] = c.pod;
     px.strict_slot[lane] = c.strict;
   }
+  // the groups that constrain / count the class, parked next to the row (whole warp; lanes 0..11 move one descriptor)
+  const int moff = __shfl_sync(FULL, c.hdr, 2), mend = __shfl_sync(FULL, c.hdr, 3);
+  const int roff = __shfl_sync(FULL, c.hdr, 4), rend = __shfl_sync(FULL, c.hdr, 5);
+  const int nm = mend - moff, nr = rend - roff;
+  const bool sm = nm <= KP_PG, sr = nr <= KP_PG;
+  int e = 0, g = 0;
+  if (sm && lane < nm) e = d.cls_match[moff + lane];
+  if (sr && lane < nr) g = d.cls_rec[roff + lane];
+  if (lane == 0) {
+    px.n_mg = sm ? nm : -1;
+    px.n_rg = sr ? nr : -1;
+  }
+  if (sm && lane < nm) px.m_e[lane] = e;
+  if (sr && lane < nr) px.r_g[lane] = g;
+  if (sm)
+    for (int i = 0; i < nm; i++) {
+      const int gi = __shfl_sync(FULL, e, i) & 0x3fffffff;
+      if (lane < (int)(sizeof(KpGroup) / 4)) reinterpret_cast<int*>(&px.mg[i])[lane] = reinterpret_cast<const int*>(&d.groups[gi])[lane];
+    }
+  if (sr)
+    for (int i = 0; i < nr; i++) {
+      const int gi = __shfl_sync(FULL, g, i);
+      if (lane < (int)(sizeof(KpGroup) / 4)) reinterpret_cast<int*>(&px.rg[i])[lane] = reinterpret_cast<const int*>(&d.groups[gi])[lane];
+    }
+  __syncwarp();
+  bool is_host = false;
+  KpGroup G;
+  if (sm && lane < nm) {
+    G = px.mg[lane];
+    is_host = G.key == d.hostname_key;
+  }
+  const unsigned hm = __ballot_sync(FULL, is_host);
+  if (is_host) px.hc[__popc(hm & ((1u << lane) - 1))] = make_int4(G.host_row, G.type | (((e >> 30) & 1) << 8), G.max_skew, e & 0x3fffffff);
+  if (lane == 0) px.n_hc = sm ? __popc(hm) : -1;
 }
 
 // Topology.Record (topology.go:197-220) for the committed placement; executed by one warp.
@@ -353,9 +425,11 @@ __device__ __forceinline__ void topo_record(const KpDev& d, const PodCtx& px, co
                                             bool allow_undef, int lane) {
   const int K = d.K;
   (void)allow_undef;  // TopologyNodeFilter.Matches never forwards the options (topologynodefilter.go:68-85)
-  for (int i = px.roff; i < px.rend; i++) {
-    int g = d.cls_rec[i];
-    KpGroup G = d.groups[g];
+  const int nr = px.rend - px.roff;
+  for (int i = 0; i < nr; i++) {
+    int g;
+    KpGroup G;
+    pod_rec(d, px, i, &g, &G);
     if (d.n_lazy && !d.g_born[g]) continue;  // the reference has not created this group yet
     bool counts = true;
     if (!G.inverse) {
@@ -403,6 +477,86 @@ __device__ __forceinline__ void topo_record(const KpDev& d, const PodCtx& px, co
       }
     }
   }
+}
+
+// ---- the domain fast path (classes flagged TKI_FP, see upload_tables in kp_api.cu) -------------------------------
+// Every topology group of such a class sits on the hostname key or on ONE other key, the problem's "topology key" TK
+// (zone in practice).  A NodeClaim that already holds a pod is pinned to a single TK value z (its slot is In{z}); for
+// such a claim TopologyGroup.Get (topologygroup.go:226-428) answers either In{z} -- the claim's requirements stay as
+// they are -- or nothing, and which of the two depends only on z and the group's counters.  So the verdict for ALL
+// single-valued claims is one bit mask over TK's values, computed once per pod:
+//   spread         z registered and count(z) + self - min <= maxSkew          (nextDomainTopologySpread :226-287)
+//   anti-affinity  z registered, empty, allowed by the pod                      (nextDomainAntiAffinity :393-428)
+//   affinity       z registered, populated, allowed by the pod; when the bootstrap rule of :356-374 could fire the
+//                  mask cannot tell (*exact = false: no pruning, the full evaluation decides)
+// Returns the AND over the pod's TK groups (all ones when it has none).  Warp-uniform.
+__device__ __forceinline__ uint64_t domain_mask(const KpDev& d, const PodCtx& px, int lane, bool* exact) {
+  uint64_t ez = ~0ull;
+  *exact = true;
+  const int nm = px.n_mg;
+  const Slot strict = px.strict_slot[d.tk_key];
+  const uint64_t univ = d.key_univ[d.tk_key];
+  const uint64_t pod_allowed = (strict.f & SF_PRESENT) ? (((strict.f & SF_COMPLEMENT) ? ~strict.m : strict.m) & univ) : univ;
+  for (int i = 0; i < nm; i++) {
+    const KpGroup G = px.mg[i];
+    if (G.key != d.tk_key) continue;
+    const int e = px.m_e[i], g = e & 0x3fffffff;
+    const bool self = (e >> 30) & 1;
+    const uint64_t reg = d.dom_reg[g], pop = d.dom_pop[g];
+    if (G.type == KP_TOPO_SPREAD) {
+      // lane v (and v + 32) reads the counter of value v; min over the domains the pod may use (domainMinCount :289-310)
+      const int32_t* cnt = d.dom_cnt + G.dom_off;
+      const long long c0 = (reg >> lane) & 1ull ? (long long)cnt[lane] : 0, c1 = (reg >> (lane + 32)) & 1ull ? (long long)cnt[lane + 32] : 0;
+      const uint64_t sup = reg & pod_allowed;
+      long long mn = 2147483647LL;
+      if ((sup >> lane) & 1ull) mn = c0;
+      if (((sup >> (lane + 32)) & 1ull) && c1 < mn) mn = c1;
+      for (int o = 16; o; o >>= 1) {
+        const long long other = __shfl_xor_sync(FULL, mn, o);
+        if (other < mn) mn = other;
+      }
+      if (G.min_domains >= 0 && __popcll(sup) < G.min_domains) mn = 0;
+      const long long add = self ? 1 : 0;
+      const bool ok0 = ((reg >> lane) & 1ull) && c0 + add - mn <= (long long)G.max_skew;
+      const bool ok1 = ((reg >> (lane + 32)) & 1ull) && c1 + add - mn <= (long long)G.max_skew;
+      const uint64_t m = (uint64_t)__ballot_sync(FULL, ok0) | ((uint64_t)__ballot_sync(FULL, ok1) << 32);
+      ez &= m;
+    } else if (G.type == KP_TOPO_ANTI_AFFINITY) {
+      ez &= reg & ~pop & pod_allowed;
+    } else {
+      const bool none_populated = (reg & pop) == 0, any_compat = (reg & pop & pod_allowed) != 0;
+      if (self && (none_populated || !any_compat))
+        *exact = false;
+      else
+        ez &= reg & pop & pod_allowed;
+    }
+  }
+  return ez;
+}
+
+// Topology.Record (topology.go:197-220) of a fast-path placement: the claim's requirements are unchanged and its TK
+// slot is In{z} (z < 0: the class has no TK group).  The class's record groups are staged and none needs the node
+// filter's requirement check (TKI_FP), so every group is one independent read-modify-write: lane i takes group i.
+__device__ __forceinline__ void topo_record_fast(const KpDev& d, const PodCtx& px, int z, int taintset, int host, int lane) {
+  if (lane < px.n_rg) {
+    const KpGroup G = px.rg[lane];
+    const int g = px.r_g[lane];
+    bool counts = true;
+    if (!G.inverse && G.taint_policy == 1) counts = tolerated(d, G.tolset, taintset);
+    if (counts) {
+      if (G.key == d.hostname_key) {
+        int32_t* c = d.host_cnt + (size_t)G.host_row * d.H + host;
+        const int32_t v = *c;
+        if (v == 0) d.g_nempty[g]--;
+        *c = v + 1;
+      } else if (z >= 0) {
+        d.dom_cnt[G.dom_off + z]++;
+        d.dom_reg[g] |= 1ull << z;
+        d.dom_pop[g] |= 1ull << z;
+      }
+    }
+  }
+  __syncwarp();
 }
 
 // InstanceTypes.SatisfiesMinValues (cloudprovider/types.go:301-337) for a NodeClaim of template n whose remaining

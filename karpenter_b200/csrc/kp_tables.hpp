@@ -38,7 +38,7 @@ struct Slot {
 };
 
 // One lane's share of a class row: lane k carries the class's requirement slots on key k, lane r its request for
-// resource r, lane i < KP_HDR header word i (lanes KP_HDR+2, +3: the tolerated-template mask, KP_HDR+4: cls_relax).  32 bytes, so staging a
+// resource r, lane i < KP_HDR header word i (lanes KP_HDR+2, +3: the tolerated-template mask, KP_HDR+4: cls_relax, KP_HDR+5: tkinfo).  32 bytes, so staging a
 // pod is two 16-byte loads per lane.
 struct ClsLane {
   uint64_t pod_m, strict_m;
@@ -200,5 +200,9 @@ struct KpDev {
   int64_t* counters;              // [8] existing evals, inflight evals, template evals, commits, slow sorts, ...
   int32_t* status;                // [1] 0 ok, 4 capacity
   int stable_order;
+  // the domain fast path (kp_kernels.cuh domain_mask): the one non-hostname key topology groups of fast-path classes
+  // use (-1: none), and per claim the value its slot on that key is pinned to (0xff: not a single In value)
+  int tk_key;
+  uint8_t* c_dom;                 // [Cmax]
   long long deadline_ns;          // 0 = none; the solve stops with KP_DEADLINE once this much device time has passed
 };

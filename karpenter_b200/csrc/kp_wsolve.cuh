@@ -54,6 +54,9 @@ struct WInst {
   // resource test.
   unsigned long long* amask;
   unsigned long long* g_amask;
+  // c_dom[c]: the value claim c's slot on the topology key is pinned to, 0xff when it is not a single In value (null: the
+  // instance does not use the domain fast path)
+  uint8_t *c_dom, *g_c_dom;
   // While the claim order, template ids and failure masks fit, they live in shared memory (CS = claims the shared
   // copies can hold, 0 = not in use); the moment a claim id reaches CS everything migrates to the global arrays below.
   int CS;
@@ -82,7 +85,7 @@ struct WInst {
   int64_t *ov_sgte, *ov_slte;
   // results
   int n_claims, n_unsched, n_uninit, status;
-  long long ev_existing, ev_inflight, ev_tmpl, commits, slow_sorts, scan_chunks, evals;
+  long long ev_existing, ev_inflight, ev_tmpl, commits, slow_sorts, scan_chunks, evals, fast_commits;
 };
 
 // index of `node` in the overlay, -1 if it is untouched (warp-uniform result)
@@ -131,6 +134,8 @@ __device__ __forceinline__ void claim_load(const KpDev& d, const WInst& I, int c
 }
 __device__ __forceinline__ void claim_store(const KpDev& d, WInst& I, int c, int lane, const Eval& ev, bool slots) {
   const int K = d.K, R = d.R, ITW = d.ITW;
+  if (slots && I.c_dom && lane == d.tk_key)
+    I.c_dom[c] = (ev.F.f == SF_PRESENT && __popcll(ev.F.m) == 1) ? (uint8_t)(__ffsll((long long)ev.F.m) - 1) : (uint8_t)0xff;
   if (c < I.CR) {
     if (slots && lane < K) {
       I.s_sflags[c * K + lane] = (uint8_t)ev.F.f;
@@ -212,6 +217,9 @@ struct ScanCtx {
   bool all_tmpl;
   int hoff, hend;                      // hostname-group checks of the class
   int first_clear, first_rclear;       // first position (>= the scan start) whose signature / request-vector bit is clear
+  bool use_ez;                         // prune claims pinned to a topology-key value outside `ez` (domain_mask)
+  uint64_t ez;
+  const int4* hc;                      // the hostname checks: staged with the pod, or cls_hchk + hoff
 };
 // U sub-chunks of 32 positions per step: their loads are independent, so a step costs one memory latency, not U.
 template <int U>
@@ -235,22 +243,41 @@ __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, co
         if (pass[u] && !sc.all_tmpl) pass[u] = (sc.tok >> I.c_tmpl[c[u]]) & 1ull;
       }
     }
-    // hostname groups: a NodeClaim is exactly one hostname domain (topologygroup.go:235-247,317-333,402-408)
-    for (int i = sc.hoff; i < sc.hend; i++) {
-      const int4 hc = d.cls_hchk[i];
-      const int type = hc.y & 0xff, self = hc.y >> 8;
-      int hcnt[U];
+    if (sc.use_ez) {
 #pragma unroll
-      for (int u = 0; u < U; u++) hcnt[u] = pass[u] ? d.host_cnt[(size_t)hc.x * d.H + E + c[u]] : 0;
+      for (int u = 0; u < U; u++)
+        if (pass[u]) {
+          const int z = I.c_dom[c[u]];
+          if (z != 0xff) pass[u] = (sc.ez >> z) & 1ull;
+        }
+    }
+    // hostname groups: a NodeClaim is exactly one hostname domain (topologygroup.go:235-247,317-333,402-408).  Two
+    // groups per round, so that all their counter loads are in flight together (one L2 latency, not one per group).
+    for (int i = sc.hoff; i < sc.hend; i += 2) {
+      const bool two = i + 1 < sc.hend;
+      const int4 ha = sc.hc[i], hb = two ? sc.hc[i + 1] : ha;
+      int ca[U], cb[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        if (!pass[u]) continue;
-        if (type == KP_TOPO_SPREAD)
-          pass[u] = hcnt[u] + self <= hc.z;
-        else if (type == KP_TOPO_AFFINITY)
-          pass[u] = hcnt[u] > 0 || (self && (d.g_ndomains[hc.w] - d.g_nempty[hc.w]) == 0);
-        else
-          pass[u] = hcnt[u] == 0;
+        ca[u] = pass[u] ? d.host_cnt[(size_t)ha.x * d.H + E + c[u]] : 0;
+        cb[u] = (two && pass[u]) ? d.host_cnt[(size_t)hb.x * d.H + E + c[u]] : 0;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        if (r == 1 && !two) break;
+        const int4 hc = r == 0 ? ha : hb;
+        const int type = hc.y & 0xff, self = hc.y >> 8;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (!pass[u]) continue;
+          const int hcnt = r == 0 ? ca[u] : cb[u];
+          if (type == KP_TOPO_SPREAD)
+            pass[u] = hcnt + self <= hc.z;
+          else if (type == KP_TOPO_AFFINITY)
+            pass[u] = hcnt > 0 || (self && (d.g_ndomains[hc.w] - d.g_nempty[hc.w]) == 0);
+          else
+            pass[u] = hcnt == 0;
+        }
       }
     }
 #pragma unroll
@@ -282,6 +309,7 @@ __device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, 
     I.g_c_tmpl[i] = I.c_tmpl[i];
     I.g_cmask[i] = I.cmask[i];
     I.g_amask[i] = I.amask[i];
+    if (I.c_dom) I.g_c_dom[i] = I.c_dom[i];
   }
   __syncwarp();
   if (lane == 0) {
@@ -290,6 +318,7 @@ __device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, 
     I.c_tmpl = I.g_c_tmpl;
     I.cmask = I.g_cmask;
     I.amask = I.g_amask;
+    if (I.c_dom) I.c_dom = I.g_c_dom;
     I.CS = 0;
   }
   __syncwarp();
@@ -339,7 +368,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
   const long long watchdog_limit = 4ll * P + 1024;
   int nC = 0;
   int pert = PERT_NONE, pert_pos = 0;
-  long long ev_existing = 0, ev_inflight = 0, ev_tmpl = 0, commits = 0, slow_sorts = 0, scan_chunks = 0, evals = 0;
+  long long ev_existing = 0, ev_inflight = 0, ev_tmpl = 0, commits = 0, slow_sorts = 0, scan_chunks = 0, evals = 0, fast_commits = 0;
   int n_unsched = 0, n_uninit = 0, status = KP_OK, n_born = 0;
   int32_t* ord = I.order;
   int32_t* cnt = I.cnt_at;
@@ -669,12 +698,34 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       sc.rbit = rbit;
       sc.tok = px.tmpl_ok;
       sc.all_tmpl = (sc.tok & d.tmpl_all) == d.tmpl_all;
-      sc.hoff = px.hoff;
-      sc.hend = px.hend;
+      if (px.n_hc >= 0) {  // hostname checks staged with the pod
+        sc.hc = px.hc;
+        sc.hoff = 0;
+        sc.hend = px.n_hc;
+      } else {
+        sc.hc = d.cls_hchk;
+        sc.hoff = px.hoff;
+        sc.hend = px.hend;
+      }
       sc.first_clear = -1;
       sc.first_rclear = -1;
+      sc.use_ez = false;
+      sc.ez = ~0ull;
+      const int tki = px.tkinfo, asig = TKI_ASIG(tki);
+      // bit of the pod's requirement set in the claims' "adds nothing" masks
+      const unsigned long long abit = asig < 64 ? 1ull << asig : 0ull;
       // topology-free and counted by no topology group (and no minValues to re-check on the shrinking type list)
-      const bool fast_ok = fbit != 0 && px.roff == px.rend && !d.mv_strict;
+      const bool fast_ok = fsig >= 0 && abit != 0 && px.roff == px.rend && !d.mv_strict;
+      // the domain fast path: topology on the hostname key and / or the topology key only (kp_kernels.cuh domain_mask)
+      bool dom_fp = (tki & TKI_FP) && I.c_dom != nullptr;
+      const bool has_tk = tki & TKI_TK;
+      if (dom_fp && has_tk) {
+        bool exact;
+        sc.ez = domain_mask(d, px, lane, &exact);
+        sc.use_ez = exact;
+        dom_fp = exact;
+      }
+      dom_fp = dom_fp && abit != 0;
       int lbf = 0, lbr = 0;
       if (fbit) lbf = __shfl_sync(FULL, fsig < 32 ? lb0 : lb1, fsig & 31);
       if (rbit) lbr = __shfl_sync(FULL, rv < 32 ? lr0 : lr1, rv & 31);
@@ -689,9 +740,19 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         if (cpos < 0) break;
         from = cpos + 1;
         {
-          if (fast_ok && (I.amask[cc] & fbit)) {
-            // ---- the pod's requirements are already implied by the claim's: CanAdd == "do the merged requests still
-            // fit a remaining instance type", and the stored list only changes when a threshold row advances
+          int zdom = -1;  // fast-path candidates of a class with topology-key groups: the claim's pinned value
+          bool fp = false;
+          if ((fast_ok || dom_fp) && (I.amask[cc] & abit)) {
+            fp = true;
+            if (!fast_ok && has_tk) {
+              zdom = I.c_dom[cc];
+              fp = zdom != 0xff;  // (the scan already tested the value against the domain mask)
+            }
+          }
+          if (fp) {
+            // ---- the pod's requirements are already implied by the claim's (and, for a fast-path topology class, the
+            // domain choice is the value the claim is pinned to): CanAdd == "do the merged requests still fit a
+            // remaining instance type", and the stored list only changes when a threshold row advances
             int64_t q;
             int j;
             claim_load_rq(d, I, cc, lane, &q, &j);
@@ -732,6 +793,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
                 I.pod_error[li] = KP_PODERR_NONE;
               }
             }
+            if (!fast_ok) topo_record_fast(d, px, zdom, d.tmpl_taintset[I.c_tmpl[cc]], E + cc, lane);
+            fast_commits++;
             __syncwarp();
             pert = PERT_INC;
             pert_pos = cpos;
@@ -748,7 +811,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           Eval ev = eval_candidate(d, px, true, b, bq, bi, bj, E + cc, scratch, lane);
           // Strict minValues (nodeclaim.go:464-475): the surviving types must still span enough distinct values
           if (d.mv_strict && ev.ok && !min_values_ok(d, I.c_tmpl[cc], ev.its, lane)) ev.ok = false;
-          if (fbit && !ev.compat_fail && !ev.changed && lane == 0) I.amask[cc] |= fbit;
+          if (abit && ev.pod_noop && lane == 0) I.amask[cc] |= abit;
           if (!ev.ok) {
             if (lane == 0) {
               ulonglong2 mk = I.cmask[cc];
@@ -857,7 +920,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       // a recycled instance must not inherit failure bits of an earlier claim with this id
       if (lane == 0) {
         I.cmask[cnew] = make_ulonglong2(0ull, 0ull);
-        I.amask[cnew] = (fbit && !ev.changed) ? fbit : 0ull;
+        const int asig_n = TKI_ASIG(px.tkinfo);
+        I.amask[cnew] = (asig_n < 64 && ev.pod_noop) ? 1ull << asig_n : 0ull;
       }
       // subtractMax (scheduler.go:840-857): remaining -= max capacity over the claim's instance types
       if (lp) {
@@ -956,6 +1020,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
     I.slow_sorts = slow_sorts;
     I.scan_chunks = scan_chunks;
     I.evals = evals;
+    I.fast_commits = fast_commits;
   }
   __syncwarp();
 }
