@@ -342,6 +342,30 @@ int kp_solve_batch(kp_handle* h, const kp_problem* const* problems, int32_t n, i
 int kp_upload_batch(kp_handle* h, const kp_problem* const* problems, int32_t n);
 int kp_solve_batch_resident(kp_handle* h, int64_t deadline_ms, kp_result* outs);
 
+/* ---- multi-GPU: NodePool-sharded provisioning ---------------------------------------------
+ * One process per GPU, one handle per process; rank r owns the pods, templates and NodeClaims of its NodePools and runs
+ * ordinary solves (kp_solve_resident / kp_solve_batch_resident).  The one exchange of the job is the global
+ * topology-domain counter table -- what the reference keeps in Topology.domainGroups / TopologyGroup.domains
+ * (topology.go:53-58, topologygroup.go:56-73) for the next scheduling round -- and it lives in the library:
+ *   kp_comm_unique_id          ncclGetUniqueId; the caller hands rank 0's id to every rank (any transport)
+ *   kp_comm_init               ncclCommInitRank on the handle's device
+ *   kp_comm_counter_slots      int32 slots an uploaded instance contributes (non-hostname groups x values of their key,
+ *                              the order of kp_result.domain_counts); instance < 0: the kp_upload instance
+ *   kp_comm_set_counter_layout size of the global table and where each instance of this handle starts in it.  From
+ *                              then on every resident solve ends, on the library's stream and inside solve_ms, with
+ *                              scatter (device) + ONE ncclAllReduce(sum, int32) over NVLink.  Without kp_comm_init
+ *                              (single GPU) the table is just the scatter.
+ *   kp_comm_global_counts      device -> host copy of the reduced table
+ * NCCL is bound at run time (dlopen("libnccl.so.2")): the library has no link-time dependency on it. */
+#define KP_COMM_ID_BYTES 128
+int kp_comm_unique_id(uint8_t* id128);
+int kp_comm_init(kp_handle* h, const uint8_t* id128, int32_t rank, int32_t world);
+int64_t kp_comm_counter_slots(kp_handle* h, int32_t instance);
+int kp_comm_set_counter_layout(kp_handle* h, int64_t total_slots, const int64_t* slot_offset, int32_t n_instances);
+int kp_comm_global_counts(kp_handle* h, int32_t* out, int64_t n);
+double kp_comm_last_allreduce_ms(kp_handle* h); /* scatter + all-reduce share of the last solve_ms */
+void kp_comm_destroy(kp_handle* h);
+
 int kp_consolidate(kp_handle* h, const kp_problem* cluster, const kp_consol_input* in, int64_t deadline_ms,
                    kp_consol_result* out);
 void kp_consol_result_free(kp_consol_result* r);

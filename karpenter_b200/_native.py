@@ -50,6 +50,15 @@ def lib():
         L.kp_solve_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
         L.kp_upload_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.kp_solve_batch_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.kp_comm_unique_id.argtypes = [C.c_void_p]
+        L.kp_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        L.kp_comm_counter_slots.argtypes = [C.c_void_p, C.c_int32]
+        L.kp_comm_counter_slots.restype = C.c_int64
+        L.kp_comm_set_counter_layout.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
+        L.kp_comm_global_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.kp_comm_last_allreduce_ms.argtypes = [C.c_void_p]
+        L.kp_comm_last_allreduce_ms.restype = C.c_double
+        L.kp_comm_destroy.argtypes = [C.c_void_p]
         L.kp_consolidate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.kp_consol_result_free.argtypes = [C.c_void_p]
         L.kp_feasibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -60,7 +69,9 @@ def lib():
 
 EXPORTS = ["kp_version", "kp_create", "kp_destroy", "kp_last_error", "kp_solve", "kp_result_free", "kp_upload",
            "kp_solve_resident", "kp_consolidate", "kp_consol_result_free", "kp_feasibility", "kp_get_stats",
-           "kp_solve_batch", "kp_upload_batch", "kp_solve_batch_resident"]
+           "kp_solve_batch", "kp_upload_batch", "kp_solve_batch_resident", "kp_comm_unique_id", "kp_comm_init",
+           "kp_comm_counter_slots", "kp_comm_set_counter_layout", "kp_comm_global_counts", "kp_comm_last_allreduce_ms",
+           "kp_comm_destroy"]
 
 
 class Handle:
@@ -101,6 +112,7 @@ class Handle:
 
     def upload(self, problem: _abi.Problem):
         self._n_resources = problem.n_resources
+        self._batch_resources = None
         self._check(lib().kp_upload(self._h, problem.ref()))
 
     def solve_resident(self, deadline_ms: int = 0) -> dict:
@@ -144,6 +156,41 @@ class Handle:
         results = (_abi.kp_result * max(n, 1))()
         rc = lib().kp_solve_batch_resident(self._h, deadline_ms, results)
         return self._batch_out(rc, results[:n], self._batch_resources)
+
+    # ---- multi-GPU (NodePool shards): the global topology-domain counter table, reduced inside the library
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        if lib().kp_comm_unique_id(buf) != 0:
+            raise SolverError(3, "ncclGetUniqueId failed (NCCL not available)")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(lib().kp_comm_init(self._h, buf, rank, world))
+
+    def counter_slots(self, instance: int = -1) -> int:
+        n = lib().kp_comm_counter_slots(self._h, instance)
+        if n < 0:
+            raise SolverError(2, "no such uploaded instance")
+        return int(n)
+
+    def set_counter_layout(self, total_slots: int, offsets):
+        """offsets: start slot of each kp_upload_batch instance (or of the kp_upload instance: one entry, batch=False)."""
+        off = np.ascontiguousarray(offsets, np.int64)
+        n = len(self._batch_resources) if getattr(self, "_batch_resources", None) is not None else 0
+        if n and n != len(off):
+            raise ValueError("one offset per uploaded batch instance")
+        self._check(lib().kp_comm_set_counter_layout(self._h, int(total_slots), off.ctypes.data, n))
+        self._gcnt = int(total_slots)
+
+    def global_counts(self) -> np.ndarray:
+        out = np.zeros(self._gcnt, np.int32)
+        self._check(lib().kp_comm_global_counts(self._h, out.ctypes.data, self._gcnt))
+        return out
+
+    def last_allreduce_ms(self) -> float:
+        return float(lib().kp_comm_last_allreduce_ms(self._h))
 
     def consolidate(self, problem: _abi.Problem, consol: _abi.ConsolInput, deadline_ms: int = 0) -> dict:
         r = _abi.kp_consol_result()

@@ -2,6 +2,8 @@
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 
+#include <dlfcn.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -92,6 +94,7 @@ struct Instance {
   };
   std::vector<Reset> resets;
   const int32_t* d_host_cnt_nodes = nullptr;
+  const uint32_t* d_host_pop_nodes = nullptr;
   // NewQueue radix sort buffers
   void *sort_keys_a = nullptr, *sort_keys_b = nullptr, *sort_tmp = nullptr;
   int32_t* sort_perm_b = nullptr;
@@ -99,7 +102,45 @@ struct Instance {
   // shared-memory plan of the solve CTA (plan_solve)
   int CS = 0, CR = 0;
   size_t smem = 0;
+  // global counter table of a sharded job (kp_comm_set_counter_layout): dom_cnt index of each slot this instance owns
+  int32_t* d_slot_src = nullptr;
+  int64_t n_slots = 0, slot_off = 0;
 };
+
+// NCCL is bound at run time (dlopen), so the library loads -- and every single-GPU entry point works -- on a box
+// without it; only kp_comm_init needs it.  Under torch the already-loaded libnccl.so.2 is the one that resolves.
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ struct KpNcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct KpNcclId {
+  char internal[128];
+};
+static NcclApi g_nccl;
+static bool nccl_load(std::string& err) {
+  if (g_nccl.lib) return true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) {
+    err = std::string("NCCL is not available: ") + dlerror();
+    return false;
+  }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, KpNcclId, int))dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    err = "libnccl lacks an expected symbol";
+    return false;
+  }
+  g_nccl.lib = lib;
+  return true;
+}
 
 struct kp_handle {
   int device = 0;
@@ -111,6 +152,13 @@ struct kp_handle {
   Instance* cur = &main;          // the instance the helpers below work on
   KpDev* d_batch_devs = nullptr;  // [batch] device copies of the instances' pointer blocks
   int2* d_batch_plan = nullptr;   // [batch] {CS, CR}
+  // sharded job: NCCL communicator + the global topology-domain counter table (device resident, all-reduced per solve)
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  int32_t* d_gcnt = nullptr;
+  int64_t gcnt_slots = 0;
+  float allreduce_ms = 0;
+  cudaEvent_t ev3 = nullptr;
   kp_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 };
@@ -173,6 +221,12 @@ __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
   if (i < n) p[i] = v;
 }
 
+// slot i of an instance's share of the global counter table <- its dom_cnt entry
+__global__ void k_scatter_counts(const int32_t* dom_cnt, const int32_t* slot_src, int64_t n, int32_t* out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = dom_cnt[slot_src[i]];
+}
+
 static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_consol_input* in, kp_consol_result* out);
 extern "C" {
 static void batch_clear(kp_handle* h);
@@ -196,6 +250,7 @@ int kp_create(int device, kp_handle** out) {
   cudaEventCreate(&h->ev0);
   cudaEventCreate(&h->ev1);
   cudaEventCreate(&h->ev2);
+  cudaEventCreate(&h->ev3);
   cudaDeviceSetLimit(cudaLimitStackSize, 16384);  // pdqsort emulation recurses (log n deep)
   *out = h;
   return KP_OK;
@@ -206,6 +261,8 @@ void kp_destroy(kp_handle* h) {
   cudaSetDevice(h->device);
   h->arena.destroy();
   for (Instance* b : h->batch) delete b;
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->ev3) cudaEventDestroy(h->ev3);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -531,6 +588,16 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   d.H = t.E + d.Cmax;
   CK(zeros(h, &d.host_cnt, (size_t)std::max(t.GH, 1) * d.H));
   CK(up(h, &h->cur->d_host_cnt_nodes, t.host_cnt_nodes));
+  d.HW = (d.H + 31) / 32;
+  CK(zeros(h, &d.host_pop, (size_t)std::max(t.GH, 1) * d.HW));
+  {  // presence bits of the existing nodes: words [0, ceil(E/32)) of every row
+    const int ew = (t.E + 31) / 32;
+    std::vector<uint32_t> bits((size_t)std::max(t.GH, 1) * std::max(ew, 1), 0);
+    for (int r = 0; r < t.GH; r++)
+      for (int n = 0; n < t.E; n++)
+        if (t.host_cnt_nodes[(size_t)r * t.E + n] > 0) bits[(size_t)r * ew + (n >> 5)] |= 1u << (n & 31);
+    CK(up(h, &h->cur->d_host_pop_nodes, bits));
+  }
   CK(zeros(h, &d.n_claims, 1));
   CK(zeros(h, &d.counters, 16));
   CK(zeros(h, &d.status, 1));
@@ -551,6 +618,12 @@ static int reset_dynamic(kp_handle* h) {
   if (t.E && t.GH)  // initial hostname-group counts of the existing nodes: rows of E ints into rows of H ints
     CK(cudaMemcpy2DAsync(d.host_cnt, (size_t)d.H * 4, h->cur->d_host_cnt_nodes, (size_t)t.E * 4, (size_t)t.E * 4, t.GH,
                          cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemsetAsync(d.host_pop, 0, (size_t)std::max(t.GH, 1) * d.HW * 4, h->stream));
+  if (t.E && t.GH) {
+    const size_t ew = (size_t)(t.E + 31) / 32;
+    CK(cudaMemcpy2DAsync(d.host_pop, (size_t)d.HW * 4, h->cur->d_host_pop_nodes, ew * 4, ew * 4, t.GH,
+                         cudaMemcpyDeviceToDevice, h->stream));
+  }
   CK(cudaMemsetAsync(d.n_claims, 0, 4, h->stream));
   CK(cudaMemsetAsync(d.counters, 0, 128, h->stream));
   CK(cudaMemsetAsync(d.status, 0, 4, h->stream));
@@ -564,6 +637,8 @@ static int do_upload(kp_handle* h, const kp_problem* p, int cmax, bool fresh_are
   if (fresh_arena) {
     if (h->cur == &h->main) batch_clear(h);  // the arena is shared: a fresh single upload invalidates every batch instance
     h->main.resident = false;
+    h->d_gcnt = nullptr;  // lived in the arena
+    h->gcnt_slots = 0;
     h->arena.reset();
   }
   h->cur->resets.clear();
@@ -737,12 +812,14 @@ static int prep_solve(kp_handle* h) {
   while (CR > 0 && fixed + tb + row_bytes(CR) > budget / 2) CR -= 32;
   CR = std::max(CR, 0);
   if (getenv("KP_CS_LIMIT")) CR = std::min(CR, 32);
+  if (const char* e = getenv("KP_CR")) CR = std::min(CR, std::max(0, atoi(e)) / 32 * 32);  // experiment knob
   tb += CR ? row_bytes(CR) : 0;  // from here on `tb` is everything in front of the small arrays
   // ... and claim order / failure masks of the first CS claims
   auto small_bytes = [&](int cs) { return (size_t)cs * 37; };  // cmask 16 B + amask 8 B + order, count, template id, c_dom
   int CS = 0;
   if (fixed + tb + small_bytes(64) + 64 <= budget) {  // the largest multiple of 32 that fits, capped at Cmax
     int lo = 64, hi = ((d.Cmax + 31) / 32) * 32;
+    if (const char* e = getenv("KP_CS_CAP")) hi = std::min(hi, std::max(64, atoi(e) / 32 * 32));  // experiment knob
     while (lo < hi) {
       int mid = ((lo + hi + 32) / 64) * 32;
       if (mid <= lo) mid = lo + 32;
@@ -760,6 +837,26 @@ static int prep_solve(kp_handle* h) {
   return KP_OK;
 }
 
+// The one collective of a NodePool-sharded job: every instance of this handle writes the
+// counters of its topology groups into its slice of the global table, then one ncclAllReduce(sum, int32) over NVLink on
+// the library's stream -- device resident from the solver kernel to the reduced table, inside the solve's event window.
+static int reduce_counters(kp_handle* h, const std::vector<Instance*>& insts) {
+  if (!h->d_gcnt) return KP_OK;
+  CK(cudaEventRecord(h->ev3, h->stream));
+  CK(cudaMemsetAsync(h->d_gcnt, 0, (size_t)h->gcnt_slots * 4, h->stream));
+  for (Instance* in : insts)
+    if (in->n_slots > 0) {
+      k_scatter_counts<<<(int)((in->n_slots + 255) / 256), 256, 0, h->stream>>>(in->dev.dom_cnt, in->d_slot_src, in->n_slots,
+                                                                                h->d_gcnt + in->slot_off);
+      h->stats.kernel_launches++;
+    }
+  if (h->comm) {
+    int rc = g_nccl.AllReduce(h->d_gcnt, h->d_gcnt, (size_t)h->gcnt_slots, /*ncclInt32*/ 2, /*ncclSum*/ 0, h->comm, h->stream);
+    if (rc != 0) return h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"), KP_ERR_CUDA;
+  }
+  return KP_OK;
+}
+
 static int run_solve(kp_handle* h) {
   Instance& in = *h->cur;
   KpDev& d = in.dev;
@@ -774,6 +871,8 @@ static int run_solve(kp_handle* h) {
   CK(cudaEventRecord(h->ev2, h->stream));
   k_wsolve<<<1, 64, in.smem, h->stream>>>(d, in.CS, in.CR);
   h->stats.kernel_launches++;
+  rc = reduce_counters(h, {&in});
+  if (rc != KP_OK) return rc;
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -781,6 +880,7 @@ static int run_solve(kp_handle* h) {
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   h->stats.solve_ms = ms;
   cudaEventElapsedTime(&in.wsolve_ms, h->ev2, h->ev1);
+  if (h->d_gcnt) cudaEventElapsedTime(&h->allreduce_ms, h->ev3, h->ev1);
   if (getenv("KP_DEBUG")) fprintf(stderr, "[kp] step %.3f ms, k_wsolve %.3f ms\n", ms, in.wsolve_ms);
   return KP_OK;
 }
@@ -921,6 +1021,97 @@ int kp_solve(kp_handle* h, const kp_problem* p, int64_t deadline_ms, kp_result* 
   }
 }
 
+// ---- multi-GPU: the global topology-domain counter table of a NodePool-sharded job --------------------------------
+int kp_comm_unique_id(uint8_t* id128) {
+  std::string err;
+  if (!nccl_load(err)) return KP_ERR_CUDA;
+  KpNcclId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return KP_ERR_CUDA;
+  memcpy(id128, &id, sizeof(id));
+  return KP_OK;
+}
+
+int kp_comm_init(kp_handle* h, const uint8_t* id128, int32_t rank, int32_t world) {
+  if (!nccl_load(h->err)) return KP_ERR_CUDA;
+  if (h->comm) {
+    g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  cudaSetDevice(h->device);
+  KpNcclId id;
+  memcpy(&id, id128, sizeof(id));
+  int rc = g_nccl.CommInitRank(&h->comm, world, id, rank);
+  if (rc != 0) return h->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"), KP_ERR_CUDA;
+  h->comm_rank = rank;
+  h->comm_world = world;
+  return KP_OK;
+}
+
+// Slots an uploaded instance contributes: its non-hostname groups in table order (regular groups in creation order, then
+// the inverse groups), one slot per value of the group's key -- the layout of kp_result.domain_counts when no group is
+// born mid-solve.  instance < 0: the kp_upload instance, else index into the kp_upload_batch list.
+static Instance* pick_instance(kp_handle* h, int32_t instance) {
+  if (instance < 0) return h->main.resident ? &h->main : nullptr;
+  return instance < (int)h->batch.size() ? h->batch[instance] : nullptr;
+}
+int64_t kp_comm_counter_slots(kp_handle* h, int32_t instance) {
+  Instance* in = pick_instance(h, instance);
+  if (!in) return -1;
+  int64_t n = 0;
+  for (int g = 0; g < in->host.G; g++)
+    if (in->host.groups[g].key != in->host.hostname_key) n += in->key_nvalues[in->host.groups[g].key];
+  return n;
+}
+
+// total_slots: size of the global table (sum over all ranks' instances); slot_offset[i]: where instance i of THIS handle
+// starts (n_instances == 0 with the kp_upload instance: slot_offset[0]).  From now on every kp_solve_resident /
+// kp_solve_batch_resident ends with scatter + all-reduce (when kp_comm_init was called) inside its solve_ms.
+int kp_comm_set_counter_layout(kp_handle* h, int64_t total_slots, const int64_t* slot_offset, int32_t n_instances) {
+  cudaSetDevice(h->device);
+  std::vector<Instance*> insts;
+  if (n_instances <= 0) {
+    if (!h->main.resident) return h->err = "kp_comm_set_counter_layout: nothing uploaded", KP_ERR_INVALID;
+    insts.push_back(&h->main);
+  } else {
+    if (n_instances != (int)h->batch.size()) return h->err = "kp_comm_set_counter_layout: batch size mismatch", KP_ERR_INVALID;
+    insts = h->batch;
+  }
+  if (total_slots < 0) return h->err = "kp_comm_set_counter_layout: negative size", KP_ERR_INVALID;
+  CK(h->arena.alloc(&h->d_gcnt, (size_t)std::max<int64_t>(total_slots, 1)));
+  h->gcnt_slots = total_slots;
+  for (size_t i = 0; i < insts.size(); i++) {
+    Instance* in = insts[i];
+    std::vector<int32_t> src;
+    for (int g = 0; g < in->host.G; g++) {
+      const int key = in->host.groups[g].key;
+      if (key == in->host.hostname_key) continue;
+      for (int v = 0; v < in->key_nvalues[key]; v++) src.push_back(g * 64 + v);
+    }
+    in->n_slots = (int64_t)src.size();
+    in->slot_off = slot_offset[i];
+    if (in->slot_off < 0 || in->slot_off + in->n_slots > total_slots)
+      return h->err = "kp_comm_set_counter_layout: slice outside the table", KP_ERR_INVALID;
+    CK(h->arena.alloc(&in->d_slot_src, std::max<size_t>(src.size(), 1)));
+    if (!src.empty()) CK(cudaMemcpyAsync(in->d_slot_src, src.data(), src.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return KP_OK;
+}
+
+int kp_comm_global_counts(kp_handle* h, int32_t* out, int64_t n) {
+  if (!h->d_gcnt || n != h->gcnt_slots) return h->err = "kp_comm_global_counts: no table of that size", KP_ERR_INVALID;
+  cudaSetDevice(h->device);
+  CK(cudaMemcpy(out, h->d_gcnt, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return KP_OK;
+}
+
+double kp_comm_last_allreduce_ms(kp_handle* h) { return h->allreduce_ms; }
+
+void kp_comm_destroy(kp_handle* h) {
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr;
+}
+
 // ---- kp_solve_batch: n independent Scheduler instances, one launch (one CTA per instance) ------------------------
 static void batch_clear(kp_handle* h) {
   for (Instance* b : h->batch) delete b;
@@ -998,6 +1189,10 @@ static int run_batch(kp_handle* h, int64_t deadline_ms, std::vector<int32_t>& st
   CK(cudaEventRecord(h->ev2, h->stream));
   k_wsolve_batch<<<n, 64, smem, h->stream>>>(h->d_batch_devs, h->d_batch_plan);
   h->stats.kernel_launches++;
+  {
+    int rc = reduce_counters(h, h->batch);
+    if (rc != KP_OK) return rc;
+  }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));  // devs / plan are host vectors: the copies above must have completed
   CK(cudaGetLastError());
@@ -1005,6 +1200,7 @@ static int run_batch(kp_handle* h, int64_t deadline_ms, std::vector<int32_t>& st
   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
   cudaEventElapsedTime(&wms, h->ev2, h->ev1);
   h->stats.solve_ms = ms;
+  if (h->d_gcnt) cudaEventElapsedTime(&h->allreduce_ms, h->ev3, h->ev1);
   if (getenv("KP_DEBUG")) fprintf(stderr, "[kp] batch of %d: step %.3f ms, k_wsolve_batch %.3f ms\n", n, ms, wms);
   for (int b = 0; b < n; b++) {
     h->batch[b]->wsolve_ms = wms;

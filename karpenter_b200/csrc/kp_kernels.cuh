@@ -193,6 +193,19 @@ __device__ __forceinline__ Slot topo_domains(const KpDev& d, int g, const KpGrou
   return out;
 }
 
+// TopologyGroup.Record on a hostname group (topologygroup.go:141-155): one more pod of the group on `host`.  The
+// presence bit answers "was the domain empty" from L1; the counter itself is a fire-and-forget reduction.
+__device__ __forceinline__ void host_record(const KpDev& d, int row, int g, int host) {
+  uint32_t* w = d.host_pop + (size_t)row * d.HW + (host >> 5);
+  const uint32_t bit = 1u << (host & 31), cur = *w;
+  if (!(cur & bit)) {
+    *w = cur | bit;
+    d.g_nempty[g]--;
+  }
+  atomicAdd(d.host_cnt + (size_t)row * d.H + host, 1);
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // One evaluated candidate, kept in the evaluating warp's registers until the winner commits.
 struct Eval {
   bool ok;
@@ -296,7 +309,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
       bool self = (e >> 30) & 1;
       if (G.key == d.hostname_key) {
         if (lane == 0) {  // candidates carry exactly one hostname: the fast paths of topologygroup.go:235-247,317-333,402-408
-          int cnt = d.host_cnt[(size_t)G.host_row * d.H + host];
+          int cnt = __ldcg(d.host_cnt + (size_t)G.host_row * d.H + host);
           bool ok;
           if (G.type == KP_TOPO_SPREAD)
             ok = cnt + (self ? 1 : 0) <= G.max_skew;
@@ -452,11 +465,7 @@ __device__ __forceinline__ void topo_record(const KpDev& d, const PodCtx& px, co
     }
     if (!counts) continue;
     if (G.key == d.hostname_key) {
-      if (lane == 0) {
-        int32_t* c = d.host_cnt + (size_t)G.host_row * d.H + host;
-        if (*c == 0) d.g_nempty[g]--;
-        (*c)++;
-      }
+      if (lane == 0) host_record(d, G.host_row, g, host);
     } else {
       uint32_t ff = __shfl_sync(FULL, F.f, G.key);
       uint64_t mm = __shfl_sync(FULL, F.m, G.key);
@@ -545,14 +554,12 @@ __device__ __forceinline__ void topo_record_fast(const KpDev& d, const PodCtx& p
     if (!G.inverse && G.taint_policy == 1) counts = tolerated(d, G.tolset, taintset);
     if (counts) {
       if (G.key == d.hostname_key) {
-        int32_t* c = d.host_cnt + (size_t)G.host_row * d.H + host;
-        const int32_t v = *c;
-        if (v == 0) d.g_nempty[g]--;
-        *c = v + 1;
+        host_record(d, G.host_row, g, host);
       } else if (z >= 0) {
         d.dom_cnt[G.dom_off + z]++;
-        d.dom_reg[g] |= 1ull << z;
-        d.dom_pop[g] |= 1ull << z;
+        const uint64_t bit = 1ull << z;
+        if (!(d.dom_reg[g] & bit)) d.dom_reg[g] |= bit;
+        if (!(d.dom_pop[g] & bit)) d.dom_pop[g] |= bit;
       }
     }
   }

@@ -146,7 +146,11 @@ struct KpDev {
   uint64_t* dom_pop;              // [G] domains with count > 0 (complement of t.emptyDomains within dom_reg)
   int32_t* g_ndomains;            // [G] hostname groups: len(t.domains)
   int32_t* g_nempty;              // [G] hostname groups: len(t.emptyDomains)
-  int32_t* host_cnt;              // [GH * H] per hostname group x host (existing nodes then claims)
+  int32_t* host_cnt;              // [GH * H] per hostname group x host (existing nodes then claims); updated with RED,
+                                  // read with ld.cg (never through L1)
+  uint32_t* host_pop;             // [GH * HW] bit (group, host): count > 0 -- what anti-affinity / affinity checks read;
+                                  // two cache lines per group and 1 000 NodeClaims, prefetched by the stager warp
+  int HW;                         // words per host_pop row = ceil(H / 32)
   int H;                          // E + claim capacity
   // existing nodes (dynamic)
   const int32_t* node_taintset;   // [E]

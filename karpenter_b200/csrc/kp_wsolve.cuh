@@ -256,11 +256,21 @@ __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, co
     for (int i = sc.hoff; i < sc.hend; i += 2) {
       const bool two = i + 1 < sc.hend;
       const int4 ha = sc.hc[i], hb = two ? sc.hc[i + 1] : ha;
+      // anti-affinity / affinity only ask "is the domain populated": one bit of host_pop (L1: the stager prefetched the
+      // row); a hostname spread needs the count
+      const bool cnt_a = (ha.y & 0xff) == KP_TOPO_SPREAD, cnt_b = (hb.y & 0xff) == KP_TOPO_SPREAD;
       int ca[U], cb[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        ca[u] = pass[u] ? d.host_cnt[(size_t)ha.x * d.H + E + c[u]] : 0;
-        cb[u] = (two && pass[u]) ? d.host_cnt[(size_t)hb.x * d.H + E + c[u]] : 0;
+        const int hi = E + c[u];
+        ca[u] = cb[u] = 0;
+        if (pass[u]) {
+          ca[u] = cnt_a ? __ldcg(d.host_cnt + (size_t)ha.x * d.H + hi)
+                        : (int)((d.host_pop[(size_t)ha.x * d.HW + (hi >> 5)] >> (hi & 31)) & 1u);
+          if (two)
+            cb[u] = cnt_b ? __ldcg(d.host_cnt + (size_t)hb.x * d.H + hi)
+                          : (int)((d.host_pop[(size_t)hb.x * d.HW + (hi >> 5)] >> (hi & 31)) & 1u);
+        }
       }
 #pragma unroll
       for (int r = 0; r < 2; r++) {
@@ -349,7 +359,22 @@ __device__ void stager_run(const KpDev& d, const WInst& I, StageRing* ring, cons
     const int li = __ldcg(I.queue + qi), X = __ldcg(I.qcls + qi);
     qi = qi + 1 >= cap ? 0 : qi + 1;
     ClassRegs c = load_class_regs(d, X, li, lane);
-    store_class_regs(d, ring->slot[idx & (KP_RING - 1)], c, lane);
+    PodCtx& slot = ring->slot[idx & (KP_RING - 1)];
+    store_class_regs(d, slot, c, lane);
+    __syncwarp();
+    // pull what the solver will read for this pod into L1 now: the presence rows of its hostname groups (the part that
+    // covers the NodeClaims: 8 lines == 8 192 claims) and the counter rows of its topology-key groups
+    if (slot.n_hc > 0) {
+      const int g8 = lane >> 3, l8 = lane & 7;  // four groups at a time, eight lines each
+      for (int i = g8; i < slot.n_hc; i += 4) {
+        const int w = (d.E >> 5) + l8 * 32;
+        if (w < d.HW) prefetch_l1(d.host_pop + (size_t)slot.hc[i].x * d.HW + w);
+      }
+    }
+    if (slot.n_mg > 0 && lane < 2 * slot.n_mg) {
+      const KpGroup& G = slot.mg[lane >> 1];
+      if (G.key == d.tk_key) prefetch_l1(d.dom_cnt + G.dom_off + (lane & 1) * 32);
+    }
     __threadfence_block();
     __syncwarp();
     if (lane == 0) ring->produced = idx + 1;

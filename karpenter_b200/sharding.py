@@ -36,6 +36,30 @@ def counter_layout(group_sizes_per_rank: Sequence[Sequence[int]]):
     return offs, total
 
 
+def instance_offsets(slots_mine: Sequence[int], rank: int, world: int, dist=None, device=None):
+    """Layout of the library-resident global counter table (include/karpsolve.h kp_comm_set_counter_layout): every rank
+    contributes the slot counts of ITS instances (kp_comm_counter_slots; a rank may hold several NodePool shards as one
+    kp_upload_batch); the table is the concatenation rank by rank, instance by instance.  One tiny all-gather of the
+    sizes.  Returns (offset of each of my instances, total slots)."""
+    sizes = [list(map(int, slots_mine))]
+    if world > 1 and dist is not None:
+        import torch
+        n = torch.tensor([len(slots_mine)], dtype=torch.int64, device=device)
+        counts = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(counts, n)
+        width = max(int(c.item()) for c in counts)
+        mine = torch.zeros(max(width, 1), dtype=torch.int64, device=device)
+        if slots_mine:
+            mine[:len(slots_mine)] = torch.tensor(list(map(int, slots_mine)), dtype=torch.int64, device=device)
+        rows = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(rows, mine)
+        sizes = [[int(v) for v in rows[r][:int(counts[r].item())].cpu()] for r in range(world)]
+    offs, total = counter_layout(sizes)
+    base = offs[rank if world > 1 and dist is not None else 0]
+    mine_off = [base + int(sum(sizes[rank if len(sizes) > 1 else 0][:i])) for i in range(len(slots_mine))]
+    return mine_off, total
+
+
 def allreduce_domain_counts(result: dict, rank: int, world: int, dist=None, device=None) -> np.ndarray:
     """The single collective of the sharded job: every rank contributes its shard's domain counters (zeros elsewhere)
     and receives the global table.  `result` is the dict of one shard's kp_solve (karpenter_b200/_abi.py)."""

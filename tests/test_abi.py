@@ -18,7 +18,7 @@ HEADER = os.path.join(ROOT, "include", "karpsolve.h")
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"^\s*(?:const\s+char\s*\*|int|void)\s+(kp_\w+)\s*\(", src, flags=re.M)))
+    return sorted(set(re.findall(r"^\s*(?:const\s+char\s*\*|int|void|int64_t|double)\s+(kp_\w+)\s*\(", src, flags=re.M)))
 
 
 def test_header_declares_the_documented_entry_points():

@@ -168,6 +168,27 @@ def test_c5_pool_shards_as_one_batch(handle):
         assert len(o["domain_counts"]) > 0 and o["domain_counts"].sum() > 0  # the table a multi-GPU run all-reduces
 
 
+def test_library_counter_table_single_gpu(handle):
+    """kp_comm_set_counter_layout without a communicator: after a resident (batch) solve the device-resident global
+    table is the concatenation of the instances' domain counters -- what the NCCL all-reduce of a multi-GPU run sums."""
+    from karpenter_b200 import sharding
+    shards = [workloads.config_c5(n_pods=6000, n_pools=3, n_its=200, app_replicas=50, pools_subset=[r]) for r in range(3)]
+    handle.upload_batch([e.problem for e in shards])
+    slots = [handle.counter_slots(i) for i in range(3)]
+    offs, total = sharding.instance_offsets(slots, 0, 1)
+    handle.set_counter_layout(total, offs)
+    outs = handle.solve_batch_resident()
+    want = np.concatenate([o["domain_counts"] for o in outs])
+    assert total == len(want) and want.sum() > 0
+    assert np.array_equal(handle.global_counts(), want)
+    assert handle.last_allreduce_ms() >= 0.0
+    # the single-instance variant
+    handle.upload(shards[1].problem)
+    handle.set_counter_layout(handle.counter_slots(), [0])
+    res = handle.solve_resident()
+    assert np.array_equal(handle.global_counts(), res["domain_counts"])
+
+
 def test_shared_to_global_migration(monkeypatch):
     """Claims outgrow the shared-memory copies of the claim order / failure bitmaps (forced early with KP_CS_LIMIT):
     the solver migrates them to HBM mid-run and the result must not change."""

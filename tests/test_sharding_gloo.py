@@ -64,6 +64,41 @@ def test_union_of_shards_is_the_unsharded_solve():
     assert sorted(per_shard) == groups(union)
 
 
+def _layout_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # rank 0 holds three NodePool shards (a kp_upload_batch of three), rank 1 one: the layout the library is given
+        slots = [12, 0, 7] if rank == 0 else [5]
+        offs, total = sharding.instance_offsets(slots, rank, world, dist)
+        q.put((rank, offs, total))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_counter_table_layout_gloo_world2():
+    """Host logic of the library-side collective (kp_comm_set_counter_layout): slices by rank, then by instance."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_layout_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert got == [(0, [0, 12, 12], 24), (1, [19], 24)]
+    assert sharding.instance_offsets([3, 4], 0, 1) == ([0, 3], 7)
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
