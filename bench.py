@@ -227,7 +227,7 @@ def time_provisioning(h, problem, n_pods, steps, warmup, torch, flush, barrier, 
         sampler.stop_flag = True
     launches = h.stats()["kernel_launches"]
     e2e_t = []
-    n_e2e = steps if e2e_steps is None else e2e_steps
+    n_e2e = min(steps, 3) if e2e_steps is None else e2e_steps
     for i in range(1 + n_e2e):
         barrier()
         t0 = time.perf_counter()
@@ -326,8 +326,8 @@ def c5_shards(rank, world):
     from karpenter_b200 import sharding, workloads
     pools = sharding.pools_of_rank(C5_POOLS, rank, world)
     n_pods = int(os.environ.get("KP_C5_PODS", C5_PODS))
-    return pools, [workloads.config_c5(n_pods=n_pods, n_pools=C5_POOLS, n_its=C5_ITS, app_replicas=1000,
-                                       pools_subset=[p]) for p in pools], n_pods
+    return pools, workloads.config_c5_shards(n_pods=n_pods, n_pools=C5_POOLS, n_its=C5_ITS, app_replicas=1000,
+                                             pool_groups=[[p] for p in pools]), n_pods
 
 
 def time_c5(h, rank, world, steps, warmup, torch, dist, flush, barrier, sampler=None):
@@ -368,7 +368,7 @@ def time_c5(h, rank, world, steps, warmup, torch, dist, flush, barrier, sampler=
     launches = h.stats()["kernel_launches"]
     table = h.global_counts()
     e2e_t = []
-    for i in range(1 + max(1, min(steps, 2))):
+    for i in range(1 + (1 if world == 1 else max(1, min(steps, 2)))):
         barrier()
         t0 = time.perf_counter()
         upload()
@@ -478,7 +478,7 @@ def main():
             line["c2"] = c2
         # ---------------- secondary: C5's 8 NodePool shards as one batch on this GPU
         if not args.no_c5:
-            m5 = time_c5(h, 0, 1, max(1, min(args.steps, 2)), 1, torch, None, flush, barrier)
+            m5 = time_c5(h, 0, 1, 1, 1, torch, None, flush, barrier)
             line["c5_one_gpu"] = {
                 "workload": C5_NAME.replace("NodePool p on rank p mod N", "all 8 NodePool shards as ONE kp_solve_batch on this GPU, one CTA each"),
                 "value": m5["n_total"] / (m5["ms"] / 1000), "unit": "pods/s", "ms_per_step": m5["ms"], "n_pods": m5["n_total"],

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KP_ABI_VERSION 2
+#define KP_ABI_VERSION 3
 
 typedef enum kp_status {
   KP_OK = 0,
@@ -284,6 +284,12 @@ typedef struct kp_result {
 #define KP_DECISION_NOOP 0
 #define KP_DECISION_DELETE 1
 #define KP_DECISION_REPLACE 2
+#define KP_DECISION_UNKNOWN 255 /* not evaluated: the deadline passed first (kp_consolidate returned KP_DEADLINE) */
+
+/* kinds of the extra pods every simulation schedules next to the candidates' (helpers.go:65-91) */
+#define KP_EXTRA_PENDING 1       /* provisionable pending pod: its errors are ignored (scheduler.go:330-334) */
+#define KP_EXTRA_DELETING_NODE 2 /* reschedulable pod of a node marked for deletion: must schedule, but landing on an
+                                    uninitialized node is no error (helpers.go:121-140) */
 
 typedef struct kp_consol_input {
   /* cluster pods that would be evicted, grouped by the node they run on */
@@ -301,6 +307,14 @@ typedef struct kp_consol_input {
    * removed, only options cheaper than the cheapest such node stay; nothing left == not a valid command, reported as
    * KP_DECISION_NOOP.  0 = plain computeConsolidation (single-node consolidation, or the caller filters itself). */
   int32_t filter_same_instance_type;
+  /* SimulateScheduling schedules, together with the candidates' pods, the cluster's pending pods and the reschedulable
+   * pods of nodes that are already being deleted (helpers.go:65-91); they take capacity and can open NodeClaims.  They
+   * are the LAST n_extra_pods rows of the cluster's pod table (rows node_pod_off[n_nodes] .. n_pods-1), with
+   * extra_pod_kind[i] = KP_EXTRA_*.  0 / NULL: none. */
+  int32_t n_extra_pods;
+  const uint8_t* extra_pod_kind;
+  /* 1: also return, per REPLACE subset, the price order of the replacement's instance types (repl_order_*) */
+  int32_t export_price_order;
 } kp_consol_input;
 
 typedef struct kp_consol_result {
@@ -312,6 +326,20 @@ typedef struct kp_consol_result {
   int32_t* n_unscheduled;     /* [n_subsets] */
   double solve_ms;
   void* _impl;
+  /* The replacement NodeClaim of every REPLACE subset as Command.Replacements needs it (consolidation.go:206-229,
+   * replacementsFromNodeClaims): its NodePool, Spec.Resources.Requests and requirements AFTER the capacity-type pins
+   * (OD -> [OD, spot] becomes spot-only, :211-214; spot-to-spot pins spot, :249), in the layout of
+   * kp_result.claim_req_* (hostname dropped).  Rows of other subsets are zero. */
+  int32_t n_keys, mask_words, n_resources;
+  int32_t* repl_template;     /* [n_subsets], -1 unless REPLACE */
+  int64_t* repl_requests;     /* [n_subsets * n_resources] */
+  uint8_t* repl_req_flags;    /* [n_subsets * n_keys] */
+  int64_t* repl_req_gte;
+  int64_t* repl_req_lte;
+  uint64_t* repl_req_mask;    /* [n_subsets * mask_words] */
+  /* export_price_order: instance types of replacement_its in OrderByPrice order (types.go:238-257), CSR over subsets */
+  int32_t* repl_order_off;    /* [n_subsets + 1] or NULL */
+  int32_t* repl_order;
 } kp_consol_result;
 
 typedef struct kp_handle kp_handle;
@@ -374,6 +402,12 @@ void kp_consol_result_free(kp_consol_result* r);
  * filterInstanceTypesByRequirements (nodeclaim.go:412-480) for a fresh NodeClaim of `template` holding one pod of
  * `class`, ignoring topology.  out: [n_classes * n_templates * it_words] */
 int kp_feasibility(kp_handle* h, const kp_problem* p, uint64_t* out_bits, int32_t* out_it_words);
+
+/* Go's sort.Slice order (pdqsort_func, unstable) of a key array under less = "<": perm_out[i] = index of the element left at
+ * position i.  Host code, no device: the disruption front-end sorts candidates by DisruptionCost with it
+ * (consolidation.go:126-131, singlenodeconsolidation.go:143-146), so that cost ties fall the way the reference's do. */
+int kp_go_sort_f64(const double* keys, int32_t n, int32_t* perm_out);
+int kp_go_sort_i64(const int64_t* keys, int32_t n, int32_t* perm_out);
 
 typedef struct kp_stats {
   double upload_ms, prep_ms, solve_ms, download_ms;

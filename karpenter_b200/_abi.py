@@ -187,7 +187,22 @@ def consol_result_to_dict(r: kp_consol_result) -> dict:
         "n_new_claims": view(r.n_new_claims, S, np.int32),
         "n_unscheduled": view(r.n_unscheduled, S, np.int32),
         "solve_ms": r.solve_ms,
+        "n_keys": r.n_keys, "mask_words": r.mask_words,
+        "repl_template": view(r.repl_template, S, np.int32),
+        "repl_requests": view(r.repl_requests, S * r.n_resources, np.int64).reshape(S, max(r.n_resources, 0)),
+        "repl_req_flags": view(r.repl_req_flags, S * r.n_keys, np.uint8).reshape(S, max(r.n_keys, 0)),
+        "repl_req_gte": view(r.repl_req_gte, S * r.n_keys, np.int64).reshape(S, max(r.n_keys, 0)),
+        "repl_req_lte": view(r.repl_req_lte, S * r.n_keys, np.int64).reshape(S, max(r.n_keys, 0)),
+        "repl_req_mask": view(r.repl_req_mask, S * r.mask_words, np.uint64).reshape(S, max(r.mask_words, 0)),
+        "repl_order_off": view(r.repl_order_off, S + 1, np.int32) if r.repl_order_off else None,
+        "repl_order": (view(r.repl_order, int(view(r.repl_order_off, S + 1, np.int32)[-1]), np.int32)
+                       if r.repl_order_off else None),
     }
+
+
+# keys of a consolidation result that must be bit-identical between the CUDA path and the oracle
+CONSOL_PARITY_KEYS = ["decision", "n_new_claims", "n_unscheduled", "replacement_its", "repl_template", "repl_requests",
+                      "repl_req_flags", "repl_req_gte", "repl_req_lte", "repl_req_mask"]
 
 
 # result keys that must be bit-identical between the CUDA path and the oracle

@@ -59,6 +59,8 @@ def lib():
         L.kp_comm_last_allreduce_ms.argtypes = [C.c_void_p]
         L.kp_comm_last_allreduce_ms.restype = C.c_double
         L.kp_comm_destroy.argtypes = [C.c_void_p]
+        L.kp_go_sort_f64.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.kp_go_sort_i64.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.kp_consolidate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.kp_consol_result_free.argtypes = [C.c_void_p]
         L.kp_feasibility.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -71,7 +73,22 @@ EXPORTS = ["kp_version", "kp_create", "kp_destroy", "kp_last_error", "kp_solve",
            "kp_solve_resident", "kp_consolidate", "kp_consol_result_free", "kp_feasibility", "kp_get_stats",
            "kp_solve_batch", "kp_upload_batch", "kp_solve_batch_resident", "kp_comm_unique_id", "kp_comm_init",
            "kp_comm_counter_slots", "kp_comm_set_counter_layout", "kp_comm_global_counts", "kp_comm_last_allreduce_ms",
-           "kp_comm_destroy"]
+           "kp_comm_destroy", "kp_go_sort_f64", "kp_go_sort_i64"]
+
+
+def go_sort_order(keys) -> np.ndarray:
+    """Order Go's sort.Slice(less = <) leaves `keys` in (indices into keys); host code of the library, no device needed."""
+    k = np.ascontiguousarray(keys)
+    perm = np.zeros(len(k), np.int32)
+    if k.dtype.kind == "f":
+        k = k.astype(np.float64)
+        rc = lib().kp_go_sort_f64(k.ctypes.data_as(C.c_void_p), len(k), perm.ctypes.data_as(C.c_void_p))
+    else:
+        k = k.astype(np.int64)
+        rc = lib().kp_go_sort_i64(k.ctypes.data_as(C.c_void_p), len(k), perm.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise SolverError(rc, "kp_go_sort failed")
+    return perm
 
 
 class Handle:
@@ -194,8 +211,11 @@ class Handle:
 
     def consolidate(self, problem: _abi.Problem, consol: _abi.ConsolInput, deadline_ms: int = 0) -> dict:
         r = _abi.kp_consol_result()
-        self._check(lib().kp_consolidate(self._h, problem.ref(), consol.ref(), deadline_ms, C.byref(r)))
+        rc = lib().kp_consolidate(self._h, problem.ref(), consol.ref(), deadline_ms, C.byref(r))
+        if rc != 1:  # KP_DEADLINE: the subsets that finished are valid, the rest read KP_DECISION_UNKNOWN
+            self._check(rc)
         out = _abi.consol_result_to_dict(r)
+        out["deadline"] = rc == 1
         lib().kp_consol_result_free(C.byref(r))
         return out
 

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "kp_consolidate.cuh"
+#include "kp_gosort_host.hpp"
 #include "kp_prep.hpp"
 
 #define CK(call)                                                                                     \
@@ -227,7 +228,8 @@ __global__ void k_scatter_counts(const int32_t* dom_cnt, const int32_t* slot_src
   if (i < n) out[i] = dom_cnt[slot_src[i]];
 }
 
-static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_consol_input* in, kp_consol_result* out);
+static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_consol_input* in, int64_t deadline_ms,
+                               kp_consol_result* out);
 extern "C" {
 static void batch_clear(kp_handle* h);
 }
@@ -235,6 +237,18 @@ static void batch_clear(kp_handle* h);
 extern "C" {
 
 int kp_version(void) { return KP_ABI_VERSION; }
+
+// sort.Slice order of a key array (host; no device needed): see kp_gosort_host.hpp
+int kp_go_sort_f64(const double* keys, int32_t n, int32_t* perm_out) {
+  if (n < 0 || (n > 0 && (!keys || !perm_out))) return KP_ERR_INVALID;
+  host_go_sort(keys, n, perm_out);
+  return KP_OK;
+}
+int kp_go_sort_i64(const int64_t* keys, int32_t n, int32_t* perm_out) {
+  if (n < 0 || (n > 0 && (!keys || !perm_out))) return KP_ERR_INVALID;
+  host_go_sort(keys, n, perm_out);
+  return KP_OK;
+}
 
 int kp_create(int device, kp_handle** out) {
   *out = nullptr;
@@ -586,8 +600,14 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(zeros(h, &d.c_dom, C));
   d.tmpl_all = t.N >= 64 ? ~0ull : ((1ull << t.N) - 1);
   d.H = t.E + d.Cmax;
-  CK(zeros(h, &d.host_cnt, (size_t)std::max(t.GH, 1) * d.H));
-  CK(up(h, &h->cur->d_host_cnt_nodes, t.host_cnt_nodes));
+  d.GHS = std::max(t.GH, 1);
+  CK(zeros(h, &d.host_cnt, (size_t)d.GHS * d.H));
+  {  // initial counts of the existing nodes, host-major like the table itself: rows [0, E)
+    std::vector<int32_t> tr((size_t)std::max(t.E, 1) * d.GHS, 0);
+    for (int r = 0; r < t.GH; r++)
+      for (int n = 0; n < t.E; n++) tr[(size_t)n * d.GHS + r] = t.host_cnt_nodes[(size_t)r * t.E + n];
+    CK(up(h, &h->cur->d_host_cnt_nodes, tr));
+  }
   d.HW = (d.H + 31) / 32;
   CK(zeros(h, &d.host_pop, (size_t)std::max(t.GH, 1) * d.HW));
   {  // presence bits of the existing nodes: words [0, ceil(E/32)) of every row
@@ -614,10 +634,9 @@ static int reset_dynamic(kp_handle* h) {
   CK(cudaMemsetAsync(d.c_npods, 0, C * 4, h->stream));
   CK(cudaMemsetAsync(d.cmask, 0, C * sizeof(ulonglong2), h->stream));
   CK(cudaMemsetAsync(d.amask, 0, C * 8, h->stream));
-  CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)std::max(t.GH, 1) * d.H * 4, h->stream));
-  if (t.E && t.GH)  // initial hostname-group counts of the existing nodes: rows of E ints into rows of H ints
-    CK(cudaMemcpy2DAsync(d.host_cnt, (size_t)d.H * 4, h->cur->d_host_cnt_nodes, (size_t)t.E * 4, (size_t)t.E * 4, t.GH,
-                         cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)d.GHS * d.H * 4, h->stream));
+  if (t.E && t.GH)  // initial hostname-group counts of the existing nodes: the first E host rows
+    CK(cudaMemcpyAsync(d.host_cnt, h->cur->d_host_cnt_nodes, (size_t)t.E * d.GHS * 4, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemsetAsync(d.host_pop, 0, (size_t)std::max(t.GH, 1) * d.HW * 4, h->stream));
   if (t.E && t.GH) {
     const size_t ew = (size_t)(t.E + 31) / 32;
@@ -1309,8 +1328,10 @@ int kp_feasibility(kp_handle* h, const kp_problem* p, uint64_t* out_bits, int32_
 
 int kp_consolidate(kp_handle* h, const kp_problem* cluster, const kp_consol_input* in, int64_t deadline_ms,
                    kp_consol_result* out) {
-  (void)deadline_ms;
-  return kp_consolidate_impl(h, cluster, in, out);
+  memset(out, 0, sizeof(*out));
+  int rc = kp_consolidate_impl(h, cluster, in, deadline_ms, out);
+  if (rc != KP_OK && rc != KP_DEADLINE) kp_consol_result_free(out);  // nothing half-built leaves the library
+  return rc;
 }
 
 void kp_consol_result_free(kp_consol_result* r) {
@@ -1318,6 +1339,14 @@ void kp_consol_result_free(kp_consol_result* r) {
   free(r->replacement_its);
   free(r->n_new_claims);
   free(r->n_unscheduled);
+  free(r->repl_template);
+  free(r->repl_requests);
+  free(r->repl_req_flags);
+  free(r->repl_req_gte);
+  free(r->repl_req_lte);
+  free(r->repl_req_mask);
+  free(r->repl_order_off);
+  free(r->repl_order);
   memset(r, 0, sizeof(*r));
 }
 }
@@ -1329,9 +1358,18 @@ __global__ void k_scatter_rank(const int32_t* perm, int64_t n, int32_t* rank) {
 
 // kp_consolidate: every subset is one SimulateScheduling + computeConsolidation (helpers.go:51-142,
 // consolidation.go:136-229); they are independent, so each runs as its own solver instance on its own warp.
-static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_consol_input* in, kp_consol_result* out) {
-  memset(out, 0, sizeof(*out));
+static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_consol_input* in, int64_t deadline_ms,
+                               kp_consol_result* out) {
+  const auto t_call = std::chrono::steady_clock::now();
   const int S = in->n_subsets;
+  const int n_extra = in->n_extra_pods > 0 ? in->n_extra_pods : 0;
+  if (p->n_nodes > 0 && !in->node_pod_off) return h->err = "kp_consolidate: node_pod_off is null", KP_ERR_INVALID;
+  const int64_t extra_row0 = p->n_nodes > 0 ? in->node_pod_off[p->n_nodes] : 0;
+  if (n_extra > 0 && (!in->extra_pod_kind || extra_row0 + n_extra != p->n_pods))
+    return h->err = "kp_consolidate: the extra pods must be the last n_extra_pods rows of the pod table, with kinds", KP_ERR_INVALID;
+  for (int i = 0; i < n_extra; i++)
+    if (in->extra_pod_kind[i] != KP_EXTRA_PENDING && in->extra_pod_kind[i] != KP_EXTRA_DELETING_NODE)
+      return h->err = "kp_consolidate: unknown extra pod kind", KP_ERR_INVALID;
   int rc = do_upload(h, p, 1);  // the cluster's pod table doubles as the "pods" of the problem (rows by node)
   if (rc != KP_OK) return rc;
   HostTables& t = h->cur->host;
@@ -1342,6 +1380,63 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   }
   const int K = t.K, R = t.R, ITW = t.ITW, E = t.E, N = t.N, T = t.T;
   const bool general = t.G > 0;  // the evicted pods carry topology constraints: one full solve per candidate set
+  const std::vector<int> key_nvalues = h->cur->key_nvalues;
+  const int hostname_key = h->cur->hostname_key;
+  // ---- result arrays (owned by `out` from here on: kp_consolidate frees them on any error return)
+  std::vector<int> woff(p->n_keys + 1, 0);
+  for (int k = 0; k < p->n_keys; k++) woff[k + 1] = woff[k] + (k == hostname_key ? 0 : (key_nvalues[k] + 63) / 64);
+  const int MW = woff[p->n_keys];
+  {
+    const size_t s1 = S ? S : 1;
+    out->n_subsets = S;
+    out->it_words = ITW;
+    out->n_keys = K;
+    out->mask_words = MW;
+    out->n_resources = R;
+    out->decision = (uint8_t*)malloc(s1);
+    memset(out->decision, KP_DECISION_UNKNOWN, s1);
+    out->replacement_its = (uint64_t*)calloc(s1 * (ITW ? ITW : 1), sizeof(uint64_t));
+    out->n_new_claims = (int32_t*)calloc(s1, sizeof(int32_t));
+    out->n_unscheduled = (int32_t*)calloc(s1, sizeof(int32_t));
+    out->repl_template = (int32_t*)malloc(s1 * 4);
+    for (size_t i = 0; i < s1; i++) out->repl_template[i] = -1;
+    out->repl_requests = (int64_t*)calloc(s1 * (R ? R : 1), 8);
+    out->repl_req_flags = (uint8_t*)calloc(s1 * (K ? K : 1), 1);
+    out->repl_req_gte = (int64_t*)calloc(s1 * (K ? K : 1), 8);
+    out->repl_req_lte = (int64_t*)calloc(s1 * (K ? K : 1), 8);
+    out->repl_req_mask = (uint64_t*)calloc(s1 * (MW ? MW : 1), 8);
+  }
+  const int order_cap = std::min(std::max(T, 1), 600);
+  std::vector<std::vector<int32_t>> order_rows(in->export_price_order ? S : 0);
+  // device slots of a replacement claim -> the ABI's per-key layout (as download() does for kp_result.claim_req_*)
+  auto store_repl = [&](int s_out, const uint8_t* sf, const uint64_t* sm, const int64_t* sg, const int64_t* sl) {
+    for (int k = 0; k < K; k++) {
+      const uint8_t f = sf[k];
+      if (!(f & SF_PRESENT) || k == hostname_key) continue;
+      out->repl_req_flags[(size_t)s_out * K + k] = KP_SLOT_PRESENT | ((f & SF_COMPLEMENT) ? KP_REQ_COMPLEMENT : 0) |
+                                                   ((f & SF_HAS_GTE) ? KP_REQ_HAS_GTE : 0) | ((f & SF_HAS_LTE) ? KP_REQ_HAS_LTE : 0);
+      if ((f & SF_HAS_GTE) && sg) out->repl_req_gte[(size_t)s_out * K + k] = sg[k];
+      if ((f & SF_HAS_LTE) && sl) out->repl_req_lte[(size_t)s_out * K + k] = sl[k];
+      if (woff[k + 1] > woff[k]) out->repl_req_mask[(size_t)s_out * MW + woff[k]] = sm[k];
+    }
+  };
+  auto finish_order = [&]() {
+    if (!in->export_price_order) return;
+    out->repl_order_off = (int32_t*)calloc((size_t)S + 1, 4);
+    size_t tot = 0;
+    for (int s_ = 0; s_ < S; s_++) {
+      tot += order_rows[s_].size();
+      out->repl_order_off[s_ + 1] = (int32_t)tot;
+    }
+    out->repl_order = (int32_t*)calloc(tot ? tot : 1, 4);
+    for (int s_ = 0; s_ < S; s_++)
+      if (!order_rows[s_].empty()) memcpy(out->repl_order + out->repl_order_off[s_], order_rows[s_].data(), order_rows[s_].size() * 4);
+  };
+  auto ms_left = [&]() -> int64_t {  // < 0: no deadline
+    if (deadline_ms <= 0) return -1;
+    const double used = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+    return std::max<int64_t>(0, deadline_ms - (int64_t)used);
+  };
   auto t_begin = std::chrono::steady_clock::now();
   // ---- host-side constants of the decision step
   auto ki = [&](int k) { return KeyInfo{t.val_int.data() + (size_t)k * 64, t.val_isint[k], t.key_univ[k]}; };
@@ -1424,6 +1519,9 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   auto upload_prices = [&](KpConsol& q) -> int {
     q.ct_key = in->capacity_type_key;
     q.ct_spot = in->ct_spot;
+    q.ct_od = in->ct_on_demand;
+    q.export_order = in->export_price_order ? 1 : 0;
+    q.order_cap = order_cap;
     q.ct_order_valid = ct_valid;
     q.spot_to_spot_enabled = in->spot_to_spot_enabled;
     q.T = T;
@@ -1451,80 +1549,174 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
       if (in->subset_nodes[i] < 0 || in->subset_nodes[i] >= E) return h->err = "subset node out of range", KP_ERR_INVALID;
   if (general) {
     // ---- general path: a candidate set is SimulateScheduling over its own stateNodes / bound pods / pending pods
-    // (helpers.go:51-142) -> a derived kp_problem -> an ordinary kp_solve on the device, then computeConsolidation
-    out->n_subsets = S;
-    out->it_words = ITW;
-    out->decision = (uint8_t*)calloc(S ? S : 1, 1);
-    out->replacement_its = (uint64_t*)calloc((size_t)(S ? S : 1) * (ITW ? ITW : 1), sizeof(uint64_t));
-    out->n_new_claims = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
-    out->n_unscheduled = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
+    // (helpers.go:51-142) -> a derived kp_problem (fresh NewTopology).  All sets of a chunk are uploaded side by side and
+    // solved by ONE k_wsolve_batch launch (one CTA per set), then k_decide_batch applies computeConsolidation.
     double total_ms = 0;
+    bool timed_out = false;
+    const int CHUNK = 296;  // two waves of 148 SMs; bounds the HBM the side-by-side tables take
     std::vector<uint8_t> is_cand(std::max(E, 1), 0), flags(std::max(E, 1), 0);
-    for (int s = 0; s < S; s++) {
-      const int so = in->subset_off[s], sn = in->subset_off[s + 1] - so;
-      std::fill(is_cand.begin(), is_cand.end(), 0);
-      for (int i = 0; i < sn; i++) is_cand[in->subset_nodes[so + i]] = 1;
-      for (int n = 0; n < E; n++)
-        flags[n] = is_cand[n] ? (uint8_t)(p->node_flags[n] & ~KP_NODE_SCHEDULABLE) : p->node_flags[n];
-      std::vector<int32_t> pod_class, run_class(p->run_class, p->run_class + p->n_running),
-          run_node(p->run_node, p->run_node + p->n_running);
-      std::vector<int64_t> creation;
-      std::vector<uint64_t> uid_hi, uid_lo;
-      for (int n = 0; n < E; n++)
-        for (int j = in->node_pod_off[n]; j < in->node_pod_off[n + 1]; j++) {
-          if (is_cand[n]) {
-            pod_class.push_back(p->pod_class[j]);
-            creation.push_back(p->pod_creation ? p->pod_creation[j] : 0);
-            uid_hi.push_back(p->pod_uid_hi[j]);
-            uid_lo.push_back(p->pod_uid_lo[j]);
-          } else {  // still running where it is: counted by the topology
-            run_class.push_back(p->pod_class[j]);
-            run_node.push_back(n);
-          }
-        }
-      if (pod_class.empty()) {  // nothing to reschedule: every pod is "placed", no NodeClaim
-        out->decision[s] = KP_DECISION_DELETE;
-        continue;
+    for (int c0 = 0; c0 < S && !timed_out; c0 += CHUNK) {
+      const int c1 = std::min(S, c0 + CHUNK);
+      if (deadline_ms > 0 && ms_left() == 0) {
+        timed_out = true;
+        break;
       }
-      kp_problem sp = *p;
-      sp.node_flags = flags.data();
-      sp.n_pods = (int64_t)pod_class.size();
-      sp.pod_class = pod_class.data();
-      sp.pod_creation = creation.data();
-      sp.pod_uid_hi = uid_hi.data();
-      sp.pod_uid_lo = uid_lo.data();
-      sp.n_running = (int64_t)run_class.size();
-      sp.run_class = run_class.data();
-      sp.run_node = run_node.data();
-      rc = do_upload(h, &sp, (int)std::max<int64_t>(sp.n_pods, 1));
-      if (rc != KP_OK) return rc;
+      batch_clear(h);
+      std::vector<int> set_of;  // instance -> subset
+      std::vector<int32_t> soff{0}, snodes_all;
+      bool first = true;
+      for (int s = c0; s < c1; s++) {
+        const int so = in->subset_off[s], sn = in->subset_off[s + 1] - so;
+        std::fill(is_cand.begin(), is_cand.end(), 0);
+        for (int i = 0; i < sn; i++) is_cand[in->subset_nodes[so + i]] = 1;
+        for (int n = 0; n < E; n++)
+          flags[n] = is_cand[n] ? (uint8_t)(p->node_flags[n] & ~KP_NODE_SCHEDULABLE) : p->node_flags[n];
+        std::vector<int32_t> pod_class, run_class(p->run_class, p->run_class + p->n_running),
+            run_node(p->run_node, p->run_node + p->n_running);
+        std::vector<int64_t> creation;
+        std::vector<uint64_t> uid_hi, uid_lo;
+        std::vector<uint8_t> kinds;
+        auto take = [&](int64_t j, uint8_t kind) {
+          pod_class.push_back(p->pod_class[j]);
+          creation.push_back(p->pod_creation ? p->pod_creation[j] : 0);
+          uid_hi.push_back(p->pod_uid_hi[j]);
+          uid_lo.push_back(p->pod_uid_lo[j]);
+          kinds.push_back(kind);
+        };
+        for (int n = 0; n < E; n++)
+          for (int j = in->node_pod_off[n]; j < in->node_pod_off[n + 1]; j++) {
+            if (is_cand[n]) {
+              take(j, 0);
+            } else {  // still running where it is: counted by the topology
+              run_class.push_back(p->pod_class[j]);
+              run_node.push_back(n);
+            }
+          }
+        for (int i = 0; i < n_extra; i++) take(extra_row0 + i, in->extra_pod_kind[i]);
+        if (pod_class.empty()) {  // nothing to reschedule: every pod is "placed", no NodeClaim
+          out->decision[s] = KP_DECISION_DELETE;
+          continue;
+        }
+        kp_problem sp = *p;
+        sp.node_flags = flags.data();
+        sp.n_pods = (int64_t)pod_class.size();
+        sp.pod_class = pod_class.data();
+        sp.pod_creation = creation.data();
+        sp.pod_uid_hi = uid_hi.data();
+        sp.pod_uid_lo = uid_lo.data();
+        sp.n_running = (int64_t)run_class.size();
+        sp.run_class = run_class.data();
+        sp.run_node = run_node.data();
+        h->batch.push_back(new Instance());
+        h->cur = h->batch.back();
+        rc = do_upload(h, &sp, (int)std::max<int64_t>(sp.n_pods, 1), first);
+        if (rc == KP_OK && n_extra > 0) {
+          uint8_t* dk;
+          cudaError_t e = up_raw(h, &dk, kinds.data(), kinds.size());
+          if (e != cudaSuccess) rc = (h->err = cudaGetErrorString(e), KP_ERR_CUDA);
+          h->cur->dev.pod_kind = dk;
+          cudaStreamSynchronize(h->stream);  // `kinds` dies with this iteration
+        }
+        h->cur = &h->main;
+        if (rc != KP_OK) return rc;
+        first = false;
+        set_of.push_back(s);
+        for (int i = 0; i < sn; i++) snodes_all.push_back(in->subset_nodes[so + i]);
+        soff.push_back((int32_t)snodes_all.size());
+      }
+      const int nb = (int)set_of.size();
+      if (nb == 0) continue;
+      h->cur = h->batch[0];  // upload_prices / arena helpers account their bytes on the current instance's handle stats
       KpConsol q;
       memset(&q, 0, sizeof(q));
       rc = upload_prices(q);
+      h->cur = &h->main;
       if (rc != KP_OK) return rc;
-      int32_t* d_snodes;
-      CK(up_raw(h, &d_snodes, in->subset_nodes + so, (size_t)sn));
-      CK(zeros(h, &q.decision, 1));
-      CK(zeros(h, &q.replacement_its, (size_t)std::max(ITW, 1)));
-      CK(zeros(h, &q.n_new_claims, 1));
-      CK(zeros(h, &q.n_unscheduled, 1));
-      rc = run_solve(h);
+      CK(h->arena.alloc(&h->d_batch_devs, (size_t)nb));
+      CK(h->arena.alloc(&h->d_batch_plan, (size_t)nb));
+      int32_t *d_soff, *d_snodes;
+      CK(up_raw(h, &d_soff, soff.data(), soff.size()));
+      CK(up_raw(h, &d_snodes, snodes_all.data(), std::max<size_t>(snodes_all.size(), 1)));
+      const size_t nb1 = (size_t)nb;
+      CK(zeros(h, &q.sort_key, nb1 * (size_t)std::max(T, 1)));
+      CK(zeros(h, &q.sort_val, nb1 * (size_t)std::max(T, 1)));
+      CK(zeros(h, &q.sort_bits, nb1 * (size_t)std::max(ITW, 1)));
+      CK(zeros(h, &q.decision, nb1));
+      CK(zeros(h, &q.replacement_its, nb1 * std::max(ITW, 1)));
+      CK(zeros(h, &q.n_new_claims, nb1));
+      CK(zeros(h, &q.n_unscheduled, nb1));
+      CK(zeros(h, &q.repl_tmpl, nb1));
+      CK(zeros(h, &q.repl_req, nb1 * std::max(R, 1)));
+      CK(zeros(h, &q.repl_sflags, nb1 * std::max(K, 1)));
+      CK(zeros(h, &q.repl_smask, nb1 * std::max(K, 1)));
+      if (t.has_bounds) {
+        CK(zeros(h, &q.repl_sgte, nb1 * std::max(K, 1)));
+        CK(zeros(h, &q.repl_slte, nb1 * std::max(K, 1)));
+      }
+      if (in->export_price_order) {
+        CK(zeros(h, &q.repl_order, nb1 * order_cap));
+        CK(zeros(h, &q.repl_order_n, nb1));
+      }
+      std::vector<int32_t> st;
+      rc = run_batch(h, ms_left() < 0 ? 0 : std::max<int64_t>(ms_left(), 1), st);
       if (rc != KP_OK) return rc;
-      int32_t status = 0;
-      CK(cudaMemcpy(&status, h->cur->dev.status, 4, cudaMemcpyDeviceToHost));
-      if (status != KP_OK) return h->err = "consolidation simulation failed", status;
       total_ms += h->stats.solve_ms;
-      k_decide<<<1, 32, 0, h->stream>>>(h->cur->dev, q, sn, d_snodes, 0);
+      bool chunk_timed_out = false;
+      for (int32_t v : st) {
+        if (v == KP_DEADLINE)
+          chunk_timed_out = true;
+        else if (v != KP_OK)
+          return h->err = "consolidation simulation failed", v;
+      }
+      if (chunk_timed_out) {  // partial simulations decide nothing (the reference drops the whole pass on ctx.Err())
+        timed_out = true;
+        break;
+      }
+      k_decide_batch<<<nb, 32, 0, h->stream>>>(h->d_batch_devs, q, d_soff, d_snodes);
       CK(cudaStreamSynchronize(h->stream));
       CK(cudaGetLastError());
-      CK(cudaMemcpy(out->decision + s, q.decision, 1, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(out->replacement_its + (size_t)s * ITW, q.replacement_its, (size_t)ITW * 8, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(out->n_new_claims + s, q.n_new_claims, 4, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(out->n_unscheduled + s, q.n_unscheduled, 4, cudaMemcpyDeviceToHost));
+      std::vector<uint8_t> dec(nb), sfl(nb1 * K);
+      std::vector<uint64_t> rep(nb1 * std::max(ITW, 1)), smk(nb1 * K);
+      std::vector<int32_t> nn(nb), nu(nb), rt(nb), on(nb), ord;
+      std::vector<int64_t> rq(nb1 * R), sg, sl;
+      CK(cudaMemcpy(dec.data(), q.decision, nb1, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(rep.data(), q.replacement_its, nb1 * ITW * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(nn.data(), q.n_new_claims, nb1 * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(nu.data(), q.n_unscheduled, nb1 * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(rt.data(), q.repl_tmpl, nb1 * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(rq.data(), q.repl_req, nb1 * R * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(sfl.data(), q.repl_sflags, nb1 * K, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(smk.data(), q.repl_smask, nb1 * K * 8, cudaMemcpyDeviceToHost));
+      if (t.has_bounds) {
+        sg.resize(nb1 * K);
+        sl.resize(nb1 * K);
+        CK(cudaMemcpy(sg.data(), q.repl_sgte, nb1 * K * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(sl.data(), q.repl_slte, nb1 * K * 8, cudaMemcpyDeviceToHost));
+      }
+      if (in->export_price_order) {
+        ord.resize(nb1 * order_cap);
+        CK(cudaMemcpy(ord.data(), q.repl_order, nb1 * order_cap * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(on.data(), q.repl_order_n, nb1 * 4, cudaMemcpyDeviceToHost));
+      }
+      for (int b_ = 0; b_ < nb; b_++) {
+        const int s = set_of[b_];
+        out->decision[s] = dec[b_];
+        memcpy(out->replacement_its + (size_t)s * ITW, rep.data() + (size_t)b_ * ITW, (size_t)ITW * 8);
+        out->n_new_claims[s] = nn[b_];
+        out->n_unscheduled[s] = nu[b_];
+        out->repl_template[s] = rt[b_];
+        memcpy(out->repl_requests + (size_t)s * R, rq.data() + (size_t)b_ * R, (size_t)R * 8);
+        if (dec[b_] == KP_DECISION_REPLACE)
+          store_repl(s, sfl.data() + (size_t)b_ * K, smk.data() + (size_t)b_ * K, t.has_bounds ? sg.data() + (size_t)b_ * K : nullptr,
+                     t.has_bounds ? sl.data() + (size_t)b_ * K : nullptr);
+        if (in->export_price_order) order_rows[s].assign(ord.begin() + (size_t)b_ * order_cap, ord.begin() + (size_t)b_ * order_cap + on[b_]);
+      }
     }
+    batch_clear(h);
+    finish_order();
     out->solve_ms = total_ms;
     h->stats.solve_ms = total_ms;
-    return KP_OK;
+    return timed_out ? KP_DEADLINE : KP_OK;
   }
   int capq = 1;
   for (int s = 0; s < S; s++) {
@@ -1536,6 +1728,7 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
     }
     capq = std::max(capq, n);
   }
+  capq += n_extra;
   // ---- device inputs
   KpConsol q;
   memset(&q, 0, sizeof(q));
@@ -1550,6 +1743,15 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   CK(up_raw(h, &tmp32, in->node_pod_off, (size_t)E + 1));
   q.node_pod_off = tmp32;
   q.pod_class = h->cur->d_pod_class;
+  q.n_extra = n_extra;
+  q.extra_row0 = (int)extra_row0;
+  if (n_extra > 0) {
+    uint8_t* dk;
+    CK(up_raw(h, &dk, in->extra_pod_kind, (size_t)n_extra));
+    q.extra_kind = dk;
+  }
+  q.deadline_ns = deadline_ms > 0 ? std::max<int64_t>(ms_left(), 1) * 1000000ll : 0;
+  CK(zeros(h, &q.t_start, 1));
   CK(zeros(h, &tmp32, (size_t)std::max<int64_t>(h->cur->P, 1)));
   int32_t* d_rank = tmp32;
   q.pod_rank = d_rank;
@@ -1584,6 +1786,7 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   CK(zeros(h, &q.last_len, slots * cq));
   CK(zeros(h, &q.clsl, slots * cq));
   CK(zeros(h, &q.rk, slots * cq));
+  if (n_extra > 0) CK(zeros(h, &q.kindl, slots * cq));
   CK(zeros(h, &q.c_tmpl, slots * cq));
   CK(zeros(h, &q.c_npods, slots * cq));
   CK(zeros(h, &q.order, slots * cq));
@@ -1614,6 +1817,20 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   CK(zeros(h, &q.replacement_its, (size_t)std::max(S, 1) * std::max(ITW, 1)));
   CK(zeros(h, &q.n_new_claims, (size_t)std::max(S, 1)));
   CK(zeros(h, &q.n_unscheduled, (size_t)std::max(S, 1)));
+  const size_t S1 = (size_t)std::max(S, 1);
+  CK(zeros(h, &q.repl_tmpl, S1));
+  CK(zeros(h, &q.repl_req, S1 * std::max(R, 1)));
+  CK(zeros(h, &q.repl_sflags, S1 * std::max(K, 1)));
+  CK(zeros(h, &q.repl_smask, S1 * std::max(K, 1)));
+  if (t.has_bounds) {
+    CK(zeros(h, &q.repl_sgte, S1 * std::max(K, 1)));
+    CK(zeros(h, &q.repl_slte, S1 * std::max(K, 1)));
+  }
+  if (in->export_price_order) {
+    CK(zeros(h, &q.repl_order, S1 * order_cap));
+    CK(zeros(h, &q.repl_order_n, S1));
+  }
+  CK(cudaMemsetAsync(q.decision, KP_DECISION_UNKNOWN, S1, h->stream));  // a subset the deadline cut off stays unknown
   CK(zeros(h, &q.next, 1));
   CK(zeros(h, &q.status, 1));
   rc = reset_dynamic(h);
@@ -1650,23 +1867,46 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   if (status != KP_OK) return h->err = "consolidation instance failed (capacity or invalid state)", status;
   // ---- results
   auto t0 = std::chrono::steady_clock::now();
-  out->n_subsets = S;
-  out->it_words = ITW;
-  out->decision = (uint8_t*)calloc(S ? S : 1, 1);
-  out->replacement_its = (uint64_t*)calloc((size_t)(S ? S : 1) * (ITW ? ITW : 1), sizeof(uint64_t));
-  out->n_new_claims = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
-  out->n_unscheduled = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
   CK(cudaMemcpy(out->decision, q.decision, (size_t)S, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(out->replacement_its, q.replacement_its, (size_t)S * ITW * 8, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(out->n_new_claims, q.n_new_claims, (size_t)S * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(out->n_unscheduled, q.n_unscheduled, (size_t)S * 4, cudaMemcpyDeviceToHost));
-  out->solve_ms = ms;
-  h->stats.bytes_d2h = (size_t)S * (9 + (size_t)ITW * 8);
-  h->stats.download_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  for (int s = 0; s < S; s++)
-    if (out->decision[s] == 255) {
-      kp_consol_result_free(out);
-      return h->err = "internal: unknown consolidation decision", KP_ERR_INVALID;
+  CK(cudaMemcpy(out->repl_template, q.repl_tmpl, (size_t)S * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out->repl_requests, q.repl_req, (size_t)S * R * 8, cudaMemcpyDeviceToHost));
+  {
+    std::vector<uint8_t> sfl((size_t)S1 * K);
+    std::vector<uint64_t> smk((size_t)S1 * K);
+    std::vector<int64_t> sg, sl;
+    CK(cudaMemcpy(sfl.data(), q.repl_sflags, (size_t)S * K, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(smk.data(), q.repl_smask, (size_t)S * K * 8, cudaMemcpyDeviceToHost));
+    if (t.has_bounds) {
+      sg.resize((size_t)S1 * K);
+      sl.resize((size_t)S1 * K);
+      CK(cudaMemcpy(sg.data(), q.repl_sgte, (size_t)S * K * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(sl.data(), q.repl_slte, (size_t)S * K * 8, cudaMemcpyDeviceToHost));
     }
+    for (int s_ = 0; s_ < S; s_++)
+      if (out->decision[s_] == KP_DECISION_REPLACE)
+        store_repl(s_, sfl.data() + (size_t)s_ * K, smk.data() + (size_t)s_ * K, t.has_bounds ? sg.data() + (size_t)s_ * K : nullptr,
+                   t.has_bounds ? sl.data() + (size_t)s_ * K : nullptr);
+      else
+        out->repl_template[s_] = -1;
+  }
+  if (in->export_price_order) {
+    std::vector<int32_t> ord((size_t)S1 * order_cap), on(S1);
+    CK(cudaMemcpy(ord.data(), q.repl_order, (size_t)S * order_cap * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(on.data(), q.repl_order_n, (size_t)S * 4, cudaMemcpyDeviceToHost));
+    for (int s_ = 0; s_ < S; s_++) order_rows[s_].assign(ord.begin() + (size_t)s_ * order_cap, ord.begin() + (size_t)s_ * order_cap + on[s_]);
+    finish_order();
+  }
+  out->solve_ms = ms;
+  h->stats.bytes_d2h = (size_t)S * (13 + (size_t)ITW * 8 + (size_t)R * 8 + (size_t)K * 9);
+  h->stats.download_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  bool unknown = false;
+  for (int s_ = 0; s_ < S; s_++) unknown = unknown || out->decision[s_] == KP_DECISION_UNKNOWN;
+  if (unknown) {
+    if (deadline_ms > 0) return KP_DEADLINE;  // the subsets that finished are valid
+    return h->err = "internal: a candidate set was not evaluated", KP_ERR_INVALID;
+  }
   return KP_OK;
 }

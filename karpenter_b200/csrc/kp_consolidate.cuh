@@ -166,6 +166,7 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     I.last_len = d.last_len;
     I.pod_target = d.pod_target;
     I.pod_error = d.pod_error;
+    I.pod_kind = d.pod_kind;
     I.Cmax = Cmax;
     I.c_tmpl = d.c_tmpl;
     I.c_npods = d.c_npods;
@@ -308,8 +309,15 @@ struct KpConsol {
   double* sort_key;              // [slots * T]
   int32_t* sort_val;             // [slots * T]
   unsigned long long* sort_bits; // [slots * ITW]
-  int ct_key, ct_spot, ct_order_valid;  // bit i of ct_order_valid: ct_order[i] is interned
+  int ct_key, ct_spot, ct_od, ct_order_valid;  // bit i of ct_order_valid: ct_order[i] is interned
   int spot_to_spot_enabled;
+  // pods every simulation schedules besides the candidates' (helpers.go:65-91): rows extra_row0 .. extra_row0+n_extra-1
+  int n_extra, extra_row0;
+  const uint8_t* extra_kind;     // [n_extra] KP_EXTRA_*
+  uint8_t* kindl;                // per warp slot [capq]: kind of local pod i (0: candidate pod)
+  // context deadline: the first warp to start stamps t_start; a warp that finds deadline_ns used up stops pulling work
+  long long deadline_ns;
+  unsigned long long* t_start;
   // per warp slot scratch
   int capq;                      // pods / claims / overlay entries an instance can hold
   int32_t *queue, *qcls, *last_len, *clsl, *rk;
@@ -334,6 +342,16 @@ struct KpConsol {
   uint64_t* replacement_its;     // [n_subsets * ITW]
   int32_t* n_new_claims;
   int32_t* n_unscheduled;
+  // the replacement NodeClaim of a REPLACE: template, requests, requirement slots after the capacity-type pins
+  int32_t* repl_tmpl;            // [n_subsets]
+  int64_t* repl_req;             // [n_subsets * R]
+  uint8_t* repl_sflags;          // [n_subsets * K]
+  uint64_t* repl_smask;
+  int64_t *repl_sgte, *repl_slte;
+  int export_order;              // also write the price order of the replacement's instance types
+  int32_t* repl_order;           // [n_subsets * order_cap] (order_cap = min(T, 600)), repl_order_n[s] entries used
+  int32_t* repl_order_n;
+  int order_cap;
   int32_t* next;                 // work counter
   int32_t* status;
 };
@@ -358,11 +376,14 @@ __device__ __forceinline__ unsigned offering_ok_mask(const KpDev& d, const Slot*
 // types) is read through the c_* pointers.  One warp; `slot` selects the warp's sort scratch in q; result row `s`.
 __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q, size_t slot, Slot* scratch,
                                               const uint8_t* c_sflags, const uint64_t* c_smask, const int64_t* c_sgte,
-                                              const int64_t* c_slte, const uint64_t* c_its, int sn, const int32_t* snodes,
-                                              int unscheduled, int n_new, int s, int lane) {
+                                              const int64_t* c_slte, const uint64_t* c_its, int c_tmpl0, const int64_t* c_req0,
+                                              int sn, const int32_t* snodes, int unscheduled, int n_new, int s, int lane) {
   const int K = d.K, ITW = d.ITW;
   int decision = KP_DECISION_NOOP;
   uint64_t rep = 0;  // lane w: word w of the replacement instance types
+  bool have_slots = false;  // scratch[] holds the claim's requirement slots (with the spot pin when it applied)
+  bool spot_pinned = false;
+  int n_ord_out = 0;
   if (!unscheduled) {
     if (n_new == 0) {
       decision = KP_DECISION_DELETE;
@@ -391,6 +412,7 @@ __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q,
       }
       if (lane < K) scratch[lane] = S;
       __syncwarp();
+      have_slots = true;
       unsigned okmask = offering_ok_mask(d, scratch, lane);
       const bool spot_path = all_spot && spot_ok;
       uint64_t cur = its;  // lane w: word w of the NodeClaim's instance types as they go through the steps below
@@ -400,7 +422,7 @@ __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q,
       int32_t* sv = q.sort_val + slot * (size_t)q.T;
       unsigned long long* sb = q.sort_bits + slot * (size_t)ITW;
       int n_ord = 0;
-      const bool need_order = n_its > 600 || (spot_path && q.spot_to_spot_enabled);
+      const bool need_order = n_its > 600 || (spot_path && q.spot_to_spot_enabled) || q.export_order;
       if (need_order) {
         const int cw = lane < ITW ? __popcll(cur) : 0;
         int pre = cw;
@@ -442,6 +464,7 @@ __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q,
         if (spot_path) {  // restrict the claim to spot (consolidation.go:252-257) and drop types without such an offering
           if (lane == q.ct_key)
             scratch[lane] = slot_add(key_info(d, lane), scratch[lane], Slot{SF_PRESENT, 1ull << q.ct_spot, 0, 0});
+          spot_pinned = true;
           __syncwarp();
           okmask = offering_ok_mask(d, scratch, lane);
           uint64_t keep = 0;
@@ -542,11 +565,53 @@ __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q,
           }
         }
         if (any) decision = KP_DECISION_REPLACE;
+        if (any && q.export_order && q.repl_order) {
+          // the surviving types in OrderByPrice order (sv[] holds the claim's types by price; ties as Go leaves them)
+          if (lane < ITW) sb[lane] = rep;
+          __syncwarp();
+          int32_t* dst = q.repl_order + (size_t)s * q.order_cap;
+          for (int b0 = 0; b0 < n_ord; b0 += 32) {
+            const int i = b0 + lane;
+            const int t = i < n_ord ? sv[i] : 0;
+            const bool in = i < n_ord && ((sb[t >> 6] >> (t & 63)) & 1ull);
+            const unsigned m = __ballot_sync(FULL, in);
+            const int at = n_ord_out + __popc(m & ((1u << lane) - 1));
+            if (in && at < q.order_cap) dst[at] = t;
+            n_ord_out += __popc(m);
+          }
+          if (n_ord_out > q.order_cap) n_ord_out = q.order_cap;
+        }
       }
     }
   }
   if (decision != KP_DECISION_REPLACE) rep = 0;
   if (lane < ITW) q.replacement_its[(size_t)s * ITW + lane] = rep;
+  if (q.repl_tmpl) {  // Command.Replacements: the NodeClaim itself (consolidation.go:206-229)
+    const bool repl = decision == KP_DECISION_REPLACE && have_slots;
+    Slot F = slot_absent();
+    if (repl && lane < K) {
+      F = scratch[lane];
+      // OD -> [OD, spot]: the price filter assumed the spot variant launches, so the claim is pinned to spot (:211-214)
+      if (!spot_pinned && lane == q.ct_key && q.ct_spot >= 0 && q.ct_od >= 0) {
+        const KeyInfo ki = key_info(d, lane);
+        if (slot_has(ki, F, q.ct_spot) && slot_has(ki, F, q.ct_od)) F = slot_add(ki, F, Slot{SF_PRESENT, 1ull << q.ct_spot, 0, 0});
+      }
+    }
+    if (lane < K) {
+      const size_t i = (size_t)s * K + lane;
+      q.repl_sflags[i] = (uint8_t)F.f;
+      q.repl_smask[i] = F.m;
+      if (q.repl_sgte) {
+        q.repl_sgte[i] = F.gte;
+        q.repl_slte[i] = F.lte;
+      }
+    }
+    if (lane < d.R) q.repl_req[(size_t)s * d.R + lane] = repl ? c_req0[lane] : 0;
+    if (lane == 0) {
+      q.repl_tmpl[s] = repl ? c_tmpl0 : -1;
+      if (q.repl_order_n) q.repl_order_n[s] = repl ? n_ord_out : 0;
+    }
+  }
   if (lane == 0) {
     q.decision[s] = (uint8_t)decision;
     q.n_new_claims[s] = n_new;
@@ -632,8 +697,26 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolid
   __syncwarp();
   int32_t* clsl = q.clsl + slot * capq;
   int32_t* rk = q.rk + slot * capq;
+  uint8_t* kindl = q.n_extra > 0 ? q.kindl + slot * capq : nullptr;
+  if (lane == 0) I.pod_kind = kindl;
+  unsigned long long t0 = 0;
+  if (q.deadline_ns > 0) {
+    if (lane == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      t0 = atomicCAS(q.t_start, 0ull, now);
+      if (t0 == 0) t0 = now;
+    }
+    t0 = __shfl_sync(FULL, t0, 0);
+  }
 
   for (;;) {
+    if (q.deadline_ns > 0) {  // context deadline (helpers.go / consolidation timeouts): finished subsets stay valid
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      now = __shfl_sync(FULL, now, 0);
+      if ((long long)(now - t0) > q.deadline_ns) break;
+    }
     int s = 0;
     if (lane == 0) s = atomicAdd(q.next, 1);
     s = __shfl_sync(FULL, s, 0);
@@ -654,6 +737,17 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolid
       }
       n += b - a;
     }
+    const int n_cand_pods = n;
+    for (int j = lane; j < q.n_extra; j += 32) {  // pending pods + pods of deleting nodes (helpers.go:65-91)
+      const int o = n + j;
+      if (o < capq) {
+        clsl[o] = q.pod_class[q.extra_row0 + j];
+        rk[o] = q.pod_rank[q.extra_row0 + j];
+      }
+    }
+    n += q.n_extra;
+    if (kindl)
+      for (int i = lane; i < n && i < capq; i += 32) kindl[i] = i < n_cand_pods ? 0 : q.extra_kind[i - n_cand_pods];
     if (n > capq) {
       if (lane == 0) *q.status = KP_ERR_CAPACITY;
       break;
@@ -688,17 +782,21 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolid
       break;
     }
     // ---- computeConsolidation (consolidation.go:136-229)
-    consol_decide(d, q, slot, W.scratch, I.c_sflags, I.c_smask, I.c_sgte, I.c_slte, I.c_its, sn, snodes,
-                  I.n_unsched + I.n_uninit, I.n_claims, s, lane);
+    consol_decide(d, q, slot, W.scratch, I.c_sflags, I.c_smask, I.c_sgte, I.c_slte, I.c_its, I.n_claims > 0 ? I.c_tmpl[0] : -1,
+                  I.c_req, sn, snodes, I.n_unsched + I.n_uninit, I.n_claims, s, lane);
   }
 }
 
 // The general consolidation path (evicted pods carry topology constraints): every candidate set is a full
-// Scheduler.Solve of its own (fresh NewTopology, k_wsolve); this kernel then applies computeConsolidation to it.
-__global__ void __launch_bounds__(32) k_decide(KpDev d, KpConsol q, int sn, const int32_t* snodes, int s) {
+// Scheduler.Solve of its own (fresh NewTopology) -- all sets of a chunk run as ONE k_wsolve_batch launch, one CTA each --
+// and this kernel then applies computeConsolidation to every instance: block b = instance b = result row b.
+__global__ void __launch_bounds__(32) k_decide_batch(const KpDev* __restrict__ devs, KpConsol q, const int32_t* __restrict__ soff,
+                                                     const int32_t* __restrict__ snodes) {
   __shared__ Slot scratch[KP_MAXK];
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x, b = blockIdx.x;
+  const KpDev& d = devs[b];
   const int unscheduled = (int)(d.counters[7] + d.counters[8]);
-  consol_decide(d, q, 0, scratch, d.c_sflags, d.c_smask, d.c_sgte, d.c_slte, d.c_its, sn, snodes, unscheduled, *d.n_claims, s,
-                lane);
+  const int n_new = *d.n_claims;
+  consol_decide(d, q, (size_t)b, scratch, d.c_sflags, d.c_smask, d.c_sgte, d.c_slte, d.c_its, n_new > 0 ? d.c_tmpl[0] : -1,
+                d.c_req, soff[b + 1] - soff[b], snodes + soff[b], unscheduled, n_new, b, lane);
 }

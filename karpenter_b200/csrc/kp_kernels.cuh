@@ -202,7 +202,7 @@ __device__ __forceinline__ void host_record(const KpDev& d, int row, int g, int 
     *w = cur | bit;
     d.g_nempty[g]--;
   }
-  atomicAdd(d.host_cnt + (size_t)row * d.H + host, 1);
+  atomicAdd(d.host_cnt + (size_t)host * d.GHS + row, 1);
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -309,7 +309,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
       bool self = (e >> 30) & 1;
       if (G.key == d.hostname_key) {
         if (lane == 0) {  // candidates carry exactly one hostname: the fast paths of topologygroup.go:235-247,317-333,402-408
-          int cnt = __ldcg(d.host_cnt + (size_t)G.host_row * d.H + host);
+          int cnt = __ldcg(d.host_cnt + (size_t)host * d.GHS + G.host_row);
           bool ok;
           if (G.type == KP_TOPO_SPREAD)
             ok = cnt + (self ? 1 : 0) <= G.max_skew;
@@ -401,6 +401,14 @@ __device__ __forceinline__ void store_class_regs(const KpDev& d, PodCtx& px, con
   const int moff = __shfl_sync(FULL, c.hdr, 2), mend = __shfl_sync(FULL, c.hdr, 3);
   const int roff = __shfl_sync(FULL, c.hdr, 4), rend = __shfl_sync(FULL, c.hdr, 5);
   const int nm = mend - moff, nr = rend - roff;
+  if (nm == 0 && nr == 0) {  // topology-free class: nothing to park
+    if (lane == 0) {
+      px.n_mg = 0;
+      px.n_rg = 0;
+      px.n_hc = 0;
+    }
+    return;
+  }
   const bool sm = nm <= KP_PG, sr = nr <= KP_PG;
   int e = 0, g = 0;
   if (sm && lane < nm) e = d.cls_match[moff + lane];

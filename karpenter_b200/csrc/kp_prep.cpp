@@ -103,9 +103,98 @@ struct HGroup {
 
 }  // namespace
 
+// One O(input) pass over everything the encoder indexes with: a buggy caller gets KP_ERR_INVALID and a message, not a
+// corrupted controller process.  (Counts, CSR offsets monotone and inside their arrays, every id inside its table.)
+static int validate_problem(const kp_problem* p, std::string& err) {
+#define KP_BAD(msg) return err = std::string("invalid problem: ") + msg, KP_ERR_INVALID
+  auto csr = [](const int32_t* off, int64_t n, int64_t limit) {
+    if (n == 0) return true;
+    if (!off || off[0] != 0) return false;
+    for (int64_t i = 0; i < n; i++)
+      if (off[i + 1] < off[i]) return false;
+    return limit < 0 || off[n] <= limit;
+  };
+  auto in = [](int64_t v, int64_t n) { return v >= 0 && v < n; };
+  if (p->n_keys < 0 || p->n_reqsets < 0 || p->n_reqs < 0 || p->n_resources < 0 || p->n_its < 0 || p->n_templates < 0 ||
+      p->n_classes < 0 || p->n_pods < 0 || p->n_nodes < 0 || p->n_running < 0 || p->n_taints < 0 || p->n_taintsets < 0 ||
+      p->n_tolerations < 0 || p->n_tolsets < 0 || p->n_labelsets < 0 || p->n_selectors < 0 || p->n_nssets < 0 ||
+      p->n_tt_strings < 0 || p->n_minvalue_keys < 0)
+    KP_BAD("negative count");
+  if (p->n_keys > 0 && (!p->key_flags || !csr(p->key_value_off, p->n_keys, -1))) KP_BAD("key_value_off");
+  const int64_t n_values = p->n_keys > 0 ? p->key_value_off[p->n_keys] : 0;
+  (void)n_values;
+  if (!csr(p->reqset_off, p->n_reqsets, p->n_reqs) || (p->n_reqsets > 0 && p->reqset_off[p->n_reqsets] != p->n_reqs)) KP_BAD("reqset_off");
+  if (p->n_reqs > 0 && (!p->req_key || !p->req_flags || !csr(p->req_val_off, p->n_reqs, -1))) KP_BAD("req_val_off");
+  for (int i = 0; i < p->n_reqs; i++) {
+    if (!in(p->req_key[i], p->n_keys)) KP_BAD("req_key out of range");
+    const int nv = p->key_value_off[p->req_key[i] + 1] - p->key_value_off[p->req_key[i]];
+    for (int e = p->req_val_off[i]; e < p->req_val_off[i + 1]; e++)
+      if (!in(p->req_vals[e], nv)) KP_BAD("req_vals: value id outside its key");
+  }
+  if (!csr(p->taintset_off, p->n_taintsets, -1) || !csr(p->tolset_off, p->n_tolsets, -1)) KP_BAD("taintset_off / tolset_off");
+  for (int i = 0; i < (p->n_taintsets ? p->taintset_off[p->n_taintsets] : 0); i++)
+    if (!in(p->taintset_ids[i], p->n_taints)) KP_BAD("taintset_ids");
+  for (int i = 0; i < (p->n_tolsets ? p->tolset_off[p->n_tolsets] : 0); i++)
+    if (!in(p->tolset_ids[i], p->n_tolerations)) KP_BAD("tolset_ids");
+  for (int i = 0; i < p->n_taints; i++)
+    if (!in(p->taint_key[i], p->n_tt_strings) || !in(p->taint_value[i], p->n_tt_strings)) KP_BAD("taint strings");
+  for (int i = 0; i < p->n_tolerations; i++)
+    if (!in(p->tol_key[i], p->n_tt_strings) || !in(p->tol_value[i], p->n_tt_strings)) KP_BAD("toleration strings");
+  if (!csr(p->it_off_off, p->n_its, -1)) KP_BAD("it_off_off");
+  const int n_off = p->n_its ? p->it_off_off[p->n_its] : 0;
+  for (int i = 0; i < p->n_its; i++)
+    if (!in(p->it_reqset[i], p->n_reqsets)) KP_BAD("it_reqset");
+  for (int i = 0; i < n_off; i++)
+    if (!in(p->off_reqset[i], p->n_reqsets)) KP_BAD("off_reqset");
+  if (!csr(p->tmpl_it_off, p->n_templates, -1)) KP_BAD("tmpl_it_off");
+  for (int n = 0; n < p->n_templates; n++) {
+    if (!in(p->tmpl_reqset[n], p->n_reqsets)) KP_BAD("tmpl_reqset");
+    if (p->tmpl_taintset[n] < -1 || p->tmpl_taintset[n] >= p->n_taintsets) KP_BAD("tmpl_taintset");
+    for (int i = p->tmpl_it_off[n]; i < p->tmpl_it_off[n + 1]; i++)
+      if (!in(p->tmpl_its[i], p->n_its)) KP_BAD("tmpl_its");
+  }
+  if (!csr(p->labelset_off, p->n_labelsets, -1) || !csr(p->selector_off, p->n_selectors, -1) || !csr(p->nsset_off, p->n_nssets, -1))
+    KP_BAD("labelset_off / selector_off / nsset_off");
+  if (p->n_selectors > 0 && !csr(p->selx_val_off, p->selector_off[p->n_selectors], -1)) KP_BAD("selx_val_off");
+  if (p->n_classes > 0 && (!csr(p->class_filter_off, p->n_classes, -1) || !csr(p->class_tsc_off, p->n_classes, -1)))
+    KP_BAD("class_filter_off / class_tsc_off");
+  for (int x = 0; x < p->n_classes; x++) {
+    if (!in(p->class_reqset[x], p->n_reqsets) || !in(p->class_strict_reqset[x], p->n_reqsets)) KP_BAD("class_reqset");
+    if (p->class_tolset[x] < -1 || p->class_tolset[x] >= p->n_tolsets) KP_BAD("class_tolset");
+    if (p->class_labelset[x] < -1 || p->class_labelset[x] >= p->n_labelsets) KP_BAD("class_labelset");
+    for (int i = p->class_filter_off[x]; i < p->class_filter_off[x + 1]; i++)
+      if (!in(p->class_filter_reqsets[i], p->n_reqsets)) KP_BAD("class_filter_reqsets");
+    if (p->class_relax_next && (p->class_relax_next[x] < -1 || p->class_relax_next[x] >= p->n_classes)) KP_BAD("class_relax_next");
+    for (int i = p->class_tsc_off[x]; i < p->class_tsc_off[x + 1]; i++) {
+      if (!in(p->tsc_key[i], p->n_keys)) KP_BAD("tsc_key");
+      if (p->tsc_selector[i] < -1 || p->tsc_selector[i] >= p->n_selectors) KP_BAD("tsc_selector");
+      if (p->tsc_nsset[i] < -1 || p->tsc_nsset[i] >= p->n_nssets) KP_BAD("tsc_nsset");
+      if (p->tsc_type[i] > KP_TOPO_ANTI_AFFINITY) KP_BAD("tsc_type");
+    }
+  }
+  for (int64_t i = 0; i < p->n_pods; i++)
+    if (!in(p->pod_class[i], p->n_classes)) KP_BAD("pod_class");
+  for (int n = 0; n < p->n_nodes; n++) {
+    if (!in(p->node_reqset[n], p->n_reqsets)) KP_BAD("node_reqset");
+    if (p->node_taintset[n] < -1 || p->node_taintset[n] >= p->n_taintsets) KP_BAD("node_taintset");
+    if (p->node_template && (p->node_template[n] < -1 || p->node_template[n] >= p->n_templates)) KP_BAD("node_template");
+  }
+  for (int64_t i = 0; i < p->n_running; i++)
+    if (!in(p->run_class[i], p->n_classes) || !in(p->run_node[i], p->n_nodes)) KP_BAD("run_class / run_node");
+  for (int m = 0; m < p->n_minvalue_keys; m++)
+    if (!in(p->minvalue_key[m], p->n_keys)) KP_BAD("minvalue_key");
+  if (p->n_minvalue_keys > 0 && !csr(p->minvalue_it_off, (int64_t)p->n_minvalue_keys * p->n_its, -1)) KP_BAD("minvalue_it_off");
+#undef KP_BAD
+  return KP_OK;
+}
+
 int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
                const std::vector<std::pair<int, int>>& extra_bound, const std::vector<int32_t>& pending_classes,
                HostTables& h, std::string& err) {
+  {
+    int rc = validate_problem(p, err);
+    if (rc != KP_OK) return rc;
+  }
   Ctx c(p, h);
   const int K = p->n_keys, R = p->n_resources, T = p->n_its, N = p->n_templates, X = p->n_classes, E = p->n_nodes;
   if (K > KP_MAXK) return err = "more than 32 active label keys", KP_ERR_CAPACITY;

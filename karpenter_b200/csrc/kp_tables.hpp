@@ -146,8 +146,11 @@ struct KpDev {
   uint64_t* dom_pop;              // [G] domains with count > 0 (complement of t.emptyDomains within dom_reg)
   int32_t* g_ndomains;            // [G] hostname groups: len(t.domains)
   int32_t* g_nempty;              // [G] hostname groups: len(t.emptyDomains)
-  int32_t* host_cnt;              // [GH * H] per hostname group x host (existing nodes then claims); updated with RED,
-                                  // read with ld.cg (never through L1)
+  int32_t* host_cnt;              // [H * GHS] HOST-major (existing nodes then claims), GHS = max(GH, 1) ints per host: only
+                                  // the rows of hosts that exist are ever touched, so the footprint (and the TLB reach it
+                                  // needs) follows the NodeClaims opened, not the capacity provisioned for them.
+                                  // Updated with RED, read with ld.cg (never through L1)
+  int GHS;
   uint32_t* host_pop;             // [GH * HW] bit (group, host): count > 0 -- what anti-affinity / affinity checks read;
                                   // two cache lines per group and 1 000 NodeClaims, prefetched by the stager warp
   int HW;                         // words per host_pop row = ceil(H / 32)
@@ -199,6 +202,7 @@ struct KpDev {
   int32_t* last_len;              // [P]
   int32_t* pod_target;            // [P]
   uint8_t* pod_error;             // [P]
+  const uint8_t* pod_kind;        // [P] or null: 0 candidate pod, KP_EXTRA_* (consolidation simulations, helpers.go:65-140)
   // scalars out
   int32_t* n_claims;              // [1]
   int64_t* counters;              // [8] existing evals, inflight evals, template evals, commits, slow sorts, ...

@@ -28,6 +28,7 @@ struct WInst {
   int32_t* last_len;    // [P]
   int32_t* pod_target;  // [P] or null
   uint8_t* pod_error;   // [P] or null
+  const uint8_t* pod_kind;  // [P] or null (all 0): see KpDev::pod_kind
   // NodeClaims
   int Cmax;
   int32_t *c_tmpl, *c_npods;
@@ -265,10 +266,10 @@ __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, co
         const int hi = E + c[u];
         ca[u] = cb[u] = 0;
         if (pass[u]) {
-          ca[u] = cnt_a ? __ldcg(d.host_cnt + (size_t)ha.x * d.H + hi)
+          ca[u] = cnt_a ? __ldcg(d.host_cnt + (size_t)hi * d.GHS + ha.x)
                         : (int)((d.host_pop[(size_t)ha.x * d.HW + (hi >> 5)] >> (hi & 31)) & 1u);
           if (two)
-            cb[u] = cnt_b ? __ldcg(d.host_cnt + (size_t)hb.x * d.H + hi)
+            cb[u] = cnt_b ? __ldcg(d.host_cnt + (size_t)hi * d.GHS + hb.x)
                           : (int)((d.host_pop[(size_t)hb.x * d.HW + (hi >> 5)] >> (hi & 31)) & 1u);
         }
       }
@@ -348,36 +349,56 @@ struct StageRing {
 
 __device__ void stager_run(const KpDev& d, const WInst& I, StageRing* ring, const int lane) {
   const int cap = I.P + 1;
-  int qi = 0;
-  for (int idx = 0;; idx++) {
+  // The queue is read 32 entries at a time (one coalesced load; entries below tail_pub never change), and the class row
+  // of pod i+1 is requested before pod i is parked, so the stager pays one L2 latency per pod at most -- it has to stay
+  // ahead of a solver that needs under 2 us per pod.
+  for (int base = 0;;) {
+    int avail;
     for (;;) {
       if (ring->done) return;
-      if (idx < ring->tail_pub && idx - ring->consumed < KP_RING) break;
+      avail = ring->tail_pub - base;
+      if (avail > 0) break;
       __nanosleep(64);
     }
     __threadfence_block();
-    const int li = __ldcg(I.queue + qi), X = __ldcg(I.qcls + qi);
-    qi = qi + 1 >= cap ? 0 : qi + 1;
-    ClassRegs c = load_class_regs(d, X, li, lane);
-    PodCtx& slot = ring->slot[idx & (KP_RING - 1)];
-    store_class_regs(d, slot, c, lane);
-    __syncwarp();
-    // pull what the solver will read for this pod into L1 now: the presence rows of its hostname groups (the part that
-    // covers the NodeClaims: 8 lines == 8 192 claims) and the counter rows of its topology-key groups
-    if (slot.n_hc > 0) {
-      const int g8 = lane >> 3, l8 = lane & 7;  // four groups at a time, eight lines each
-      for (int i = g8; i < slot.n_hc; i += 4) {
-        const int w = (d.E >> 5) + l8 * 32;
-        if (w < d.HW) prefetch_l1(d.host_pop + (size_t)slot.hc[i].x * d.HW + w);
+    if (avail > 32) avail = 32;
+    int li = 0, X = 0;
+    if (lane < avail) {
+      const int qi = (base + lane) % cap;
+      li = __ldcg(I.queue + qi);
+      X = __ldcg(I.qcls + qi);
+    }
+    ClassRegs nxt = load_class_regs(d, __shfl_sync(FULL, X, 0), __shfl_sync(FULL, li, 0), lane);
+    for (int i = 0; i < avail; i++) {
+      const int idx = base + i;
+      const ClassRegs c = nxt;
+      if (i + 1 < avail) nxt = load_class_regs(d, __shfl_sync(FULL, X, i + 1), __shfl_sync(FULL, li, i + 1), lane);
+      for (;;) {
+        if (ring->done) return;
+        if (idx - ring->consumed < KP_RING) break;
+        __nanosleep(32);
       }
+      PodCtx& slot = ring->slot[idx & (KP_RING - 1)];
+      store_class_regs(d, slot, c, lane);
+      __syncwarp();
+      // pull what the solver will read for this pod into L1 now: the presence rows of its hostname groups (the part
+      // that covers the NodeClaims: 8 lines == 8 192 claims) and the counter rows of its topology-key groups
+      if (slot.n_hc > 0) {
+        const int g8 = lane >> 3, l8 = lane & 7;  // four groups at a time, eight lines each
+        for (int k = g8; k < slot.n_hc; k += 4) {
+          const int w = (d.E >> 5) + l8 * 32;
+          if (w < d.HW) prefetch_l1(d.host_pop + (size_t)slot.hc[k].x * d.HW + w);
+        }
+      }
+      if (slot.n_mg > 0 && lane < 2 * slot.n_mg) {
+        const KpGroup& G = slot.mg[lane >> 1];
+        if (G.key == d.tk_key) prefetch_l1(d.dom_cnt + G.dom_off + (lane & 1) * 32);
+      }
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) ring->produced = idx + 1;
     }
-    if (slot.n_mg > 0 && lane < 2 * slot.n_mg) {
-      const KpGroup& G = slot.mg[lane >> 1];
-      if (G.key == d.tk_key) prefetch_l1(d.dom_cnt + G.dom_off + (lane & 1) * 32);
-    }
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 0) ring->produced = idx + 1;
+    base += avail;
   }
 }
 
@@ -606,7 +627,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
                 I.pod_error[li] = KP_PODERR_NONE;
               }
             }
-            if (!(d.node_flags[node] & KP_NODE_INITIALIZED)) n_uninit++;  // helpers.go:121-140
+            // helpers.go:121-140: an uninitialized target is an error for a candidate's pod only
+            if (!(d.node_flags[node] & KP_NODE_INITIALIZED) && (!I.pod_kind || I.pod_kind[li] == 0)) n_uninit++;
             topo_record(d, px, ev.F, d.node_taintset[node], node, false, lane);
             ev_existing += node + 1;
             found = true;
@@ -1031,8 +1053,15 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
   }
   // len(Pods) of every claim is the count stored next to it in the claim order
   for (int i = lane; i < nC; i += 32) I.c_npods[ord[i]] = cnt[i];
-  // pods still queued when the loop ends are the PodErrors (scheduler.go:415-423)
+  // pods still queued when the loop ends are the PodErrors (scheduler.go:415-423); a simulation ignores the errors of
+  // provisionable pending pods (AllNonPendingPodsScheduled, scheduler.go:330-334)
   n_unsched = tail - head;
+  if (I.pod_kind && n_unsched > 0) {
+    int keep = 0;
+    for (int i = head + lane; i < tail; i += 32) keep += I.pod_kind[I.queue[i % cap]] != KP_EXTRA_PENDING;
+    for (int o = 16; o; o >>= 1) keep += __shfl_xor_sync(FULL, keep, o);
+    n_unsched = keep;
+  }
   if (lane == 0) {
     I.n_claims = nC;
     I.n_unsched = n_unsched;

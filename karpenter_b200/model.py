@@ -168,6 +168,10 @@ class Pod:
     # topology domains (nodeclaim.go:136-176).  One alternative is supported (a bound PV / one storage class).
     volume_requirements: List[List[NodeSelectorRequirement]] = field(default_factory=list)
     creation_timestamp: int = 0
+    # disruption cost inputs (utils/disruption/disruption.go:48-70): Spec.Priority and the
+    # controller.kubernetes.io/pod-deletion-cost annotation (None: absent)
+    priority: Optional[int] = None
+    deletion_cost: Optional[str] = None
 
 
 @dataclass
@@ -212,6 +216,10 @@ class StateNode:
     instance_type: Optional[str] = None
     pods: List[Pod] = field(default_factory=list)          # reschedulable pods bound to the node (consolidation)
     running_pods: List[Pod] = field(default_factory=list)  # other bound pods, only counted by the topology
+    # NodeClaim lifetime for LifetimeRemaining (utils/disruption/disruption.go:36-46): Spec.ExpireAfter in seconds
+    # (None: never) and the NodeClaim's age in seconds
+    expire_after_s: Optional[float] = None
+    age_s: float = 0.0
 
 
 @dataclass

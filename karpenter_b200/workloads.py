@@ -153,40 +153,82 @@ def config_c5(n_pods=10_000_000, n_pools=8, n_its=1000, app_replicas=1000, pools
     """C5: pods pinned to one of `n_pools` NodePools (selector + toleration of the pool's taint); half the pods carry
     the C2 constraint mix, half the C3 mix (apps never span pools).  `pools_subset` keeps only the pods (and pools) of
     the given pool indices -- the shard one rank owns when the job is split by NodePool."""
-    b = ProblemBuilder()
-    its = kwok.aws_instance_types(n_its)
-    for it in its:
-        b.add_instance_type(it)
-    pools = [f"pool-{i}" for i in range(n_pools)]
     keep = list(range(n_pools)) if pools_subset is None else list(pools_subset)
-    for i in keep:
-        b.add_nodepool(default_nodepool(pools[i], taints=[Taint(f"bench/{pools[i]}", "true", "NoSchedule")],
-                                        zones=kwok.AWS_ZONES[:3]), list(range(len(its))))
+    return config_c5_shards(n_pods, n_pools, n_its, app_replicas, [keep])[0]
+
+
+def config_c5_shards(n_pods=10_000_000, n_pools=8, n_its=1000, app_replicas=1000, pool_groups=None) -> List[EncodedProblem]:
+    """Several shards of C5 at once (one EncodedProblem per entry of `pool_groups`, default: one per pool): the pod
+    draws are computed once and shared, so building all 8 shards of the 10 M-pod job costs little more than one."""
+    pools = [f"pool-{i}" for i in range(n_pools)]
+    groups = [[i] for i in range(n_pools)] if pool_groups is None else [list(g) for g in pool_groups]
+    its = kwok.aws_instance_types(n_its)
+    zones = kwok.AWS_ZONES
+    archs = ["x86_64", "arm64"]
     half = n_pods // 2
-    cls_a, uid_a, pool_a = _c2_pods(b, half, None, SEED, pools)
+    # ---- C2 half: draws shared by every shard
+    d2 = draws(half, 8, SEED)
+    ci2, mi2 = (d2[:, 0] % np.uint64(5)).astype(np.int8), (d2[:, 1] % np.uint64(6)).astype(np.int8)
+    zsel = np.where(d2[:, 2] % np.uint64(2) == 0, (d2[:, 3] % np.uint64(4)).astype(np.int8), -1).astype(np.int8)
+    asel = np.where(d2[:, 4] % np.uint64(4) == 0, (d2[:, 5] % np.uint64(2)).astype(np.int8), -1).astype(np.int8)
+    t = (d2[:, 6] % np.uint64(40)).astype(np.int8)
+    tol = np.where(t < 2, 0, np.where(t % 2 == 0, 1, 2)).astype(np.int8)
+    pool_a = (np.arange(half) % n_pools).astype(np.int16)
+    uid_a_hi = d2[:, 7].copy()
+    uid_a_lo = splitmix64(SEED + 2, np.arange(half, dtype=np.uint64))
+    del d2
+    # ---- C3 half
     n_b = n_pods - half
     per_pool = n_b // n_pools
     n_apps_pool = max(1, per_pool // app_replicas)
-    d = draws(n_b, 4, SEED + 1)
-    ci, mi = (d[:, 0] % np.uint64(5)).astype(int), (d[:, 1] % np.uint64(6)).astype(int)
-    pool_b = np.arange(n_b) % n_pools
-    app_b = (np.arange(n_b) // n_pools) // app_replicas
-    app_b = np.minimum(app_b, n_apps_pool - 1)
-    cls_b = np.zeros(n_b, np.int32)
-    for pl in range(n_pools):
-        if pl not in keep:
-            continue
-        tbl = _app_classes(b, n_apps_pool, {NODEPOOL_LABEL: pools[pl]},
-                           [Toleration(f"bench/{pools[pl]}", "Exists", "", "")], prefix=f"p{pl}-app")
-        m = pool_b == pl
-        cls_b[m] = tbl[app_b[m], ci[m], mi[m]]
-    cls = np.concatenate([cls_a, cls_b])
-    uid_hi = np.concatenate([uid_a, d[:, 2]])
-    uid_lo = np.concatenate([splitmix64(SEED + 2, np.arange(half, dtype=np.uint64)), d[:, 3]])
-    pool = np.concatenate([pool_a, pool_b])
-    m = np.isin(pool, keep)
-    b.set_pod_arrays(cls[m], np.zeros(int(m.sum()), np.int64), uid_hi[m], uid_lo[m])
-    return b.build()
+    d3 = draws(n_b, 4, SEED + 1)
+    ci3, mi3 = (d3[:, 0] % np.uint64(5)).astype(np.int8), (d3[:, 1] % np.uint64(6)).astype(np.int8)
+    pool_b = (np.arange(n_b) % n_pools).astype(np.int16)
+    app_b = np.minimum((np.arange(n_b) // n_pools) // app_replicas, n_apps_pool - 1)
+    out = []
+    for keep in groups:
+        b = ProblemBuilder()
+        for it in its:
+            b.add_instance_type(it)
+        for i in keep:
+            b.add_nodepool(default_nodepool(pools[i], taints=[Taint(f"bench/{pools[i]}", "true", "NoSchedule")],
+                                            zones=kwok.AWS_ZONES[:3]), list(range(len(its))))
+        # class tables of the kept pools only
+        table2 = np.zeros((5, 6, 5, 3, 3, n_pools), np.int32)
+        for pl in keep:
+            key = f"bench/{pools[pl]}"
+            for c in range(5):
+                for m in range(6):
+                    for z in range(-1, 4):
+                        for a in range(-1, 2):
+                            for k in range(3):
+                                sel = {NODEPOOL_LABEL: pools[pl]}
+                                if z >= 0:
+                                    sel[ZONE_LABEL] = zones[z]
+                                if a >= 0:
+                                    sel[ARCH_LABEL] = archs[a]
+                                tols = []
+                                if k == 1:
+                                    tols = [Toleration(key, "Equal", "true", "NoSchedule")]
+                                elif k == 2:
+                                    tols = [Toleration(key, "Exists", "", "")]
+                                table2[c, m, z + 1, a + 1, k, pl] = b.pod_class(
+                                    Pod(requests=_requests(c, m), node_selector=sel, tolerations=tols))
+        ma = np.isin(pool_a, keep)
+        cls_a = table2[ci2[ma], mi2[ma], zsel[ma] + 1, asel[ma] + 1, tol[ma], pool_a[ma]]
+        mb = np.isin(pool_b, keep)
+        cls_b = np.zeros(int(mb.sum()), np.int32)
+        pb, ab, cb, mmb = pool_b[mb], app_b[mb], ci3[mb], mi3[mb]
+        for pl in keep:
+            tbl = _app_classes(b, n_apps_pool, {NODEPOOL_LABEL: pools[pl]},
+                               [Toleration(f"bench/{pools[pl]}", "Exists", "", "")], prefix=f"p{pl}-app")
+            m = pb == pl
+            cls_b[m] = tbl[ab[m], cb[m], mmb[m]]
+        cls = np.concatenate([cls_a, cls_b])
+        b.set_pod_arrays(cls, np.zeros(len(cls), np.int64), np.concatenate([uid_a_hi[ma], d3[mb, 2]]),
+                         np.concatenate([uid_a_lo[ma], d3[mb, 3]]))
+        out.append(b.build())
+    return out
 
 
 def config_c4(n_nodes=10_000, n_pods=200_000, n_candidates=100, max_subset=3, n_its=144, catalog="generic",

@@ -716,6 +716,26 @@ int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol
   out->replacement_its = (uint64_t*)calloc((size_t)(S ? S : 1) * (ITW ? ITW : 1), sizeof(uint64_t));
   out->n_new_claims = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
   out->n_unscheduled = (int32_t*)calloc(S ? S : 1, sizeof(int32_t));
+  // the replacement NodeClaim of a REPLACE (consolidation.go:206-229)
+  const int K = p->n_keys;
+  std::vector<int> woff(K + 1, 0);
+  for (int k = 0; k < K; k++) woff[k + 1] = woff[k] + (k == P.hostname_key ? 0 : (P.nvalues(k) + 63) / 64);
+  const int MW = woff[K];
+  const size_t s1 = S ? S : 1;
+  out->n_keys = K;
+  out->mask_words = MW;
+  out->n_resources = P.R;
+  out->repl_template = (int32_t*)malloc(s1 * 4);
+  for (size_t i = 0; i < s1; i++) out->repl_template[i] = -1;
+  out->repl_requests = (int64_t*)calloc(s1 * (P.R ? P.R : 1), 8);
+  out->repl_req_flags = (uint8_t*)calloc(s1 * (K ? K : 1), 1);
+  out->repl_req_gte = (int64_t*)calloc(s1 * (K ? K : 1), 8);
+  out->repl_req_lte = (int64_t*)calloc(s1 * (K ? K : 1), 8);
+  out->repl_req_mask = (uint64_t*)calloc(s1 * (MW ? MW : 1), 8);
+  std::vector<std::vector<int32_t>> order_rows(in->export_price_order ? S : 0);
+  const int n_extra = in->n_extra_pods > 0 ? in->n_extra_pods : 0;
+  const int64_t extra_row0 = p->n_nodes > 0 ? in->node_pod_off[p->n_nodes] : 0;
+  if (n_extra > 0 && (!in->extra_pod_kind || extra_row0 + n_extra != p->n_pods)) return KP_ERR_INVALID;
   const int ct_order[3] = {in->ct_reserved, in->ct_spot, in->ct_on_demand};
   auto t0 = std::chrono::steady_clock::now();
   auto one_subset = [&](int s_i) {
@@ -735,6 +755,11 @@ int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol
           bound.push_back({p->pod_class[j], n});  // still running where it is
         }
       }
+    const size_t n_cand_pods = rows.size();
+    for (int i = 0; i < n_extra; i++) {  // pending pods + reschedulable pods of deleting nodes (helpers.go:65-91)
+      rows.push_back(extra_row0 + i);
+      pending.push_back(p->pod_class[extra_row0 + i]);
+    }
     Scheduler sch(P);
     sch.init(active, bound, pending);
     std::vector<int32_t> targets;
@@ -742,10 +767,12 @@ int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol
     sch.solve(rows, &targets, &errors);
     int unscheduled = 0;
     for (size_t i = 0; i < targets.size(); i++) {
-      if (targets[i] == KP_TARGET_UNSCHEDULED)
-        unscheduled++;
-      else if (targets[i] >= 0 && !(p->node_flags[targets[i]] & KP_NODE_INITIALIZED))
-        unscheduled++;  // helpers.go:121-140 UninitializedNodeError
+      const int kind = i < n_cand_pods ? 0 : in->extra_pod_kind[i - n_cand_pods];
+      if (targets[i] == KP_TARGET_UNSCHEDULED) {
+        if (kind != KP_EXTRA_PENDING) unscheduled++;  // AllNonPendingPodsScheduled (scheduler.go:330-334)
+      } else if (targets[i] >= 0 && !(p->node_flags[targets[i]] & KP_NODE_INITIALIZED)) {
+        if (kind == 0) unscheduled++;  // helpers.go:121-140 UninitializedNodeError, not for pods of deleting nodes
+      }
     }
     int n_new = (int)sch.claim_store.size();
     out->n_new_claims[s_i] = n_new;
@@ -851,6 +878,21 @@ int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol
       }
       decision = KP_DECISION_REPLACE;
       for (int it : kept) rep[it >> 6] |= 1ull << (it & 63);
+      // OD -> [OD, spot]: pin the replacement to spot (consolidation.go:206-214); the spot-to-spot path pinned it above
+      if (!(all_spot && spot_ok) && in->capacity_type_key >= 0 && in->ct_spot >= 0 && in->ct_on_demand >= 0) {
+        Requirement cur = c.reqs.get(in->capacity_type_key);
+        if (has(P, cur, in->ct_spot) && has(P, cur, in->ct_on_demand)) {
+          Requirement r;
+          r.key = in->capacity_type_key;
+          r.values.push_back(in->ct_spot);
+          c.reqs.add(P, r);
+        }
+      }
+      out->repl_template[s_i] = c.tmpl;
+      for (int r = 0; r < P.R; r++) out->repl_requests[(size_t)s_i * P.R + r] = c.requests.v[r];
+      export_requirements(P, c.reqs, MW, woff, out->repl_req_flags + (size_t)s_i * K, out->repl_req_gte + (size_t)s_i * K,
+                          out->repl_req_lte + (size_t)s_i * K, out->repl_req_mask + (size_t)s_i * MW);
+      if (in->export_price_order) order_rows[s_i].assign(kept.begin(), kept.end());
     } while (0);
     out->decision[s_i] = decision;
   };
@@ -866,6 +908,17 @@ int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol
   }
   auto t1 = std::chrono::steady_clock::now();
   out->solve_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  if (in->export_price_order) {
+    out->repl_order_off = (int32_t*)calloc((size_t)S + 1, 4);
+    size_t tot = 0;
+    for (int s_ = 0; s_ < S; s_++) {
+      tot += order_rows[s_].size();
+      out->repl_order_off[s_ + 1] = (int32_t)tot;
+    }
+    out->repl_order = (int32_t*)calloc(tot ? tot : 1, 4);
+    for (int s_ = 0; s_ < S; s_++)
+      if (!order_rows[s_].empty()) memcpy(out->repl_order + out->repl_order_off[s_], order_rows[s_].data(), order_rows[s_].size() * 4);
+  }
   return KP_OK;
 }
 
@@ -874,6 +927,14 @@ void orc_consol_result_free(kp_consol_result* r) {
   free(r->replacement_its);
   free(r->n_new_claims);
   free(r->n_unscheduled);
+  free(r->repl_template);
+  free(r->repl_requests);
+  free(r->repl_req_flags);
+  free(r->repl_req_gte);
+  free(r->repl_req_lte);
+  free(r->repl_req_mask);
+  free(r->repl_order_off);
+  free(r->repl_order);
   memset(r, 0, sizeof(*r));
 }
 

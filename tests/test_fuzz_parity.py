@@ -120,13 +120,30 @@ def consolidation_case(seed):
     return pools, per_pool, nodes, sets, rng.random() < 0.5  # ... and whether spot-to-spot consolidation is enabled
 
 
+def consolidation_extras(seed):
+    """Pending pods and pods of deleting nodes that every simulation of the case also schedules (helpers.go:65-91):
+    every other seed has some."""
+    import random
+    rng = random.Random(77_000 + seed)
+    if seed % 2 == 0:
+        return {}
+    extra = fuzz.pods(rng, 8, uid0=50_000)
+    if seed % 4 != 0 and seed % 4 != 3:  # keep the topology-free seeds topology-free
+        pass
+    if seed % 4:
+        extra = [p for p in extra if not (p.topology_spread_constraints or p.pod_affinity or p.pod_anti_affinity)]
+    k = rng.randint(0, len(extra))
+    return dict(pending_pods=extra[:k], deleting_node_pods=extra[k:])
+
+
 @pytest.mark.gpu
 def test_fuzz_consolidation_parity_gpu():
     from karpenter_b200.disruption import Consolidation
     bad, ran = [], 0
     for seed in range(CAP or 200):
         pools, per_pool, nodes, sets, s2s = consolidation_case(seed)
-        kw = dict(spot_to_spot=s2s, filter_same_instance_type=seed % 2 == 1)
+        kw = dict(spot_to_spot=s2s, filter_same_instance_type=seed % 2 == 1, price_order=seed % 5 == 0,
+                  **consolidation_extras(seed))
         orc = Consolidation(pools, per_pool, nodes, backend=oracle_lib.consolidate, **kw)
         try:
             orc.compute(sets)
@@ -143,7 +160,8 @@ def test_fuzz_consolidation_parity_gpu():
         finally:
             gpu.close()
         ran += 1
-        for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+        from karpenter_b200 import _abi
+        for k in _abi.CONSOL_PARITY_KEYS + (["repl_order_off", "repl_order"] if kw["price_order"] else []):
             if not np.array_equal(gpu.raw[k], orc.raw[k]):
                 bad.append((seed, k, gpu.raw[k].tolist()[:8], orc.raw[k].tolist()[:8]))
                 break
@@ -157,7 +175,8 @@ def test_consolidation_generator_on_oracle():
     for seed in range(60):
         pools, per_pool, nodes, sets, s2s = consolidation_case(seed)
         try:
-            for c in Consolidation(pools, per_pool, nodes, spot_to_spot=s2s, backend=oracle_lib.consolidate).compute(sets):
+            for c in Consolidation(pools, per_pool, nodes, spot_to_spot=s2s, backend=oracle_lib.consolidate,
+                                   **consolidation_extras(seed)).compute(sets):
                 decisions[c.decision] += 1
         except RuntimeError:
             decisions["rejected"] += 1

@@ -65,7 +65,8 @@ def test_existing_nodes_parity(handle, kw):
 
 
 def _consol_same(gpu, orc, what):
-    for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+    from karpenter_b200 import _abi
+    for k in _abi.CONSOL_PARITY_KEYS:
         assert np.array_equal(gpu[k], orc[k]), f"{what}{k}: {np.argwhere(gpu[k] != orc[k])[:5].tolist()}"
 
 
@@ -126,6 +127,98 @@ def test_c4_full_size_sampled_parity(handle):
     orc = oracle_lib.consolidate(enc.problem, _abi.ConsolInput(**smp), threads=8)
     for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
         assert np.array_equal(gpu[k][pick], orc[k]), k
+
+
+def _topology_cluster(n_nodes, pods_per_node, seed=3):
+    """Existing nodes whose pods carry a zonal spread + hostname anti-affinity per app: candidate sets of such a cluster
+    take kp_consolidate's general path (one Scheduler instance per set)."""
+    import random
+    from karpenter_b200 import kwok
+    from karpenter_b200.model import (ARCH_LABEL, CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, INSTANCE_TYPE_LABEL, NODEPOOL_LABEL,
+                                      OS_LABEL, ZONE_LABEL, LabelSelector, Pod, PodAffinityTerm, StateNode,
+                                      TopologySpreadConstraint, quantity_units)
+    rng = random.Random(seed)
+    its = kwok.generic_instance_types()[:60]
+    linux = [it for it in its if it.name.endswith("-linux") and int(it.capacity["cpu"]) >= 4]
+    pool = workloads.default_nodepool()
+    nodes, uid = [], 1
+    for n in range(n_nodes):
+        it = rng.choice(linux)
+        pl = []
+        full = int((int(it.capacity["cpu"]) * 1000 - 100) // 250)
+        fill = max(1, int(full * rng.choice([0.15, 0.5, 0.9, 1.0, 1.0])))  # a mix of full and half-empty nodes
+        for _ in range(min(fill, pods_per_node)):
+            app = {"app": f"a{rng.randrange(6)}"}
+            sel = LabelSelector.of(app)
+            pl.append(Pod(name=f"p{uid}", uid=uid, labels=app, requests={"cpu": "250m", "memory": "128Mi"},
+                          topology_spread_constraints=[TopologySpreadConstraint(2, ZONE_LABEL, sel)],
+                          pod_anti_affinity=[PodAffinityTerm(sel, HOSTNAME_LABEL)] if rng.random() < 0.3 else []))
+            uid += 1
+        used = {"cpu": 250 * len(pl), "memory": (128 << 20) * len(pl), "pods": len(pl)}
+        avail = {r: quantity_units(r, it.capacity[r]) - quantity_units(r, it.overhead.get(r, 0)) - used[r]
+                 for r in ("cpu", "memory", "pods")}
+        avail["cpu"] = f"{avail['cpu']}m"
+        cap = dict(it.capacity)
+        cap["nodes"] = 1
+        labels = {HOSTNAME_LABEL: f"node-{n:03d}", ZONE_LABEL: kwok.KWOK_ZONES[n % 4], CAPACITY_TYPE_LABEL: "on-demand",
+                  OS_LABEL: "linux", ARCH_LABEL: it.name.split("-")[2], NODEPOOL_LABEL: "default", INSTANCE_TYPE_LABEL: it.name}
+        nodes.append(StateNode(name=f"node-{n:03d}", labels=labels, available=avail, capacity=cap, nodepool="default",
+                               instance_type=it.name, pods=pl))
+    return pool, its, nodes
+
+
+def test_general_consolidation_is_one_batch_launch():
+    """120 candidate sets whose pods carry topology constraints: every set is its own Scheduler instance (fresh
+    NewTopology), all of them solved by ONE k_wsolve_batch launch per chunk instead of one launch + sync per set."""
+    import random
+    from karpenter_b200 import _abi
+    from karpenter_b200.disruption import Consolidation
+    pool, its, nodes = _topology_cluster(40, 40)
+    rng = random.Random(11)
+    names = [n.name for n in nodes]
+    sets = [rng.sample(names, rng.randint(1, 3)) for _ in range(120)]
+    orc = Consolidation([pool], {"default": its}, nodes, backend=oracle_lib.consolidate, filter_same_instance_type=True)
+    want = orc.compute(sets)
+    gpu = Consolidation([pool], {"default": its}, nodes, filter_same_instance_type=True)
+    try:
+        got = gpu.compute(sets)
+        st = gpu._handle.stats()
+    finally:
+        gpu.close()
+    for k in _abi.CONSOL_PARITY_KEYS:
+        assert np.array_equal(gpu.raw[k], orc.raw[k]), k
+    assert got == want and len({c.decision for c in want}) >= 2
+    assert st["kernel_launches"] < 20 * len(sets)  # prep kernels per instance, ONE solver launch for the chunk
+
+
+def test_consolidate_deadline_keeps_finished_subsets(handle):
+    """kp_consolidate honours the deadline: KP_DEADLINE, finished subsets identical to the full run, the rest UNKNOWN."""
+    from karpenter_b200 import _abi
+    enc, consol = workloads.config_c4(n_nodes=3000, n_pods=60000, n_candidates=60, max_subset=3)
+    ci = _abi.ConsolInput(**consol)
+    full = handle.consolidate(enc.problem, ci)
+    assert not full["deadline"] and 255 not in set(full["decision"].tolist())
+    part = handle.consolidate(enc.problem, ci, deadline_ms=1)
+    if part["deadline"]:
+        done = part["decision"] != 255
+        assert done.sum() < len(done)
+        for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+            assert np.array_equal(part[k][done], full[k][done]), k
+
+
+def test_malformed_problem_is_refused_not_dereferenced(handle):
+    """Input validation (kp_prep.cpp validate_problem): ids outside their tables come back as KP_ERR_INVALID."""
+    for field, bad in (("pod_class", 10 ** 6), ("class_reqset", -3), ("tmpl_its", 99999), ("req_vals", 1 << 20),
+                       ("it_reqset", 1 << 20)):
+        enc = workloads.config_c2(n_pods=200, n_its=50)
+        arr = enc.problem.get(field).copy()
+        arr[len(arr) // 2] = bad
+        enc.problem.set(field, arr)
+        with pytest.raises(_native.SolverError) as e:
+            handle.solve(enc.problem)
+        assert e.value.code == 2 and "invalid problem" in str(e.value), (field, str(e.value))
+    enc = workloads.config_c2(n_pods=200, n_its=50)   # and the handle still works afterwards
+    assert_same(handle.solve(enc.problem), oracle_lib.solve(enc.problem), "after invalid ")
 
 
 def test_solve_batch_matches_single_solves(handle):

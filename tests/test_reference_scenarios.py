@@ -324,23 +324,86 @@ def _node(name, it, zone="test-zone-1", ct="on-demand", pod_list=(), initialized
                      pods=list(pod_list), initialized=initialized)
 
 
-def consolidate(which, nodes, candidate_sets, its=None):
+def consolidate(which, nodes, candidate_sets, its=None, np_=None, **kw):
+    from karpenter_b200 import _abi
     from karpenter_b200.disruption import Consolidation
     import numpy as np
     its = its or fake.default_instance_types()
-    np_ = nodepool()
-    orc = Consolidation([np_], {np_.name: its}, nodes, backend=oracle_lib.consolidate)
+    np_ = np_ or nodepool()
+    orc = Consolidation([np_], {np_.name: its}, nodes, backend=oracle_lib.consolidate, **kw)
     cmds = orc.compute(candidate_sets)
     if which == "gpu":
-        gpu = Consolidation([np_], {np_.name: its}, nodes)
+        gpu = Consolidation([np_], {np_.name: its}, nodes, **kw)
         try:
             got = gpu.compute(candidate_sets)
         finally:
             gpu.close()
-        for k in ("decision", "n_new_claims", "n_unscheduled", "replacement_its"):
+        for k in _abi.CONSOL_PARITY_KEYS:
             assert np.array_equal(gpu.raw[k], orc.raw[k]), k
+        assert got == cmds
         return got
     return cmds
+
+
+# SimulateScheduling schedules pending pods and the pods of deleting nodes together with the candidates' (helpers.go:65-91)
+@pytest.mark.parametrize("which", BACKENDS)
+def test_simulation_pending_pod_takes_the_room(which):
+    its = {it.name: it for it in fake.default_instance_types()}
+    d = its["default-instance-type"]  # 4 cpu: 3.9 allocatable
+    p = pods(4, requests={"cpu": "1"})
+    nodes = [_node("node-1", d, pod_list=p[:2]), _node("node-2", d, pod_list=p[2:3])]
+    # alone, node-2's pod moves to node-1: delete.  With a pending pod of the same size (older uid: queued first) the room
+    # on node-1 is gone and the simulation has to open a NodeClaim.
+    (alone,) = consolidate(which, nodes, [["node-2"]])
+    assert alone.decision == "delete"
+    pending = pods(1, uid0=0, requests={"cpu": "1"})
+    (cmd,) = consolidate(which, nodes, [["node-2"]], pending_pods=pending)
+    assert cmd.n_new_node_claims == 1 and cmd.decision != "delete"
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_simulation_ignores_errors_of_pending_pods_only(which):  # AllNonPendingPodsScheduled, scheduler.go:330-334
+    its = {it.name: it for it in fake.default_instance_types()}
+    d = its["default-instance-type"]
+    p = pods(3, requests={"cpu": "1"})
+    nodes = [_node("node-1", d, pod_list=p[:2]), _node("node-2", d, pod_list=p[2:])]
+    stuck = pods(1, uid0=90, requests={"cpu": "1"}, node_selector={ZONE_LABEL: "no-such-zone"})
+    (cmd,) = consolidate(which, nodes, [["node-2"]], pending_pods=stuck)
+    assert cmd.decision == "delete" and cmd.n_unscheduled == 0       # a pending pod that cannot schedule blocks nothing
+    (cmd,) = consolidate(which, nodes, [["node-2"]], deleting_node_pods=stuck)
+    assert cmd.decision == "noop" and cmd.n_unscheduled == 1          # the same pod coming off a deleting node does
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_simulation_deleting_node_pod_on_uninitialized_node_is_fine(which):  # helpers.go:121-140
+    its = {it.name: it for it in fake.default_instance_types()}
+    d = its["default-instance-type"]
+    p = pods(2, requests={"cpu": "3"})
+    nodes = [_node("node-1", d, pod_list=[], initialized=False), _node("node-2", d, pod_list=p[:1])]
+    # node-2's pod can only go to the uninitialized node-1: that is an error for a candidate's pod ...
+    (cmd,) = consolidate(which, nodes, [["node-2"]])
+    assert cmd.decision == "noop" and cmd.n_unscheduled == 1
+    # ... but not for the pod of a node that is already being deleted (it lands there in the simulation; the candidate's
+    # own pod then needs a NodeClaim)
+    (cmd,) = consolidate(which, nodes, [["node-2"]], deleting_node_pods=pods(1, uid0=0, requests={"cpu": "3"}))
+    assert cmd.n_unscheduled == 0 and cmd.n_new_node_claims == 1
+
+
+@pytest.mark.parametrize("which", BACKENDS)
+def test_replacement_is_pinned_to_spot_when_od_goes_to_od_or_spot(which):  # consolidation.go:206-214
+    from karpenter_b200.model import NodePool
+    its = fake.default_instance_types()
+    by = {it.name: it for it in its}
+    np_ = NodePool(name="default", requirements=[req(CAPACITY_TYPE_LABEL, "In", "on-demand", "spot")])
+    p = pods(1, requests={"cpu": "1"})
+    nodes = [_node("node-1", by["default-instance-type"], ct="on-demand", pod_list=p)]
+    (cmd,) = consolidate(which, nodes, [["node-1"]], np_=np_, price_order=True)
+    assert cmd.decision == "replace" and cmd.replacement_nodepool == "default"
+    ct = cmd.replacement_requirements[CAPACITY_TYPE_LABEL]
+    assert not ct["complement"] and ct["values"] == ["spot"]
+    assert cmd.replacement_requests["cpu"] >= 1000 and cmd.replacement_requests["pods"] == 1
+    prices = [min(o.price for o in by[n].offerings if o.available) for n in cmd.replacement_instance_types]
+    assert prices == sorted(prices) and len(prices) >= 1               # OrderByPrice order survives the round trip
 
 
 @pytest.mark.parametrize("which", BACKENDS)
