@@ -37,7 +37,7 @@ typedef enum kp_status {
   KP_ERR_INVALID = 2,      /* malformed problem */
   KP_ERR_CUDA = 3,         /* device / driver failure; message via kp_last_error */
   KP_ERR_CAPACITY = 4,     /* a compiled limit was exceeded (e.g. > KP_MAX_RESOURCES) */
-  KP_ERR_UNSUPPORTED = 5   /* feature of the reference not built yet (reserved offerings, host ports, minValues in kp_consolidate) */
+  KP_ERR_UNSUPPORTED = 5   /* feature of the reference not built yet (host ports, CSI volume limits, minValues in kp_consolidate) */
 } kp_status;
 
 /* ---- requirement encoding --------------------------------------------------------------------------------------
@@ -142,10 +142,9 @@ typedef struct kp_problem {
   const double* off_price;        /* [n_offerings] */
   const uint8_t* off_available;   /* [n_offerings] */
   const uint8_t* off_reserved;    /* [n_offerings], may be NULL.  1 == Offering.CapacityType() is "reserved" AND the
-                                     ReservedCapacity feature gate is on, i.e. the reference would run the offering through
-                                     its ReservationManager (reservationmanager.go:28-110, nodeclaim.go:240-307).  That
-                                     bookkeeping is not built: a problem with an available reserved offering is refused
-                                     with KP_ERR_UNSUPPORTED rather than solved as if reservations were unlimited. */
+                                     ReservedCapacity feature gate is on, i.e. the reference runs the offering through
+                                     its ReservationManager (reservationmanager.go:28-110, nodeclaim.go:240-307); such
+                                     an offering needs off_reservation_id / off_reservation_capacity below. */
 
   /* ---- NodeClaimTemplates, one per NodePool, already in OrderByWeight order (utils/nodepool/nodepool.go:161) ---- */
   int32_t n_templates;
@@ -239,6 +238,25 @@ typedef struct kp_problem {
    * decoder derives from the result. */
   int32_t min_values_best_effort;
   int32_t claim_order_mode; /* 0 = Go sort.Slice (pdqsort_func) tie order, 1 = stable */
+
+  /* ---- reserved capacity (ReservationManager, reservationmanager.go:28-110; offeringsToReserve nodeclaim.go:240-287) ----
+   * Offering.ReservationID() interned to 0 .. n_reservations-1 (-1 for offerings that are not reserved) and
+   * Offering.ReservationCapacity.  The manager starts every id at the smallest capacity any of its offerings reports
+   * (reservationmanager.go:38-47).  A NodeClaim reserves every id it could still launch into and releases what later
+   * pods rule out.  reserved_offering_strict = 1 is ReservedOfferingModeStrict (scheduler.go:96-98, what the provisioner
+   * and the disruption simulations run with, provisioner.go:347): compatible reserved offerings that cannot be reserved
+   * fail the NodeClaim with a ReservedOfferingError, which stops the NodePool fallback (scheduler.go:632-646) and the
+   * preference relaxation (scheduler.go:451).  All NULL / 0 when no offering is reserved. */
+  const int32_t* off_reservation_id;       /* [n_offerings] */
+  const int32_t* off_reservation_capacity; /* [n_offerings] */
+  int32_t n_reservations;                  /* <= 64 */
+  int32_t reserved_offering_strict;
+  /* FinalizeScheduling (nodeclaim.go:291-307) pins a NodeClaim that holds reservations to capacity-type In [reserved] and
+   * reservation-id In [held ids]; the returned claim requirements (and the ones consolidation prices, consolidation.go:186)
+   * are the finalized ones.  Key of karpenter.sh/capacity-type and value id of "reserved" in it; key of the
+   * reservation-id label and, per reservation id, its value id in that key. */
+  int32_t reservation_capacity_type_key, reservation_reserved_value, reservation_id_key;
+  const int32_t* reservation_value;        /* [n_reservations] */
 } kp_problem;
 
 /* pod_target encoding */
@@ -249,6 +267,8 @@ typedef struct kp_problem {
 #define KP_PODERR_NONE 0
 #define KP_PODERR_NO_TEMPLATES 1       /* scheduler.go:510-512 */
 #define KP_PODERR_INCOMPATIBLE 2       /* every template rejected the pod (multierr of scheduler.go:683) */
+#define KP_PODERR_RESERVED 3           /* ReservedOfferingError (nodeclaim.go:64-79): compatible reserved capacity exists but
+                                          is taken; the pod was neither relaxed nor sent to a lower-weight NodePool */
 
 #define KP_SLOT_PRESENT 0x10u /* or-ed with KP_REQ_* in claim_req_flags */
 
@@ -278,6 +298,8 @@ typedef struct kp_result {
   int64_t n_existing_evals, n_inflight_evals, n_template_evals, n_commits;
   double solve_ms; /* device time of the solve kernels (CUDA events) */
   void* _impl;
+  /* NodeClaim.reservedOfferings as a bit set over reservation ids (claim_req_* already carry FinalizeScheduling's pins) */
+  uint64_t* claim_reservations; /* [n_claims] */
 } kp_result;
 
 /* ---- consolidation ---- */

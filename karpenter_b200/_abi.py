@@ -174,6 +174,7 @@ def result_to_dict(r: kp_result, n_resources: int) -> dict:
         "n_template_evals": r.n_template_evals,
         "n_commits": r.n_commits,
         "solve_ms": r.solve_ms,
+        "claim_reservations": view(r.claim_reservations, C_, np.uint64),
     }
     return out
 
@@ -209,5 +210,5 @@ CONSOL_PARITY_KEYS = ["decision", "n_new_claims", "n_unscheduled", "replacement_
 PARITY_KEYS = [
     "pod_target", "pod_error", "n_claims", "claim_template", "claim_npods", "claim_rank", "claim_requests",
     "claim_its", "claim_req_flags", "claim_req_gte", "claim_req_lte", "claim_req_mask", "group_domain_off",
-    "domain_counts",
+    "domain_counts", "claim_reservations",
 ]

@@ -395,7 +395,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
         if (per_key[k] > 0 && (d.tk_key < 0 || per_key[k] > per_key[d.tk_key])) d.tk_key = k;
       bool lazy = false;
       for (int32_t b : t.g_born) lazy = lazy || b == 0;
-      const bool fp_global = !t.has_bounds && !lazy && !t.min_values_strict && !getenv("KP_NO_DOMAIN_FP");
+      const bool fp_global = !t.has_bounds && !lazy && !t.min_values_strict && t.n_rsv == 0 && !getenv("KP_NO_DOMAIN_FP");
       // set inclusion of requirement slots without bounds: values(a) within values(b)
       auto slot_subset = [&](int rs_a, int rs_b, int k) {
         const size_t ia = (size_t)rs_a * t.K + k, ib = (size_t)rs_b * t.K + k;
@@ -444,6 +444,8 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
           if (fp && !G.inverse && G.affinity_policy == 1 && G.filter_n > 0 && !filter_implied(x, G)) fp = false;
         }
         if (fp) info |= TKI_FP | (has_tk ? TKI_TK : 0);
+        if (it->second < 64) info |= TKI_ABIT;
+        if (nm + nr > 0) info |= TKI_TOPO;
         tkinfo[x] = info;
       }
     }
@@ -461,6 +463,9 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
         auto it = fsigs.find(key);
         if (it == fsigs.end()) it = fsigs.emplace(key, (int)fsigs.size()).first;
         hh[6] = it->second;
+        // the accepted-signature fast path: topology-free, counted by no group, nothing to re-check on the type list
+        if ((tkinfo[x] & TKI_ABIT) && t.cls_rec_off[x + 1] == t.cls_rec_off[x] && !t.min_values_strict && t.n_rsv == 0)
+          tkinfo[x] |= TKI_FAST;
       }
       {
         auto key = std::make_pair(t.cls_rs[x], t.cls_tolset[x]);
@@ -598,6 +603,35 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(zeros(h, &d.cmask, C));
   CK(zeros(h, &d.amask, C));
   CK(zeros(h, &d.c_dom, C));
+  // reserved capacity
+  d.n_rsv = t.n_rsv;
+  d.rsv_strict = t.rsv_strict ? 1 : 0;
+  d.rsv_sets = 0;
+  {
+    std::vector<int32_t> sr(std::max(t.D, 1), -1);
+    for (int dd = 0; dd < t.D && dd < (int)t.set_rsv.size(); dd++) {
+      sr[dd] = t.set_rsv[dd];
+      if (sr[dd] >= 0) d.rsv_sets |= 1u << dd;
+    }
+    CK(up(h, &d.set_rsv, sr));
+    std::vector<int32_t> cap0 = t.rsv_cap0;
+    if (cap0.empty()) cap0.push_back(0);
+    CK(up_mut(h, &d.rsv_cap, cap0));
+    CK(zeros(h, &d.c_rsv, C));
+    d.rsv_ct_key = p->reservation_capacity_type_key;
+    d.rsv_reserved_val = p->reservation_reserved_value;
+    d.rsv_id_key = p->reservation_id_key;
+    memset(d.rsv_val_of, 0, sizeof(d.rsv_val_of));
+    if (t.n_rsv > 0) {
+      if (d.rsv_ct_key < 0 || d.rsv_ct_key >= t.K || d.rsv_id_key < 0 || d.rsv_id_key >= t.K || !p->reservation_value ||
+          d.rsv_reserved_val < 0 || d.rsv_reserved_val >= 64)
+        return h->err = "reserved offerings need reservation_capacity_type_key / reservation_id_key / reservation_value", KP_ERR_INVALID;
+      for (int i = 0; i < t.n_rsv; i++) {
+        if (p->reservation_value[i] < 0 || p->reservation_value[i] >= 64) return h->err = "reservation_value out of range", KP_ERR_INVALID;
+        d.rsv_val_of[i] = 1ull << p->reservation_value[i];
+      }
+    }
+  }
   d.tmpl_all = t.N >= 64 ? ~0ull : ((1ull << t.N) - 1);
   d.H = t.E + d.Cmax;
   d.GHS = std::max(t.GH, 1);
@@ -634,6 +668,7 @@ static int reset_dynamic(kp_handle* h) {
   CK(cudaMemsetAsync(d.c_npods, 0, C * 4, h->stream));
   CK(cudaMemsetAsync(d.cmask, 0, C * sizeof(ulonglong2), h->stream));
   CK(cudaMemsetAsync(d.amask, 0, C * 8, h->stream));
+  CK(cudaMemsetAsync(d.c_rsv, 0, C * 8, h->stream));
   CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)d.GHS * d.H * 4, h->stream));
   if (t.E && t.GH)  // initial hostname-group counts of the existing nodes: the first E host rows
     CK(cudaMemcpyAsync(d.host_cnt, h->cur->d_host_cnt_nodes, (size_t)t.E * d.GHS * 4, cudaMemcpyDeviceToDevice, h->stream));
@@ -927,6 +962,8 @@ static int download(kp_handle* h, kp_result* out) {
   out->claim_template = (int32_t*)calloc(c1, 4);
   out->claim_npods = (int32_t*)calloc(c1, 4);
   out->claim_rank = (int32_t*)calloc(c1, 4);
+  out->claim_reservations = (uint64_t*)calloc(c1, 8);
+  CK(cudaMemcpy(out->claim_reservations, d.c_rsv, C * 8, cudaMemcpyDeviceToHost));
   out->claim_requests = (int64_t*)calloc(c1 * R, 8);
   out->it_words = ITW;
   out->claim_its = (uint64_t*)calloc(c1 * (ITW ? ITW : 1), 8);
@@ -1298,6 +1335,7 @@ void kp_result_free(kp_result* r) {
   free(r->claim_req_mask);
   free(r->group_domain_off);
   free(r->domain_counts);
+  free(r->claim_reservations);
   memset(r, 0, sizeof(*r));
 }
 
@@ -1787,6 +1825,10 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   CK(zeros(h, &q.clsl, slots * cq));
   CK(zeros(h, &q.rk, slots * cq));
   if (n_extra > 0) CK(zeros(h, &q.kindl, slots * cq));
+  if (t.n_rsv > 0) {
+    CK(zeros(h, &q.rsv_cap, slots * (size_t)t.n_rsv));
+    CK(zeros(h, &q.c_rsv, slots * cq));
+  }
   CK(zeros(h, &q.c_tmpl, slots * cq));
   CK(zeros(h, &q.c_npods, slots * cq));
   CK(zeros(h, &q.order, slots * cq));

@@ -206,6 +206,8 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     I.g_amask = d.amask;
     I.c_dom = d.c_dom;
     I.g_c_dom = d.c_dom;
+    I.rsv_cap = d.rsv_cap;
+    I.c_rsv = d.c_rsv;
     I.CR = 0;
     unsigned char* p = tab + d_in.tab_bytes;
     if (CR > 0) {  // rows of the first CR claims
@@ -244,6 +246,7 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
   wsolve_run<false, true>(d, I, sh.ring.slot[0], sh.scratch, lane, &sh.ring);
   const int nC = I.n_claims;
   claim_rows_flush(d, I, nC, lane);
+  claims_finalize(d, I.c_sflags, I.c_smask, I.c_rsv, nC, lane);
   if (I.CS > 0) {  // the host reads the final order (claim_rank) and template ids from global memory
     for (int i = lane; i < nC; i += 32) {
       d_in.order[i] = I.order[i];
@@ -315,6 +318,8 @@ struct KpConsol {
   int n_extra, extra_row0;
   const uint8_t* extra_kind;     // [n_extra] KP_EXTRA_*
   uint8_t* kindl;                // per warp slot [capq]: kind of local pod i (0: candidate pod)
+  int32_t* rsv_cap;              // per warp slot [n_rsv]: the simulation's own ReservationManager
+  unsigned long long* c_rsv;     // per warp slot [capq]
   // context deadline: the first warp to start stamps t_start; a warp that finds deadline_ns used up stops pulling work
   long long deadline_ns;
   unsigned long long* t_start;
@@ -355,21 +360,6 @@ struct KpConsol {
   int32_t* next;                 // work counter
   int32_t* status;
 };
-
-// bit dd: Requirements.Compatible(S, offering requirement set dd, AllowUndefinedWellKnownLabels)
-__device__ __forceinline__ unsigned offering_ok_mask(const KpDev& d, const Slot* S, int lane) {
-  bool ok = false;
-  if (lane < d.D) {
-    uint32_t keys = d.off_keys[lane];
-    ok = true;
-    while (keys) {
-      const int k = __ffs(keys) - 1;
-      keys &= keys - 1;
-      if (!slot_compatible(key_info(d, k), S[k], d.off_slots[(size_t)lane * d.K + k], d.key_wellknown[k], true)) ok = false;
-    }
-  }
-  return __ballot_sync(FULL, ok);
-}
 
 // computeConsolidation (consolidation.go:136-229) for one simulated candidate set: `unscheduled` pods could not be
 // placed (or only on uninitialized nodes), `n_new` NodeClaims were opened; claim 0's row (requirement slots, instance
@@ -685,6 +675,8 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolid
     I.CR = 0;
     I.c_dom = nullptr;  // candidate sets with topology take the batch path (k_wsolve_batch)
     I.g_c_dom = nullptr;
+    I.rsv_cap = d.n_rsv ? q.rsv_cap + slot * d.n_rsv : nullptr;
+    I.c_rsv = d.n_rsv ? q.c_rsv + slot * capq : nullptr;
     I.ov_cap = capq;
     I.ov_node = q.ov_node + slot * capq;
     I.ov_rem = q.ov_rem + slot * capq * R;
@@ -767,6 +759,7 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolid
       I.n_removed = sn;
       I.removed = snodes;
     }
+    for (int i = lane; i < d.n_rsv; i += 32) I.rsv_cap[i] = d.rsv_cap[i];  // NewReservationManager: a fresh one per simulation
     for (int i = lane; i < N * R; i += 32) {  // updateRemainingResources over stateNodes minus candidates
       const int t = i / R, r = i % R;
       int64_t rem = q.tmpl_remaining0[i];
@@ -781,6 +774,7 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolid
       if (lane == 0) *q.status = I.status;
       break;
     }
+    claims_finalize(d, I.c_sflags, I.c_smask, I.c_rsv, I.n_claims, lane);
     // ---- computeConsolidation (consolidation.go:136-229)
     consol_decide(d, q, slot, W.scratch, I.c_sflags, I.c_smask, I.c_sgte, I.c_slte, I.c_its, I.n_claims > 0 ? I.c_tmpl[0] : -1,
                   I.c_req, sn, snodes, I.n_unsched + I.n_uninit, I.n_claims, s, lane);

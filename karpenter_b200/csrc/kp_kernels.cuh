@@ -224,6 +224,9 @@ struct Eval {
 #define KP_PG 6              // groups per list staged with the pod; a class with more reads them from HBM
 #define TKI_FP 0x100         // tkinfo: the class may take the domain fast path (see wsolve_run)
 #define TKI_TK 0x200         // ... and has at least one group on the topology key
+#define TKI_FAST 0x400       // topology-free class that may take the accepted-signature fast path
+#define TKI_ABIT 0x800       // the class's requirement set has an "adds nothing" bit (asig < 64)
+#define TKI_TOPO 0x1000      // some topology group constrains or counts the class
 #define TKI_ASIG(t) ((t) & 0xff)  // requirement-set id for the "adds nothing" masks (amask), 0xff: none
 struct PodCtx {
   union {
@@ -494,6 +497,76 @@ __device__ __forceinline__ void topo_record(const KpDev& d, const PodCtx& px, co
       }
     }
   }
+}
+
+// bit dd: Requirements.Compatible(S, offering requirement set dd, AllowUndefinedWellKnownLabels)
+__device__ __forceinline__ unsigned offering_ok_mask(const KpDev& d, const Slot* S, int lane) {
+  bool ok = false;
+  if (lane < d.D) {
+    uint32_t keys = d.off_keys[lane];
+    ok = true;
+    while (keys) {
+      const int k = __ffs(keys) - 1;
+      keys &= keys - 1;
+      if (!slot_compatible(key_info(d, k), S[k], d.off_slots[(size_t)lane * d.K + k], d.key_wellknown[k], true)) ok = false;
+    }
+  }
+  return __ballot_sync(FULL, ok);
+}
+
+// offeringsToReserve (nodeclaim.go:240-287) for a candidate NodeClaim whose requirement slots after the pod are in
+// `scratch` and whose surviving instance types are `its` (word `lane`).  `held` = reservation ids the claim holds now
+// (0 for a fresh one).  Returns the ids to hold afterwards; *error = ReservedOfferingError (strict mode only).
+__device__ __forceinline__ unsigned long long offerings_to_reserve(const KpDev& d, const int32_t* rsv_cap, const Slot* scratch,
+                                                                    uint64_t its, unsigned long long held, int lane, bool* error) {
+  *error = false;
+  unsigned sets = offering_ok_mask(d, scratch, lane) & d.rsv_sets;  // reserved offerings compatible with the requirements
+  unsigned long long compat = 0;
+  while (sets) {
+    const int dd = __ffs(sets) - 1;
+    sets &= sets - 1;
+    const bool hit = lane < d.ITW && (its & d.offset_bits[(size_t)dd * d.ITW + lane]) != 0;  // ... of a surviving, available type
+    if (__any_sync(FULL, hit)) compat |= 1ull << d.set_rsv[dd];
+  }
+  // ReservationManager.CanReserve (reservationmanager.go:55-70): already held by this claim, or capacity left
+  const bool c0 = lane < d.n_rsv && rsv_cap[lane] > 0, c1 = lane + 32 < d.n_rsv && rsv_cap[lane + 32] > 0;
+  const unsigned long long avail = (unsigned long long)__ballot_sync(FULL, c0) | ((unsigned long long)__ballot_sync(FULL, c1) << 32);
+  const unsigned long long take = compat & (held | avail);
+  if (d.rsv_strict && take == 0 && (compat != 0 || held != 0)) *error = true;
+  return take;
+}
+// NodeClaim.Add's bookkeeping (nodeclaim.go:216-218): reserve the new ids, release the ones no longer compatible
+__device__ __forceinline__ void reservations_commit(const KpDev& d, int32_t* rsv_cap, unsigned long long held,
+                                                    unsigned long long take, int lane) {
+  const unsigned long long inc = held & ~take, dec = take & ~held;
+  if (lane < d.n_rsv) rsv_cap[lane] += (int)((inc >> lane) & 1ull) - (int)((dec >> lane) & 1ull);
+  if (lane + 32 < d.n_rsv) rsv_cap[lane + 32] += (int)((inc >> (lane + 32)) & 1ull) - (int)((dec >> (lane + 32)) & 1ull);
+  __syncwarp();
+}
+
+// FinalizeScheduling (nodeclaim.go:291-307) on the claim rows in global memory: a NodeClaim that holds reservations is
+// pinned to capacity-type In [reserved] and reservation-id In [held ids].  One warp, after the solve.
+__device__ __forceinline__ void claims_finalize(const KpDev& d, uint8_t* sflags, uint64_t* smask, const unsigned long long* c_rsv,
+                                                int nC, int lane) {
+  if (!d.n_rsv || d.rsv_ct_key < 0 || d.rsv_id_key < 0) return;
+  for (int c = lane; c < nC; c += 32) {
+    const unsigned long long held = c_rsv[c];
+    if (!held) continue;
+    sflags[(size_t)c * d.K + d.rsv_ct_key] = SF_PRESENT;
+    smask[(size_t)c * d.K + d.rsv_ct_key] = 1ull << d.rsv_reserved_val;
+    uint64_t vals = 0;
+    for (unsigned long long h = held; h;) {
+      const int id = __ffsll((long long)h) - 1;
+      h &= h - 1;
+      vals |= d.rsv_val_of[id];
+    }
+    const size_t i = (size_t)c * d.K + d.rsv_id_key;
+    const Slot cur{sflags[i], smask[i], 0, 0};
+    const Slot out = slot_add_nb(cur, Slot{SF_PRESENT, vals, 0, 0});  // Requirements.Add: intersect with what is there
+    sflags[i] = (uint8_t)out.f;
+    smask[i] = out.m;
+  }
+  __syncwarp();
 }
 
 // ---- the domain fast path (classes flagged TKI_FP, see upload_tables in kp_api.cu) -------------------------------

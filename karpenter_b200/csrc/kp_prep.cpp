@@ -201,11 +201,31 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   if (R > KP_MAXR || R < 1) return err = "resource count out of range", KP_ERR_CAPACITY;
   const int ITW = (T + 63) / 64;
   if (ITW > KP_MAX_ITW) return err = "more than 2048 instance types", KP_ERR_CAPACITY;
-  if (p->off_reserved)  // the ReservationManager (reservationmanager.go:28-110) is not built: refuse, never approximate
+  // reserved offerings run through the ReservationManager (reservationmanager.go:28-110): every one needs its id
+  h.n_rsv = 0;
+  h.rsv_strict = p->reserved_offering_strict != 0;
+  if (p->off_reserved) {
+    bool any = false;
     for (int t = 0; t < T; t++)
-      for (int o = p->it_off_off[t]; o < p->it_off_off[t + 1]; o++)
-        if (p->off_reserved[o] && p->off_available[o])
-          return err = "reserved-capacity offerings (ReservationManager) are not supported yet", KP_ERR_UNSUPPORTED;
+      for (int o = p->it_off_off[t]; o < p->it_off_off[t + 1]; o++) any = any || p->off_reserved[o];
+    if (any) {
+      if (!p->off_reservation_id || !p->off_reservation_capacity || p->n_reservations <= 0)
+        return err = "reserved offerings need off_reservation_id / off_reservation_capacity / n_reservations", KP_ERR_INVALID;
+      if (p->n_reservations > 64) return err = "more than 64 capacity reservations", KP_ERR_CAPACITY;
+      h.n_rsv = p->n_reservations;
+      h.rsv_cap0.assign(h.n_rsv, -1);
+      for (int t = 0; t < T; t++)
+        for (int o = p->it_off_off[t]; o < p->it_off_off[t + 1]; o++) {
+          if (!p->off_reserved[o]) continue;
+          const int id = p->off_reservation_id[o];
+          if (id < 0 || id >= h.n_rsv) return err = "off_reservation_id out of range", KP_ERR_INVALID;
+          const int cap = p->off_reservation_capacity[o];  // NewReservationManager keeps the smallest (:38-47)
+          if (h.rsv_cap0[id] < 0 || h.rsv_cap0[id] > cap) h.rsv_cap0[id] = cap;
+        }
+      for (int32_t& v : h.rsv_cap0)
+        if (v < 0) v = 0;
+    }
+  }
   h.K = K;
   h.R = R;
   h.T = T;
@@ -355,7 +375,10 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
     for (int t = 0; t < T; t++)
       for (int o = p->it_off_off[t]; o < p->it_off_off[t + 1]; o++) {
         int rs = p->off_reqset[o];
+        // a distinct set = (requirements, reservation id): every set has at most one reservation behind it
+        const int32_t rid = (h.n_rsv > 0 && p->off_reserved[o]) ? p->off_reservation_id[o] : -1;
         std::string key((const char*)&h.rs_flags[(size_t)rs * K], K);
+        key.append((const char*)&rid, 4);
         key.append((const char*)&h.rs_mask[(size_t)rs * K], K * 8);
         key.append((const char*)&h.rs_gte[(size_t)rs * K], K * 8);
         key.append((const char*)&h.rs_lte[(size_t)rs * K], K * 8);
@@ -366,6 +389,7 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
           if (d >= KP_MAX_OFFSETS) return err = "more than 32 distinct offering requirement sets", KP_ERR_CAPACITY;
           seen[key] = d;
           h.offset_rs.push_back(rs);
+          h.set_rsv.push_back(rid);
           h.offset_bits.resize((size_t)(d + 1) * ITW, 0);
         } else {
           d = it->second;

@@ -35,6 +35,10 @@ struct HostTables {
   std::vector<uint64_t> ge_bits;
   std::vector<int32_t> offset_rs;
   std::vector<int32_t> off_set;  // [offerings] index of the offering's distinct requirement set
+  // reserved capacity (ReservationManager): reservation id behind a distinct offering set (-1: none), initial capacity
+  int n_rsv = 0;
+  bool rsv_strict = false;
+  std::vector<int32_t> set_rsv, rsv_cap0;
   std::vector<uint64_t> offset_bits;
   std::vector<int64_t> it_capacity, it_alloc;
   std::vector<int32_t> tmpl_rs, tmpl_taintset;

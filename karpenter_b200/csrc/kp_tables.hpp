@@ -208,6 +208,15 @@ struct KpDev {
   int64_t* counters;              // [8] existing evals, inflight evals, template evals, commits, slow sorts, ...
   int32_t* status;                // [1] 0 ok, 4 capacity
   int stable_order;
+  // reserved capacity (reservationmanager.go:28-110, nodeclaim.go:240-287): reservation id behind each distinct offering
+  // set (-1: not reserved), remaining capacity per id, ids held per NodeClaim (bit set)
+  int n_rsv, rsv_strict;
+  unsigned rsv_sets;              // bit dd: offering set dd is a reserved one
+  const int32_t* set_rsv;         // [D]
+  int32_t* rsv_cap;               // [n_rsv]
+  unsigned long long* c_rsv;      // [Cmax]
+  int rsv_ct_key, rsv_reserved_val, rsv_id_key;  // FinalizeScheduling's pins (nodeclaim.go:291-307)
+  unsigned long long rsv_val_of[64];             // value bit (in rsv_id_key) of reservation id i
   // the domain fast path (kp_kernels.cuh domain_mask): the one non-hostname key topology groups of fast-path classes
   // use (-1: none), and per claim the value its slot on that key is pinned to (0xff: not a single In value)
   int tk_key;

@@ -58,6 +58,10 @@ struct WInst {
   // c_dom[c]: the value claim c's slot on the topology key is pinned to, 0xff when it is not a single In value (null: the
   // instance does not use the domain fast path)
   uint8_t *c_dom, *g_c_dom;
+  // ReservationManager state of the instance (reservationmanager.go:28-110): remaining capacity per reservation id and
+  // the ids each NodeClaim holds (null / unused when the problem has no reserved offerings)
+  int32_t* rsv_cap;
+  unsigned long long* c_rsv;
   // While the claim order, template ids and failure masks fit, they live in shared memory (CS = claims the shared
   // copies can hold, 0 = not in use); the moment a claim id reaches CS everything migrates to the global arrays below.
   int CS;
@@ -745,34 +749,42 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       sc.rbit = rbit;
       sc.tok = px.tmpl_ok;
       sc.all_tmpl = (sc.tok & d.tmpl_all) == d.tmpl_all;
-      if (px.n_hc >= 0) {  // hostname checks staged with the pod
-        sc.hc = px.hc;
-        sc.hoff = 0;
-        sc.hend = px.n_hc;
-      } else {
-        sc.hc = d.cls_hchk;
-        sc.hoff = px.hoff;
-        sc.hend = px.hend;
-      }
       sc.first_clear = -1;
       sc.first_rclear = -1;
       sc.use_ez = false;
       sc.ez = ~0ull;
-      const int tki = px.tkinfo, asig = TKI_ASIG(tki);
+      // tkinfo (host-computed per class, kp_api.cu upload_tables): which shortcuts the class may take
+      const int tki = px.tkinfo;
       // bit of the pod's requirement set in the claims' "adds nothing" masks
-      const unsigned long long abit = asig < 64 ? 1ull << asig : 0ull;
-      // topology-free and counted by no topology group (and no minValues to re-check on the shrinking type list)
-      const bool fast_ok = fsig >= 0 && abit != 0 && px.roff == px.rend && !d.mv_strict;
+      const unsigned long long abit = (tki & TKI_ABIT) ? 1ull << (tki & 63) : 0ull;
+      // topology-free and counted by no topology group (no minValues / reservations to re-check on the shrinking type list)
+      const bool fast_ok = tki & TKI_FAST;
       // the domain fast path: topology on the hostname key and / or the topology key only (kp_kernels.cuh domain_mask)
-      bool dom_fp = (tki & TKI_FP) && I.c_dom != nullptr;
-      const bool has_tk = tki & TKI_TK;
-      if (dom_fp && has_tk) {
-        bool exact;
-        sc.ez = domain_mask(d, px, lane, &exact);
-        sc.use_ez = exact;
-        dom_fp = exact;
+      bool dom_fp = false, has_tk = false;
+      if (tki & TKI_TOPO) {
+        if (px.n_hc >= 0) {  // hostname checks staged with the pod
+          sc.hc = px.hc;
+          sc.hoff = 0;
+          sc.hend = px.n_hc;
+        } else {
+          sc.hc = d.cls_hchk;
+          sc.hoff = px.hoff;
+          sc.hend = px.hend;
+        }
+        dom_fp = (tki & TKI_FP) && I.c_dom != nullptr;
+        has_tk = tki & TKI_TK;
+        if (dom_fp && has_tk) {
+          bool exact;
+          sc.ez = domain_mask(d, px, lane, &exact);
+          sc.use_ez = exact;
+          dom_fp = exact;
+        }
+        dom_fp = dom_fp && abit != 0;
+      } else {
+        sc.hc = nullptr;
+        sc.hoff = 0;
+        sc.hend = 0;
       }
-      dom_fp = dom_fp && abit != 0;
       int lbf = 0, lbr = 0;
       if (fbit) lbf = __shfl_sync(FULL, fsig < 32 ? lb0 : lb1, fsig & 31);
       if (rbit) lbr = __shfl_sync(FULL, rv < 32 ? lr0 : lr1, rv & 31);
@@ -859,6 +871,16 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           // Strict minValues (nodeclaim.go:464-475): the surviving types must still span enough distinct values
           if (d.mv_strict && ev.ok && !min_values_ok(d, I.c_tmpl[cc], ev.its, lane)) ev.ok = false;
           if (abit && ev.pod_noop && lane == 0) I.amask[cc] |= abit;
+          unsigned long long held = 0, take = 0;
+          if (d.n_rsv && ev.ok) {  // offeringsToReserve (nodeclaim.go:197-200): a ReservedOfferingError is just "next claim" here
+            if (lane < K) scratch[lane] = ev.F;
+            __syncwarp();
+            held = I.c_rsv[cc];
+            bool rerr;
+            take = offerings_to_reserve(d, I.rsv_cap, scratch, ev.its, held, lane, &rerr);
+            __syncwarp();
+            if (rerr) ev.ok = false;
+          }
           if (!ev.ok) {
             if (lane == 0) {
               ulonglong2 mk = I.cmask[cc];
@@ -871,6 +893,10 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           }
           // NodeClaim.Add (nodeclaim.go:207-219)
           claim_store(d, I, cc, lane, ev, ev.changed);
+          if (d.n_rsv) {
+            reservations_commit(d, I.rsv_cap, held, take, lane);
+            if (lane == 0) I.c_rsv[cc] = take;
+          }
           if (lane == 0) {
             cnt[cpos]++;
             if (I.pod_target) {
@@ -952,6 +978,20 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       const int64_t bq = lane < R ? d.tmpl_daemon[(size_t)n * R + lane] : 0;
       Eval ev = eval_candidate(d, px, true, b, bq, tw, -1, E + cnew, scratch, lane);
       if (d.mv_strict && ev.ok && !min_values_ok(d, n, ev.its, lane)) ev.ok = false;
+      unsigned long long take = 0;
+      if (d.n_rsv && ev.ok) {
+        if (lane < K) scratch[lane] = ev.F;
+        __syncwarp();
+        bool rerr;
+        take = offerings_to_reserve(d, I.rsv_cap, scratch, ev.its, 0ull, lane, &rerr);
+        __syncwarp();
+        if (rerr) {
+          // compatible reserved capacity of this NodePool is taken: no NodePool of lower weight may take the pod
+          // (scheduler.go:632-646), and the pod is not relaxed either (:447-453)
+          err = KP_PODERR_RESERVED;
+          break;
+        }
+      }
       if (!ev.ok) continue;
       // NewNodeClaim + Add
       claim_store(d, I, cnew, lane, ev, true);
@@ -967,9 +1007,10 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       // a recycled instance must not inherit failure bits of an earlier claim with this id
       if (lane == 0) {
         I.cmask[cnew] = make_ulonglong2(0ull, 0ull);
-        const int asig_n = TKI_ASIG(px.tkinfo);
-        I.amask[cnew] = (asig_n < 64 && ev.pod_noop) ? 1ull << asig_n : 0ull;
+        I.amask[cnew] = ((px.tkinfo & TKI_ABIT) && ev.pod_noop) ? 1ull << (px.tkinfo & 63) : 0ull;
+        if (d.n_rsv) I.c_rsv[cnew] = take;
       }
+      if (d.n_rsv) reservations_commit(d, I.rsv_cap, 0ull, take, lane);
       // subtractMax (scheduler.go:840-857): remaining -= max capacity over the claim's instance types
       if (lp) {
         for (int r = 0; r < R; r++) {
@@ -1008,7 +1049,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
     }
     if (status != KP_OK) break;
     if (!found) {
-      const int nx = px.relax;  // staged with the class row: cls_relax[Xc]
+      const int nx = err == KP_PODERR_RESERVED ? -1 : px.relax;  // staged with the class row: cls_relax[Xc]
       if (nx >= 0) {  // Preferences.Relax dropped one soft constraint (preferences.go:38-57): same pod, next class row
         Xc = nx;
         // Topology.Update of the relaxed pod (scheduler.go:462): groups only relaxed pods own come into being now

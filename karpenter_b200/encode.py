@@ -24,7 +24,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _abi
-from .model import (CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, NODEPOOL_LABEL, NORMALIZED_LABELS, WELL_KNOWN_LABELS, InstanceType, LabelSelector,
+from .model import (CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, NODEPOOL_LABEL, NORMALIZED_LABELS, RESERVATION_ID_LABEL, WELL_KNOWN_LABELS, InstanceType, LabelSelector,
                     NodePool, NodeSelectorRequirement, Pod, StateNode, Taint, Toleration, quantity_units)
 
 EFFECTS = {"": 0, "NoSchedule": 1, "PreferNoSchedule": 2, "NoExecute": 3}
@@ -177,6 +177,7 @@ class ProblemBuilder:
         self.preference_policy = "Respect"  # or "Ignore": scheduler.IgnorePreferences (scheduler.go:81-101)
         self.min_values_policy = "Strict"   # or "BestEffort": scheduler.MinValuesPolicy (scheduler.go:110-114)
         self.reserved_capacity = True       # FeatureGates.ReservedCapacity (options.go:169-177, default on)
+        self.reserved_offering_strict = True  # DisableReservedCapacityFallback: what the provisioner runs (provisioner.go:347)
 
     # ---- resources ----
     def res_index(self, name: str) -> int:
@@ -203,10 +204,22 @@ class ProblemBuilder:
             name=it.name, reqset=self.reqset([canonical_requirement(r) for r in it.requirements]),
             capacity=self.res_vector(it.capacity), overhead=self.res_vector(it.overhead),
             offerings=[(self.reqset([canonical_requirement(r) for r in o.requirements]), float(o.price),
-                        bool(o.available)) for o in it.offerings])
+                        bool(o.available), self._reservation(o)) for o in it.offerings])
         self.it_index.setdefault(it.name, len(self.its))  # names may repeat (the AWS catalog lists linux + windows rows)
         self.its.append(row)
         return len(self.its) - 1
+
+    def _reservation(self, o):
+        """(interned reservation id, capacity) of a reserved offering, (-1, 0) otherwise.  Offering.ReservationID() is the
+        value of the reservation-id requirement (types.go:432-434)."""
+        ct = [r for r in o.requirements if r.key == CAPACITY_TYPE_LABEL and r.operator == "In" and tuple(r.values) == ("reserved",)]
+        if not ct or not self.reserved_capacity:
+            return (-1, 0)
+        rid = [r.values[0] for r in o.requirements if r.key == RESERVATION_ID_LABEL and r.operator == "In" and len(r.values) == 1]
+        name = rid[0] if rid else ""
+        if not hasattr(self, "reservation_ids"):
+            self.reservation_ids = {}
+        return (self.reservation_ids.setdefault(name, len(self.reservation_ids)), int(o.reservation_capacity))
 
     def add_nodepool(self, np_: NodePool, instance_types: Sequence[str], daemon: Optional[Dict[str, object]] = None):
         """NewNodeClaimTemplate (nodeclaimtemplate.go:57-79): requirements + labels + nodepool/nodeclass labels."""
@@ -466,17 +479,25 @@ class ProblemBuilder:
         P.set("it_capacity", cap)
         P.set("it_cap_present", capp)
         P.set("it_overhead", ovh)
-        oo, orq, opr, oav, orsv = [0], [], [], [], []
+        oo, orq, opr, oav, orsv, orid, ocap = [0], [], [], [], [], [], []
         for it in self.its:
-            for (rs, price, av) in it["offerings"]:
+            for (rs, price, av, (rid, rcap)) in it["offerings"]:
                 orq.append(rs)
                 opr.append(price)
                 oav.append(1 if av else 0)
                 # Offering.CapacityType() == reserved (types.go:385-387) while the ReservedCapacity gate is on
-                orsv.append(1 if self.reserved_capacity and any(
-                    r[0] == CAPACITY_TYPE_LABEL and not r[1] and tuple(r[2]) == ("reserved",) for r in self.reqsets.rows[rs]) else 0)
+                orsv.append(1 if rid >= 0 else 0)
+                orid.append(rid)
+                ocap.append(rcap)
             oo.append(len(orq))
         P.set("off_reserved", orsv)
+        n_rsv = len(getattr(self, "reservation_ids", {}))
+        if n_rsv:
+            P.set("off_reservation_id", orid)
+            P.set("off_reservation_capacity", ocap)
+        P.set("n_reservations", n_rsv)
+        P.set("reserved_offering_strict", 1 if self.reserved_offering_strict else 0)
+        self._reservation_fields_pending = n_rsv
         P.set("it_off_off", oo)
         P.set("off_reqset", orq)
         P.set("off_price", opr)
@@ -612,6 +633,16 @@ class ProblemBuilder:
         enc = EncodedProblem(P, keys, {k: sorted(values[k]) for k in keys}, list(self.resources),
                              [it["name"] for it in self.its], [t["name"] for t in tmpls], [n["name"] for n in nodes],
                              node_pos, nodes)
+        ids = getattr(self, "reservation_ids", {})
+        enc.reservation_names = [n for n, _ in sorted(ids.items(), key=lambda kv: kv[1])]
+        if ids:  # FinalizeScheduling's pins (nodeclaim.go:291-307) are applied by the solver itself
+            P.set("reservation_capacity_type_key", enc.key_id(CAPACITY_TYPE_LABEL))
+            P.set("reservation_reserved_value", enc.value_id(CAPACITY_TYPE_LABEL, "reserved"))
+            P.set("reservation_id_key", enc.key_id(RESERVATION_ID_LABEL))
+            P.set("reservation_value", [enc.value_id(RESERVATION_ID_LABEL, n) for n in enc.reservation_names])
+        else:
+            P.set("reservation_capacity_type_key", -1)
+            P.set("reservation_id_key", -1)
         # what the decoder needs to report minValues per NodeClaim (nodeclaim.go:186-191)
         enc.min_values_policy = self.min_values_policy
         enc.tmpl_min_values = []
@@ -667,6 +698,11 @@ class EncodedProblem:
                                 lte=int(res["claim_req_lte"][claim, k]) if f & 4 else None)
             woff += words
         return out
+
+    def decode_reservations(self, res: dict, claim: int) -> List[str]:
+        """NodeClaim.reservedOfferings as reservation ids (kp_result.claim_reservations)."""
+        m = int(res["claim_reservations"][claim]) if "claim_reservations" in res and len(res["claim_reservations"]) else 0
+        return [n for i, n in enumerate(getattr(self, "reservation_names", [])) if m >> i & 1]
 
     def decode_min_values(self, res: dict, claim: int) -> Dict[str, dict]:
         """minValues of the NodeClaim's requirements.  Strict: the NodePool's.  BestEffort: lowered to the number of distinct

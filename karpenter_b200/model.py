@@ -174,11 +174,18 @@ class Pod:
     deletion_cost: Optional[str] = None
 
 
+# cloudprovider.ReservationIDLabel (pkg/cloudprovider/types.go:49-52) is the provider's to name; this is the fake provider's
+# (pkg/test/v1alpha1/labels.go:20), which also registers it as a well-known label (fake/cloudprovider.go:44-48)
+RESERVATION_ID_LABEL = "karpenter.test.sh/reservation-id"
+WELL_KNOWN_LABELS.add(RESERVATION_ID_LABEL)
+
+
 @dataclass
 class Offering:
     requirements: List[NodeSelectorRequirement]
     price: float
     available: bool = True
+    reservation_capacity: int = 0  # Offering.ReservationCapacity (types.go:372-379); the id is the reservation-id requirement
 
 
 @dataclass

@@ -24,6 +24,7 @@ from .model import (CAPACITY_TYPE_LABEL, InstanceType, NodeClaimResult, NodePool
 POD_ERRORS = {
     1: "nodepool requirements filtered out all available instance types",                      # scheduler.go:511
     2: "incompatible with every nodepool (taints, requirements, topology, resources or offerings)",  # scheduler.go:683
+    3: "one or more instance types with compatible reserved offerings are available, but could not be reserved",  # nodeclaim.go:277
 }
 
 
@@ -99,7 +100,7 @@ class Scheduler:
             else:
                 by_claim.setdefault(-2 - t, []).append(p)
         for k in range(res["n_claims"]):
-            reqs = enc.decode_requirements(res, k)
+            reqs = enc.decode_requirements(res, k)  # FinalizeScheduling's reservation pins are already in
             for key, mv in enc.decode_min_values(res, k).items():
                 reqs.setdefault(key, dict(complement=True, values=[], gte=None, lte=None)).update(mv)
             claims.append(NodeClaimResult(

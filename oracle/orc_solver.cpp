@@ -29,6 +29,7 @@ namespace orc {
 
 struct InflightClaim {
   int tmpl;
+  std::vector<int> reserved;  // reservation ids of NodeClaim.reservedOfferings (ascending)
   Requirements reqs;
   std::vector<int> its;  // InstanceTypeOptions (global ids, template order)
   Res requests;          // Spec.Resources.Requests
@@ -101,8 +102,49 @@ struct Scheduler {
   Counters ctr;
   bool stable_order;
   WorkerPool* pool = nullptr;  // null: evaluate candidates serially
+  // ReservationManager (reservationmanager.go:28-110): remaining capacity per reservation id; which ids a NodeClaim
+  // holds lives on the claim (InflightClaim::reserved == reservations[hostname])
+  std::vector<int> rsv_cap;
+  bool rsv_strict;
 
-  Scheduler(const Prob& prob) : P(prob), p(prob.p), topo(prob), stable_order(prob.p->claim_order_mode == 1) {}
+  Scheduler(const Prob& prob) : P(prob), p(prob.p), topo(prob), stable_order(prob.p->claim_order_mode == 1) {
+    rsv_strict = p->reserved_offering_strict != 0;
+    // NewReservationManager (:33-52): the least capacity any offering of the id reports
+    rsv_cap.assign(p->n_reservations > 0 ? p->n_reservations : 0, -1);
+    if (p->off_reserved && p->off_reservation_id)
+      for (int t = 0; t < p->n_its; t++)
+        for (int o = p->it_off_off[t]; o < p->it_off_off[t + 1]; o++) {
+          if (!p->off_reserved[o]) continue;
+          const int id = p->off_reservation_id[o], cap = p->off_reservation_capacity[o];
+          if (rsv_cap[id] < 0 || rsv_cap[id] > cap) rsv_cap[id] = cap;
+        }
+    for (int& c : rsv_cap)
+      if (c < 0) c = 0;
+  }
+
+  // offeringsToReserve (nodeclaim.go:240-287).  false == ReservedOfferingError (strict mode only)
+  bool offerings_to_reserve(const InflightClaim& c, const std::vector<int>& its, const Requirements& reqs,
+                            std::vector<int>* out) const {
+    out->clear();
+    if (rsv_cap.empty()) return true;
+    bool has_compatible = false;
+    std::set<int> ids;
+    for (int it : its)
+      for (int o = p->it_off_off[it]; o < p->it_off_off[it + 1]; o++) {
+        if (!p->off_reserved[o] || !p->off_available[o]) continue;
+        if (!compatible(P, P, reqs, P.reqsets[p->off_reqset[o]], true)) continue;
+        has_compatible = true;
+        const int id = p->off_reservation_id[o];
+        const bool held = std::find(c.reserved.begin(), c.reserved.end(), id) != c.reserved.end();
+        if (held || rsv_cap[id] > 0) ids.insert(id);  // ReservationManager.CanReserve (:55-70)
+      }
+    if (rsv_strict) {
+      if (has_compatible && ids.empty()) return false;
+      if (!c.reserved.empty() && ids.empty()) return false;
+    }
+    out->assign(ids.begin(), ids.end());
+    return true;
+  }
 
   bool offering_compatible(const Requirements& reqs, int it) const {
     for (int o = p->it_off_off[it]; o < p->it_off_off[it + 1]; o++)
@@ -198,7 +240,9 @@ struct Scheduler {
   }
 
   // nodeclaim.go:114-202
-  bool claim_can_add(InflightClaim& c, int cls, Requirements* out_reqs, std::vector<int>* out_its) {
+  bool claim_can_add(InflightClaim& c, int cls, Requirements* out_reqs, std::vector<int>* out_its,
+                     std::vector<int>* out_rsv = nullptr, bool* rsv_error = nullptr) {
+    if (rsv_error) *rsv_error = false;
     int taintset = p->tmpl_taintset[c.tmpl];
     if (!P.tolerates(taintset, p->class_tolset[cls])) return false;
     const Requirements& pod_reqs = P.reqsets[p->class_reqset[cls]];
@@ -212,13 +256,26 @@ struct Scheduler {
     Res total = merge(P.R, c.requests, class_requests(cls));
     std::vector<int> rem = filter_instance_types(c.its, reqs, total);
     if (rem.empty()) return false;
+    std::vector<int> rsv;
+    if (!offerings_to_reserve(c, rem, reqs, &rsv)) {  // nodeclaim.go:197-200
+      if (rsv_error) *rsv_error = true;
+      return false;
+    }
+    if (out_rsv) *out_rsv = rsv;
     *out_reqs = reqs;
     *out_its = rem;
     return true;
   }
 
   // nodeclaim.go:207-219
-  void claim_add(InflightClaim& c, int64_t pod, int cls, const Requirements& reqs, const std::vector<int>& its) {
+  void claim_add(InflightClaim& c, int64_t pod, int cls, const Requirements& reqs, const std::vector<int>& its,
+                 const std::vector<int>& rsv = {}) {
+    // Reserve the new ids, release the ones the tighter requirements ruled out (nodeclaim.go:216-218, :223-235)
+    for (int id : rsv)
+      if (std::find(c.reserved.begin(), c.reserved.end(), id) == c.reserved.end()) rsv_cap[id]--;
+    for (int id : c.reserved)
+      if (std::find(rsv.begin(), rsv.end(), id) == rsv.end()) rsv_cap[id]++;
+    c.reserved = rsv;
     c.pods.push_back(pod);
     c.its = its;
     c.requests = merge(P.R, c.requests, class_requests(cls));
@@ -265,7 +322,7 @@ struct Scheduler {
     struct Slot_ {
       int idx = INT32_MAX;
       Requirements r;
-      std::vector<int> its;
+      std::vector<int> its, rsv;
     };
     std::vector<Slot_> slots(pool->W);
     pool->run([&](int w) {
@@ -273,12 +330,13 @@ struct Scheduler {
         int i = next.fetch_add(1, std::memory_order_relaxed);
         if (i >= n || i > best.load(std::memory_order_relaxed)) return;
         Requirements r;
-        std::vector<int> its;
-        if (claim_can_add(*new_claims[i], cls, &r, &its)) {
+        std::vector<int> its, rsv;
+        if (claim_can_add(*new_claims[i], cls, &r, &its, &rsv)) {
           if (i < slots[w].idx) {
             slots[w].idx = i;
             slots[w].r = std::move(r);
             slots[w].its = std::move(its);
+            slots[w].rsv = std::move(rsv);
           }
           int cur = best.load();
           while (i < cur && !best.compare_exchange_weak(cur, i)) {
@@ -295,7 +353,7 @@ struct Scheduler {
     ctr.inflight += b + 1;
     for (auto& sl : slots)
       if (sl.idx == b) {
-        claim_add(*new_claims[b], pod, cls, sl.r, sl.its);
+        claim_add(*new_claims[b], pod, cls, sl.r, sl.its, sl.rsv);
         *target = KP_TARGET_CLAIM(new_claims[b]->created);
         return true;
       }
@@ -307,10 +365,10 @@ struct Scheduler {
     if (pool && new_claims.size() >= 32) return add_to_inflight_parallel(pod, cls, target);
     for (size_t i = 0; i < new_claims.size(); i++) {
       Requirements r;
-      std::vector<int> its;
+      std::vector<int> its, rsv;
       ctr.inflight++;
-      if (claim_can_add(*new_claims[i], cls, &r, &its)) {
-        claim_add(*new_claims[i], pod, cls, r, its);
+      if (claim_can_add(*new_claims[i], cls, &r, &its, &rsv)) {
+        claim_add(*new_claims[i], pod, cls, r, its, rsv);
         *target = KP_TARGET_CLAIM(new_claims[i]->created);
         return true;
       }
@@ -319,7 +377,8 @@ struct Scheduler {
   }
 
   // scheduler.go:592-684
-  bool add_to_new_claim(int64_t pod, int cls, int* target) {
+  bool add_to_new_claim(int64_t pod, int cls, int* target, bool* reserved_error) {
+    *reserved_error = false;
     for (int n = 0; n < p->n_templates; n++) {
       if (!tmpl_alive[n]) continue;
       ctr.tmpl++;
@@ -355,11 +414,20 @@ struct Scheduler {
       c.its = its;
       c.requests = P.res_row(p->tmpl_daemon, n, P.all_mask());
       Requirements r;
-      std::vector<int> rem_its;
-      if (!claim_can_add(c, cls, &r, &rem_its)) continue;
+      std::vector<int> rem_its, rsv;
+      bool rsv_err = false;
+      if (!claim_can_add(c, cls, &r, &rem_its, &rsv, &rsv_err)) {
+        // A NodePool with compatible reserved capacity that is taken: no fallback to a NodePool of lower weight
+        // (scheduler.go:632-646) -- the lowest index that succeeded OR reported this error decides
+        if (rsv_err) {
+          *reserved_error = true;
+          return false;
+        }
+        continue;
+      }
       auto owned = std::make_unique<InflightClaim>(std::move(c));
       owned->created = (int)claim_store.size();
-      claim_add(*owned, pod, cls, r, rem_its);
+      claim_add(*owned, pod, cls, r, rem_its, rsv);
       new_claims.push_back(owned.get());
       *target = KP_TARGET_CLAIM(owned->created);
       // subtractMax (scheduler.go:840-857)
@@ -393,8 +461,9 @@ struct Scheduler {
       *err = KP_PODERR_NO_TEMPLATES;
       return false;
     }
-    if (add_to_new_claim(pod, cls, target)) return true;
-    *err = KP_PODERR_INCOMPATIBLE;
+    bool reserved_error = false;
+    if (add_to_new_claim(pod, cls, target, &reserved_error)) return true;
+    *err = reserved_error ? KP_PODERR_RESERVED : KP_PODERR_INCOMPATIBLE;
     return false;
   }
 
@@ -440,6 +509,7 @@ struct Scheduler {
           placed = true;
           break;
         }
+        if (err == KP_PODERR_RESERVED) break;  // never relax on a ReservedOfferingError (scheduler.go:447-453)
         int nx = p->class_relax_next ? p->class_relax_next[cls] : -1;  // Preferences.Relax (preferences.go:38-57)
         if (nx < 0) break;
         cls = nx;
@@ -455,9 +525,23 @@ struct Scheduler {
         last_len[pod] = q.size() - head;
       }
     }
-    // FinalizeScheduling (nodeclaim.go:291-307): drop the hostname requirement
+    // FinalizeScheduling (nodeclaim.go:291-307): drop the hostname requirement; a claim that holds reservations is
+    // pinned to capacity-type In [reserved] and reservation-id In [held ids]
     if (P.hostname_key >= 0)
       for (auto* c : new_claims) c->reqs.m.erase(P.hostname_key);
+    if (!rsv_cap.empty() && p->reservation_capacity_type_key >= 0 && p->reservation_id_key >= 0 && p->reservation_value)
+      for (auto* c : new_claims) {
+        if (c->reserved.empty()) continue;
+        Requirement ct;
+        ct.key = p->reservation_capacity_type_key;
+        ct.values.push_back(p->reservation_reserved_value);
+        c->reqs.m[ct.key] = ct;  // overwritten, not intersected (:300)
+        Requirement rid;
+        rid.key = p->reservation_id_key;
+        for (int id : c->reserved) rid.values.push_back(p->reservation_value[id]);
+        std::sort(rid.values.begin(), rid.values.end());
+        c->reqs.add(P, rid);
+      }
   }
 };
 
@@ -532,12 +616,14 @@ static void export_requirements(const Prob& P, const Requirements& reqs, int mas
   }
 }
 
-// reserved-capacity offerings need the ReservationManager (reservationmanager.go:28-110): not restated, refused
-static bool has_reserved_offerings(const kp_problem* p) {
+// reserved offerings without their reservation id / capacity cannot be run through the ReservationManager
+static bool reserved_offerings_malformed(const kp_problem* p) {
   if (!p->off_reserved) return false;
   for (int t = 0; t < p->n_its; t++)
     for (int o = p->it_off_off[t]; o < p->it_off_off[t + 1]; o++)
-      if (p->off_reserved[o] && p->off_available[o]) return true;
+      if (p->off_reserved[o] && (!p->off_reservation_id || !p->off_reservation_capacity || p->off_reservation_id[o] < 0 ||
+                                 p->off_reservation_id[o] >= p->n_reservations || p->n_reservations > 64))
+        return true;
   return false;
 }
 
@@ -577,6 +663,9 @@ static void fill_result(const Prob& P, Scheduler& s, const std::vector<int32_t>&
   out->claim_req_gte = (int64_t*)calloc(c1 * (K ? K : 1), sizeof(int64_t));
   out->claim_req_lte = (int64_t*)calloc(c1 * (K ? K : 1), sizeof(int64_t));
   out->claim_req_mask = (uint64_t*)calloc(c1 * (MW ? MW : 1), sizeof(uint64_t));
+  out->claim_reservations = (uint64_t*)calloc(c1, sizeof(uint64_t));
+  for (int k = 0; k < C; k++)
+    for (int id : s.claim_store[k]->reserved) out->claim_reservations[k] |= 1ull << id;
   for (size_t pos = 0; pos < s.new_claims.size(); pos++) out->claim_rank[s.new_claims[pos]->created] = (int32_t)pos;
   for (int k = 0; k < C; k++) {
     InflightClaim& c = *s.claim_store[k];
@@ -626,7 +715,7 @@ int orc_solve(const kp_problem* p, kp_result* out) { return orc_solve_mt(p, out,
 
 // threads > 1: in-flight candidates are evaluated by a worker pool like the reference's parallelizeUntil
 int orc_solve_mt(const kp_problem* p, kp_result* out, int threads) {
-  if (has_reserved_offerings(p)) return KP_ERR_UNSUPPORTED;
+  if (reserved_offerings_malformed(p)) return KP_ERR_INVALID;
   if (p->n_resources > KP_MAX_RESOURCES) return KP_ERR_CAPACITY;
   Prob P(p);
   Scheduler s(P);
@@ -670,6 +759,7 @@ void orc_result_free(kp_result* r) {
   free(r->claim_req_mask);
   free(r->group_domain_off);
   free(r->domain_counts);
+  free(r->claim_reservations);
   memset(r, 0, sizeof(*r));
 }
 
@@ -704,7 +794,8 @@ int orc_consolidate(const kp_problem* p, const kp_consol_input* in, kp_consol_re
 }
 // subsets are independent simulations: `threads` workers take them round-robin
 int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol_result* out, int threads) {
-  if (has_min_values(p) || has_reserved_offerings(p)) return KP_ERR_UNSUPPORTED;
+  if (has_min_values(p)) return KP_ERR_UNSUPPORTED;
+  if (reserved_offerings_malformed(p)) return KP_ERR_INVALID;
   Prob P(p);
   Pricing pr(P);
   int ITW = (p->n_its + 63) / 64;

@@ -97,6 +97,69 @@ def test_fuzz_parity_gpu(soft):
     assert ran >= (CAP * 3 // 4 if CAP else 300), ran
 
 
+def encode_reserved(seed):
+    """the soft problems with capacity reservations on some instance types (reserved offerings of capacity 1-3, some shared
+    between types); strict mode on two seeds of three, fallback on the third"""
+    import random
+    from karpenter_b200.model import CAPACITY_TYPE_LABEL, RESERVATION_ID_LABEL, ZONE_LABEL, NodeSelectorRequirement, Offering
+    pools, per_pool, nodes, pl = fuzz.problem(seed, n_pods=[5, 20, 60, 150][seed % 4])
+    fuzz.soften(seed, pools, pl)
+    rng = random.Random(31_000 + seed)
+    its = per_pool[pools[0].name]
+    ids = [f"r-{i}" for i in range(rng.randint(1, 5))]
+    for it in its:
+        if rng.random() < 0.6:
+            for r in it.requirements:
+                if r.key == CAPACITY_TYPE_LABEL and "reserved" not in r.values:
+                    object.__setattr__(r, "values", tuple(r.values) + ("reserved",))
+            for _ in range(rng.randint(1, 2)):
+                it.offerings = list(it.offerings) + [Offering(
+                    [NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "In", ("reserved",)),
+                     NodeSelectorRequirement(ZONE_LABEL, "In", (rng.choice(fuzz.ZONES),)),
+                     NodeSelectorRequirement(RESERVATION_ID_LABEL, "In", (rng.choice(ids),))],
+                    0.0001, rng.random() < 0.9, reservation_capacity=rng.randint(1, 3))]
+    for p in pools:  # let the pools launch reserved capacity
+        for i, r in enumerate(p.requirements):
+            if r.key == CAPACITY_TYPE_LABEL and r.operator == "In" and "reserved" not in r.values:
+                p.requirements[i] = NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "In", tuple(r.values) + ("reserved",))
+
+    class S(Scheduler):
+        def _builder(self):
+            b = super()._builder()
+            b.reserved_offering_strict = seed % 3 != 2
+            return b
+    return S(pools, per_pool, nodes, claim_order="go" if seed % 3 else "stable").encode(pl)
+
+
+def test_reserved_generator_reserves():
+    stats = collections.Counter()
+    for seed in range(120):
+        enc = encode_reserved(seed)
+        res = oracle_lib.solve(enc.problem)
+        stats["held"] += int(res["claim_reservations"].any())
+        stats["reserved_errors"] += int((res["pod_error"] == 3).any())
+        stats["multi"] += int(res["n_claims"] > 2)
+    assert stats["held"] >= 40 and stats["reserved_errors"] >= 10 and stats["multi"] >= 40, stats
+
+
+@pytest.mark.gpu
+def test_fuzz_reserved_capacity_parity_gpu():
+    h = _native.Handle()
+    bad = []
+    try:
+        for seed in range(CAP or 250):
+            enc = encode_reserved(seed)
+            orc = oracle_lib.solve(enc.problem)
+            gpu = h.solve(enc.problem)
+            try:
+                assert_same(gpu, orc, f"seed {seed} ")
+            except AssertionError as e:
+                bad.append((seed, str(e)[:200]))
+    finally:
+        h.close()
+    assert not bad, bad[:10]
+
+
 def consolidation_case(seed):
     """A random small cluster (topology-free pods bound to nodes) and random candidate sets of 1-3 nodes."""
     import random

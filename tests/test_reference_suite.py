@@ -325,37 +325,6 @@ def test_multi_node_replacement_by_one_of_the_removed_types(which):  # multinode
     assert single.decision == "delete"
 
 
-# ---- what the library refuses instead of approximating ---------------------------------------------------------------
-def _reserved_catalog():
-    its = fake.default_instance_types()
-    its[0].offerings = list(its[0].offerings) + [
-        Offering([req(CAPACITY_TYPE_LABEL, "In", "reserved"), req(ZONE_LABEL, "In", "test-zone-1")], 0.01, True)]
-    return its
-
-
-def test_oracle_refuses_reserved_capacity_offerings():
-    from karpenter_b200.scheduler import Scheduler
-    from tests import oracle_lib
-    np_ = _pool()
-    s = Scheduler([np_], {np_.name: _reserved_catalog()}, backend=oracle_lib.solve)
-    with pytest.raises(RuntimeError):
-        s.solve(Cluster("oracle").pods(1))
-
-
-@pytest.mark.gpu
-def test_library_refuses_reserved_capacity_offerings():
-    from karpenter_b200 import _native
-    from karpenter_b200.scheduler import Scheduler
-    np_ = _pool()
-    s = Scheduler([np_], {np_.name: _reserved_catalog()})
-    try:
-        with pytest.raises(_native.SolverError) as e:
-            s.solve(Cluster("gpu").pods(1))
-        assert e.value.code == 5 and "reserved" in str(e.value)
-    finally:
-        s.close()
-
-
 # ---- NodePool limits (provisioning/suite_test.go:742-935) -------------------------------------------------------------
 def _limited(which, **limits):
     return Cluster(which, pools=[NodePool(name="default", requirements=[req(CAPACITY_TYPE_LABEL, "In", "spot", "on-demand", "reserved")],
