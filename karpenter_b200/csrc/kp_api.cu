@@ -100,6 +100,7 @@ struct Instance {
   void *sort_keys_a = nullptr, *sort_keys_b = nullptr, *sort_tmp = nullptr;
   int32_t* sort_perm_b = nullptr;
   size_t sort_tmp_bytes = 0;
+  bool lean = false;  // no topology group / bound / minValues / reservation: the lean instantiation of the solver serves it
   // shared-memory plan of the solve CTA (plan_solve)
   int CS = 0, CR = 0;
   size_t smem = 0;
@@ -885,6 +886,7 @@ static int prep_solve(kp_handle* h) {
     CS = lo;
   }
   if (const char* lim = getenv("KP_CS_LIMIT")) CS = std::min(CS, std::max(0, atoi(lim)) / 32 * 32);  // test knob
+  in.lean = in.host.G == 0 && !in.host.has_bounds && !in.host.min_values_strict && in.host.n_rsv == 0 && !getenv("KP_NO_LEAN");
   in.CS = CS;
   in.CR = CR;
   in.smem = fixed + tb + (CS ? small_bytes(CS) : 0) + 64;
@@ -921,9 +923,12 @@ static int run_solve(kp_handle* h) {
   h->stats.kernel_launches = 0;
   rc = prep_solve(h);
   if (rc != KP_OK) return rc;
-  CK(cudaFuncSetAttribute(k_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)in.smem));
+  CK(cudaFuncSetAttribute(in.lean ? k_wsolve<true> : k_wsolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)in.smem));
   CK(cudaEventRecord(h->ev2, h->stream));
-  k_wsolve<<<1, 64, in.smem, h->stream>>>(d, in.CS, in.CR);
+  if (in.lean)
+    k_wsolve<true><<<1, 64, in.smem, h->stream>>>(d, in.CS, in.CR);
+  else
+    k_wsolve<false><<<1, 64, in.smem, h->stream>>>(d, in.CS, in.CR);
   h->stats.kernel_launches++;
   rc = reduce_counters(h, {&in});
   if (rc != KP_OK) return rc;
@@ -1241,9 +1246,14 @@ static int run_batch(kp_handle* h, int64_t deadline_ms, std::vector<int32_t>& st
   h->cur = &h->main;
   CK(cudaMemcpyAsync(h->d_batch_devs, devs.data(), sizeof(KpDev) * n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_batch_plan, plan.data(), sizeof(int2) * n, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaFuncSetAttribute(k_wsolve_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bool all_lean = true;
+  for (Instance* b : h->batch) all_lean = all_lean && b->lean;
+  CK(cudaFuncSetAttribute(all_lean ? k_wsolve_batch<true> : k_wsolve_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaEventRecord(h->ev2, h->stream));
-  k_wsolve_batch<<<n, 64, smem, h->stream>>>(h->d_batch_devs, h->d_batch_plan);
+  if (all_lean)
+    k_wsolve_batch<true><<<n, 64, smem, h->stream>>>(h->d_batch_devs, h->d_batch_plan);
+  else
+    k_wsolve_batch<false><<<n, 64, smem, h->stream>>>(h->d_batch_devs, h->d_batch_plan);
   h->stats.kernel_launches++;
   {
     int rc = reduce_counters(h, h->batch);
@@ -1812,9 +1822,13 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   const size_t fixed = KP_ALIGN16(sizeof(ConsolShared));
   size_t tb = plan_tables(h, fixed, budget);
   size_t smem = fixed + tb + 64;
-  CK(cudaFuncSetAttribute(k_consolidate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool lean = !t.has_bounds && !t.min_values_strict && t.n_rsv == 0 && !getenv("KP_NO_LEAN");  // (G == 0 on this path)
+  CK(cudaFuncSetAttribute(lean ? k_consolidate<true> : k_consolidate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1, n_sm = 148;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_consolidate, CONSOL_WARPS * 32, smem);
+  if (lean)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_consolidate<true>, CONSOL_WARPS * 32, smem);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_consolidate<false>, CONSOL_WARPS * 32, smem);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
   per_sm = std::max(per_sm, 1);
   int grid = std::min(n_sm * per_sm, std::max(1, (S + CONSOL_WARPS - 1) / CONSOL_WARPS));
@@ -1895,7 +1909,10 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   rc = launch_node_cand(h);
   if (rc != KP_OK) return rc;
   if (S > 0) {
-    k_consolidate<<<grid, CONSOL_WARPS * 32, smem, h->stream>>>(d, q);
+    if (lean)
+      k_consolidate<true><<<grid, CONSOL_WARPS * 32, smem, h->stream>>>(d, q);
+    else
+      k_consolidate<false><<<grid, CONSOL_WARPS * 32, smem, h->stream>>>(d, q);
     h->stats.kernel_launches++;
   }
   CK(cudaEventRecord(h->ev1, h->stream));

@@ -146,6 +146,7 @@ struct WSolveShared {
 };
 
 // warp 0: the solver; warp 1: the pod stager (see StageRing)
+template <bool LEAN>
 __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WSolveShared& sh = *reinterpret_cast<WSolveShared*>(smem_raw);
@@ -243,10 +244,10 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     stager_run(d, I, &sh.ring, lane);
     return;
   }
-  wsolve_run<false, true>(d, I, sh.ring.slot[0], sh.scratch, lane, &sh.ring);
+  wsolve_run<false, true, LEAN>(d, I, sh.ring.slot[0], sh.scratch, lane, &sh.ring);
   const int nC = I.n_claims;
   claim_rows_flush(d, I, nC, lane);
-  claims_finalize(d, I.c_sflags, I.c_smask, I.c_rsv, nC, lane);
+  if (!LEAN) claims_finalize(d, I.c_sflags, I.c_smask, I.c_rsv, nC, lane);
   if (I.CS > 0) {  // the host reads the final order (claim_rank) and template ids from global memory
     for (int i = lane; i < nC; i += 32) {
       d_in.order[i] = I.order[i];
@@ -269,14 +270,16 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     d.counters[9] = I.fast_commits;
   }
 }
+template <bool LEAN>
 __global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS, int CR) {
-  wsolve_cta(d_in, CS, CR);
+  wsolve_cta<LEAN>(d_in, CS, CR);
 }
 // Many Scheduler instances in one launch, one CTA (== one SM) each: NodePool shards of a provisioning pass, or the
 // candidate sets of a consolidation pass whose pods carry topology constraints (SimulateScheduling, helpers.go:51-142).
 // Instances share nothing but the device; plan[b] = {CS, CR} of instance b.
+template <bool LEAN>
 __global__ void __launch_bounds__(64, 1) k_wsolve_batch(const KpDev* __restrict__ devs, const int2* __restrict__ plan) {
-  wsolve_cta(devs[blockIdx.x], plan[blockIdx.x].x, plan[blockIdx.x].y);
+  wsolve_cta<LEAN>(devs[blockIdx.x], plan[blockIdx.x].x, plan[blockIdx.x].y);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -626,6 +629,7 @@ struct ConsolShared {
 #ifndef CONSOL_MIN_CTAS
 #define CONSOL_MIN_CTAS 2
 #endif
+template <bool LEAN>
 __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolidate(const __grid_constant__ KpDev d_in,
                                                                     const __grid_constant__ KpConsol q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -769,12 +773,12 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolid
       I.tmpl_remaining[i] = rem;
     }
     __syncwarp();
-    wsolve_run<true, false>(d, I, W.ctx, W.scratch, lane);
+    wsolve_run<true, false, LEAN>(d, I, W.ctx, W.scratch, lane);
     if (I.status != KP_OK) {
       if (lane == 0) *q.status = I.status;
       break;
     }
-    claims_finalize(d, I.c_sflags, I.c_smask, I.c_rsv, I.n_claims, lane);
+    if (!LEAN) claims_finalize(d, I.c_sflags, I.c_smask, I.c_rsv, I.n_claims, lane);
     // ---- computeConsolidation (consolidation.go:136-229)
     consol_decide(d, q, slot, W.scratch, I.c_sflags, I.c_smask, I.c_sgte, I.c_slte, I.c_its, I.n_claims > 0 ? I.c_tmpl[0] : -1,
                   I.c_req, sn, snodes, I.n_unsched + I.n_uninit, I.n_claims, s, lane);

@@ -274,6 +274,8 @@ __device__ __forceinline__ void pod_rec(const KpDev& d, const PodCtx& px, int i,
 //   base       lane k: the candidate's current requirement slot
 //   host       index of the candidate's hostname domain in host_cnt
 //   scratch    per-warp shared memory, KP_MAXK slots
+// LEAN: the problem has no topology group, no Gt / Lt bound, no minValues and no reservation -- those parts compile away
+template <bool LEAN = false>
 __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px, bool is_claim, const Slot& base,
                                                int64_t base_q, uint64_t base_its, int base_j, int host, Slot* scratch,
                                                int lane) {
@@ -290,7 +292,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   KeyInfo ki = lane < K ? key_info(d, lane) : KeyInfo{d.val_int, 0ull, 0ull};
   Slot pod = lane < K ? px.pod_slot[lane] : slot_absent();
   // requirements.Compatible(pod requirements) then Add
-  const bool nb = !d.has_bounds;
+  const bool nb = LEAN || !d.has_bounds;
   bool bad = lane < K && !(nb ? slot_compatible_nb(base, pod, wk, allow_undef) : slot_compatible(ki, base, pod, wk, allow_undef));
   if (__any_sync(FULL, bad)) {
     ev.compat_fail = true;
@@ -298,7 +300,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
   }
   Slot M = lane < K ? (nb ? slot_add_nb(base, pod) : slot_add(ki, base, pod)) : slot_absent();
   // Topology.AddRequirements (topology.go:226-248)
-  const int nm = px.mend - px.moff;
+  const int nm = LEAN ? 0 : px.mend - px.moff;
   if (nm > 0) {
     ev.pod_noop = !__any_sync(FULL, lane < K && !slot_eq(M, base));
     Slot Tt = M;

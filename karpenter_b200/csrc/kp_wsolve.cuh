@@ -104,6 +104,7 @@ __device__ __forceinline__ int ov_find(const WInst& I, int node, int lane) {
 }
 
 // a NodeClaim's row: requirement slot of key `lane`, requests / threshold row of resource `lane`, instance-type word `lane`
+template <bool LEAN = false>
 __device__ __forceinline__ void claim_load(const KpDev& d, const WInst& I, int c, int lane, Slot* b, int64_t* q,
                                            uint64_t* its, int* j) {
   const int K = d.K, R = d.R, ITW = d.ITW;
@@ -132,14 +133,15 @@ __device__ __forceinline__ void claim_load(const KpDev& d, const WInst& I, int c
     }
     if (lane < ITW) *its = I.c_its[(size_t)c * ITW + lane];
   }
-  if (d.has_bounds && lane < K) {
+  if (!LEAN && d.has_bounds && lane < K) {
     b->gte = I.c_sgte[(size_t)c * K + lane];
     b->lte = I.c_slte[(size_t)c * K + lane];
   }
 }
+template <bool LEAN = false>
 __device__ __forceinline__ void claim_store(const KpDev& d, WInst& I, int c, int lane, const Eval& ev, bool slots) {
   const int K = d.K, R = d.R, ITW = d.ITW;
-  if (slots && I.c_dom && lane == d.tk_key)
+  if (!LEAN && slots && I.c_dom && lane == d.tk_key)
     I.c_dom[c] = (ev.F.f == SF_PRESENT && __popcll(ev.F.m) == 1) ? (uint8_t)(__ffsll((long long)ev.F.m) - 1) : (uint8_t)0xff;
   if (c < I.CR) {
     if (slots && lane < K) {
@@ -162,7 +164,7 @@ __device__ __forceinline__ void claim_store(const KpDev& d, WInst& I, int c, int
     }
     if (lane < ITW) I.c_its[(size_t)c * ITW + lane] = ev.its;
   }
-  if (slots && d.has_bounds && lane < K) {
+  if (!LEAN && slots && d.has_bounds && lane < K) {
     I.c_sgte[(size_t)c * K + lane] = ev.F.gte;
     I.c_slte[(size_t)c * K + lane] = ev.F.lte;
   }
@@ -227,7 +229,7 @@ struct ScanCtx {
   const int4* hc;                      // the hostname checks: staged with the pod, or cls_hchk + hoff
 };
 // U sub-chunks of 32 positions per step: their loads are independent, so a step costs one memory latency, not U.
-template <int U>
+template <int U, bool LEAN = false>
 __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, const int32_t* ord, int nC, int from,
                                               ScanCtx& sc, int lane, int E, int* cc_out) {
   const ulonglong2* cm = I.cmask;
@@ -248,7 +250,7 @@ __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, co
         if (pass[u] && !sc.all_tmpl) pass[u] = (sc.tok >> I.c_tmpl[c[u]]) & 1ull;
       }
     }
-    if (sc.use_ez) {
+    if (!LEAN && sc.use_ez) {
 #pragma unroll
       for (int u = 0; u < U; u++)
         if (pass[u]) {
@@ -258,7 +260,7 @@ __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, co
     }
     // hostname groups: a NodeClaim is exactly one hostname domain (topologygroup.go:235-247,317-333,402-408).  Two
     // groups per round, so that all their counter loads are in flight together (one L2 latency, not one per group).
-    for (int i = sc.hoff; i < sc.hend; i += 2) {
+    for (int i = sc.hoff; !LEAN && i < sc.hend; i += 2) {
       const bool two = i + 1 < sc.hend;
       const int4 ha = sc.hc[i], hb = two ? sc.hc[i + 1] : ha;
       // anti-affinity / affinity only ask "is the domain populated": one bit of host_pop (L1: the stager prefetched the
@@ -408,7 +410,9 @@ __device__ void stager_run(const KpDev& d, const WInst& I, StageRing* ring, cons
 
 // One Scheduler.Solve over the instance's queue.  OVERLAY: existing-node state = shared base + private overlay.
 // STAGED: pods arrive through a StageRing filled by a second warp instead of being staged inline.
-template <bool OVERLAY, bool STAGED>
+// LEAN: no topology group, Gt / Lt bound, minValues or reservation anywhere in the problem (the host decides): the code for
+// them is not even compiled into that instance, which keeps the serial chain's instruction footprint small.
+template <bool OVERLAY, bool STAGED, bool LEAN = false>
 __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch, const int lane, StageRing* ring = nullptr) {
   const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, EW = d.EW;
   const int P = I.P;
@@ -562,12 +566,12 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             int64_t rem = 0;
             uint32_t pr;
             if (OVERLAY && oi >= 0) {
-              if (lane < K) nb = load_slot(I.ov_sflags, I.ov_smask, I.ov_sgte, I.ov_slte, (size_t)oi * K + lane, d.has_bounds);
+              if (lane < K) nb = load_slot(I.ov_sflags, I.ov_smask, I.ov_sgte, I.ov_slte, (size_t)oi * K + lane, (!LEAN && d.has_bounds));
               if (lane < R) rem = I.ov_rem[(size_t)oi * R + lane];
               pr = I.ov_present[oi];
             } else {
               if (lane < K)
-                nb = load_slot(I.node_sflags, I.node_smask, I.node_sgte, I.node_slte, (size_t)node * K + lane, d.has_bounds);
+                nb = load_slot(I.node_sflags, I.node_smask, I.node_sgte, I.node_slte, (size_t)node * K + lane, (!LEAN && d.has_bounds));
               if (lane < R) rem = I.node_rem[(size_t)node * R + lane];
               pr = I.node_rem_present[node];
             }
@@ -582,7 +586,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
               if (!OVERLAY && lane == 0) I.nfit[(size_t)rv * EW + (node >> 5)] &= ~(1u << (node & 31));  // monotone
               continue;
             }
-            Eval ev = eval_candidate(d, px, false, nb, 0, 0, 0, node, scratch, lane);
+            Eval ev = eval_candidate<LEAN>(d, px, false, nb, 0, 0, 0, node, scratch, lane);
             if (!ev.ok) continue;
             // ExistingNode.Add (existingnode.go:147-155)
             if (OVERLAY) {
@@ -601,7 +605,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
                 const size_t i = (size_t)oi * K + lane;
                 I.ov_sflags[i] = (uint8_t)ev.F.f;
                 I.ov_smask[i] = ev.F.m;
-                if (d.has_bounds) {
+                if ((!LEAN && d.has_bounds)) {
                   I.ov_sgte[i] = ev.F.gte;
                   I.ov_slte[i] = ev.F.lte;
                 }
@@ -614,7 +618,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
                 const size_t i = (size_t)node * K + lane;
                 I.node_sflags[i] = (uint8_t)ev.F.f;
                 I.node_smask[i] = ev.F.m;
-                if (d.has_bounds) {
+                if ((!LEAN && d.has_bounds)) {
                   I.node_sgte[i] = ev.F.gte;
                   I.node_slte[i] = ev.F.lte;
                 }
@@ -633,7 +637,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             }
             // helpers.go:121-140: an uninitialized target is an error for a candidate's pod only
             if (!(d.node_flags[node] & KP_NODE_INITIALIZED) && (!I.pod_kind || I.pod_kind[li] == 0)) n_uninit++;
-            topo_record(d, px, ev.F, d.node_taintset[node], node, false, lane);
+            if (!LEAN) topo_record(d, px, ev.F, d.node_taintset[node], node, false, lane);
             ev_existing += node + 1;
             found = true;
           }
@@ -761,7 +765,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       const bool fast_ok = tki & TKI_FAST;
       // the domain fast path: topology on the hostname key and / or the topology key only (kp_kernels.cuh domain_mask)
       bool dom_fp = false, has_tk = false;
-      if (tki & TKI_TOPO) {
+      if (!LEAN && (tki & TKI_TOPO)) {
         if (px.n_hc >= 0) {  // hostname checks staged with the pod
           sc.hc = px.hc;
           sc.hoff = 0;
@@ -794,8 +798,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       while (scanned && !found) {
         int cc;
         // classes with hostname checks read one counter per candidate from HBM/L2: scan 128 positions per step there
-        const int cpos = sc.hend > sc.hoff ? next_candidate<4>(d, I, ord, nC, from, sc, lane, E, &cc)
-                                           : next_candidate<1>(d, I, ord, nC, from, sc, lane, E, &cc);
+        const int cpos = sc.hend > sc.hoff ? next_candidate<4, LEAN>(d, I, ord, nC, from, sc, lane, E, &cc)
+                                           : next_candidate<1, LEAN>(d, I, ord, nC, from, sc, lane, E, &cc);
         if (cpos < 0) break;
         from = cpos + 1;
         {
@@ -852,7 +856,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
                 I.pod_error[li] = KP_PODERR_NONE;
               }
             }
-            if (!fast_ok) topo_record_fast(d, px, zdom, d.tmpl_taintset[I.c_tmpl[cc]], E + cc, lane);
+            if (!LEAN && !fast_ok) topo_record_fast(d, px, zdom, d.tmpl_taintset[I.c_tmpl[cc]], E + cc, lane);
             fast_commits++;
             __syncwarp();
             pert = PERT_INC;
@@ -865,14 +869,14 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           int64_t bq;
           uint64_t bi;
           int bj;
-          claim_load(d, I, cc, lane, &b, &bq, &bi, &bj);
+          claim_load<LEAN>(d, I, cc, lane, &b, &bq, &bi, &bj);
           evals++;
-          Eval ev = eval_candidate(d, px, true, b, bq, bi, bj, E + cc, scratch, lane);
+          Eval ev = eval_candidate<LEAN>(d, px, true, b, bq, bi, bj, E + cc, scratch, lane);
           // Strict minValues (nodeclaim.go:464-475): the surviving types must still span enough distinct values
-          if (d.mv_strict && ev.ok && !min_values_ok(d, I.c_tmpl[cc], ev.its, lane)) ev.ok = false;
+          if (!LEAN && d.mv_strict && ev.ok && !min_values_ok(d, I.c_tmpl[cc], ev.its, lane)) ev.ok = false;
           if (abit && ev.pod_noop && lane == 0) I.amask[cc] |= abit;
           unsigned long long held = 0, take = 0;
-          if (d.n_rsv && ev.ok) {  // offeringsToReserve (nodeclaim.go:197-200): a ReservedOfferingError is just "next claim" here
+          if (!LEAN && d.n_rsv && ev.ok) {  // offeringsToReserve (nodeclaim.go:197-200): a ReservedOfferingError is just "next claim" here
             if (lane < K) scratch[lane] = ev.F;
             __syncwarp();
             held = I.c_rsv[cc];
@@ -892,8 +896,8 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             continue;
           }
           // NodeClaim.Add (nodeclaim.go:207-219)
-          claim_store(d, I, cc, lane, ev, ev.changed);
-          if (d.n_rsv) {
+          claim_store<LEAN>(d, I, cc, lane, ev, ev.changed);
+          if (!LEAN && d.n_rsv) {
             reservations_commit(d, I.rsv_cap, held, take, lane);
             if (lane == 0) I.c_rsv[cc] = take;
           }
@@ -904,7 +908,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
               I.pod_error[li] = KP_PODERR_NONE;
             }
           }
-          topo_record(d, px, ev.F, d.tmpl_taintset[I.c_tmpl[cc]], E + cc, true, lane);
+          if (!LEAN) topo_record(d, px, ev.F, d.tmpl_taintset[I.c_tmpl[cc]], E + cc, true, lane);
           __syncwarp();
           pert = PERT_INC;
           pert_pos = cpos;
@@ -976,10 +980,10 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       }
       Slot b = lane < K ? rs_slot(d, d.tmpl_rs[n], lane) : slot_absent();
       const int64_t bq = lane < R ? d.tmpl_daemon[(size_t)n * R + lane] : 0;
-      Eval ev = eval_candidate(d, px, true, b, bq, tw, -1, E + cnew, scratch, lane);
-      if (d.mv_strict && ev.ok && !min_values_ok(d, n, ev.its, lane)) ev.ok = false;
+      Eval ev = eval_candidate<LEAN>(d, px, true, b, bq, tw, -1, E + cnew, scratch, lane);
+      if (!LEAN && d.mv_strict && ev.ok && !min_values_ok(d, n, ev.its, lane)) ev.ok = false;
       unsigned long long take = 0;
-      if (d.n_rsv && ev.ok) {
+      if (!LEAN && d.n_rsv && ev.ok) {
         if (lane < K) scratch[lane] = ev.F;
         __syncwarp();
         bool rerr;
@@ -994,7 +998,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       }
       if (!ev.ok) continue;
       // NewNodeClaim + Add
-      claim_store(d, I, cnew, lane, ev, true);
+      claim_store<LEAN>(d, I, cnew, lane, ev, true);
       if (lane == 0) {
         I.c_tmpl[cnew] = n;
         ord[cnew] = cnew;
@@ -1008,9 +1012,9 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       if (lane == 0) {
         I.cmask[cnew] = make_ulonglong2(0ull, 0ull);
         I.amask[cnew] = ((px.tkinfo & TKI_ABIT) && ev.pod_noop) ? 1ull << (px.tkinfo & 63) : 0ull;
-        if (d.n_rsv) I.c_rsv[cnew] = take;
+        if (!LEAN && d.n_rsv) I.c_rsv[cnew] = take;
       }
-      if (d.n_rsv) reservations_commit(d, I.rsv_cap, 0ull, take, lane);
+      if (!LEAN && d.n_rsv) reservations_commit(d, I.rsv_cap, 0ull, take, lane);
       // subtractMax (scheduler.go:840-857): remaining -= max capacity over the claim's instance types
       if (lp) {
         for (int r = 0; r < R; r++) {
@@ -1031,7 +1035,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         }
       }
       // Topology.Register(hostname) (nodeclaim.go:213): every hostname group learns the new, empty domain
-      if (d.GH > 0) {
+      if (!LEAN && d.GH > 0) {
         for (int g = lane; g < d.G; g += 32)
           if (d.groups[g].key == d.hostname_key) {
             d.g_ndomains[g]++;
@@ -1039,7 +1043,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           }
         __syncwarp();
       }
-      topo_record(d, px, ev.F, d.tmpl_taintset[n], E + cnew, true, lane);
+      if (!LEAN) topo_record(d, px, ev.F, d.tmpl_taintset[n], E + cnew, true, lane);
       __syncwarp();
       nC = cnew + 1;
       pert = PERT_APPEND;
@@ -1053,7 +1057,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       if (nx >= 0) {  // Preferences.Relax dropped one soft constraint (preferences.go:38-57): same pod, next class row
         Xc = nx;
         // Topology.Update of the relaxed pod (scheduler.go:462): groups only relaxed pods own come into being now
-        for (int i = d.cls_lazy_off[nx]; i < d.cls_lazy_off[nx + 1]; i++) {
+        for (int i = d.cls_lazy_off[nx]; !LEAN && i < d.cls_lazy_off[nx + 1]; i++) {
           const int g = d.cls_lazy[i];
           if (d.g_born[g]) continue;
           if (lane == 0) {
