@@ -431,6 +431,30 @@ int kp_feasibility(kp_handle* h, const kp_problem* p, uint64_t* out_bits, int32_
 int kp_go_sort_f64(const double* keys, int32_t n, int32_t* perm_out);
 int kp_go_sort_i64(const int64_t* keys, int32_t n, int32_t* perm_out);
 
+/* Test hook: the DEVICE's requirement algebra (karpenter_b200/csrc/kp_slot.hpp, what the kernels run) on caller-provided
+ * requirement pairs over one 64-value key, one thread per case -- so the reference's own known-answer tables
+ * (pkg/scheduling/requirement_test.go:103-1084, requirements_test.go:57-543) can be run against it directly.
+ * flags: KP_REQ_COMPLEMENT | KP_REQ_HAS_GTE | KP_REQ_HAS_LTE | KP_SLOT_PRESENT (0: the key is undefined on that side). */
+typedef struct kp_slot_case {
+  uint64_t mask_a, mask_b;
+  int64_t gte_a, lte_a, gte_b, lte_b;
+  uint32_t flags_a, flags_b;
+  int32_t value;           /* for Has(a, value) */
+  int32_t well_known;      /* the key is in WellKnownLabels */
+  int32_t allow_undefined; /* Compatible(a <- b, AllowUndefinedWellKnownLabels) */
+  int32_t _pad;
+} kp_slot_case;
+typedef struct kp_slot_out {
+  uint64_t mask;           /* Intersection(a, b) */
+  int64_t gte, lte;
+  uint32_t flags;
+  int32_t op;              /* Operator() of the intersection: 0 In, 1 NotIn, 2 Exists, 3 DoesNotExist */
+  int32_t has_intersection, has_value, compatible;
+  int32_t _pad;
+} kp_slot_out;
+int kp_debug_slot_algebra(kp_handle* h, const int64_t* value_int /* [64] */, uint64_t value_is_int, uint64_t universe,
+                          const kp_slot_case* cases, int32_t n, kp_slot_out* out);
+
 typedef struct kp_stats {
   double upload_ms, prep_ms, solve_ms, download_ms;
   int64_t bytes_h2d, bytes_d2h;

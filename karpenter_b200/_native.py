@@ -59,6 +59,7 @@ def lib():
         L.kp_comm_last_allreduce_ms.argtypes = [C.c_void_p]
         L.kp_comm_last_allreduce_ms.restype = C.c_double
         L.kp_comm_destroy.argtypes = [C.c_void_p]
+        L.kp_debug_slot_algebra.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int32, C.c_void_p]
         L.kp_go_sort_f64.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.kp_go_sort_i64.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.kp_consolidate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
@@ -69,11 +70,17 @@ def lib():
     return _LIB
 
 
+SLOT_CASE = np.dtype([("mask_a", "<u8"), ("mask_b", "<u8"), ("gte_a", "<i8"), ("lte_a", "<i8"), ("gte_b", "<i8"), ("lte_b", "<i8"),
+                      ("flags_a", "<u4"), ("flags_b", "<u4"), ("value", "<i4"), ("well_known", "<i4"), ("allow_undefined", "<i4"),
+                      ("_pad", "<i4")])
+SLOT_OUT = np.dtype([("mask", "<u8"), ("gte", "<i8"), ("lte", "<i8"), ("flags", "<u4"), ("op", "<i4"), ("has_intersection", "<i4"),
+                     ("has_value", "<i4"), ("compatible", "<i4"), ("_pad", "<i4")])
+
 EXPORTS = ["kp_version", "kp_create", "kp_destroy", "kp_last_error", "kp_solve", "kp_result_free", "kp_upload",
            "kp_solve_resident", "kp_consolidate", "kp_consol_result_free", "kp_feasibility", "kp_get_stats",
            "kp_solve_batch", "kp_upload_batch", "kp_solve_batch_resident", "kp_comm_unique_id", "kp_comm_init",
            "kp_comm_counter_slots", "kp_comm_set_counter_layout", "kp_comm_global_counts", "kp_comm_last_allreduce_ms",
-           "kp_comm_destroy", "kp_go_sort_f64", "kp_go_sort_i64"]
+           "kp_comm_destroy", "kp_go_sort_f64", "kp_go_sort_i64", "kp_debug_slot_algebra"]
 
 
 def go_sort_order(keys) -> np.ndarray:
@@ -224,6 +231,16 @@ class Handle:
         out = np.zeros((problem.n_classes, problem.n_templates, itw), np.uint64)
         w = C.c_int32()
         self._check(lib().kp_feasibility(self._h, problem.ref(), out.ctypes.data, C.byref(w)))
+        return out
+
+    def slot_algebra(self, value_int, is_int: int, universe: int, cases: np.ndarray) -> np.ndarray:
+        """kp_debug_slot_algebra: structured arrays in the layout of kp_slot_case / kp_slot_out."""
+        vi = np.zeros(64, np.int64)
+        vi[:len(value_int)] = value_int
+        cases = np.ascontiguousarray(cases, SLOT_CASE)
+        out = np.zeros(len(cases), SLOT_OUT)
+        self._check(lib().kp_debug_slot_algebra(self._h, vi.ctypes.data, is_int, universe, cases.ctypes.data, len(cases),
+                                                out.ctypes.data))
         return out
 
     def stats(self) -> dict:

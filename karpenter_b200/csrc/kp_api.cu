@@ -229,9 +229,54 @@ __global__ void k_scatter_counts(const int32_t* dom_cnt, const int32_t* slot_src
   if (i < n) out[i] = dom_cnt[slot_src[i]];
 }
 
+__global__ void k_slot_kats(const int64_t* val_int, uint64_t isint, uint64_t univ, const kp_slot_case* cs, int n, kp_slot_out* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const KeyInfo ki{val_int, isint, univ};
+  const kp_slot_case c = cs[i];
+  const Slot a{c.flags_a, c.mask_a, c.gte_a, c.lte_a}, b{c.flags_b, c.mask_b, c.gte_b, c.lte_b};
+  kp_slot_out o;
+  memset(&o, 0, sizeof(o));
+  if (slot_present(a) && slot_present(b)) {
+    const Slot r = slot_intersection(ki, a, b);
+    o.mask = r.m;
+    o.gte = r.gte;
+    o.lte = r.lte;
+    o.flags = r.f;
+    o.op = slot_op(r);
+    o.has_intersection = slot_has_intersection(ki, a, b);
+  }
+  o.has_value = c.value >= 0 ? slot_has(ki, a, c.value) : 0;
+  o.compatible = slot_compatible(ki, a, b, c.well_known != 0, c.allow_undefined != 0);
+  out[i] = o;
+}
+
 static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_consol_input* in, int64_t deadline_ms,
                                kp_consol_result* out);
 extern "C" {
+
+int kp_debug_slot_algebra(kp_handle* h, const int64_t* value_int, uint64_t value_is_int, uint64_t universe,
+                          const kp_slot_case* cases, int32_t n, kp_slot_out* out) {
+  if (n < 0 || !value_int || (n > 0 && (!cases || !out))) return h->err = "kp_debug_slot_algebra: bad arguments", KP_ERR_INVALID;
+  cudaSetDevice(h->device);
+  int64_t* dv = nullptr;
+  kp_slot_case* dc = nullptr;
+  kp_slot_out* dout = nullptr;
+  CK(cudaMalloc(&dv, 64 * 8));
+  CK(cudaMalloc(&dc, sizeof(kp_slot_case) * std::max(n, 1)));
+  CK(cudaMalloc(&dout, sizeof(kp_slot_out) * std::max(n, 1)));
+  CK(cudaMemcpy(dv, value_int, 64 * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dc, cases, sizeof(kp_slot_case) * n, cudaMemcpyHostToDevice));
+  if (n > 0) k_slot_kats<<<(n + 127) / 128, 128, 0, h->stream>>>(dv, value_is_int, universe, dc, n, dout);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout, sizeof(kp_slot_out) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dv);
+  cudaFree(dc);
+  cudaFree(dout);
+  return KP_OK;
+}
+
 static void batch_clear(kp_handle* h);
 }
 

@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _abi
 from .model import (CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, NODEPOOL_LABEL, NORMALIZED_LABELS, RESERVATION_ID_LABEL, WELL_KNOWN_LABELS, InstanceType, LabelSelector,
-                    NodePool, NodeSelectorRequirement, Pod, StateNode, Taint, Toleration, quantity_units)
+                    NodePool, NodeSelectorRequirement, Pod, StateNode, Taint, Toleration, effective_requests, quantity_units)
 
 EFFECTS = {"": 0, "NoSchedule": 1, "PreferNoSchedule": 2, "NoExecute": 3}
 TOL_OPS = {"": 0, "Equal": 0, "Exists": 1, "Lt": 2, "Gt": 3}
@@ -264,7 +264,8 @@ class ProblemBuilder:
                 raise ValueError("several volume topology alternatives for one pod are not supported yet")
             reqs = reqs + [canonical_requirement(r) for r in pod.volume_requirements[0]]
         # everything a scheduling decision or a later relaxation step can depend on
-        key = (tuple(sorted((k, quantity_units(k, v)) for k, v in pod.requests.items())), tuple(reqs), tuple(strict_reqs),
+        eff = effective_requests(pod)  # resources.Ceiling: init containers, sidecars, overhead, pod-level resources
+        key = (tuple(sorted(eff.items())), tuple(reqs), tuple(strict_reqs),
                tuple(pod.tolerations), pod.namespace, tuple(sorted(pod.labels.items())), tuple(tscs),
                tuple(tuple(a) for a in pod_filter_requirements(pod)),
                tuple(pod.node_affinity_preferred) if respect else (),
@@ -273,7 +274,7 @@ class ProblemBuilder:
         n_before = len(self.classes.rows)
         cid = self.classes.get(key)
         if cid == n_before:
-            requests = dict(pod.requests)
+            requests = {k: (f"{v}m" if k == "cpu" else v) for k, v in eff.items()}
             vec = self.res_vector(requests)
             vec.append((self.res_index("pods"), 1))  # RequestsForPods adds pods: 1 (resources.go:37)
             row = dict(pod=pod, requests=vec, reqset=self.reqset(reqs), strict=self.reqset(strict_reqs),

@@ -71,6 +71,63 @@ def quantity_units(name: str, q) -> int:
     return int(f)
 
 
+def _q(name, v):
+    return quantity_units(name, v)
+
+
+def _ceiling_side(main: Dict[str, object], inits, side: str, overhead: Dict[str, object], pod_level: Dict[str, object]) -> Dict[str, int]:
+    """One side (requests or limits) of resources.Ceiling == component-helpers resource.PodRequests / PodLimits
+    (pkg/utils/resources/resources.go:113-118; k8s.io/component-helpers v0.35 resource/helpers.go):
+      total  = sum(containers) + sum(sidecars)
+      init_i = requests(init_i) + sum(sidecars declared BEFORE init_i)      (a sidecar counts itself plus the earlier ones)
+      result = max(total, max_i init_i) per resource, pod-level resources override the names they carry, + overhead."""
+    total = {k: _q(k, v) for k, v in main.items()}
+    sidecars: Dict[str, int] = {}
+    peak: Dict[str, int] = {}
+    for c in inits:
+        cur = {k: _q(k, v) for k, v in getattr(c, side).items()}
+        if c.restart_always:
+            for k, v in cur.items():
+                total[k] = total.get(k, 0) + v
+                sidecars[k] = sidecars.get(k, 0) + v
+            cur = dict(sidecars)
+        else:
+            for k, v in sidecars.items():
+                cur[k] = cur.get(k, 0) + v
+        for k, v in cur.items():
+            if v > peak.get(k, 0) or k not in peak:
+                peak[k] = max(v, peak.get(k, v))
+    for k, v in peak.items():
+        if v > total.get(k, 0) or k not in total:
+            total[k] = max(v, total.get(k, v))
+    for k, v in pod_level.items():  # PodLevelResources: cpu / memory / hugepages replace the aggregate
+        if k in ("cpu", "memory") or k.startswith("hugepages-"):
+            total[k] = _q(k, v)
+    if overhead:
+        for k, v in overhead.items():
+            total[k] = total.get(k, 0) + _q(k, v)
+    return total
+
+
+def ceiling(pod) -> Tuple[Dict[str, int], Dict[str, int]]:
+    """resources.Ceiling(pod) -> (requests, limits) in the solver's exact integer units (milli-cpu, bytes, counts).  Overhead
+    is added to a limit only where a limit exists (PodLimits)."""
+    req = _ceiling_side(pod.requests, pod.init_containers, "requests", pod.overhead, pod.pod_level_requests)
+    lim = _ceiling_side(pod.limits, pod.init_containers, "limits", {}, pod.pod_level_limits)
+    for k, v in pod.overhead.items():
+        if k in lim:
+            lim[k] += _q(k, v)
+    return req, lim
+
+
+def effective_requests(pod) -> Dict[str, int]:
+    """PodData.Requests without the pods: 1 entry (scheduler.go:471-491, resources.go:30-39): what the encoder puts into the
+    class row.  A pod without init containers / overhead / pod-level resources keeps its `requests`."""
+    if not (pod.init_containers or pod.overhead or pod.pod_level_requests):
+        return {k: _q(k, v) for k, v in pod.requests.items()}
+    return ceiling(pod)[0]
+
+
 @dataclass(frozen=True)
 class NodeSelectorRequirement:
     """corev1.NodeSelectorRequirement / v1.NodeSelectorRequirementWithMinValues."""
@@ -147,6 +204,15 @@ class WeightedPodAffinityTerm:
 
 
 @dataclass
+class Container:
+    """corev1.Container as resources.Ceiling reads it: requests / limits, and RestartPolicy == Always for an init container
+    that is a sidecar."""
+    requests: Dict[str, object] = field(default_factory=dict)
+    limits: Dict[str, object] = field(default_factory=dict)
+    restart_always: bool = False
+
+
+@dataclass
 class Pod:
     name: str = ""
     namespace: str = "default"
@@ -172,6 +238,14 @@ class Pod:
     # controller.kubernetes.io/pod-deletion-cost annotation (None: absent)
     priority: Optional[int] = None
     deletion_cost: Optional[str] = None
+    # what resources.Ceiling folds into the effective requests besides the containers' sum (`requests` / `limits` above
+    # are that sum): init containers in spec order, sidecars among them (restart_always); RuntimeClass overhead; pod-level
+    # resources (Spec.Resources), which replace the aggregate for the resources they name
+    limits: Dict[str, object] = field(default_factory=dict)
+    init_containers: List["Container"] = field(default_factory=list)
+    overhead: Dict[str, object] = field(default_factory=dict)
+    pod_level_requests: Dict[str, object] = field(default_factory=dict)
+    pod_level_limits: Dict[str, object] = field(default_factory=dict)
 
 
 # cloudprovider.ReservationIDLabel (pkg/cloudprovider/types.go:49-52) is the provider's to name; this is the fake provider's
