@@ -11,7 +11,7 @@ import numpy as np
 from . import _abi
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(CSRC, "libkarpsolve.so")
+LIB_PATH = os.environ.get("KP_LIB_PATH") or os.path.join(CSRC, "libkarpsolve.so")  # KP_LIB_PATH: experiment builds only
 _LIB = None
 
 STATUS = {0: "OK", 1: "DEADLINE", 2: "INVALID", 3: "CUDA", 4: "CAPACITY", 5: "UNSUPPORTED"}
