@@ -257,6 +257,17 @@ typedef struct kp_problem {
    * reservation-id label and, per reservation id, its value id in that key. */
   int32_t reservation_capacity_type_key, reservation_reserved_value, reservation_id_key;
   const int32_t* reservation_value;        /* [n_reservations] */
+
+  /* ---- host ports (pkg/scheduling/hostportusage.go:35-108) ----
+   * Every distinct <hostIP, hostPort, protocol> of the Solve (pods, daemonset pods, pods bound to the nodes) interned to a bit
+   * (<= 64).  hostport_conflicts[i]: the entries HostPort.Matches entry i (same protocol and port, equal IPs or one of them
+   * unspecified -- :50-62; i itself included).  A pod cannot join a node / NodeClaim whose used ports Match one of its own
+   * (Conflicts :75-88); joining adds its ports.  All NULL / 0: no pod of the Solve uses host ports. */
+  int32_t n_hostports;
+  const uint64_t* hostport_conflicts; /* [n_hostports] */
+  const uint64_t* class_hostports;    /* [n_classes] GetHostPorts(pod) (:93-118) */
+  const uint64_t* node_hostports;     /* [n_nodes] StateNode.HostPortUsage(): ports of the pods bound to the node */
+  const uint64_t* tmpl_hostports;     /* [n_templates] daemonHostPortUsage[template] (scheduler.go:794-811) */
 } kp_problem;
 
 /* pod_target encoding */

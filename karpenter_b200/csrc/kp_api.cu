@@ -602,6 +602,17 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
           if (l == KP_HDR + 3) c.hdr = (int32_t)(tok[x] >> 32);
           if (l == KP_HDR + 4) c.hdr = t.cls_relax[x];
           if (l == KP_HDR + 5) c.hdr = tkinfo[x];
+          if (l >= KP_HDR + 6 && l <= KP_HDR + 9 && p->n_hostports > 0 && p->class_hostports) {
+            const uint64_t ports = p->class_hostports[x];
+            uint64_t conf = 0;
+            for (uint64_t m = ports; m;) {
+              const int i = __builtin_ctzll(m);
+              m &= m - 1;
+              conf |= p->hostport_conflicts[i];
+            }
+            const uint64_t v = l < KP_HDR + 8 ? ports : conf;
+            c.hdr = (int32_t)(((l - KP_HDR) & 1) ? (v >> 32) : (v & 0xffffffffull));
+          }
         }
       CK(up(h, &d.cls_lane, rows));
     }
@@ -649,6 +660,20 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   CK(zeros(h, &d.cmask, C));
   CK(zeros(h, &d.amask, C));
   CK(zeros(h, &d.c_dom, C));
+  // host ports
+  d.n_hostports = p->n_hostports > 0 ? p->n_hostports : 0;
+  if (d.n_hostports > 64) return h->err = "more than 64 distinct host ports", KP_ERR_CAPACITY;
+  if (d.n_hostports > 0 && !p->hostport_conflicts) return h->err = "hostport_conflicts is null", KP_ERR_INVALID;
+  {
+    std::vector<unsigned long long> np(std::max(t.E, 1), 0ull), tp(std::max(t.N, 1), 0ull);
+    for (int n = 0; n < t.E; n++)
+      if (d.n_hostports && p->node_hostports) np[n] = p->node_hostports[t.node_map[n]];
+    for (int n = 0; n < t.N; n++)
+      if (d.n_hostports && p->tmpl_hostports) tp[n] = p->tmpl_hostports[n];
+    CK(up_mut(h, &d.node_ports, np));
+    CK(up(h, &d.tmpl_ports, tp));
+    CK(zeros(h, &d.c_ports, C));
+  }
   // reserved capacity
   d.n_rsv = t.n_rsv;
   d.rsv_strict = t.rsv_strict ? 1 : 0;
@@ -931,7 +956,8 @@ static int prep_solve(kp_handle* h) {
     CS = lo;
   }
   if (const char* lim = getenv("KP_CS_LIMIT")) CS = std::min(CS, std::max(0, atoi(lim)) / 32 * 32);  // test knob
-  in.lean = in.host.G == 0 && !in.host.has_bounds && !in.host.min_values_strict && in.host.n_rsv == 0 && !getenv("KP_NO_LEAN");
+  in.lean = in.host.G == 0 && !in.host.has_bounds && !in.host.min_values_strict && in.host.n_rsv == 0 && d.n_hostports == 0 &&
+            !getenv("KP_NO_LEAN");
   in.CS = CS;
   in.CR = CR;
   in.smem = fixed + tb + (CS ? small_bytes(CS) : 0) + 64;
@@ -1867,7 +1893,7 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   const size_t fixed = KP_ALIGN16(sizeof(ConsolShared));
   size_t tb = plan_tables(h, fixed, budget);
   size_t smem = fixed + tb + 64;
-  const bool lean = !t.has_bounds && !t.min_values_strict && t.n_rsv == 0 && !getenv("KP_NO_LEAN");  // (G == 0 on this path)
+  const bool lean = !t.has_bounds && !t.min_values_strict && t.n_rsv == 0 && d.n_hostports == 0 && !getenv("KP_NO_LEAN");  // (G == 0 here)
   CK(cudaFuncSetAttribute(lean ? k_consolidate<true> : k_consolidate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1, n_sm = 148;
   if (lean)
@@ -1887,6 +1913,10 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   if (t.n_rsv > 0) {
     CK(zeros(h, &q.rsv_cap, slots * (size_t)t.n_rsv));
     CK(zeros(h, &q.c_rsv, slots * cq));
+  }
+  if (d.n_hostports > 0) {
+    CK(zeros(h, &q.c_ports, slots * cq));
+    CK(zeros(h, &q.ov_ports, slots * cq));
   }
   CK(zeros(h, &q.c_tmpl, slots * cq));
   CK(zeros(h, &q.c_npods, slots * cq));

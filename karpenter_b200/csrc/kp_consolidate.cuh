@@ -209,6 +209,9 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     I.g_c_dom = d.c_dom;
     I.rsv_cap = d.rsv_cap;
     I.c_rsv = d.c_rsv;
+    I.c_ports = d.c_ports;
+    I.node_ports = d.node_ports;
+    I.ov_ports = nullptr;
     I.CR = 0;
     unsigned char* p = tab + d_in.tab_bytes;
     if (CR > 0) {  // rows of the first CR claims
@@ -323,6 +326,7 @@ struct KpConsol {
   uint8_t* kindl;                // per warp slot [capq]: kind of local pod i (0: candidate pod)
   int32_t* rsv_cap;              // per warp slot [n_rsv]: the simulation's own ReservationManager
   unsigned long long* c_rsv;     // per warp slot [capq]
+  unsigned long long *c_ports, *ov_ports;  // per warp slot [capq]: host ports of the simulation's claims / touched nodes
   // context deadline: the first warp to start stamps t_start; a warp that finds deadline_ns used up stops pulling work
   long long deadline_ns;
   unsigned long long* t_start;
@@ -681,6 +685,9 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolid
     I.g_c_dom = nullptr;
     I.rsv_cap = d.n_rsv ? q.rsv_cap + slot * d.n_rsv : nullptr;
     I.c_rsv = d.n_rsv ? q.c_rsv + slot * capq : nullptr;
+    I.c_ports = d.n_hostports ? q.c_ports + slot * capq : nullptr;
+    I.ov_ports = d.n_hostports ? q.ov_ports + slot * capq : nullptr;
+    I.node_ports = d.node_ports;  // shared base, read-only here
     I.ov_cap = capq;
     I.ov_node = q.ov_node + slot * capq;
     I.ov_rem = q.ov_rem + slot * capq * R;

@@ -235,8 +235,10 @@ struct PodCtx {
       unsigned long long tmpl_ok;  // bit n: template n's taints are tolerated (taints.go:49-66)
       int relax;                   // class after one Preferences.Relax step, -1: nothing left to relax
       int tkinfo;                  // TKI_*
+      unsigned long long ports;      // host ports of the pod (interned entries, hostportusage.go:93-118)
+      unsigned long long port_conf;  // every entry that Matches one of them (:50-62)
     };
-    int hdr[KP_HDR + 6];  // the class header, then class id, pod id, tmpl_ok (lo, hi), relax, tkinfo
+    int hdr[KP_HDR + 10];  // the class header, then class id, pod id, tmpl_ok (lo, hi), relax, tkinfo, ports, port_conf
   };
   int64_t req[KP_MAXR];
   Slot pod_slot[KP_MAXK];
@@ -371,7 +373,7 @@ __device__ __forceinline__ Eval eval_candidate(const KpDev& d, const PodCtx& px,
 // A class row in flight between global memory and the shared PodCtx (one warp; lane k: key k, lane r: resource r,
 // lane i < KP_HDR: header word i).
 struct ClassRegs {
-  int hdr;                // lanes 0..KP_HDR+5: header row, class, pod, tmpl_ok lo / hi, relax, tkinfo
+  int hdr;                // lanes 0..KP_HDR+9: header row, class, pod, tmpl_ok lo / hi, relax, tkinfo, ports, port_conf
   int64_t req;
   Slot pod, strict;
 };
@@ -396,7 +398,7 @@ __device__ __forceinline__ ClassRegs load_class_regs(const KpDev& d, int X, int 
   return c;
 }
 __device__ __forceinline__ void store_class_regs(const KpDev& d, PodCtx& px, const ClassRegs& c, int lane) {
-  if (lane < KP_HDR + 6) px.hdr[lane] = c.hdr;
+  if (lane < KP_HDR + 10) px.hdr[lane] = c.hdr;
   if (lane < d.R) px.req[lane] = c.req;
   if (lane < d.K) {
     px.pod_slot[lane] = c.pod;

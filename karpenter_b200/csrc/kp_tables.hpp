@@ -208,6 +208,12 @@ struct KpDev {
   int64_t* counters;              // [8] existing evals, inflight evals, template evals, commits, slow sorts, ...
   int32_t* status;                // [1] 0 ok, 4 capacity
   int stable_order;
+  // host ports (hostportusage.go:35-108): interned <ip, port, protocol> entries in use per NodeClaim / existing node; a
+  // class row carries the pod's own entries and everything that Matches them
+  int n_hostports;
+  unsigned long long* c_ports;        // [Cmax]
+  unsigned long long* node_ports;     // [E]
+  const unsigned long long* tmpl_ports;  // [N]
   // reserved capacity (reservationmanager.go:28-110, nodeclaim.go:240-287): reservation id behind each distinct offering
   // set (-1: not reserved), remaining capacity per id, ids held per NodeClaim (bit set)
   int n_rsv, rsv_strict;

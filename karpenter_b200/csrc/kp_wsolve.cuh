@@ -62,6 +62,8 @@ struct WInst {
   // the ids each NodeClaim holds (null / unused when the problem has no reserved offerings)
   int32_t* rsv_cap;
   unsigned long long* c_rsv;
+  // host ports in use per NodeClaim / per existing node (direct mode) / per overlay entry (consolidation)
+  unsigned long long *c_ports, *node_ports, *ov_ports;
   // While the claim order, template ids and failure masks fit, they live in shared memory (CS = claims the shared
   // copies can hold, 0 = not in use); the moment a claim id reaches CS everything migrates to the global arrays below.
   int CS;
@@ -575,6 +577,11 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
               if (lane < R) rem = I.node_rem[(size_t)node * R + lane];
               pr = I.node_rem_present[node];
             }
+            // HostPortUsage.Conflicts (existingnode.go:76-82)
+            if (!LEAN && px.port_conf) {
+              const unsigned long long used = (OVERLAY && oi >= 0) ? I.ov_ports[oi] : I.node_ports[node];
+              if (used & px.port_conf) continue;
+            }
             // resources.Fits(pod requests, remaining) (resources.go:150-163)
             bool bad = false;
             if (lane < R) {
@@ -590,6 +597,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             if (!ev.ok) continue;
             // ExistingNode.Add (existingnode.go:147-155)
             if (OVERLAY) {
+              const bool oi_new = oi < 0;
               if (oi < 0) {
                 oi = I.n_ov;
                 if (oi >= I.ov_cap) {
@@ -612,6 +620,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
               }
               if (lane < R) I.ov_rem[(size_t)oi * R + lane] = rem - px.req[lane];
               if (lane == 0) I.ov_present[oi] = pr | ((1u << R) - 1);
+              if (!LEAN && d.n_hostports && lane == 0) I.ov_ports[oi] = (oi_new ? I.node_ports[node] : I.ov_ports[oi]) | px.ports;
               __syncwarp();
             } else {
               if (ev.changed && lane < K) {
@@ -627,6 +636,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
               if (lane == 0) {
                 I.node_rem_present[node] = pr | ((1u << R) - 1);
                 I.node_npods[node]++;
+                if (!LEAN && px.ports) I.node_ports[node] |= px.ports;
               }
             }
             if (lane == 0) {
@@ -803,6 +813,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         if (cpos < 0) break;
         from = cpos + 1;
         {
+          if (!LEAN && px.port_conf && (I.c_ports[cc] & px.port_conf)) continue;  // host ports (nodeclaim.go:120-124)
           int zdom = -1;  // fast-path candidates of a class with topology-key groups: the claim's pinned value
           bool fp = false;
           if ((fast_ok || dom_fp) && (I.amask[cc] & abit)) {
@@ -850,6 +861,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             }
             claim_store_rq(d, I, cc, lane, q, lo, any_adv, its);
             if (lane == 0) {
+              if (!LEAN && px.ports) I.c_ports[cc] |= px.ports;
               cnt[cpos]++;
               if (I.pod_target) {
                 I.pod_target[li] = KP_TARGET_CLAIM(cc);
@@ -902,6 +914,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             if (lane == 0) I.c_rsv[cc] = take;
           }
           if (lane == 0) {
+            if (!LEAN && px.ports) I.c_ports[cc] |= px.ports;
             cnt[cpos]++;
             if (I.pod_target) {
               I.pod_target[li] = KP_TARGET_CLAIM(cc);
@@ -973,6 +986,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         break;
       }
       if (!((px.tmpl_ok >> n) & 1ull)) continue;
+      if (!LEAN && px.port_conf && (d.tmpl_ports[n] & px.port_conf)) continue;  // the daemons' ports (scheduler.go:794-811)
       if (I.CS && cnew >= I.CS) {  // the shared-memory copies are full: continue on the global arrays
         migrate_small(d, I, nC, lane);
         ord = I.order;
@@ -1013,6 +1027,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         I.cmask[cnew] = make_ulonglong2(0ull, 0ull);
         I.amask[cnew] = ((px.tkinfo & TKI_ABIT) && ev.pod_noop) ? 1ull << (px.tkinfo & 63) : 0ull;
         if (!LEAN && d.n_rsv) I.c_rsv[cnew] = take;
+        if (!LEAN && d.n_hostports) I.c_ports[cnew] = d.tmpl_ports[n] | px.ports;
       }
       if (!LEAN && d.n_rsv) reservations_commit(d, I.rsv_cap, 0ull, take, lane);
       // subtractMax (scheduler.go:840-857): remaining -= max capacity over the claim's instance types

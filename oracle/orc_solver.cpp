@@ -30,6 +30,7 @@ namespace orc {
 struct InflightClaim {
   int tmpl;
   std::vector<int> reserved;  // reservation ids of NodeClaim.reservedOfferings (ascending)
+  uint64_t ports = 0;         // hostPortUsage: interned <ip, port, protocol> entries in use (daemons + pods)
   Requirements reqs;
   std::vector<int> its;  // InstanceTypeOptions (global ids, template order)
   Res requests;          // Spec.Resources.Requests
@@ -39,6 +40,7 @@ struct InflightClaim {
 };
 
 struct ExistingNode {
+  uint64_t ports = 0;  // StateNode.HostPortUsage()
   int node;
   Res remaining;
   Requirements reqs;
@@ -120,6 +122,18 @@ struct Scheduler {
         }
     for (int& c : rsv_cap)
       if (c < 0) c = 0;
+  }
+
+  // HostPortUsage.Conflicts (hostportusage.go:75-88): some port of the pod Matches a port in use
+  uint64_t class_ports(int cls) const { return p->class_hostports ? p->class_hostports[cls] : 0ull; }
+  bool ports_conflict(uint64_t used, int cls) const {
+    uint64_t mine = class_ports(cls);
+    while (mine) {
+      const int i = __builtin_ctzll(mine);
+      mine &= mine - 1;
+      if (used & p->hostport_conflicts[i]) return true;
+    }
+    return false;
   }
 
   // offeringsToReserve (nodeclaim.go:240-287).  false == ReservedOfferingError (strict mode only)
@@ -210,6 +224,7 @@ struct Scheduler {
       e.remaining = P.res_row(p->node_available, i, p->node_avail_present ? p->node_avail_present[i] : P.all_mask());
       e.reqs = topo.node_label_reqs(i);  // existingnode.go:61-63
       e.taintset = p->node_taintset[i];
+      e.ports = p->node_hostports ? p->node_hostports[i] : 0ull;
       if (P.hostname_key >= 0) topo.register_domain(P.hostname_key, p->node_hostname[i]);
       existing.push_back(std::move(e));
       int t = p->node_template ? p->node_template[i] : -1;  // updateRemainingResources (scheduler.go:728-735)
@@ -225,6 +240,7 @@ struct Scheduler {
   bool existing_can_add(ExistingNode& n, int cls, Requirements* out) {
     ctr.existing++;
     if (!P.tolerates(n.taintset, p->class_tolset[cls])) return false;
+    if (ports_conflict(n.ports, cls)) return false;  // existingnode.go:76-82
     if (!fits(P.R, class_requests(cls), n.remaining)) return false;
     const Requirements& pod_reqs = P.reqsets[p->class_reqset[cls]];
     if (!compatible(P, P, n.reqs, pod_reqs, false)) return false;
@@ -245,6 +261,7 @@ struct Scheduler {
     if (rsv_error) *rsv_error = false;
     int taintset = p->tmpl_taintset[c.tmpl];
     if (!P.tolerates(taintset, p->class_tolset[cls])) return false;
+    if (ports_conflict(c.ports, cls)) return false;  // nodeclaim.go:120-124
     const Requirements& pod_reqs = P.reqsets[p->class_reqset[cls]];
     Requirements reqs = c.reqs;
     if (!compatible(P, P, reqs, pod_reqs, true)) return false;
@@ -276,6 +293,7 @@ struct Scheduler {
     for (int id : c.reserved)
       if (std::find(rsv.begin(), rsv.end(), id) == rsv.end()) rsv_cap[id]++;
     c.reserved = rsv;
+    c.ports |= class_ports(cls);  // hostPortUsage.Add (nodeclaim.go:215)
     c.pods.push_back(pod);
     c.its = its;
     c.requests = merge(P.R, c.requests, class_requests(cls));
@@ -295,6 +313,7 @@ struct Scheduler {
         Res q = class_requests(cls);
         for (int k = 0; k < P.R; k++) n.remaining.v[k] -= q.v[k];  // SubtractFrom creates missing keys
         n.remaining.present |= P.all_mask();
+        n.ports |= class_ports(cls);  // existingnode.go:153
         n.reqs = r;
         topo.record(cls, n.taintset, r);
         ctr.commits++;
@@ -412,6 +431,7 @@ struct Scheduler {
         c.reqs.add(P, h);
       }
       c.its = its;
+      c.ports = p->tmpl_hostports ? p->tmpl_hostports[n] : 0ull;  // daemonHostPortUsage (scheduler.go:794-811)
       c.requests = P.res_row(p->tmpl_daemon, n, P.all_mask());
       Requirements r;
       std::vector<int> rem_its, rsv;
