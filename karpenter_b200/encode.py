@@ -25,7 +25,8 @@ import numpy as np
 
 from . import _abi
 from .model import (CAPACITY_TYPE_LABEL, HOSTNAME_LABEL, NODEPOOL_LABEL, NORMALIZED_LABELS, RESERVATION_ID_LABEL, WELL_KNOWN_LABELS, InstanceType, LabelSelector,
-                    NodePool, NodeSelectorRequirement, Pod, StateNode, Taint, Toleration, effective_requests, quantity_units)
+                    NodePool, NodeSelectorRequirement, Pod, StateNode, Taint, Toleration, effective_requests, host_port_key,
+                    host_ports_match, quantity_units)
 
 EFFECTS = {"": 0, "NoSchedule": 1, "PreferNoSchedule": 2, "NoExecute": 3}
 TOL_OPS = {"": 0, "Equal": 0, "Exists": 1, "Lt": 2, "Gt": 3}
@@ -221,8 +222,20 @@ class ProblemBuilder:
             self.reservation_ids = {}
         return (self.reservation_ids.setdefault(name, len(self.reservation_ids)), int(o.reservation_capacity))
 
-    def add_nodepool(self, np_: NodePool, instance_types: Sequence[str], daemon: Optional[Dict[str, object]] = None):
-        """NewNodeClaimTemplate (nodeclaimtemplate.go:57-79): requirements + labels + nodepool/nodeclass labels."""
+    def _ports(self, host_ports) -> int:
+        """bit set of interned <ip, port, protocol> entries"""
+        if not hasattr(self, "hostports"):
+            self.hostports = {}
+        m = 0
+        for hp in host_ports:
+            m |= 1 << self.hostports.setdefault(host_port_key(hp), len(self.hostports))
+        return m
+
+    def add_nodepool(self, np_: NodePool, instance_types: Sequence[str], daemon: Optional[Dict[str, object]] = None,
+                     daemon_host_ports=()):
+        """NewNodeClaimTemplate (nodeclaimtemplate.go:57-79): requirements + labels + nodepool/nodeclass labels.
+        daemon_host_ports: the host ports of the daemonset pods that would run on a node of the pool
+        (getDaemonHostPortUsage, scheduler.go:794-811)."""
         reqs = [canonical_requirement(r) for r in np_.requirements]
         labels = dict(np_.labels)
         labels[NODEPOOL_LABEL] = np_.name
@@ -231,7 +244,7 @@ class ProblemBuilder:
         self.templates.append(dict(
             name=np_.name, weight=np_.weight, reqset=self.reqset(reqs), taintset=self.taintset(np_.taints),
             its=[n if isinstance(n, int) else self.it_index[n] for n in instance_types],
-            daemon=self.res_vector(daemon or {}),
+            daemon=self.res_vector(daemon or {}), ports=self._ports(daemon_host_ports),
             limits=self.res_vector(np_.limits)))
 
     def pod_class(self, pod: Pod) -> int:
@@ -267,7 +280,7 @@ class ProblemBuilder:
         eff = effective_requests(pod)  # resources.Ceiling: init containers, sidecars, overhead, pod-level resources
         key = (tuple(sorted(eff.items())), tuple(reqs), tuple(strict_reqs),
                tuple(pod.tolerations), pod.namespace, tuple(sorted(pod.labels.items())), tuple(tscs),
-               tuple(tuple(a) for a in pod_filter_requirements(pod)),
+               tuple(tuple(a) for a in pod_filter_requirements(pod)), tuple(sorted(host_port_key(h) for h in pod.host_ports)),
                tuple(pod.node_affinity_preferred) if respect else (),
                tuple((w.weight for w in pod.pod_affinity_preferred)) if respect else (),
                tuple((w.weight for w in pod.pod_anti_affinity_preferred)) if respect else ())
@@ -277,7 +290,7 @@ class ProblemBuilder:
             requests = {k: (f"{v}m" if k == "cpu" else v) for k, v in eff.items()}
             vec = self.res_vector(requests)
             vec.append((self.res_index("pods"), 1))  # RequestsForPods adds pods: 1 (resources.go:37)
-            row = dict(pod=pod, requests=vec, reqset=self.reqset(reqs), strict=self.reqset(strict_reqs),
+            row = dict(pod=pod, requests=vec, ports=self._ports(pod.host_ports), reqset=self.reqset(reqs), strict=self.reqset(strict_reqs),
                        tolset=self.tolset(pod.tolerations), namespace=self.namespaces.get(pod.namespace),
                        labelset=self.labelsets.get(tuple(sorted(pod.labels.items()))),
                        filters=[self.reqset(a) for a in pod_filter_requirements(pod)] if tscs else [],
@@ -314,7 +327,9 @@ class ProblemBuilder:
                    capacity=self.res_vector(n.capacity),
                    flags=(1 if n.schedulable else 0) | (2 if n.initialized else 0) | (4 if n.managed else 0),
                    template=template_index.get(n.nodepool, -1) if n.nodepool else -1,
-                   instance_type=n.instance_type, labels=labels)
+                   instance_type=n.instance_type, labels=labels,
+                   ports=self._ports(list(n.host_ports) + [h for p in n.running_pods for h in p.host_ports]),
+                   pod_ports=[self._ports(p.host_ports) for p in n.pods])
         self.nodes.append(row)
         return len(self.nodes) - 1
 
@@ -520,6 +535,13 @@ class ProblemBuilder:
         dm, _ = dense([t["daemon"] for t in tmpls])
         lm, lp = dense([t["limits"] for t in tmpls])
         P.set("tmpl_daemon", dm)
+        if getattr(self, "hostports", None):  # host ports (hostportusage.go:35-108): entries interned to bits, who Matches whom
+            ents = sorted(self.hostports.items(), key=lambda kv: kv[1])
+            if len(ents) > 64:
+                raise ValueError("more than 64 distinct host ports in one Solve")
+            P.set("n_hostports", len(ents))
+            P.set("hostport_conflicts", np.array([sum(1 << j for b, j in ents if host_ports_match(a, b)) for a, _ in ents], np.uint64))
+            P.set("tmpl_hostports", np.array([t["ports"] for t in tmpls], np.uint64))
         P.set("tmpl_limits", lm)
         P.set("tmpl_limit_present", lp)
         # labels / selectors / namespaces
@@ -578,6 +600,8 @@ class ProblemBuilder:
         P.set("class_filter_reqsets", fr)
         P.set("class_tsc_off", to)
         P.set("class_relax_next", relax_next)
+        if getattr(self, "hostports", None):
+            P.set("class_hostports", np.array([c["ports"] for c in self.class_rows], np.uint64))
         for k, arr in cols.items():
             P.set("tsc_" + k, arr)
         # pods
@@ -608,6 +632,14 @@ class ProblemBuilder:
         P.set("node_available", av)
         P.set("node_avail_present", avp)
         P.set("node_capacity", cp)
+        if getattr(self, "hostports", None):
+            # a node's reschedulable pods (`pods`) stay bound unless the node is a consolidation candidate: their ports count
+            def all_ports(n):
+                m = n["ports"]
+                for b in n["pod_ports"]:
+                    m |= b
+                return m
+            P.set("node_hostports", np.array([all_ports(n) for n in nodes], np.uint64))
         P.set("node_template", [tmpl_index.get(self.templates[n["template"]]["name"], -1) if n["template"] >= 0 else -1
                                 for n in nodes])
         P.set("n_running", len(self.running))

@@ -75,6 +75,20 @@ def _q(name, v):
     return quantity_units(name, v)
 
 
+def host_port_key(hp) -> Tuple[str, int, str]:
+    """(ip, port, protocol) in canonical form: GetHostPorts' defaults (hostportusage.go:93-118) and one spelling for the
+    unspecified address (net.IP.IsUnspecified: 0.0.0.0 and ::)."""
+    ip, port, proto = hp
+    ip = "" if ip in ("", "0.0.0.0", "::") else ip
+    return (ip, int(port), proto or "TCP")
+
+
+def host_ports_match(a, b) -> bool:
+    """HostPort.Matches (hostportusage.go:50-62): same protocol and port, IPs equal or one of them unspecified."""
+    a, b = host_port_key(a), host_port_key(b)
+    return a[2] == b[2] and a[1] == b[1] and (a[0] == b[0] or a[0] == "" or b[0] == "")
+
+
 def _ceiling_side(main: Dict[str, object], inits, side: str, overhead: Dict[str, object], pod_level: Dict[str, object]) -> Dict[str, int]:
     """One side (requests or limits) of resources.Ceiling == component-helpers resource.PodRequests / PodLimits
     (pkg/utils/resources/resources.go:113-118; k8s.io/component-helpers v0.35 resource/helpers.go):
@@ -246,6 +260,9 @@ class Pod:
     overhead: Dict[str, object] = field(default_factory=dict)
     pod_level_requests: Dict[str, object] = field(default_factory=dict)
     pod_level_limits: Dict[str, object] = field(default_factory=dict)
+    # container ports with a hostPort: (hostIP, hostPort, protocol); "" / "0.0.0.0" / "::" are the unspecified address, the
+    # protocol defaults to TCP (scheduling.GetHostPorts, hostportusage.go:93-118)
+    host_ports: List[Tuple[str, int, str]] = field(default_factory=list)
 
 
 # cloudprovider.ReservationIDLabel (pkg/cloudprovider/types.go:49-52) is the provider's to name; this is the fake provider's
@@ -301,6 +318,8 @@ class StateNode:
     # (None: never) and the NodeClaim's age in seconds
     expire_after_s: Optional[float] = None
     age_s: float = 0.0
+    # StateNode.HostPortUsage(): host ports of pods bound to the node that are not listed in `pods` / `running_pods`
+    host_ports: List[Tuple[str, int, str]] = field(default_factory=list)
 
 
 @dataclass

@@ -31,12 +31,14 @@ POD_ERRORS = {
 class Scheduler:
     def __init__(self, node_pools: Sequence[NodePool], instance_types: Dict[str, List[InstanceType]],
                  state_nodes: Sequence[StateNode] = (), daemon_overhead: Optional[Dict[str, dict]] = None,
+                 daemon_host_ports: Optional[Dict[str, list]] = None,
                  claim_order: str = "go", backend: Optional[Callable] = None, device: int = -1,
                  preference_policy: str = "Respect", min_values_policy: str = "Strict"):
         self.node_pools = list(node_pools)
         self.instance_types = instance_types
         self.state_nodes = list(state_nodes)
         self.daemon_overhead = daemon_overhead or {}
+        self.daemon_host_ports = daemon_host_ports or {}  # NodePool name -> host ports of its daemonset pods
         self.claim_order = claim_order
         self.preference_policy = preference_policy  # "Ignore" == scheduler.IgnorePreferences (scheduler.go:81-101)
         self.min_values_policy = min_values_policy  # "BestEffort" == MinValuesPolicyBestEffort (scheduler.go:110-114)
@@ -57,7 +59,7 @@ class Scheduler:
                 if id(it) not in index:
                     index[id(it)] = b.add_instance_type(it)
                 ids.append(index[id(it)])
-            b.add_nodepool(np_, ids, self.daemon_overhead.get(np_.name))
+            b.add_nodepool(np_, ids, self.daemon_overhead.get(np_.name), self.daemon_host_ports.get(np_.name, ()))
         self._it_index = index
         return b
 

@@ -160,6 +160,57 @@ def test_fuzz_reserved_capacity_parity_gpu():
     assert not bad, bad[:10]
 
 
+def encode_ports(seed):
+    """the soft problems with host ports on a third of the pods (a handful of ports / addresses / protocols, wildcard
+    addresses included), ports already in use on some existing nodes and a daemon port on one NodePool"""
+    import random
+    pools, per_pool, nodes, pl = fuzz.problem(seed, n_pods=[5, 20, 60, 150][seed % 4])
+    fuzz.soften(seed, pools, pl)
+    rng = random.Random(47_000 + seed)
+    entries = [(ip, port, proto) for ip in ("", "0.0.0.0", "10.0.0.1", "10.0.0.2") for port in (80, 443, 8080)
+               for proto in ("TCP", "UDP")]
+    rng.shuffle(entries)
+    entries = entries[:rng.randint(2, 12)]
+    for p in pl:
+        if rng.random() < 0.35:
+            p.host_ports = rng.sample(entries, rng.randint(1, min(3, len(entries))))
+    for n in nodes:
+        if rng.random() < 0.5:
+            n.host_ports = rng.sample(entries, rng.randint(1, min(2, len(entries))))
+    daemon = {pools[rng.randrange(len(pools))].name: [rng.choice(entries)]} if rng.random() < 0.4 else {}
+    return Scheduler(pools, per_pool, nodes, claim_order="go" if seed % 3 else "stable", daemon_host_ports=daemon).encode(pl)
+
+
+def test_ports_generator_conflicts():
+    stats = collections.Counter()
+    for seed in range(120):
+        enc = encode_ports(seed)
+        plain = encode_soft(seed)
+        res, ref = oracle_lib.solve(enc.problem), oracle_lib.solve(plain.problem)
+        stats["ports"] += int(enc.problem.n_hostports > 1)
+        stats["changed"] += int(res["n_claims"] != ref["n_claims"] or not np.array_equal(res["pod_target"], ref["pod_target"]))
+        stats["more_claims"] += int(res["n_claims"] > ref["n_claims"])
+    assert stats["ports"] >= 100 and stats["changed"] >= 40 and stats["more_claims"] >= 20, stats
+
+
+@pytest.mark.gpu
+def test_fuzz_host_ports_parity_gpu():
+    h = _native.Handle()
+    bad = []
+    try:
+        for seed in range(CAP or 250):
+            enc = encode_ports(seed)
+            orc = oracle_lib.solve(enc.problem)
+            gpu = h.solve(enc.problem)
+            try:
+                assert_same(gpu, orc, f"seed {seed} ")
+            except AssertionError as e:
+                bad.append((seed, str(e)[:200]))
+    finally:
+        h.close()
+    assert not bad, bad[:10]
+
+
 def consolidation_case(seed):
     """A random small cluster (topology-free pods bound to nodes) and random candidate sets of 1-3 nodes."""
     import random
@@ -178,6 +229,14 @@ def consolidation_case(seed):
         n.pods = cand[:k]
     if seed % 3 == 0:  # soft constraints on the evicted pods: the simulation relaxes them like the provisioner does
         fuzz.soften(seed, pools, [p for n in nodes for p in n.pods])
+    if seed % 5 == 1:  # host ports on some of the bound pods and on the nodes themselves
+        ents = [(ip, port, "TCP") for ip in ("", "10.0.0.1", "10.0.0.2") for port in (80, 443)]
+        for n in nodes:
+            if rng.random() < 0.4:
+                n.host_ports = [rng.choice(ents)]
+            for p in n.pods:
+                if rng.random() < 0.5:
+                    p.host_ports = [rng.choice(ents)]
     names = [n.name for n in nodes]
     sets = [rng.sample(names, rng.randint(1, min(3, len(names)))) for _ in range(rng.randint(1, 12))]
     return pools, per_pool, nodes, sets, rng.random() < 0.5  # ... and whether spot-to-spot consolidation is enabled
