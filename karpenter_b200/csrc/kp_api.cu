@@ -667,7 +667,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
   {
     std::vector<unsigned long long> np(std::max(t.E, 1), 0ull), tp(std::max(t.N, 1), 0ull);
     for (int n = 0; n < t.E; n++)
-      if (d.n_hostports && p->node_hostports) np[n] = p->node_hostports[t.node_map[n]];
+      if (d.n_hostports && p->node_hostports) np[n] = p->node_hostports[n];
     for (int n = 0; n < t.N; n++)
       if (d.n_hostports && p->tmpl_hostports) tp[n] = p->tmpl_hostports[n];
     CK(up_mut(h, &d.node_ports, np));

@@ -69,7 +69,6 @@ struct HostTables {
   std::vector<uint8_t> node_sflags;
   std::vector<uint64_t> node_smask;
   std::vector<int64_t> node_sgte, node_slte;
-  std::vector<int32_t> node_map;  // schedulable node slot -> original node index
   std::vector<int32_t> group_out_order;  // result order: regular groups (creation order) then inverse groups
 };
 
