@@ -37,7 +37,7 @@ typedef enum kp_status {
   KP_ERR_INVALID = 2,      /* malformed problem */
   KP_ERR_CUDA = 3,         /* device / driver failure; message via kp_last_error */
   KP_ERR_CAPACITY = 4,     /* a compiled limit was exceeded (e.g. > KP_MAX_RESOURCES) */
-  KP_ERR_UNSUPPORTED = 5   /* feature of the reference not built yet (host ports, CSI volume limits, minValues in kp_consolidate) */
+  KP_ERR_UNSUPPORTED = 5   /* feature of the reference not built yet (CSI volume limits, minValues in kp_consolidate) */
 } kp_status;
 
 /* ---- requirement encoding --------------------------------------------------------------------------------------
@@ -470,6 +470,7 @@ typedef struct kp_stats {
   double upload_ms, prep_ms, solve_ms, download_ms;
   int64_t bytes_h2d, bytes_d2h;
   int64_t kernel_launches;
+  int64_t cohort_pods; /* pods of the last solve that were committed by cohort steps (runs of identical pods) */
 } kp_stats;
 int kp_get_stats(kp_handle* h, kp_stats* out);
 

@@ -101,6 +101,7 @@ struct Instance {
   int32_t* sort_perm_b = nullptr;
   size_t sort_tmp_bytes = 0;
   bool lean = false;  // no topology group / bound / minValues / reservation: the lean instantiation of the solver serves it
+  bool cohort = false;  // the queue holds long runs of identical pods: the cohort instantiation serves it (kp_wsolve.cuh cohort_try)
   // shared-memory plan of the solve CTA (plan_solve)
   int CS = 0, CR = 0;
   size_t smem = 0;
@@ -815,6 +816,21 @@ static int do_upload(kp_handle* h, const kp_problem* p, int cmax, bool fresh_are
     }
   }
   CK(up_raw(h, &h->cur->d_class_rank, rank.data(), rank.size()));
+  {
+    // Pods of classes that are alone in their (cpu, memory) rank stand together in the queue (byCPUAndMemoryDescending, then
+    // creation time and UID, which interleave the classes of one rank): when they are at least a quarter of the queue the
+    // solve runs the cohort instantiation.  KP_COHORT=1 / KP_NO_COHORT=1 force the choice.
+    const int X = h->cur->host.X;
+    std::vector<int64_t> pods_of(std::max(X, 1), 0), classes_at(std::max(X, 1), 0);
+    for (size_t i = 0; i < P; i++) pods_of[p->pod_class[i]]++;
+    for (int x = 0; x < X; x++)
+      if (pods_of[x] > 0) classes_at[rank[x]]++;
+    int64_t in_runs = 0;
+    for (int x = 0; x < X; x++)
+      if (pods_of[x] > 1 && classes_at[rank[x]] == 1) in_runs += pods_of[x];
+    h->cur->cohort = (in_runs * 4 >= (int64_t)P && P > 0 && !getenv("KP_NO_COHORT")) || getenv("KP_COHORT");
+    d.cohort = h->cur->cohort ? 1 : 0;
+  }
   {  // NewQueue sort: key / permutation ping-pong buffers and cub's scratch, sized once per upload
     int64_t* ka;
     int64_t* kb;
@@ -992,14 +1008,17 @@ static int run_solve(kp_handle* h) {
   if (rc != KP_OK) return rc;
   CK(cudaEventRecord(h->ev0, h->stream));
   h->stats.kernel_launches = 0;
+  h->stats.cohort_pods = 0;
   rc = prep_solve(h);
   if (rc != KP_OK) return rc;
-  CK(cudaFuncSetAttribute(in.lean ? k_wsolve<true> : k_wsolve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)in.smem));
+  const void* fn = in.lean ? (in.cohort ? (const void*)k_wsolve<true, true> : (const void*)k_wsolve<true, false>)
+                           : (in.cohort ? (const void*)k_wsolve<false, true> : (const void*)k_wsolve<false, false>);
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)in.smem));
   CK(cudaEventRecord(h->ev2, h->stream));
-  if (in.lean)
-    k_wsolve<true><<<1, 64, in.smem, h->stream>>>(d, in.CS, in.CR);
-  else
-    k_wsolve<false><<<1, 64, in.smem, h->stream>>>(d, in.CS, in.CR);
+  {
+    void* args[] = {(void*)&d, (void*)&in.CS, (void*)&in.CR};
+    CK(cudaLaunchKernel(fn, dim3(1), dim3(64), args, in.smem, h->stream));
+  }
   h->stats.kernel_launches++;
   rc = reduce_counters(h, {&in});
   if (rc != KP_OK) return rc;
@@ -1023,9 +1042,10 @@ static int download(kp_handle* h, kp_result* out) {
   int64_t counters[16];
   CK(cudaMemcpy(&nclaims, d.n_claims, 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(counters, d.counters, 128, cudaMemcpyDeviceToHost));
+  h->stats.cohort_pods += counters[5];
   if (getenv("KP_DEBUG"))
-    fprintf(stderr, "[kp] slow_sorts=%lld evals=%lld commits=%lld fast_commits=%lld\n", (long long)counters[4],
-            (long long)counters[6], (long long)counters[3], (long long)counters[9]);
+    fprintf(stderr, "[kp] slow_sorts=%lld evals=%lld commits=%lld fast_commits=%lld cohort_pods=%lld\n", (long long)counters[4],
+            (long long)counters[6], (long long)counters[3], (long long)counters[9], (long long)counters[5]);
   int64_t P = h->cur->P;
   int K = h->cur->n_keys, R = h->cur->n_resources, ITW = (h->cur->n_its + 63) / 64;
   size_t C = (size_t)nclaims, c1 = C ? C : 1;
@@ -1303,6 +1323,7 @@ static int run_batch(kp_handle* h, int64_t deadline_ms, std::vector<int32_t>& st
   }
   CK(cudaEventRecord(h->ev0, h->stream));
   h->stats.kernel_launches = 0;
+  h->stats.cohort_pods = 0;
   std::vector<KpDev> devs(n);
   std::vector<int2> plan(n);
   size_t smem = 0;
@@ -1317,14 +1338,19 @@ static int run_batch(kp_handle* h, int64_t deadline_ms, std::vector<int32_t>& st
   h->cur = &h->main;
   CK(cudaMemcpyAsync(h->d_batch_devs, devs.data(), sizeof(KpDev) * n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_batch_plan, plan.data(), sizeof(int2) * n, cudaMemcpyHostToDevice, h->stream));
-  bool all_lean = true;
-  for (Instance* b : h->batch) all_lean = all_lean && b->lean;
-  CK(cudaFuncSetAttribute(all_lean ? k_wsolve_batch<true> : k_wsolve_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bool all_lean = true, any_cohort = false;
+  for (Instance* b : h->batch) {
+    all_lean = all_lean && b->lean;
+    any_cohort = any_cohort || b->cohort;
+  }
+  const void* fn = all_lean ? (any_cohort ? (const void*)k_wsolve_batch<true, true> : (const void*)k_wsolve_batch<true, false>)
+                            : (any_cohort ? (const void*)k_wsolve_batch<false, true> : (const void*)k_wsolve_batch<false, false>);
+  CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaEventRecord(h->ev2, h->stream));
-  if (all_lean)
-    k_wsolve_batch<true><<<n, 64, smem, h->stream>>>(h->d_batch_devs, h->d_batch_plan);
-  else
-    k_wsolve_batch<false><<<n, 64, smem, h->stream>>>(h->d_batch_devs, h->d_batch_plan);
+  {
+    void* args[] = {(void*)&h->d_batch_devs, (void*)&h->d_batch_plan};
+    CK(cudaLaunchKernel(fn, dim3(n), dim3(64), args, smem, h->stream));
+  }
   h->stats.kernel_launches++;
   {
     int rc = reduce_counters(h, h->batch);
@@ -1971,6 +1997,7 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   // ---- kernels
   CK(cudaEventRecord(h->ev0, h->stream));
   h->stats.kernel_launches = 0;
+  h->stats.cohort_pods = 0;
   if (d.N > 0) {
     k_feasibility<<<(d.N * 32 + 255) / 256, 256, 0, h->stream>>>(d, nullptr, 1);
     h->stats.kernel_launches++;

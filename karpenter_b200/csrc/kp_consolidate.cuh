@@ -146,7 +146,7 @@ struct WSolveShared {
 };
 
 // warp 0: the solver; warp 1: the pod stager (see StageRing)
-template <bool LEAN>
+template <bool LEAN, bool COHORT>
 __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WSolveShared& sh = *reinterpret_cast<WSolveShared*>(smem_raw);
@@ -161,6 +161,7 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     sh.ring.consumed = 0;
     sh.ring.tail_pub = (int)d.P;
     sh.ring.done = 0;
+    sh.ring.skip_to = 0;
     I.P = (int)d.P;
     I.queue = d.queue;
     I.qcls = d.qcls;
@@ -244,10 +245,10 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
   }
   __syncthreads();
   if (warp == 1) {
-    stager_run(d, I, &sh.ring, lane);
+    stager_run<COHORT>(d, I, &sh.ring, lane);
     return;
   }
-  wsolve_run<false, true, LEAN>(d, I, sh.ring.slot[0], sh.scratch, lane, &sh.ring);
+  wsolve_run<false, true, LEAN, COHORT>(d, I, sh.ring.slot[0], sh.scratch, lane, &sh.ring);
   const int nC = I.n_claims;
   claim_rows_flush(d, I, nC, lane);
   if (!LEAN) claims_finalize(d, I.c_sflags, I.c_smask, I.c_rsv, nC, lane);
@@ -273,16 +274,16 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     d.counters[9] = I.fast_commits;
   }
 }
-template <bool LEAN>
+template <bool LEAN, bool COHORT>
 __global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS, int CR) {
-  wsolve_cta<LEAN>(d_in, CS, CR);
+  wsolve_cta<LEAN, COHORT>(d_in, CS, CR);
 }
 // Many Scheduler instances in one launch, one CTA (== one SM) each: NodePool shards of a provisioning pass, or the
 // candidate sets of a consolidation pass whose pods carry topology constraints (SimulateScheduling, helpers.go:51-142).
 // Instances share nothing but the device; plan[b] = {CS, CR} of instance b.
-template <bool LEAN>
+template <bool LEAN, bool COHORT>
 __global__ void __launch_bounds__(64, 1) k_wsolve_batch(const KpDev* __restrict__ devs, const int2* __restrict__ plan) {
-  wsolve_cta<LEAN>(devs[blockIdx.x], plan[blockIdx.x].x, plan[blockIdx.x].y);
+  wsolve_cta<LEAN, COHORT>(devs[blockIdx.x], plan[blockIdx.x].x, plan[blockIdx.x].y);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -250,6 +250,10 @@ struct PodCtx {
   KpGroup rg[KP_PG];
   int n_hc;            // hostname-group checks among the staged match groups (the scan's per-candidate tests)
   int4 hc[KP_PG];      // {host_row, type | self << 8, max_skew, group}
+  // the run of identical pods this one starts in the queue (stager only): entries h .. h + run_n - 1 of the first pass
+  // share the class, run_pod[i] is the pod of entry h + i.  The solver may commit a whole run in one step (cohorts).
+  int run_n;
+  int run_pod[32];
 };
 // entry i of the pod's match / record list
 __device__ __forceinline__ void pod_match(const KpDev& d, const PodCtx& px, int i, int* e, KpGroup* G) {

@@ -211,6 +211,7 @@ struct KpDev {
   // host ports (hostportusage.go:35-108): interned <ip, port, protocol> entries in use per NodeClaim / existing node; a
   // class row carries the pod's own entries and everything that Matches them
   int n_hostports;
+  int cohort;  // cohort commits of identical pods allowed (kp_wsolve.cuh), 0 with KP_NO_COHORT
   unsigned long long* c_ports;        // [Cmax]
   unsigned long long* node_ports;     // [E]
   const unsigned long long* tmpl_ports;  // [N]

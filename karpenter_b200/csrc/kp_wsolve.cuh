@@ -320,6 +320,66 @@ __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, co
   return -1;
 }
 
+// The cheap tests of next_candidate for ONE claim per lane, without the topology-key mask (which changes from pod to pod
+// of a cohort): failure bits, tolerated template, hostname groups.
+template <bool LEAN>
+__device__ __forceinline__ bool cheap_pass(const KpDev& d, const WInst& I, const ScanCtx& sc, int c, int E) {
+  const ulonglong2 mk = I.cmask[c];
+  bool pass = !(mk.x & sc.fbit) && !(mk.y & sc.rbit);
+  if (pass && !sc.all_tmpl) pass = (sc.tok >> I.c_tmpl[c]) & 1ull;
+  for (int i = sc.hoff; !LEAN && pass && i < sc.hend; i++) {
+    const int4 hc = sc.hc[i];
+    const int type = hc.y & 0xff, self = hc.y >> 8, hi = E + c;
+    const int hcnt = type == KP_TOPO_SPREAD ? __ldcg(d.host_cnt + (size_t)hi * d.GHS + hc.x)
+                                            : (int)((d.host_pop[(size_t)hc.x * d.HW + (hi >> 5)] >> (hi & 31)) & 1u);
+    if (type == KP_TOPO_SPREAD)
+      pass = hcnt + self <= hc.z;
+    else if (type == KP_TOPO_AFFINITY)
+      pass = hcnt > 0 || (self && (d.g_ndomains[hc.w] - d.g_nempty[hc.w]) == 0);
+    else
+      pass = hcnt == 0;
+  }
+  return pass;
+}
+
+// CanAdd of k more pods of the staged class on a claim whose requirements they leave as they are (the "adds nothing" fast
+// path): do the merged requests still fit a remaining instance type?  The stored list only changes when a threshold row
+// advances.  Monotone in k.  Outputs (lane r: requests / threshold row; lane w: instance-type word when *any_adv).
+__device__ __forceinline__ bool fp_fit(const KpDev& d, const WInst& I, const PodCtx& px, int cc, int k, int lane, int64_t* q_out,
+                                       int* lo_out, bool* any_adv_out, uint64_t* its_out) {
+  int64_t q;
+  int j;
+  claim_load_rq(d, I, cc, lane, &q, &j);
+  int lo = j;
+  bool adv = false;
+  if (lane < d.R) {
+    q += px.req[lane] * (int64_t)k;
+    const int end = d.ge_off[lane + 1];
+    while (lo < end && d.ge_vals[lo] < q) lo++;
+    adv = lo != j;
+  }
+  unsigned advm = __ballot_sync(FULL, adv);
+  const bool any_adv = advm != 0;
+  uint64_t its = 0;
+  bool ok = true;
+  if (any_adv) {
+    its = claim_load_its(d, I, cc, lane);
+    const int jj = (lane < d.R && lo == d.ge_off[lane + 1]) ? -1 : lo;
+    while (advm) {
+      const int r = __ffs(advm) - 1;
+      advm &= advm - 1;
+      const int jr = __shfl_sync(FULL, jj, r);
+      if (lane < d.ITW) its &= jr >= 0 ? d.ge_bits[(size_t)jr * d.ITW + lane] : 0ull;
+    }
+    ok = __any_sync(FULL, its != 0);
+  }
+  *q_out = q;
+  *lo_out = lo;
+  *any_adv_out = any_adv;
+  *its_out = its;
+  return ok;
+}
+
 // shared -> global migration of the small per-claim arrays (see WInst::CS); executed once, by the whole warp
 __device__ __forceinline__ void migrate_small(const KpDev& d, WInst& I, int nC, int lane) {
   for (int i = lane; i < nC; i += 32) {
@@ -352,9 +412,11 @@ struct StageRing {
   volatile int consumed;  // pods the solver is done with (solver)
   volatile int tail_pub;  // queue entries below this index are valid (solver; grows with every requeue)
   volatile int done;
+  volatile int skip_to;   // queue entries below this index were committed as part of a cohort: nothing to stage (solver)
   PodCtx slot[KP_RING];
 };
 
+template <bool COHORT>
 __device__ void stager_run(const KpDev& d, const WInst& I, StageRing* ring, const int lane) {
   const int cap = I.P + 1;
   // The queue is read 32 entries at a time (one coalesced load; entries below tail_pub never change), and the class row
@@ -364,30 +426,51 @@ __device__ void stager_run(const KpDev& d, const WInst& I, StageRing* ring, cons
     int avail;
     for (;;) {
       if (ring->done) return;
-      avail = ring->tail_pub - base;
+      const int sk = __shfl_sync(FULL, (int)ring->skip_to, 0);
+      if (sk > base) base = sk;
+      avail = __shfl_sync(FULL, (int)ring->tail_pub, 0) - base;
       if (avail > 0) break;
       __nanosleep(64);
     }
     __threadfence_block();
     if (avail > 32) avail = 32;
-    int li = 0, X = 0;
+    int li = 0, X = -1;
     if (lane < avail) {
       const int qi = (base + lane) % cap;
       li = __ldcg(I.queue + qi);
       X = __ldcg(I.qcls + qi);
     }
     ClassRegs nxt = load_class_regs(d, __shfl_sync(FULL, X, 0), __shfl_sync(FULL, li, 0), lane);
+    bool rebased = false;
     for (int i = 0; i < avail; i++) {
       const int idx = base + i;
       const ClassRegs c = nxt;
       if (i + 1 < avail) nxt = load_class_regs(d, __shfl_sync(FULL, X, i + 1), __shfl_sync(FULL, li, i + 1), lane);
+      int sk = 0;
       for (;;) {
         if (ring->done) return;
-        if (idx - ring->consumed < KP_RING) break;
+        sk = ring->skip_to;
+        if (sk > idx || idx - ring->consumed < KP_RING) break;
         __nanosleep(32);
+      }
+      sk = __shfl_sync(FULL, sk, 0);
+      if (sk > idx) {  // the solver committed this entry with a cohort: restart the block at the first entry it still needs
+        base = sk;
+        rebased = true;
+        break;
       }
       PodCtx& slot = ring->slot[idx & (KP_RING - 1)];
       store_class_regs(d, slot, c, lane);
+      // the run of identical pods starting here (first pass only: requeued pods are tried one at a time)
+      if (COHORT) {
+        const int Xi = __shfl_sync(FULL, X, i);
+        const unsigned same = __ballot_sync(FULL, lane >= i && lane < avail && X == Xi && base + lane < I.P);
+        const unsigned tail_m = same >> i;  // bit t: entry idx + t is in the block and of the same class
+        const int run = tail_m == FULL ? 32 : __ffs(~tail_m) - 1;
+        const int rp = __shfl_sync(FULL, li, (i + lane) & 31);
+        slot.run_pod[lane] = rp;
+        if (lane == 0) slot.run_n = run;
+      }
       __syncwarp();
       // pull what the solver will read for this pod into L1 now: the presence rows of its hostname groups (the part
       // that covers the NodeClaims: 8 lines == 8 192 claims) and the counter rows of its topology-key groups
@@ -406,15 +489,257 @@ __device__ void stager_run(const KpDev& d, const WInst& I, StageRing* ring, cons
       __syncwarp();
       if (lane == 0) ring->produced = idx + 1;
     }
-    base += avail;
+    if (!rebased) base += avail;
   }
+}
+
+// ---- cohorts -----------------------------------------------------------------------------------------------------
+// The stager reports the run of identical pods a queue entry starts (PodCtx::run_n).  When the class takes the fast path
+// (requirements implied by the claim's, domain = the claim's pinned value), the targets of the next pods follow from the
+// claim order alone, so a run commits in one step:
+//   one claim, alone in its tie group of the order (nobody else has its pod count): the next pods land on it again until
+//     it is full or its count passes the next claim's -- k pods with ONE resource test (fp_fit is monotone in k);
+//   a tie group of several claims: every commit moves its claim to the end of the group (the stable result of
+//     sort.Slice(len(Pods)), see the sort stage of wsolve_run), so the following pods take the following claims of the
+//     group, each at most once; the moves are applied in closed form.
+// Everything else -- a candidate that needs the full evaluation, a sort Go would not do stably, the end of the 32-claim
+// window -- ends the cohort and the next pod takes the ordinary path: the result is the reference's, pod for pod.  The
+// last pick is never moved here: the reference sorts at the start of the NEXT pod's in-flight stage (scheduler.go:504),
+// which may never come (end of the queue, a pod an existing node takes); it is left to the sort stage as PERT_INC.
+// Kept out of line: the ordinary path's instruction footprint (one warp, no latency hiding) must not grow with it.
+struct CohortOut {
+  int state;          // 0: not attempted (take the ordinary path)  1: the candidate was tried, failed and is marked  2: committed
+  int npods;          // pods committed (state 2)
+  int nevals;
+  long long ev_sum;   // sum of (position + 1) over the commits: what the reference evaluated
+  int pert, pert_pos;
+  unsigned moved;     // window lanes whose claim moved to the end of the group; the group is [w0, gE]
+  int w0, gE;
+};
+template <bool LEAN>
+__device__ __noinline__ CohortOut cohort_try(const KpDev& d, WInst& I, const PodCtx& px, const ScanCtx sc, int32_t* ord, int32_t* cnt,
+                                             const int nC, const int lb, const int cpos, const int cc, const int E, const int lane,
+                                             const unsigned long long abit, const unsigned long long rbit, const bool fast_ok,
+                                             const bool has_tk) {
+  CohortOut out;
+  out.state = 0;
+  out.npods = 0;
+  out.nevals = 0;
+  out.ev_sum = 0;
+  out.pert = PERT_NONE;
+  out.pert_pos = 0;
+  out.moved = 0;
+  out.w0 = 0;
+  out.gE = 0;
+  bool fp0 = (I.amask[cc] & abit) != 0;
+  if (fp0 && !fast_ok && has_tk) fp0 = I.c_dom[cc] != 0xff;
+  if (!fp0) return out;
+  // the window: 32 positions from the first one that passes every test that does not depend on the pod's domain mask
+  // (claims pinned to a value this pod may not use can be the next pod's target)
+  int w0 = cpos;
+  if (!LEAN && sc.use_ez) {
+    ScanCtx st = sc;
+    st.use_ez = false;
+    st.first_clear = 0;
+    st.first_rclear = 0;
+    int c2;
+    w0 = st.hend > st.hoff ? next_candidate<4, LEAN>(d, I, ord, nC, lb, st, lane, E, &c2)
+                           : next_candidate<1, LEAN>(d, I, ord, nC, lb, st, lane, E, &c2);
+    if (w0 < 0 || w0 > cpos) w0 = cpos;
+  }
+  const int pw = w0 + lane;
+  int wc = -1, wn = -1;
+  if (pw < nC) {
+    wc = ord[pw];
+    wn = cnt[pw];
+  }
+  const int c0 = __shfl_sync(FULL, wn, 0);
+  const unsigned gmask = __ballot_sync(FULL, pw < nC && wn == c0);
+  const int gsz = gmask == FULL ? 32 : __ffs(~gmask) - 1;  // the tie group is contiguous: the order is sorted
+  const int L = px.run_n;
+  if (fast_ok && gsz == 1) {
+    // ---- one claim, k pods
+    const int nxt = __shfl_sync(FULL, wn, 1);
+    int kcap = L;
+    if (w0 + 1 < nC && (long long)nxt - c0 + 1 < kcap) kcap = nxt - c0 + 1;  // the count may pass the next one only once
+    int64_t q, qb;
+    int lo, lob;
+    bool adv, advb;
+    uint64_t its, itsb;
+    int k = kcap;
+    out.nevals = 1;
+    if (!fp_fit(d, I, px, cc, k, lane, &q, &lo, &adv, &its)) {
+      int good = 0, bad = kcap;
+      while (bad - good > 1) {
+        const int mid = (good + bad) >> 1;
+        if (fp_fit(d, I, px, cc, mid, lane, &qb, &lob, &advb, &itsb)) {
+          good = mid;
+          q = qb;
+          lo = lob;
+          adv = advb;
+          its = itsb;
+        } else {
+          bad = mid;
+        }
+      }
+      k = good;
+    }
+    if (k == 0) {  // not even one: permanent for this request vector
+      if (lane == 0) I.cmask[cc].y |= rbit;
+      __syncwarp();
+      out.state = 1;
+      return out;
+    }
+    claim_store_rq(d, I, cc, lane, q, lo, adv, its);
+    if (lane == 0) cnt[cpos] += k;
+    if (I.pod_target && lane < k) {
+      I.pod_target[px.run_pod[lane]] = KP_TARGET_CLAIM(cc);
+      I.pod_error[px.run_pod[lane]] = KP_PODERR_NONE;
+    }
+    __syncwarp();
+    out.state = 2;
+    out.npods = k;
+    out.ev_sum = (long long)k * (cpos + 1);
+    out.pert = PERT_INC;
+    out.pert_pos = cpos;
+    return out;
+  }
+  if (!(gsz >= 2 && cpos < w0 + gsz && (d.stable_order || nC <= 12 || nC >= 50))) return out;
+  // ---- a tie group: the static verdict of every window claim, then one pick per pod
+  bool wpass = false, wfp = false;
+  int wz = -1;
+  if (lane < gsz) {
+    wpass = cheap_pass<LEAN>(d, I, sc, wc, E);
+    if (wpass) {
+      wfp = (I.amask[wc] & abit) != 0;
+      if (wfp && !fast_ok && has_tk) {
+        wz = I.c_dom[wc];
+        wfp = wz != 0xff;
+      }
+    }
+  }
+  unsigned avail = __ballot_sync(FULL, wpass && wfp);
+  const unsigned bar = __ballot_sync(FULL, wpass && !wfp);  // would need the full evaluation: nothing beyond it
+  if (bar) avail &= (1u << (__ffs(bar) - 1)) - 1;
+  if (!((avail >> (cpos - w0)) & 1u)) return out;
+  const bool gend_known = gsz < 32 || w0 + 32 >= nC;
+  unsigned picked = 0;  // claims whose move is settled (every pick but the last)
+  int npick = 0, nmoved = 0, my_t = -1, j = 0;
+  int prev_l = -1, prev_pj = 0;
+  bool prev_inv = false;
+  while (j < L) {
+    if (prev_l >= 0) {
+      // pod j reaches the in-flight stage (its class fails on the existing nodes): the reference sorts now.  An inversion
+      // exists iff a claim of the old count still follows the previous pick; Go repairs it stably unless the pick stands at
+      // one of the positions choosePivot samples (see the sort stage)
+      bool stable = true;
+      if (prev_inv && !d.stable_order && nC > 12) {
+        const int q4 = nC / 4, pj = prev_pj;
+        stable = !(pj == q4 - 1 || pj == q4 || pj == 2 * q4 - 1 || pj == 2 * q4 || pj == 3 * q4 - 1 || pj == 3 * q4);
+      }
+      if (!stable) break;  // the real pdqsort decides: the sort stage runs it
+      if (lane == prev_l) my_t = nmoved;
+      nmoved++;
+      picked |= 1u << prev_l;
+      prev_l = -1;
+    }
+    unsigned allowed = avail;
+    if (!LEAN && has_tk) {
+      uint64_t ez = sc.ez;
+      if (j > 0) {
+        bool exact;
+        ez = domain_mask(d, px, lane, &exact);
+        if (!exact) break;
+      }
+      allowed &= __ballot_sync(FULL, wz >= 0 && ((ez >> wz) & 1ull));
+    }
+    if (!allowed) break;
+    const int l = __ffs(allowed) - 1;
+    const int cl = __shfl_sync(FULL, wc, l);
+    int64_t q;
+    int lo;
+    bool adv;
+    uint64_t its;
+    out.nevals++;
+    avail &= ~(1u << l);
+    if (!fp_fit(d, I, px, cl, 1, lane, &q, &lo, &adv, &its)) {  // full: the same pod takes the next claim
+      if (lane == 0) I.cmask[cl].y |= rbit;
+      __syncwarp();
+      continue;
+    }
+    claim_store_rq(d, I, cl, lane, q, lo, adv, its);
+    const int pj = w0 + l - __popc(picked & ((1u << l) - 1));  // where the claim stands right now
+    out.ev_sum += pj + 1;
+    if (lane == 0 && I.pod_target) {
+      I.pod_target[px.run_pod[j]] = KP_TARGET_CLAIM(cl);
+      I.pod_error[px.run_pod[j]] = KP_PODERR_NONE;
+    }
+    if (!LEAN && !fast_ok) topo_record_fast(d, px, __shfl_sync(FULL, wz, l), d.tmpl_taintset[I.c_tmpl[cl]], E + cl, lane);
+    __syncwarp();
+    const unsigned rest = gmask & ~picked & ~(1u << l);
+    prev_inv = !gend_known || (rest & ~((2u << l) - 1u)) != 0;
+    prev_l = l;
+    prev_pj = pj;
+    j++;
+    npick++;
+  }
+  if (npick == 0) {  // (every tried claim was full and is marked)
+    out.state = 1;
+    return out;
+  }
+  // ---- the settled moves in closed form.  Every stable move takes its claim (count c0 + 1 now) right behind the last
+  // claim that still has c0 pods: the group ends up as [not moved, in order][moved, LAST one first].
+  const int m = nmoved;
+  int gE = w0 + gsz - 1;  // last position of the tie group
+  if (gsz == 32 && m > 0) {  // it may go on behind the window: those claims close up by m
+    for (int s0 = w0 + 32;; s0 += 32) {
+      const int i = s0 + lane;
+      const bool in = i < nC && cnt[i] == c0;
+      const int vo = in ? ord[i] : 0;
+      const unsigned gk = __ballot_sync(FULL, in);
+      const int n = gk == FULL ? 32 : __ffs(~gk) - 1;
+      __syncwarp();
+      if (lane < n) {
+        ord[i - m] = vo;
+        cnt[i - m] = c0;
+      }
+      __syncwarp();
+      gE = s0 + n - 1;
+      if (n < 32) break;
+    }
+  }
+  const bool mv = (picked >> lane) & 1u;
+  const int rank = __popc(~picked & ((1u << lane) - 1));  // claims below me that stay
+  __syncwarp();
+  if (lane < gsz) {
+    if (mv) {
+      ord[gE - my_t] = wc;
+      cnt[gE - my_t] = c0 + 1;
+    } else {
+      ord[w0 + rank] = wc;
+      cnt[w0 + rank] = lane == prev_l ? c0 + 1 : c0;
+    }
+  }
+  __syncwarp();
+  out.state = 2;
+  out.npods = npick;
+  out.moved = picked;
+  out.w0 = w0;
+  out.gE = gE;
+  if (prev_l >= 0) {
+    out.pert = PERT_INC;
+    out.pert_pos = w0 + __popc(~picked & ((1u << prev_l) - 1));
+  }
+  return out;
 }
 
 // One Scheduler.Solve over the instance's queue.  OVERLAY: existing-node state = shared base + private overlay.
 // STAGED: pods arrive through a StageRing filled by a second warp instead of being staged inline.
+// COHORT: runs of identical pods may commit in one step (cohort_try); instantiated separately because the mere call site
+// costs the ordinary path 7 % (register allocation of a 250-register loop) -- the host picks it when the queue has runs.
 // LEAN: no topology group, Gt / Lt bound, minValues or reservation anywhere in the problem (the host decides): the code for
 // them is not even compiled into that instance, which keeps the serial chain's instruction footprint small.
-template <bool OVERLAY, bool STAGED, bool LEAN = false>
+template <bool OVERLAY, bool STAGED, bool LEAN = false, bool COHORT = false>
 __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch, const int lane, StageRing* ring = nullptr) {
   const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, EW = d.EW;
   const int P = I.P;
@@ -805,6 +1130,13 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       const int lb = lbf > lbr ? lbf : lbr;  // below either bound a claim fails for one of the two reasons
       const bool scanned = (sc.tok & d.tmpl_all) != 0;
       int from = lb;
+      // ---- cohorts (cohort_try): a run of identical fast-path pods may commit in one step
+      unsigned coh_moved = 0;
+      int coh_w0 = 0, coh_gE = 0, coh_extra = 0;
+      bool coh_ok = COHORT && STAGED && !OVERLAY && d.cohort && Xc == X && px.run_n >= 2 && abit != 0 && (fast_ok || dom_fp) &&
+                    (LEAN || (px.ports == 0 && px.port_conf == 0)) && (fast_ok || !has_tk || n_active_nodes == 0);
+      for (int i = sc.hoff; !LEAN && coh_ok && i < sc.hend; i++)
+        if ((sc.hc[i].y & 0xff) == KP_TOPO_AFFINITY) coh_ok = false;  // "is any domain populated" changes with every record
       while (scanned && !found) {
         int cc;
         // classes with hostname checks read one counter per candidate from HBM/L2: scan 128 positions per step there
@@ -814,6 +1146,23 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         from = cpos + 1;
         {
           if (!LEAN && px.port_conf && (I.c_ports[cc] & px.port_conf)) continue;  // host ports (nodeclaim.go:120-124)
+          if (COHORT && coh_ok) {
+            const CohortOut co = cohort_try<LEAN>(d, I, px, sc, ord, cnt, nC, lb, cpos, cc, E, lane, abit, rbit, fast_ok, has_tk);
+            evals += co.nevals;
+            if (co.state == 2) {
+              fast_commits += co.npods;
+              ev_inflight += co.ev_sum;
+              coh_extra = co.npods - 1;
+              coh_moved = co.moved;
+              coh_w0 = co.w0;
+              coh_gE = co.gE;
+              pert = co.pert;
+              pert_pos = co.pert_pos;
+              found = true;
+              continue;
+            }
+            if (co.state == 1) continue;  // the candidate was tried and is marked: go on scanning
+          }
           int zdom = -1;  // fast-path candidates of a class with topology-key groups: the claim's pinned value
           bool fp = false;
           if ((fast_ok || dom_fp) && (I.amask[cc] & abit)) {
@@ -828,32 +1177,11 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             // domain choice is the value the claim is pinned to): CanAdd == "do the merged requests still fit a
             // remaining instance type", and the stored list only changes when a threshold row advances
             int64_t q;
-            int j;
-            claim_load_rq(d, I, cc, lane, &q, &j);
+            int lo;
+            bool any_adv;
+            uint64_t its;
+            const bool ok = fp_fit(d, I, px, cc, 1, lane, &q, &lo, &any_adv, &its);
             evals++;
-            int lo = j;
-            bool adv = false;
-            if (lane < R) {
-              q += px.req[lane];
-              const int end = d.ge_off[lane + 1];
-              while (lo < end && d.ge_vals[lo] < q) lo++;
-              adv = lo != j;
-            }
-            unsigned advm = __ballot_sync(FULL, adv);
-            const bool any_adv = advm != 0;
-            uint64_t its = 0;
-            bool ok = true;
-            if (any_adv) {
-              its = claim_load_its(d, I, cc, lane);
-              const int jj = (lane < R && lo == d.ge_off[lane + 1]) ? -1 : lo;
-              while (advm) {
-                const int r = __ffs(advm) - 1;
-                advm &= advm - 1;
-                const int jr = __shfl_sync(FULL, jj, r);
-                if (lane < ITW) its &= jr >= 0 ? d.ge_bits[(size_t)jr * ITW + lane] : 0ull;
-              }
-              ok = __any_sync(FULL, its != 0);
-            }
             if (!ok) {  // nothing left that holds the merged requests: permanent for this request vector
               if (lane == 0) I.cmask[cc].y |= rbit;
               __syncwarp();
@@ -946,6 +1274,33 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
             lr0 = nb;
           else
             lr1 = nb;
+        }
+      }
+      if (found && coh_moved) {
+        // the cohort rearranged [coh_w0, coh_gE]: a bound inside follows the claims that stayed (all of them rejected its
+        // signature before; the ones that moved went behind them)
+        const int w0 = coh_w0, gE = coh_gE;
+#define KP_COH_ADJ(b)                                                          \
+  if ((b) > w0 && (b) <= gE) {                                                 \
+    const int nb_ = (b) - w0;                                                  \
+    (b) -= __popc(coh_moved & (nb_ >= 32 ? FULL : (1u << nb_) - 1u));          \
+  }
+        KP_COH_ADJ(lb0)
+        KP_COH_ADJ(lb1)
+        KP_COH_ADJ(lr0)
+        KP_COH_ADJ(lr1)
+#undef KP_COH_ADJ
+      }
+      if (found && coh_extra > 0) {  // the rest of the cohort left the queue together with its first pod
+        commits += coh_extra;
+        watchdog += coh_extra;
+        scan_chunks += coh_extra + 1;  // (reported as cohort_pods)
+        if (E > 0) ev_existing += (long long)coh_extra * n_active_nodes;
+        head += coh_extra;
+        hq += coh_extra;
+        if (hq >= cap) hq -= cap;
+        if (STAGED) {
+          if (lane == 0) ring->skip_to = head;
         }
       }
       if (found) {

@@ -133,6 +133,48 @@ def config_c3(n_apps=1000, replicas=1000, n_its=1000, zones=3) -> EncodedProblem
     return b.build()
 
 
+def config_deployments(n_deployments=1000, replicas=1000, n_its=1000, zones=3, topology=True, seed=SEED) -> EncodedProblem:
+    """Deployment-shaped variant of C3 / C2 (not a BASELINE configuration): `n_deployments` Deployments of `replicas`
+    IDENTICAL pods each, every Deployment with its own CPU request, so byCPUAndMemoryDescending keeps a Deployment's pods
+    together in the queue -- what a scale-up of real Deployments looks like, and what the solver's cohort commits are for.
+    topology=True: zonal spread (maxSkew 1) + hostname anti-affinity per Deployment (C3's constraints); False: C2's
+    zone / arch selectors and tolerations against a tainted NodePool."""
+    b = ProblemBuilder()
+    its = kwok.aws_instance_types(n_its)
+    for it in its:
+        b.add_instance_type(it)
+    zones_l = kwok.AWS_ZONES
+    if topology:
+        b.add_nodepool(default_nodepool(zones=zones_l[:zones]), list(range(len(its))))
+    else:
+        b.add_nodepool(default_nodepool("default", taints=[Taint("bench/dedicated", "true", "NoSchedule")]), list(range(len(its))))
+    d = draws(n_deployments, 8, seed)
+    cls = np.zeros(n_deployments, np.int32)
+    for a in range(n_deployments):
+        c, m = int(d[a, 0] % np.uint64(5)), int(d[a, 1] % np.uint64(6))
+        req = {"cpu": f"{CPU_MILLI[c] + a % 97}m", "memory": f"{MEM_MI[m] + a // 97}Mi"}  # unique (cpu, memory) per Deployment
+        if topology:
+            labels = {"app": f"dep-{a:05d}"}
+            sel = LabelSelector.of(labels)
+            pod = Pod(labels=labels, requests=req, topology_spread_constraints=[TopologySpreadConstraint(1, ZONE_LABEL, sel)],
+                      pod_anti_affinity=[PodAffinityTerm(sel, HOSTNAME_LABEL)])
+        else:
+            nsel = {}
+            if int(d[a, 2] % np.uint64(2)) == 0:
+                nsel[ZONE_LABEL] = zones_l[int(d[a, 3] % np.uint64(4))]
+            if int(d[a, 4] % np.uint64(4)) == 0:
+                nsel[ARCH_LABEL] = ["x86_64", "arm64"][int(d[a, 5] % np.uint64(2))]
+            t = int(d[a, 6] % np.uint64(40))
+            tols = [] if t < 2 else ([Toleration("bench/dedicated", "Equal", "true", "NoSchedule")] if t % 2 == 0
+                                     else [Toleration("bench/dedicated", "Exists", "", "")])
+            pod = Pod(requests=req, node_selector=nsel, tolerations=tols)
+        cls[a] = b.pod_class(pod)
+    n_pods = n_deployments * replicas
+    u = draws(n_pods, 2, seed + 5)
+    b.set_pod_arrays(np.repeat(cls, replicas), np.zeros(n_pods, np.int64), u[:, 0], u[:, 1])
+    return b.build()
+
+
 def _app_classes(b: ProblemBuilder, n_apps: int, extra_selector=None, tolerations=(), prefix="app"):
     table = np.zeros((n_apps, 5, 6), np.int32)
     for a in range(n_apps):

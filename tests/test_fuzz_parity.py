@@ -211,6 +211,67 @@ def test_fuzz_host_ports_parity_gpu():
     assert not bad, bad[:10]
 
 
+def encode_replicas(seed):
+    """Few deployments with many replicas each (600 - 3 000 pods) on small instance types, so that the queue holds long runs of
+    identical pods and the solve opens 50+ NodeClaims: the solver's cohort commits (kp_wsolve.cuh) against the pod-by-pod
+    reference.  Every deployment gets its own CPU request (the queue then keeps its pods together)."""
+    import random
+    from karpenter_b200.model import quantity_units
+    rng = random.Random(91_000 + seed)
+    pools, per_pool, nodes, pl = fuzz.problem(seed, n_pods=[600, 1500, 3000][seed % 3], with_nodes=seed % 4 == 0)
+    if seed % 5 == 0:
+        fuzz.soften(seed, pools, pl)
+    if seed % 4 == 1:  # topology-free seeds: the solver's lean build
+        for p in pl:
+            p.topology_spread_constraints, p.pod_affinity, p.pod_anti_affinity = [], [], []
+            p.pod_affinity_preferred, p.pod_anti_affinity_preferred = [], []
+    shapes = {}
+    for p in pl:
+        key = repr((p.requests, p.labels, p.namespace, p.node_selector, p.node_affinity_required, p.tolerations,
+                    p.topology_spread_constraints, p.pod_affinity, p.pod_anti_affinity, p.node_affinity_preferred,
+                    p.pod_affinity_preferred, p.pod_anti_affinity_preferred))
+        i = shapes.setdefault(key, len(shapes))
+        if seed % 7:  # one seed of seven keeps the interleaved queue of the plain generator
+            p.requests = dict(p.requests, cpu=f"{quantity_units('cpu', p.requests['cpu']) + i}m")
+        p.creation_timestamp = 0
+    if seed % 2:  # small machines only: many NodeClaims
+        for name, its in per_pool.items():
+            small = sorted(its, key=lambda it: quantity_units("cpu", it.capacity["cpu"]))
+            per_pool[name] = small[:max(2, len(small) // 3)]
+    return Scheduler(pools, per_pool, nodes, claim_order="go" if seed % 3 else "stable").encode(pl)
+
+
+def test_replica_generator_has_runs_and_claims():
+    stats = collections.Counter()
+    for seed in range(24):
+        enc = encode_replicas(seed)
+        res = oracle_lib.solve(enc.problem)
+        stats["claims50"] += int(res["n_claims"] >= 50)
+        stats["claims13_49"] += int(13 <= res["n_claims"] < 50)
+        stats["groups"] += int(res["n_groups"] > 0)
+        stats["lean"] += int(res["n_groups"] == 0)
+        stats["placed"] += int((res["pod_target"] != -1).sum() > 300)
+    assert stats["claims50"] >= 6 and stats["groups"] >= 6 and stats["lean"] >= 4 and stats["placed"] >= 8, stats
+
+
+@pytest.mark.gpu
+def test_fuzz_replica_cohorts_parity_gpu():
+    h = _native.Handle()
+    bad = []
+    try:
+        for seed in range(CAP or 120):
+            enc = encode_replicas(seed)
+            orc = oracle_lib.solve(enc.problem)
+            gpu = h.solve(enc.problem)
+            try:
+                assert_same(gpu, orc, f"seed {seed} ")
+            except AssertionError as e:
+                bad.append((seed, str(e)[:200]))
+    finally:
+        h.close()
+    assert not bad, bad[:10]
+
+
 def consolidation_case(seed):
     """A random small cluster (topology-free pods bound to nodes) and random candidate sets of 1-3 nodes."""
     import random

@@ -401,3 +401,31 @@ def test_more_than_64_requirement_signatures_and_request_vectors(handle):
     pool = NodePool(name="default", requirements=[NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "In", ("spot", "on-demand"))])
     enc = Scheduler([pool], {"default": its}).encode(pods)
     assert_same(handle.solve(enc.problem), oracle_lib.solve(enc.problem), "many signatures ")
+
+
+# ---- cohort commits (kp_wsolve.cuh cohort_try): Deployment-shaped queues, where a Deployment's identical pods stand together
+@pytest.mark.parametrize("deps,replicas,topology,order", [(40, 300, True, 0), (40, 300, True, 1), (150, 200, True, 0),
+                                                          (60, 500, False, 0), (300, 100, False, 1), (8, 2500, False, 0)])
+def test_deployment_cohorts_parity(handle, deps, replicas, topology, order):
+    enc = workloads.config_deployments(deps, replicas, n_its=300, topology=topology)
+    enc.problem.set("claim_order_mode", order)
+    gpu = handle.solve(enc.problem)
+    st = handle.stats()
+    assert st["cohort_pods"] > deps * replicas // 4, st      # the cohort instantiation ran and committed runs
+    assert_same(gpu, oracle_lib.solve(enc.problem, threads=8), f"deployments {deps}x{replicas} ")
+
+
+def test_cohorts_are_the_same_solve_at_scale(handle, monkeypatch):
+    """100 Deployments x 1 000 replicas (C3's constraints, 1 000 types): cohorts on and off give the same bits; the oracle
+    checks a 200-replica version of the same shape above."""
+    enc = workloads.config_deployments(100, 1000, n_its=1000, topology=True)
+    on = handle.solve(enc.problem)
+    assert handle.stats()["cohort_pods"] > 50_000
+    monkeypatch.setenv("KP_NO_COHORT", "1")
+    h2 = _native.Handle()
+    try:
+        off = h2.solve(enc.problem)
+        assert h2.stats()["cohort_pods"] == 0
+    finally:
+        h2.close()
+    assert_same(on, off, "cohorts on/off ")
