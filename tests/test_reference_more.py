@@ -1,17 +1,17 @@
-"""Further reference cases restated against the ORACLE only (CPU tier).  They were written after this round's GPU budget
-was spent, so their CUDA-path twins (the `gpu` parametrisation the other scenario files carry) wait for the next round;
-what they pin is the oracle itself: capacity-type / architecture spreads seen through node affinity, in-flight nodes
-with taints (topology_test.go:815-940, suite_test.go:2025-2209)."""
+"""Further reference cases on both tiers (the file started as oracle-only pins at the end of round 1; every case now has its
+CUDA-path twin): capacity-type / architecture spreads seen through node affinity, in-flight nodes with taints
+(topology_test.go:815-940, suite_test.go:2025-2209), the spot-to-spot consolidation rules (consolidation_test.go:1033-1218)."""
 import pytest
 
 from karpenter_b200.model import ARCH_LABEL, CAPACITY_TYPE_LABEL, INSTANCE_TYPE_LABEL, ZONE_LABEL, Taint, Toleration
 from tests.test_reference_scenarios import req
 from tests.test_reference_topology import LABELS, Cluster, _pool, spread
 
-W = "oracle"
+BACKENDS = [pytest.param("oracle", id="oracle"), pytest.param("gpu", id="gpu", marks=pytest.mark.gpu)]
 
 
-def test_capacity_type_spread_excludes_pods_outside_the_node_affinity():  # topology_test.go:815-850
+@pytest.mark.parametrize("W", BACKENDS)
+def test_capacity_type_spread_excludes_pods_outside_the_node_affinity(W):  # topology_test.go:815-850
     c = Cluster(W)
     c.provision(c.pods(1, labels=LABELS, node_affinity_required=[[req(ZONE_LABEL, "In", "test-zone-1"),
                                                                   req(CAPACITY_TYPE_LABEL, "In", "on-demand")]]))
@@ -21,7 +21,8 @@ def test_capacity_type_spread_excludes_pods_outside_the_node_affinity():  # topo
     assert c.skew(CAPACITY_TYPE_LABEL) == [1, 5]
 
 
-def test_capacity_type_spread_sees_the_existing_on_demand_node():  # topology_test.go:852-894
+@pytest.mark.parametrize("W", BACKENDS)
+def test_capacity_type_spread_sees_the_existing_on_demand_node(W):  # topology_test.go:852-894
     c = Cluster(W, pools=[_pool(requirements=[req(ARCH_LABEL, "In", "amd64", "arm64")])])
     c.provision(c.pods(1, labels=LABELS, node_selector={INSTANCE_TYPE_LABEL: "single-pod-instance-type"},
                        node_affinity_required=[[req(CAPACITY_TYPE_LABEL, "In", "on-demand")]]))
@@ -30,7 +31,8 @@ def test_capacity_type_spread_sees_the_existing_on_demand_node():  # topology_te
     assert c.skew(CAPACITY_TYPE_LABEL) == [1, 2]
 
 
-def test_arch_spread_sees_the_existing_amd64_node():  # topology_test.go:895-938
+@pytest.mark.parametrize("W", BACKENDS)
+def test_arch_spread_sees_the_existing_amd64_node(W):  # topology_test.go:895-938
     c = Cluster(W, pools=[_pool(requirements=[req(ARCH_LABEL, "In", "amd64", "arm64")])])
     c.provision(c.pods(1, labels=LABELS, node_selector={INSTANCE_TYPE_LABEL: "single-pod-instance-type"},
                        node_affinity_required=[[req(ARCH_LABEL, "In", "amd64")]]))
@@ -39,7 +41,8 @@ def test_arch_spread_sees_the_existing_amd64_node():  # topology_test.go:895-938
     assert c.skew(ARCH_LABEL) == [1, 2]
 
 
-def test_untainted_in_flight_node_is_assumed():  # suite_test.go:2026-2047
+@pytest.mark.parametrize("W", BACKENDS)
+def test_untainted_in_flight_node_is_assumed(W):  # suite_test.go:2026-2047
     c = Cluster(W)
     first = c.pods(1, requests={"cpu": "10m"})
     c.provision(first)
@@ -48,7 +51,8 @@ def test_untainted_in_flight_node_is_assumed():  # suite_test.go:2026-2047
     assert c.bound[id(first[0])] == c.bound[id(second[0])]
 
 
-def test_tainted_in_flight_node_with_a_toleration():  # suite_test.go:2086-2117, the tolerating twin
+@pytest.mark.parametrize("W", BACKENDS)
+def test_tainted_in_flight_node_with_a_toleration(W):  # suite_test.go:2086-2117, the tolerating twin
     c = Cluster(W)
     first = c.pods(1, requests={"cpu": "10m"})
     c.provision(first)
@@ -77,7 +81,7 @@ def _assorted(n):
     return out[:n]
 
 
-def _spot_case(n_types, spot_to_spot=True):
+def _spot_case(W, n_types, spot_to_spot=True):
     from karpenter_b200.disruption import Consolidation
     from karpenter_b200.model import NodePool, Offering
     from tests import oracle_lib
@@ -91,15 +95,21 @@ def _spot_case(n_types, spot_to_spot=True):
     np_ = NodePool(name="default", requirements=[req(CAPACITY_TYPE_LABEL, "In", "spot", "on-demand"),
                                                  req(ARCH_LABEL, "In", "amd64", "arm64")], limits={"cpu": "2000"})
     n = _node("spot-node", node_it, zone=zone, ct="spot", pod_list=pods(1, requests={"cpu": "100m"}))
-    c = Consolidation([np_], {np_.name: its}, [n], spot_to_spot=spot_to_spot, backend=oracle_lib.consolidate)
-    return c.compute([["spot-node"]])[0]
+    c = Consolidation([np_], {np_.name: its}, [n], spot_to_spot=spot_to_spot,
+                      backend=oracle_lib.consolidate if W == "oracle" else None)
+    try:
+        return c.compute([["spot-node"]])[0]
+    finally:
+        c.close()
 
 
+@pytest.mark.parametrize("W", BACKENDS)
 @pytest.mark.parametrize("n_types", [5, 20])
-def test_spot_to_spot_needs_fifteen_cheaper_types(n_types):  # consolidation_test.go:1033-1107, 1149-1218
-    cmd = _spot_case(n_types)
+def test_spot_to_spot_needs_fifteen_cheaper_types(W, n_types):  # consolidation_test.go:1033-1107, 1149-1218
+    cmd = _spot_case(W, n_types)
     assert cmd.decision == "noop" and cmd.n_new_node_claims == 1  # a cheaper spot type exists, but only one of them
 
 
-def test_spot_to_spot_needs_the_feature_gate():  # consolidation_test.go:1108-1148
-    assert _spot_case(20, spot_to_spot=False).decision == "noop"
+@pytest.mark.parametrize("W", BACKENDS)
+def test_spot_to_spot_needs_the_feature_gate(W):  # consolidation_test.go:1108-1148
+    assert _spot_case(W, 20, spot_to_spot=False).decision == "noop"
