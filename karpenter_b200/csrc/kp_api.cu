@@ -1519,8 +1519,10 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   if (rc != KP_OK) return rc;
   HostTables& t = h->cur->host;
   KpDev& d = h->cur->dev;
-  if (t.has_min_values) {  // RemoveInstanceTypeOptionsByPriceAndMinValues / Truncate with minValues (nodeclaim.go:309-318)
-    h->err = "consolidation with minValues on a NodePool is not supported yet";
+  if (t.has_min_values && !t.min_values_strict) {
+    // BestEffort lowers minValues per NodeClaim during the simulation (nodeclaim.go:186-191); carrying those per-claim values
+    // through RemoveInstanceTypeOptionsByPriceAndMinValues is not built.  Strict (the default policy) is served.
+    h->err = "consolidation with minValues under the BestEffort policy is not supported yet";
     return KP_ERR_UNSUPPORTED;
   }
   const int K = t.K, R = t.R, ITW = t.ITW, E = t.E, N = t.N, T = t.T;

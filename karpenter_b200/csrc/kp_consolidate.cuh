@@ -375,12 +375,13 @@ struct KpConsol {
 __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q, size_t slot, Slot* scratch,
                                               const uint8_t* c_sflags, const uint64_t* c_smask, const int64_t* c_sgte,
                                               const int64_t* c_slte, const uint64_t* c_its, int c_tmpl0, const int64_t* c_req0,
-                                              int sn, const int32_t* snodes, int unscheduled, int n_new, int s, int lane) {
+                                              int c_npods0, int sn, const int32_t* snodes, int unscheduled, int n_new, int s,
+                                              int lane) {
   const int K = d.K, ITW = d.ITW;
   int decision = KP_DECISION_NOOP;
   uint64_t rep = 0;  // lane w: word w of the replacement instance types
   bool have_slots = false;  // scratch[] holds the claim's requirement slots (with the spot pin when it applied)
-  bool spot_pinned = false;
+  bool spot_pinned = false, mv_dropped = false;
   int n_ord_out = 0;
   if (!unscheduled) {
     if (n_new == 0) {
@@ -454,9 +455,17 @@ __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q,
           for (int i = lane; i < n_ord; i += 32) atomicOr(&sb[sv[i] >> 6], 1ull << (sv[i] & 63));
           __syncwarp();
           cur = lane < ITW ? sb[lane] : 0ull;
+          // Truncate (types.go:339-351): the 600 cheapest must still satisfy minValues, else TruncateInstanceTypes drops the
+          // NodeClaim and its pods become PodErrors (scheduler.go:361-379): not all pods scheduled, nothing to do
+          if (d.mv_strict && !min_values_ok(d, c_tmpl0, cur, lane)) {
+            mv_dropped = true;
+            unscheduled = c_npods0;
+          }
         }
       }
-      if (spot_path && !q.spot_to_spot_enabled) {
+      if (mv_dropped) {
+        decision = KP_DECISION_NOOP;
+      } else if (spot_path && !q.spot_to_spot_enabled) {
         decision = KP_DECISION_NOOP;  // computeSpotToSpotConsolidation needs the feature gate (consolidation.go:239)
       } else {
         if (spot_path) {  // restrict the claim to spot (consolidation.go:252-257) and drop types without such an offering
@@ -497,6 +506,8 @@ __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q,
           }
         }
         bool any = __any_sync(FULL, rep != 0);
+        // ... and SatisfiesMinValues of what is left (nodeclaim.go:314-316): an error is "Filtering by price", no command
+        if (any && d.mv_strict && !min_values_ok(d, c_tmpl0, rep, lane)) any = false;
         if (any && spot_path && sn == 1) {
           // single-node spot-to-spot: at least 15 cheaper types, and only the 15 cheapest go out (consolidation.go:283-312)
           int total = lane < ITW ? __popcll(rep) : 0;
@@ -506,22 +517,40 @@ __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q,
           } else {
             if (lane < ITW) sb[lane] = rep;
             __syncwarp();
-            uint64_t first15 = 0;  // lane w collects its words' bits; walk the price order 32 entries at a time
-            int taken = 0;
-            for (int b0 = 0; b0 < n_ord && taken < 15; b0 += 32) {
-              const int i = b0 + lane;
-              const int t = i < n_ord ? sv[i] : 0;
-              const bool in = i < n_ord && ((sb[t >> 6] >> (t & 63)) & 1ull);
-              const unsigned m = __ballot_sync(FULL, in);
-              const int rank = taken + __popc(m & ((1u << lane) - 1));
-              const bool take = in && rank < 15;
-              for (int l = 0; l < 32; l++) {  // hand each taken type to the lane that owns its word
-                const int tt = __shfl_sync(FULL, take ? t : -1, l);
-                if (tt >= 0 && (tt >> 6) == lane) first15 |= 1ull << (tt & 63);
+            // the first n of the surviving types in price order, as a bitmap (lane w: word w)
+            auto prefix_bits = [&](int n) {
+              uint64_t acc = 0;
+              int taken = 0;
+              for (int b0 = 0; b0 < n_ord && taken < n; b0 += 32) {
+                const int i = b0 + lane;
+                const int t = i < n_ord ? sv[i] : 0;
+                const bool in = i < n_ord && ((sb[t >> 6] >> (t & 63)) & 1ull);
+                const unsigned m = __ballot_sync(FULL, in);
+                const int rank = taken + __popc(m & ((1u << lane) - 1));
+                const bool take = in && rank < n;
+                for (int l = 0; l < 32; l++) {  // hand each taken type to the lane that owns its word
+                  const int tt = __shfl_sync(FULL, take ? t : -1, l);
+                  if (tt >= 0 && (tt >> 6) == lane) acc |= 1ull << (tt & 63);
+                }
+                taken += __popc(m);
               }
-              taken += __popc(m);
+              return acc;
+            };
+            // 15, or as many as minValues needs if that is more: the shortest prefix of the price order that satisfies every
+            // key (consolidation.go:296-312, types.go:301-337).  All `total` types satisfy them (checked above).
+            uint64_t first = prefix_bits(15);
+            if (d.mv_strict && !min_values_ok(d, c_tmpl0, first, lane)) {
+              int bad = 15, good = total;
+              while (good - bad > 1) {
+                const int mid = (good + bad) >> 1;
+                if (min_values_ok(d, c_tmpl0, prefix_bits(mid), lane))
+                  good = mid;
+                else
+                  bad = mid;
+              }
+              first = prefix_bits(good);
             }
-            rep = first15;
+            rep = first;
           }
         }
         if (any && q.filter_same_type && sn >= 2) {
@@ -560,6 +589,8 @@ __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q,
               }
             rep = keep;
             any = __any_sync(FULL, rep != 0);
+            // RemoveInstanceTypeOptionsByPriceAndMinValues again (multinodeconsolidation.go:220-224)
+            if (any && d.mv_strict && !min_values_ok(d, c_tmpl0, rep, lane)) any = false;
           }
         }
         if (any) decision = KP_DECISION_REPLACE;
@@ -789,7 +820,7 @@ __global__ void __launch_bounds__(CONSOL_WARPS * 32, CONSOL_MIN_CTAS) k_consolid
     if (!LEAN) claims_finalize(d, I.c_sflags, I.c_smask, I.c_rsv, I.n_claims, lane);
     // ---- computeConsolidation (consolidation.go:136-229)
     consol_decide(d, q, slot, W.scratch, I.c_sflags, I.c_smask, I.c_sgte, I.c_slte, I.c_its, I.n_claims > 0 ? I.c_tmpl[0] : -1,
-                  I.c_req, sn, snodes, I.n_unsched + I.n_uninit, I.n_claims, s, lane);
+                  I.c_req, I.n_claims > 0 ? I.c_npods[0] : 0, sn, snodes, I.n_unsched + I.n_uninit, I.n_claims, s, lane);
   }
 }
 
@@ -804,5 +835,5 @@ __global__ void __launch_bounds__(32) k_decide_batch(const KpDev* __restrict__ d
   const int unscheduled = (int)(d.counters[7] + d.counters[8]);
   const int n_new = *d.n_claims;
   consol_decide(d, q, (size_t)b, scratch, d.c_sflags, d.c_smask, d.c_sgte, d.c_slte, d.c_its, n_new > 0 ? d.c_tmpl[0] : -1,
-                d.c_req, soff[b + 1] - soff[b], snodes + soff[b], unscheduled, n_new, b, lane);
+                d.c_req, n_new > 0 ? d.c_npods[0] : 0, soff[b + 1] - soff[b], snodes + soff[b], unscheduled, n_new, b, lane);
 }

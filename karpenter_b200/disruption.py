@@ -42,8 +42,9 @@ class Consolidation:
                  state_nodes: Sequence[StateNode], spot_to_spot: bool = False, backend: Optional[Callable] = None,
                  device: int = -1, preference_policy: str = "Respect", filter_same_instance_type: bool = False,
                  pending_pods: Sequence = (), deleting_node_pods: Sequence = (), price_order: bool = False,
-                 solve_backend: Optional[Callable] = None):
+                 solve_backend: Optional[Callable] = None, min_values_policy: str = "Strict"):
         self.node_pools = list(node_pools)
+        self.min_values_policy = min_values_policy  # options.MinValuesPolicy; kp_consolidate serves Strict only
         self.instance_types = instance_types
         # sortExistingNodes order (scheduler.go:738-751): initialized first, then by name
         self.state_nodes = sorted(state_nodes, key=lambda n: (not n.initialized, n.name))
@@ -64,6 +65,7 @@ class Consolidation:
     def _encode(self, candidate_sets):
         b = ProblemBuilder()
         b.preference_policy = self.preference_policy
+        b.min_values_policy = self.min_values_policy
         index: Dict[int, int] = {}
         by_name: Dict[str, int] = {}
         for np_ in self.node_pools:
@@ -144,6 +146,7 @@ class Consolidation:
         names = set(candidate_set)
         b = ProblemBuilder()
         b.preference_policy = self.preference_policy
+        b.min_values_policy = self.min_values_policy
         index, it_names = {}, []
         for np_ in self.node_pools:
             ids = []

@@ -814,7 +814,9 @@ int orc_consolidate(const kp_problem* p, const kp_consol_input* in, kp_consol_re
 }
 // subsets are independent simulations: `threads` workers take them round-robin
 int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol_result* out, int threads) {
-  if (has_min_values(p)) return KP_ERR_UNSUPPORTED;
+  // BestEffort lowers minValues per NodeClaim during the simulation (nodeclaim.go:186-191); carrying those per-claim values
+  // through the decision is not built: refused, like the CUDA path does
+  if (has_min_values(p) && p->min_values_best_effort) return KP_ERR_UNSUPPORTED;
   if (reserved_offerings_malformed(p)) return KP_ERR_INVALID;
   Prob P(p);
   Pricing pr(P);
@@ -900,7 +902,15 @@ int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol
       InflightClaim& c = *sch.claim_store[0];
       // SimulateScheduling: TruncateInstanceTypes(MaxInstanceTypes = 600) (helpers.go:120, scheduler.go:361-379)
       pr.order_by_price(c.its, c.reqs);
-      if (c.its.size() > 600) c.its.resize(600);
+      if (c.its.size() > 600) {
+        c.its.resize(600);
+        // Truncate (types.go:339-351): the 600 cheapest must still satisfy minValues, else TruncateInstanceTypes drops the
+        // NodeClaim and its pods become PodErrors (scheduler.go:361-379) -- not all pods scheduled, nothing to do
+        if (c.reqs.has_min_values() && !sch.satisfies_min_values(c.its, c.reqs)) {
+          out->n_unscheduled[s_i] = (int32_t)c.pods.size();
+          break;
+        }
+      }
       // getCandidatePrices (consolidation.go:319-337)
       double price = 0;
       bool zero = false;
@@ -949,10 +959,25 @@ int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol
       std::vector<int> kept;  // RemoveInstanceTypeOptionsByPriceAndMinValues (nodeclaim.go:309-318)
       for (int it : c.its)
         if (pr.worst_launch_price(it, c.reqs, in->capacity_type_key, ct_order) < price) kept.push_back(it);
+      // ... and SatisfiesMinValues of what is left (nodeclaim.go:314-316): an error is "Filtering by price", no command
+      if (c.reqs.has_min_values() && !sch.satisfies_min_values(kept, c.reqs)) break;
       if (kept.empty()) break;
       if (all_spot && spot_ok && (in->subset_off[s_i + 1] - in->subset_off[s_i]) == 1) {
         if (kept.size() < 15) break;  // MinInstanceTypesForSpotToSpotConsolidation
-        kept.resize(15);
+        // the 15 cheapest go out -- or as many as minValues needs, if that is more (consolidation.go:296-312; the shortest
+        // prefix of the price order that satisfies every key, types.go:301-337)
+        size_t cap = 15;
+        if (c.reqs.has_min_values()) {
+          std::vector<int> prefix;
+          for (size_t i = 0; i < kept.size(); i++) {
+            prefix.push_back(kept[i]);
+            if (sch.satisfies_min_values(prefix, c.reqs)) {
+              cap = std::max<size_t>(15, i + 1);
+              break;
+            }
+          }
+        }
+        kept.resize(std::min(cap, kept.size()));
       }
       if (in->filter_same_instance_type && in->subset_off[s_i + 1] - in->subset_off[s_i] >= 2) {
         // filterOutSameInstanceType (multinodeconsolidation.go:189-226)
@@ -985,7 +1010,10 @@ int orc_consolidate_mt(const kp_problem* p, const kp_consol_input* in, kp_consol
         for (int it : kept)
           if (pr.worst_launch_price(it, c.reqs, in->capacity_type_key, ct_order) < max_price) kept2.push_back(it);
         kept.swap(kept2);
-        if (kept.empty()) break;  // not a valid command for the binary search (multinodeconsolidation.go:157-163)
+        // RemoveInstanceTypeOptionsByPriceAndMinValues again (multinodeconsolidation.go:220-224): an error or an empty list
+        // is not a valid command for the binary search (:157-163)
+        if (c.reqs.has_min_values() && !sch.satisfies_min_values(kept, c.reqs)) break;
+        if (kept.empty()) break;
       }
       decision = KP_DECISION_REPLACE;
       for (int it : kept) rep[it >> 6] |= 1ull << (it & 63);

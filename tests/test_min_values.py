@@ -152,12 +152,14 @@ def test_min_values_many_pods_wide_catalog(which):
     assert len(loose.new_node_claims) < len(r.new_node_claims)  # minValues costs nodes: claims stop growing earlier
 
 
-def test_consolidation_with_min_values_is_refused_by_the_oracle_too():
+def test_consolidation_with_best_effort_min_values_is_refused_by_the_oracle_too():
+    """Strict minValues are served by kp_consolidate (tests/test_consolidation_min_values.py); BestEffort is not."""
     from karpenter_b200.disruption import Consolidation
     from tests.test_reference_scenarios import _node
     its = two_types()
     np_ = NodePool(name="default", requirements=[mreq(INSTANCE_TYPE_LABEL, "Exists", min_values=2)])
     n = _node("n1", its[1], zone="test-zone-1-spot", ct="spot", pod_list=pods(1, **SMALL))
-    c = Consolidation([np_], {np_.name: its}, [n], backend=oracle_lib.consolidate)
+    c = Consolidation([np_], {np_.name: its}, [n], backend=oracle_lib.consolidate, min_values_policy="BestEffort")
     with pytest.raises(RuntimeError):
         c.compute([["n1"]])
+    assert Consolidation([np_], {np_.name: its}, [n], backend=oracle_lib.consolidate).compute([["n1"]])[0].decision == "noop"
