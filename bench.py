@@ -198,6 +198,42 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def time_encoder(n_pods_headline, e2e_ms):
+    """The Python mirror's encoder on real Pod objects (the headline feeds class ids, as the cgo shim would after interning):
+    200 apps x 1 000 replicas of C3's shape as `Pod` objects carrying their owner's template key, Scheduler.encode timed."""
+    from karpenter_b200 import workloads
+    from karpenter_b200.model import HOSTNAME_LABEL, ZONE_LABEL, LabelSelector, Pod, PodAffinityTerm, TopologySpreadConstraint
+    from karpenter_b200.scheduler import Scheduler
+    apps, reps = 200, 1000
+    its = workloads.kwok.aws_instance_types(C3_ITS)
+    pool = workloads.default_nodepool(zones=workloads.kwok.AWS_ZONES[:3])
+    pods = []
+    for a in range(apps):
+        labels = {"app": f"app-{a:05d}"}
+        sel = LabelSelector.of(labels)
+        tsc = [TopologySpreadConstraint(1, ZONE_LABEL, sel)]
+        anti = [PodAffinityTerm(sel, HOSTNAME_LABEL)]
+        req = {"cpu": f"{250 * (1 + a % 4)}m", "memory": f"{256 * (1 + a % 6)}Mi"}
+        for r in range(reps):
+            pods.append(Pod(name=f"p{a}-{r}", uid=(a << 32) | r, labels=labels, requests=req, topology_spread_constraints=tsc,
+                            pod_anti_affinity=anti, template=a))
+    s = Scheduler([pool], {pool.name: its}, backend=lambda p: None)
+    t0 = time.perf_counter()
+    s.encode(pods)
+    with_t = time.perf_counter() - t0
+    for p in pods:
+        p.template = None
+    t0 = time.perf_counter()
+    s.encode(pods[:50_000])
+    without_t = (time.perf_counter() - t0) * len(pods) / 50_000
+    rate = len(pods) / with_t
+    return {"pods_per_s": rate, "pods_per_s_without_template_keys": len(pods) / without_t,
+            "sample": f"{len(pods)} Pod objects ({apps} apps x {reps} replicas, C3's shape, {C3_ITS} instance types), "
+                      "Scheduler.encode: catalog + NodePool + pods -> kp_problem; Pod.template = the owner's pod-template key",
+            "e2e_with_encode_ms_extrapolated": e2e_ms + 1000.0 * n_pods_headline / rate,
+            "note": "extrapolated to the headline's pod count from the sample's rate; the headline e2e starts from class ids"}
+
+
 def peak_gbs():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0), "measured"
@@ -393,6 +429,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-consolidation", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--no-deployments", action="store_true")
     ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--consol-nodes", type=int, default=10_000)
     ap.add_argument("--consol-pods", type=int, default=200_000)
@@ -476,6 +513,18 @@ def main():
                 c2["cpu_baseline"] = {"value": C2_PODS / dt, "unit": "pods/s", "cores": threads, "kind": "port",
                                       "sample": f"the full workload ({C2_PODS} pods), one Solve, {threads} thread(s)"}
             line["c2"] = c2
+        # ---------------- secondary: a Deployment-shaped queue (cohort commits) and the Python encoder on Pod objects
+        if not args.no_deployments:
+            encd = workloads.config_deployments(C3_APPS, C3_REPLICAS, n_its=C3_ITS, topology=True)
+            md = time_provisioning(h, encd.problem, n_pods_dep := C3_APPS * C3_REPLICAS, 2, 1, torch, flush, barrier, e2e_steps=1)
+            line["deployments"] = {
+                "workload": "NOT a BASELINE config: 1 000 Deployments x 1 000 identical replicas with C3's constraints (zonal spread + "
+                            "hostname anti-affinity), every Deployment with its own CPU request so that its pods stand together in the "
+                            "queue; the solver's cohort instantiation commits runs of identical pods in one step",
+                "value": n_pods_dep / (md["ms"] / 1000), "unit": "pods/s", "ms_per_step": md["ms"], "us_per_pod": 1000 * md["ms"] / n_pods_dep,
+                "cohort_pods": int(md["stats"].get("cohort_pods", 0)), "node_claims": int(md["res"]["n_claims"]),
+                "unscheduled": int((md["res"]["pod_target"] == -1).sum())}
+            line["encoder"] = time_encoder(n_pods, m["e2e_ms"])
         # ---------------- secondary: C5's 8 NodePool shards as one batch on this GPU
         if not args.no_c5:
             m5 = time_c5(h, 0, 1, 1, 1, torch, None, flush, barrier)

@@ -170,6 +170,7 @@ class ProblemBuilder:
         self.templates: List[dict] = []
         self.nodes: List[dict] = []
         self.pods: List[Tuple[int, int, int]] = []  # (class, creation, uid)
+        self._template_class: Dict[object, int] = {}
         self.running: List[Tuple[int, int]] = []
         self.extra_keys = set()
         self.claim_order_mode = 0
@@ -307,7 +308,14 @@ class ProblemBuilder:
         return cid
 
     def add_pod(self, pod: Pod) -> int:
-        self.pods.append((self.pod_class(pod), pod.creation_timestamp, pod.uid))
+        t = pod.template
+        if t is None:
+            cid = self.pod_class(pod)
+        else:  # pods of one template are one class: intern the spec once
+            cid = self._template_class.get(t)
+            if cid is None:
+                cid = self._template_class[t] = self.pod_class(pod)
+        self.pods.append((cid, pod.creation_timestamp, pod.uid))
         return len(self.pods) - 1
 
     def set_pod_arrays(self, pod_class, creation, uid_hi, uid_lo):

@@ -61,8 +61,25 @@ def parse_quantity(q) -> Fraction:
     return Fraction(s)
 
 
+_UNITS_CACHE: Dict[Tuple[str, object], int] = {}
+
+
 def quantity_units(name: str, q) -> int:
-    """Exact integer in the resource's unit: milli for cpu, base units (bytes / count) otherwise."""
+    """Exact integer in the resource's unit: milli for cpu, base units (bytes / count) otherwise.  Memoised: a pass over
+    10^5 pods parses the same few quantity strings over and over (the reference caches PodData per pod for the same reason,
+    scheduler.go:471-491)."""
+    if isinstance(q, (str, int)):
+        hit = _UNITS_CACHE.get((name, q))
+        if hit is not None:
+            return hit
+        v = _quantity_units(name, q)
+        if len(_UNITS_CACHE) < 65536:
+            _UNITS_CACHE[(name, q)] = v
+        return v
+    return _quantity_units(name, q)
+
+
+def _quantity_units(name: str, q) -> int:
     f = parse_quantity(q)
     if name == "cpu":
         f = f * 1000
@@ -263,6 +280,10 @@ class Pod:
     # container ports with a hostPort: (hostIP, hostPort, protocol); "" / "0.0.0.0" / "::" are the unspecified address, the
     # protocol defaults to TCP (scheduling.GetHostPorts, hostportusage.go:93-118)
     host_ports: List[Tuple[str, int, str]] = field(default_factory=list)
+    # Optional: an opaque key two pods share only if everything the scheduler looks at is identical (the owner's
+    # pod-template-hash in practice).  The encoder then interns the spec once per key instead of once per pod -- what the
+    # reference's per-pod PodData cache (scheduler.go:471-491) buys it, and the shim's job when 10^6 pods arrive.
+    template: Optional[object] = None
 
 
 # cloudprovider.ReservationIDLabel (pkg/cloudprovider/types.go:49-52) is the provider's to name; this is the fake provider's

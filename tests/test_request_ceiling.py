@@ -48,3 +48,24 @@ def test_ceiled_requests_reach_the_solver():
     assert all(quantity_units("cpu", by[n].capacity["cpu"]) >= 3250 for n in claim.instance_type_options)
     plain = Scheduler([pool], {"default": its}, backend=oracle_lib.solve).solve([Pod(name="q", uid=2, requests={"cpu": "500m"})])
     assert len(plain.new_node_claims[0].instance_type_options) > len(claim.instance_type_options)
+
+
+def test_template_keys_intern_the_same_classes():
+    """Pod.template (an owner's pod-template key) lets the encoder intern a spec once per key: same problem, bit for bit."""
+    import random
+    import numpy as np
+    from karpenter_b200.scheduler import Scheduler
+    from tests import fuzz
+    rng = random.Random(3)
+    pl = fuzz.pods(rng, 3000)
+    pools, its = fuzz.node_pools(rng), fuzz.instance_types(rng)
+    s = Scheduler(pools, {p.name: its for p in pools}, backend=lambda p: None)
+    plain = s.encode(pl).problem
+    keys = {}
+    for p in pl:
+        p.template = keys.setdefault(repr((p.requests, p.labels, p.namespace, p.node_selector, p.node_affinity_required, p.tolerations,
+                                           p.topology_spread_constraints, p.pod_affinity, p.pod_anti_affinity)), len(keys))
+    keyed = s.encode(pl).problem
+    assert plain.n_classes == keyed.n_classes
+    for k in ("pod_class", "class_requests", "class_reqset", "pod_uid_lo"):
+        assert np.array_equal(plain.get(k), keyed.get(k)), k
