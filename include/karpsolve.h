@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KP_ABI_VERSION 3
+#define KP_ABI_VERSION 4
 
 typedef enum kp_status {
   KP_OK = 0,
@@ -268,6 +268,12 @@ typedef struct kp_problem {
   const uint64_t* class_hostports;    /* [n_classes] GetHostPorts(pod) (:93-118) */
   const uint64_t* node_hostports;     /* [n_nodes] StateNode.HostPortUsage(): ports of the pods bound to the node */
   const uint64_t* tmpl_hostports;     /* [n_templates] daemonHostPortUsage[template] (scheduler.go:794-811) */
+  /* ---- Results.TruncateInstanceTypes (scheduler.go:361-379, types.go:339-351; provisioner.go:380 calls it with
+   * MaxInstanceTypes = 600 right after Solve): > 0: every new NodeClaim keeps its max_instance_types cheapest types
+   * (OrderByPrice over its requirements, types.go:238-257) in claim_its; a truncated list that breaks the NodePool's minValues
+   * under the Strict policy marks the claim dropped (kp_result.claim_dropped) and its pods KP_PODERR_MINVALUES_TRUNCATED.
+   * 0: claim_its is the full list and the caller truncates. */
+  int32_t max_instance_types;
 } kp_problem;
 
 /* pod_target encoding */
@@ -280,6 +286,9 @@ typedef struct kp_problem {
 #define KP_PODERR_INCOMPATIBLE 2       /* every template rejected the pod (multierr of scheduler.go:683) */
 #define KP_PODERR_RESERVED 3           /* ReservedOfferingError (nodeclaim.go:64-79): compatible reserved capacity exists but
                                           is taken; the pod was neither relaxed nor sent to a lower-weight NodePool */
+
+#define KP_PODERR_MINVALUES_TRUNCATED 4 /* the pod's NodeClaim was dropped by TruncateInstanceTypes (scheduler.go:368-373); pod_target
+                                          still names the claim */
 
 #define KP_SLOT_PRESENT 0x10u /* or-ed with KP_REQ_* in claim_req_flags */
 
@@ -311,6 +320,7 @@ typedef struct kp_result {
   void* _impl;
   /* NodeClaim.reservedOfferings as a bit set over reservation ids (claim_req_* already carry FinalizeScheduling's pins) */
   uint64_t* claim_reservations; /* [n_claims] */
+  uint8_t* claim_dropped;       /* [n_claims] 1: TruncateInstanceTypes dropped the claim (max_instance_types > 0 only) */
 } kp_result;
 
 /* ---- consolidation ---- */

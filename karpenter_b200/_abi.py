@@ -175,6 +175,7 @@ def result_to_dict(r: kp_result, n_resources: int) -> dict:
         "n_commits": r.n_commits,
         "solve_ms": r.solve_ms,
         "claim_reservations": view(r.claim_reservations, C_, np.uint64),
+        "claim_dropped": view(r.claim_dropped, C_, np.uint8),
     }
     return out
 
@@ -210,5 +211,5 @@ CONSOL_PARITY_KEYS = ["decision", "n_new_claims", "n_unscheduled", "replacement_
 PARITY_KEYS = [
     "pod_target", "pod_error", "n_claims", "claim_template", "claim_npods", "claim_rank", "claim_requests",
     "claim_its", "claim_req_flags", "claim_req_gte", "claim_req_lte", "claim_req_mask", "group_domain_off",
-    "domain_counts", "claim_reservations",
+    "domain_counts", "claim_reservations", "claim_dropped",
 ]

@@ -102,6 +102,13 @@ struct Instance {
   size_t sort_tmp_bytes = 0;
   bool lean = false;  // no topology group / bound / minValues / reservation: the lean instantiation of the solver serves it
   bool cohort = false;  // the queue holds long runs of identical pods: the cohort instantiation serves it (kp_wsolve.cuh cohort_try)
+  // Results.TruncateInstanceTypes inside the solve (kp_problem.max_instance_types > 0): price lists + per-warp sort scratch
+  int max_its = 0;
+  PriceTabs price_tabs{};
+  double* trunc_key = nullptr;
+  int32_t* trunc_val = nullptr;
+  unsigned long long* trunc_bits = nullptr;
+  uint8_t* d_dropped = nullptr;
   // shared-memory plan of the solve CTA (plan_solve)
   int CS = 0, CR = 0;
   size_t smem = 0;
@@ -283,6 +290,7 @@ static void batch_clear(kp_handle* h);
 
 extern "C" {
 
+#define KP_TRUNC_BLOCKS 148  // k_truncate_claims: 4 warps per block, one claim per warp at a time
 int kp_version(void) { return KP_ABI_VERSION; }
 
 // sort.Slice order of a key array (host; no device needed): see kp_gosort_host.hpp
@@ -741,6 +749,7 @@ static int reset_dynamic(kp_handle* h) {
   CK(cudaMemsetAsync(d.cmask, 0, C * sizeof(ulonglong2), h->stream));
   CK(cudaMemsetAsync(d.amask, 0, C * 8, h->stream));
   CK(cudaMemsetAsync(d.c_rsv, 0, C * 8, h->stream));
+  if (h->cur->d_dropped) CK(cudaMemsetAsync(h->cur->d_dropped, 0, C, h->stream));
   CK(cudaMemsetAsync(d.host_cnt, 0, (size_t)d.GHS * d.H * 4, h->stream));
   if (t.E && t.GH)  // initial hostname-group counts of the existing nodes: the first E host rows
     CK(cudaMemcpyAsync(d.host_cnt, h->cur->d_host_cnt_nodes, (size_t)t.E * d.GHS * 4, cudaMemcpyDeviceToDevice, h->stream));
@@ -830,6 +839,38 @@ static int do_upload(kp_handle* h, const kp_problem* p, int cmax, bool fresh_are
       if (pods_of[x] > 1 && classes_at[rank[x]] == 1) in_runs += pods_of[x];
     h->cur->cohort = (in_runs * 4 >= (int64_t)P && P > 0 && !getenv("KP_NO_COHORT")) || getenv("KP_COHORT");
     d.cohort = h->cur->cohort ? 1 : 0;
+  }
+  h->cur->max_its = p->max_instance_types > 0 ? p->max_instance_types : 0;
+  if (h->cur->max_its > 0) {
+    const HostTables& t = h->cur->host;
+    const int T = p->n_its;
+    // OrderByPrice lists: available offerings per instance type, cheapest first (types.go:238-257)
+    std::vector<int32_t> ml_off((size_t)T + 1, 0), ml_set;
+    std::vector<double> ml_price;
+    for (int ti = 0; ti < T; ti++) {
+      std::vector<std::pair<double, int>> ent;
+      for (int o = p->it_off_off[ti]; o < p->it_off_off[ti + 1]; o++)
+        if (p->off_available[o]) ent.push_back({p->off_price[o], t.off_set[o]});
+      std::stable_sort(ent.begin(), ent.end(),
+                       [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });
+      for (auto& e : ent) {
+        ml_price.push_back(e.first);
+        ml_set.push_back(e.second);
+      }
+      ml_off[(size_t)ti + 1] = (int32_t)ml_set.size();
+    }
+    if (ml_set.empty()) {
+      ml_set.push_back(0);
+      ml_price.push_back(0);
+    }
+    CK(up(h, &h->cur->price_tabs.ml_off, ml_off));
+    CK(up(h, &h->cur->price_tabs.ml_set, ml_set));
+    CK(up(h, &h->cur->price_tabs.ml_price, ml_price));
+    const size_t NW = (size_t)KP_TRUNC_BLOCKS * 4;
+    CK(h->arena.alloc(&h->cur->trunc_key, NW * std::max(T, 1)));
+    CK(h->arena.alloc(&h->cur->trunc_val, NW * std::max(T, 1)));
+    CK(h->arena.alloc(&h->cur->trunc_bits, NW * std::max((T + 63) / 64, 1)));
+    CK(zeros(h, &h->cur->d_dropped, (size_t)std::max<int64_t>(h->cur->dev.Cmax, 1)));
   }
   {  // NewQueue sort: key / permutation ping-pong buffers and cub's scratch, sized once per upload
     int64_t* ka;
@@ -1020,6 +1061,12 @@ static int run_solve(kp_handle* h) {
     CK(cudaLaunchKernel(fn, dim3(1), dim3(64), args, in.smem, h->stream));
   }
   h->stats.kernel_launches++;
+  if (in.max_its > 0) {  // Results.TruncateInstanceTypes (scheduler.go:361-379)
+    k_truncate_claims<<<KP_TRUNC_BLOCKS, 128, 0, h->stream>>>(d, in.price_tabs, in.max_its, in.trunc_key, in.trunc_val, in.trunc_bits,
+                                                               in.d_dropped);
+    if (in.P > 0) k_mark_dropped<<<(int)((in.P + 255) / 256), 256, 0, h->stream>>>(d.pod_target, d.pod_error, in.d_dropped, in.P);
+    h->stats.kernel_launches += 2;
+  }
   rc = reduce_counters(h, {&in});
   if (rc != KP_OK) return rc;
   CK(cudaEventRecord(h->ev1, h->stream));
@@ -1060,6 +1107,8 @@ static int download(kp_handle* h, kp_result* out) {
   out->claim_rank = (int32_t*)calloc(c1, 4);
   out->claim_reservations = (uint64_t*)calloc(c1, 8);
   CK(cudaMemcpy(out->claim_reservations, d.c_rsv, C * 8, cudaMemcpyDeviceToHost));
+  out->claim_dropped = (uint8_t*)calloc(c1, 1);
+  if (h->cur->d_dropped) CK(cudaMemcpy(out->claim_dropped, h->cur->d_dropped, C, cudaMemcpyDeviceToHost));
   out->claim_requests = (int64_t*)calloc(c1 * R, 8);
   out->it_words = ITW;
   out->claim_its = (uint64_t*)calloc(c1 * (ITW ? ITW : 1), 8);
@@ -1352,6 +1401,13 @@ static int run_batch(kp_handle* h, int64_t deadline_ms, std::vector<int32_t>& st
     CK(cudaLaunchKernel(fn, dim3(n), dim3(64), args, smem, h->stream));
   }
   h->stats.kernel_launches++;
+  for (Instance* b : h->batch)
+    if (b->max_its > 0) {
+      k_truncate_claims<<<KP_TRUNC_BLOCKS, 128, 0, h->stream>>>(b->dev, b->price_tabs, b->max_its, b->trunc_key, b->trunc_val,
+                                                                 b->trunc_bits, b->d_dropped);
+      if (b->P > 0) k_mark_dropped<<<(int)((b->P + 255) / 256), 256, 0, h->stream>>>(b->dev.pod_target, b->dev.pod_error, b->d_dropped, b->P);
+      h->stats.kernel_launches += 2;
+    }
   {
     int rc = reduce_counters(h, h->batch);
     if (rc != KP_OK) return rc;
@@ -1443,6 +1499,7 @@ void kp_result_free(kp_result* r) {
   free(r->group_domain_off);
   free(r->domain_counts);
   free(r->claim_reservations);
+  free(r->claim_dropped);
   memset(r, 0, sizeof(*r));
 }
 

@@ -372,6 +372,52 @@ struct KpConsol {
 // computeConsolidation (consolidation.go:136-229) for one simulated candidate set: `unscheduled` pods could not be
 // placed (or only on uninitialized nodes), `n_new` NodeClaims were opened; claim 0's row (requirement slots, instance
 // types) is read through the c_* pointers.  One warp; `slot` selects the warp's sort scratch in q; result row `s`.
+// OrderByPrice lists of the catalog: the available offerings of every instance type, cheapest first, with the offering
+// requirement set each belongs to (host-built; shared by the consolidation decision and Results.TruncateInstanceTypes)
+struct PriceTabs {
+  const int32_t* ml_off;   // [T+1]
+  const int32_t* ml_set;
+  const double* ml_price;
+};
+// InstanceTypes.OrderByPrice (types.go:238-257) of the types in `cur` (lane w: word w of the bitmap; n_its of them) under
+// the requirements whose compatible offering sets are `okmask`: sk / sv receive (price, type) in the order Go's sort.Slice
+// leaves them, starting from the provider order (ascending type index).
+__device__ __forceinline__ void order_by_price(const PriceTabs& pt, uint64_t cur, int n_its, unsigned okmask, double* sk,
+                                               int32_t* sv, int ITW, int lane) {
+  const int cw = lane < ITW ? __popcll(cur) : 0;
+  int pre = cw;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(FULL, pre, o);
+    if (lane >= o) pre += t;
+  }
+  int at = pre - cw;
+  for (uint64_t bits = lane < ITW ? cur : 0ull; bits;) {
+    const int b = __ffsll((long long)bits) - 1;
+    bits &= bits - 1;
+    const int t = lane * 64 + b;
+    double mp = 1.7976931348623157e308;
+    for (int e = pt.ml_off[t]; e < pt.ml_off[t + 1]; e++)
+      if ((okmask >> pt.ml_set[e]) & 1u) {
+        mp = pt.ml_price[e];
+        break;
+      }
+    sk[at] = mp;
+    sv[at] = t;
+    at++;
+  }
+  __syncwarp();
+  WarpSorterT<double> srt{sk, sv, lane};
+  srt.pdqsort(0, n_its, WarpSorterT<double>::bits_len((unsigned long long)n_its));
+}
+// the first n entries of sv as a bitmap (sb: ITW words of scratch); lane w returns word w
+__device__ __forceinline__ uint64_t first_types_bitmap(const int32_t* sv, int n, unsigned long long* sb, int ITW, int lane) {
+  if (lane < ITW) sb[lane] = 0ull;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) atomicOr(&sb[sv[i] >> 6], 1ull << (sv[i] & 63));
+  __syncwarp();
+  return lane < ITW ? sb[lane] : 0ull;
+}
+
 __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q, size_t slot, Slot* scratch,
                                               const uint8_t* c_sflags, const uint64_t* c_smask, const int64_t* c_sgte,
                                               const int64_t* c_slte, const uint64_t* c_its, int c_tmpl0, const int64_t* c_req0,
@@ -423,38 +469,11 @@ __device__ __forceinline__ void consol_decide(const KpDev& d, const KpConsol& q,
       int n_ord = 0;
       const bool need_order = n_its > 600 || (spot_path && q.spot_to_spot_enabled) || q.export_order;
       if (need_order) {
-        const int cw = lane < ITW ? __popcll(cur) : 0;
-        int pre = cw;
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(FULL, pre, o);
-          if (lane >= o) pre += t;
-        }
-        int at = pre - cw;  // provider order == ascending instance type index
-        for (uint64_t bits = lane < ITW ? cur : 0ull; bits;) {
-          const int b = __ffsll((long long)bits) - 1;
-          bits &= bits - 1;
-          const int t = lane * 64 + b;
-          double mp = 1.7976931348623157e308;
-          for (int e = q.ml_off[t]; e < q.ml_off[t + 1]; e++)
-            if ((okmask >> q.ml_set[e]) & 1u) {
-              mp = q.ml_price[e];
-              break;
-            }
-          sk[at] = mp;
-          sv[at] = t;
-          at++;
-        }
+        order_by_price(PriceTabs{q.ml_off, q.ml_set, q.ml_price}, cur, n_its, okmask, sk, sv, ITW, lane);
         n_ord = n_its;
-        __syncwarp();
-        WarpSorterT<double> srt{sk, sv, lane};
-        srt.pdqsort(0, n_ord, WarpSorterT<double>::bits_len((unsigned long long)n_ord));
         if (n_ord > 600) {
           n_ord = 600;
-          if (lane < ITW) sb[lane] = 0ull;
-          __syncwarp();
-          for (int i = lane; i < n_ord; i += 32) atomicOr(&sb[sv[i] >> 6], 1ull << (sv[i] & 63));
-          __syncwarp();
-          cur = lane < ITW ? sb[lane] : 0ull;
+          cur = first_types_bitmap(sv, n_ord, sb, ITW, lane);
           // Truncate (types.go:339-351): the 600 cheapest must still satisfy minValues, else TruncateInstanceTypes drops the
           // NodeClaim and its pods become PodErrors (scheduler.go:361-379): not all pods scheduled, nothing to do
           if (d.mv_strict && !min_values_ok(d, c_tmpl0, cur, lane)) {
@@ -836,4 +855,41 @@ __global__ void __launch_bounds__(32) k_decide_batch(const KpDev* __restrict__ d
   const int n_new = *d.n_claims;
   consol_decide(d, q, (size_t)b, scratch, d.c_sflags, d.c_smask, d.c_sgte, d.c_slte, d.c_its, n_new > 0 ? d.c_tmpl[0] : -1,
                 d.c_req, n_new > 0 ? d.c_npods[0] : 0, soff[b + 1] - soff[b], snodes + soff[b], unscheduled, n_new, b, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Results.TruncateInstanceTypes (scheduler.go:361-379; provisioner.go:380 calls it right after Solve): every new NodeClaim
+// keeps its `max_n` cheapest instance types (Truncate, types.go:339-351: OrderByPrice over the claim's requirements); a
+// truncated list that breaks the NodePool's minValues (Strict) drops the claim.  One warp per claim, grid-stride; slot w of
+// the scratch arrays belongs to warp w.
+__global__ void __launch_bounds__(128) k_truncate_claims(KpDev d, PriceTabs pt, int max_n, double* sort_key, int32_t* sort_val,
+                                                         unsigned long long* sort_bits, uint8_t* dropped) {
+  __shared__ Slot scratch[4][KP_MAXK];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, warp = blockIdx.x * 4 + wi, nw = gridDim.x * 4;
+  const int K = d.K, ITW = d.ITW, nC = *d.n_claims;
+  double* sk = sort_key + (size_t)warp * d.T;
+  int32_t* sv = sort_val + (size_t)warp * d.T;
+  unsigned long long* sb = sort_bits + (size_t)warp * ITW;
+  for (int c = warp; c < nC; c += nw) {
+    const uint64_t its = lane < ITW ? d.c_its[(size_t)c * ITW + lane] : 0ull;
+    int n_its = lane < ITW ? __popcll(its) : 0;
+    for (int o = 16; o; o >>= 1) n_its += __shfl_xor_sync(FULL, n_its, o);
+    if (n_its <= max_n) continue;  // (the order itself is not part of the result)
+    if (lane < K) scratch[wi][lane] = load_slot(d.c_sflags, d.c_smask, d.c_sgte, d.c_slte, (size_t)c * K + lane, d.has_bounds);
+    __syncwarp();
+    const unsigned okmask = offering_ok_mask(d, scratch[wi], lane);
+    order_by_price(pt, its, n_its, okmask, sk, sv, ITW, lane);
+    const uint64_t cur = first_types_bitmap(sv, max_n, sb, ITW, lane);
+    if (lane < ITW) d.c_its[(size_t)c * ITW + lane] = cur;
+    const bool ok = !d.mv_strict || min_values_ok(d, d.c_tmpl[c], cur, lane);
+    if (lane == 0 && !ok) dropped[c] = 1;
+    __syncwarp();
+  }
+}
+// ... and the pods of a dropped claim become PodErrors (scheduler.go:368-373)
+__global__ void __launch_bounds__(256) k_mark_dropped(const int32_t* pod_target, uint8_t* pod_error, const uint8_t* dropped, int64_t P) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int t = pod_target[i];
+  if (t <= -2 && dropped[-2 - t]) pod_error[i] = KP_PODERR_MINVALUES_TRUNCATED;
 }

@@ -178,6 +178,7 @@ class ProblemBuilder:
         self.max_values_per_key = 64  # width of the per-key value mask; wider keys go through value compaction
         self.preference_policy = "Respect"  # or "Ignore": scheduler.IgnorePreferences (scheduler.go:81-101)
         self.min_values_policy = "Strict"   # or "BestEffort": scheduler.MinValuesPolicy (scheduler.go:110-114)
+        self.max_instance_types = 0         # > 0: Results.TruncateInstanceTypes inside the solve (provisioner.go:380 uses 600)
         self.reserved_capacity = True       # FeatureGates.ReservedCapacity (options.go:169-177, default on)
         self.reserved_offering_strict = True  # DisableReservedCapacityFallback: what the provisioner runs (provisioner.go:347)
 
@@ -670,6 +671,7 @@ class ProblemBuilder:
         P.set("minvalue_it_vals", mv_vals)
         self.minvalue_keys = mv_keys
         P.set("min_values_best_effort", 1 if self.min_values_policy == "BestEffort" else 0)
+        P.set("max_instance_types", int(self.max_instance_types))
         P.set("claim_order_mode", self.claim_order_mode)
         enc = EncodedProblem(P, keys, {k: sorted(values[k]) for k in keys}, list(self.resources),
                              [it["name"] for it in self.its], [t["name"] for t in tmpls], [n["name"] for n in nodes],

@@ -25,6 +25,7 @@ POD_ERRORS = {
     1: "nodepool requirements filtered out all available instance types",                      # scheduler.go:511
     2: "incompatible with every nodepool (taints, requirements, topology, resources or offerings)",  # scheduler.go:683
     3: "one or more instance types with compatible reserved offerings are available, but could not be reserved",  # nodeclaim.go:277
+    4: "pod didn't schedule because NodePool couldn't meet minValues requirements",  # scheduler.go:371 (after truncation)
 }
 
 
@@ -33,8 +34,9 @@ class Scheduler:
                  state_nodes: Sequence[StateNode] = (), daemon_overhead: Optional[Dict[str, dict]] = None,
                  daemon_host_ports: Optional[Dict[str, list]] = None,
                  claim_order: str = "go", backend: Optional[Callable] = None, device: int = -1,
-                 preference_policy: str = "Respect", min_values_policy: str = "Strict"):
+                 preference_policy: str = "Respect", min_values_policy: str = "Strict", max_instance_types: int = 0):
         self.node_pools = list(node_pools)
+        self.max_instance_types = max_instance_types  # > 0: Results.TruncateInstanceTypes (provisioner.go:380: 600) in the solve
         self.instance_types = instance_types
         self.state_nodes = list(state_nodes)
         self.daemon_overhead = daemon_overhead or {}
@@ -52,6 +54,7 @@ class Scheduler:
         b.claim_order_mode = 1 if self.claim_order == "stable" else 0
         b.preference_policy = self.preference_policy
         b.min_values_policy = self.min_values_policy
+        b.max_instance_types = self.max_instance_types
         index: Dict[int, int] = {}
         for np_ in self.node_pools:
             ids = []
@@ -99,9 +102,13 @@ class Scheduler:
                 errors[id(p)] = POD_ERRORS.get(int(res["pod_error"][i]), "unschedulable")
             elif t >= 0:
                 existing.setdefault(enc.node_names[t], []).append(p)
+            elif res["claim_dropped"][-2 - t]:  # TruncateInstanceTypes dropped the NodeClaim (scheduler.go:368-373)
+                errors[id(p)] = POD_ERRORS[4]
             else:
                 by_claim.setdefault(-2 - t, []).append(p)
         for k in range(res["n_claims"]):
+            if res["claim_dropped"][k]:
+                continue
             reqs = enc.decode_requirements(res, k)  # FinalizeScheduling's reservation pins are already in
             for key, mv in enc.decode_min_values(res, k).items():
                 reqs.setdefault(key, dict(complement=True, values=[], gte=None, lte=None)).update(mv)

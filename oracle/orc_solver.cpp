@@ -684,8 +684,21 @@ static void fill_result(const Prob& P, Scheduler& s, const std::vector<int32_t>&
   out->claim_req_lte = (int64_t*)calloc(c1 * (K ? K : 1), sizeof(int64_t));
   out->claim_req_mask = (uint64_t*)calloc(c1 * (MW ? MW : 1), sizeof(uint64_t));
   out->claim_reservations = (uint64_t*)calloc(c1, sizeof(uint64_t));
+  out->claim_dropped = (uint8_t*)calloc(c1, 1);
   for (int k = 0; k < C; k++)
     for (int id : s.claim_store[k]->reserved) out->claim_reservations[k] |= 1ull << id;
+  if (p->max_instance_types > 0) {  // Results.TruncateInstanceTypes (scheduler.go:361-379)
+    Pricing pr(P);
+    for (int k = 0; k < C; k++) {
+      InflightClaim& c = *s.claim_store[k];
+      if ((int)c.its.size() <= p->max_instance_types) continue;  // (the order itself is not part of the result)
+      pr.order_by_price(c.its, c.reqs);
+      c.its.resize(p->max_instance_types);
+      if (!p->min_values_best_effort && c.reqs.has_min_values() && !s.satisfies_min_values(c.its, c.reqs)) out->claim_dropped[k] = 1;
+    }
+    for (int64_t i = 0; i < n; i++)
+      if (out->pod_target[i] <= -2 && out->claim_dropped[-2 - out->pod_target[i]]) out->pod_error[i] = KP_PODERR_MINVALUES_TRUNCATED;
+  }
   for (size_t pos = 0; pos < s.new_claims.size(); pos++) out->claim_rank[s.new_claims[pos]->created] = (int32_t)pos;
   for (int k = 0; k < C; k++) {
     InflightClaim& c = *s.claim_store[k];
@@ -780,6 +793,7 @@ void orc_result_free(kp_result* r) {
   free(r->group_domain_off);
   free(r->domain_counts);
   free(r->claim_reservations);
+  free(r->claim_dropped);
   memset(r, 0, sizeof(*r));
 }
 

@@ -21,7 +21,7 @@ def digest(res: dict) -> str:
     h = hashlib.sha256()
     for k in _abi.PARITY_KEYS:
         v = res[k]
-        if k == "claim_reservations" and not np.any(v):
+        if k in ("claim_reservations", "claim_dropped") and not np.any(v):
             continue  # added in ABI 3: a solution without reservations keeps its earlier digest
         if isinstance(v, np.ndarray):
             h.update(k.encode() + str(v.dtype).encode() + str(v.shape).encode() + np.ascontiguousarray(v).tobytes())
