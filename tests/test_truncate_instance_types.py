@@ -72,18 +72,19 @@ def test_the_cheapest_types_survive(which):  # types.go:238-257,339-351
 
 
 @pytest.mark.gpu
-def test_truncate_600_of_1000_types_parity():
-    """C3's shape on the 1 000-type AWS-KWOK catalog: every NodeClaim starts with hundreds of types; 600 (and 60) cheapest kept."""
+def test_truncate_on_the_1000_type_catalog_parity():
+    """C3's shape on the 1 000-type AWS-KWOK catalog: the NodeClaims end with 240 - 430 types; the 600 (nothing to cut), 300 and 60
+    cheapest kept."""
     from karpenter_b200 import _native, workloads
     from tests.parity import assert_same
     h = _native.Handle()
     try:
-        for cap in (600, 60):
+        for cap in (600, 300, 60):
             enc = workloads.config_c3(n_apps=20, replicas=200, n_its=1000)
             enc.problem.set("max_instance_types", cap)
             gpu, orc = h.solve(enc.problem), oracle_lib.solve(enc.problem, threads=8)
             assert_same(gpu, orc, f"truncate {cap} ")
             n = np.array([sum(bin(int(w)).count("1") for w in row) for row in gpu["claim_its"]])
-            assert n.max() <= cap and (n == cap).any()
+            assert n.max() <= cap and (cap == 600 or (n == cap).any())
     finally:
         h.close()
