@@ -147,6 +147,7 @@ class Consolidation:
         b = ProblemBuilder()
         b.preference_policy = self.preference_policy
         b.min_values_policy = self.min_values_policy
+        b.max_instance_types = 600  # SimulateScheduling truncates its results (helpers.go:120, scheduling.MaxInstanceTypes)
         index, it_names = {}, []
         for np_ in self.node_pools:
             ids = []
