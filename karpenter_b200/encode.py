@@ -241,7 +241,7 @@ class ProblemBuilder:
         reqs = [canonical_requirement(r) for r in np_.requirements]
         labels = dict(np_.labels)
         labels[NODEPOOL_LABEL] = np_.name
-        labels["karpenter.kwok.sh/kwoknodeclass"] = np_.node_class
+        labels[np_.node_class_label_key()] = np_.node_class  # v1.NodeClassLabelKey(nodeClassRef group / kind)
         reqs += label_requirements(labels)
         self.templates.append(dict(
             name=np_.name, weight=np_.weight, reqset=self.reqset(reqs), taintset=self.taintset(np_.taints),

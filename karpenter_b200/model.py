@@ -318,6 +318,13 @@ class NodePool:
     taints: List[Taint] = field(default_factory=list)
     limits: Dict[str, object] = field(default_factory=dict)
     node_class: str = "default"
+    # spec.template.spec.nodeClassRef group / kind: the NodeClaim template carries the label NodeClassLabelKey(gk) =
+    # "<group>/<lower(kind)>" (pkg/apis/v1/labels.go:162-164, nodeclaimtemplate.go:60-65); the defaults are KWOK's
+    node_class_group: str = "karpenter.kwok.sh"
+    node_class_kind: str = "KWOKNodeClass"
+
+    def node_class_label_key(self) -> str:
+        return f"{self.node_class_group}/{self.node_class_kind.lower()}"
 
 
 @dataclass
