@@ -274,6 +274,12 @@ typedef struct kp_problem {
    * under the Strict policy marks the claim dropped (kp_result.claim_dropped) and its pods KP_PODERR_MINVALUES_TRUNCATED.
    * 0: claim_its is the full list and the caller truncates. */
   int32_t max_instance_types;
+  /* ---- several volume-topology alternatives for one pod (PodData.VolumeRequirements, nodeclaim.go:136-153,
+   * existingnode.go:98-113) ----
+   * The encoder registers one class per alternative -- the same pod, alternative i added to class_reqset (never to
+   * class_strict_reqset: the topology sees the pod's own requirements) -- and chains them: class_vol_next[x] is the class to try
+   * on a candidate that rejected x, -1 at the end.  pod_class names the head of a chain.  NULL: no pod has more than one. */
+  const int32_t* class_vol_next; /* [n_classes] or NULL */
 } kp_problem;
 
 /* pod_target encoding */

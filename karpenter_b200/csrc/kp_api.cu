@@ -504,8 +504,14 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
         tkinfo[x] = info;
       }
     }
+    // classes of a volume-alternative chain: the candidate loop tries the chain on every candidate, so nothing a single
+    // requirement set says about a candidate may be cached (signatures, shortcut flags), and every node is a candidate
+    std::vector<uint8_t> in_chain(std::max(t.X, 1), 0);
+    for (int x = 0; x < t.X; x++)
+      if (t.cls_vol_next[x] >= 0) in_chain[x] = in_chain[t.cls_vol_next[x]] = 1;
     for (int x = 0; x < t.X; x++) {
       int32_t* hh = &hdr[(size_t)x * KP_HDR];
+      if (in_chain[x]) tkinfo[x] = 0xff;
       hh[0] = t.cls_tolset[x];
       hh[1] = t.cls_rv[x];
       hh[2] = t.cls_match_off[x];
@@ -513,7 +519,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
       hh[4] = t.cls_rec_off[x];
       hh[5] = t.cls_rec_off[x + 1];
       hh[6] = -1;
-      if (t.cls_match_off[x + 1] == t.cls_match_off[x] && offerings_monotone && row_monotone(t.cls_rs[x])) {
+      if (!in_chain[x] && t.cls_match_off[x + 1] == t.cls_match_off[x] && offerings_monotone && row_monotone(t.cls_rs[x])) {
         auto key = std::make_pair(t.cls_rs[x], 0);  // failure bits record requirement incompatibility only
         auto it = fsigs.find(key);
         if (it == fsigs.end()) it = fsigs.emplace(key, (int)fsigs.size()).first;
@@ -523,11 +529,11 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
           tkinfo[x] |= TKI_FAST;
       }
       {
-        auto key = std::make_pair(t.cls_rs[x], t.cls_tolset[x]);
+        auto key = std::make_pair(in_chain[x] ? -1 : t.cls_rs[x], t.cls_tolset[x]);  // -1: tolerations only (k_node_cand)
         auto it = nsigs.find(key);
         if (it == nsigs.end()) {
           it = nsigs.emplace(key, (int)nsigs.size()).first;
-          nsig_rs.push_back(t.cls_rs[x]);
+          nsig_rs.push_back(key.first);
           nsig_tolset.push_back(t.cls_tolset[x]);
         }
         hh[7] = it->second;
@@ -611,6 +617,7 @@ static int upload_tables(kp_handle* h, const kp_problem* p, int cmax_hint) {
           if (l == KP_HDR + 3) c.hdr = (int32_t)(tok[x] >> 32);
           if (l == KP_HDR + 4) c.hdr = t.cls_relax[x];
           if (l == KP_HDR + 5) c.hdr = tkinfo[x];
+          if (l == KP_HDR + 10) c.hdr = t.cls_vol_next[x];
           if (l >= KP_HDR + 6 && l <= KP_HDR + 9 && p->n_hostports > 0 && p->class_hostports) {
             const uint64_t ports = p->class_hostports[x];
             uint64_t conf = 0;
@@ -1014,7 +1021,8 @@ static int prep_solve(kp_handle* h) {
   }
   if (const char* lim = getenv("KP_CS_LIMIT")) CS = std::min(CS, std::max(0, atoi(lim)) / 32 * 32);  // test knob
   in.lean = in.host.G == 0 && !in.host.has_bounds && !in.host.min_values_strict && in.host.n_rsv == 0 && d.n_hostports == 0 &&
-            !getenv("KP_NO_LEAN");
+            !in.host.has_vol_alts && !getenv("KP_NO_LEAN");
+  if (in.host.has_vol_alts) in.cohort = false;  // (the volume-alternative instantiation exists without cohorts only)
   in.CS = CS;
   in.CR = CR;
   in.smem = fixed + tb + (CS ? small_bytes(CS) : 0) + 64;
@@ -1054,6 +1062,7 @@ static int run_solve(kp_handle* h) {
   if (rc != KP_OK) return rc;
   const void* fn = in.lean ? (in.cohort ? (const void*)k_wsolve<true, true> : (const void*)k_wsolve<true, false>)
                            : (in.cohort ? (const void*)k_wsolve<false, true> : (const void*)k_wsolve<false, false>);
+  if (in.host.has_vol_alts) fn = (const void*)k_wsolve<false, false, true>;
   CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)in.smem));
   CK(cudaEventRecord(h->ev2, h->stream));
   {
@@ -1392,8 +1401,12 @@ static int run_batch(kp_handle* h, int64_t deadline_ms, std::vector<int32_t>& st
     all_lean = all_lean && b->lean;
     any_cohort = any_cohort || b->cohort;
   }
+  bool any_vol = false;
+  for (Instance* b : h->batch) any_vol = any_vol || b->host.has_vol_alts;
+  if (any_vol) any_cohort = false;
   const void* fn = all_lean ? (any_cohort ? (const void*)k_wsolve_batch<true, true> : (const void*)k_wsolve_batch<true, false>)
                             : (any_cohort ? (const void*)k_wsolve_batch<false, true> : (const void*)k_wsolve_batch<false, false>);
+  if (any_vol) fn = (const void*)k_wsolve_batch<false, false, true>;
   CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaEventRecord(h->ev2, h->stream));
   {
@@ -1576,6 +1589,10 @@ static int kp_consolidate_impl(kp_handle* h, const kp_problem* p, const kp_conso
   if (rc != KP_OK) return rc;
   HostTables& t = h->cur->host;
   KpDev& d = h->cur->dev;
+  if (t.has_vol_alts) {
+    h->err = "consolidation with pods that have several volume-topology alternatives is not supported yet";
+    return KP_ERR_UNSUPPORTED;
+  }
   if (t.has_min_values && !t.min_values_strict) {
     // BestEffort lowers minValues per NodeClaim during the simulation (nodeclaim.go:186-191); carrying those per-claim values
     // through RemoveInstanceTypeOptionsByPriceAndMinValues is not built.  Strict (the default policy) is served.

@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(256) k_node_cand(KpDev d, const int32_t* nsig_
   if (n < d.E) {
     if (row < d.n_nsig) {
       bit = tolerated(d, nsig_tolset[row], d.node_taintset[n]);
-      const int rs = nsig_rs[row];
-      for (int k = 0; k < d.K && bit; k++) {
+      const int rs = nsig_rs[row];  // -1: a class with volume-topology alternatives -- every tolerated node is a candidate
+      for (int k = 0; rs >= 0 && k < d.K && bit; k++) {
         Slot pod = rs_slot(d, rs, k);
         if (!slot_present(pod)) continue;
         Slot nd = load_slot(d.node_sflags, d.node_smask, d.node_sgte, d.node_slte, (size_t)n * d.K + k, d.has_bounds);
@@ -146,7 +146,7 @@ struct WSolveShared {
 };
 
 // warp 0: the solver; warp 1: the pod stager (see StageRing)
-template <bool LEAN, bool COHORT>
+template <bool LEAN, bool COHORT, bool VOL>
 __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WSolveShared& sh = *reinterpret_cast<WSolveShared*>(smem_raw);
@@ -248,7 +248,7 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     stager_run<COHORT>(d, I, &sh.ring, lane);
     return;
   }
-  wsolve_run<false, true, LEAN, COHORT>(d, I, sh.ring.slot[0], sh.scratch, lane, &sh.ring);
+  wsolve_run<false, true, LEAN, COHORT, VOL>(d, I, sh.ring.slot[0], sh.scratch, lane, &sh.ring);
   const int nC = I.n_claims;
   claim_rows_flush(d, I, nC, lane);
   if (!LEAN) claims_finalize(d, I.c_sflags, I.c_smask, I.c_rsv, nC, lane);
@@ -274,16 +274,16 @@ __device__ __forceinline__ void wsolve_cta(const KpDev& d_in, int CS, int CR) {
     d.counters[9] = I.fast_commits;
   }
 }
-template <bool LEAN, bool COHORT>
+template <bool LEAN, bool COHORT, bool VOL = false>
 __global__ void __launch_bounds__(64, 1) k_wsolve(const __grid_constant__ KpDev d_in, int CS, int CR) {
-  wsolve_cta<LEAN, COHORT>(d_in, CS, CR);
+  wsolve_cta<LEAN, COHORT, VOL>(d_in, CS, CR);
 }
 // Many Scheduler instances in one launch, one CTA (== one SM) each: NodePool shards of a provisioning pass, or the
 // candidate sets of a consolidation pass whose pods carry topology constraints (SimulateScheduling, helpers.go:51-142).
 // Instances share nothing but the device; plan[b] = {CS, CR} of instance b.
-template <bool LEAN, bool COHORT>
+template <bool LEAN, bool COHORT, bool VOL = false>
 __global__ void __launch_bounds__(64, 1) k_wsolve_batch(const KpDev* __restrict__ devs, const int2* __restrict__ plan) {
-  wsolve_cta<LEAN, COHORT>(devs[blockIdx.x], plan[blockIdx.x].x, plan[blockIdx.x].y);
+  wsolve_cta<LEAN, COHORT, VOL>(devs[blockIdx.x], plan[blockIdx.x].x, plan[blockIdx.x].y);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -237,8 +237,9 @@ struct PodCtx {
       int tkinfo;                  // TKI_*
       unsigned long long ports;      // host ports of the pod (interned entries, hostportusage.go:93-118)
       unsigned long long port_conf;  // every entry that Matches one of them (:50-62)
+      int vol_next;                  // class carrying the pod's next volume-topology alternative, -1: none
     };
-    int hdr[KP_HDR + 10];  // the class header, then class id, pod id, tmpl_ok (lo, hi), relax, tkinfo, ports, port_conf
+    int hdr[KP_HDR + 11];  // the class header, then class id, pod id, tmpl_ok (lo, hi), relax, tkinfo, ports, port_conf, vol_next
   };
   int64_t req[KP_MAXR];
   Slot pod_slot[KP_MAXK];
@@ -402,7 +403,7 @@ __device__ __forceinline__ ClassRegs load_class_regs(const KpDev& d, int X, int 
   return c;
 }
 __device__ __forceinline__ void store_class_regs(const KpDev& d, PodCtx& px, const ClassRegs& c, int lane) {
-  if (lane < KP_HDR + 10) px.hdr[lane] = c.hdr;
+  if (lane < KP_HDR + 11) px.hdr[lane] = c.hdr;
   if (lane < d.R) px.req[lane] = c.req;
   if (lane < d.K) {
     px.pod_slot[lane] = c.pod;

@@ -165,6 +165,15 @@ static int validate_problem(const kp_problem* p, std::string& err) {
     for (int i = p->class_filter_off[x]; i < p->class_filter_off[x + 1]; i++)
       if (!in(p->class_filter_reqsets[i], p->n_reqsets)) KP_BAD("class_filter_reqsets");
     if (p->class_relax_next && (p->class_relax_next[x] < -1 || p->class_relax_next[x] >= p->n_classes)) KP_BAD("class_relax_next");
+    if (p->class_vol_next) {
+      if (p->class_vol_next[x] < -1 || p->class_vol_next[x] >= p->n_classes) KP_BAD("class_vol_next");
+      int steps = 0;  // a chain ends, and its members are the same pod: same requests
+      for (int c = p->class_vol_next[x]; c >= 0; c = p->class_vol_next[c]) {
+        if (c >= p->n_classes || ++steps > p->n_classes) KP_BAD("class_vol_next (cyclic)");
+        for (int r = 0; r < p->n_resources; r++)
+          if (p->class_requests[(size_t)c * p->n_resources + r] != p->class_requests[(size_t)x * p->n_resources + r]) KP_BAD("class_vol_next (requests differ)");
+      }
+    }
     for (int i = p->class_tsc_off[x]; i < p->class_tsc_off[x + 1]; i++) {
       if (!in(p->tsc_key[i], p->n_keys)) KP_BAD("tsc_key");
       if (p->tsc_selector[i] < -1 || p->tsc_selector[i] >= p->n_selectors) KP_BAD("tsc_selector");
@@ -523,6 +532,12 @@ int kp_prepare(const kp_problem* p, const std::vector<uint8_t>& node_active,
   h.cls_rs.assign(p->class_reqset, p->class_reqset + X);
   h.cls_strict_rs.assign(p->class_strict_reqset, p->class_strict_reqset + X);
   h.cls_tolset.assign(p->class_tolset, p->class_tolset + X);
+  h.cls_vol_next.assign(std::max(X, 1), -1);
+  if (p->class_vol_next)
+    for (int x = 0; x < X; x++) {
+      h.cls_vol_next[x] = p->class_vol_next[x];
+      h.has_vol_alts = h.has_vol_alts || p->class_vol_next[x] >= 0;
+    }
   h.cls_relax.assign(std::max(X, 1), -1);
   if (p->class_relax_next)
     for (int x = 0; x < X; x++) h.cls_relax[x] = p->class_relax_next[x];

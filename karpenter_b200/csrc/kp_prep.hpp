@@ -47,6 +47,8 @@ struct HostTables {
   std::vector<uint32_t> tmpl_limit_present;
   std::vector<int64_t> cls_req;
   std::vector<int32_t> cls_relax;  // class after one Preferences.Relax step, -1: none
+  std::vector<int32_t> cls_vol_next;  // next volume-topology alternative of a class (kp_problem.class_vol_next), -1: none
+  bool has_vol_alts = false;
   std::vector<int32_t> g_born, g_birth, cls_lazy_off, cls_lazy;  // groups born mid-solve (KpDev::g_born)
   int n_regular = 0;                                               // groups [0, n_regular) are regular, the rest inverse
   // minValues: per template a list of (table m, need); per table m the value range [mv_val_off[m], mv_val_off[m+1]) of

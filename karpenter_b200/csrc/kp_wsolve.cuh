@@ -733,13 +733,35 @@ __device__ __noinline__ CohortOut cohort_try(const KpDev& d, WInst& I, const Pod
   return out;
 }
 
+// The pod's next volume-topology alternative (nodeclaim.go:136-153): the requirement slots of class `alt` replace the staged
+// ones -- everything else of the row is the same pod.  next_alt: the class after `alt` in the chain, -1 at its end.
+__device__ __forceinline__ void load_alt_slots(const KpDev& d, PodCtx& px, int alt, int lane) {
+  if (lane < d.K) {
+    const ClsLane c = d.cls_lane[(size_t)alt * 32 + lane];
+    Slot sl;
+    sl.f = c.pod_f;
+    sl.m = c.pod_m;
+    sl.gte = 0;
+    sl.lte = 0;
+    if (d.has_bounds) {
+      sl.gte = d.cp_g[(size_t)alt * d.K + lane];
+      sl.lte = d.cp_l[(size_t)alt * d.K + lane];
+    }
+    px.pod_slot[lane] = sl;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ int next_alt(const KpDev& d, int alt) { return d.cls_lane[(size_t)alt * 32 + KP_HDR + 10].hdr; }
+
 // One Scheduler.Solve over the instance's queue.  OVERLAY: existing-node state = shared base + private overlay.
 // STAGED: pods arrive through a StageRing filled by a second warp instead of being staged inline.
 // COHORT: runs of identical pods may commit in one step (cohort_try); instantiated separately because the mere call site
 // costs the ordinary path 7 % (register allocation of a 250-register loop) -- the host picks it when the queue has runs.
+// VOL: some pod has several volume-topology alternatives (kp_problem.class_vol_next): every candidate evaluation walks the
+// pod's chain of alternative requirement rows; compiled into an instantiation of its own for the same reason as COHORT.
 // LEAN: no topology group, Gt / Lt bound, minValues or reservation anywhere in the problem (the host decides): the code for
 // them is not even compiled into that instance, which keeps the serial chain's instruction footprint small.
-template <bool OVERLAY, bool STAGED, bool LEAN = false, bool COHORT = false>
+template <bool OVERLAY, bool STAGED, bool LEAN = false, bool COHORT = false, bool VOL = false>
 __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch, const int lane, StageRing* ring = nullptr) {
   const int K = d.K, R = d.R, ITW = d.ITW, E = d.E, EW = d.EW;
   const int P = I.P;
@@ -854,7 +876,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
     const PodCtx& px = pxw;
     const int rv = px.rv, fsig = px.fsig;
     const unsigned long long fbit = (fsig >= 0 && fsig < 64) ? 1ull << fsig : 0ull;
-    const unsigned long long rbit = rv < 64 ? 1ull << rv : 0ull;
+    const unsigned long long rbit = (rv < 64 && !(VOL && px.vol_next >= 0)) ? 1ull << rv : 0ull;
     bool found = false;
 
     // ================= addToExistingNode (scheduler.go:520-555) =================
@@ -919,6 +941,13 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
               continue;
             }
             Eval ev = eval_candidate<LEAN>(d, px, false, nb, 0, 0, 0, node, scratch, lane);
+            if (VOL && !ev.ok && px.vol_next >= 0) {  // the other volume-topology alternatives (existingnode.go:98-113)
+              for (int alt = px.vol_next; alt >= 0 && !ev.ok; alt = next_alt(d, alt)) {
+                load_alt_slots(d, pxw, alt, lane);
+                ev = eval_candidate<LEAN>(d, px, false, nb, 0, 0, 0, node, scratch, lane);
+              }
+              if (!ev.ok) load_alt_slots(d, pxw, Xc, lane);  // the next candidate starts with the first alternative again
+            }
             if (!ev.ok) continue;
             // ExistingNode.Add (existingnode.go:147-155)
             if (OVERLAY) {
@@ -1211,20 +1240,32 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
           int bj;
           claim_load<LEAN>(d, I, cc, lane, &b, &bq, &bi, &bj);
           evals++;
-          Eval ev = eval_candidate<LEAN>(d, px, true, b, bq, bi, bj, E + cc, scratch, lane);
-          // Strict minValues (nodeclaim.go:464-475): the surviving types must still span enough distinct values
-          if (!LEAN && d.mv_strict && ev.ok && !min_values_ok(d, I.c_tmpl[cc], ev.its, lane)) ev.ok = false;
-          if (abit && ev.pod_noop && lane == 0) I.amask[cc] |= abit;
+          Eval ev;
           unsigned long long held = 0, take = 0;
-          if (!LEAN && d.n_rsv && ev.ok) {  // offeringsToReserve (nodeclaim.go:197-200): a ReservedOfferingError is just "next claim" here
-            if (lane < K) scratch[lane] = ev.F;
-            __syncwarp();
-            held = I.c_rsv[cc];
-            bool rerr;
-            take = offerings_to_reserve(d, I.rsv_cap, scratch, ev.its, held, lane, &rerr);
-            __syncwarp();
-            if (rerr) ev.ok = false;
+          bool alt_loaded = false;
+          for (int alt = -1;;) {
+            ev = eval_candidate<LEAN>(d, px, true, b, bq, bi, bj, E + cc, scratch, lane);
+            // Strict minValues (nodeclaim.go:464-475): the surviving types must still span enough distinct values
+            if (!LEAN && d.mv_strict && ev.ok && !min_values_ok(d, I.c_tmpl[cc], ev.its, lane)) ev.ok = false;
+            if (abit && ev.pod_noop && lane == 0) I.amask[cc] |= abit;
+            held = 0;
+            take = 0;
+            if (!LEAN && d.n_rsv && ev.ok) {  // offeringsToReserve (nodeclaim.go:197-200): a ReservedOfferingError is just "next claim" here
+              if (lane < K) scratch[lane] = ev.F;
+              __syncwarp();
+              held = I.c_rsv[cc];
+              bool rerr;
+              take = offerings_to_reserve(d, I.rsv_cap, scratch, ev.its, held, lane, &rerr);
+              __syncwarp();
+              if (rerr) ev.ok = false;
+            }
+            if (!VOL || ev.ok) break;
+            alt = alt < 0 ? px.vol_next : next_alt(d, alt);  // the other volume-topology alternatives (nodeclaim.go:136-153)
+            if (alt < 0) break;
+            load_alt_slots(d, pxw, alt, lane);
+            alt_loaded = true;
           }
+          if (VOL && alt_loaded && !ev.ok) load_alt_slots(d, pxw, Xc, lane);  // the next candidate starts with the first alternative
           if (!ev.ok) {
             if (lane == 0) {
               ulonglong2 mk = I.cmask[cc];
@@ -1349,21 +1390,33 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
       }
       Slot b = lane < K ? rs_slot(d, d.tmpl_rs[n], lane) : slot_absent();
       const int64_t bq = lane < R ? d.tmpl_daemon[(size_t)n * R + lane] : 0;
-      Eval ev = eval_candidate<LEAN>(d, px, true, b, bq, tw, -1, E + cnew, scratch, lane);
-      if (!LEAN && d.mv_strict && ev.ok && !min_values_ok(d, n, ev.its, lane)) ev.ok = false;
+      Eval ev;
       unsigned long long take = 0;
-      if (!LEAN && d.n_rsv && ev.ok) {
-        if (lane < K) scratch[lane] = ev.F;
-        __syncwarp();
-        bool rerr;
-        take = offerings_to_reserve(d, I.rsv_cap, scratch, ev.its, 0ull, lane, &rerr);
-        __syncwarp();
-        if (rerr) {
-          // compatible reserved capacity of this NodePool is taken: no NodePool of lower weight may take the pod
-          // (scheduler.go:632-646), and the pod is not relaxed either (:447-453)
-          err = KP_PODERR_RESERVED;
-          break;
+      bool rerr = false, alt_loaded = false;
+      for (int alt = -1;;) {
+        ev = eval_candidate<LEAN>(d, px, true, b, bq, tw, -1, E + cnew, scratch, lane);
+        if (!LEAN && d.mv_strict && ev.ok && !min_values_ok(d, n, ev.its, lane)) ev.ok = false;
+        take = 0;
+        rerr = false;
+        if (!LEAN && d.n_rsv && ev.ok) {
+          if (lane < K) scratch[lane] = ev.F;
+          __syncwarp();
+          take = offerings_to_reserve(d, I.rsv_cap, scratch, ev.its, 0ull, lane, &rerr);
+          __syncwarp();
+          if (rerr) ev.ok = false;
         }
+        if (!VOL || ev.ok) break;
+        alt = alt < 0 ? px.vol_next : next_alt(d, alt);  // the other volume-topology alternatives: the last one's error counts
+        if (alt < 0) break;
+        load_alt_slots(d, pxw, alt, lane);
+        alt_loaded = true;
+      }
+      if (VOL && alt_loaded && !ev.ok) load_alt_slots(d, pxw, Xc, lane);
+      if (rerr) {
+        // compatible reserved capacity of this NodePool is taken: no NodePool of lower weight may take the pod
+        // (scheduler.go:632-646), and the pod is not relaxed either (:447-453)
+        err = KP_PODERR_RESERVED;
+        break;
       }
       if (!ev.ok) continue;
       // NewNodeClaim + Add

@@ -271,13 +271,14 @@ class ProblemBuilder:
                 tscs.append((kind, t.topology_key, t.label_selector, ns, 0, -1, False, False, soft))
         strict_reqs = pod_requirements(pod, strict=True)
         reqs = pod_requirements(pod, strict=not respect)  # scheduler.go:471-491 updateCachedPodData
+        vol_rest = ()
         if pod.volume_requirements:
             # CanAdd tries the volume alternatives in turn, each added to the NODE's requirements behind the pod's own and
-            # kept out of the strict requirements the topology sees (nodeclaim.go:136-176, existingnode.go:98-140).  With
-            # one alternative that is: requirements = pod AND volume, strict requirements = pod.
-            if len(pod.volume_requirements) > 1:
-                raise ValueError("several volume topology alternatives for one pod are not supported yet")
+            # kept out of the strict requirements the topology sees (nodeclaim.go:136-176, existingnode.go:98-140): this
+            # class carries the first one (requirements = pod AND volume, strict requirements = pod), class_vol_next chains
+            # to the class of the same pod with the remaining alternatives
             reqs = reqs + [canonical_requirement(r) for r in pod.volume_requirements[0]]
+            vol_rest = tuple(tuple(canonical_requirement(r) for r in alt) for alt in pod.volume_requirements[1:])
         # everything a scheduling decision or a later relaxation step can depend on
         eff = effective_requests(pod)  # resources.Ceiling: init containers, sidecars, overhead, pod-level resources
         key = (tuple(sorted(eff.items())), tuple(reqs), tuple(strict_reqs),
@@ -285,7 +286,7 @@ class ProblemBuilder:
                tuple(tuple(a) for a in pod_filter_requirements(pod)), tuple(sorted(host_port_key(h) for h in pod.host_ports)),
                tuple(pod.node_affinity_preferred) if respect else (),
                tuple((w.weight for w in pod.pod_affinity_preferred)) if respect else (),
-               tuple((w.weight for w in pod.pod_anti_affinity_preferred)) if respect else ())
+               tuple((w.weight for w in pod.pod_anti_affinity_preferred)) if respect else (), vol_rest)
         n_before = len(self.classes.rows)
         cid = self.classes.get(key)
         if cid == n_before:
@@ -305,7 +306,10 @@ class ProblemBuilder:
                                         nsset=self.nssets.get(tuple(ns)), max_skew=skew, min_domains=mind,
                                         taint_policy=int(tp), affinity_policy=int(ap), preferred=int(soft)))
                 self.extra_keys.add(NORMALIZED_LABELS.get(tkey, tkey))
+            row["vol_next"] = -1
             self.class_rows.append(row)
+            if vol_rest:
+                row["vol_next"] = self.pod_class(replace(pod, volume_requirements=list(pod.volume_requirements[1:])))
         return cid
 
     def add_pod(self, pod: Pod) -> int:
@@ -611,6 +615,8 @@ class ProblemBuilder:
         P.set("class_relax_next", relax_next)
         if getattr(self, "hostports", None):
             P.set("class_hostports", np.array([c["ports"] for c in self.class_rows], np.uint64))
+        if any(c.get("vol_next", -1) >= 0 for c in self.class_rows):
+            P.set("class_vol_next", np.array([c.get("vol_next", -1) for c in self.class_rows], np.int32))
         for k, arr in cols.items():
             P.set("tsc_" + k, arr)
         # pods

@@ -237,12 +237,21 @@ struct Scheduler {
   Res class_requests(int cls) const { return P.res_row(p->class_requests, cls, P.all_mask()); }
 
   // existingnode.go:70-143
+  // volume-topology alternatives (nodeclaim.go:136-153, existingnode.go:98-113): class_vol_next chains the classes that carry
+  // the same pod with the next alternative folded into class_reqset; a candidate that rejects one is offered the next
+  int vol_next(int x) const { return p->class_vol_next ? p->class_vol_next[x] : -1; }
   bool existing_can_add(ExistingNode& n, int cls, Requirements* out) {
     ctr.existing++;
+    for (int x = cls; x >= 0; x = vol_next(x))
+      if (existing_can_add_alt(n, cls, x, out)) return true;
+    return false;
+  }
+  // cls: the pod's class (tolerations, ports, requests, topology); x: the class whose requirement set is tried
+  bool existing_can_add_alt(ExistingNode& n, int cls, int x, Requirements* out) {
     if (!P.tolerates(n.taintset, p->class_tolset[cls])) return false;
     if (ports_conflict(n.ports, cls)) return false;  // existingnode.go:76-82
     if (!fits(P.R, class_requests(cls), n.remaining)) return false;
-    const Requirements& pod_reqs = P.reqsets[p->class_reqset[cls]];
+    const Requirements& pod_reqs = P.reqsets[p->class_reqset[x]];
     if (!compatible(P, P, n.reqs, pod_reqs, false)) return false;
     Requirements node_reqs = n.reqs;
     node_reqs.add_all(P, pod_reqs);
@@ -258,11 +267,17 @@ struct Scheduler {
   // nodeclaim.go:114-202
   bool claim_can_add(InflightClaim& c, int cls, Requirements* out_reqs, std::vector<int>* out_its,
                      std::vector<int>* out_rsv = nullptr, bool* rsv_error = nullptr) {
+    for (int x = cls; x >= 0; x = vol_next(x))  // the LAST alternative's error is the one CanAdd returns (nodeclaim.go:145-152)
+      if (claim_can_add_alt(c, cls, x, out_reqs, out_its, out_rsv, rsv_error)) return true;
+    return false;
+  }
+  bool claim_can_add_alt(InflightClaim& c, int cls, int x, Requirements* out_reqs, std::vector<int>* out_its,
+                         std::vector<int>* out_rsv, bool* rsv_error) {
     if (rsv_error) *rsv_error = false;
     int taintset = p->tmpl_taintset[c.tmpl];
     if (!P.tolerates(taintset, p->class_tolset[cls])) return false;
     if (ports_conflict(c.ports, cls)) return false;  // nodeclaim.go:120-124
-    const Requirements& pod_reqs = P.reqsets[p->class_reqset[cls]];
+    const Requirements& pod_reqs = P.reqsets[p->class_reqset[x]];
     Requirements reqs = c.reqs;
     if (!compatible(P, P, reqs, pod_reqs, true)) return false;
     reqs.add_all(P, pod_reqs);

@@ -272,6 +272,65 @@ def test_fuzz_replica_cohorts_parity_gpu():
     assert not bad, bad[:10]
 
 
+def encode_volumes(seed):
+    """the soft problems with 2 - 3 volume-topology alternatives (zones, sometimes with a capacity type) on a third of the pods"""
+    import random
+    from karpenter_b200.model import CAPACITY_TYPE_LABEL, ZONE_LABEL, NodeSelectorRequirement
+    pools, per_pool, nodes, pl = fuzz.problem(seed, n_pods=[5, 20, 60, 150][seed % 4])
+    fuzz.soften(seed, pools, pl)
+    rng = random.Random(53_000 + seed)
+    shapes = {}
+    for p in pl:
+        key = id(p.requests), tuple(sorted(p.labels.items())), p.namespace
+        if key not in shapes:
+            alts = []
+            if rng.random() < 0.35:
+                for _ in range(rng.randint(2, 3)):
+                    alt = [NodeSelectorRequirement(ZONE_LABEL, "In", tuple(rng.sample(fuzz.ZONES + ["no-such-zone"], rng.randint(1, 2))))]
+                    if rng.random() < 0.3:
+                        alt.append(NodeSelectorRequirement(CAPACITY_TYPE_LABEL, "In", (rng.choice(fuzz.CTS),)))
+                    alts.append(alt)
+            shapes[key] = alts
+        if shapes[key]:
+            p.volume_requirements = shapes[key]
+    return Scheduler(pools, per_pool, nodes, claim_order="go" if seed % 3 else "stable").encode(pl)
+
+
+def test_volume_generator_uses_later_alternatives():
+    stats = collections.Counter()
+    for seed in range(120):
+        enc = encode_volumes(seed)
+        nxt = enc.problem.get("class_vol_next")
+        if nxt is None:
+            continue
+        stats["chains"] += 1
+        res = oracle_lib.solve(enc.problem)
+        one = enc.problem.get("class_vol_next").copy()
+        enc.problem.set("class_vol_next", np.full_like(one, -1))   # only the first alternative
+        first_only = oracle_lib.solve(enc.problem)
+        enc.problem.set("class_vol_next", one)
+        stats["later_alternative_matters"] += int(not np.array_equal(res["pod_target"], first_only["pod_target"]))
+    assert stats["chains"] >= 60 and stats["later_alternative_matters"] >= 15, stats
+
+
+@pytest.mark.gpu
+def test_fuzz_volume_alternatives_parity_gpu():
+    h = _native.Handle()
+    bad = []
+    try:
+        for seed in range(CAP or 250):
+            enc = encode_volumes(seed)
+            orc = oracle_lib.solve(enc.problem)
+            gpu = h.solve(enc.problem)
+            try:
+                assert_same(gpu, orc, f"seed {seed} ")
+            except AssertionError as e:
+                bad.append((seed, str(e)[:200]))
+    finally:
+        h.close()
+    assert not bad, bad[:10]
+
+
 def consolidation_case(seed):
     """A random small cluster (topology-free pods bound to nodes) and random candidate sets of 1-3 nodes."""
     import random
