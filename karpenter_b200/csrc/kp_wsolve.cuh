@@ -233,9 +233,10 @@ struct ScanCtx {
 // U sub-chunks of 32 positions per step: their loads are independent, so a step costs one memory latency, not U.
 template <int U, bool LEAN = false>
 __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, const int32_t* ord, int nC, int from,
-                                              ScanCtx& sc, int lane, int E, int* cc_out) {
+                                              ScanCtx& sc, int lane, int E, int* cc_out, int limit = 0x7fffffff) {
   const ulonglong2* cm = I.cmask;
-  for (int base = from & ~31; base < nC; base += 32 * U) {
+  if (limit > nC) limit = nC;  // positions at and above `limit` are not looked at: the caller continues there
+  for (int base = from & ~31; base < limit; base += 32 * U) {
     bool pass[U], fclear[U], rclear[U];
     int c[U];
 #pragma unroll
@@ -243,7 +244,7 @@ __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, co
       const int pos = base + u * 32 + lane;
       c[u] = -1;
       pass[u] = fclear[u] = rclear[u] = false;
-      if (pos < nC && pos >= from) {
+      if (pos < limit && pos >= from) {
         c[u] = ord[pos];
         const ulonglong2 mk = cm[c[u]];
         fclear[u] = !(mk.x & sc.fbit);
@@ -1168,9 +1169,16 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         if ((sc.hc[i].y & 0xff) == KP_TOPO_AFFINITY) coh_ok = false;  // "is any domain populated" changes with every record
       while (scanned && !found) {
         int cc;
-        // classes with hostname checks read one counter per candidate from HBM/L2: scan 128 positions per step there
-        const int cpos = sc.hend > sc.hoff ? next_candidate<4, LEAN>(d, I, ord, nC, from, sc, lane, E, &cc)
-                                           : next_candidate<1, LEAN>(d, I, ord, nC, from, sc, lane, E, &cc);
+        // classes with hostname checks read presence words / counters per candidate: 128 positions per step there (their
+        // loads overlap) -- after ONE 32-wide step: most pods find their claim among the first positions of the scan
+        int cpos;
+        if (sc.hend > sc.hoff) {
+          const int lim = (from & ~31) + 32;
+          cpos = next_candidate<1, LEAN>(d, I, ord, nC, from, sc, lane, E, &cc, lim);
+          if (cpos < 0 && lim < nC) cpos = next_candidate<4, LEAN>(d, I, ord, nC, lim, sc, lane, E, &cc);
+        } else {
+          cpos = next_candidate<1, LEAN>(d, I, ord, nC, from, sc, lane, E, &cc);
+        }
         if (cpos < 0) break;
         from = cpos + 1;
         {
