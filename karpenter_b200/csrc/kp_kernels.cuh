@@ -610,10 +610,7 @@ __device__ __forceinline__ uint64_t domain_mask(const KpDev& d, const PodCtx& px
       long long mn = 2147483647LL;
       if ((sup >> lane) & 1ull) mn = c0;
       if (((sup >> (lane + 32)) & 1ull) && c1 < mn) mn = c1;
-      for (int o = 16; o; o >>= 1) {
-        const long long other = __shfl_xor_sync(FULL, mn, o);
-        if (other < mn) mn = other;
-      }
+      mn = __reduce_min_sync(FULL, (int)mn);  // (counts and the sentinel fit an int: one redux instead of five shuffle rounds)
       if (G.min_domains >= 0 && __popcll(sup) < G.min_domains) mn = 0;
       const long long add = self ? 1 : 0;
       const bool ok0 = ((reg >> lane) & 1ull) && c0 + add - mn <= (long long)G.max_skew;

@@ -236,7 +236,7 @@ __device__ __forceinline__ int next_candidate(const KpDev& d, const WInst& I, co
                                               ScanCtx& sc, int lane, int E, int* cc_out, int limit = 0x7fffffff) {
   const ulonglong2* cm = I.cmask;
   if (limit > nC) limit = nC;  // positions at and above `limit` are not looked at: the caller continues there
-  for (int base = from & ~31; base < limit; base += 32 * U) {
+  for (int base = from; base < limit; base += 32 * U) {  // (unaligned: a step always looks at 32 * U fresh positions)
     bool pass[U], fclear[U], rclear[U];
     int c[U];
 #pragma unroll
@@ -1173,7 +1173,7 @@ __device__ void wsolve_run(const KpDev& d, WInst& I, PodCtx& ctx, Slot* scratch,
         // loads overlap) -- after ONE 32-wide step: most pods find their claim among the first positions of the scan
         int cpos;
         if (sc.hend > sc.hoff) {
-          const int lim = (from & ~31) + 32;
+          const int lim = from + 32;
           cpos = next_candidate<1, LEAN>(d, I, ord, nC, from, sc, lane, E, &cc, lim);
           if (cpos < 0 && lim < nC) cpos = next_candidate<4, LEAN>(d, I, ord, nC, lim, sc, lane, E, &cc);
         } else {
