@@ -1,0 +1,118 @@
+"""oracle/orc_cached.cpp -- the CUDA solver's algorithm (failure bits, accepted-signature fast path, threshold bitmaps, scan
+bounds, incremental Go sort) as scalar C++ on one host core, used by bench.py's cpu_baseline legs -- against the oracle:
+same targets, errors, NodeClaims, order, requests and instance-type lists on the topology-free shapes it serves."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from karpenter_b200 import _abi, workloads
+from tests import oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = ["pod_target", "pod_error", "n_claims", "claim_template", "claim_npods", "claim_rank", "claim_requests", "claim_its"]
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ROOT, "oracle", "liborc_cached.so")
+        if not os.path.exists(path):
+            oracle_lib.build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_cached_solve.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        _LIB.orc_cached_free.argtypes = [C.c_void_p]
+    return _LIB
+
+
+def cached_solve(problem):
+    """-> (result dict with KEYS, solve ms, prep ms), or None when the shape is outside the lean instantiation"""
+    r = _abi.kp_result()
+    prep = C.c_double()
+    rc = lib().orc_cached_solve(problem.ref(), C.byref(r), C.byref(prep))
+    if rc == 5:
+        return None
+    assert rc == 0, rc
+    Cn, R, W = r.n_claims, problem.n_resources, r.it_words
+    out = {"pod_target": _abi.view(r.pod_target, r.n_pods, np.int32).copy(), "pod_error": _abi.view(r.pod_error, r.n_pods, np.uint8).copy(),
+           "n_claims": Cn, "claim_template": _abi.view(r.claim_template, Cn, np.int32).copy(),
+           "claim_npods": _abi.view(r.claim_npods, Cn, np.int32).copy(), "claim_rank": _abi.view(r.claim_rank, Cn, np.int32).copy(),
+           "claim_requests": _abi.view(r.claim_requests, Cn * R, np.int64).reshape(Cn, R).copy(),
+           "claim_its": _abi.view(r.claim_its, Cn * W, np.uint64).reshape(Cn, W).copy()}
+    ms = r.solve_ms
+    lib().orc_cached_free(C.byref(r))
+    return out, ms, prep.value
+
+
+def same(a, b, what):
+    for k in KEYS:
+        if isinstance(a[k], np.ndarray):
+            assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), f"{what}{k}"
+        else:
+            assert a[k] == b[k], f"{what}{k}"
+
+
+@pytest.mark.parametrize("n_pods,order", [(13, 0), (300, 0), (3000, 0), (3000, 1), (30_000, 0)])
+def test_c2_shapes_match_the_oracle(n_pods, order):
+    enc = workloads.config_c2(n_pods=n_pods, n_its=500)
+    enc.problem.set("claim_order_mode", order)
+    got = cached_solve(enc.problem)
+    assert got is not None
+    same(got[0], oracle_lib.solve(enc.problem, threads=8), f"C2[{n_pods}] ")
+
+
+@pytest.mark.parametrize("n_pods", [60, 1000])
+def test_c1_shapes_match_the_oracle(n_pods):
+    enc = workloads.config_c1(n_pods=n_pods)
+    got = cached_solve(enc.problem)
+    assert got is not None
+    same(got[0], oracle_lib.solve(enc.problem), f"C1[{n_pods}] ")
+
+
+def test_topology_free_fuzz_problems_match_the_oracle():
+    """the fuzz generator's problems that happen to be in scope (no topology, bounds, nodes, limits, preferences)"""
+    from tests.test_fuzz_parity import encode
+    ran = 0
+    for seed in range(400):
+        enc = encode(seed)
+        got = cached_solve(enc.problem)
+        if got is None:
+            continue
+        try:
+            ref = oracle_lib.solve(enc.problem)
+        except RuntimeError:
+            continue
+        same(got[0], ref, f"seed {seed} ")
+        ran += 1
+    assert ran >= 3, ran
+
+
+def test_stripped_fuzz_problems_match_the_oracle():
+    """the fuzz generator's problems made topology-free: several NodePools with weights and taints, selectors, In / NotIn /
+    Exists / DoesNotExist node affinity, tolerations, up to 400 pods -- and both claim-order modes"""
+    from karpenter_b200.scheduler import Scheduler
+    from tests import fuzz
+    ran = 0
+    for seed in range(300):
+        pools, per_pool, _, pl = fuzz.problem(seed, with_nodes=False)
+        for p in pl:
+            p.topology_spread_constraints, p.pod_affinity, p.pod_anti_affinity = [], [], []
+        for np_ in pools:
+            np_.limits = {}
+        enc = Scheduler(pools, per_pool, [], claim_order="go" if seed % 3 else "stable").encode(pl)
+        got = cached_solve(enc.problem)
+        if got is None:
+            continue
+        try:
+            ref = oracle_lib.solve(enc.problem)
+        except RuntimeError:
+            continue
+        same(got[0], ref, f"seed {seed} ")
+        ran += 1
+    assert ran >= 80, ran
+
+
+def test_out_of_scope_shapes_are_refused():
+    assert cached_solve(workloads.config_c3(n_apps=3, replicas=5, n_its=50).problem) is None
