@@ -198,6 +198,27 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def cached_cpu_baseline(oracle_lib, problem, n_pods, gpu_res):
+    """oracle/orc_cached.cpp: the solver's OWN algorithm (failure bits, accepted-signature fast path, threshold bitmaps, scan
+    bounds, incremental Go sort) as scalar C++ on ONE host core, over the same prepared tables -- what separates the algorithm's
+    share of a speed-up from the hardware's.  Topology-free shapes only (the lean instantiation's); never fatal for the bench."""
+    try:
+        best = None
+        for _ in range(3):
+            got = oracle_lib.cached_solve(problem)
+            if got is None:
+                return {"unavailable": "shape outside the lean instantiation"}
+            res, ms, prep = got
+            best = ms if best is None else min(best, ms)
+        same = all(np.array_equal(np.asarray(res[k]), np.asarray(gpu_res[k])) for k in oracle_lib.CACHED_KEYS)
+        return {"value": n_pods / (best / 1000), "unit": "pods/s", "ms": best, "host_prep_ms": prep, "cores": 1, "kind": "cached port",
+                "identical_to_the_gpu_result": bool(same),
+                "sample": "the full workload, the CUDA solver's algorithm as scalar C++ on one host core, tables prepared before the "
+                          "clock starts (best of 3)"}
+    except Exception as e:  # noqa: BLE001 -- a baseline leg must not take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def time_encoder(n_pods_headline, e2e_ms):
     """The Python mirror's encoder on real Pod objects (the headline feeds class ids, as the cgo shim would after interning):
     200 apps x 1 000 replicas of C3's shape as `Pod` objects carrying their owner's template key, Scheduler.encode timed."""
@@ -512,6 +533,7 @@ def main():
                 dt = time.perf_counter() - t0
                 c2["cpu_baseline"] = {"value": C2_PODS / dt, "unit": "pods/s", "cores": threads, "kind": "port",
                                       "sample": f"the full workload ({C2_PODS} pods), one Solve, {threads} thread(s)"}
+                c2["cpu_baseline_cached"] = cached_cpu_baseline(oracle_lib, enc2.problem, C2_PODS, m2["res"])
             line["c2"] = c2
         # ---------------- secondary: a Deployment-shaped queue (cohort commits) and the Python encoder on Pod objects
         if not args.no_deployments:

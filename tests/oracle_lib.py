@@ -59,3 +59,41 @@ def feasibility(problem) -> np.ndarray:
     rc = lib().orc_feasibility(problem.ref(), out.ctypes.data, C.byref(w))
     assert rc == 0 and w.value == itw
     return out
+
+
+# ---- oracle/orc_cached.cpp: the CUDA solver's algorithm on one host core (bench.py cpu_baseline legs, tests) -------------
+_CACHED = None
+CACHED_KEYS = ["pod_target", "pod_error", "n_claims", "claim_template", "claim_npods", "claim_rank", "claim_requests", "claim_its"]
+
+
+def cached_lib():
+    global _CACHED
+    if _CACHED is None:
+        path = os.path.join(ROOT, "oracle", "liborc_cached.so")
+        if not os.path.exists(path):
+            build()
+        _CACHED = C.CDLL(path)
+        _CACHED.orc_cached_solve.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        _CACHED.orc_cached_free.argtypes = [C.c_void_p]
+    return _CACHED
+
+
+def cached_solve(problem):
+    """-> (result dict with CACHED_KEYS, solve ms on one core with the tables prepared, prep ms), or None when the shape is
+    outside what orc_cached.cpp serves (KP_ERR_UNSUPPORTED)"""
+    r = _abi.kp_result()
+    prep = C.c_double()
+    rc = cached_lib().orc_cached_solve(problem.ref(), C.byref(r), C.byref(prep))
+    if rc == 5:
+        return None
+    if rc != 0:
+        raise RuntimeError(f"orc_cached_solve failed: {rc}")
+    Cn, R, W = r.n_claims, problem.n_resources, r.it_words
+    out = {"pod_target": _abi.view(r.pod_target, r.n_pods, np.int32).copy(), "pod_error": _abi.view(r.pod_error, r.n_pods, np.uint8).copy(),
+           "n_claims": Cn, "claim_template": _abi.view(r.claim_template, Cn, np.int32).copy(),
+           "claim_npods": _abi.view(r.claim_npods, Cn, np.int32).copy(), "claim_rank": _abi.view(r.claim_rank, Cn, np.int32).copy(),
+           "claim_requests": _abi.view(r.claim_requests, Cn * R, np.int64).reshape(Cn, R).copy(),
+           "claim_its": _abi.view(r.claim_its, Cn * W, np.uint64).reshape(Cn, W).copy()}
+    ms = r.solve_ms
+    cached_lib().orc_cached_free(C.byref(r))
+    return out, ms, prep.value

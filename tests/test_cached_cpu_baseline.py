@@ -1,49 +1,14 @@
 """oracle/orc_cached.cpp -- the CUDA solver's algorithm (failure bits, accepted-signature fast path, threshold bitmaps, scan
 bounds, incremental Go sort) as scalar C++ on one host core, used by bench.py's cpu_baseline legs -- against the oracle:
 same targets, errors, NodeClaims, order, requests and instance-type lists on the topology-free shapes it serves."""
-import ctypes as C
-import os
-
 import numpy as np
 import pytest
 
 from karpenter_b200 import _abi, workloads
 from tests import oracle_lib
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KEYS = ["pod_target", "pod_error", "n_claims", "claim_template", "claim_npods", "claim_rank", "claim_requests", "claim_its"]
-_LIB = None
-
-
-def lib():
-    global _LIB
-    if _LIB is None:
-        path = os.path.join(ROOT, "oracle", "liborc_cached.so")
-        if not os.path.exists(path):
-            oracle_lib.build()
-        _LIB = C.CDLL(path)
-        _LIB.orc_cached_solve.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
-        _LIB.orc_cached_free.argtypes = [C.c_void_p]
-    return _LIB
-
-
-def cached_solve(problem):
-    """-> (result dict with KEYS, solve ms, prep ms), or None when the shape is outside the lean instantiation"""
-    r = _abi.kp_result()
-    prep = C.c_double()
-    rc = lib().orc_cached_solve(problem.ref(), C.byref(r), C.byref(prep))
-    if rc == 5:
-        return None
-    assert rc == 0, rc
-    Cn, R, W = r.n_claims, problem.n_resources, r.it_words
-    out = {"pod_target": _abi.view(r.pod_target, r.n_pods, np.int32).copy(), "pod_error": _abi.view(r.pod_error, r.n_pods, np.uint8).copy(),
-           "n_claims": Cn, "claim_template": _abi.view(r.claim_template, Cn, np.int32).copy(),
-           "claim_npods": _abi.view(r.claim_npods, Cn, np.int32).copy(), "claim_rank": _abi.view(r.claim_rank, Cn, np.int32).copy(),
-           "claim_requests": _abi.view(r.claim_requests, Cn * R, np.int64).reshape(Cn, R).copy(),
-           "claim_its": _abi.view(r.claim_its, Cn * W, np.uint64).reshape(Cn, W).copy()}
-    ms = r.solve_ms
-    lib().orc_cached_free(C.byref(r))
-    return out, ms, prep.value
+KEYS = oracle_lib.CACHED_KEYS
+cached_solve = oracle_lib.cached_solve
 
 
 def same(a, b, what):
