@@ -201,13 +201,13 @@ def run_reference(args, rank, world):
 def cached_cpu_baseline(oracle_lib, problem, n_pods, gpu_res):
     """oracle/orc_cached.cpp: the solver's OWN algorithm (failure bits, accepted-signature fast path, threshold bitmaps, scan
     bounds, incremental Go sort) as scalar C++ on ONE host core, over the same prepared tables -- what separates the algorithm's
-    share of a speed-up from the hardware's.  Topology-free shapes only (the lean instantiation's); never fatal for the bench."""
+    share of a speed-up from the hardware's.  New-NodeClaim provisioning shapes (C2, C3); never fatal for the bench."""
     try:
         best = None
         for _ in range(3):
             got = oracle_lib.cached_solve(problem)
             if got is None:
-                return {"unavailable": "shape outside the lean instantiation"}
+                return {"unavailable": "shape outside what oracle/orc_cached.cpp serves"}
             res, ms, prep = got
             best = ms if best is None else min(best, ms)
         same = all(np.array_equal(np.asarray(res[k]), np.asarray(gpu_res[k])) for k in oracle_lib.CACHED_KEYS)
@@ -516,6 +516,7 @@ def main():
                                     "sample": f"the first {apps} of the {args.apps} apps with all their {C3_REPLICAS} replicas "
                                               f"({apps * C3_REPLICAS} pods), one Solve, {threads} thread(s) (fastest of 1/8/16) "
                                               f"of {os.cpu_count()} host cores"}
+            line["cpu_baseline_cached"] = cached_cpu_baseline(oracle_lib, enc.problem, n_pods, res)
         # ---------------- secondary: C2
         if not args.no_c2:
             enc2 = workloads.config_c2(n_pods=C2_PODS, n_its=C2_ITS)

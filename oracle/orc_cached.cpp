@@ -8,9 +8,9 @@
 // the SAME prepared tables (kp_prep.cpp: the host half of libkarpsolve.so), as plain scalar C++: the ratio oracle : this
 // is the algorithm's share of a speed-up, the ratio this : GPU the hardware's.
 //
-// Scope: the shape the solver's LEAN instantiation serves (kp_wsolve.cuh, LEAN = true): no topology group, no Gt / Lt
-// bound, no minValues, no reservation, no host port, no volume alternative -- plus, here, no existing node, no NodePool
-// limit and no preference ladder.  Anything else: KP_ERR_UNSUPPORTED.  Results are checked against the oracle
+// Scope: provisioning into new NodeClaims -- requirement algebra without Gt / Lt bounds, taints, topology groups (spread,
+// affinity, anti-affinity, node filters and policies, the domain fast path), no minValues, no reservation, no host port, no
+// volume alternative, no existing node, no NodePool limit, no preference ladder.  Anything else: KP_ERR_UNSUPPORTED.  Results are checked against the oracle
 // (tests/test_cached_cpu_baseline.py); each step cites the device code it mirrors.
 #include <chrono>
 #include <cstdlib>
@@ -31,6 +31,7 @@ struct Claim {
   std::vector<int> j;         // threshold row per resource (fits_word)
   std::vector<uint64_t> its;  // InstanceTypeOptions
   int tmpl = 0;
+  int dom = 0xff;  // the topology-key value the claim is pinned to (c_dom), 0xff: none
 };
 
 struct Solver {
@@ -48,6 +49,14 @@ struct Solver {
   std::vector<std::vector<uint64_t>> failm, deadm, accm;  // per claim: bits over fsig / rv / asig ids
   std::vector<int> lbf, lbr;                              // scan lower bounds per fsig / rv
   long long slow_sorts = 0, fast_commits = 0;
+  // topology (kp_kernels.cuh): counters per group and domain, hostname groups counted per NodeClaim
+  int tk_key = -1, GH = 0;
+  std::vector<int32_t> dom_cnt, g_ndomains, g_nempty;
+  std::vector<uint64_t> dom_reg, dom_pop;
+  std::vector<int32_t> host_cnt;            // [claim * GH + row]
+  std::vector<uint8_t> cls_fp, cls_tk;      // per class: domain fast path allowed (TKI_FP), has a topology-key group (TKI_TK)
+  struct HostCheck { int row, type, self, max_skew, g; };
+  std::vector<std::vector<HostCheck>> cls_hc;  // the hostname groups among a class's match groups
 
   KeyInfo ki(int k) const { return KeyInfo{t.val_int.data() + (size_t)k * 64, t.val_isint[k], t.key_univ[k]}; }
   Slot rs_slot(int rs, int k) const {
@@ -115,7 +124,151 @@ struct Solver {
     }
   }
 
-  // kp_kernels.cuh eval_candidate, LEAN, is_claim: NodeClaim.CanAdd (nodeclaim.go:114-202)
+  bool tolerated(int tolset, int taintset) const {
+    if (taintset < 0 || t.n_taintsets == 0) return true;
+    return t.tol_ok[(size_t)(tolset + 1) * t.n_taintsets + taintset];
+  }
+  // kp_kernels.cuh topo_domains: TopologyGroup.Get for a non-hostname key (topologygroup.go:226-428)
+  Slot topo_domains(int g, const KpGroup& G, bool self, const Slot& pod_d, const Slot& node_d) const {
+    const KeyInfo kk = ki(G.key);
+    const int32_t* cnt = dom_cnt.data() + G.dom_off;
+    const uint64_t reg = dom_reg[g], pop = dom_pop[g];
+    const uint64_t pod_allowed = slot_allowed(kk, pod_d), node_allowed = slot_allowed(kk, node_d);
+    const bool node_in = slot_present(node_d) && slot_op(node_d) == OP_IN;
+    Slot out{SF_PRESENT, 0ull, 0, 0};
+    if (G.type == KP_TOPO_SPREAD) {
+      const uint64_t sup = reg & pod_allowed;
+      long long mn = 2147483647LL;
+      for (uint64_t m = sup; m; m &= m - 1) mn = std::min<long long>(mn, cnt[__builtin_ctzll(m)]);
+      if (G.min_domains >= 0 && __builtin_popcountll(sup) < G.min_domains) mn = 0;
+      long long best_c = 2147483647LL;
+      int best = -1;
+      for (uint64_t cand = node_in ? (node_d.m & reg) : (reg & node_allowed); cand; cand &= cand - 1) {
+        const int v = __builtin_ctzll(cand);
+        const long long c = (long long)cnt[v] + (self ? 1 : 0);
+        if (c - mn <= (long long)G.max_skew && c < best_c) {
+          best = v;
+          best_c = c;
+        }
+      }
+      if (best >= 0) out.m = 1ull << best;
+      return out;
+    }
+    if (G.type == KP_TOPO_AFFINITY) {
+      const uint64_t opts = node_in ? (node_d.m & pod_allowed & reg & pop) : (reg & pod_allowed & pop & node_allowed);
+      if (opts) {
+        out.m = opts;
+        return out;
+      }
+      const bool none_populated = (reg & pop) == 0, any_compat = (reg & pop & pod_allowed) != 0;
+      if (self && (none_populated || !any_compat)) {
+        const Slot pd = slot_present(pod_d) ? pod_d : slot_exists(), nd = slot_present(node_d) ? node_d : slot_exists();
+        const uint64_t a = reg & slot_allowed(kk, slot_intersection(kk, pd, nd));
+        if (a) out.m |= a & (~a + 1);
+        const uint64_t b = reg & pod_allowed;
+        if (b) out.m |= b & (~b + 1);
+      }
+      return out;
+    }
+    out.m = reg & ~pop & node_allowed & pod_allowed;
+    return out;
+  }
+  // kp_kernels.cuh domain_mask: the verdict of the class's topology-key groups for every claim pinned to one value
+  uint64_t domain_mask(int cls, bool* exact) const {
+    uint64_t ez = ~0ull;
+    *exact = true;
+    const Slot strict = rs_slot(t.cls_strict_rs[cls], tk_key);
+    const uint64_t univ = t.key_univ[tk_key];
+    const uint64_t pod_allowed = (strict.f & SF_PRESENT) ? (((strict.f & SF_COMPLEMENT) ? ~strict.m : strict.m) & univ) : univ;
+    for (int i = t.cls_match_off[cls]; i < t.cls_match_off[cls + 1]; i++) {
+      const int e = t.cls_match[i], g = e & 0x3fffffff;
+      const KpGroup& G = t.groups[g];
+      if (G.key != tk_key) continue;
+      const bool self = (e >> 30) & 1;
+      const uint64_t reg = dom_reg[g], pop = dom_pop[g];
+      if (G.type == KP_TOPO_SPREAD) {
+        const int32_t* cnt = dom_cnt.data() + G.dom_off;
+        const uint64_t sup = reg & pod_allowed;
+        long long mn = 2147483647LL;
+        for (uint64_t m = sup; m; m &= m - 1) mn = std::min<long long>(mn, cnt[__builtin_ctzll(m)]);
+        if (G.min_domains >= 0 && __builtin_popcountll(sup) < G.min_domains) mn = 0;
+        uint64_t okm = 0;
+        for (uint64_t m = reg; m; m &= m - 1) {
+          const int v = __builtin_ctzll(m);
+          if ((long long)cnt[v] + (self ? 1 : 0) - mn <= (long long)G.max_skew) okm |= 1ull << v;
+        }
+        ez &= okm;
+      } else if (G.type == KP_TOPO_ANTI_AFFINITY) {
+        ez &= reg & ~pop & pod_allowed;
+      } else {
+        const bool none_populated = (reg & pop) == 0, any_compat = (reg & pop & pod_allowed) != 0;
+        if (self && (none_populated || !any_compat))
+          *exact = false;
+        else
+          ez &= reg & pop & pod_allowed;
+      }
+    }
+    return ez;
+  }
+  void host_record(int row, int g, int host) {
+    int32_t& c = host_cnt[(size_t)host * GH + row];
+    if (c == 0) g_nempty[g]--;
+    c++;
+  }
+  // kp_kernels.cuh topo_record: Topology.Record (topology.go:197-220) of a placement with final requirements F
+  void topo_record(int cls, const std::vector<Slot>& F, int taintset, int host) {
+    for (int i = t.cls_rec_off[cls]; i < t.cls_rec_off[cls + 1]; i++) {
+      const int g = t.cls_rec[i];
+      const KpGroup& G = t.groups[g];
+      bool counts = true;
+      if (!G.inverse) {
+        if (G.affinity_policy == 1 && G.filter_n > 0) {
+          bool any_alt = false;
+          for (int a = 0; a < G.filter_n && !any_alt; a++) {
+            const int rs = t.filter_rs[G.filter_off + a];
+            bool bad = false;
+            for (int k = 0; k < K && !bad; k++) bad = !slot_compatible(ki(k), F[k], rs_slot(rs, k), t.key_wellknown[k], false);
+            any_alt = !bad;
+          }
+          counts = any_alt;
+        }
+        if (counts && G.taint_policy == 1) counts = tolerated(G.tolset, taintset);
+      }
+      if (!counts) continue;
+      if (G.key == t.hostname_key) {
+        host_record(G.host_row, g, host);
+      } else if (F[G.key].f & SF_PRESENT) {
+        uint64_t rec = 0;
+        if (G.inverse || G.type == KP_TOPO_ANTI_AFFINITY)
+          rec = F[G.key].m;
+        else if (!(F[G.key].f & SF_COMPLEMENT) && __builtin_popcountll(F[G.key].m) == 1)
+          rec = F[G.key].m;
+        for (uint64_t b = rec; b; b &= b - 1) dom_cnt[G.dom_off + __builtin_ctzll(b)]++;
+        dom_reg[g] |= rec;
+        dom_pop[g] |= rec;
+      }
+    }
+  }
+  // kp_kernels.cuh topo_record_fast: the claim's requirements are unchanged and its topology-key slot is In{z}
+  void topo_record_fast(int cls, int z, int taintset, int host) {
+    for (int i = t.cls_rec_off[cls]; i < t.cls_rec_off[cls + 1]; i++) {
+      const int g = t.cls_rec[i];
+      const KpGroup& G = t.groups[g];
+      if (!G.inverse && G.taint_policy == 1 && !tolerated(G.tolset, taintset)) continue;
+      if (G.key == t.hostname_key) {
+        host_record(G.host_row, g, host);
+      } else if (z >= 0) {
+        dom_cnt[G.dom_off + z]++;
+        dom_reg[g] |= 1ull << z;
+        dom_pop[g] |= 1ull << z;
+      }
+    }
+  }
+  static int pinned(const Slot& s) {
+    return (s.f == SF_PRESENT && __builtin_popcountll(s.m) == 1) ? __builtin_ctzll(s.m) : 0xff;
+  }
+
+  // kp_kernels.cuh eval_candidate, is_claim: NodeClaim.CanAdd (nodeclaim.go:114-202)
   struct Eval {
     bool ok = false, res_dead = false, changed = false, compat_fail = false, pod_noop = false;
     std::vector<Slot> F;
@@ -123,7 +276,7 @@ struct Solver {
     std::vector<int> j;
     std::vector<uint64_t> its;
   };
-  void eval(int cls, const std::vector<Slot>& base, const std::vector<int64_t>& bq, const std::vector<uint64_t>& bits,
+  void eval(int cls, int host, const std::vector<Slot>& base, const std::vector<int64_t>& bq, const std::vector<uint64_t>& bits,
             const std::vector<int>& bj, Eval& ev) const {
     ev = Eval();
     evals_++;
@@ -139,6 +292,39 @@ struct Solver {
       if (!slot_eq(ev.F[k], base[k])) ev.changed = true;
     }
     ev.pod_noop = !ev.changed;
+    // Topology.AddRequirements (topology.go:226-248), eval_candidate's topology branch
+    const int moff = t.cls_match_off[cls], mend = t.cls_match_off[cls + 1];
+    if (mend > moff) {
+      std::vector<Slot>& M = ev.F;
+      std::vector<Slot> Tt = M;
+      for (int i = moff; i < mend; i++) {
+        const int e = t.cls_match[i], g = e & 0x3fffffff;
+        const bool self = (e >> 30) & 1;
+        const KpGroup& G = t.groups[g];
+        if (G.key == t.hostname_key) {  // a NodeClaim is exactly one hostname domain
+          const int c = host < (int)(host_cnt.size() / std::max(GH, 1)) ? host_cnt[(size_t)host * GH + G.host_row] : 0;
+          bool ok;
+          if (G.type == KP_TOPO_SPREAD)
+            ok = c + (self ? 1 : 0) <= G.max_skew;
+          else if (G.type == KP_TOPO_AFFINITY)
+            ok = c > 0 || (self && (g_ndomains[g] - g_nempty[g]) == 0);
+          else
+            ok = c == 0;
+          if (!ok) return;
+        } else {
+          const Slot dm = topo_domains(g, G, self, rs_slot(t.cls_strict_rs[cls], G.key), M[G.key]);
+          if (dm.m == 0) return;  // topologyError: no eligible domain
+          Tt[G.key] = slot_add(ki(G.key), Tt[G.key], dm);
+        }
+      }
+      for (int k = 0; k < K; k++)
+        if (!slot_compatible(ki(k), M[k], Tt[k], t.key_wellknown[k], true)) return;
+      ev.changed = false;
+      for (int k = 0; k < K; k++) {
+        M[k] = slot_add(ki(k), M[k], Tt[k]);
+        if (!slot_eq(M[k], base[k])) ev.changed = true;
+      }
+    }
     ev.q = bq;
     for (int r = 0; r < R; r++) ev.q[r] += t.cls_req[(size_t)cls * R + r];
     ev.j = bj;
@@ -162,10 +348,21 @@ struct Solver {
     for (int x = 0; x < X; x++) relax = relax || t.cls_relax[x] >= 0;
     bool limits = false;
     for (int n = 0; n < N; n++) limits = limits || t.tmpl_limit_present[n] != 0;
-    if (t.G > 0 || t.has_bounds || t.has_min_values || t.n_rsv > 0 || p->n_hostports > 0 || t.has_vol_alts || p->n_nodes > 0 ||
-        relax || limits || N > 64) {
-      err = "orc_cached: only the topology-free shape of the solver's lean instantiation";
+    bool lazy = false;
+    for (int32_t b : t.g_born) lazy = lazy || b == 0;
+    if (t.has_bounds || t.has_min_values || t.n_rsv > 0 || p->n_hostports > 0 || t.has_vol_alts || p->n_nodes > 0 || relax ||
+        limits || lazy || N > 64) {
+      err = "orc_cached: shape outside what the cached CPU baseline serves";
       return KP_ERR_UNSUPPORTED;
+    }
+    GH = t.GH;
+    dom_cnt = t.dom_cnt, dom_reg = t.dom_reg, dom_pop = t.dom_pop, g_ndomains = t.g_ndomains, g_nempty = t.g_nempty;
+    {  // kp_api.cu upload_tables: the topology key = the non-hostname key most groups sit on
+      std::vector<int> per_key(std::max(K, 1), 0);
+      for (int g = 0; g < t.G; g++)
+        if (t.groups[g].key != t.hostname_key && t.groups[g].key >= 0) per_key[t.groups[g].key]++;
+      for (int k = 0; k < K; k++)
+        if (per_key[k] > 0 && (tk_key < 0 || per_key[k] > per_key[tk_key])) tk_key = k;
     }
     // kp_api.cu upload_tables: signatures and shortcut flags per class
     auto row_monotone = [&](int rs) {
@@ -179,17 +376,64 @@ struct Solver {
     };
     bool offerings_monotone = true;
     for (int dd = 0; dd < t.D; dd++) offerings_monotone = offerings_monotone && row_monotone(t.offset_rs[dd]);
+    auto slot_subset = [&](int rs_a, int rs_b, int k) {
+      const size_t ia = (size_t)rs_a * K + k, ib = (size_t)rs_b * K + k;
+      const bool ac = t.rs_flags[ia] & SF_COMPLEMENT, bc = t.rs_flags[ib] & SF_COMPLEMENT;
+      const uint64_t am = t.rs_mask[ia], bm = t.rs_mask[ib];
+      if (!ac && !bc) return (am & ~bm) == 0;
+      if (!ac && bc) return (am & bm) == 0;
+      if (ac && bc) return (bm & ~am) == 0;
+      return false;
+    };
+    auto filter_implied = [&](int x, const KpGroup& G) {
+      for (int a = 0; a < G.filter_n; a++) {
+        const int rs = t.filter_rs[G.filter_off + a];
+        bool ok = true;
+        for (int k = 0; k < K && ok; k++) {
+          if (!(t.rs_flags[(size_t)rs * K + k] & SF_PRESENT)) continue;
+          ok = (t.rs_flags[(size_t)t.cls_rs[x] * K + k] & SF_PRESENT) && slot_subset(t.cls_rs[x], rs, k);
+        }
+        if (ok) return true;
+      }
+      return false;
+    };
     fsig.assign(X, -1), asig.assign(X, 0), fast.assign(X, 0), tok.assign(X, 0);
+    cls_fp.assign(X, 0), cls_tk.assign(X, 0), cls_hc.assign(X, {});
     std::map<int, int> fs, as;
     for (int x = 0; x < X; x++) {
       auto ia = as.find(t.cls_rs[x]);
       if (ia == as.end()) ia = as.emplace(t.cls_rs[x], (int)as.size()).first;
       asig[x] = ia->second;
-      if (offerings_monotone && row_monotone(t.cls_rs[x])) {
+      {  // the domain fast path (TKI_FP): every group of the class on the hostname key or on the topology key
+        const int nm = t.cls_match_off[x + 1] - t.cls_match_off[x], nr = t.cls_rec_off[x + 1] - t.cls_rec_off[x];
+        bool fp = nm + nr > 0, has_tk = false;
+        for (int i = t.cls_match_off[x]; i < t.cls_match_off[x + 1] && fp; i++) {
+          const KpGroup& G = t.groups[t.cls_match[i] & 0x3fffffff];
+          if (G.key == tk_key)
+            has_tk = true;
+          else if (G.key != t.hostname_key)
+            fp = false;
+        }
+        for (int i = t.cls_rec_off[x]; i < t.cls_rec_off[x + 1] && fp; i++) {
+          const KpGroup& G = t.groups[t.cls_rec[i]];
+          if (G.key == tk_key)
+            has_tk = true;
+          else if (G.key != t.hostname_key)
+            fp = false;
+          if (fp && !G.inverse && G.affinity_policy == 1 && G.filter_n > 0 && !filter_implied(x, G)) fp = false;
+        }
+        cls_fp[x] = fp, cls_tk[x] = fp && has_tk;
+        for (int i = t.cls_match_off[x]; i < t.cls_match_off[x + 1]; i++) {
+          const int e = t.cls_match[i], g = e & 0x3fffffff;
+          const KpGroup& G = t.groups[g];
+          if (G.key == t.hostname_key) cls_hc[x].push_back(HostCheck{G.host_row, G.type, (e >> 30) & 1, G.max_skew, g});
+        }
+      }
+      if (t.cls_match_off[x + 1] == t.cls_match_off[x] && offerings_monotone && row_monotone(t.cls_rs[x])) {
         auto it = fs.find(t.cls_rs[x]);
         if (it == fs.end()) it = fs.emplace(t.cls_rs[x], (int)fs.size()).first;
         fsig[x] = it->second;
-        fast[x] = 1;
+        fast[x] = t.cls_rec_off[x + 1] == t.cls_rec_off[x];  // (TKI_FAST: counted by no group either)
       }
       for (int n = 0; n < N; n++) {
         const int ts = t.tmpl_taintset[n];
@@ -321,6 +565,19 @@ struct Solver {
         const int lb = std::max(lbf_, lbr_);
         const bool scanned = (tok[cls] & tmpl_all) != 0;
         int first_clear = -1, first_rclear = -1;
+        // the class's shortcuts (wsolve_run: tkinfo): topology-free fast path, or the domain fast path with its mask
+        const bool topo = t.cls_match_off[cls + 1] > t.cls_match_off[cls] || t.cls_rec_off[cls + 1] > t.cls_rec_off[cls];
+        const bool fast_ok = fast[cls];
+        bool dom_fp = topo && cls_fp[cls], use_ez = false;
+        const bool has_tk = cls_tk[cls];
+        uint64_t ez = ~0ull;
+        if (dom_fp && has_tk) {
+          bool exact;
+          ez = domain_mask(cls, &exact);
+          use_ez = exact;
+          dom_fp = exact;
+        }
+        const std::vector<HostCheck>& hcs = cls_hc[cls];
         for (int pos = lb; scanned && pos < nC && !found; pos++) {
           const int c = ord[pos];
           const bool fclear = fs < 0 || !bit(failm[c], fs), rclear = !bit(deadm[c], rv);
@@ -329,7 +586,31 @@ struct Solver {
           if (!fclear || !rclear) continue;
           Claim& cl = claims[c];
           if (!((tok[cls] >> cl.tmpl) & 1ull)) continue;
-          if (fast[cls] && bit(accm[c], asig[cls])) {
+          if (use_ez && cl.dom != 0xff && !((ez >> cl.dom) & 1ull)) continue;  // pinned to a value the pod may not use
+          {  // hostname groups: a NodeClaim is one hostname domain (next_candidate)
+            bool pass = true;
+            for (const HostCheck& hc : hcs) {
+              const int hcnt = host_cnt[(size_t)c * GH + hc.row];
+              if (hc.type == KP_TOPO_SPREAD)
+                pass = hcnt + hc.self <= hc.max_skew;
+              else if (hc.type == KP_TOPO_AFFINITY)
+                pass = hcnt > 0 || (hc.self && (g_ndomains[hc.g] - g_nempty[hc.g]) == 0);
+              else
+                pass = hcnt == 0;
+              if (!pass) break;
+            }
+            if (!pass) continue;
+          }
+          int zdom = -1;
+          bool fp = false;
+          if ((fast_ok || dom_fp) && bit(accm[c], asig[cls])) {
+            fp = true;
+            if (!fast_ok && has_tk) {
+              zdom = cl.dom;
+              fp = zdom != 0xff;
+            }
+          }
+          if (fp) {
             // the accepted-signature fast path (fp_fit): the requirements stay, only the resource test can fail
             evals_++;
             std::vector<int64_t>& q = ev.q;
@@ -345,18 +626,23 @@ struct Solver {
             cl.j.swap(ev.j);
             cl.its.swap(ev.its);
             fast_commits++;
+            if (!fast_ok) topo_record_fast(cls, zdom, t.tmpl_taintset[cl.tmpl], c);
           } else {
-            eval(cls, cl.s, cl.q, cl.its, cl.j, ev);
+            eval(cls, c, cl.s, cl.q, cl.its, cl.j, ev);
             if (ev.pod_noop) set(accm[c], asig[cls]);
             if (!ev.ok) {
               if (ev.res_dead) set(deadm[c], rv);
               if (ev.compat_fail && fs >= 0) set(failm[c], fs);
               continue;
             }
-            if (ev.changed) cl.s = ev.F;
+            if (ev.changed) {
+              cl.s = ev.F;
+              if (tk_key >= 0) cl.dom = pinned(ev.F[tk_key]);
+            }
             cl.q = ev.q;
             cl.j = ev.j;
             cl.its = ev.its;
+            if (topo) topo_record(cls, ev.F, t.tmpl_taintset[cl.tmpl], c);
           }
           cnt[c]++;
           target[li] = KP_TARGET_CLAIM(c);
@@ -380,10 +666,11 @@ struct Solver {
         std::vector<Slot> b(K);
         for (int k = 0; k < K; k++) b[k] = rs_slot(t.tmpl_rs[n], k);
         std::vector<int64_t> bq(t.tmpl_daemon.begin() + (size_t)n * R, t.tmpl_daemon.begin() + (size_t)(n + 1) * R);
-        eval(cls, b, bq, tw, std::vector<int>(R, -1), ev);
+        eval(cls, (int)claims.size(), b, bq, tw, std::vector<int>(R, -1), ev);
         if (!ev.ok) continue;
         Claim cl;
         cl.s = ev.F;
+        if (tk_key >= 0) cl.dom = pinned(ev.F[tk_key]);
         cl.q = ev.q;
         cl.j = ev.j;
         cl.its = ev.its;
@@ -396,6 +683,15 @@ struct Solver {
         deadm.emplace_back(rw, 0ull);
         accm.emplace_back(aw, 0ull);
         if (ev.pod_noop) set(accm[cnew], asig[cls]);
+        if (GH > 0) {  // Topology.Register(hostname) (nodeclaim.go:213): every hostname group learns the new, empty domain
+          host_cnt.resize((size_t)(cnew + 1) * GH, 0);
+          for (int g = 0; g < t.G; g++)
+            if (t.groups[g].key == t.hostname_key) {
+              g_ndomains[g]++;
+              g_nempty[g]++;
+            }
+        }
+        if (t.cls_rec_off[cls + 1] > t.cls_rec_off[cls]) topo_record(cls, claims[cnew].s, t.tmpl_taintset[n], cnew);
         target[li] = KP_TARGET_CLAIM(cnew);
         perr[li] = KP_PODERR_NONE;
         pert = PERT_APPEND;

@@ -79,5 +79,39 @@ def test_stripped_fuzz_problems_match_the_oracle():
     assert ran >= 80, ran
 
 
+@pytest.mark.parametrize("apps,replicas,order", [(3, 5, 0), (10, 30, 0), (40, 50, 0), (40, 50, 1), (30, 400, 0)])
+def test_c3_shapes_match_the_oracle(apps, replicas, order):
+    enc = workloads.config_c3(n_apps=apps, replicas=replicas, n_its=300)
+    enc.problem.set("claim_order_mode", order)
+    got = cached_solve(enc.problem)
+    assert got is not None
+    same(got[0], oracle_lib.solve(enc.problem, threads=4), f"C3[{apps}x{replicas}] ")
+
+
+def test_topology_fuzz_problems_match_the_oracle():
+    """the fuzz generator's problems with their topology constraints (spread with minDomains and policies, pod affinity and
+    anti-affinity on hostname / zone / capacity type, namespaces), without existing nodes and NodePool limits"""
+    from karpenter_b200.scheduler import Scheduler
+    from tests import fuzz
+    ran = topo = 0
+    for seed in range(400):
+        pools, per_pool, _, pl = fuzz.problem(seed, with_nodes=False)
+        for np_ in pools:
+            np_.limits = {}
+        enc = Scheduler(pools, per_pool, [], claim_order="go" if seed % 3 else "stable").encode(pl)
+        got = cached_solve(enc.problem)
+        if got is None:
+            continue
+        try:
+            ref = oracle_lib.solve(enc.problem)
+        except RuntimeError:
+            continue
+        same(got[0], ref, f"seed {seed} ")
+        ran += 1
+        topo += int(ref["n_groups"] > 0)
+    assert ran >= 100 and topo >= 40, (ran, topo)
+
+
 def test_out_of_scope_shapes_are_refused():
-    assert cached_solve(workloads.config_c3(n_apps=3, replicas=5, n_its=50).problem) is None
+    from tests.test_fuzz_parity import encode_reserved
+    assert cached_solve(encode_reserved(1).problem) is None
