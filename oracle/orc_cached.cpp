@@ -53,7 +53,17 @@ struct Solver {
   int tk_key = -1, GH = 0;
   std::vector<int32_t> dom_cnt, g_ndomains, g_nempty;
   std::vector<uint64_t> dom_reg, dom_pop;
-  std::vector<int32_t> host_cnt;            // [claim * GH + row]
+  std::vector<int32_t> host_cnt;            // [host * GH + row]; host = node index, or E + NodeClaim id
+  // existing nodes (ExistingNode, existingnode.go:40-66): remaining resources, label slots; candidate bitmaps per class
+  // signature (k_node_cand): nstat[nsig] = taints tolerated and labels compatible, nfit[rv] = the request vector fits
+  int E = 0;
+  std::vector<int64_t> node_rem;
+  std::vector<uint32_t> node_rem_present;
+  std::vector<Slot> node_slot;
+  std::vector<int32_t> node_npods;
+  std::vector<int> nsig;                                // per class
+  std::vector<std::vector<uint64_t>> nstat, nfit;       // bit per node
+  std::vector<uint64_t> nactive;
   std::vector<uint8_t> cls_fp, cls_tk;      // per class: domain fast path allowed (TKI_FP), has a topology-key group (TKI_TK)
   struct HostCheck { int row, type, self, max_skew, g; };
   std::vector<std::vector<HostCheck>> cls_hc;  // the hostname groups among a class's match groups
@@ -276,15 +286,17 @@ struct Solver {
     std::vector<int> j;
     std::vector<uint64_t> its;
   };
+  // is_claim = false: ExistingNode.CanAdd after the taint / Fits checks (existingnode.go:70-143): no undefined-key allowance,
+  // no instance types
   void eval(int cls, int host, const std::vector<Slot>& base, const std::vector<int64_t>& bq, const std::vector<uint64_t>& bits,
-            const std::vector<int>& bj, Eval& ev) const {
+            const std::vector<int>& bj, Eval& ev, bool is_claim = true) const {
     ev = Eval();
     evals_++;
     const int rs = t.cls_rs[cls];
     ev.F.resize(K);
     for (int k = 0; k < K; k++) {
       const Slot pod = rs_slot(rs, k);
-      if (!slot_compatible_nb(base[k], pod, t.key_wellknown[k], true)) {
+      if (!slot_compatible_nb(base[k], pod, t.key_wellknown[k], is_claim)) {
         ev.compat_fail = true;
         return;
       }
@@ -302,7 +314,7 @@ struct Solver {
         const bool self = (e >> 30) & 1;
         const KpGroup& G = t.groups[g];
         if (G.key == t.hostname_key) {  // a NodeClaim is exactly one hostname domain
-          const int c = host < (int)(host_cnt.size() / std::max(GH, 1)) ? host_cnt[(size_t)host * GH + G.host_row] : 0;
+          const int c = (size_t)(host + 1) * GH <= host_cnt.size() ? host_cnt[(size_t)host * GH + G.host_row] : 0;
           bool ok;
           if (G.type == KP_TOPO_SPREAD)
             ok = c + (self ? 1 : 0) <= G.max_skew;
@@ -318,12 +330,16 @@ struct Solver {
         }
       }
       for (int k = 0; k < K; k++)
-        if (!slot_compatible(ki(k), M[k], Tt[k], t.key_wellknown[k], true)) return;
+        if (!slot_compatible(ki(k), M[k], Tt[k], t.key_wellknown[k], is_claim)) return;
       ev.changed = false;
       for (int k = 0; k < K; k++) {
         M[k] = slot_add(ki(k), M[k], Tt[k]);
         if (!slot_eq(M[k], base[k])) ev.changed = true;
       }
+    }
+    if (!is_claim) {
+      ev.ok = true;
+      return;
     }
     ev.q = bq;
     for (int r = 0; r < R; r++) ev.q[r] += t.cls_req[(size_t)cls * R + r];
@@ -340,6 +356,7 @@ struct Solver {
 
   int prepare(std::string& err) {
     std::vector<uint8_t> active(p->n_nodes, 0);
+    for (int i = 0; i < p->n_nodes; i++) active[i] = (p->node_flags[i] & KP_NODE_SCHEDULABLE) != 0;
     std::vector<int32_t> pending(p->pod_class, p->pod_class + p->n_pods);
     int rc = kp_prepare(p, active, {}, pending, t, err);
     if (rc != KP_OK) return rc;
@@ -350,12 +367,21 @@ struct Solver {
     for (int n = 0; n < N; n++) limits = limits || t.tmpl_limit_present[n] != 0;
     bool lazy = false;
     for (int32_t b : t.g_born) lazy = lazy || b == 0;
-    if (t.has_bounds || t.has_min_values || t.n_rsv > 0 || p->n_hostports > 0 || t.has_vol_alts || p->n_nodes > 0 || relax ||
-        limits || lazy || N > 64) {
+    if (t.has_bounds || t.has_min_values || t.n_rsv > 0 || p->n_hostports > 0 || t.has_vol_alts || relax || limits || lazy || N > 64) {
       err = "orc_cached: shape outside what the cached CPU baseline serves";
       return KP_ERR_UNSUPPORTED;
     }
     GH = t.GH;
+    E = t.E;
+    node_rem = t.node_rem, node_rem_present = t.node_rem_present, node_npods.assign(std::max(E, 1), 0);
+    node_slot.resize((size_t)std::max(E, 1) * K);
+    for (size_t i = 0; i < (size_t)E * K; i++) node_slot[i] = Slot{t.node_sflags[i], t.node_smask[i], 0, 0};
+    nactive.assign((size_t)(std::max(E, 1) + 63) / 64, 0ull);
+    for (int n = 0; n < E; n++)
+      if (t.node_flags[n] & KP_NODE_SCHEDULABLE) set(nactive, n);
+    host_cnt.assign((size_t)E * GH, 0);
+    for (int r = 0; r < GH; r++)
+      for (int n = 0; n < E; n++) host_cnt[(size_t)n * GH + r] = t.host_cnt_nodes[(size_t)r * E + n];
     dom_cnt = t.dom_cnt, dom_reg = t.dom_reg, dom_pop = t.dom_pop, g_ndomains = t.g_ndomains, g_nempty = t.g_nempty;
     {  // kp_api.cu upload_tables: the topology key = the non-hostname key most groups sit on
       std::vector<int> per_key(std::max(K, 1), 0);
@@ -455,6 +481,58 @@ struct Solver {
       compat_off(S, w);
       for (int i = 0; i < ITW; i++) tmpl_its[(size_t)n * ITW + i] = w[i] & t.tmpl_its_raw[(size_t)n * ITW + i];
     }
+    // k_node_cand: candidate bitmaps of the existing nodes per (requirement set, toleration set) and per request vector
+    bool nodes_gain_keys = false;
+    for (int g = 0; g < t.G; g++) nodes_gain_keys = nodes_gain_keys || t.groups[g].key != t.hostname_key;
+    for (int x = 0; x < X; x++)
+      for (int k = 0; k < K; k++) {
+        const Slot sl = rs_slot(t.cls_rs[x], k);
+        if (slot_present(sl) && op_is_negative(slot_op(sl))) nodes_gain_keys = true;
+      }
+    const bool strict_undefined = !nodes_gain_keys;
+    nsig.assign(X, 0);
+    std::map<std::pair<int, int>, int> ns;
+    const size_t ew = nactive.size();
+    for (int x = 0; x < X; x++) {
+      auto key = std::make_pair(t.cls_rs[x], t.cls_tolset[x]);
+      auto it = ns.find(key);
+      if (it == ns.end()) {
+        it = ns.emplace(key, (int)ns.size()).first;
+        nstat.emplace_back(ew, 0ull);
+        for (int n = 0; n < E; n++) {
+          bool ok = tolerated(t.cls_tolset[x], t.node_taintset[n]);
+          for (int k = 0; k < K && ok; k++) {
+            const Slot pod = rs_slot(t.cls_rs[x], k);
+            if (!slot_present(pod)) continue;
+            const Slot nd = node_slot[(size_t)n * K + k];
+            if (!slot_present(nd)) {
+              if (strict_undefined && !op_is_negative(slot_op(pod))) ok = false;
+            } else if (!slot_has_intersection(ki(k), nd, pod) && !(op_is_negative(slot_op(pod)) && op_is_negative(slot_op(nd)))) {
+              ok = false;
+            }
+          }
+          if (ok) set(nstat.back(), n);
+        }
+      }
+      nsig[x] = it->second;
+    }
+    nfit.assign(std::max(t.n_rv, 1), std::vector<uint64_t>(ew, 0ull));
+    std::vector<uint8_t> rv_done(std::max(t.n_rv, 1), 0);
+    for (int x = 0; x < X; x++) {
+      const int rv = t.cls_rv[x];
+      if (rv_done[rv]) continue;
+      rv_done[rv] = 1;
+      for (int n = 0; n < E; n++) {
+        bool ok = true;
+        for (int r = 0; r < R; r++) {
+          const int64_t rem = node_rem[(size_t)n * R + r];
+          const bool present = (node_rem_present[n] >> r) & 1;
+          if (present && rem < 0) ok = false;
+          if (t.cls_req[(size_t)x * R + r] > (present ? rem : 0)) ok = false;
+        }
+        if (ok) set(nfit[rv], n);
+      }
+    }
     return KP_OK;
   }
 
@@ -506,6 +584,40 @@ struct Solver {
       head++;
       const int cls = p->pod_class[li], rv = t.cls_rv[cls], fs = fsig[cls];
       const int nC = (int)claims.size();
+      // ---- addToExistingNode (scheduler.go:520-555): the first node in order that passes
+      if (E > 0) {
+        bool placed = false;
+        const std::vector<uint64_t>&fitrow = nfit[rv], &strow = nstat[nsig[cls]];
+        for (size_t w = 0; w < nactive.size() && !placed; w++) {
+          for (uint64_t bits = fitrow[w] & strow[w] & nactive[w]; bits && !placed; bits &= bits - 1) {
+            const int node = (int)w * 64 + __builtin_ctzll(bits);
+            bool bad = false;  // resources.Fits(pod requests, remaining) (resources.go:150-163)
+            for (int r = 0; r < R; r++) {
+              const int64_t rem = node_rem[(size_t)node * R + r];
+              const bool present = (node_rem_present[node] >> r) & 1;
+              if (present && rem < 0) bad = true;
+              if (t.cls_req[(size_t)cls * R + r] > (present ? rem : 0)) bad = true;
+            }
+            if (bad) {
+              nfit[rv][w] &= ~(1ull << (node & 63));  // monotone: remaining resources only shrink
+              continue;
+            }
+            std::vector<Slot> nb(node_slot.begin() + (size_t)node * K, node_slot.begin() + (size_t)(node + 1) * K);
+            eval(cls, node, nb, {}, {}, {}, ev, false);
+            if (!ev.ok) continue;
+            if (ev.changed)
+              for (int k = 0; k < K; k++) node_slot[(size_t)node * K + k] = ev.F[k];
+            for (int r = 0; r < R; r++) node_rem[(size_t)node * R + r] -= t.cls_req[(size_t)cls * R + r];
+            node_rem_present[node] |= (1u << R) - 1;
+            node_npods[node]++;
+            target[li] = node;
+            perr[li] = KP_PODERR_NONE;
+            if (t.cls_rec_off[cls + 1] > t.cls_rec_off[cls]) topo_record(cls, ev.F, t.node_taintset[node], node);
+            placed = true;
+          }
+        }
+        if (placed) continue;
+      }
       // ---- sort.Slice(newNodeClaims, len(Pods) asc) (scheduler.go:504), wsolve_run's sort stage
       if (pert != PERT_NONE) {
         const int q = pert_pos;
@@ -590,7 +702,7 @@ struct Solver {
           {  // hostname groups: a NodeClaim is one hostname domain (next_candidate)
             bool pass = true;
             for (const HostCheck& hc : hcs) {
-              const int hcnt = host_cnt[(size_t)c * GH + hc.row];
+              const int hcnt = host_cnt[(size_t)(E + c) * GH + hc.row];
               if (hc.type == KP_TOPO_SPREAD)
                 pass = hcnt + hc.self <= hc.max_skew;
               else if (hc.type == KP_TOPO_AFFINITY)
@@ -626,9 +738,9 @@ struct Solver {
             cl.j.swap(ev.j);
             cl.its.swap(ev.its);
             fast_commits++;
-            if (!fast_ok) topo_record_fast(cls, zdom, t.tmpl_taintset[cl.tmpl], c);
+            if (!fast_ok) topo_record_fast(cls, zdom, t.tmpl_taintset[cl.tmpl], E + c);
           } else {
-            eval(cls, c, cl.s, cl.q, cl.its, cl.j, ev);
+            eval(cls, E + c, cl.s, cl.q, cl.its, cl.j, ev);
             if (ev.pod_noop) set(accm[c], asig[cls]);
             if (!ev.ok) {
               if (ev.res_dead) set(deadm[c], rv);
@@ -642,7 +754,7 @@ struct Solver {
             cl.q = ev.q;
             cl.j = ev.j;
             cl.its = ev.its;
-            if (topo) topo_record(cls, ev.F, t.tmpl_taintset[cl.tmpl], c);
+            if (topo) topo_record(cls, ev.F, t.tmpl_taintset[cl.tmpl], E + c);
           }
           cnt[c]++;
           target[li] = KP_TARGET_CLAIM(c);
@@ -666,7 +778,7 @@ struct Solver {
         std::vector<Slot> b(K);
         for (int k = 0; k < K; k++) b[k] = rs_slot(t.tmpl_rs[n], k);
         std::vector<int64_t> bq(t.tmpl_daemon.begin() + (size_t)n * R, t.tmpl_daemon.begin() + (size_t)(n + 1) * R);
-        eval(cls, (int)claims.size(), b, bq, tw, std::vector<int>(R, -1), ev);
+        eval(cls, E + (int)claims.size(), b, bq, tw, std::vector<int>(R, -1), ev);
         if (!ev.ok) continue;
         Claim cl;
         cl.s = ev.F;
@@ -684,14 +796,14 @@ struct Solver {
         accm.emplace_back(aw, 0ull);
         if (ev.pod_noop) set(accm[cnew], asig[cls]);
         if (GH > 0) {  // Topology.Register(hostname) (nodeclaim.go:213): every hostname group learns the new, empty domain
-          host_cnt.resize((size_t)(cnew + 1) * GH, 0);
+          host_cnt.resize((size_t)(E + cnew + 1) * GH, 0);
           for (int g = 0; g < t.G; g++)
             if (t.groups[g].key == t.hostname_key) {
               g_ndomains[g]++;
               g_nempty[g]++;
             }
         }
-        if (t.cls_rec_off[cls + 1] > t.cls_rec_off[cls]) topo_record(cls, claims[cnew].s, t.tmpl_taintset[n], cnew);
+        if (t.cls_rec_off[cls + 1] > t.cls_rec_off[cls]) topo_record(cls, claims[cnew].s, t.tmpl_taintset[n], E + cnew);
         target[li] = KP_TARGET_CLAIM(cnew);
         perr[li] = KP_PODERR_NONE;
         pert = PERT_APPEND;

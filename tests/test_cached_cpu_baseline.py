@@ -112,6 +112,37 @@ def test_topology_fuzz_problems_match_the_oracle():
     assert ran >= 100 and topo >= 40, (ran, topo)
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(n_nodes=50, n_pods=1500), dict(n_nodes=400, n_pods=2500, fill=0.9)])
+def test_existing_nodes_match_the_oracle(kw):
+    enc = workloads.config_existing(**kw)
+    got = cached_solve(enc.problem)
+    assert got is not None
+    same(got[0], oracle_lib.solve(enc.problem), f"existing nodes {kw} ")
+
+
+def test_fuzz_problems_with_existing_nodes_match_the_oracle():
+    """the fuzz generator's problems as they are (existing nodes with running pods, taints, topology), NodePool limits cleared"""
+    from karpenter_b200.scheduler import Scheduler
+    from tests import fuzz
+    ran = nodes = 0
+    for seed in range(400):
+        pools, per_pool, state_nodes, pl = fuzz.problem(seed)
+        for np_ in pools:
+            np_.limits = {}
+        enc = Scheduler(pools, per_pool, state_nodes, claim_order="go" if seed % 3 else "stable").encode(pl)
+        got = cached_solve(enc.problem)
+        if got is None:
+            continue
+        try:
+            ref = oracle_lib.solve(enc.problem)
+        except RuntimeError:
+            continue
+        same(got[0], ref, f"seed {seed} ")
+        ran += 1
+        nodes += int(bool(state_nodes) and (ref["pod_target"] >= 0).any())
+    assert ran >= 100 and nodes >= 30, (ran, nodes)
+
+
 def test_out_of_scope_shapes_are_refused():
     from tests.test_fuzz_parity import encode_reserved
     assert cached_solve(encode_reserved(1).problem) is None
