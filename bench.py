@@ -375,6 +375,21 @@ def run_consolidation(args, h, rank, world, dist, torch):
         out["cpu_baseline"] = {"value": n / dt, "unit": "subsets/s", "cores": threads, "kind": "port",
                                "sample": f"{n} of the {S} subsets, evenly spaced (independent simulations, one per thread "
                                          f"at a time), {threads} of {os.cpu_count()} host cores"}
+        try:  # the solver's own algorithm on ONE host core (oracle/orc_cached.cpp); never fatal for the bench
+            got = oracle_lib.cached_consolidate(enc.problem, _abi.ConsolInput(**consol))
+            if got is None:
+                out["cpu_baseline_cached"] = {"unavailable": "shape outside what oracle/orc_cached.cpp serves"}
+            else:
+                cres, cms, cprep = got
+                same = all(np.array_equal(np.asarray(cres[k]), np.asarray(res[k]))
+                           for k in ("decision", "replacement_its", "n_new_claims", "n_unscheduled"))
+                out["cpu_baseline_cached"] = {
+                    "value": S / (cms / 1000), "unit": "subsets/s", "ms": cms, "host_prep_ms": cprep, "cores": 1, "kind": "cached port",
+                    "identical_to_the_gpu_result": bool(same),
+                    "sample": "all subsets, the CUDA path's algorithm (candidate bitmaps, failure bits, fast path, price lists) as "
+                              "scalar C++ on one host core, one simulation after the other"}
+        except Exception as e:  # noqa: BLE001
+            out["cpu_baseline_cached"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     return out
 
 

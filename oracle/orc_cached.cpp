@@ -376,6 +376,7 @@ struct Solver {
     node_rem = t.node_rem, node_rem_present = t.node_rem_present, node_npods.assign(std::max(E, 1), 0);
     node_slot.resize((size_t)std::max(E, 1) * K);
     for (size_t i = 0; i < (size_t)E * K; i++) node_slot[i] = Slot{t.node_sflags[i], t.node_smask[i], 0, 0};
+    touched.assign(std::max(E, 1), 0);
     nactive.assign((size_t)(std::max(E, 1) + 63) / 64, 0ull);
     for (int n = 0; n < E; n++)
       if (t.node_flags[n] & KP_NODE_SCHEDULABLE) set(nactive, n);
@@ -536,11 +537,11 @@ struct Solver {
     return KP_OK;
   }
 
-  int solve(kp_result* out) {
-    const int64_t P = p->n_pods;
-    // NewQueue (queue.go:72-108): class rank by cpu desc, memory desc; then creation time, then UID
-    std::vector<int64_t> rank(std::max(X, 1), 0);
-    {
+  // NewQueue (queue.go:72-108): class rank by cpu desc, memory desc; then creation time, then UID
+  std::vector<int64_t> rank;
+  void sort_rows(std::vector<int32_t>& rows) {
+    if (rank.empty()) {
+      rank.assign(std::max(X, 1), 0);
       std::vector<int> idx(X);
       std::iota(idx.begin(), idx.end(), 0);
       auto key = [&](int x) { return std::make_pair(-t.cls_sort_cpu[x], -t.cls_sort_mem[x]); };
@@ -551,9 +552,7 @@ struct Solver {
         rank[idx[i]] = r;
       }
     }
-    std::vector<int32_t> queue(P);
-    std::iota(queue.begin(), queue.end(), 0);
-    std::stable_sort(queue.begin(), queue.end(), [&](int32_t a, int32_t b) {
+    std::stable_sort(rows.begin(), rows.end(), [&](int32_t a, int32_t b) {
       const int64_t ra = rank[p->pod_class[a]], rb = rank[p->pod_class[b]];
       if (ra != rb) return ra < rb;
       const int64_t ta = p->pod_creation ? p->pod_creation[a] : 0, tb = p->pod_creation ? p->pod_creation[b] : 0;
@@ -561,8 +560,41 @@ struct Solver {
       if (p->pod_uid_hi[a] != p->pod_uid_hi[b]) return p->pod_uid_hi[a] < p->pod_uid_hi[b];
       return p->pod_uid_lo[a] < p->pod_uid_lo[b];
     });
-    std::vector<int32_t> target(P, KP_TARGET_UNSCHEDULED), last_len(P, 0);
-    std::vector<uint8_t> perr(P, 0);
+  }
+  // a consolidation simulation works on a private view of the existing nodes: what it changes is logged and undone
+  struct NodeUndo {
+    int node;
+    std::vector<int64_t> rem;
+    uint32_t present;
+    std::vector<Slot> slot;
+    int32_t npods;
+  };
+  std::vector<NodeUndo> undo;
+  std::vector<uint8_t> touched;
+  void reset_claims() {
+    claims.clear(), ord.clear(), cnt.clear(), failm.clear(), deadm.clear(), accm.clear();
+    std::fill(lbf.begin(), lbf.end(), 0);
+    std::fill(lbr.begin(), lbr.end(), 0);
+  }
+  void undo_nodes() {
+    for (const NodeUndo& u : undo) {
+      std::copy(u.rem.begin(), u.rem.end(), node_rem.begin() + (size_t)u.node * R);
+      node_rem_present[u.node] = u.present;
+      std::copy(u.slot.begin(), u.slot.end(), node_slot.begin() + (size_t)u.node * K);
+      node_npods[u.node] = u.npods;
+      touched[u.node] = 0;
+    }
+    undo.clear();
+  }
+
+  // One Scheduler.Solve over the pods `rows` (in queue order): target / perr per position in `rows`
+  void run(const std::vector<int32_t>& rows, std::vector<int32_t>& target, std::vector<uint8_t>& perr, bool overlay) {
+    const int64_t P = (int64_t)rows.size();
+    std::vector<int32_t> queue(P);
+    std::iota(queue.begin(), queue.end(), 0);
+    target.assign(P, KP_TARGET_UNSCHEDULED);
+    perr.assign(P, 0);
+    std::vector<int32_t> last_len(P, 0);
     const uint64_t tmpl_all = N >= 64 ? ~0ull : ((1ull << N) - 1);
     int alive_tmpl = 0;
     for (int n = 0; n < N; n++) {
@@ -582,7 +614,7 @@ struct Solver {
       const int32_t li = queue[head];
       if ((int64_t)head >= P && last_len[li] == len) break;  // a full cycle without progress
       head++;
-      const int cls = p->pod_class[li], rv = t.cls_rv[cls], fs = fsig[cls];
+      const int cls = p->pod_class[rows[li]], rv = t.cls_rv[cls], fs = fsig[cls];
       const int nC = (int)claims.size();
       // ---- addToExistingNode (scheduler.go:520-555): the first node in order that passes
       if (E > 0) {
@@ -599,12 +631,17 @@ struct Solver {
               if (t.cls_req[(size_t)cls * R + r] > (present ? rem : 0)) bad = true;
             }
             if (bad) {
-              nfit[rv][w] &= ~(1ull << (node & 63));  // monotone: remaining resources only shrink
+              if (!overlay) nfit[rv][w] &= ~(1ull << (node & 63));  // monotone: remaining resources only shrink
               continue;
             }
             std::vector<Slot> nb(node_slot.begin() + (size_t)node * K, node_slot.begin() + (size_t)(node + 1) * K);
             eval(cls, node, nb, {}, {}, {}, ev, false);
             if (!ev.ok) continue;
+            if (overlay && !touched[node]) {
+              touched[node] = 1;
+              undo.push_back(NodeUndo{node, std::vector<int64_t>(node_rem.begin() + (size_t)node * R, node_rem.begin() + (size_t)(node + 1) * R),
+                                      node_rem_present[node], nb, node_npods[node]});
+            }
             if (ev.changed)
               for (int k = 0; k < K; k++) node_slot[(size_t)node * K + k] = ev.F[k];
             for (int r = 0; r < R; r++) node_rem[(size_t)node * R + r] -= t.cls_req[(size_t)cls * R + r];
@@ -817,6 +854,22 @@ struct Solver {
       queue.push_back(li);
       last_len[li] = (int32_t)((int64_t)queue.size() - (int64_t)head);
     }
+  }
+
+  int solve(kp_result* out) {
+    const int64_t P = p->n_pods;
+    std::vector<int32_t> rows(P);
+    std::iota(rows.begin(), rows.end(), 0);
+    sort_rows(rows);
+    std::vector<int32_t> tl;
+    std::vector<uint8_t> el;
+    run(rows, tl, el, false);
+    std::vector<int32_t> target(P, KP_TARGET_UNSCHEDULED);
+    std::vector<uint8_t> perr(P, 0);
+    for (int64_t i = 0; i < P; i++) {
+      target[rows[i]] = tl[i];
+      perr[rows[i]] = el[i];
+    }
     // ---- result (the fields the parity test compares)
     memset(out, 0, sizeof(*out));
     const int C = (int)claims.size();
@@ -844,11 +897,291 @@ struct Solver {
     out->n_commits = fast_commits;
     return KP_OK;
   }
+
+  // ---- consolidation: SimulateScheduling + computeConsolidation per candidate set (disruption/helpers.go:51-142,
+  // consolidation.go:136-229) -- k_consolidate and consol_decide on one core, topology-free pods only
+  unsigned offering_ok_mask(const std::vector<Slot>& S) const {
+    unsigned m = 0;
+    for (int dd = 0; dd < t.D; dd++) {
+      bool ok = true;
+      for (uint32_t keys = t.off_keys[dd]; keys && ok; keys &= keys - 1) {
+        const int k = __builtin_ctz(keys);
+        ok = slot_compatible(ki(k), S[k], t.off_slots[(size_t)dd * K + k], t.key_wellknown[k], true);
+      }
+      if (ok) m |= 1u << dd;
+    }
+    return m;
+  }
+  int consolidate(const kp_consol_input* in, kp_consol_result* out, std::string& err) {
+    if (t.G > 0 || in->n_extra_pods > 0) {
+      err = "orc_cached: consolidation of topology-free candidate pods without extra pods only";
+      return KP_ERR_UNSUPPORTED;
+    }
+    const int T = t.T, S = in->n_subsets, ct_key = in->capacity_type_key;
+    auto full_slot = [&](int rs, int k) {
+      const size_t i = (size_t)rs * K + k;
+      return Slot{t.rs_flags[i], t.rs_mask[i], t.rs_gte[i], t.rs_lte[i]};
+    };
+    // getCandidatePrices (consolidation.go:319-337): the cheapest offering compatible with the node's labels
+    std::vector<double> node_price(std::max(E, 1), -1.0);
+    for (int n = 0; n < E; n++) {
+      const int it = in->node_it[n];
+      if (it < 0) continue;
+      bool any = false;
+      double best = 0;
+      for (int o = p->it_off_off[it]; o < p->it_off_off[it + 1]; o++) {
+        bool ok = true;
+        for (int k = 0; k < K && ok; k++)
+          ok = slot_compatible(ki(k), full_slot(p->node_reqset[n], k), full_slot(p->off_reqset[o], k), t.key_wellknown[k], true);
+        if (!ok) continue;
+        if (!any || p->off_price[o] < best) best = p->off_price[o];
+        any = true;
+      }
+      if (any) node_price[n] = best;
+    }
+    // WorstLaunchPrice lists per capacity type in the order reserved, spot, on-demand (types.go:480-491), OrderByPrice lists
+    const int ct_order[3] = {in->ct_reserved, in->ct_spot, in->ct_on_demand};
+    int ct_valid = 0;
+    std::vector<uint8_t> ctmask(std::max(t.D, 1), 0);
+    for (int i = 0; i < 3; i++) {
+      if (ct_key < 0 || ct_order[i] < 0) continue;
+      ct_valid |= 1 << i;
+      for (int dd = 0; dd < t.D; dd++) {
+        bool ok = true;
+        for (int k = 0; k < K && ok; k++) {
+          const Slot ex = k == ct_key ? Slot{SF_PRESENT, 1ull << ct_order[i], 0, 0} : Slot{0u, 0ull, 0, 0};
+          ok = slot_compatible(ki(k), ex, t.off_slots[(size_t)dd * K + k], t.key_wellknown[k], true);
+        }
+        if (ok) ctmask[dd] |= 1 << i;
+      }
+    }
+    std::vector<int32_t> wl_off((size_t)T * 3 + 1, 0), wl_set, ml_off((size_t)T + 1, 0), ml_set;
+    std::vector<double> wl_price, ml_price;
+    for (int ti = 0; ti < T; ti++) {
+      for (int ci = 0; ci < 3; ci++) {
+        std::vector<std::pair<double, int>> ent;
+        for (int o = p->it_off_off[ti]; o < p->it_off_off[ti + 1]; o++)
+          if (p->off_available[o] && ((ctmask[t.off_set[o]] >> ci) & 1)) ent.push_back({p->off_price[o], t.off_set[o]});
+        std::stable_sort(ent.begin(), ent.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
+        for (auto& e : ent) {
+          wl_price.push_back(e.first);
+          wl_set.push_back(e.second);
+        }
+        wl_off[(size_t)ti * 3 + ci + 1] = (int32_t)wl_set.size();
+      }
+      std::vector<std::pair<double, int>> ent;
+      for (int o = p->it_off_off[ti]; o < p->it_off_off[ti + 1]; o++)
+        if (p->off_available[o]) ent.push_back({p->off_price[o], t.off_set[o]});
+      std::stable_sort(ent.begin(), ent.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });
+      for (auto& e : ent) {
+        ml_price.push_back(e.first);
+        ml_set.push_back(e.second);
+      }
+      ml_off[(size_t)ti + 1] = (int32_t)ml_set.size();
+    }
+    const double INF = 1.7976931348623157e308;
+    auto worst = [&](int ty, unsigned okmask) {
+      for (int ci = 0; ci < 3; ci++) {
+        if (ct_key < 0 || !((ct_valid >> ci) & 1)) continue;
+        for (int e = wl_off[(size_t)ty * 3 + ci]; e < wl_off[(size_t)ty * 3 + ci + 1]; e++)
+          if ((okmask >> wl_set[e]) & 1u) return wl_price[e];
+      }
+      return INF;
+    };
+    auto has = [&](const std::vector<uint64_t>& m, int ty) { return (m[ty >> 6] >> (ty & 63)) & 1ull; };
+    // ---- result arrays
+    memset(out, 0, sizeof(*out));
+    const size_t s1 = S ? S : 1;
+    out->n_subsets = S;
+    out->it_words = ITW;
+    out->decision = (uint8_t*)calloc(s1, 1);
+    out->replacement_its = (uint64_t*)calloc(s1 * ITW, 8);
+    out->n_new_claims = (int32_t*)calloc(s1, 4);
+    out->n_unscheduled = (int32_t*)calloc(s1, 4);
+    std::vector<int32_t> rows, tl;
+    std::vector<uint8_t> el;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int s_i = 0; s_i < S; s_i++) {
+      const int32_t* snodes = in->subset_nodes + in->subset_off[s_i];
+      const int sn = in->subset_off[s_i + 1] - in->subset_off[s_i];
+      // ---- SimulateScheduling: the candidates leave, their pods are scheduled against the rest of the cluster
+      rows.clear();
+      for (int i = 0; i < sn; i++) {
+        const int n = snodes[i];
+        nactive[n >> 6] &= ~(1ull << (n & 63));
+        for (int j = in->node_pod_off[n]; j < in->node_pod_off[n + 1]; j++) rows.push_back(j);
+      }
+      sort_rows(rows);
+      reset_claims();
+      run(rows, tl, el, true);
+      int unscheduled = 0;
+      for (size_t i = 0; i < tl.size(); i++) {
+        if (tl[i] == KP_TARGET_UNSCHEDULED)
+          unscheduled++;
+        else if (tl[i] >= 0 && !(p->node_flags[tl[i]] & KP_NODE_INITIALIZED))
+          unscheduled++;  // helpers.go:121-140 UninitializedNodeError
+      }
+      undo_nodes();
+      for (int i = 0; i < sn; i++)
+        if (p->node_flags[snodes[i]] & KP_NODE_SCHEDULABLE) nactive[snodes[i] >> 6] |= 1ull << (snodes[i] & 63);
+      const int n_new = (int)claims.size();
+      out->n_new_claims[s_i] = n_new;
+      out->n_unscheduled[s_i] = unscheduled;
+      // ---- computeConsolidation (consol_decide)
+      int decision = KP_DECISION_NOOP;
+      std::vector<uint64_t> rep(ITW, 0ull);
+      if (!unscheduled && n_new == 0) decision = KP_DECISION_DELETE;
+      if (!unscheduled && n_new == 1) {
+        std::vector<Slot> Sx = claims[0].s;
+        std::vector<uint64_t> cur = claims[0].its;
+        int n_its = 0;
+        for (uint64_t w : cur) n_its += __builtin_popcountll(w);
+        double price = 0;
+        bool zero = false, all_spot = true;
+        for (int i = 0; i < sn; i++) {
+          const double np = node_price[snodes[i]];
+          if (np < 0) zero = true;
+          price += np;
+          if (!in->node_is_spot[snodes[i]]) all_spot = false;
+        }
+        if (zero) price = 0.0;
+        const bool spot_ok = ct_key >= 0 && in->ct_spot >= 0 && slot_has(ki(ct_key), Sx[ct_key], in->ct_spot);
+        unsigned okmask = offering_ok_mask(Sx);
+        const bool spot_path = all_spot && spot_ok;
+        // OrderByPrice + Truncate(600): the order only matters when it truncates or for the 15-cheapest rule
+        std::vector<int32_t> order;  // types in price order
+        if (n_its > 600 || (spot_path && in->spot_to_spot_enabled)) {
+          std::vector<int32_t> types, perm;
+          std::vector<double> key;
+          for (int w = 0; w < ITW; w++)
+            for (uint64_t b = cur[w]; b; b &= b - 1) {
+              const int ty = w * 64 + __builtin_ctzll(b);
+              double mp = INF;
+              for (int e = ml_off[ty]; e < ml_off[ty + 1]; e++)
+                if ((okmask >> ml_set[e]) & 1u) {
+                  mp = ml_price[e];
+                  break;
+                }
+              types.push_back(ty);
+              key.push_back(mp);
+            }
+          perm.resize(types.size());
+          std::iota(perm.begin(), perm.end(), 0);
+          HostGoSort<double> gs{key.data(), perm.data()};
+          gs.pdqsort(0, (int)perm.size(), HostGoSort<double>::bits_len((unsigned long long)perm.size()));
+          for (int32_t i : perm) order.push_back(types[i]);
+          if (order.size() > 600) {
+            order.resize(600);
+            std::fill(cur.begin(), cur.end(), 0ull);
+            for (int32_t ty : order) cur[ty >> 6] |= 1ull << (ty & 63);
+          }
+        }
+        if (!(spot_path && !in->spot_to_spot_enabled)) {
+          if (spot_path) {  // restrict the claim to spot and drop types without such an offering (consolidation.go:252-257)
+            Sx[ct_key] = slot_add(ki(ct_key), Sx[ct_key], Slot{SF_PRESENT, 1ull << in->ct_spot, 0, 0});
+            okmask = offering_ok_mask(Sx);
+            for (int w = 0; w < ITW; w++) {
+              uint64_t keep = 0;
+              for (uint64_t b = cur[w]; b; b &= b - 1) {
+                const int ty = w * 64 + __builtin_ctzll(b);
+                for (int e = ml_off[ty]; e < ml_off[ty + 1]; e++)
+                  if ((okmask >> ml_set[e]) & 1u) {
+                    keep |= 1ull << (ty & 63);
+                    break;
+                  }
+              }
+              cur[w] = keep;
+            }
+          }
+          // RemoveInstanceTypeOptionsByPriceAndMinValues (nodeclaim.go:309-318): keep WorstLaunchPrice < price
+          bool any = false;
+          for (int w = 0; w < ITW; w++)
+            for (uint64_t b = cur[w]; b; b &= b - 1) {
+              const int ty = w * 64 + __builtin_ctzll(b);
+              if (worst(ty, okmask) < price) {
+                rep[w] |= 1ull << (ty & 63);
+                any = true;
+              }
+            }
+          if (any && spot_path && sn == 1) {  // at least 15 cheaper types, only the 15 cheapest go out (consolidation.go:283-312)
+            int total = 0;
+            for (uint64_t w : rep) total += __builtin_popcountll(w);
+            if (total < 15) {
+              any = false;
+            } else {
+              std::vector<uint64_t> first(ITW, 0ull);
+              int taken = 0;
+              for (int32_t ty : order) {
+                if (taken >= 15) break;
+                if (has(rep, ty)) {
+                  first[ty >> 6] |= 1ull << (ty & 63);
+                  taken++;
+                }
+              }
+              rep = first;
+            }
+          }
+          if (any && in->filter_same_instance_type && sn >= 2) {  // filterOutSameInstanceType (multinodeconsolidation.go:189-226)
+            double max_price = INF;
+            for (int i = 0; i < sn; i++) {
+              const int ty = in->node_it[snodes[i]];
+              if (ty < 0 || !has(rep, ty)) continue;
+              double mine = INF;
+              for (int j = 0; j < sn; j++)
+                if (in->node_it[snodes[j]] == ty && node_price[snodes[j]] >= 0 && node_price[snodes[j]] < mine) mine = node_price[snodes[j]];
+              if (mine > 1e308) mine = 0.0;
+              if (mine < max_price) max_price = mine;
+            }
+            if (max_price < 1e308) {
+              any = false;
+              for (int w = 0; w < ITW; w++) {
+                uint64_t keep = 0;
+                for (uint64_t b = rep[w]; b; b &= b - 1) {
+                  const int ty = w * 64 + __builtin_ctzll(b);
+                  if (worst(ty, okmask) < max_price) keep |= 1ull << (ty & 63);
+                }
+                rep[w] = keep;
+                any = any || keep;
+              }
+            }
+          }
+          if (any) decision = KP_DECISION_REPLACE;
+        }
+      }
+      out->decision[s_i] = (uint8_t)decision;
+      if (decision == KP_DECISION_REPLACE)
+        for (int w = 0; w < ITW; w++) out->replacement_its[(size_t)s_i * ITW + w] = rep[w];
+    }
+    out->solve_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return KP_OK;
+  }
 };
 
 }  // namespace
 
 extern "C" {
+// kp_consolidate's fast path on one host core: decision, replacement_its, n_new_claims, n_unscheduled of `out` (free with
+// orc_cached_consol_free); solve_ms = the simulations + decisions alone (tables and price lists prepared before)
+int orc_cached_consolidate(const kp_problem* p, const kp_consol_input* in, kp_consol_result* out, double* prep_ms) {
+  Solver s;
+  s.p = p;
+  std::string err;
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = s.prepare(err);
+  if (rc != KP_OK) return rc;
+  auto t1 = std::chrono::steady_clock::now();
+  rc = s.consolidate(in, out, err);
+  if (prep_ms) *prep_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  return rc;
+}
+void orc_cached_consol_free(kp_consol_result* r) {
+  free(r->decision);
+  free(r->replacement_its);
+  free(r->n_new_claims);
+  free(r->n_unscheduled);
+  memset(r, 0, sizeof(*r));
+}
+
 // One Scheduler.Solve with the CUDA solver's caches on one host core.  Fills pod_target, pod_error, n_claims,
 // claim_template / npods / rank / requests / its of `out` (free with orc_cached_free); solve_ms = the solve alone (tables
 // prepared before the clock starts, like the resident GPU number), KP_ERR_UNSUPPORTED outside the lean shape.

@@ -97,3 +97,25 @@ def cached_solve(problem):
     ms = r.solve_ms
     cached_lib().orc_cached_free(C.byref(r))
     return out, ms, prep.value
+
+
+def cached_consolidate(problem, consol):
+    """kp_consolidate's fast path on one host core (oracle/orc_cached.cpp) -> (dict with decision / replacement_its /
+    n_new_claims / n_unscheduled, solve ms, prep ms), or None outside its scope"""
+    lib_ = cached_lib()
+    lib_.orc_cached_consolidate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    lib_.orc_cached_consol_free.argtypes = [C.c_void_p]
+    r = _abi.kp_consol_result()
+    prep = C.c_double()
+    rc = lib_.orc_cached_consolidate(problem.ref(), consol.ref(), C.byref(r), C.byref(prep))
+    if rc == 5:
+        return None
+    if rc != 0:
+        raise RuntimeError(f"orc_cached_consolidate failed: {rc}")
+    S, W = r.n_subsets, r.it_words
+    out = {"decision": _abi.view(r.decision, S, np.uint8).copy(),
+           "replacement_its": _abi.view(r.replacement_its, S * W, np.uint64).reshape(S, W).copy(),
+           "n_new_claims": _abi.view(r.n_new_claims, S, np.int32).copy(), "n_unscheduled": _abi.view(r.n_unscheduled, S, np.int32).copy()}
+    ms = r.solve_ms
+    lib_.orc_cached_consol_free(C.byref(r))
+    return out, ms, prep.value

@@ -143,6 +143,39 @@ def test_fuzz_problems_with_existing_nodes_match_the_oracle():
     assert ran >= 100 and nodes >= 30, (ran, nodes)
 
 
+CONSOL_KEYS = ["decision", "n_new_claims", "n_unscheduled", "replacement_its"]
+
+
+@pytest.mark.parametrize("kw", [dict(n_nodes=300, n_pods=1500, n_candidates=12, max_subset=3),
+                                dict(n_nodes=200, n_pods=2500, n_candidates=10, max_subset=3),
+                                dict(n_nodes=1000, n_pods=12000, n_candidates=14, max_subset=3),
+                                dict(n_nodes=400, n_pods=4000, n_candidates=16, max_subset=2, spot_fraction=1.0, spot_to_spot=True),
+                                dict(n_nodes=400, n_pods=4000, n_candidates=16, max_subset=2, spot_fraction=0.5)])
+def test_c4_consolidation_matches_the_oracle(kw):
+    enc, consol = workloads.config_c4(**kw)
+    ci = _abi.ConsolInput(**consol)
+    got = oracle_lib.cached_consolidate(enc.problem, ci)
+    assert got is not None
+    ref = oracle_lib.consolidate(enc.problem, ci, threads=8)
+    for k in CONSOL_KEYS:
+        assert np.array_equal(got[0][k], ref[k]), (k, np.argwhere(got[0][k] != ref[k])[:5].tolist())
+
+
+def test_c4_uninitialized_nodes_and_unknown_instance_type_match_the_oracle():
+    enc, consol = workloads.config_c4(n_nodes=300, n_pods=1500, n_candidates=12, max_subset=2)
+    flags = enc.problem.get("node_flags").copy()
+    flags[::7] &= ~np.uint8(2)  # KP_NODE_INITIALIZED
+    enc.problem.set("node_flags", flags)
+    node_it = consol["node_it"].copy()
+    node_it[consol["subset_nodes"][0]] = -1
+    consol["node_it"] = node_it
+    ci = _abi.ConsolInput(**consol)
+    got = oracle_lib.cached_consolidate(enc.problem, ci)
+    ref = oracle_lib.consolidate(enc.problem, ci, threads=8)
+    for k in CONSOL_KEYS:
+        assert np.array_equal(got[0][k], ref[k]), k
+
+
 def test_out_of_scope_shapes_are_refused():
     from tests.test_fuzz_parity import encode_reserved
     assert cached_solve(encode_reserved(1).problem) is None
