@@ -8,10 +8,12 @@
 // the SAME prepared tables (kp_prep.cpp: the host half of libkarpsolve.so), as plain scalar C++: the ratio oracle : this
 // is the algorithm's share of a speed-up, the ratio this : GPU the hardware's.
 //
-// Scope: provisioning into new NodeClaims -- requirement algebra without Gt / Lt bounds, taints, topology groups (spread,
-// affinity, anti-affinity, node filters and policies, the domain fast path), no minValues, no reservation, no host port, no
-// volume alternative, no existing node, no NodePool limit, no preference ladder.  Anything else: KP_ERR_UNSUPPORTED.  Results are checked against the oracle
-// (tests/test_cached_cpu_baseline.py); each step cites the device code it mirrors.
+// Scope: Scheduler.Solve with existing nodes, in-flight and new NodeClaims -- requirement algebra without Gt / Lt bounds,
+// taints, topology groups (spread, affinity, anti-affinity, node filters and policies, the domain fast path) -- and
+// kp_consolidate's fast path (topology-free candidate pods: simulation on a private view of the nodes + computeConsolidation
+// with the price lists).  Not served: minValues, reservations, host ports, volume alternatives, NodePool limits, the
+// preference ladder, consolidation with topology or extra pods: KP_ERR_UNSUPPORTED.  Results are checked against the oracle
+// (tests/test_cached_cpu_baseline.py) and, inside bench.py, against the GPU's; each step cites the device code it mirrors.
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
