@@ -452,7 +452,7 @@ def time_c5(h, rank, world, steps, warmup, torch, dist, flush, barrier, sampler=
     return {"ms": float(np.mean(dev_ms)), "ms_all": [round(float(x), 3) for x in dev_ms], "allreduce_ms": float(np.mean(ar_ms)),
             "wall": wall, "launches_per_step": int(launches), "e2e_ms": 1000 * float(np.mean(e2e_t)), "stats": st,
             "outs": outs, "n_total": n_total, "pools": pools, "counter_slots": int(total_slots),
-            "counter_sum": int(table.sum()), "n_mine": int(sum(int(p.n_pods) for p in problems))}
+            "counter_sum": int(table.sum()), "n_mine": int(sum(int(p.n_pods) for p in problems)), "problems": problems}
 
 
 def main():
@@ -574,6 +574,25 @@ def main():
                 "counter_table_slots": m5["counter_slots"], "counter_table_sum": m5["counter_sum"],
                 "node_claims": int(sum(int(o["n_claims"]) for o in m5["outs"])),
                 "unscheduled": int(sum(int((o["pod_target"] == -1).sum()) for o in m5["outs"]))}
+            if not args.no_cpu_baseline:
+                try:  # the solver's own algorithm on ONE host core, pool after pool (oracle/orc_cached.cpp); never fatal
+                    from tests import oracle_lib
+                    tot_ms, same, per_pool = 0.0, True, []
+                    for prob, gpu_out in zip(m5["problems"], m5["outs"]):
+                        got = oracle_lib.cached_solve(prob)
+                        if got is None:
+                            raise RuntimeError("shape outside what oracle/orc_cached.cpp serves")
+                        cres, cms, _ = got
+                        tot_ms += cms
+                        per_pool.append(round(cms, 1))
+                        same = same and all(np.array_equal(np.asarray(cres[k]), np.asarray(gpu_out[k])) for k in oracle_lib.CACHED_KEYS)
+                    line["c5_one_gpu"]["cpu_baseline_cached"] = {
+                        "value": m5["n_total"] / (tot_ms / 1000), "unit": "pods/s", "ms": tot_ms, "ms_per_pool": per_pool, "cores": 1,
+                        "kind": "cached port", "identical_to_the_gpu_result": bool(same),
+                        "sample": "all 8 NodePool shards, one after the other on one host core (they are independent: 8 cores would "
+                                  "take the time of the slowest pool)"}
+                except Exception as e:  # noqa: BLE001
+                    line["c5_one_gpu"]["cpu_baseline_cached"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     else:
         # ---------------- headline at N > 1: C5, NodePool -> rank, library-side all-reduce inside the timed step
         m5 = time_c5(h, rank, world, args.steps, args.warmup, torch, dist, flush, barrier, sampler)

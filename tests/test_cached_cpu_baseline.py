@@ -143,6 +143,15 @@ def test_fuzz_problems_with_existing_nodes_match_the_oracle():
     assert ran >= 100 and nodes >= 30, (ran, nodes)
 
 
+def test_c5_shards_match_the_oracle():
+    """C5's constraint mix (C2 half + C3 half, pods pinned to their NodePool) at 1/64 size, shard by shard"""
+    shards = workloads.config_c5_shards(160_000, 8, 1000, 1000, [[p] for p in range(8)])
+    for i, enc in enumerate(shards[:3]):
+        got = cached_solve(enc.problem)
+        assert got is not None
+        same(got[0], oracle_lib.solve(enc.problem, threads=8), f"C5 shard {i} ")
+
+
 CONSOL_KEYS = ["decision", "n_new_claims", "n_unscheduled", "replacement_its"]
 
 
